@@ -1,0 +1,101 @@
+"""ctypes bindings of libhikari_b200.so (include/hikari_b200.h + include/hikari_host.h).
+
+The library is the product: if it is missing this module raises — there is no Python / CPU fallback for the path."""
+import ctypes as C
+import os
+
+from . import layout as L
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhikari_b200.so")
+
+HK_OK = 0
+HK_ERR_INVALID_ARGUMENT, HK_ERR_CUDA, HK_ERR_NOT_READY, HK_ERR_OUT_OF_MEMORY, HK_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+
+# every symbol the two headers declare: name -> (restype, argtypes)
+_P = C.c_void_p
+_U32, _I, _SZ, _U64 = C.c_uint32, C.c_int, C.c_size_t, C.c_uint64
+
+
+class Settings(C.Structure):
+    """hikari_settings (include/hikari_host.h) == HikariSettings, src/lib.rs:399-433."""
+    _fields_ = [("direct_validate_interval", _U32), ("emissive_validate_interval", _U32),
+                ("max_temporal_reuse_count", _U32), ("max_spatial_reuse_count", _U32),
+                ("max_reservoir_lifetime", C.c_float), ("solar_angle", C.c_float), ("indirect_bounces", _U32),
+                ("max_indirect_luminance", C.c_float), ("clear_color", C.c_float * 4), ("temporal_reuse", _U32),
+                ("emissive_spatial_reuse", _U32), ("indirect_spatial_reuse", _U32), ("denoise", _U32), ("taa", _U32),
+                ("upscale_kind", _U32), ("upscale_ratio", C.c_float), ("upscale_sharpness", C.c_float)]
+
+
+SYMBOLS = {
+    # include/hikari_b200.h
+    "hk_context_create": (_I, [C.POINTER(_P), _I, _U32, _U32, _U32, _U32, _P]),
+    "hk_context_destroy": (None, [_P]),
+    "hk_context_resize": (_I, [_P, _U32, _U32, _U32, _U32]),
+    "hk_reset_temporal_state": (_I, [_P]),
+    "hk_scene_upload": (_I, [_P, C.POINTER(L.SceneDesc)]),
+    "hk_set_noise": (_I, [_P, _P]),
+    "hk_prepass_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
+    "hk_light_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
+    "hk_post_process_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
+    "hk_render_frame": (_I, [_P, C.POINTER(L.FrameInputs)]),
+    "hk_get_output": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_SZ)]),
+    "hk_readback": (_I, [_P, _I, _P, _SZ]),
+    "hk_upload_state": (_I, [_P, _I, _P, _SZ]),
+    "hk_sync": (_I, [_P]),
+    "hk_trace_rays": (_I, [_P, _P, _SZ, _P]),
+    "hk_set_profiling": (_I, [_P, _I, _I]),
+    "hk_set_keep_intermediates": (_I, [_P, _I]),
+    "hk_get_stats": (_I, [_P, C.POINTER(L.FrameStats)]),
+    "hk_band_rows": (_I, [_P, C.POINTER(_U32), C.POINTER(_U32)]),
+    "hk_last_error": (C.c_char_p, [_P]),
+    "hk_version": (C.c_char_p, []),
+    # include/hikari_host.h
+    "hikari_settings_default": (None, [C.POINTER(Settings)]),
+    "hikari_upscale_ratio": (C.c_float, [C.POINTER(Settings)]),
+    "hikari_make_frame_inputs": (None, [C.POINTER(Settings), _U64, C.POINTER(L.View), C.POINTER(L.PreviousView),
+                                        C.POINTER(L.Lights), C.POINTER(L.FrameInputs)]),
+    "hikari_graph_name": (C.c_char_p, []),
+    "hikari_world_create": (_P, []),
+    "hikari_world_destroy": (None, [_P]),
+    "hikari_world_add_mesh": (_U32, [_P, _P, _P, _P, _U32, _P, _U32, _U32]),
+    "hikari_world_add_material": (_U32, [_P, _P]),
+    "hikari_world_add_texture": (_U32, [_P, C.POINTER(L.TextureDesc)]),
+    "hikari_world_add_instance": (_U32, [_P, _U32, _U32, _P, _U32]),
+    "hikari_world_prepare": (None, [_P]),
+    "hikari_world_scene_desc": (None, [_P, C.POINTER(L.SceneDesc)]),
+    "hikari_world_mesh_error": (_I, [_P, _U32]),
+    "hikari_plugin_create": (_P, []),
+    "hikari_plugin_destroy": (None, [_P]),
+    "hikari_plugin_build": (_I, [_P, _I, _U32, _U32, _U32, _U32, _P, _P]),
+    "hikari_plugin_upload_scene": (_I, [_P, _P]),
+    "hikari_plugin_run_frame": (_I, [_P, C.POINTER(Settings), C.POINTER(L.View), C.POINTER(L.PreviousView), C.POINTER(L.Lights)]),
+    "hikari_plugin_context": (_P, [_P]),
+    "hikari_plugin_frame_counter": (_U64, [_P]),
+    "hikari_plugin_set_frame_counter": (None, [_P, _U64]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a). There is no fallback path.")
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(_lib, name)   # AttributeError if the library does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+    return _lib
+
+
+class HikariError(RuntimeError):
+    pass
+
+
+def check(rc, ctx=None):
+    if rc != HK_OK:
+        msg = lib().hk_last_error(ctx)
+        raise HikariError(f"hk error {rc}: {msg.decode() if msg else ''}")

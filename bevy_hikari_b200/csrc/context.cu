@@ -1,0 +1,521 @@
+// context.cu — implementation of the C ABI in include/hikari_b200.h: device memory ownership, scene upload, pass
+// scheduling on one CUDA stream (what LightNode::run / PostProcessNode::run do with a wgpu command encoder,
+// src/light.rs:590-702, src/post_process.rs:1140-1234), read-back / state upload for tests.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "hikari_b200.h"
+#include "hk_kernels.h"
+
+using namespace hkd;
+
+// Rows a band needs beyond the rows it owns so that owned pixels equal an unsharded render:
+// a-trous reach 8+4+2+1 = 15 (+1 for the 3x3 variance blur), spatial reuse radius 20 on top of that.
+static const int GHOST_DEMOD = 15, GHOST_L0 = 7, GHOST_L1 = 3, GHOST_L2 = 1;
+static const int GHOST_SPATIAL = GHOST_DEMOD + 1;           // 16
+static const int GHOST_TEMPORAL = GHOST_SPATIAL + 20;       // 36
+
+struct hk_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Band band{};
+    size_t band_pixels = 0, owned_pixels = 0;
+    std::vector<void*> allocations;        // per-pixel planes
+    std::vector<void*> scene_allocations;  // scene buffers
+    Planes planes{};
+    DeviceScene scene{};
+    bool scene_ready = false, noise_ready = false;
+    uint8_t* noise = nullptr;
+    Counters* counters = nullptr;
+    bool count_rays = false, time_passes = false, keep_intermediates = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    hk_frame_stats stats{};
+    uint32_t launches = 0;
+    std::string error;
+};
+
+static std::string g_create_error;
+
+static int set_error(hk_context* c, int code, const std::string& msg) {
+    if (c) c->error = msg; else g_create_error = msg;
+    return code;
+}
+#define HK_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return set_error(ctx, e__ == cudaErrorMemoryAllocation ? HK_ERR_OUT_OF_MEMORY : HK_ERR_CUDA,   \
+                             std::string(#call) + ": " + cudaGetErrorString(e__));                         \
+    } while (0)
+
+template <class T>
+static cudaError_t alloc_plane(hk_context* ctx, T** out, size_t count, std::vector<void*>& list) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(p, 0, count * sizeof(T), ctx->stream);
+    list.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return e;
+}
+
+static void free_list(std::vector<void*>& list) {
+    for (void* p : list) cudaFree(p);
+    list.clear();
+}
+
+static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end) {
+    if (width == 0 || height == 0 || row_begin >= row_end || row_end > height)
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "bad size or row band");
+    free_list(ctx->allocations);
+    Band b;
+    b.W = (int)width; b.H = (int)height; b.r0 = (int)row_begin; b.r1 = (int)row_end;
+    b.a0 = b.r0 - GHOST_TEMPORAL < 0 ? 0 : b.r0 - GHOST_TEMPORAL;
+    b.a1 = b.r1 + GHOST_TEMPORAL > b.H ? b.H : b.r1 + GHOST_TEMPORAL;
+    ctx->band = b;
+    const size_t n = (size_t)b.W * (size_t)(b.a1 - b.a0);
+    ctx->band_pixels = n;
+    ctx->owned_pixels = (size_t)b.W * (size_t)(b.r1 - b.r0);
+    Planes& p = ctx->planes;
+    auto& L = ctx->allocations;
+    HK_CUDA(alloc_plane(ctx, &p.pos_depth, n, L));
+    HK_CUDA(alloc_plane(ctx, &p.normal, n, L));
+    HK_CUDA(alloc_plane(ctx, &p.depth_gradient, n, L));
+    HK_CUDA(alloc_plane(ctx, &p.instance_material, n, L));
+    HK_CUDA(alloc_plane(ctx, &p.velocity_uv, n, L));
+    HK_CUDA(alloc_plane(ctx, &p.albedo, n, L));
+    for (int i = 0; i < 3; ++i) {
+        HK_CUDA(alloc_plane(ctx, &p.render[i], n, L));
+        HK_CUDA(alloc_plane(ctx, &p.variance[i], n, L));
+        HK_CUDA(alloc_plane(ctx, &p.dn_variance[i], n, L));
+        HK_CUDA(alloc_plane(ctx, &p.dn_render[i], n, L));
+        for (int l = 0; l < 4; ++l) HK_CUDA(alloc_plane(ctx, &p.dn_internal[l][i], n, L));
+    }
+    for (int r = 0; r < 10; ++r)
+        for (int q = 0; q < 4; ++q) HK_CUDA(alloc_plane(ctx, &p.reservoir[r].q[q], n, L));
+    HK_CUDA(alloc_plane(ctx, &p.tone_mapped, ctx->owned_pixels, L));
+    return HK_OK;
+}
+
+extern "C" {
+
+const char* hk_version(void) { return "hikari_b200 0.1 (sm_100a)"; }
+
+const char* hk_last_error(hk_context* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int hk_context_create(hk_context** out, int cuda_device, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end,
+                      void* cuda_stream) {
+    hk_context* ctx = nullptr;
+    if (!out) return set_error(nullptr, HK_ERR_INVALID_ARGUMENT, "out == NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_error(nullptr, HK_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                                   " (this library has no CPU fallback)");
+    if (cuda_device < 0 || cuda_device >= ndev) return set_error(nullptr, HK_ERR_INVALID_ARGUMENT, "bad cuda_device");
+    HK_CUDA(cudaSetDevice(cuda_device));
+    hk_context* c = new hk_context();
+    c->device = cuda_device;
+    ctx = c;
+    if (cuda_stream) c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return set_error(nullptr, HK_ERR_CUDA, cudaGetErrorString(e)); }
+        c->own_stream = true;
+    }
+    int rc = allocate_planes(c, width, height, row_begin, row_end);
+    if (rc == HK_OK) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, sizeof(Counters)) != cudaSuccess) rc = set_error(c, HK_ERR_OUT_OF_MEMORY, "counters");
+        else { c->counters = reinterpret_cast<Counters*>(p); cudaMemsetAsync(p, 0, sizeof(Counters), c->stream); }
+    }
+    if (rc == HK_OK)
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = set_error(c, HK_ERR_CUDA, "cudaEventCreate");
+    if (rc != HK_OK) {
+        g_create_error = c->error;
+        hk_context_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return HK_OK;
+}
+
+void hk_context_destroy(hk_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_list(ctx->allocations);
+    free_list(ctx->scene_allocations);
+    if (ctx->noise) cudaFree(ctx->noise);
+    if (ctx->counters) cudaFree(ctx->counters);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int hk_context_resize(hk_context* ctx, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return allocate_planes(ctx, width, height, row_begin, row_end);  // planes come back zeroed (light.rs:342-363)
+}
+
+int hk_reset_temporal_state(hk_context* ctx) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < 10; ++r)
+        for (int q = 0; q < 4; ++q) HK_CUDA(cudaMemsetAsync(ctx->planes.reservoir[r].q[q], 0, ctx->band_pixels * sizeof(uint4), ctx->stream));
+    return HK_OK;
+}
+
+}  // extern "C"
+
+template <class T>
+static cudaError_t upload(hk_context* ctx, const T** dst, const T* src, uint32_t count) {
+    void* p = nullptr;
+    size_t bytes = (size_t)count * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes + 64);   // +64: 16-byte vector loads at the tail stay in bounds
+    if (e != cudaSuccess) return e;
+    ctx->scene_allocations.push_back(p);
+    e = cudaMemsetAsync(p, 0, bytes + 64, ctx->stream);
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    *dst = reinterpret_cast<const T*>(p);
+    return e;
+}
+
+extern "C" {
+
+int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
+    if (!ctx || !s) return HK_ERR_INVALID_ARGUMENT;
+    if ((s->vertex_count && !s->vertices) || (s->primitive_count && !s->primitives) || (s->instance_count && !s->instances) ||
+        (s->material_count && !s->materials) || (s->asset_node_count && !s->asset_nodes) ||
+        (s->instance_node_count && !s->instance_nodes) || (s->emissive_node_count && !s->emissive_nodes) ||
+        (s->emissive_count && !s->emissives) || (s->alias_count && !s->alias_table) || (s->texture_count && !s->textures))
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "scene buffer pointer is NULL with a non-zero count");
+    // validate indices once so that kernels can skip bounds checks
+    for (uint32_t i = 0; i < s->instance_count; ++i) {
+        const hk_instance& in = s->instances[i];
+        if (in.material >= s->material_count || (uint64_t)in.mesh.node_offset + in.mesh.node_count > s->asset_node_count)
+            return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "instance references a material / node range out of bounds");
+    }
+    HK_CUDA(cudaSetDevice(ctx->device));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_list(ctx->scene_allocations);
+    ctx->scene_ready = false;
+    DeviceScene d{};
+    HK_CUDA(upload(ctx, &d.vertices, s->vertices, s->vertex_count));
+    HK_CUDA(upload(ctx, &d.primitives, s->primitives, s->primitive_count));
+    HK_CUDA(upload(ctx, &d.asset_nodes, s->asset_nodes, s->asset_node_count));
+    HK_CUDA(upload(ctx, &d.alias_table, s->alias_table, s->alias_count));
+    HK_CUDA(upload(ctx, &d.instances, s->instances, s->instance_count));
+    HK_CUDA(upload(ctx, &d.instance_nodes, s->instance_nodes, s->instance_node_count));
+    HK_CUDA(upload(ctx, &d.materials, s->materials, s->material_count));
+    HK_CUDA(upload(ctx, &d.emissive_nodes, s->emissive_nodes, s->emissive_node_count));
+    HK_CUDA(upload(ctx, &d.emissives, s->emissives, s->emissive_count));
+    d.instance_node_count = s->instance_node_count;
+    d.emissive_node_count = s->emissive_node_count;
+    d.texture_count = s->texture_count;
+    d.textures = nullptr;
+    if (s->texture_count) {
+        // decode to linear float4 texels on the host (sRGB LUT built with the same libm call as the oracle's)
+        float srgb_lut[256], lin_lut[256];
+        for (int i = 0; i < 256; ++i) {
+            double v = i / 255.0;
+            lin_lut[i] = (float)v;
+            srgb_lut[i] = (float)(v <= 0.04045 ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4));
+        }
+        std::vector<uint4> info(s->texture_count);
+        size_t total = 0;
+        for (uint32_t t = 0; t < s->texture_count; ++t) {
+            const hk_texture_desc& td = s->textures[t];
+            if (!td.rgba8 || !td.width || !td.height) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "bad texture");
+            info[t] = make_uint4((uint32_t)total, td.width, td.height,
+                                 (td.address_mode_u & 3u) | ((td.address_mode_v & 3u) << 2) | (td.filter_linear ? 16u : 0u));
+            total += (size_t)td.width * td.height;
+        }
+        if (total > 0xFFFFFFFFull) return set_error(ctx, HK_ERR_UNSUPPORTED, "texture atlas too large");
+        std::vector<float4> texels(total);
+        for (uint32_t t = 0; t < s->texture_count; ++t) {
+            const hk_texture_desc& td = s->textures[t];
+            const float* lut = td.srgb ? srgb_lut : lin_lut;
+            float4* dst = texels.data() + info[t].x;
+            size_t n = (size_t)td.width * td.height;
+            for (size_t i = 0; i < n; ++i)
+                dst[i] = make_float4(lut[td.rgba8[4 * i]], lut[td.rgba8[4 * i + 1]], lut[td.rgba8[4 * i + 2]], lin_lut[td.rgba8[4 * i + 3]]);
+        }
+        HK_CUDA(upload(ctx, &d.texture_texels, texels.data(), (uint32_t)total));
+        HK_CUDA(upload(ctx, &d.texture_info, info.data(), s->texture_count));
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging vectors die at scope exit
+    }
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));      // caller's arrays may be freed after return
+    ctx->scene = d;
+    ctx->scene_ready = true;
+    return HK_OK;
+}
+
+int hk_set_noise(hk_context* ctx, const uint8_t* rgba) {
+    if (!ctx || !rgba) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = 16u * 64u * 64u * 4u;
+    if (!ctx->noise) { void* p = nullptr; HK_CUDA(cudaMalloc(&p, bytes)); ctx->noise = reinterpret_cast<uint8_t*>(p); }
+    HK_CUDA(cudaMemcpyAsync(ctx->noise, rgba, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->noise_ready = true;
+    return HK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ scheduling
+static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
+    if (!ctx || !in) return HK_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene_ready || !ctx->noise_ready) return set_error(ctx, HK_ERR_NOT_READY, "scene or noise not uploaded");
+    if (in->frame.upscale_ratio != 1.0f)
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "upscale_ratio != 1 (render size must equal target size in this build)");
+    if (in->frame.direct_validate_interval == 0 || in->frame.emissive_validate_interval == 0)
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "validate interval must be >= 1");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return set_error(ctx, HK_ERR_CUDA, "cudaSetDevice");
+    P.in = *in;
+    P.scene = ctx->scene;
+    P.planes = ctx->planes;
+    P.band = ctx->band;
+    P.counters = ctx->count_rays ? ctx->counters : nullptr;
+    P.noise = ctx->noise;
+    float s, c;
+    hk::sincos_(in->frame.solar_angle, &s, &c);
+    P.cos_solar_angle = c;
+    P.random_frame = hk::random_float(in->frame.number);
+    return HK_OK;
+}
+static void rows(const hk_context* ctx, KParams& P, int ghost) {
+    P.row_lo = ctx->band.r0 - ghost < ctx->band.a0 ? ctx->band.a0 : ctx->band.r0 - ghost;
+    P.row_hi = ctx->band.r1 + ghost > ctx->band.a1 ? ctx->band.a1 : ctx->band.r1 + ghost;
+}
+static int check_launch(hk_context* ctx) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ctx, HK_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    return HK_OK;
+}
+
+static int run_prepass(hk_context* ctx, KParams& P) {
+    rows(ctx, P, GHOST_TEMPORAL);
+    hk_launch_gbuffer(P, ctx->count_rays, ctx->stream);
+    ctx->launches += 1;
+    return check_launch(ctx);
+}
+static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, light.rs:645-699 (albedo is fused in the prepass)
+    const hk_frame_uniform& f = P.in.frame;
+    rows(ctx, P, GHOST_TEMPORAL);
+    hk_launch_direct(P, false, ctx->count_rays, ctx->stream);
+    hk_launch_direct(P, true, ctx->count_rays, ctx->stream);
+    ctx->launches += 2;
+    if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); hk_launch_spatial(P, true, ctx->stream); ctx->launches += 1; }
+    rows(ctx, P, GHOST_TEMPORAL);
+    hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
+    ctx->launches += 1;
+    if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); hk_launch_spatial(P, false, ctx->stream); ctx->launches += 1; }
+    return check_launch(ctx);
+}
+static int run_post(hk_context* ctx, KParams& P, bool fuse) {  // PostProcessNode::run, post_process.rs:1190-1234
+    if (P.in.denoise) {
+        const int signals = (P.in.frame.indirect_bounces == 0) ? 2 : 3;  // post_process.rs:949-954
+        rows(ctx, P, GHOST_DEMOD); hk_launch_demodulation(P, signals, ctx->stream);
+        rows(ctx, P, GHOST_L0); hk_launch_denoise_level(P, 0, signals, false, false, ctx->stream);
+        rows(ctx, P, GHOST_L1); hk_launch_denoise_level(P, 1, signals, false, false, ctx->stream);
+        rows(ctx, P, GHOST_L2); hk_launch_denoise_level(P, 2, signals, false, false, ctx->stream);
+        rows(ctx, P, 0); hk_launch_denoise_level(P, 3, signals, fuse, !fuse || ctx->keep_intermediates, ctx->stream);
+        ctx->launches += 5;
+        if (!fuse) { hk_launch_tone_mapping(P, ctx->stream); ctx->launches += 1; }
+    } else {
+        rows(ctx, P, 0);
+        hk_launch_tone_mapping(P, ctx->stream);
+        ctx->launches += 1;
+    }
+    return check_launch(ctx);
+}
+
+int hk_prepass_run(hk_context* ctx, const hk_frame_inputs* in) {
+    KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
+    ctx->launches = 0;
+    return run_prepass(ctx, P);
+}
+int hk_light_run(hk_context* ctx, const hk_frame_inputs* in) {
+    KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
+    ctx->launches = 0;
+    return run_light(ctx, P);
+}
+int hk_post_process_run(hk_context* ctx, const hk_frame_inputs* in) {
+    KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
+    ctx->launches = 0;
+    return run_post(ctx, P, false);
+}
+int hk_render_frame(hk_context* ctx, const hk_frame_inputs* in) {
+    KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
+    ctx->launches = 0;
+    const bool t = ctx->time_passes;
+    if (ctx->count_rays) HK_CUDA(cudaMemsetAsync(ctx->counters, 0, sizeof(Counters), ctx->stream));
+    if (t) cudaEventRecord(ctx->ev[0], ctx->stream);
+    rc = run_prepass(ctx, P); if (rc) return rc;
+    if (t) cudaEventRecord(ctx->ev[1], ctx->stream);
+    rc = run_light(ctx, P); if (rc) return rc;
+    if (t) cudaEventRecord(ctx->ev[2], ctx->stream);
+    rc = run_post(ctx, P, true); if (rc) return rc;
+    if (t) cudaEventRecord(ctx->ev[3], ctx->stream);
+    return HK_OK;
+}
+
+int hk_sync(hk_context* ctx) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HK_OK;
+}
+
+int hk_set_profiling(hk_context* ctx, int count_rays, int time_passes) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    ctx->count_rays = count_rays != 0;
+    ctx->time_passes = time_passes != 0;
+    return HK_OK;
+}
+int hk_set_keep_intermediates(hk_context* ctx, int keep) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    ctx->keep_intermediates = keep != 0;
+    return HK_OK;
+}
+
+int hk_get_stats(hk_context* ctx, hk_frame_stats* out) {
+    if (!ctx || !out) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    memset(out, 0, sizeof(*out));
+    if (ctx->count_rays) {
+        Counters h;
+        HK_CUDA(cudaMemcpy(&h, ctx->counters, sizeof(h), cudaMemcpyDeviceToHost));
+        out->primary_rays = h.primary; out->tlas_rays = h.tlas; out->blas_rays = h.blas;
+    }
+    if (ctx->time_passes) {
+        cudaEventElapsedTime(&out->ms_prepass, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&out->ms_light, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&out->ms_post_process, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&out->ms_total, ctx->ev[0], ctx->ev[3]);
+    }
+    out->kernel_launches = ctx->launches;
+    return HK_OK;
+}
+
+int hk_band_rows(hk_context* ctx, uint32_t* a0, uint32_t* a1) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    if (a0) *a0 = (uint32_t)ctx->band.a0;
+    if (a1) *a1 = (uint32_t)ctx->band.a1;
+    return HK_OK;
+}
+
+}  // extern "C"
+
+// ----------------------------------------------------------------------------------------- outputs / state
+__global__ void k_gather_reservoir(ReservoirPlanes b, size_t first, size_t n, uint4* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int q = 0; q < 4; ++q) out[4 * i + q] = b.q[q][first + i];
+}
+__global__ void k_scatter_reservoir(ReservoirPlanes b, size_t first, size_t n, const uint4* in) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int q = 0; q < 4; ++q) b.q[q][first + i] = in[4 * i + q];
+}
+
+// device pointer of the owned rows of a plane + bytes per pixel; reservoirs are handled separately
+static void* owned_plane(hk_context* ctx, int which, size_t* bpp) {
+    const Planes& p = ctx->planes;
+    const size_t first = (size_t)(ctx->band.r0 - ctx->band.a0) * (size_t)ctx->band.W;
+    switch (which) {
+        case HK_OUT_TONE_MAPPED: *bpp = 8; return p.tone_mapped;
+        case HK_OUT_RENDER_DIRECT: case HK_OUT_RENDER_EMISSIVE: case HK_OUT_RENDER_INDIRECT:
+            *bpp = 8; return p.render[which - HK_OUT_RENDER_DIRECT] + first;
+        case HK_OUT_VARIANCE_DIRECT: case HK_OUT_VARIANCE_EMISSIVE: case HK_OUT_VARIANCE_INDIRECT:
+            *bpp = 4; return p.variance[which - HK_OUT_VARIANCE_DIRECT] + first;
+        case HK_OUT_ALBEDO: *bpp = 8; return p.albedo + first;
+        case HK_OUT_DENOISED_DIRECT: case HK_OUT_DENOISED_EMISSIVE: case HK_OUT_DENOISED_INDIRECT:
+            *bpp = 8; return p.dn_render[which - HK_OUT_DENOISED_DIRECT] + first;
+        case HK_OUT_GBUFFER_POSITION: *bpp = 16; return p.pos_depth + first;
+        case HK_OUT_GBUFFER_NORMAL: *bpp = 4; return p.normal + first;
+        case HK_OUT_GBUFFER_DEPTH_GRADIENT: *bpp = 8; return p.depth_gradient + first;
+        case HK_OUT_GBUFFER_INSTANCE_MATERIAL: *bpp = 8; return p.instance_material + first;
+        case HK_OUT_GBUFFER_VELOCITY_UV: *bpp = 16; return p.velocity_uv + first;
+    }
+    return nullptr;
+}
+
+extern "C" {
+
+int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes) {
+    if (!ctx || !device_ptr) return HK_ERR_INVALID_ARGUMENT;
+    if (which != HK_OUT_TONE_MAPPED) return set_error(ctx, HK_ERR_UNSUPPORTED, "only HK_OUT_TONE_MAPPED is exposed as a device pointer");
+    *device_ptr = ctx->planes.tone_mapped;
+    if (bytes) *bytes = ctx->owned_pixels * 8;
+    return HK_OK;
+}
+
+static int transfer(hk_context* ctx, int which, void* host, size_t bytes, bool to_host) {
+    if (!ctx || !host) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = ctx->owned_pixels;
+    if (which >= HK_OUT_RESERVOIR_0 && which < HK_OUT_RESERVOIR_0 + 10) {
+        if (bytes != n * 64) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
+        uint4* tmp = nullptr;
+        HK_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), bytes));
+        const size_t first = (size_t)(ctx->band.r0 - ctx->band.a0) * (size_t)ctx->band.W;
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        cudaError_t e;
+        if (to_host) {
+            k_gather_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], first, n, tmp);
+            e = cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        } else {
+            e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+            k_scatter_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], first, n, tmp);
+        }
+        cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+        cudaFree(tmp);
+        HK_CUDA(e);
+        HK_CUDA(e2);
+        return HK_OK;
+    }
+    size_t bpp = 0;
+    void* dev = owned_plane(ctx, which, &bpp);
+    if (!dev) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown plane id");
+    if (bytes != n * bpp) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
+    if (to_host) HK_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    else HK_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HK_OK;
+}
+int hk_readback(hk_context* ctx, int which, void* host, size_t bytes) { return transfer(ctx, which, host, bytes, true); }
+int hk_upload_state(hk_context* ctx, int which, const void* host, size_t bytes) {
+    return transfer(ctx, which, const_cast<void*>(host), bytes, false);
+}
+
+int hk_trace_rays(hk_context* ctx, const hk_ray* rays, size_t n, hk_hit* hits) {
+    if (!ctx || (n && (!rays || !hits))) return HK_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene_ready) return set_error(ctx, HK_ERR_NOT_READY, "scene not uploaded");
+    if (n == 0) return HK_OK;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    hk_ray* d_rays = nullptr; hk_hit* d_hits = nullptr;
+    HK_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_rays), n * sizeof(hk_ray)));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_hits), n * sizeof(hk_hit));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(hk_ray), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) { hk_launch_trace_rays(ctx->scene, d_rays, n, d_hits, ctx->stream); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_hits, n * sizeof(hk_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_rays); cudaFree(d_hits);
+    HK_CUDA(e);
+    return HK_OK;
+}
+
+}  // extern "C"

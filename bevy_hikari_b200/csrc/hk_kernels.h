@@ -1,0 +1,15 @@
+// hk_kernels.h — host-callable launchers of the CUDA kernels (implemented in kernels_light.cu / kernels_post.cu).
+#pragma once
+#include "hk_device.cuh"
+
+void hk_launch_gbuffer(const hkd::KParams& P, bool count, cudaStream_t st);
+void hk_launch_albedo(const hkd::KParams& P, cudaStream_t st);
+void hk_launch_direct(const hkd::KParams& P, bool emissive, bool count, cudaStream_t st);
+void hk_launch_indirect(const hkd::KParams& P, bool multi, bool count, cudaStream_t st);
+void hk_launch_spatial(const hkd::KParams& P, bool emissive, cudaStream_t st);
+void hk_launch_trace_rays(const hkd::DeviceScene& sc, const hk_ray* rays, size_t n, hk_hit* hits, cudaStream_t st);
+
+// post process: `signals` = 2 or 3 (post_process.rs:949-954)
+void hk_launch_demodulation(const hkd::KParams& P, int signals, cudaStream_t st);
+void hk_launch_denoise_level(const hkd::KParams& P, int level, int signals, bool fuse_tone_mapping, bool keep_denoised, cudaStream_t st);
+void hk_launch_tone_mapping(const hkd::KParams& P, cudaStream_t st);

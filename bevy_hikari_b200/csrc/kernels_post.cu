@@ -1,0 +1,218 @@
+// kernels_post.cu — the post-process node of the B200 path: demodulation, 4-level edge-stopping a-trous denoise and
+// tone mapping.  Replaces src/shaders/denoise.wgsl + tone_mapping.wgsl as dispatched by PostProcessNode::run
+// (src/post_process.rs:1140-1234): 3 x (1 + 4) + 1 = 16 dispatches there, 5 launches here —
+//   * the three signals (sun / emissive / indirect) are filtered by the same thread: the geometric edge-stopping
+//     weights (normal^16, depth/gradient, instance) depend only on the G-buffer and are computed once per tap instead
+//     of three times; only the luminance weight is per signal.  Per signal the arithmetic and its order are the
+//     reference's, so results are bit-identical to running the passes one signal at a time;
+//   * level 3 re-modulates with albedo, and (optionally) sums the signals and applies Reinhard tone mapping in the
+//     same thread, so denoise_render[3] never has to be re-read.
+#include "hk_device.cuh"
+#include "hk_kernels.h"
+
+namespace hkd {
+
+__device__ __forceinline__ vec4 load16(const uint2* plane, size_t i) {
+    uint2 u = plane[i];
+    uvec2 w; w.x = u.x; w.y = u.y;
+    return unpack_rgba16f(w);
+}
+__device__ __forceinline__ void store16(uint2* plane, size_t i, vec4 v) {
+    uvec2 w = pack_rgba16f(v);
+    plane[i] = make_uint2(w.x, w.y);
+}
+__device__ __forceinline__ bool bad3(vec3 v) {  // any_is_nan_vec3(v) || any(v > F32_MAX), denoise.wgsl:190,239
+    return is_nan(v.x) || is_nan(v.y) || is_nan(v.z) || v.x > F32_MAX || v.y > F32_MAX || v.z > F32_MAX;
+}
+__device__ __forceinline__ float kernel_at(const KParams& P, int a, int b) { return P.in.frame.kernel[a][b]; }
+
+// ----------------------------------------------------------------------------------------- demodulation
+// denoise.wgsl:135-162 for all signals of a pixel.
+__global__ void __launch_bounds__(CTA_THREADS) k_demodulation(const __grid_constant__ KParams P, int signals) {
+    int x, y;
+    tile_pixel(x, y, P.row_lo);
+    if (x >= P.band.W || y >= P.row_hi) return;
+    const size_t idx = band_index(P.band, x, y);
+    const vec3 albedo = xyz(load16(P.planes.albedo, idx));
+    for (int sgl = 0; sgl < signals; ++sgl) {
+        vec3 irradiance = xyz(load16(P.planes.render[sgl], idx));
+        vec3 q = irradiance / albedo;
+        irradiance = v3(albedo.x < 0.01f ? 0.0f : q.x, albedo.y < 0.01f ? 0.0f : q.y, albedo.z < 0.01f ? 0.0f : q.z);
+        store16(P.planes.dn_internal[0][sgl], idx, v4(irradiance, 1.0f));
+        float sum_variance = 0.0f;
+        // accumulate_variance order of denoise.wgsl:152-160: x outer (-1,0,1), y inner (-1,0,1)
+#pragma unroll
+        for (int ox = -1; ox <= 1; ++ox) {
+#pragma unroll
+            for (int oy = -1; oy <= 1; ++oy) {
+                int sx = x + ox, sy = y + oy;
+                if (sx < 0 || sy < 0 || sx >= P.band.W || sy >= P.band.H) continue;
+                float variance = P.planes.variance[sgl][band_index(P.band, sx, sy)];
+                if (variance > F32_MAX) continue;
+                sum_variance += kernel_at(P, oy + 1, ox + 1) * fmax_(variance, 0.0f);
+            }
+        }
+        P.planes.dn_variance[sgl][idx] = sum_variance;
+    }
+}
+
+// --------------------------------------------------------------------------------------------- denoise level
+struct SignalAcc {
+    vec3 irradiance, sum_irradiance;
+    float sum_w, lum, variance, ff_moment_1, ff_moment_2, ff_count;
+};
+
+template <int LEVEL, bool FUSE_TONE_MAPPING>
+__global__ void __launch_bounds__(CTA_THREADS) k_denoise(const __grid_constant__ KParams P, int signals, int keep_denoised) {
+    constexpr int STEP = 8 >> LEVEL;  // denoise.wgsl:101-114: coarse to fine
+    int x, y;
+    tile_pixel(x, y, P.row_lo);
+    if (x >= P.band.W || y >= P.row_hi) return;
+    const size_t idx = band_index(P.band, x, y);
+    const float depth = P.planes.pos_depth[idx].w;
+    vec4 result[3];
+    result[0] = result[1] = result[2] = v4(0.0f);
+    if (!(depth < F32_EPSILON)) {
+        const float2 dg = P.planes.depth_gradient[idx];
+        const vec2 depth_gradient = v2(dg.x, dg.y);
+        const vec3 normal = normalize(xyz(unpack4x8snorm(P.planes.normal[idx])));
+        const float instance = P.planes.instance_material[idx].x;
+
+        SignalAcc acc[3];
+#pragma unroll
+        for (int sgl = 0; sgl < 3; ++sgl) {
+            if (sgl >= signals) continue;
+            SignalAcc& a = acc[sgl];
+            a.variance = P.planes.dn_variance[sgl][idx];
+            a.irradiance = xyz(load16(P.planes.dn_internal[LEVEL][sgl], idx));
+            a.sum_irradiance = a.irradiance * kernel_at(P, 1, 1);
+            a.sum_w = kernel_at(P, 1, 1);
+            if (bad3(a.irradiance)) { a.irradiance = v3(0.0f); a.sum_irradiance = v3(0.0f); a.sum_w = 0.0f; }
+            a.lum = luminance(a.irradiance);
+            a.ff_moment_1 = 0.0f; a.ff_moment_2 = 0.0f; a.ff_count = 0.0f;
+        }
+
+        // tap order of denoise.wgsl:252-268
+        const int OX[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+        const int OY[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int ox = OX[t], oy = OY[t];
+            const int sx = x + ox * STEP, sy = y + oy * STEP;
+            if (sx < 0 || sy < 0 || sx >= P.band.W || sy >= P.band.H) continue;
+            const size_t sidx = band_index(P.band, sx, sy);
+            // geometric weights: once per tap for all signals
+            const vec3 sample_normal = normalize(xyz(unpack4x8snorm(P.planes.normal[sidx])));
+            const float sample_depth = P.planes.pos_depth[sidx].w;
+            const float sample_instance = P.planes.instance_material[sidx].x;
+            const float w_normal = pow16(fmax_(0.0f, dot(normal, sample_normal)));                                       // :44-47
+            const float w_depth = exp_((-fabsf(depth - sample_depth)) / (fabsf(dot(depth_gradient, v2((float)ox, (float)oy))) + 0.01f));  // :50-53
+            const float w_instance = fmax_(0.0f, 1.0f - fabsf(instance - sample_instance));                              // :63-65
+            const float w_geometry = w_normal * w_depth * w_instance;
+            const float k = kernel_at(P, oy + 1, ox + 1);
+#pragma unroll
+            for (int sgl = 0; sgl < 3; ++sgl) {
+                if (sgl >= signals) continue;
+                SignalAcc& a = acc[sgl];
+                vec3 irr = xyz(load16(P.planes.dn_internal[LEVEL][sgl], sidx));
+                if (bad3(irr)) continue;
+                float sample_luminance = luminance(irr);
+                float w_luminance = exp_((-fabsf(a.lum - sample_luminance)) / (4.0f * pow025(a.variance) + 0.001f));    // :56-61
+                float w = clampf(w_geometry * w_luminance, 0.0f, 1.0f) * k;
+                a.sum_irradiance = a.sum_irradiance + irr * w;
+                a.sum_w += w;
+                if (sgl != 0) {  // FIREFLY_FILTERING: emissive + indirect only (post_process.rs:1193-1197)
+                    a.ff_moment_1 += sample_luminance;
+                    a.ff_moment_2 += sample_luminance * sample_luminance;
+                    a.ff_count += 1.0f;
+                }
+            }
+        }
+
+        vec4 albedo = v4(1.0f);
+        if (LEVEL == 3) albedo = load16(P.planes.albedo, idx);
+#pragma unroll
+        for (int sgl = 0; sgl < 3; ++sgl) {
+            if (sgl >= signals) continue;
+            SignalAcc& a = acc[sgl];
+            vec3 irradiance = (a.sum_w < 0.0001f) ? v3(0.0f) : a.sum_irradiance / a.sum_w;
+            if (sgl != 0) {
+                float ff_mean = a.ff_moment_1 / a.ff_count;
+                float ff_var = a.ff_moment_2 / a.ff_count - ff_mean * ff_mean;
+                if (a.lum > ff_mean + 3.0f * sqrtf(ff_var)) irradiance = ff_mean / a.lum * irradiance;
+            }
+            vec4 color = v4(irradiance, 1.0f);
+            if (LEVEL == 3) color = color * albedo;  // denoise.wgsl:314-315
+            result[sgl] = color;
+        }
+    }
+
+    if (LEVEL < 3) {
+        for (int sgl = 0; sgl < signals; ++sgl) store16(P.planes.dn_internal[LEVEL + 1][sgl], idx, result[sgl]);
+        return;
+    }
+    // level 3 -> denoise_render (Rgba16Float), then tone_mapping.wgsl:21-32 on the f16-rounded values
+    vec4 color = v4(0.0f);
+    for (int sgl = 0; sgl < signals; ++sgl) {
+        uvec2 w = pack_rgba16f(result[sgl]);
+        if (!FUSE_TONE_MAPPING || keep_denoised) P.planes.dn_render[sgl][idx] = make_uint2(w.x, w.y);
+        if (FUSE_TONE_MAPPING) color = color + unpack_rgba16f(w);
+    }
+    if (FUSE_TONE_MAPPING && y >= P.band.r0 && y < P.band.r1) {
+        vec3 rgb = reinhard_luminance(vmax(xyz(color), 0.0039f));
+        color = v4(rgb, color.w);
+        if (!(color.w > 0.0f))
+            color = v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]);
+        store16(P.planes.tone_mapped, (size_t)(y - P.band.r0) * (size_t)P.band.W + (size_t)x, color);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- tone mapping
+// tone_mapping.wgsl:21-32 stand-alone (denoise off, or nodes run one by one); inputs per post_process.rs:940-954.
+__global__ void __launch_bounds__(CTA_THREADS) k_tone_mapping(const __grid_constant__ KParams P) {
+    int x, y;
+    tile_pixel(x, y, P.row_lo);
+    if (x >= P.band.W || y >= P.row_hi) return;
+    const size_t idx = band_index(P.band, x, y);
+    const bool dn = P.in.denoise != 0u;
+    uint2* const* src = dn ? P.planes.dn_render : P.planes.render;
+    vec4 color = load16(src[0], idx);
+    color = color + load16(src[1], idx);
+    if (P.in.frame.indirect_bounces != 0u) color = color + load16(src[2], idx);
+    vec3 rgb = reinhard_luminance(vmax(xyz(color), 0.0039f));
+    color = v4(rgb, color.w);
+    if (!(color.w > 0.0f))
+        color = v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]);
+    store16(P.planes.tone_mapped, (size_t)(y - P.band.r0) * (size_t)P.band.W + (size_t)x, color);
+}
+
+static dim3 grid_for(const KParams& P) {
+    int rows = P.row_hi - P.row_lo;
+    return dim3((unsigned)((P.band.W + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
+}
+
+}  // namespace hkd
+
+using namespace hkd;
+
+void hk_launch_demodulation(const KParams& P, int signals, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo) return;
+    k_demodulation<<<grid_for(P), CTA_THREADS, 0, st>>>(P, signals);
+}
+void hk_launch_denoise_level(const KParams& P, int level, int signals, bool fuse_tone_mapping, bool keep_denoised, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo) return;
+    dim3 g = grid_for(P);
+    int keep = keep_denoised ? 1 : 0;
+    switch (level) {
+        case 0: k_denoise<0, false><<<g, CTA_THREADS, 0, st>>>(P, signals, keep); break;
+        case 1: k_denoise<1, false><<<g, CTA_THREADS, 0, st>>>(P, signals, keep); break;
+        case 2: k_denoise<2, false><<<g, CTA_THREADS, 0, st>>>(P, signals, keep); break;
+        default:
+            if (fuse_tone_mapping) k_denoise<3, true><<<g, CTA_THREADS, 0, st>>>(P, signals, keep);
+            else k_denoise<3, false><<<g, CTA_THREADS, 0, st>>>(P, signals, keep);
+    }
+}
+void hk_launch_tone_mapping(const KParams& P, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo) return;
+    k_tone_mapping<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+}

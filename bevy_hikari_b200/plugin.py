@@ -1,0 +1,231 @@
+"""Python face of the host mirror (bevy_hikari_b200/host/hikari.hpp): the names a bevy-hikari user knows —
+HikariPlugin, HikariSettings, Taa, Upscale, graph NAME — driving libhikari_b200.so through ctypes.  No arithmetic of
+the path happens here; this file only moves bytes across the C ABI."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _ffi
+from . import layout as L
+from ._ffi import Settings, check, lib
+
+TAA_JASMINE, TAA_NONE = 0, 1
+UPSCALE_FSR1, UPSCALE_SMAA_TU4X = 0, 1
+NOISE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "noise_rgba8_64x64x16.bin")
+
+
+def graph_name():
+    return lib().hikari_graph_name().decode()
+
+
+def HikariSettings(**overrides):
+    """HikariSettings::default() (src/lib.rs:435-455) with keyword overrides, as a ctypes struct."""
+    s = Settings()
+    lib().hikari_settings_default(C.byref(s))
+    for k, v in overrides.items():
+        if k == "clear_color":
+            s.clear_color[:] = list(v)
+        elif not hasattr(s, k):
+            raise AttributeError(f"HikariSettings has no field {k}")
+        else:
+            setattr(s, k, v)
+    return s
+
+
+def make_frame_inputs(settings, frame_counter, view, previous_view, lights):
+    out = L.FrameInputs()
+    lib().hikari_make_frame_inputs(C.byref(settings), int(frame_counter), C.byref(view), C.byref(previous_view),
+                                   C.byref(lights), C.byref(out))
+    return out
+
+
+def load_noise():
+    a = np.fromfile(NOISE_PATH, np.uint8)
+    assert a.size == 16 * 64 * 64 * 4, "data/noise_rgba8_64x64x16.bin is damaged"
+    return a
+
+
+class World:
+    """MeshMaterialPlugin's render-world state: meshes, materials, textures, instances -> the nine GPU buffers."""
+
+    def __init__(self):
+        self._w = lib().hikari_world_create()
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "_w", None):
+            lib().hikari_world_destroy(self._w)
+            self._w = None
+
+    def add_mesh(self, positions, normals, uvs, indices=None, topology=0):
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float32) for a in (positions, normals, uvs)]
+        n = len(arrs[0]) if arrs[0] is not None else 0
+        idx = None if indices is None else np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        ptr = lambda a: None if a is None else a.ctypes.data
+        return lib().hikari_world_add_mesh(self._w, ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), n, ptr(idx),
+                                           0 if idx is None else idx.size, topology)
+
+    def add_material(self, material_record):
+        m = np.zeros(1, L.MATERIAL)
+        m[0] = material_record
+        return lib().hikari_world_add_material(self._w, m.ctypes.data)
+
+    def add_texture(self, rgba, address_mode_u=0, address_mode_v=0, filter_linear=1, srgb=1):
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        t = L.TextureDesc(rgba.ctypes.data, rgba.shape[1], rgba.shape[0], address_mode_u, address_mode_v, filter_linear, srgb)
+        return lib().hikari_world_add_texture(self._w, C.byref(t))
+
+    def add_instance(self, mesh, material, transform16, visible=True):
+        t = np.ascontiguousarray(transform16, np.float32).reshape(16)
+        return lib().hikari_world_add_instance(self._w, mesh, material, t.ctypes.data, 1 if visible else 0)
+
+    def prepare(self):
+        lib().hikari_world_prepare(self._w)
+
+    def mesh_error(self, mesh):
+        return lib().hikari_world_mesh_error(self._w, mesh)
+
+    def scene_desc(self):
+        d = L.SceneDesc()
+        lib().hikari_world_scene_desc(self._w, C.byref(d))
+        return d
+
+    def buffers(self):
+        """Copies of the nine buffers as numpy structured arrays (for comparison with the oracle's builder)."""
+        d = self.scene_desc()
+        out = {}
+        counts = {"vertices": d.vertex_count, "primitives": d.primitive_count, "asset_nodes": d.asset_node_count,
+                  "alias_table": d.alias_count, "instances": d.instance_count, "instance_nodes": d.instance_node_count,
+                  "materials": d.material_count, "emissive_nodes": d.emissive_node_count, "emissives": d.emissive_count}
+        for name, dt in L.SCENE_BUFFERS:
+            n = counts[name]
+            ptr = getattr(d, name)
+            if n == 0 or not ptr:
+                out[name] = np.zeros(0, dt)
+            else:
+                out[name] = np.frombuffer(C.string_at(ptr, n * dt.itemsize), dt).copy()
+        return out
+
+
+def scene_desc_from_buffers(buffers, textures=()):
+    """hk_scene_desc over numpy arrays (keeps them alive on the returned object)."""
+    d = L.SceneDesc()
+    keep = []
+    names = {"vertices": "vertex_count", "primitives": "primitive_count", "asset_nodes": "asset_node_count",
+             "alias_table": "alias_count", "instances": "instance_count", "instance_nodes": "instance_node_count",
+             "materials": "material_count", "emissive_nodes": "emissive_node_count", "emissives": "emissive_count"}
+    for name, dt in L.SCENE_BUFFERS:
+        a = np.ascontiguousarray(buffers[name], dt)
+        keep.append(a)
+        setattr(d, name, a.ctypes.data if a.size else None)
+        setattr(d, names[name], a.size)
+    if textures:
+        arr = (L.TextureDesc * len(textures))()
+        for i, t in enumerate(textures):
+            rgba = np.ascontiguousarray(t["rgba"], np.uint8)
+            keep.append(rgba)
+            arr[i] = L.TextureDesc(rgba.ctypes.data, rgba.shape[1], rgba.shape[0], int(t.get("address_mode_u", 0)),
+                                   int(t.get("address_mode_v", 0)), int(t.get("filter_linear", 1)), int(t.get("srgb", 1)))
+        keep.append(arr)
+        d.textures = C.cast(arr, C.c_void_p)
+        d.texture_count = len(textures)
+    d._keep = keep
+    return d
+
+
+class HikariPlugin:
+    """HikariPlugin + one camera with `CameraRenderGraph::new(graph::NAME)` (src/lib.rs:95-370)."""
+
+    def __init__(self, width, height, cuda_device=0, row_begin=0, row_end=None, cuda_stream=None):
+        self.width, self.height = width, height
+        self.row_begin, self.row_end = row_begin, height if row_end is None else row_end
+        self._p = lib().hikari_plugin_create()
+        noise = load_noise()
+        rc = lib().hikari_plugin_build(self._p, cuda_device, width, height, self.row_begin, self.row_end, noise.ctypes.data,
+                                       cuda_stream)
+        if rc != _ffi.HK_OK:
+            msg = lib().hk_last_error(None).decode()
+            lib().hikari_plugin_destroy(self._p)
+            self._p = None
+            raise _ffi.HikariError(f"HikariPlugin.build failed ({rc}): {msg}")
+        self.ctx = lib().hikari_plugin_context(self._p)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().hikari_plugin_destroy(self._p)
+            self._p = None
+            self.ctx = None
+
+    __del__ = close
+
+    @property
+    def owned_rows(self):
+        return self.row_end - self.row_begin
+
+    def upload_scene(self, world):
+        check(lib().hikari_plugin_upload_scene(self._p, world._w), self.ctx)
+
+    def upload_scene_desc(self, desc):
+        check(lib().hk_scene_upload(self.ctx, C.byref(desc)), self.ctx)
+
+    @property
+    def frame_counter(self):
+        return lib().hikari_plugin_frame_counter(self._p)
+
+    @frame_counter.setter
+    def frame_counter(self, v):
+        lib().hikari_plugin_set_frame_counter(self._p, int(v))
+
+    def run_frame(self, settings, view, previous_view, lights):
+        check(lib().hikari_plugin_run_frame(self._p, C.byref(settings), C.byref(view), C.byref(previous_view), C.byref(lights)),
+              self.ctx)
+
+    # individual nodes / raw C ABI
+    def prepass(self, inputs): check(lib().hk_prepass_run(self.ctx, C.byref(inputs)), self.ctx)
+    def light(self, inputs): check(lib().hk_light_run(self.ctx, C.byref(inputs)), self.ctx)
+    def post_process(self, inputs): check(lib().hk_post_process_run(self.ctx, C.byref(inputs)), self.ctx)
+    def render_frame(self, inputs): check(lib().hk_render_frame(self.ctx, C.byref(inputs)), self.ctx)
+    def sync(self): check(lib().hk_sync(self.ctx), self.ctx)
+    def reset_temporal_state(self): check(lib().hk_reset_temporal_state(self.ctx), self.ctx)
+    def set_profiling(self, count_rays, time_passes): check(lib().hk_set_profiling(self.ctx, int(count_rays), int(time_passes)), self.ctx)
+    def set_keep_intermediates(self, keep): check(lib().hk_set_keep_intermediates(self.ctx, int(keep)), self.ctx)
+
+    def stats(self):
+        s = L.FrameStats()
+        check(lib().hk_get_stats(self.ctx, C.byref(s)), self.ctx)
+        return s
+
+    def readback(self, which, out=None):
+        bpp, dt, comps = L.OUT_FORMATS[which]
+        n = self.owned_rows * self.width
+        if out is None:
+            out = np.empty(n * bpp, np.uint8)
+        check(lib().hk_readback(self.ctx, which, out.ctypes.data, n * bpp), self.ctx)
+        return view_plane(out, which, self.owned_rows, self.width)
+
+    def readback_into(self, which, host_ptr, nbytes):
+        check(lib().hk_readback(self.ctx, which, host_ptr, nbytes), self.ctx)
+
+    def upload_state(self, which, array):
+        a = np.ascontiguousarray(array)
+        check(lib().hk_upload_state(self.ctx, which, a.ctypes.data, a.nbytes), self.ctx)
+
+    def output_device_pointer(self):
+        p, b = C.c_void_p(), C.c_size_t()
+        check(lib().hk_get_output(self.ctx, L.OUT_TONE_MAPPED, C.byref(p), C.byref(b)), self.ctx)
+        return p.value, b.value
+
+    def trace_rays(self, rays):
+        rays = np.ascontiguousarray(rays, L.RAY)
+        hits = np.zeros(len(rays), L.HIT)
+        check(lib().hk_trace_rays(self.ctx, rays.ctypes.data, len(rays), hits.ctypes.data), self.ctx)
+        return hits
+
+
+def view_plane(raw, which, rows, width):
+    bpp, dt, comps = L.OUT_FORMATS[which]
+    a = np.frombuffer(raw, dt) if not isinstance(dt, np.dtype) or dt.names is None else np.frombuffer(raw, dt)
+    if comps == 1:
+        return a.reshape(rows, width)
+    return a.reshape(rows, width, comps)

@@ -1,0 +1,193 @@
+"""The reference's example scenes restated as data (examples/cornell.rs, examples/city.rs) + the benchmark configs of
+BASELINE.json.  A scene = what the Bevy app spawns: meshes, materials, textures, instances, a camera, lights."""
+import math
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import camera as cam
+from . import layout as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCENES = os.path.join(ROOT, "scenes")
+F = np.float32
+
+
+@dataclass
+class SceneData:
+    meshes: list                      # (positions, normals, uvs, indices)
+    materials: np.ndarray             # L.MATERIAL records
+    textures: list                    # dicts: rgba, address_mode_u/v, filter_linear, srgb
+    inst_mesh: list = field(default_factory=list)
+    inst_material: list = field(default_factory=list)
+    inst_transform: list = field(default_factory=list)   # 16 floats, column-major
+    eye: tuple = (0.0, 1.0, 4.0)
+    target: tuple = (0.0, 1.0, 0.0)
+    fov: float = math.pi / 4.0        # bevy PerspectiveProjection default
+    near: float = 0.1
+    sun_illuminance: float = None     # lux; None = no DirectionalLight
+    sun_direction_to_light: tuple = (0.0, 1.0, 0.0)
+
+    def view_inputs(self, width, height):
+        proj = cam.perspective_infinite_reverse_rh(self.fov, width / height, self.near)
+        world = cam.look_at(self.eye, self.target)
+        view = cam.make_view(world, proj, width, height)
+        return view, cam.make_previous_view(view), cam.make_lights(self.sun_illuminance, (1.0, 1.0, 1.0),
+                                                                   self.sun_direction_to_light)
+
+    def populate(self, world):
+        """Spawn everything into a plugin.World (host mirror) and prepare the GPU buffers."""
+        for t in self.textures:
+            world.add_texture(t["rgba"], t["address_mode_u"], t["address_mode_v"], t["filter_linear"], t["srgb"])
+        for m in self.meshes:
+            world.add_mesh(*m)
+        for m in self.materials:
+            world.add_material(m)
+        for me, ma, xf in zip(self.inst_mesh, self.inst_material, self.inst_transform):
+            world.add_instance(int(me), int(ma), xf)
+        world.prepare()
+        return world
+
+
+def _load_npz(name, texture_offset=0):
+    z = np.load(os.path.join(SCENES, name + ".npz"))
+    meshes = [(z[f"m{i}_pos"], z[f"m{i}_nrm"], z[f"m{i}_uv"], z[f"m{i}_idx"]) for i in range(int(z["mesh_count"]))]
+    n = len(z["mat_base_color"])
+    mats = np.zeros(n, L.MATERIAL)
+    mats["base_color"] = z["mat_base_color"]
+    mats["emissive"] = z["mat_emissive"]
+    mats["perceptual_roughness"] = z["mat_perceptual_roughness"]
+    mats["metallic"] = z["mat_metallic"]
+    mats["reflectance"] = z["mat_reflectance"]
+    tex = z["mat_textures"].astype(np.int64)
+    tex = np.where(tex == 0xFFFFFFFF, 0xFFFFFFFF, tex + texture_offset).astype(np.uint32)
+    for k, name_ in enumerate(("base_color_texture", "emissive_texture", "metallic_roughness_texture", "normal_map_texture",
+                               "occlusion_texture")):
+        mats[name_] = tex[:, k]
+    textures = []
+    for t in range(int(z["tex_count"])):
+        info = z[f"t{t}_info"]
+        textures.append({"rgba": z[f"t{t}_rgba"], "address_mode_u": int(info[0]), "address_mode_v": int(info[1]),
+                         "filter_linear": int(info[2]), "srgb": int(info[3])})
+    return meshes, mats, textures, z["inst_mesh"], z["inst_material"], z["inst_transform"]
+
+
+def cornell():
+    """examples/cornell.rs:37-61: cornell.glb, camera (0,1,4) -> (0,1,0), no directional light."""
+    meshes, mats, textures, im, imat, ixf = _load_npz("cornell")
+    return SceneData(meshes, mats, textures, list(im), list(imat), list(ixf), eye=(0.0, 1.0, 4.0), target=(0.0, 1.0, 0.0))
+
+
+def _translation(x, y, z, s=(1.0, 1.0, 1.0)):
+    m = np.zeros((4, 4), F)
+    m[0, 0], m[1, 1], m[2, 2], m[3, 3] = s[0], s[1], s[2], 1.0
+    m[3, :3] = (x, y, z)
+    return m.reshape(16)
+
+
+def _compose(parent16, child16):
+    a, b = parent16.reshape(4, 4).astype(np.float64), child16.reshape(4, 4).astype(np.float64)
+    return (b @ a).astype(F).reshape(16)
+
+
+def _plane_mesh(size=1.0):
+    """bevy shape::Plane { size }: 4 vertices, normal +Y."""
+    e = size / 2.0
+    pos = np.array([[e, 0, -e], [e, 0, e], [-e, 0, e], [-e, 0, -e]], F)
+    nrm = np.tile(np.array([[0, 1, 0]], F), (4, 1))
+    uv = np.array([[1, 0], [1, 1], [0, 1], [0, 0]], F)
+    idx = np.array([0, 2, 1, 0, 3, 2], np.uint32)
+    return pos, nrm, uv, idx
+
+
+def _uv_sphere_mesh(radius=0.5, sectors=36, stacks=18):
+    """bevy shape::UVSphere."""
+    pos, nrm, uv = [], [], []
+    for i in range(stacks + 1):
+        stack_angle = math.pi / 2 - i * math.pi / stacks
+        xy, z = radius * math.cos(stack_angle), radius * math.sin(stack_angle)
+        for j in range(sectors + 1):
+            a = j * 2 * math.pi / sectors
+            x, y = xy * math.cos(a), xy * math.sin(a)
+            pos.append((x, y, z)); nrm.append((x / radius, y / radius, z / radius)); uv.append((j / sectors, i / stacks))
+    idx = []
+    for i in range(stacks):
+        k1, k2 = i * (sectors + 1), (i + 1) * (sectors + 1)
+        for j in range(sectors):
+            if i != 0:
+                idx += [k1, k2, k1 + 1]
+            if i != stacks - 1:
+                idx += [k1 + 1, k2, k2 + 1]
+            k1 += 1; k2 += 1
+    return np.array(pos, F), np.array(nrm, F), np.array(uv, F), np.array(idx, np.uint32)
+
+
+def city():
+    """examples/city.rs:56-202 after all loads: ground plane x100, emissive sphere at (0,1,0), 12 Low-Poly houses,
+    sun 10 klx, camera (0,2.5,20) -> origin."""
+    meshes, mat_list, textures = [], [], []
+    inst_mesh, inst_mat, inst_xf = [], [], []
+
+    def std_material(base=(1, 1, 1, 1), emissive=(0, 0, 0, 1), rough=0.089, metallic=0.01, refl=0.5):
+        m = np.zeros((), L.MATERIAL)
+        m["base_color"], m["emissive"] = base, emissive
+        m["perceptual_roughness"], m["metallic"], m["reflectance"] = rough, metallic, refl
+        for k in ("base_color_texture", "emissive_texture", "metallic_roughness_texture", "normal_map_texture", "occlusion_texture"):
+            m[k] = 0xFFFFFFFF
+        return m
+
+    # ground (city.rs: plane size 1 scaled 100, base colour 0.5 grey, perceptual_roughness 0.5) and the emissive sphere
+    meshes.append(_plane_mesh(1.0)); mat_list.append(std_material(base=(0.5, 0.5, 0.5, 1.0), rough=0.5))
+    inst_mesh.append(0); inst_mat.append(0); inst_xf.append(_translation(0, 0, 0, (100.0, 1.0, 100.0)))
+    meshes.append(_uv_sphere_mesh(0.5, 36, 18)); mat_list.append(std_material(base=(1, 1, 1, 1), emissive=(1.0, 1.0, 1.0, 0.5)))
+    inst_mesh.append(1); inst_mat.append(1); inst_xf.append(_translation(0.0, 1.0, 0.0))
+
+    def add_house(name, positions):
+        hm, hmat, htex, him, himat, hixf = _load_npz(name, texture_offset=len(textures))
+        mesh0, mat0 = len(meshes), len(mat_list)
+        meshes.extend(hm); mat_list.extend(list(hmat)); textures.extend(htex)
+        for p in positions:
+            parent = _translation(*p)
+            for me, ma, xf in zip(him, himat, hixf):
+                inst_mesh.append(mesh0 + int(me)); inst_mat.append(mat0 + int(ma)); inst_xf.append(_compose(parent, xf))
+
+    add_house("house2", [(-12.0, 0.0, 0.0), (-4.0, 0.0, 0.0), (4.0, 0.0, 0.0), (12.0, 0.0, 0.0)])
+    add_house("house3", [(-12.0, 0.0, 8.0), (-4.0, 0.0, -8.0), (4.0, 0.0, 8.0), (12.0, 0.0, -8.0)])
+    add_house("house", [(-12.0, 0.0, -8.0), (-4.0, 0.0, 8.0), (4.0, 0.0, -8.0), (12.0, 0.0, 8.0)])
+    mats = np.array(mat_list, L.MATERIAL)
+    return SceneData(meshes, mats, textures, inst_mesh, inst_mat, inst_xf, eye=(0.0, 2.5, 20.0), target=(0.0, 0.0, 0.0),
+                     sun_illuminance=10000.0,
+                     sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 4.0, math.pi / 4.0, 0.0)))
+
+
+SCENE_BUILDERS = {"cornell": cornell, "city": city}
+
+# BASELINE.json configs.  All run with Upscale::SmaaTu4x{ratio 1.0}, Taa::None so that the render
+# resolution equals the stated resolution.
+CONFIGS = {
+    # configs[0]: cornell 256x256, 1 indirect bounce, denoise off
+    "cornell_256": dict(scene="cornell", width=256, height=256,
+                        settings=dict(indirect_bounces=1, denoise=0, temporal_reuse=1, emissive_spatial_reuse=0,
+                                      indirect_spatial_reuse=1)),
+    # configs[1]: cornell 1920x1080, 2 bounces, ReSTIR temporal + spatial (emissive and indirect) + denoise  <- bench default
+    "cornell_1080p": dict(scene="cornell", width=1920, height=1080,
+                          settings=dict(indirect_bounces=2, denoise=1, temporal_reuse=1, emissive_spatial_reuse=1,
+                                        indirect_spatial_reuse=1)),
+    # configs[3]: city 3840x2160, 2 bounces, indirect spatial + denoise, row bands over 4 GPUs
+    "city_4k": dict(scene="city", width=3840, height=2160,
+                    settings=dict(indirect_bounces=2, denoise=1, temporal_reuse=1, emissive_spatial_reuse=0,
+                                  indirect_spatial_reuse=1)),
+    # configs[4]: city 7680x4320, 4 bounces, full ReSTIR + denoise, 8 GPUs
+    "city_8k": dict(scene="city", width=7680, height=4320,
+                    settings=dict(indirect_bounces=4, denoise=1, temporal_reuse=1, emissive_spatial_reuse=1,
+                                  indirect_spatial_reuse=1)),
+}
+
+
+def config_settings(name, **extra):
+    from . import plugin
+    kw = dict(taa=plugin.TAA_NONE, upscale_kind=plugin.UPSCALE_SMAA_TU4X, upscale_ratio=1.0)
+    kw.update(CONFIGS[name]["settings"])
+    kw.update(extra)
+    return plugin.HikariSettings(**kw)

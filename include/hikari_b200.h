@@ -1,0 +1,160 @@
+/* hikari_b200.h — the C ABI of libhikari_b200.so: the drop-in boundary for bevy-hikari's per-frame GPU path.
+ *
+ * The reference has no FFI; its hot path sits behind three Bevy render-graph nodes that encode wgpu compute
+ * dispatches.  Each entry point below replaces one of those Rust call sites (file:line under /root/reference):
+ *
+ *   hk_context_create / _resize   prepare_light_textures + ReservoirCache        src/light.rs:307-383
+ *                                 prepass_textures_system                        src/prepass.rs:285-428
+ *                                 prepare_post_process_textures                  src/post_process.rs:635-747
+ *   hk_scene_upload               MeshRenderAssets/InstanceRenderAssets/MaterialRenderAssets::write_buffer
+ *                                 (the 9 storage buffers of bind group 2)        src/mesh_material/mod.rs:684-808
+ *                                 texture array of bind group 3                  src/mesh_material/mod.rs:760-799
+ *   hk_set_noise                  NoiseTextures::as_bind_group (bind group 4)    src/lib.rs:518-598
+ *   hk_prepass_run                PrepassNode::run                               src/prepass.rs:769-851
+ *   hk_light_run                  LightNode::run                                 src/light.rs:590-702
+ *   hk_post_process_run           PostProcessNode::run (denoise + tone mapping)  src/post_process.rs:1140-1234
+ *   hk_render_frame               the three nodes in graph order                 src/lib.rs:258-365
+ *   hk_get_output / hk_readback   the texture views later nodes bind             src/light.rs:297-304,
+ *                                                                                src/post_process.rs:622-633
+ *
+ * Conventions: plain C, plain pointers and sizes, no C++/torch types.  Every function returns HK_OK (0) or a
+ * negative HK_ERR_* and never throws or aborts; hk_last_error() gives the message.  Like the reference nodes
+ * (src/light.rs:606-617) a frame with missing inputs is skipped, but here that is reported as HK_ERR_NOT_READY
+ * instead of silently returning Ok.  One context = one GPU = one CUDA stream = one caller thread at a time.
+ * All work is stream-ordered and asynchronous until hk_sync()/hk_readback().  There is no CPU fallback:
+ * without a CUDA device hk_context_create fails.
+ */
+#ifndef HIKARI_B200_H
+#define HIKARI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#include "hk_layout.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HK_OK 0
+#define HK_ERR_INVALID_ARGUMENT (-1)
+#define HK_ERR_CUDA (-2)
+#define HK_ERR_NOT_READY (-3)     /* scene / noise not uploaded yet (reference: node returns Ok(()) and skips) */
+#define HK_ERR_OUT_OF_MEMORY (-4)
+#define HK_ERR_UNSUPPORTED (-5)
+
+typedef struct hk_context hk_context;
+
+/* One RGBA8 texture of the bindless array (src/mesh_material/material.rs:55-87). */
+typedef struct hk_texture_desc {
+    const uint8_t* rgba8;      /* width*height*4, row-major, already linearised the way the wgpu format would */
+    uint32_t width, height;
+    uint32_t address_mode_u;   /* 0 = repeat, 1 = clamp-to-edge, 2 = mirror-repeat */
+    uint32_t address_mode_v;
+    uint32_t filter_linear;    /* 0 = nearest, 1 = bilinear (mip level 0 only, light.wgsl:756) */
+    uint32_t srgb;             /* 1 = decode sRGB -> linear on fetch (Rgba8UnormSrgb) */
+} hk_texture_desc;
+
+/* The nine storage buffers of src/shaders/mesh_material_bindings.wgsl:5-22, host pointers, copied before return. */
+typedef struct hk_scene_desc {
+    const hk_vertex* vertices;           uint32_t vertex_count;
+    const hk_primitive* primitives;      uint32_t primitive_count;
+    const hk_node* asset_nodes;          uint32_t asset_node_count;      /* Nodes.count (mesh.rs:56) */
+    const hk_alias_entry* alias_table;   uint32_t alias_count;
+    const hk_instance* instances;        uint32_t instance_count;
+    const hk_node* instance_nodes;       uint32_t instance_node_count;   /* Nodes.count (instance.rs:94) */
+    const hk_material* materials;        uint32_t material_count;
+    const hk_node* emissive_nodes;       uint32_t emissive_node_count;   /* Nodes.count (instance.rs:97) */
+    const hk_emissive* emissives;        uint32_t emissive_count;
+    const hk_texture_desc* textures;     uint32_t texture_count;         /* 0 => NO_TEXTURE variant (light.rs:141-143) */
+} hk_scene_desc;
+
+/* What bind group 0 carries each frame (src/prepass.rs:81-125, src/light.rs:630-639) + the settings that pick passes. */
+typedef struct hk_frame_inputs {
+    hk_frame_uniform frame;          /* FrameUniform::extract_component, src/view.rs:141-193 */
+    hk_view view;
+    hk_previous_view previous_view;
+    hk_lights lights;
+    uint32_t denoise;                /* HikariSettings::denoise (src/lib.rs:428) */
+    uint32_t taa_jitter;             /* 1 = TEMPORAL_ANTI_ALIASING jitter in the prepass (prepass.wgsl:52-54) */
+    uint32_t smaa_tu4x;              /* 1 = SMAA_TU4X jitter index rule (prepass.wgsl:31-35) */
+    uint32_t _pad;
+} hk_frame_inputs;
+
+/* Identifiers for hk_get_output / hk_readback / hk_upload_state.  Read-back formats are the reference's texture /
+ * buffer formats (src/prepass.rs:43-47, src/light.rs:29-31,51-60, src/post_process.rs:29), row-major, tightly packed,
+ * rows [row_begin,row_end) of the context's band. */
+enum {
+    HK_OUT_TONE_MAPPED = 0,      /* Rgba16Float, 8 B/px   post_process.rs:974-981 */
+    HK_OUT_RENDER_DIRECT = 1,    /* Rgba16Float           light.rs:372 render[0] */
+    HK_OUT_RENDER_EMISSIVE = 2,
+    HK_OUT_RENDER_INDIRECT = 3,
+    HK_OUT_VARIANCE_DIRECT = 4,  /* R32Float              light.rs:371 variance[0] */
+    HK_OUT_VARIANCE_EMISSIVE = 5,
+    HK_OUT_VARIANCE_INDIRECT = 6,
+    HK_OUT_ALBEDO = 7,           /* Rgba16Float           light.rs:373 */
+    HK_OUT_DENOISED_DIRECT = 8,  /* Rgba16Float           post_process.rs:714 denoise_render[0] */
+    HK_OUT_DENOISED_EMISSIVE = 9,
+    HK_OUT_DENOISED_INDIRECT = 10,
+    HK_OUT_GBUFFER_POSITION = 16,           /* Rgba32Float 16 B/px */
+    HK_OUT_GBUFFER_NORMAL = 17,             /* Rgba8Snorm   4 B/px */
+    HK_OUT_GBUFFER_DEPTH_GRADIENT = 18,     /* Rg32Float    8 B/px */
+    HK_OUT_GBUFFER_INSTANCE_MATERIAL = 19,  /* Rg32Float    8 B/px (id + 0.5) */
+    HK_OUT_GBUFFER_VELOCITY_UV = 20,        /* Rgba32Float 16 B/px */
+    HK_OUT_RESERVOIR_0 = 32      /* .. HK_OUT_RESERVOIR_0+9 : PackedReservoir 64 B/px, buffer index as in light.rs:518 */
+};
+
+/* Per-frame counters and timings (rays = traverse_top calls + stand-alone traverse_bottom calls). */
+typedef struct hk_frame_stats {
+    uint64_t primary_rays;       /* G-buffer rays (the reference rasterises these) */
+    uint64_t tlas_rays;          /* traverse_top calls of the light passes (light.wgsl:442) */
+    uint64_t blas_rays;          /* stand-alone traverse_bottom calls (light.wgsl:687) */
+    float ms_prepass, ms_light, ms_post_process, ms_total;   /* CUDA-event times of the last frame, if enabled */
+    uint32_t kernel_launches;    /* kernels launched by the last hk_render_frame */
+    uint32_t _pad;
+} hk_frame_stats;
+
+typedef struct hk_ray {   /* test hook input: a world-space ray exactly as traverse_top takes it */
+    float origin[3];    float max_distance;
+    float direction[3]; float early_distance;
+    uint32_t exclude_instance; uint32_t _pad[3];
+} hk_ray;
+typedef struct hk_hit {   /* light.wgsl:270-279 */
+    float u, v, distance;
+    uint32_t instance_index, primitive_index;
+} hk_hit;
+
+/* width x height = the camera target (HikariSettings upscale ratio 1: render size == target size).
+ * [row_begin,row_end) = the band of rows this context owns (whole frame: 0,height).  The context renders the band
+ * plus the ghost rows it needs so that owned rows are bit-identical to an unsharded render.
+ * cuda_stream: a cudaStream_t to run on, or NULL to let the context create its own. */
+int hk_context_create(hk_context** out, int cuda_device, uint32_t width, uint32_t height,
+                      uint32_t row_begin, uint32_t row_end, void* cuda_stream);
+void hk_context_destroy(hk_context* ctx);
+int hk_context_resize(hk_context* ctx, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end);
+int hk_reset_temporal_state(hk_context* ctx);   /* zero reservoirs, as re-allocation does in light.rs:342-363 */
+
+int hk_scene_upload(hk_context* ctx, const hk_scene_desc* scene);
+int hk_set_noise(hk_context* ctx, const uint8_t* rgba8_64x64x16);   /* 16 textures of 64x64 RGBA8, lib.rs:189-219 */
+
+int hk_prepass_run(hk_context* ctx, const hk_frame_inputs* in);
+int hk_light_run(hk_context* ctx, const hk_frame_inputs* in);
+int hk_post_process_run(hk_context* ctx, const hk_frame_inputs* in);
+int hk_render_frame(hk_context* ctx, const hk_frame_inputs* in);     /* prepass -> light -> post process */
+
+int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes);  /* HK_OUT_TONE_MAPPED only: owned rows */
+int hk_readback(hk_context* ctx, int which, void* host, size_t bytes);            /* synchronises */
+int hk_upload_state(hk_context* ctx, int which, const void* host, size_t bytes);  /* inverse of hk_readback (tests) */
+int hk_sync(hk_context* ctx);
+
+int hk_trace_rays(hk_context* ctx, const hk_ray* rays, size_t n, hk_hit* hits);   /* F3/F4 parity hook */
+int hk_set_profiling(hk_context* ctx, int count_rays, int time_passes);
+int hk_set_keep_intermediates(hk_context* ctx, int keep);   /* 1: hk_render_frame also writes HK_OUT_DENOISED_* */
+int hk_get_stats(hk_context* ctx, hk_frame_stats* out);
+int hk_band_rows(hk_context* ctx, uint32_t* alloc_row_begin, uint32_t* alloc_row_end); /* owned rows +- ghost rows */
+
+const char* hk_last_error(hk_context* ctx);    /* ctx may be NULL: error of the last failed hk_context_create */
+const char* hk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,72 @@
+/* hikari_host.h — C view of the host mirror (bevy_hikari_b200/host/hikari.hpp) for ctypes / other-language callers.
+ * Everything here sits ABOVE the drop-in boundary (include/hikari_b200.h): it restates, in C++, the Rust host code
+ * of the reference for this path (settings -> uniform, mesh/instance/material preparation, node order) because no
+ * Rust toolchain exists in this image.  A real Bevy host would keep its own Rust versions of these and bind only
+ * hikari_b200.h. */
+#ifndef HIKARI_HOST_H
+#define HIKARI_HOST_H
+#include "hikari_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { HIKARI_TAA_JASMINE = 0, HIKARI_TAA_NONE = 1 };              /* src/lib.rs:466-471 */
+enum { HIKARI_UPSCALE_FSR1 = 0, HIKARI_UPSCALE_SMAA_TU4X = 1 };    /* src/lib.rs:473-487 */
+
+typedef struct hikari_settings {   /* HikariSettings, src/lib.rs:399-433, same field names */
+    uint32_t direct_validate_interval;
+    uint32_t emissive_validate_interval;
+    uint32_t max_temporal_reuse_count;
+    uint32_t max_spatial_reuse_count;
+    float max_reservoir_lifetime;
+    float solar_angle;
+    uint32_t indirect_bounces;
+    float max_indirect_luminance;
+    float clear_color[4];
+    uint32_t temporal_reuse;
+    uint32_t emissive_spatial_reuse;
+    uint32_t indirect_spatial_reuse;
+    uint32_t denoise;
+    uint32_t taa;
+    uint32_t upscale_kind;
+    float upscale_ratio;
+    float upscale_sharpness;
+} hikari_settings;
+
+typedef struct hikari_world hikari_world;     /* MeshMaterialPlugin's render-world resources */
+typedef struct hikari_plugin hikari_plugin;   /* HikariPlugin + one camera */
+
+void hikari_settings_default(hikari_settings* out);                       /* HikariSettings::default(), lib.rs:435-455 */
+float hikari_upscale_ratio(const hikari_settings* s);                     /* Upscale::ratio(), lib.rs:501-505 */
+void hikari_make_frame_inputs(const hikari_settings* s, uint64_t frame_counter, const hk_view* view,
+                              const hk_previous_view* previous_view, const hk_lights* lights, hk_frame_inputs* out);
+const char* hikari_graph_name(void);                                      /* graph::NAME, lib.rs:44 */
+
+hikari_world* hikari_world_create(void);
+void hikari_world_destroy(hikari_world* w);
+/* topology: 0 = TriangleList, 1 = TriangleStrip, 2 = anything else.  NULL attribute => PrepareMeshError (mod.rs:301-308). */
+uint32_t hikari_world_add_mesh(hikari_world* w, const float* positions, const float* normals, const float* uvs,
+                               uint32_t vertex_count, const uint32_t* indices, uint32_t index_count, uint32_t topology);
+uint32_t hikari_world_add_material(hikari_world* w, const hk_material* m);
+uint32_t hikari_world_add_texture(hikari_world* w, const hk_texture_desc* t);
+uint32_t hikari_world_add_instance(hikari_world* w, uint32_t mesh, uint32_t material, const float* transform16, uint32_t visible);
+void hikari_world_prepare(hikari_world* w);                               /* prepare_mesh_assets -> materials -> instances */
+void hikari_world_scene_desc(hikari_world* w, hk_scene_desc* out);        /* pointers valid until the next prepare */
+int hikari_world_mesh_error(hikari_world* w, uint32_t mesh);              /* PrepareMeshError as int, 0 = ok */
+
+hikari_plugin* hikari_plugin_create(void);
+void hikari_plugin_destroy(hikari_plugin* p);
+int hikari_plugin_build(hikari_plugin* p, int cuda_device, uint32_t width, uint32_t height, uint32_t row_begin,
+                        uint32_t row_end, const uint8_t* noise_rgba8_64x64x16, void* cuda_stream);
+int hikari_plugin_upload_scene(hikari_plugin* p, hikari_world* w);
+int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk_view* view,
+                            const hk_previous_view* previous_view, const hk_lights* lights);
+hk_context* hikari_plugin_context(hikari_plugin* p);
+uint64_t hikari_plugin_frame_counter(hikari_plugin* p);
+void hikari_plugin_set_frame_counter(hikari_plugin* p, uint64_t v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1553 @@
+// ORACLE — test infrastructure, not product code.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may build, load or call this file.  The product (libhikari_b200.so) never does.
+//
+// CPU restatement (C++17 + OpenMP) of the reference's per-frame GPU path, pass by pass, texture format by texture
+// format, exactly as LightNode::run (src/light.rs:590-702) and PostProcessNode::run (src/post_process.rs:1140-1234)
+// dispatch it.  Every function cites the WGSL it follows (paths relative to /root/reference/src/shaders).
+//
+// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path and
+// cannot be built here (no rustc / wgpu / Vulkan), so this restatement is anchored on the WGSL source alone.
+// Deviations that are forced and documented:
+//   * the G-buffer is ray-cast (hko_prepass) instead of rasterised (prepass.wgsl:40-100) — same five planes, same
+//     formats, oracle-defined coverage;
+//   * implementation-defined WGSL arithmetic (FMA contraction, sin/cos/exp/pow accuracy, NaN in min/max/clamp/pack)
+//     is fixed by include/hk_math.h;
+//   * the racy scatter store_previous_spatial_reservoir(previous_coords) (light.wgsl:1094,1201,1458) is resolved
+//     in raster order, last writer wins.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "hikari_b200.h"
+#include "hk_math.h"
+
+using namespace hk;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ state
+struct Texture {
+    std::vector<vec4> texels;  // decoded (sRGB -> linear already applied per texel)
+    uint32_t w = 0, h = 0, mode_u = 0, mode_v = 0, linear = 1;
+};
+
+struct Sample {  // light.wgsl:49-57
+    vec4 radiance = v4(0.0f);
+    vec4 random = v4(0.0f);
+    vec4 visible_position = v4(0.0f);
+    vec3 visible_normal = v3(0.0f);
+    uint32_t visible_instance = 0;
+    vec4 sample_position = v4(0.0f);
+    vec3 sample_normal = v3(0.0f);
+};
+struct Reservoir {  // light.wgsl:59-66
+    Sample s;
+    float count = 0, lifetime = 0, w = 0, w_sum = 0, w2_sum = 0;
+};
+struct Ray { vec3 origin, direction, inv_direction; };
+struct Aabb { vec3 min, max; };
+struct Intersection { vec2 uv = v2(0, 0); float distance = 0; };
+struct Hit { Intersection intersection; uint32_t instance_index = 0, primitive_index = 0; };
+struct Surface { vec4 base_color, emissive; float reflectance, metallic, roughness, occlusion; };
+struct HitInfo {
+    vec4 position = v4(0.0f);
+    vec3 normal = v3(0.0f);
+    vec2 uv = v2(0, 0);
+    uint32_t instance_index = 0, material_index = 0;
+};
+struct LightCandidate {
+    vec3 direction = v3(0.0f);
+    float max_distance = 0, min_distance = 0;
+    uint32_t emissive_instance = 0;
+    float p = 0;
+};
+
+struct ScatterWrite { int32_t index; hk_packed_reservoir value; };
+
+}  // namespace
+
+struct hko_context {
+    int W = 0, H = 0;  // full (deferred) size; render size == full size at upscale ratio 1
+    int RW = 0, RH = 0;
+    // scene (bind group 2)
+    std::vector<hk_vertex> vertices;
+    std::vector<hk_primitive> primitives;
+    std::vector<hk_node> asset_nodes;
+    std::vector<hk_alias_entry> alias_table;
+    std::vector<hk_instance> instances;
+    std::vector<hk_node> instance_nodes;
+    std::vector<hk_material> materials;
+    std::vector<hk_node> emissive_nodes;
+    std::vector<hk_emissive> emissives;
+    std::vector<Texture> textures;
+    bool scene_ready = false, noise_ready = false;
+    std::vector<uint8_t> noise;  // 16 x 64 x 64 x 4
+    // G-buffer (bind group 1), reference formats
+    std::vector<vec4> position;            // Rgba32Float
+    std::vector<uint32_t> normal;          // Rgba8Snorm
+    std::vector<vec2> depth_gradient;      // Rg32Float
+    std::vector<vec2> instance_material;   // Rg32Float
+    std::vector<vec4> velocity_uv;         // Rgba32Float
+    // light textures (bind group 5) and reservoirs (bind group 6)
+    std::vector<uvec2> albedo;             // Rgba16Float, full size
+    std::vector<uvec2> render[3];          // Rgba16Float
+    std::vector<float> variance[3];        // R32Float
+    std::vector<hk_packed_reservoir> reservoir[10];
+    // post process
+    std::vector<uvec2> denoise_internal[4];
+    std::vector<float> denoise_internal_variance;
+    std::vector<uvec2> denoise_render[3];
+    std::vector<uvec2> tone_mapping_output;
+    // per-frame
+    hk_frame_inputs in;
+    std::atomic<uint64_t> primary_rays{0}, tlas_rays{0}, blas_rays{0};
+    std::string error;
+    int threads = 0;
+};
+
+namespace {
+
+using Ctx = hko_context;
+
+inline vec3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+inline vec4 ld4(const float* p) { return v4(p[0], p[1], p[2], p[3]); }
+inline mat4 ldm(const float* p) { mat4 m; for (int c = 0; c < 4; ++c) m.c[c] = ld4(p + 4 * c); return m; }
+
+inline vec2 coords_to_uv(ivec2 coords, ivec2 size) {  // utils.wgsl:37-39
+    return (v2((float)coords.x, (float)coords.y) + 0.5f) / v2((float)size.x, (float)size.y);
+}
+inline vec2 clip_to_uv(vec4 clip) {  // utils.wgsl:30-35
+    vec2 uv = v2(clip.x, clip.y) / clip.w;
+    uv = (uv + 1.0f) * 0.5f;
+    uv.y = 1.0f - uv.y;
+    return uv;
+}
+
+// ------------------------------------------------------------------------------------------- reservoirs
+Reservoir unpack_reservoir(const hk_packed_reservoir& packed) {  // light.wgsl:77-109
+    Reservoir r;
+    vec2 t0 = unpack2x16float(packed.reservoir[0]);
+    vec2 t1 = unpack2x16float(packed.reservoir[1]);
+    r.count = t0.x; r.w = t0.y; r.w_sum = t1.x; r.w2_sum = t1.y;
+    t0 = unpack2x16float(packed.radiance[0]);
+    t1 = unpack2x16float(packed.radiance[1]);
+    r.s.radiance = v4(t0.x, t0.y, t1.x, t1.y);
+    t0 = unpack2x16unorm(packed.random[0]);
+    t1 = unpack2x16unorm(packed.random[1]);
+    r.s.random = v4(t0.x, t0.y, t1.x, t1.y);
+    vec4 t2 = unpack4x8snorm(packed.visible_normal);
+    r.s.visible_position = ld4(packed.visible_position);
+    r.s.visible_normal = normalize(xyz(t2));
+    r.lifetime = 127.0f * (1.0f + t2.w);
+    t2 = unpack4x8snorm(packed.sample_normal);
+    r.s.sample_position = v4(packed.sample_position[0], packed.sample_position[1], packed.sample_position[2], t2.w);
+    r.s.sample_normal = normalize(xyz(t2));
+    r.s.visible_instance = f32_to_u32(packed.sample_position[3]);
+    return r;
+}
+hk_packed_reservoir pack_reservoir(const Reservoir& r) {  // light.wgsl:111-136
+    hk_packed_reservoir p;
+    p.reservoir[0] = pack2x16float(r.count, r.w);
+    p.reservoir[1] = pack2x16float(r.w_sum, r.w2_sum);
+    p.radiance[0] = pack2x16float(r.s.radiance.x, r.s.radiance.y);
+    p.radiance[1] = pack2x16float(r.s.radiance.z, r.s.radiance.w);
+    p.random[0] = pack2x16unorm(r.s.random.x, r.s.random.y);
+    p.random[1] = pack2x16unorm(r.s.random.z, r.s.random.w);
+    p.visible_position[0] = r.s.visible_position.x; p.visible_position[1] = r.s.visible_position.y;
+    p.visible_position[2] = r.s.visible_position.z; p.visible_position[3] = r.s.visible_position.w;
+    p.sample_position[0] = r.s.sample_position.x; p.sample_position[1] = r.s.sample_position.y;
+    p.sample_position[2] = r.s.sample_position.z; p.sample_position[3] = (float)r.s.visible_instance;
+    p.visible_normal = pack4x8snorm(v4(r.s.visible_normal, r.lifetime / 127.0f - 1.0f));
+    p.sample_normal = pack4x8snorm(v4(r.s.sample_normal, r.s.sample_position.w));
+    return p;
+}
+void set_reservoir(Reservoir& r, const Sample& s, float w_new) {  // light.wgsl:138-144
+    r.count = 1.0f; r.lifetime = 0.0f; r.w_sum = w_new; r.w2_sum = w_new * w_new; r.s = s;
+}
+void update_reservoir(Reservoir& r, const Sample& s, float w_new) {  // light.wgsl:146-173
+    r.w_sum += w_new;
+    r.w2_sum += w_new * w_new;
+    r.count = r.count + 1.0f;
+    float rand = fract(sum4(s.random));
+    if (rand < w_new / r.w_sum) r.s = s;
+}
+void merge_reservoir(Reservoir& r, const Reservoir& other, float p) {  // light.wgsl:175-179
+    float count = r.count;
+    update_reservoir(r, other.s, p * other.w * other.count);
+    r.count = count + other.count;
+}
+inline bool uv_inside(vec2 uv) { return fabsf(uv.x - 0.5f) < 0.5f && fabsf(uv.y - 0.5f) < 0.5f; }     // all(abs(uv-0.5) < 0.5)
+inline bool uv_inside_eq(vec2 uv) { return fabsf(uv.x - 0.5f) <= 0.5f && fabsf(uv.y - 0.5f) <= 0.5f; }  // <=
+inline int32_t uv_to_index(vec2 uv, ivec2 size) {
+    ivec2 c; c.x = f32_to_i32(uv.x * (float)size.x); c.y = f32_to_i32(uv.y * (float)size.y);
+    return c.x + size.x * c.y;
+}
+Reservoir load_previous(const std::vector<hk_packed_reservoir>& buf, vec2 uv, ivec2 size) {  // light.wgsl:181-190,201-210
+    Reservoir r;
+    if (uv_inside(uv)) r = unpack_reservoir(buf[uv_to_index(uv, size)]);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------- tracing
+inline vec3 instance_position_world_to_local(const hk_instance& inst, vec3 p) {  // light.wgsl:306-310
+    vec4 q = mul_transposed(ldm(inst.inverse_transpose_model), v4(p, 1.0f));
+    return xyz(q) / q.w;
+}
+inline vec3 instance_direction_world_to_local(const hk_instance& inst, vec3 p) {  // light.wgsl:312-316
+    return xyz(mul_transposed(ldm(inst.inverse_transpose_model), v4(p, 0.0f)));
+}
+inline vec3 instance_position_local_to_world(const hk_instance& inst, vec3 p) {  // light.wgsl:318-322
+    vec4 q = mul(ldm(inst.model), v4(p, 1.0f));
+    return xyz(q) / q.w;
+}
+inline vec3 instance_normal_local_to_world(const hk_instance& inst, vec3 n) {  // light.wgsl:324-338
+    mat3 m;
+    m.c[0] = ld3(inst.inverse_transpose_model + 0);
+    m.c[1] = ld3(inst.inverse_transpose_model + 4);
+    m.c[2] = ld3(inst.inverse_transpose_model + 8);
+    return normalize(mul(m, n));
+}
+inline bool inside_aabb(vec3 p, const Aabb& a) {  // light.wgsl:340-342
+    return p.x > a.min.x && p.y > a.min.y && p.z > a.min.z && p.x < a.max.x && p.y < a.max.y && p.z < a.max.z;
+}
+inline float intersects_aabb(const Ray& ray, const Aabb& aabb) {  // light.wgsl:344-362
+    vec3 t1 = (aabb.min - ray.origin) * ray.inv_direction;
+    vec3 t2 = (aabb.max - ray.origin) * ray.inv_direction;
+    float t_min = fmin_(t1.x, t2.x);
+    float t_max = fmax_(t1.x, t2.x);
+    t_min = fmax_(t_min, fmin_(t1.y, t2.y));
+    t_max = fmin_(t_max, fmax_(t1.y, t2.y));
+    t_min = fmax_(t_min, fmin_(t1.z, t2.z));
+    t_max = fmin_(t_max, fmax_(t1.z, t2.z));
+    float t = F32_MAX;
+    if (t_max >= t_min && t_max >= 0.0f) t = t_min;
+    return t;
+}
+inline Intersection intersects_triangle(const Ray& ray, const hk_primitive& tri) {  // light.wgsl:364-398
+    Intersection result;
+    result.distance = F32_MAX;
+    vec3 p0 = ld3(tri.vertices[0].position), p1 = ld3(tri.vertices[1].position), p2 = ld3(tri.vertices[2].position);
+    vec3 ab = p1 - p0;
+    vec3 ac = p2 - p0;
+    vec3 u_vec = cross(ray.direction, ac);
+    float det = dot(ab, u_vec);
+    if (fabsf(det) < F32_EPSILON) return result;
+    float inv_det = 1.0f / det;
+    vec3 ao = ray.origin - p0;
+    float u = dot(ao, u_vec) * inv_det;
+    if (u < 0.0f || u > 1.0f) { result.uv = v2(u, 0.0f); return result; }
+    vec3 v_vec = cross(ao, ab);
+    float v = dot(ray.direction, v_vec) * inv_det;
+    result.uv = v2(u, v);
+    if (v < 0.0f || u + v > 1.0f) return result;
+    float distance = dot(ac, v_vec) * inv_det;
+    if (distance > F32_EPSILON) result.distance = distance;
+    return result;
+}
+bool traverse_bottom(const Ctx& c, Hit& hit, const Ray& ray, const hk_mesh_index& mesh, float early_distance) {  // light.wgsl:400-440
+    bool intersected = false;
+    uint32_t index = 0;
+    for (; index < mesh.node_count;) {
+        uint32_t node_index = mesh.node_offset + index;
+        const hk_node& node = c.asset_nodes[node_index];
+        Aabb aabb;
+        if (node.entry_index >= BVH_LEAF_FLAG) {
+            uint32_t primitive_index = mesh.primitive + node.entry_index - BVH_LEAF_FLAG;
+            const hk_primitive& prim = c.primitives[primitive_index];
+            vec3 p0 = ld3(prim.vertices[0].position), p1 = ld3(prim.vertices[1].position), p2 = ld3(prim.vertices[2].position);
+            aabb.min = vmin(p0, vmin(p1, p2));
+            aabb.max = vmax(p0, vmax(p1, p2));
+            if (intersects_aabb(ray, aabb) < hit.intersection.distance) {
+                Intersection intersection = intersects_triangle(ray, prim);
+                if (intersection.distance < hit.intersection.distance) {
+                    hit.intersection = intersection;
+                    hit.primitive_index = primitive_index;
+                    intersected = true;
+                    if (intersection.distance < early_distance) return intersected;
+                }
+            }
+            index = node.exit_index;
+        } else {
+            aabb.min = ld3(node.min);
+            aabb.max = ld3(node.max);
+            index = (intersects_aabb(ray, aabb) < hit.intersection.distance) ? node.entry_index : node.exit_index;
+        }
+    }
+    return intersected;
+}
+Hit traverse_top(const Ctx& c, const Ray& ray, float max_distance, float early_distance, uint32_t exclude_instance) {  // light.wgsl:442-486
+    Hit hit;
+    hit.intersection.distance = max_distance;
+    hit.instance_index = U32_MAX;
+    hit.primitive_index = U32_MAX;
+    uint32_t index = 0;
+    const uint32_t count = (uint32_t)c.instance_nodes.size();
+    for (; index < count;) {
+        const hk_node& node = c.instance_nodes[index];
+        Aabb aabb;
+        if (node.entry_index >= BVH_LEAF_FLAG) {
+            uint32_t instance_index = node.entry_index - BVH_LEAF_FLAG;
+            const hk_instance& instance = c.instances[instance_index];
+            aabb.min = ld3(instance.min);
+            aabb.max = ld3(instance.max);
+            if (instance_index != exclude_instance && intersects_aabb(ray, aabb) < hit.intersection.distance) {
+                Ray r;
+                r.origin = instance_position_world_to_local(instance, ray.origin);
+                r.direction = instance_direction_world_to_local(instance, ray.direction);
+                r.inv_direction = 1.0f / r.direction;
+                if (traverse_bottom(c, hit, r, instance.mesh, early_distance)) {
+                    hit.instance_index = instance_index;
+                    if (hit.intersection.distance < early_distance) return hit;
+                }
+            }
+            index = node.exit_index;
+        } else {
+            aabb.min = ld3(node.min);
+            aabb.max = ld3(node.max);
+            index = (intersects_aabb(ray, aabb) < hit.intersection.distance) ? node.entry_index : node.exit_index;
+        }
+    }
+    return hit;
+}
+HitInfo empty_hit_info(vec3 position, vec3 direction) {  // light.wgsl:488-494
+    HitInfo info;
+    info.instance_index = U32_MAX;
+    info.material_index = U32_MAX;
+    info.position = v4(position + direction * DISTANCE_MAX, 0.0f);
+    return info;
+}
+HitInfo hit_info(const Ctx& c, const Ray& ray, const Hit& hit) {  // light.wgsl:496-523
+    HitInfo info;
+    info.instance_index = hit.instance_index;
+    info.material_index = U32_MAX;
+    if (hit.instance_index != U32_MAX) {
+        const hk_instance& instance = c.instances[hit.instance_index];
+        const hk_primitive& prim = c.primitives[hit.primitive_index];
+        const hk_vertex& a = c.vertices[instance.mesh.vertex + prim.vertices[0].index];
+        const hk_vertex& b = c.vertices[instance.mesh.vertex + prim.vertices[1].index];
+        const hk_vertex& d = c.vertices[instance.mesh.vertex + prim.vertices[2].index];
+        vec2 uv0 = v2(a.u, a.v), uv1 = v2(b.u, b.v), uv2 = v2(d.u, d.v);
+        vec2 uv = hit.intersection.uv;
+        info.uv = uv0 + uv.x * (uv1 - uv0) + uv.y * (uv2 - uv0);
+        vec3 n0 = ld3(a.normal), n1 = ld3(b.normal), n2 = ld3(d.normal);
+        info.normal = n0 + uv.x * (n1 - n0) + uv.y * (n2 - n0);
+        info.normal = instance_normal_local_to_world(instance, info.normal);
+        info.position = v4(ray.origin + ray.direction * hit.intersection.distance, 1.0f);
+        info.material_index = instance.material;
+    } else {
+        info.position = v4(ray.origin + ray.direction * DISTANCE_MAX, 0.0f);
+    }
+    return info;
+}
+void occlude_hit_info(const Ray& ray, const Hit& hit, HitInfo& info) {  // light.wgsl:526-533
+    if (hit.instance_index != U32_MAX) {
+        info.instance_index = hit.instance_index;
+        info.material_index = U32_MAX;
+        info.position = v4(ray.origin + ray.direction * hit.intersection.distance, 1.0f);
+        info.normal = v3(0.0f);
+    }
+}
+
+// --------------------------------------------------------------------------------------------- sampling
+inline vec2 sample_uniform_disk(vec2 rand) {  // light.wgsl:537-541
+    float r = sqrtf(rand.x);
+    float theta = 2.0f * PI * rand.y;
+    float s, c; sincos_(theta, &s, &c);
+    return v2(r * c, r * s);
+}
+inline vec4 sample_cosine_hemisphere(vec2 rand) {  // light.wgsl:544-549
+    vec2 t = sample_uniform_disk(rand);
+    vec3 direction = v3(t.x, t.y, sqrtf(1.0f - dot(t, t)));
+    float pdf = 2.0f * INV_TAU * direction.z;
+    return v4(direction, pdf);
+}
+inline vec4 sample_uniform_cone(vec2 rand, float cos_angle) {  // light.wgsl:552-559
+    float z = 1.0f - (1.0f - cos_angle) * rand.x;
+    float theta = TAU * rand.y;
+    float r = sqrtf(1.0f - z * z);
+    float s, c; sincos_(theta, &s, &c);
+    vec3 direction = v3(r * c, r * s, z);
+    float pdf = INV_TAU / (1.0f - cos_angle);
+    return v4(direction, pdf);
+}
+inline vec2 sample_uniform_triangle_barycentric(vec2 rand) {  // light.wgsl:562-565
+    float srx = sqrtf(rand.x);
+    return v2(1.0f - srx, rand.y * srx);
+}
+inline vec4 compute_directional_cone(const Ctx& c) {  // light.wgsl:571-573
+    float s, co; sincos_(c.in.frame.solar_angle, &s, &co);
+    return v4(ld3(c.in.lights.direction_to_light), co);
+}
+inline vec3 compute_emissive_radiance(vec4 emissive) {  // light.wgsl:594-596
+    return 255.0f * emissive.w * xyz(emissive);
+}
+
+LightCandidate select_light_candidate(Ctx& c, vec4 rand, vec3 position, vec3 normal, uint32_t instance, HitInfo& info) {  // light.wgsl:599-708
+    LightCandidate candidate;
+    candidate.max_distance = F32_MAX;
+    candidate.min_distance = DISTANCE_MAX;
+    candidate.emissive_instance = DONT_SAMPLE_EMISSIVE;
+
+    vec4 cone = compute_directional_cone(c);
+    vec3 rand_direction = mul(normal_basis(xyz(cone)), xyz(sample_uniform_cone(v2(rand.z, rand.w), cone.w)));
+    candidate.direction = rand_direction;
+    candidate.p = 1.0f;
+    info = empty_hit_info(position, rand_direction);
+    if (instance == DONT_SAMPLE_EMISSIVE) return candidate;
+
+    hk_emissive emissive;
+    memset(&emissive, 0, sizeof(emissive));
+    float count = 0.0f;
+    uint32_t index = 0;
+    float rand_1d = rand.x;
+    const uint32_t ncount = (uint32_t)c.emissive_nodes.size();
+    for (; index < ncount;) {
+        const hk_node& node = c.emissive_nodes[index];
+        Aabb aabb;
+        if (node.entry_index >= BVH_LEAF_FLAG) {
+            uint32_t emissive_index = node.entry_index - BVH_LEAF_FLAG;
+            const hk_emissive& cur = c.emissives[emissive_index];
+            aabb.min = ld3(cur.position) - cur.radius;
+            aabb.max = ld3(cur.position) + cur.radius;
+            if (instance != cur.instance && inside_aabb(position, aabb)) {
+                rand_1d = fract(rand_1d + GOLDEN_RATIO);
+                count += 1.0f;
+                if (rand_1d < 1.0f / count) {
+                    candidate.emissive_instance = cur.instance;
+                    emissive = cur;
+                }
+            }
+            index = node.exit_index;
+        } else {
+            aabb.min = ld3(node.min);
+            aabb.max = ld3(node.max);
+            index = inside_aabb(position, aabb) ? node.entry_index : node.exit_index;
+        }
+    }
+
+    if (candidate.emissive_instance != DONT_SAMPLE_EMISSIVE) {
+        uint32_t alias_index = std::min(f32_to_u32(rand.x * (float)emissive.alias_table_count), emissive.alias_table_count - 1u);
+        const hk_alias_entry& alias_entry = c.alias_table[emissive.alias_table_offset + alias_index];
+        uint32_t primitive_index = (rand.y < alias_entry.prob) ? alias_entry.index : alias_index;
+
+        const hk_instance& emissive_instance = c.instances[candidate.emissive_instance];
+        const hk_primitive& prim = c.primitives[emissive_instance.mesh.primitive + primitive_index];
+        vec2 b = sample_uniform_triangle_barycentric(v2(rand.z, rand.w));
+        vec3 lp = b.x * ld3(prim.vertices[0].position) + b.y * ld3(prim.vertices[1].position) +
+                  (1.0f - b.x - b.y) * ld3(prim.vertices[2].position);
+        vec3 p = instance_position_local_to_world(emissive_instance, lp);
+
+        Hit hit;
+        hit.intersection.distance = F32_MAX;
+        hit.instance_index = U32_MAX;
+        hit.primitive_index = U32_MAX;
+
+        Ray ray;
+        ray.origin = position + normal * RAY_BIAS;
+        ray.direction = normalize(p - position);
+        ray.inv_direction = v3(0.0f);
+
+        Ray r;
+        r.origin = instance_position_world_to_local(emissive_instance, ray.origin);
+        r.direction = instance_direction_world_to_local(emissive_instance, ray.direction);
+        r.inv_direction = 1.0f / r.direction;
+
+        candidate.direction = ray.direction;
+        bool front = dot(candidate.direction, normal) > 0.0f;
+        if (front) c.blas_rays.fetch_add(1, std::memory_order_relaxed);
+        if (front && traverse_bottom(c, hit, r, emissive_instance.mesh, 0.0f)) {
+            hit.instance_index = emissive.instance;
+            info = hit_info(c, ray, hit);
+            candidate.max_distance = hit.intersection.distance;
+            candidate.min_distance = hit.intersection.distance - 0.1f;
+            vec3 delta = xyz(info.position) - position;
+            candidate.p = dot(delta, delta) / fabsf(dot(ray.direction, info.normal) * emissive.surface_area);
+            candidate.p = candidate.p / count;
+        } else {
+            info = empty_hit_info(ray.origin, ray.direction);
+            candidate.emissive_instance = DONT_SAMPLE_EMISSIVE;
+            candidate.direction = rand_direction;
+            candidate.p = 1.0f;
+        }
+    }
+    return candidate;
+}
+
+// ---------------------------------------------------------------------------------------------- shading
+inline vec3 calculate_view(const Ctx& c, vec4 world_position, bool is_orthographic) {  // light.wgsl:714-727
+    if (is_orthographic) {
+        const float* vp = c.in.view.view_proj;
+        return normalize(v3(vp[0 * 4 + 2], vp[1 * 4 + 2], vp[2 * 4 + 2]));
+    }
+    return normalize(ld3(c.in.view.world_position) - xyz(world_position));
+}
+inline bool is_orthographic(const Ctx& c) { return c.in.view.projection[3 * 4 + 3] == 1.0f; }
+
+vec4 sample_texture(const Texture& t, vec2 uv) {  // textureSampleLevel(textures[id], samplers[id], uv, 0.0)
+    auto wrap = [](int i, int n, uint32_t mode) {
+        if (mode == 0) { i %= n; if (i < 0) i += n; return i; }
+        if (mode == 1) return std::min(std::max(i, 0), n - 1);
+        int period = 2 * n; i %= period; if (i < 0) i += period;
+        return (i < n) ? i : period - 1 - i;
+    };
+    if (!t.linear) {
+        int x = (int)floorf(uv.x * (float)t.w), y = (int)floorf(uv.y * (float)t.h);
+        return t.texels[(size_t)wrap(y, (int)t.h, t.mode_v) * t.w + wrap(x, (int)t.w, t.mode_u)];
+    }
+    float fx = uv.x * (float)t.w - 0.5f, fy = uv.y * (float)t.h - 0.5f;
+    float x0f = floorf(fx), y0f = floorf(fy);
+    float ax = fx - x0f, ay = fy - y0f;
+    int x0 = (int)x0f, y0 = (int)y0f;
+    int xa = wrap(x0, (int)t.w, t.mode_u), xb = wrap(x0 + 1, (int)t.w, t.mode_u);
+    int ya = wrap(y0, (int)t.h, t.mode_v), yb = wrap(y0 + 1, (int)t.h, t.mode_v);
+    vec4 t00 = t.texels[(size_t)ya * t.w + xa], t10 = t.texels[(size_t)ya * t.w + xb];
+    vec4 t01 = t.texels[(size_t)yb * t.w + xa], t11 = t.texels[(size_t)yb * t.w + xb];
+    vec4 top = t00 * (1.0f - ax) + t10 * ax;
+    vec4 bot = t01 * (1.0f - ax) + t11 * ax;
+    return top * (1.0f - ay) + bot * ay;
+}
+
+Surface retreive_surface(const Ctx& c, uint32_t material_index, vec2 uv) {  // light.wgsl:730-742 / 749-781
+    Surface surface;
+    const hk_material& material = c.materials[material_index];
+    surface.base_color = ld4(material.base_color);
+    surface.emissive = ld4(material.emissive);
+    surface.metallic = material.metallic;
+    surface.occlusion = 1.0f;
+    if (!c.textures.empty()) {
+        uint32_t id = material.base_color_texture;
+        if (id != U32_MAX) surface.base_color = surface.base_color * sample_texture(c.textures[id], uv);
+        id = material.emissive_texture;
+        if (id != U32_MAX) surface.emissive = surface.emissive * sample_texture(c.textures[id], uv);
+        id = material.metallic_roughness_texture;
+        if (id != U32_MAX) surface.metallic *= sample_texture(c.textures[id], uv).x;
+        id = material.occlusion_texture;
+        if (id != U32_MAX) surface.occlusion = sample_texture(c.textures[id], uv).x;
+    }
+    surface.roughness = perceptualRoughnessToRoughness(material.perceptual_roughness);
+    surface.reflectance = material.reflectance;
+    return surface;
+}
+vec4 retreive_emissive(const Ctx& c, uint32_t material_index, vec2 uv) {  // light.wgsl:744-747 / 783-793
+    const hk_material& material = c.materials[material_index];
+    vec4 emissive = ld4(material.emissive);
+    if (!c.textures.empty()) {
+        uint32_t id = material.emissive_texture;
+        if (id != U32_MAX) emissive = emissive * sample_texture(c.textures[id], uv);
+    }
+    return emissive;
+}
+vec3 lit(vec3 radiance, vec3 diffuse_color, float roughness, vec3 F0, vec3 Lv, vec3 N, vec3 V) {  // light.wgsl:796-818
+    vec3 Hv = normalize(Lv + V);
+    float NoL = saturate(dot(N, Lv));
+    float NoH = saturate(dot(N, Hv));
+    float LoH = saturate(dot(Lv, Hv));
+    float NdotV = fmax_(dot(N, V), 0.0001f);
+    vec3 diffuse = diffuse_color * Fd_Burley(roughness, NdotV, NoL, LoH);
+    float specular_intensity = 1.0f;
+    vec3 specular_light = specular(F0, roughness, NdotV, NoL, NoH, LoH, specular_intensity);
+    return (specular_light + diffuse) * radiance * NoL;
+}
+vec3 ambient(const Ctx& c, vec3 diffuse_color, float roughness, float occlusion, vec3 F0, vec3 N, vec3 V) {  // light.wgsl:820-833
+    float NdotV = fmax_(dot(N, V), 0.0001f);
+    vec3 diffuse_ambient = EnvBRDFApprox(diffuse_color, 1.0f, NdotV);
+    vec3 specular_ambient = EnvBRDFApprox(F0, roughness, NdotV);
+    return occlusion * (diffuse_ambient + specular_ambient) * xyz(ld4(c.in.lights.ambient_color));
+}
+vec4 input_radiance(const Ctx& c, const Ray& ray, const HitInfo& info, bool sample_directional, uint32_t sample_emissive,
+                    bool sample_ambient) {  // light.wgsl:835-867
+    vec3 radiance = v3(0.0f);
+    float amb = 0.0f;
+    if (info.instance_index == U32_MAX) {
+        vec4 cone = compute_directional_cone(c);
+        bool hit_directional = dot(ray.direction, xyz(cone)) >= cone.w;
+        if (sample_directional && hit_directional) {
+            radiance = xyz(ld4(c.in.lights.directional_color));
+            amb = 0.0f;
+        } else {
+            radiance = sample_ambient ? xyz(ld4(c.in.lights.ambient_color)) : v3(0.0f);
+            amb = 1.0f;
+        }
+    } else {
+        if (sample_emissive == info.instance_index) {
+            vec4 emissive = retreive_emissive(c, info.material_index, info.uv);
+            radiance = compute_emissive_radiance(emissive);
+        }
+    }
+    return v4(radiance, 1.0f - amb);
+}
+vec3 shading(const Ctx& c, vec3 V, vec3 N, vec3 Lv, const Surface& surface, vec4 in_radiance) {  // light.wgsl:869-888
+    vec3 base_color = xyz(surface.base_color);
+    float reflectance = surface.reflectance, roughness = surface.roughness, metallic = surface.metallic;
+    float occlusion = surface.occlusion;
+    vec3 F0 = v3(0.16f * reflectance * reflectance * (1.0f - metallic)) + base_color * metallic;
+    vec3 diffuse_color = base_color * (1.0f - metallic);
+    vec3 lit_radiance = lit(xyz(in_radiance), diffuse_color, roughness, F0, Lv, N, V);
+    vec3 ambient_radiance = ambient(c, diffuse_color, roughness, occlusion, F0, N, V);
+    return mix(lit_radiance, ambient_radiance, 1.0f - in_radiance.w);
+}
+vec3 env_brdf(vec3 V, vec3 N, const Surface& surface) {  // light.wgsl:890-908
+    vec3 base_color = xyz(surface.base_color);
+    float reflectance = surface.reflectance, roughness = surface.roughness, metallic = surface.metallic;
+    float occlusion = surface.occlusion;
+    float NdotV = fmax_(dot(N, V), 0.0001f);
+    vec3 F0 = v3(0.16f * reflectance * reflectance * (1.0f - metallic)) + base_color * metallic;
+    vec3 diffuse_color = base_color * (1.0f - metallic);
+    vec3 diffuse_ambient = EnvBRDFApprox(diffuse_color, 1.0f, NdotV);
+    vec3 specular_ambient = EnvBRDFApprox(F0, roughness, NdotV);
+    return occlusion * (diffuse_ambient + specular_ambient);
+}
+
+// ----------------------------------------------------------------------------------------------- restir
+inline float reservoir_lifetime(const Ctx& c) {  // light.wgsl:913-915
+    return (c.in.frame.max_reservoir_lifetime <= 1.0f) ? F32_MAX : c.in.frame.max_reservoir_lifetime;
+}
+bool check_previous_reservoir(Reservoir& r, const Sample& s) {  // light.wgsl:917-935
+    float depth_ratio = r.s.visible_position.w / s.visible_position.w;
+    depth_ratio = (depth_ratio < 1.0f) ? 1.0f / depth_ratio : depth_ratio;
+    bool depth_miss = depth_ratio > 1.05f * (1.0f + 0.5f * s.random.x);
+    bool instance_miss = r.s.visible_instance != s.visible_instance;
+    bool normal_miss = dot(s.visible_normal, r.s.visible_normal) < 0.9f;
+    if (depth_miss || normal_miss || instance_miss) { r = Reservoir(); return false; }
+    return true;
+}
+void temporal_restir(Reservoir& r, const Sample& s, float w_new, uint32_t max_sample_count) {  // light.wgsl:937-952
+    update_reservoir(r, s, w_new);
+    float m = (float)max_sample_count;
+    if (r.count > m) {
+        r.w_sum *= m / r.count;
+        r.w2_sum *= m / r.count;
+        r.count = m;
+    }
+}
+float compute_jacobian(const Sample& q, const Sample& r) {  // light.wgsl:985-1004
+    vec3 normal = q.sample_normal;
+    float cos_phi_1 = fabsf(dot(normalize(xyz(r.visible_position) - xyz(q.sample_position)), normal));
+    float cos_phi_2 = fabsf(dot(normalize(xyz(q.visible_position) - xyz(q.sample_position)), normal));
+    float term_1 = cos_phi_1 / fmax_(0.0001f, cos_phi_2);
+    float num = length(xyz(q.visible_position) - xyz(q.sample_position));
+    num *= num;
+    float denom = length(xyz(r.visible_position) - xyz(q.sample_position));
+    denom *= denom;
+    float term_2 = num / fmax_(denom, 0.0001f);
+    float jacobian = term_1 * term_2;
+    return clampf(jacobian, 1.0f, 50.0f);
+}
+inline float variance_of(const Reservoir& r) {  // light.wgsl:1224-1226
+    float variance = r.w2_sum / r.count - sq(r.w_sum / r.count);
+    variance = (r.count < 1.0f) ? variance : variance / r.count;
+    return fmin_(variance, MAX_VARIANCE);
+}
+
+// ------------------------------------------------------------------------------------------ G-buffer I/O
+struct Deferred {
+    const Ctx& c;
+    explicit Deferred(const Ctx& ctx) : c(ctx) {}
+    ivec2 size() const { ivec2 s; s.x = c.W; s.y = c.H; return s; }
+    vec2 jittered_uv(vec2 uv, float amount) const {  // light.wgsl:1007-1011 (0.25) / denoise.wgsl:37-41 (0.5)
+        vec2 texel_size = v2(1.0f, 1.0f) / v2((float)c.W, (float)c.H);
+        float ratio = c.in.frame.upscale_ratio - 1.0f;
+        float sgn = ((c.in.frame.number & 1u) == 0u) ? -amount : amount;
+        return uv + sgn * texel_size * ratio;
+    }
+    ivec2 jittered_coords(vec2 uv) const {  // light.wgsl:1013-1017
+        vec2 d = jittered_uv(uv, 0.25f);
+        ivec2 r; r.x = f32_to_i32(d.x * (float)c.W); r.y = f32_to_i32(d.y * (float)c.H);
+        return r;
+    }
+    bool in_bounds(ivec2 p) const { return p.x >= 0 && p.y >= 0 && p.x < c.W && p.y < c.H; }
+    // textureLoad out of bounds returns zero (robust access)
+    vec4 position(ivec2 p) const { return in_bounds(p) ? c.position[(size_t)p.y * c.W + p.x] : v4(0.0f); }
+    vec4 normal(ivec2 p) const { return in_bounds(p) ? unpack4x8snorm(c.normal[(size_t)p.y * c.W + p.x]) : v4(0.0f); }
+    vec2 depth_gradient(ivec2 p) const { return in_bounds(p) ? c.depth_gradient[(size_t)p.y * c.W + p.x] : v2(0, 0); }
+    vec2 instance_material(ivec2 p) const { return in_bounds(p) ? c.instance_material[(size_t)p.y * c.W + p.x] : v2(0, 0); }
+    vec4 velocity_uv(ivec2 p) const { return in_bounds(p) ? c.velocity_uv[(size_t)p.y * c.W + p.x] : v4(0.0f); }
+    // textureSampleLevel(..., nearest_sampler, uv, 0.0): clamp-to-edge nearest
+    ivec2 nearest(vec2 uv) const {
+        ivec2 p; p.x = (int)floorf(uv.x * (float)c.W); p.y = (int)floorf(uv.y * (float)c.H);
+        p.x = std::min(std::max(p.x, 0), c.W - 1); p.y = std::min(std::max(p.y, 0), c.H - 1);
+        return p;
+    }
+};
+
+inline vec4 noise_random(const Ctx& c, ivec2 coords) {  // light.wgsl:1075-1079
+    uint32_t number = c.in.frame.number;
+    uint32_t noise_id = number % NOISE_TEXTURE_COUNT;
+    vec2 noise_uv = (v2((float)coords.x, (float)coords.y) + (float)number + 0.5f) / v2(64.0f, 64.0f);
+    // nearest + repeat
+    int tx = (int)floorf(fract(noise_uv.x) * 64.0f), ty = (int)floorf(fract(noise_uv.y) * 64.0f);
+    tx = std::min(tx, 63); ty = std::min(ty, 63);
+    const uint8_t* t = &c.noise[(((size_t)noise_id * 64 + ty) * 64 + tx) * 4];
+    vec4 rnd = v4((float)t[0] / 255.0f, (float)t[1] / 255.0f, (float)t[2] / 255.0f, (float)t[3] / 255.0f);
+    return fract(rnd + (float)number * GOLDEN_RATIO);
+}
+
+template <class F>
+void for_pixels(Ctx& c, int w, int h, F f) {
+#pragma omp parallel for schedule(dynamic, 4) num_threads(c.threads)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) f(x, y);
+}
+
+// ------------------------------------------------------------------------------- P0: G-buffer (ray cast)
+// Replaces the raster prepass (prepass.wgsl:40-100, prepass.rs:760-852): same five planes, cleared to 0.
+vec2 frame_jitter(const Ctx& c) {  // prepass.wgsl:30-38
+    uint32_t index = c.in.smaa_tu4x ? ((c.in.frame.number >> 1u) & 15u) : (c.in.frame.number & 15u);
+    const float* h = c.in.frame.halton[index >> 1u];
+    return ((index & 1u) == 0u) ? v2(h[0], h[1]) : v2(h[2], h[3]);
+}
+Ray primary_ray(const Ctx& c, float px, float py, vec2 jitter_ndc) {
+    vec2 uv = v2(px + 0.5f, py + 0.5f) / v2((float)c.W, (float)c.H);
+    vec2 ndc = v2(uv.x * 2.0f - 1.0f, (1.0f - uv.y) * 2.0f - 1.0f) - jitter_ndc;
+    vec4 p = mul(ldm(c.in.view.inverse_view_proj), v4(ndc.x, ndc.y, 1.0f, 1.0f));
+    vec3 near_point = xyz(p) / p.w;
+    Ray ray;
+    ray.origin = ld3(c.in.view.world_position);
+    ray.direction = normalize(near_point - ray.origin);
+    ray.inv_direction = 1.0f / ray.direction;
+    return ray;
+}
+void pass_prepass(Ctx& c) {
+    const mat4 view_proj = ldm(c.in.view.view_proj);
+    const mat4 prev_view_proj = ldm(c.in.previous_view.view_proj);
+    vec2 jitter_ndc = v2(0.0f, 0.0f);
+    if (c.in.taa_jitter) {  // prepass.wgsl:52-54,71: clip.xy += (jx, -jy) * w with j = 2 * halton * texel
+        vec2 j = 2.0f * frame_jitter(c) * (v2(1.0f, 1.0f) / v2(c.in.view.viewport[2], c.in.view.viewport[3]));
+        jitter_ndc = v2(j.x, -j.y);
+    }
+    for_pixels(c, c.W, c.H, [&](int x, int y) {
+        size_t idx = (size_t)y * c.W + x;
+        Ray ray = primary_ray(c, (float)x, (float)y, jitter_ndc);
+        c.primary_rays.fetch_add(1, std::memory_order_relaxed);
+        Hit hit = traverse_top(c, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
+        if (hit.instance_index == U32_MAX) {
+            c.position[idx] = v4(0.0f); c.normal[idx] = 0u; c.depth_gradient[idx] = v2(0, 0);
+            c.instance_material[idx] = v2(0, 0); c.velocity_uv[idx] = v4(0.0f);
+            return;
+        }
+        const hk_instance& inst = c.instances[hit.instance_index];
+        const hk_primitive& prim = c.primitives[hit.primitive_index];
+        const hk_vertex& a = c.vertices[inst.mesh.vertex + prim.vertices[0].index];
+        const hk_vertex& b = c.vertices[inst.mesh.vertex + prim.vertices[1].index];
+        const hk_vertex& d = c.vertices[inst.mesh.vertex + prim.vertices[2].index];
+        float u = hit.intersection.uv.x, v = hit.intersection.uv.y;
+        vec3 world_position = ray.origin + ray.direction * hit.intersection.distance;
+        vec4 clip = mul(view_proj, v4(world_position, 1.0f));
+        float depth = clip.z / clip.w;
+        // vertex stage: world_normal = mesh_normal_local_to_world(vertex.normal) (normalised per vertex), interpolated
+        vec3 n0 = instance_normal_local_to_world(inst, ld3(a.normal));
+        vec3 n1 = instance_normal_local_to_world(inst, ld3(b.normal));
+        vec3 n2 = instance_normal_local_to_world(inst, ld3(d.normal));
+        vec3 world_normal = n0 + u * (n1 - n0) + v * (n2 - n0);
+        vec2 uv0 = v2(a.u, a.v), uv1 = v2(b.u, b.v), uv2 = v2(d.u, d.v);
+        vec2 tex_uv = uv0 + u * (uv1 - uv0) + v * (uv2 - uv0);
+        // dpdx / dpdy of clip_position.z: NDC depth is affine in screen space on a planar triangle
+        const mat4 model = ldm(inst.model);
+        vec3 P0 = xyz(mul(model, v4(ld3(prim.vertices[0].position), 1.0f)));
+        vec3 P1 = xyz(mul(model, v4(ld3(prim.vertices[1].position), 1.0f)));
+        vec3 P2 = xyz(mul(model, v4(ld3(prim.vertices[2].position), 1.0f)));
+        vec3 Ng = cross(P1 - P0, P2 - P0);
+        auto plane_depth = [&](float px, float py) {
+            Ray r2 = primary_ray(c, px, py, jitter_ndc);
+            float t = dot(P0 - r2.origin, Ng) / dot(r2.direction, Ng);
+            vec4 cl = mul(view_proj, v4(r2.origin + r2.direction * t, 1.0f));
+            return cl.z / cl.w;
+        };
+        vec2 grad = v2(plane_depth((float)x + 1.0f, (float)y) - depth, plane_depth((float)x, (float)y + 1.0f) - depth);
+        vec2 velocity = clip_to_uv(clip) - clip_to_uv(mul(prev_view_proj, v4(world_position, 1.0f)));
+        c.position[idx] = v4(world_position, depth);
+        c.normal[idx] = pack4x8snorm(v4(world_normal, 1.0f));
+        c.depth_gradient[idx] = grad;
+        c.instance_material[idx] = v2((float)hit.instance_index + 0.5f, (float)inst.material + 0.5f);
+        c.velocity_uv[idx] = v4(velocity.x, velocity.y, tex_uv.x, tex_uv.y);
+    });
+}
+
+// ------------------------------------------------------------------------------ P1: full_screen_albedo
+void pass_albedo(Ctx& c) {  // light.wgsl:1019-1042
+    Deferred g(c);
+    for_pixels(c, c.W, c.H, [&](int x, int y) {
+        ivec2 coords; coords.x = x; coords.y = y;
+        size_t idx = (size_t)y * c.W + x;
+        vec4 position_depth = g.position(coords);
+        vec4 position = v4(xyz(position_depth), 1.0f);
+        float depth = position_depth.w;
+        if (depth < F32_EPSILON) { c.albedo[idx] = pack_rgba16f(v4(0.0f)); return; }
+        vec3 normal = xyz(g.normal(coords));
+        vec2 im = g.instance_material(coords);
+        vec4 velocity_uv = g.velocity_uv(coords);
+        Surface surface = retreive_surface(c, f32_to_u32(im.y), v2(velocity_uv.z, velocity_uv.w));
+        vec3 view_direction = calculate_view(c, position, is_orthographic(c));
+        c.albedo[idx] = pack_rgba16f(v4(env_brdf(view_direction, normal, surface), 1.0f));
+    });
+}
+
+// ------------------------------------------------------------------------------------- P2: direct_lit
+struct PassBuffers {  // bind group 6 (light.rs:518-546) + bind group 5
+    std::vector<hk_packed_reservoir>* previous_reservoir;           // binding 0
+    std::vector<hk_packed_reservoir>* reservoir;                    // binding 1
+    std::vector<hk_packed_reservoir>* previous_spatial_reservoir;   // binding 2
+    std::vector<hk_packed_reservoir>* spatial_reservoir;            // binding 3
+    std::vector<float>* variance;
+    std::vector<uvec2>* render;
+};
+PassBuffers bind(Ctx& c, int signal) {
+    static const int temporal[3] = {0, 2, 6}, spatial[3] = {4, 4, 8};
+    int current = (int)(c.in.frame.number % 2u), previous = 1 - current;
+    PassBuffers b;
+    b.previous_reservoir = &c.reservoir[current + temporal[signal]];
+    b.reservoir = &c.reservoir[previous + temporal[signal]];
+    b.previous_spatial_reservoir = &c.reservoir[current + spatial[signal]];
+    b.spatial_reservoir = &c.reservoir[previous + spatial[signal]];
+    b.variance = &c.variance[signal];
+    b.render = &c.render[signal];
+    return b;
+}
+// deferred scatter log: writes to previous_spatial_reservoir applied in raster order of the writer
+struct ScatterLog {
+    std::vector<std::vector<ScatterWrite>> rows;
+    explicit ScatterLog(int h) : rows(h) {}
+    void push(int y, int32_t index, const hk_packed_reservoir& v) { rows[y].push_back({index, v}); }
+    void apply(std::vector<hk_packed_reservoir>& buf) {
+        for (auto& row : rows)
+            for (auto& w : row) buf[w.index] = w.value;
+    }
+};
+
+template <bool EMISSIVE_LIT, bool RENDER_EMISSIVE>
+void pass_direct_lit(Ctx& c, int signal) {  // light.wgsl:1044-1261
+    Deferred g(c);
+    PassBuffers B = bind(c, signal);
+    ScatterLog scatter(c.RH);
+    const hk_frame_uniform& frame = c.in.frame;
+    ivec2 render_size; render_size.x = c.RW; render_size.y = c.RH;
+    for_pixels(c, c.RW, c.RH, [&](int x, int y) {
+        ivec2 coords; coords.x = x; coords.y = y;
+        vec2 uv = coords_to_uv(coords, render_size);
+        int32_t idx = coords.x + render_size.x * coords.y;
+        Sample s;
+        ivec2 deferred_coords = g.jittered_coords(uv);
+        vec4 position_depth = g.position(deferred_coords);
+        vec4 position = v4(xyz(position_depth), 1.0f);
+        float depth = position_depth.w;
+        if (depth < F32_EPSILON) {
+            Reservoir r;
+            set_reservoir(r, s, 0.0f);
+            hk_packed_reservoir p = pack_reservoir(r);
+            (*B.reservoir)[idx] = p;
+            (*B.spatial_reservoir)[idx] = p;
+            scatter.push(y, idx, p);
+            (*B.variance)[idx] = 0.0f;
+            (*B.render)[idx] = pack_rgba16f(v4(0.0f));
+            return;
+        }
+        vec3 normal = xyz(g.normal(deferred_coords));
+        vec2 imf = g.instance_material(deferred_coords);
+        uint32_t instance_id = f32_to_u32(imf.x), material_id = f32_to_u32(imf.y);
+        vec4 velocity_uv = g.velocity_uv(deferred_coords);
+
+        s.random = noise_random(c, coords);
+        s.visible_position = v4(xyz(position), depth);
+        s.visible_normal = normal;
+        s.visible_instance = instance_id;
+
+        Ray ray; ray.origin = ray.direction = ray.inv_direction = v3(0.0f);
+        Hit hit;
+        HitInfo info;
+
+        vec2 previous_uv = g.jittered_uv(uv, 0.25f) - v2(velocity_uv.x, velocity_uv.y);
+        Reservoir r = load_previous(*B.previous_reservoir, previous_uv, render_size);
+        if (!check_previous_reservoir(r, s) && uv_inside_eq(previous_uv))
+            scatter.push(y, uv_to_index(previous_uv, render_size), pack_reservoir(r));
+
+        const uint32_t validate_interval = EMISSIVE_LIT ? frame.emissive_validate_interval : frame.direct_validate_interval;
+        const uint32_t select_light_instance = EMISSIVE_LIT ? instance_id : DONT_SAMPLE_EMISSIVE;
+
+        if (frame.number % validate_interval != 0u || r.count < 4.0f) {
+            LightCandidate candidate = select_light_candidate(c, s.random, xyz(s.visible_position), s.visible_normal,
+                                                              select_light_instance, info);
+            ray.origin = xyz(position) + normal * RAY_BIAS;
+            ray.direction = candidate.direction;
+            ray.inv_direction = 1.0f / ray.direction;
+            bool trace_condition = dot(candidate.direction, normal) > 0.0f;
+            trace_condition = trace_condition && candidate.p > 0.0f;
+            if (EMISSIVE_LIT) trace_condition = trace_condition && candidate.emissive_instance != DONT_SAMPLE_EMISSIVE;
+            if (trace_condition) {
+                c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                hit = traverse_top(c, ray, candidate.max_distance, candidate.min_distance, candidate.emissive_instance);
+                occlude_hit_info(ray, hit, info);
+                if (EMISSIVE_LIT) s.radiance = input_radiance(c, ray, info, false, candidate.emissive_instance, false);
+                else s.radiance = input_radiance(c, ray, info, true, DONT_SAMPLE_EMISSIVE, false);
+            }
+            s.sample_position = info.position;
+            s.sample_normal = info.normal;
+            float w_new = (candidate.p > 0.0f) ? luminance(xyz(s.radiance)) / candidate.p : 0.0f;
+            temporal_restir(r, s, w_new, frame.max_temporal_reuse_count);
+        }
+
+        if (frame.number % validate_interval == 0u) {
+            LightCandidate candidate = select_light_candidate(c, r.s.random, xyz(r.s.visible_position), r.s.visible_normal,
+                                                              select_light_instance, info);
+            ray.origin = xyz(s.visible_position) + s.visible_normal * RAY_BIAS;
+            ray.direction = normalize(xyz(r.s.sample_position) - xyz(s.visible_position));
+            ray.inv_direction = 1.0f / ray.direction;
+            vec4 validate_radiance = v4(0.0f);
+            bool trace_condition = dot(candidate.direction, r.s.visible_normal) > 0.0f;
+            trace_condition = trace_condition && candidate.p > 0.0f;
+            if (EMISSIVE_LIT) trace_condition = trace_condition && candidate.emissive_instance != DONT_SAMPLE_EMISSIVE;
+            if (trace_condition) {
+                c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                hit = traverse_top(c, ray, candidate.max_distance, candidate.min_distance, candidate.emissive_instance);
+                occlude_hit_info(ray, hit, info);
+                if (EMISSIVE_LIT) validate_radiance = input_radiance(c, ray, info, false, candidate.emissive_instance, false);
+                else validate_radiance = input_radiance(c, ray, info, true, DONT_SAMPLE_EMISSIVE, false);
+            }
+            if (r.count >= 4.0f) {
+                s.random = r.s.random;
+                s.sample_position = info.position;
+                s.sample_normal = info.normal;
+                s.radiance = validate_radiance;
+            }
+            float luminance_ratio = luminance(xyz(validate_radiance)) / fmax_(luminance(xyz(r.s.radiance)), 0.0001f);
+            if (luminance_ratio > 1.25f || luminance_ratio < 0.8f) {
+                if (uv_inside_eq(previous_uv)) scatter.push(y, uv_to_index(previous_uv, render_size), pack_reservoir(r));
+                float w_new = (candidate.p > 0.0f) ? luminance(xyz(s.radiance)) / candidate.p : 0.0f;
+                set_reservoir(r, s, w_new);
+            }
+        }
+
+        float total_lum = r.count * luminance(xyz(r.s.radiance));
+        r.w = (total_lum > 0.0f) ? r.w_sum / total_lum : 0.0f;
+        r.s.visible_position = s.visible_position;
+        r.s.visible_normal = s.visible_normal;
+        r.lifetime += 1.0f;
+        (*B.variance)[idx] = variance_of(r);
+        if (frame.temporal_reuse > 0u) (*B.reservoir)[idx] = pack_reservoir(r);
+
+        Surface surface = retreive_surface(c, material_id, v2(velocity_uv.z, velocity_uv.w));
+        vec3 view_direction = calculate_view(c, position, is_orthographic(c));
+        vec3 out_radiance = shading(c, view_direction, r.s.visible_normal,
+                                    normalize(xyz(r.s.sample_position) - xyz(r.s.visible_position)), surface, r.s.radiance);
+        out_radiance = out_radiance * r.w;
+        vec3 out_color = RENDER_EMISSIVE ? out_radiance + compute_emissive_radiance(surface.emissive) : out_radiance;
+        (*B.render)[idx] = pack_rgba16f(v4(out_color, 1.0f));
+    });
+    scatter.apply(*B.previous_spatial_reservoir);
+}
+
+// ----------------------------------------------------------------------------- P3: indirect_lit_ambient
+template <bool MULTIPLE_BOUNCES>
+void pass_indirect(Ctx& c) {  // light.wgsl:1263-1498
+    Deferred g(c);
+    PassBuffers B = bind(c, 2);
+    ScatterLog scatter(c.RH);
+    const hk_frame_uniform& frame = c.in.frame;
+    ivec2 render_size; render_size.x = c.RW; render_size.y = c.RH;
+    for_pixels(c, c.RW, c.RH, [&](int x, int y) {
+        ivec2 coords; coords.x = x; coords.y = y;
+        vec2 uv = coords_to_uv(coords, render_size);
+        int32_t idx = coords.x + render_size.x * coords.y;
+        ivec2 deferred_coords = g.jittered_coords(uv);
+        vec4 position_depth = g.position(deferred_coords);
+        vec4 position = v4(xyz(position_depth), 1.0f);
+        float depth = position_depth.w;
+        Sample s;
+        Reservoir r;
+        if (frame.indirect_bounces == 0u || depth < F32_EPSILON) {
+            hk_packed_reservoir p = pack_reservoir(r);
+            (*B.reservoir)[idx] = p;
+            (*B.spatial_reservoir)[idx] = p;
+            scatter.push(y, idx, p);
+            (*B.variance)[idx] = 0.0f;
+            (*B.render)[idx] = pack_rgba16f(v4(0.0f));
+            return;
+        }
+        vec3 normal = normalize(xyz(g.normal(deferred_coords)));
+        vec2 imf = g.instance_material(deferred_coords);
+        uint32_t instance_id = f32_to_u32(imf.x), material_id = f32_to_u32(imf.y);
+        vec4 velocity_uv = g.velocity_uv(deferred_coords);
+
+        s.random = noise_random(c, coords);
+        s.visible_position = v4(xyz(position), depth);
+        s.visible_normal = normal;
+        s.visible_instance = instance_id;
+
+        Ray ray;
+        Hit hit;
+        HitInfo info;
+        float pdf = 0.0f;
+        Surface surface;
+
+        if (MULTIPLE_BOUNCES) {
+            Sample bounce_sample = s;
+            vec3 color_transport = v3(1.0f);
+            for (uint32_t n = 0u; n < frame.indirect_bounces &&
+                                  (color_transport.x > 0.01f || color_transport.y > 0.01f || color_transport.z > 0.01f); n += 1u) {
+                vec4 rand_sample = sample_cosine_hemisphere(v2(bounce_sample.random.x, bounce_sample.random.y));
+                ray.origin = xyz(bounce_sample.visible_position) + bounce_sample.visible_normal * RAY_BIAS;
+                ray.direction = mul(normal_basis(bounce_sample.visible_normal), xyz(rand_sample));
+                ray.inv_direction = 1.0f / ray.direction;
+                c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                hit = traverse_top(c, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
+                info = hit_info(c, ray, hit);
+                if (n == 0u) {
+                    s.sample_position = info.position;
+                    s.sample_normal = info.normal;
+                    pdf = rand_sample.w;
+                }
+                bounce_sample.sample_position = info.position;
+                bounce_sample.sample_normal = info.normal;
+                if (hit.instance_index != U32_MAX) {
+                    vec3 out_radiance = v3(0.0f);
+                    surface = retreive_surface(c, info.material_index, info.uv);
+                    surface.roughness = 1.0f;
+                    LightCandidate candidate = select_light_candidate(c, bounce_sample.random, xyz(bounce_sample.sample_position),
+                                                                      bounce_sample.sample_normal, info.instance_index, info);
+                    bool sample_directional = (candidate.emissive_instance == DONT_SAMPLE_EMISSIVE);
+                    vec3 bounce_view_direction = normalize(xyz(bounce_sample.visible_position) - xyz(bounce_sample.sample_position));
+                    if (dot(candidate.direction, bounce_sample.sample_normal) > 0.0f && candidate.p > 0.0f) {
+                        ray.origin = xyz(bounce_sample.sample_position) + bounce_sample.sample_normal * RAY_BIAS;
+                        ray.direction = candidate.direction;
+                        ray.inv_direction = 1.0f / ray.direction;
+                        c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                        hit = traverse_top(c, ray, candidate.max_distance, candidate.min_distance, candidate.emissive_instance);
+                        occlude_hit_info(ray, hit, info);
+                        vec4 in_radiance = input_radiance(c, ray, info, sample_directional, candidate.emissive_instance, false);
+                        out_radiance = shading(c, bounce_view_direction, bounce_sample.sample_normal, ray.direction, surface, in_radiance);
+                        out_radiance = out_radiance / candidate.p;
+                        if (n > 0u) out_radiance = (rand_sample.w < 0.01f) ? v3(0.0f) : out_radiance / rand_sample.w;
+                        float out_luminance = luminance(out_radiance);
+                        if (out_luminance > frame.max_indirect_luminance)
+                            out_radiance = out_radiance * frame.max_indirect_luminance / out_luminance;
+                        s.radiance = s.radiance + v4(color_transport * out_radiance, 1.0f);
+                    }
+                    color_transport = color_transport * env_brdf(bounce_view_direction, bounce_sample.sample_normal, surface);
+                    bounce_sample.random = fract(bounce_sample.random + (float)frame.number * GOLDEN_RATIO);
+                    bounce_sample.visible_position = bounce_sample.sample_position;
+                    bounce_sample.visible_normal = bounce_sample.sample_normal;
+                } else {
+                    vec3 out_radiance = xyz(input_radiance(c, ray, info, false, DONT_SAMPLE_EMISSIVE, true));
+                    s.radiance = s.radiance + v4(color_transport * out_radiance, 0.0f);
+                    break;
+                }
+            }
+        } else {
+            vec4 rand_sample = sample_cosine_hemisphere(v2(s.random.x, s.random.y));
+            ray.origin = xyz(s.visible_position) + s.visible_normal * RAY_BIAS;
+            ray.direction = mul(normal_basis(s.visible_normal), xyz(rand_sample));
+            ray.inv_direction = 1.0f / ray.direction;
+            c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+            hit = traverse_top(c, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
+            info = hit_info(c, ray, hit);
+            s.sample_position = info.position;
+            s.sample_normal = info.normal;
+            pdf = rand_sample.w;
+            if (hit.instance_index != U32_MAX) {
+                vec3 out_radiance = v3(0.0f);
+                surface = retreive_surface(c, info.material_index, info.uv);
+                surface.roughness = 1.0f;
+                LightCandidate candidate = select_light_candidate(c, s.random, xyz(s.sample_position), s.sample_normal,
+                                                                  info.instance_index, info);
+                bool sample_directional = (candidate.emissive_instance == DONT_SAMPLE_EMISSIVE);
+                if (dot(candidate.direction, s.sample_normal) > 0.0f && candidate.p > 0.0f) {
+                    ray.origin = xyz(s.sample_position) + s.sample_normal * RAY_BIAS;
+                    ray.direction = candidate.direction;
+                    ray.inv_direction = 1.0f / ray.direction;
+                    c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                    hit = traverse_top(c, ray, candidate.max_distance, candidate.min_distance, candidate.emissive_instance);
+                    occlude_hit_info(ray, hit, info);
+                    vec4 in_radiance = input_radiance(c, ray, info, sample_directional, candidate.emissive_instance, false);
+                    out_radiance = shading(c, normalize(xyz(s.visible_position) - xyz(s.sample_position)), s.sample_normal,
+                                           ray.direction, surface, in_radiance);
+                    out_radiance = out_radiance / candidate.p;
+                    s.radiance = s.radiance + v4(out_radiance, 1.0f);
+                }
+            } else {
+                vec3 out_radiance = xyz(input_radiance(c, ray, info, false, DONT_SAMPLE_EMISSIVE, true));
+                s.radiance = s.radiance + v4(out_radiance, 0.0f);
+            }
+        }
+
+        // ReSTIR: temporal
+        vec2 previous_uv = g.jittered_uv(uv, 0.25f) - v2(velocity_uv.x, velocity_uv.y);
+        r = load_previous(*B.previous_reservoir, previous_uv, render_size);
+        if (!check_previous_reservoir(r, s) && uv_inside_eq(previous_uv))
+            scatter.push(y, uv_to_index(previous_uv, render_size), pack_reservoir(r));
+
+        surface = retreive_surface(c, material_id, v2(velocity_uv.z, velocity_uv.w));
+        vec3 view_direction = calculate_view(c, position, is_orthographic(c));
+        vec3 sample_radiance = shading(c, view_direction, s.visible_normal,
+                                       normalize(xyz(s.sample_position) - xyz(s.visible_position)), surface, s.radiance);
+        float w_new = (pdf > 0.0f) ? luminance(sample_radiance) / pdf : 0.0f;
+        temporal_restir(r, s, w_new, frame.max_temporal_reuse_count);
+
+        vec3 out_radiance = shading(c, view_direction, r.s.visible_normal,
+                                    normalize(xyz(r.s.sample_position) - xyz(r.s.visible_position)), surface, r.s.radiance);
+        float total_lum = r.count * luminance(out_radiance);
+        r.w = (total_lum > 0.0f) ? r.w_sum / total_lum : 0.0f;
+        r.s.visible_position = s.visible_position;
+        r.s.visible_normal = s.visible_normal;
+        r.lifetime += 1.0f;
+        (*B.variance)[idx] = variance_of(r);
+        if (frame.temporal_reuse > 0u) (*B.reservoir)[idx] = pack_reservoir(r);
+        (*B.render)[idx] = pack_rgba16f(v4(out_radiance * r.w, 1.0f));
+    });
+    scatter.apply(*B.previous_spatial_reservoir);
+}
+
+// ----------------------------------------------------------------------------------- P4: spatial_reuse
+template <bool EMISSIVE_LIT, bool RENDER_EMISSIVE>
+void pass_spatial_reuse(Ctx& c, int signal) {  // light.wgsl:1500-1684
+    Deferred g(c);
+    PassBuffers B = bind(c, signal);
+    const hk_frame_uniform& frame = c.in.frame;
+    const uint32_t SPATIAL_REUSE_COUNT = EMISSIVE_LIT ? 8u : 16u;       // light.wgsl:246-252
+    const float SPATIAL_REUSE_RANGE = EMISSIVE_LIT ? 10.0f : 20.0f;
+    const uint32_t SPATIAL_REUSE_TAPS = 4u;
+    ivec2 render_size; render_size.x = c.RW; render_size.y = c.RH;
+    // The 8x8 workgroup cache (light.wgsl:1500-1501,1584-1591) holds unpack(reservoir_buffer[..]) of the same dispatch's
+    // inputs, so reading the buffer directly is value-identical; the oracle reads the buffer.
+    for_pixels(c, c.RW, c.RH, [&](int x, int y) {
+        ivec2 coords; coords.x = x; coords.y = y;
+        vec2 uv = coords_to_uv(coords, render_size);
+        int32_t idx = coords.x + render_size.x * coords.y;
+        ivec2 deferred_coords = g.jittered_coords(uv);
+        vec4 position_depth = g.position(deferred_coords);
+        vec4 position = v4(xyz(position_depth), 1.0f);
+        float depth = position_depth.w;
+        Reservoir r = unpack_reservoir((*B.reservoir)[idx]);
+        if (depth < F32_EPSILON) {
+            (*B.spatial_reservoir)[idx] = pack_reservoir(r);
+            (*B.render)[idx] = pack_rgba16f(v4(0.0f));
+            return;
+        }
+        vec2 imf = g.instance_material(deferred_coords);
+        uint32_t material_id = f32_to_u32(imf.y);
+        vec4 velocity_uv = g.velocity_uv(deferred_coords);
+        Surface surface = retreive_surface(c, material_id, v2(velocity_uv.z, velocity_uv.w));
+        bool use_spatial_variance = r.count <= 4.0f;
+        vec2 previous_uv = g.jittered_uv(uv, 0.25f) - v2(velocity_uv.x, velocity_uv.y);
+        Reservoir q = r;
+        const Sample s = q.s;
+        if (r.lifetime <= reservoir_lifetime(c)) r = load_previous(*B.previous_spatial_reservoir, previous_uv, render_size);
+        vec3 view_direction = calculate_view(c, position, is_orthographic(c));
+        if (EMISSIVE_LIT) {
+            merge_reservoir(r, q, luminance(xyz(q.s.radiance)));
+        } else {
+            vec3 out_radiance = shading(c, view_direction, s.visible_normal,
+                                        normalize(xyz(s.sample_position) - xyz(s.visible_position)), surface, s.radiance);
+            merge_reservoir(r, q, luminance(out_radiance));
+        }
+        r.s.visible_position = s.visible_position;
+        r.s.visible_normal = s.visible_normal;
+
+        for (uint32_t i = 1u; i <= SPATIAL_REUSE_COUNT; i += 1u) {
+            float ang = TAU * fract((float)i * GOLDEN_RATIO + sum4(s.random) + random_float(frame.number));
+            float rad = sqrtf((float)i / (float)SPATIAL_REUSE_COUNT) * SPATIAL_REUSE_RANGE;
+            float sn, cs; sincos_(ang, &sn, &cs);
+            vec2 offset = rad * v2(cs, sn);
+            ivec2 sample_coords;
+            sample_coords.x = f32_to_i32(offset.x + (float)coords.x);
+            sample_coords.y = f32_to_i32(offset.y + (float)coords.y);
+            vec2 sample_uv = coords_to_uv(sample_coords, render_size);
+            ivec2 sample_deferred_coords = g.jittered_coords(sample_uv);
+            if (sample_uv.x < 0.0f || sample_uv.y < 0.0f || sample_uv.x > 1.0f || sample_uv.y > 1.0f) continue;
+
+            float sample_depth = g.position(sample_deferred_coords).w;
+            q = unpack_reservoir((*B.reservoir)[sample_coords.x + render_size.x * sample_coords.y]);
+
+            float depth_ratio = depth / sample_depth;
+            if (depth_ratio < 0.9f || depth_ratio > 1.1f) continue;
+            bool normal_miss = dot(s.visible_normal, q.s.visible_normal) < 0.866f;
+            if (q.count < F32_EPSILON || normal_miss) continue;
+            vec3 sample_direction = normalize(xyz(q.s.sample_position) - xyz(s.visible_position));
+            if (dot(sample_direction, s.visible_normal) < 0.0f) continue;
+
+            float tap_interval = fmax_(1.0f, rad / (float)(SPATIAL_REUSE_TAPS + 1u));
+            uint32_t tap_count = f32_to_u32(rad / tap_interval);
+            bool occluded = false;
+            for (uint32_t j = 1u; j <= tap_count; j += 1u) {
+                float tap_dist = (float)j * tap_interval;
+                vec2 tap_offset = tap_dist * normalize(offset);
+                vec2 tap_uv = uv + tap_offset / v2((float)render_size.x, (float)render_size.y);
+                ivec2 tap_deferred_coords = g.jittered_coords(tap_uv);
+                float tap_depth = g.position(tap_deferred_coords).w;
+                float ref_depth = mixf(depth, sample_depth, (float)j / (float)(tap_count + 1u));
+                if (tap_depth > ref_depth + 0.00001f) { occluded = true; break; }
+            }
+            if (occluded) continue;
+
+            float jacobian = (q.s.sample_position.w > 0.5f) ? compute_jacobian(q.s, s) : 1.0f;
+            if (EMISSIVE_LIT) {
+                merge_reservoir(r, q, luminance(xyz(q.s.radiance)) / jacobian);
+            } else {
+                vec3 out_radiance = shading(c, view_direction, s.visible_normal, sample_direction, surface, q.s.radiance);
+                merge_reservoir(r, q, luminance(out_radiance) / jacobian);
+            }
+        }
+
+        float m = (float)frame.max_spatial_reuse_count;
+        if (r.count > m) {
+            r.w_sum *= m / r.count;
+            r.w2_sum *= m / r.count;
+            r.count = m;
+        }
+        vec3 out_radiance = shading(c, view_direction, s.visible_normal,
+                                    normalize(xyz(r.s.sample_position) - xyz(s.visible_position)), surface, r.s.radiance);
+        float total_lum = EMISSIVE_LIT ? r.count * luminance(xyz(r.s.radiance)) : r.count * luminance(out_radiance);
+        r.w = (total_lum > 0.0f) ? r.w_sum / total_lum : 0.0f;
+        r.lifetime += 1.0f;
+        (*B.spatial_reservoir)[idx] = pack_reservoir(r);
+        if (use_spatial_variance) (*B.variance)[idx] = variance_of(r);
+        vec3 out_color = RENDER_EMISSIVE ? r.w * out_radiance + compute_emissive_radiance(surface.emissive) : r.w * out_radiance;
+        (*B.render)[idx] = pack_rgba16f(v4(out_color, 1.0f));
+    });
+}
+
+// ------------------------------------------------------------------------------------------ P5/P6: denoise
+inline vec4 tex16(const std::vector<uvec2>& t, int w, int h, ivec2 p) {  // textureLoad on a storage texture
+    if (p.x < 0 || p.y < 0 || p.x >= w || p.y >= h) return v4(0.0f);
+    return unpack_rgba16f(t[(size_t)p.y * w + p.x]);
+}
+inline float kernel_at(const hk_frame_uniform& f, int col, int row) { return f.kernel[col][row]; }  // frame.kernel[a][b]
+
+void pass_demodulation(Ctx& c, int signal) {  // denoise.wgsl:135-162
+    Deferred g(c);
+    const hk_frame_uniform& frame = c.in.frame;
+    ivec2 output_size; output_size.x = c.RW; output_size.y = c.RH;
+    ivec2 input_size = output_size;
+    for_pixels(c, c.RW, c.RH, [&](int x, int y) {
+        ivec2 coords; coords.x = x; coords.y = y;
+        size_t idx = (size_t)y * c.RW + x;
+        vec2 uv = coords_to_uv(coords, output_size);
+        vec2 deferred_uv = g.jittered_uv(uv, 0.5f);
+        ivec2 ap = g.nearest(deferred_uv);
+        vec3 albedo = xyz(unpack_rgba16f(c.albedo[(size_t)ap.y * c.W + ap.x]));
+        ivec2 rp; rp.x = std::min(std::max((int)floorf(uv.x * (float)c.RW), 0), c.RW - 1);
+        rp.y = std::min(std::max((int)floorf(uv.y * (float)c.RH), 0), c.RH - 1);
+        vec3 irradiance = xyz(unpack_rgba16f(c.render[signal][(size_t)rp.y * c.RW + rp.x]));
+        vec3 q = irradiance / albedo;
+        irradiance = v3(albedo.x < 0.01f ? 0.0f : q.x, albedo.y < 0.01f ? 0.0f : q.y, albedo.z < 0.01f ? 0.0f : q.z);
+        c.denoise_internal[0][idx] = pack_rgba16f(v4(irradiance, 1.0f));
+
+        float sum_variance = 0.0f;
+        auto accumulate_variance = [&](int ox, int oy) {  // denoise.wgsl:116-133
+            vec2 sample_uv = uv + v2((float)ox, (float)oy) / v2((float)input_size.x, (float)input_size.y);
+            if (sample_uv.x < 0.0f || sample_uv.y < 0.0f || sample_uv.x > 1.0f || sample_uv.y > 1.0f) return;
+            ivec2 p; p.x = std::min(std::max((int)floorf(sample_uv.x * (float)c.RW), 0), c.RW - 1);
+            p.y = std::min(std::max((int)floorf(sample_uv.y * (float)c.RH), 0), c.RH - 1);
+            float variance = c.variance[signal][(size_t)p.y * c.RW + p.x];
+            if (variance > F32_MAX) return;
+            sum_variance += kernel_at(frame, oy + 1, ox + 1) * fmax_(variance, 0.0f);
+        };
+        accumulate_variance(-1, -1); accumulate_variance(-1, 0); accumulate_variance(-1, 1);
+        accumulate_variance(0, -1);  accumulate_variance(0, 0);  accumulate_variance(0, 1);
+        accumulate_variance(1, -1);  accumulate_variance(1, 0);  accumulate_variance(1, 1);
+        c.denoise_internal_variance[idx] = sum_variance;
+    });
+}
+
+template <int LEVEL, bool FIREFLY_FILTERING>
+void pass_denoise(Ctx& c, int signal) {  // denoise.wgsl:164-319
+    Deferred g(c);
+    const hk_frame_uniform& frame = c.in.frame;
+    const int step_size = 8 >> LEVEL;  // denoise.wgsl:101-114
+    const std::vector<uvec2>& input = c.denoise_internal[LEVEL];
+    std::vector<uvec2>& output = (LEVEL == 3) ? c.denoise_render[signal] : c.denoise_internal[LEVEL + 1];
+    ivec2 output_size; output_size.x = c.RW; output_size.y = c.RH;
+    for_pixels(c, c.RW, c.RH, [&](int x, int y) {
+        ivec2 coords; coords.x = x; coords.y = y;
+        size_t idx = (size_t)y * c.RW + x;
+        vec2 uv = coords_to_uv(coords, output_size);
+        vec2 deferred_uv = g.jittered_uv(uv, 0.5f);
+        ivec2 dp = g.nearest(deferred_uv);
+        float depth = g.position(dp).w;
+        vec2 depth_gradient = g.depth_gradient(dp);
+        vec3 normal = normalize(xyz(g.normal(dp)));
+        float instance = g.instance_material(dp).x;
+        if (depth < F32_EPSILON) { output[idx] = pack_rgba16f(v4(0.0f)); return; }
+
+        float variance = c.denoise_internal_variance[idx];
+        vec3 irradiance = xyz(tex16(input, c.RW, c.RH, coords));
+        vec3 sum_irradiance = irradiance * kernel_at(frame, 1, 1);
+        float sum_w = kernel_at(frame, 1, 1);
+        auto bad = [](vec3 v) { return is_nan(v.x) || is_nan(v.y) || is_nan(v.z) || v.x > F32_MAX || v.y > F32_MAX || v.z > F32_MAX; };
+        if (bad(irradiance)) { irradiance = v3(0.0f); sum_irradiance = v3(0.0f); sum_w = 0.0f; }
+        float lum = luminance(irradiance);
+        float ff_moment_1 = 0.0f, ff_moment_2 = 0.0f, ff_count = 0.0f;
+
+        auto accumulate_irradiance = [&](int ox, int oy) {  // denoise.wgsl:164-213
+            ivec2 sample_coords; sample_coords.x = coords.x + ox * step_size; sample_coords.y = coords.y + oy * step_size;
+            vec2 sample_uv = coords_to_uv(sample_coords, output_size);
+            vec2 sample_deferred_uv = g.jittered_uv(sample_uv, 0.5f);
+            if (sample_uv.x < 0.0f || sample_uv.y < 0.0f || sample_uv.x > 1.0f || sample_uv.y > 1.0f) return;
+            vec3 irr = xyz(tex16(input, c.RW, c.RH, sample_coords));
+            if (bad(irr)) return;
+            ivec2 sp = g.nearest(sample_deferred_uv);
+            vec3 sample_normal = normalize(xyz(g.normal(sp)));
+            float sample_depth = g.position(sp).w;
+            float sample_instance = g.instance_material(sp).x;
+            float sample_luminance = luminance(irr);
+            float w_normal = pow16(fmax_(0.0f, dot(normal, sample_normal)));                                    // :44-47
+            float w_depth = exp_((-fabsf(depth - sample_depth)) /
+                                 (fabsf(dot(depth_gradient, v2((float)ox, (float)oy))) + 0.01f));               // :50-53
+            float w_instance = fmax_(0.0f, 1.0f - fabsf(instance - sample_instance));                           // :63-65
+            float w_luminance = exp_((-fabsf(lum - sample_luminance)) / (4.0f * pow025(variance) + 0.001f));    // :56-61
+            float w = clampf(w_normal * w_depth * w_instance * w_luminance, 0.0f, 1.0f) * kernel_at(frame, oy + 1, ox + 1);
+            sum_irradiance = sum_irradiance + irr * w;
+            sum_w += w;
+            if (FIREFLY_FILTERING) {
+                ff_moment_1 += sample_luminance;
+                ff_moment_2 += sample_luminance * sample_luminance;
+                ff_count += 1.0f;
+            }
+        };
+        accumulate_irradiance(-1, -1); accumulate_irradiance(0, -1); accumulate_irradiance(1, -1);
+        accumulate_irradiance(-1, 0);  accumulate_irradiance(1, 0);
+        accumulate_irradiance(-1, 1);  accumulate_irradiance(0, 1);  accumulate_irradiance(1, 1);
+
+        irradiance = (sum_w < 0.0001f) ? v3(0.0f) : sum_irradiance / sum_w;
+        if (FIREFLY_FILTERING) {
+            float ff_mean = ff_moment_1 / ff_count;
+            float ff_var = ff_moment_2 / ff_count - ff_mean * ff_mean;
+            if (lum > ff_mean + 3.0f * sqrtf(ff_var)) irradiance = ff_mean / lum * irradiance;
+        }
+        vec4 color = v4(irradiance, 1.0f);
+        if (LEVEL == 3) {
+            ivec2 ap = g.nearest(deferred_uv);
+            vec4 albedo = unpack_rgba16f(c.albedo[(size_t)ap.y * c.W + ap.x]);
+            color = color * albedo;
+        }
+        output[idx] = pack_rgba16f(color);
+    });
+}
+
+void pass_tone_mapping(Ctx& c) {  // tone_mapping.wgsl:21-32 ; inputs per post_process.rs:940-954
+    const bool dn = c.in.denoise != 0;
+    const std::vector<uvec2>& direct = dn ? c.denoise_render[0] : c.render[0];
+    const std::vector<uvec2>& emissive = dn ? c.denoise_render[1] : c.render[1];
+    const std::vector<uvec2>* indirect = dn ? &c.denoise_render[2] : &c.render[2];
+    const bool no_indirect = c.in.frame.indirect_bounces == 0;  // fallback 1x1 texture: only texel (0,0) is in bounds
+    for_pixels(c, c.RW, c.RH, [&](int x, int y) {
+        size_t idx = (size_t)y * c.RW + x;
+        vec4 color = unpack_rgba16f(direct[idx]);
+        color = color + unpack_rgba16f(emissive[idx]);
+        if (!no_indirect) color = color + unpack_rgba16f((*indirect)[idx]);
+        vec3 rgb = reinhard_luminance(vmax(xyz(color), 0.0039f));
+        color = v4(rgb, color.w);
+        if (!(color.w > 0.0f)) color = ld4(c.in.frame.clear_color);
+        c.tone_mapping_output[idx] = pack_rgba16f(color);
+    });
+}
+
+// ----------------------------------------------------------------------------------------- node drivers
+void light_node(Ctx& c) {  // LightNode::run, light.rs:590-702
+    pass_albedo(c);
+    pass_direct_lit<false, true>(c, 0);                       // direct_lit + RENDER_EMISSIVE (light.rs:409-414)
+    pass_direct_lit<true, false>(c, 1);                       // direct_emissive: EMISSIVE_LIT (light.rs:415-420)
+    if (c.in.frame.emissive_spatial_reuse) pass_spatial_reuse<true, false>(c, 1);
+    if (c.in.frame.indirect_bounces < 2) pass_indirect<false>(c); else pass_indirect<true>(c);
+    if (c.in.frame.indirect_spatial_reuse) pass_spatial_reuse<false, false>(c, 2);
+}
+void post_process_node(Ctx& c) {  // PostProcessNode::run, post_process.rs:1140-1234
+    if (c.in.denoise) {
+        int signals = (c.in.frame.indirect_bounces == 0) ? 2 : 3;  // post_process.rs:949-954
+        for (int sgl = 0; sgl < signals; ++sgl) {
+            pass_demodulation(c, sgl);
+            if (sgl == 0) {  // denoise_direct: no FIREFLY_FILTERING (post_process.rs:1193-1197)
+                pass_denoise<0, false>(c, sgl); pass_denoise<1, false>(c, sgl);
+                pass_denoise<2, false>(c, sgl); pass_denoise<3, false>(c, sgl);
+            } else {
+                pass_denoise<0, true>(c, sgl); pass_denoise<1, true>(c, sgl);
+                pass_denoise<2, true>(c, sgl); pass_denoise<3, true>(c, sgl);
+            }
+        }
+    }
+    pass_tone_mapping(c);
+}
+
+int fail(Ctx* c, int code, const char* msg) { if (c) c->error = msg; return code; }
+
+template <class T>
+void assign(std::vector<T>& dst, const T* src, uint32_t n) { dst.assign(src, src + n); }
+
+}  // namespace
+
+// ================================================================================================ C API
+extern "C" {
+
+int hko_context_create(hko_context** out, uint32_t width, uint32_t height, int threads) {
+    if (!out || !width || !height) return HK_ERR_INVALID_ARGUMENT;
+    Ctx* c = new Ctx();
+    c->W = c->RW = (int)width;
+    c->H = c->RH = (int)height;
+    c->threads = threads > 0 ? threads : 1;
+    size_t n = (size_t)width * height;
+    c->position.assign(n, v4(0.0f)); c->normal.assign(n, 0u); c->depth_gradient.assign(n, v2(0, 0));
+    c->instance_material.assign(n, v2(0, 0)); c->velocity_uv.assign(n, v4(0.0f));
+    uvec2 z2; z2.x = z2.y = 0;
+    c->albedo.assign(n, z2);
+    hk_packed_reservoir zr; memset(&zr, 0, sizeof(zr));
+    for (int i = 0; i < 3; ++i) { c->render[i].assign(n, z2); c->variance[i].assign(n, 0.0f); c->denoise_render[i].assign(n, z2); }
+    for (int i = 0; i < 10; ++i) c->reservoir[i].assign(n, zr);
+    for (int i = 0; i < 4; ++i) c->denoise_internal[i].assign(n, z2);
+    c->denoise_internal_variance.assign(n, 0.0f);
+    c->tone_mapping_output.assign(n, z2);
+    memset(&c->in, 0, sizeof(c->in));
+    *out = c;
+    return HK_OK;
+}
+void hko_context_destroy(hko_context* c) { delete c; }
+int hko_reset_temporal_state(hko_context* c) {
+    hk_packed_reservoir zr; memset(&zr, 0, sizeof(zr));
+    for (int i = 0; i < 10; ++i) std::fill(c->reservoir[i].begin(), c->reservoir[i].end(), zr);
+    return HK_OK;
+}
+int hko_scene_upload(hko_context* c, const hk_scene_desc* s) {
+    if (!c || !s) return HK_ERR_INVALID_ARGUMENT;
+    assign(c->vertices, s->vertices, s->vertex_count);
+    assign(c->primitives, s->primitives, s->primitive_count);
+    assign(c->asset_nodes, s->asset_nodes, s->asset_node_count);
+    assign(c->alias_table, s->alias_table, s->alias_count);
+    assign(c->instances, s->instances, s->instance_count);
+    assign(c->instance_nodes, s->instance_nodes, s->instance_node_count);
+    assign(c->materials, s->materials, s->material_count);
+    assign(c->emissive_nodes, s->emissive_nodes, s->emissive_node_count);
+    assign(c->emissives, s->emissives, s->emissive_count);
+    c->textures.clear();
+    float srgb_lut[256], lin_lut[256];
+    for (int i = 0; i < 256; ++i) {
+        double v = i / 255.0;
+        lin_lut[i] = (float)v;
+        srgb_lut[i] = (float)(v <= 0.04045 ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4));
+    }
+    for (uint32_t t = 0; t < s->texture_count; ++t) {
+        const hk_texture_desc& d = s->textures[t];
+        Texture tex;
+        tex.w = d.width; tex.h = d.height; tex.mode_u = d.address_mode_u; tex.mode_v = d.address_mode_v; tex.linear = d.filter_linear;
+        tex.texels.resize((size_t)d.width * d.height);
+        const float* lut = d.srgb ? srgb_lut : lin_lut;
+        for (size_t i = 0; i < tex.texels.size(); ++i)
+            tex.texels[i] = v4(lut[d.rgba8[4 * i]], lut[d.rgba8[4 * i + 1]], lut[d.rgba8[4 * i + 2]], lin_lut[d.rgba8[4 * i + 3]]);
+        c->textures.push_back(std::move(tex));
+    }
+    c->scene_ready = true;
+    return HK_OK;
+}
+int hko_set_noise(hko_context* c, const uint8_t* rgba) {
+    c->noise.assign(rgba, rgba + 16 * 64 * 64 * 4);
+    c->noise_ready = true;
+    return HK_OK;
+}
+static int begin(hko_context* c, const hk_frame_inputs* in) {
+    if (!c || !in) return HK_ERR_INVALID_ARGUMENT;
+    if (!c->scene_ready || !c->noise_ready) return fail(c, HK_ERR_NOT_READY, "scene or noise not uploaded");
+    if (in->frame.upscale_ratio != 1.0f) return fail(c, HK_ERR_UNSUPPORTED, "upscale_ratio != 1");
+    c->in = *in;
+    return HK_OK;
+}
+int hko_prepass_run(hko_context* c, const hk_frame_inputs* in) { int e = begin(c, in); if (e) return e; pass_prepass(*c); return HK_OK; }
+int hko_light_run(hko_context* c, const hk_frame_inputs* in) { int e = begin(c, in); if (e) return e; light_node(*c); return HK_OK; }
+int hko_post_process_run(hko_context* c, const hk_frame_inputs* in) { int e = begin(c, in); if (e) return e; post_process_node(*c); return HK_OK; }
+int hko_render_frame(hko_context* c, const hk_frame_inputs* in) {
+    int e = begin(c, in); if (e) return e;
+    pass_prepass(*c); light_node(*c); post_process_node(*c);
+    return HK_OK;
+}
+// single passes, for per-pass parity from identical inputs.  pass ids: 0 albedo, 1 direct(sun), 2 direct(emissive),
+// 3 spatial(emissive), 4 indirect, 5 spatial(indirect), 6 denoise chain of signal `arg`, 7 tone mapping
+int hko_run_pass(hko_context* c, const hk_frame_inputs* in, int pass, int arg) {
+    int e = begin(c, in); if (e) return e;
+    switch (pass) {
+        case 0: pass_albedo(*c); break;
+        case 1: pass_direct_lit<false, true>(*c, 0); break;
+        case 2: pass_direct_lit<true, false>(*c, 1); break;
+        case 3: pass_spatial_reuse<true, false>(*c, 1); break;
+        case 4: if (c->in.frame.indirect_bounces < 2) pass_indirect<false>(*c); else pass_indirect<true>(*c); break;
+        case 5: pass_spatial_reuse<false, false>(*c, 2); break;
+        case 6:
+            pass_demodulation(*c, arg);
+            if (arg == 0) { pass_denoise<0, false>(*c, arg); pass_denoise<1, false>(*c, arg); pass_denoise<2, false>(*c, arg); pass_denoise<3, false>(*c, arg); }
+            else { pass_denoise<0, true>(*c, arg); pass_denoise<1, true>(*c, arg); pass_denoise<2, true>(*c, arg); pass_denoise<3, true>(*c, arg); }
+            break;
+        case 7: pass_tone_mapping(*c); break;
+        default: return HK_ERR_INVALID_ARGUMENT;
+    }
+    return HK_OK;
+}
+static void* plane(hko_context* c, int which, size_t* bytes) {
+    size_t n = (size_t)c->W * c->H;
+    auto R = [&](void* p, size_t b) { *bytes = b * n; return p; };
+    switch (which) {
+        case HK_OUT_TONE_MAPPED: return R(c->tone_mapping_output.data(), 8);
+        case HK_OUT_RENDER_DIRECT: case HK_OUT_RENDER_EMISSIVE: case HK_OUT_RENDER_INDIRECT:
+            return R(c->render[which - HK_OUT_RENDER_DIRECT].data(), 8);
+        case HK_OUT_VARIANCE_DIRECT: case HK_OUT_VARIANCE_EMISSIVE: case HK_OUT_VARIANCE_INDIRECT:
+            return R(c->variance[which - HK_OUT_VARIANCE_DIRECT].data(), 4);
+        case HK_OUT_ALBEDO: return R(c->albedo.data(), 8);
+        case HK_OUT_DENOISED_DIRECT: case HK_OUT_DENOISED_EMISSIVE: case HK_OUT_DENOISED_INDIRECT:
+            return R(c->denoise_render[which - HK_OUT_DENOISED_DIRECT].data(), 8);
+        case HK_OUT_GBUFFER_POSITION: return R(c->position.data(), 16);
+        case HK_OUT_GBUFFER_NORMAL: return R(c->normal.data(), 4);
+        case HK_OUT_GBUFFER_DEPTH_GRADIENT: return R(c->depth_gradient.data(), 8);
+        case HK_OUT_GBUFFER_INSTANCE_MATERIAL: return R(c->instance_material.data(), 8);
+        case HK_OUT_GBUFFER_VELOCITY_UV: return R(c->velocity_uv.data(), 16);
+        default:
+            if (which >= HK_OUT_RESERVOIR_0 && which < HK_OUT_RESERVOIR_0 + 10) return R(c->reservoir[which - HK_OUT_RESERVOIR_0].data(), 64);
+    }
+    return nullptr;
+}
+int hko_readback(hko_context* c, int which, void* host, size_t bytes) {
+    size_t b = 0; void* p = plane(c, which, &b);
+    if (!p || bytes != b) return fail(c, HK_ERR_INVALID_ARGUMENT, "bad plane id or size");
+    memcpy(host, p, b);
+    return HK_OK;
+}
+int hko_upload_state(hko_context* c, int which, const void* host, size_t bytes) {
+    size_t b = 0; void* p = plane(c, which, &b);
+    if (!p || bytes != b) return fail(c, HK_ERR_INVALID_ARGUMENT, "bad plane id or size");
+    memcpy(p, host, b);
+    return HK_OK;
+}
+int hko_trace_rays(hko_context* c, const hk_ray* rays, size_t n, hk_hit* hits) {
+    if (!c->scene_ready) return fail(c, HK_ERR_NOT_READY, "scene not uploaded");
+#pragma omp parallel for num_threads(c->threads)
+    for (long long i = 0; i < (long long)n; ++i) {
+        Ray r;
+        r.origin = ld3(rays[i].origin); r.direction = ld3(rays[i].direction); r.inv_direction = 1.0f / r.direction;
+        Hit h = traverse_top(*c, r, rays[i].max_distance, rays[i].early_distance, rays[i].exclude_instance);
+        hits[i].u = h.intersection.uv.x; hits[i].v = h.intersection.uv.y; hits[i].distance = h.intersection.distance;
+        hits[i].instance_index = h.instance_index; hits[i].primitive_index = h.primitive_index;
+    }
+    return HK_OK;
+}
+int hko_get_stats(hko_context* c, hk_frame_stats* out) {
+    memset(out, 0, sizeof(*out));
+    out->primary_rays = c->primary_rays.exchange(0);
+    out->tlas_rays = c->tlas_rays.exchange(0);
+    out->blas_rays = c->blas_rays.exchange(0);
+    return HK_OK;
+}
+const char* hko_last_error(hko_context* c) { return c ? c->error.c_str() : ""; }
+
+// scalar primitives exported for known-answer tests of include/hk_math.h
+float hko_math_exp2(float x) { return exp2_(x); }
+float hko_math_exp(float x) { return exp_(x); }
+void hko_math_sincos(float x, float* s, float* c) { sincos_(x, s, c); }
+uint32_t hko_math_pack2x16float(float a, float b) { return pack2x16float(a, b); }
+float hko_math_f16_to_f32(uint16_t h) { return f16_bits_to_f32(h); }
+uint32_t hko_math_pack4x8snorm(float x, float y, float z, float w) { return pack4x8snorm(v4(x, y, z, w)); }
+uint32_t hko_math_pack2x16unorm(float a, float b) { return pack2x16unorm(a, b); }
+uint32_t hko_math_hash(uint32_t v) { return hash_u32(v); }
+void hko_math_normal_basis(const float* n, float* out9) {
+    mat3 m = normal_basis(v3(n[0], n[1], n[2]));
+    for (int i = 0; i < 3; ++i) { out9[3 * i] = m.c[i].x; out9[3 * i + 1] = m.c[i].y; out9[3 * i + 2] = m.c[i].z; }
+}
+void hko_pack_reservoir_roundtrip(const hk_packed_reservoir* in, hk_packed_reservoir* out) { *out = pack_reservoir(unpack_reservoir(*in)); }
+
+}  // extern "C"

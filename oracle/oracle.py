@@ -1,0 +1,123 @@
+"""ORACLE (test infrastructure): ctypes wrapper of oracle/libhk_oracle.so, the CPU restatement of the reference's
+per-frame passes (oracle/hk_oracle.cpp).  Imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs — never by the product package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from bevy_hikari_b200 import layout as L
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhk_oracle.so")
+_P, _I, _U32, _SZ = C.c_void_p, C.c_int, C.c_uint32, C.c_size_t
+
+
+def build(force=False):
+    src = [os.path.join(HERE, "hk_oracle.cpp")] + [os.path.join(HERE, "..", "include", h)
+                                                   for h in ("hk_math.h", "hk_layout.h", "hikari_b200.h")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
+        r = subprocess.run(["make", "-C", HERE, "-B", "libhk_oracle.so"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        sig = {
+            "hko_context_create": (_I, [C.POINTER(_P), _U32, _U32, _I]),
+            "hko_context_destroy": (None, [_P]),
+            "hko_reset_temporal_state": (_I, [_P]),
+            "hko_scene_upload": (_I, [_P, C.POINTER(L.SceneDesc)]),
+            "hko_set_noise": (_I, [_P, _P]),
+            "hko_prepass_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
+            "hko_light_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
+            "hko_post_process_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
+            "hko_render_frame": (_I, [_P, C.POINTER(L.FrameInputs)]),
+            "hko_run_pass": (_I, [_P, C.POINTER(L.FrameInputs), _I, _I]),
+            "hko_readback": (_I, [_P, _I, _P, _SZ]),
+            "hko_upload_state": (_I, [_P, _I, _P, _SZ]),
+            "hko_trace_rays": (_I, [_P, _P, _SZ, _P]),
+            "hko_get_stats": (_I, [_P, C.POINTER(L.FrameStats)]),
+            "hko_last_error": (C.c_char_p, [_P]),
+            "hko_math_exp2": (C.c_float, [C.c_float]),
+            "hko_math_exp": (C.c_float, [C.c_float]),
+            "hko_math_sincos": (None, [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+            "hko_math_pack2x16float": (_U32, [C.c_float, C.c_float]),
+            "hko_math_f16_to_f32": (C.c_float, [C.c_uint16]),
+            "hko_math_pack4x8snorm": (_U32, [C.c_float] * 4),
+            "hko_math_pack2x16unorm": (_U32, [C.c_float, C.c_float]),
+            "hko_math_hash": (_U32, [_U32]),
+            "hko_math_normal_basis": (None, [_P, _P]),
+            "hko_pack_reservoir_roundtrip": (None, [_P, _P]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(_lib, name)
+            fn.restype, fn.argtypes = res, args
+    return _lib
+
+
+PASS_ALBEDO, PASS_DIRECT, PASS_EMISSIVE, PASS_EMISSIVE_SPATIAL, PASS_INDIRECT, PASS_INDIRECT_SPATIAL, PASS_DENOISE, PASS_TONE_MAPPING = range(8)
+
+
+class Oracle:
+    def __init__(self, width, height, noise, threads=None):
+        self.width, self.height = width, height
+        p = _P()
+        threads = threads or os.cpu_count() or 1
+        self.threads = threads
+        rc = lib().hko_context_create(C.byref(p), width, height, threads)
+        assert rc == 0
+        self.ctx = p
+        noise = np.ascontiguousarray(noise, np.uint8)
+        assert lib().hko_set_noise(self.ctx, noise.ctypes.data) == 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            lib().hko_context_destroy(self.ctx)
+            self.ctx = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"oracle error {rc}: {lib().hko_last_error(self.ctx).decode()}")
+
+    def upload_scene_desc(self, desc): self._check(lib().hko_scene_upload(self.ctx, C.byref(desc)))
+    def reset_temporal_state(self): self._check(lib().hko_reset_temporal_state(self.ctx))
+    def prepass(self, inputs): self._check(lib().hko_prepass_run(self.ctx, C.byref(inputs)))
+    def light(self, inputs): self._check(lib().hko_light_run(self.ctx, C.byref(inputs)))
+    def post_process(self, inputs): self._check(lib().hko_post_process_run(self.ctx, C.byref(inputs)))
+    def render_frame(self, inputs): self._check(lib().hko_render_frame(self.ctx, C.byref(inputs)))
+    def run_pass(self, inputs, which, arg=0): self._check(lib().hko_run_pass(self.ctx, C.byref(inputs), which, arg))
+
+    def readback(self, which):
+        from bevy_hikari_b200.plugin import view_plane
+        bpp, dt, comps = L.OUT_FORMATS[which]
+        raw = np.empty(self.width * self.height * bpp, np.uint8)
+        self._check(lib().hko_readback(self.ctx, which, raw.ctypes.data, raw.size))
+        return view_plane(raw, which, self.height, self.width)
+
+    def upload_state(self, which, array):
+        a = np.ascontiguousarray(array)
+        self._check(lib().hko_upload_state(self.ctx, which, a.ctypes.data, a.nbytes))
+
+    def trace_rays(self, rays):
+        rays = np.ascontiguousarray(rays, L.RAY)
+        hits = np.zeros(len(rays), L.HIT)
+        self._check(lib().hko_trace_rays(self.ctx, rays.ctypes.data, len(rays), hits.ctypes.data))
+        return hits
+
+    def stats(self):
+        s = L.FrameStats()
+        self._check(lib().hko_get_stats(self.ctx, C.byref(s)))
+        return s
