@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — one "step" = one frame of the hot path (prepass rays + light passes + denoise + tone mapping).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cornell_1080p] [--impl ours|reference]
+
+N = 1: the workload is BASELINE.json configs[1] — cornell 1920x1080, 2 bounces, ReSTIR temporal + spatial (emissive
+and indirect), denoise on — unless --config says otherwise.  N > 1 (launched by torchrun, one rank per GPU): the frame is
+split in N horizontal row bands; every rank renders its band + ghost rows with no data-path exchange,
+then ONE NCCL all-gather assembles the tone-mapped frame on every rank ("scaling": "strong" — total work is fixed).
+
+Timing: W warm-up frames, then exactly K frames bracketed by barrier + torch.cuda.synchronize(), CUDA events on the
+context's stream (which is torch's current stream), MAX over ranks.  Frames continue the temporal sequence
+(frame numbers W+1 .. W+K), so validation frames (every 3rd / 5th) are inside the timed region.  The per-frame working
+set (~880 B/px of planes = 1.8 GB at 1080p) is far larger than the 126 MB L2, so no explicit flush is needed.
+
+value      Mrays/s, device-resident: rays = traverse_top calls + stand-alone traverse_bottom calls of the light passes
+           (SURVEY.md 8(d)), counted exactly by replaying the same frames with the counting kernel variants AFTER the timed
+           region (counters are compiled out of the timed kernels); primary (G-buffer) rays are reported separately.
+e2e        same metric through the public plugin API with host buffers: HikariPlugin.run_frame(settings, view, lights)
+           (host structs -> kernel parameters) + read-back of the tone-mapped band into pinned host memory every frame.
+roofline   dominant kernel (largest share of the frame): algorithmic bytes/pixel x pixels / its mean
+           CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference: the oracle (CPU restatement of the reference's WGSL; the reference itself is Rust + wgpu
+           and cannot be built offline) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic bytes per render pixel: unique compulsory traffic of each reference pass
+BYTES_PER_PIXEL = {"gbuffer": 52 + 52, "direct": 184, "emissive": 184, "emissive_spatial": 244, "indirect": 184,
+                   "indirect_spatial": 244, "demodulation": 32, "denoise_0": 56, "denoise_1": 56, "denoise_2": 56,
+                   "denoise_3": 56 + 8, "tone_mapping": 32}
+PER_SIGNAL = {"demodulation", "denoise_0", "denoise_1", "denoise_2", "denoise_3"}   # x signals (fused over signals here)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def band(height, rank, world):
+    """rows [r0, r1) owned by `rank`: contiguous bands, equal sizes (the all-gather needs equal contributions)."""
+    assert height % world == 0, "image height must be divisible by the number of GPUs"
+    rows = height // world
+    return rank * rows, (rank + 1) * rows
+
+
+def make_bench(config):
+    from bevy_hikari_b200 import plugin, scenes
+    cfg = scenes.CONFIGS[config]
+    scene = scenes.SCENE_BUILDERS[cfg["scene"]]()
+    world = scene.populate(plugin.World())
+    W, H = cfg["width"], cfg["height"]
+    view, pview, lights = scene.view_inputs(W, H)
+    settings = scenes.config_settings(config)
+    return cfg, scene, world, W, H, view, pview, lights, settings
+
+
+def config_json(config, cfg, settings, world_size):
+    return {"workload": f"{config}: {cfg['scene']} {cfg['width']}x{cfg['height']}, {settings.indirect_bounces} bounces, "
+                        f"temporal+{'emissive+' if settings.emissive_spatial_reuse else ''}"
+                        f"{'indirect ' if settings.indirect_spatial_reuse else ''}spatial ReSTIR, denoise {'on' if settings.denoise else 'off'}",
+            "scene": cfg["scene"], "width": cfg["width"], "height": cfg["height"], "indirect_bounces": int(settings.indirect_bounces),
+            "emissive_spatial_reuse": int(settings.emissive_spatial_reuse), "indirect_spatial_reuse": int(settings.indirect_spatial_reuse),
+            "denoise": int(settings.denoise), "upscale": "SmaaTu4x{ratio:1.0}", "taa": "None",
+            "parallelism": f"row-bands x{world_size}" if world_size > 1 else "single GPU",
+            "l2": "per-frame working set (>1 GB of planes) exceeds L2; no explicit flush"}
+
+
+# ================================================================================================== ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bevy_hikari_b200 import layout as L
+    from bevy_hikari_b200 import plugin
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world_size == args.gpus or world_size == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    cfg, scene, world, W, H, view, pview, lights, settings = make_bench(args.config)
+    r0, r1 = band(H, rank, world_size)
+    stream = torch.cuda.current_stream()
+    dev = plugin.HikariPlugin(W, H, cuda_device=local_rank, row_begin=r0, row_end=r1, cuda_stream=stream.cuda_stream)
+    dev.upload_scene(world)
+    own_px = (r1 - r0) * W
+
+    # the context's tone-mapped band as a torch tensor (zero copy) for the all-gather
+    ptr, nbytes = dev.output_device_pointer()
+
+    class _Ext:  # __cuda_array_interface__ view of the context-owned buffer
+        __cuda_array_interface__ = {"shape": (nbytes // 2,), "typestr": "<f2", "data": (ptr, False), "version": 3}
+    tile = torch.as_tensor(_Ext(), device=f"cuda:{local_rank}")
+    frame_buf = torch.empty(world_size * tile.numel(), dtype=torch.float16, device=tile.device) if world_size > 1 else None
+    pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world_size == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=tile.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(vals):
+        if world_size == 1:
+            return vals
+        t = torch.tensor(vals, dtype=torch.float64, device=tile.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    W_, K = args.warmup, args.steps
+
+    def frame_inputs(n):
+        return plugin.make_frame_inputs(settings, n, view, pview, lights)
+
+    # ---------------------------------------------------------------- device-resident arm ("value")
+    dev.reset_temporal_state()
+    dev.set_profiling(False, True)        # per-kernel CUDA events on, ray counters off
+    inputs = [frame_inputs(n) for n in range(1, W_ + K + 1)]
+    for n in range(W_):
+        dev.render_frame(inputs[n])
+        if world_size > 1:
+            dist.all_gather_into_tensor(frame_buf, tile)
+    kernel_ms = np.zeros(len(L.KERNEL_NAMES))
+    launches = 0
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for n in range(W_, W_ + K):
+        dev.render_frame(inputs[n])
+        if world_size > 1:
+            dist.all_gather_into_tensor(frame_buf, tile)
+        # stats of the PREVIOUS frame would need a sync; collect per-kernel times after the loop from a replay below
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    ms_per_step = ms_total / K
+
+    # per-kernel times: same frames again (timed per frame, synchronised per frame so events can be read)
+    dev.reset_temporal_state()
+    for n in range(W_ + K):
+        dev.render_frame(inputs[n])
+        if n >= W_:
+            st = dev.stats()
+            kernel_ms += np.array(st.ms_kernel[:len(L.KERNEL_NAMES)])
+            launches += st.kernel_launches
+    kernel_ms /= K
+    launches_per_frame = launches // K + (1 if world_size > 1 else 0)
+
+    # exact ray counts of the timed frames: replay with the counting kernel variants
+    dev.reset_temporal_state()
+    dev.set_profiling(True, False)
+    rays = np.zeros(3)
+    for n in range(W_ + K):
+        dev.render_frame(inputs[n])
+        if n >= W_:
+            st = dev.stats()
+            rays += np.array([st.primary_rays, st.tlas_rays, st.blas_rays], dtype=np.float64)
+    rays = np.array(reduce_sum(list(rays)))
+    light_rays = rays[1] + rays[2]
+    value = light_rays / (ms_total * 1e-3) / 1e6
+
+    # ---------------------------------------------------------------- end-to-end arm ("e2e")
+    dev.set_profiling(False, False)
+    dev.reset_temporal_state()
+    dev.frame_counter = 0
+    h2d = ctypes.sizeof(L.FrameInputs)
+    for n in range(W_):
+        dev.run_frame(settings, view, pview, lights)
+        dev.readback_into(L.OUT_TONE_MAPPED, pinned.data_ptr(), nbytes)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for n in range(K):
+        dev.run_frame(settings, view, pview, lights)                      # host structs -> kernel parameters
+        dev.readback_into(L.OUT_TONE_MAPPED, pinned.data_ptr(), nbytes)   # D2H of the band into pinned memory (syncs)
+    e1.record(stream)
+    barrier()
+    e2e_ms = reduce_max(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+    e2e_value = light_rays / (e2e_ms * 1e-3) / 1e6
+
+    if rank != 0:
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    peak, peak_kind = peaks()
+    signals = 3 if settings.indirect_bounces else 2
+    ran = [(kernel_ms[i], name) for i, name in enumerate(L.KERNEL_NAMES) if kernel_ms[i] > 0]
+    dom_ms, dom = max(ran)
+    rows_launched = {"gbuffer": 36, "direct": 36, "emissive": 36, "indirect": 36, "emissive_spatial": 16, "indirect_spatial": 16,
+                     "demodulation": 15, "denoise_0": 7, "denoise_1": 3, "denoise_2": 1, "denoise_3": 0, "tone_mapping": 0}
+    def launch_pixels(name):
+        g = rows_launched[name]
+        lo, hi = max(0, r0 - g), min(H, r1 + g)
+        return (hi - lo) * W
+    bpp = BYTES_PER_PIXEL[dom] * (signals if dom in PER_SIGNAL else 1)
+    if dom == "denoise_3":
+        bpp += BYTES_PER_PIXEL["tone_mapping"]      # fused tone mapping
+    alg_bytes = bpp * launch_pixels(dom)
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    frame_bpp = sum(BYTES_PER_PIXEL[name] * (signals if name in PER_SIGNAL else 1) for _, name in ran)
+    if kernel_ms[L.KERNEL_NAMES.index("tone_mapping")] == 0:
+        frame_bpp += BYTES_PER_PIXEL["tone_mapping"]
+    frame_achieved = frame_bpp * W * H / (ms_per_step * 1e-3) / 1e9
+
+    out = {
+        "metric": "Mrays/s", "value": round(value, 3), "unit": "Mrays/s", "n_gpus": world_size, "steps": K, "warmup": W_,
+        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "reference asset cornell.glb + blue-noise seed (no synthetic inputs exist for this path)",
+        "config": config_json(args.config, cfg, settings, world_size),
+        "rays_per_frame": {"light_tlas": rays[1] / K, "light_blas": rays[2] / K, "primary": rays[0] / K},
+        "fps": round(1e3 / ms_per_step, 2),
+        "e2e": {"value": round(e2e_value, 3), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / K, 5),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": nbytes},
+        "gpu_launches": int(launches_per_frame * K),
+        "kernel_ms": {name: round(float(kernel_ms[i]), 5) for i, name in enumerate(L.KERNEL_NAMES) if kernel_ms[i] > 0},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 5), "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                     "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "frame": {"bytes_per_pixel": frame_bpp, "achieved": round(frame_achieved, 2),
+                               "frac": round(frame_achieved / peak, 5)}},
+        "clocks": clocks,
+    }
+    if world_size == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_sample(args.config, seconds_budget=25.0)
+    print(json.dumps(out), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+# ============================================================================================ CPU arms
+def oracle_for(config, width, height, threads=None):
+    from bevy_hikari_b200 import plugin, scenes
+    from oracle import oracle
+    cfg = scenes.CONFIGS[config]
+    scene = scenes.SCENE_BUILDERS[cfg["scene"]]()
+    world = scene.populate(plugin.World())       # host-side scene preparation only; no CUDA call
+    view, pview, lights = scene.view_inputs(width, height)
+    settings = scenes.config_settings(config)
+    orc = oracle.Oracle(width, height, plugin.load_noise(), threads)
+    orc.upload_scene_desc(world.scene_desc())
+    return orc, settings, view, pview, lights
+
+
+def cpu_baseline_sample(config, seconds_budget):
+    """The oracle on the host cores, on a bounded sample: frames 1.. of the same scene / settings at 1/4 x 1/4 of the
+    resolution (rays per pixel do not depend on resolution), as many frames as fit in the budget (at least 2)."""
+    from bevy_hikari_b200 import plugin, scenes
+    cfg = scenes.CONFIGS[config]
+    w, h = cfg["width"] // 4, cfg["height"] // 4
+    orc, settings, view, pview, lights = oracle_for(config, w, h)
+    rays, frames, t_total = 0.0, 0, 0.0
+    n = 1
+    while frames < 2 or (t_total < seconds_budget and frames < 64):
+        inp = plugin.make_frame_inputs(settings, n, view, pview, lights)
+        t0 = time.perf_counter()
+        orc.render_frame(inp)
+        dt = time.perf_counter() - t0
+        st = orc.stats()
+        if n > 1:   # frame 1 is warm-up (page faults)
+            rays += st.tlas_rays + st.blas_rays
+            t_total += dt
+            frames += 1
+        n += 1
+    return {"value": round(rays / t_total / 1e6, 4), "unit": "Mrays/s", "cores": orc.threads, "kind": "port",
+            "ms_per_frame_sample": round(t_total / frames * 1e3, 2),
+            "sample": f"{frames} frames of {config} at {w}x{h} (1/16 of the pixels, same scene/settings/frame sequence), "
+                      f"oracle = C++/OpenMP restatement of the reference WGSL; the reference (Rust+wgpu) cannot be built offline"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bevy_hikari_b200 import plugin, scenes
+    cfg = scenes.CONFIGS[args.config]
+    w, h = cfg["width"] // 4, cfg["height"] // 4
+    orc, settings, view, pview, lights = oracle_for(args.config, w, h)
+    W_, K = args.warmup, args.steps
+    for n in range(1, W_ + 1):
+        orc.render_frame(plugin.make_frame_inputs(settings, n, view, pview, lights))
+    orc.stats()
+    rays = 0.0
+    t0 = time.perf_counter()
+    for n in range(W_ + 1, W_ + K + 1):
+        orc.render_frame(plugin.make_frame_inputs(settings, n, view, pview, lights))
+    dt = time.perf_counter() - t0
+    st = orc.stats()
+    rays = st.tlas_rays + st.blas_rays
+    value = rays / dt / 1e6
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = (f"each step = one frame of {args.config} at {w}x{h} (1/16 of the pixels; rays/pixel are resolution independent), "
+              f"CPU restatement of the reference WGSL (oracle/hk_oracle.cpp, OpenMP); the reference's own wgpu path needs "
+              f"rustc + a Vulkan ICD, neither exists offline")
+    out = {"impl": "reference", "metric": "Mrays/s", "value": round(value, 4), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": K,
+           "warmup": W_, "ms_per_step": round(dt / K * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "reference asset cornell.glb + blue-noise seed",
+           "config": config_json(args.config, cfg, settings, world_size),
+           "cpu_baseline": {"value": round(value, 4), "unit": "Mrays/s", "cores": orc.threads, "kind": "port", "sample": sample},
+           "e2e": {"value": round(value, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--config", default="cornell_1080p")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,8 @@ struct hk_context {
     Counters* counters = nullptr;
     bool count_rays = false, time_passes = false, keep_intermediates = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t kev[HK_K_COUNT][2] = {};   // per-kernel begin/end
+    bool kran[HK_K_COUNT] = {};
     hk_frame_stats stats{};
     uint32_t launches = 0;
     std::string error;
@@ -139,6 +141,10 @@ int hk_context_create(hk_context** out, int cuda_device, uint32_t width, uint32_
     if (rc == HK_OK)
         for (int i = 0; i < 4; ++i)
             if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = set_error(c, HK_ERR_CUDA, "cudaEventCreate");
+    if (rc == HK_OK)
+        for (int i = 0; i < HK_K_COUNT; ++i)
+            for (int j = 0; j < 2; ++j)
+                if (cudaEventCreate(&c->kev[i][j]) != cudaSuccess) rc = set_error(c, HK_ERR_CUDA, "cudaEventCreate");
     if (rc != HK_OK) {
         g_create_error = c->error;
         hk_context_destroy(c);
@@ -157,6 +163,8 @@ void hk_context_destroy(hk_context* ctx) {
     if (ctx->noise) cudaFree(ctx->noise);
     if (ctx->counters) cudaFree(ctx->counters);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < HK_K_COUNT; ++i)
+        for (int j = 0; j < 2; ++j) if (ctx->kev[i][j]) cudaEventDestroy(ctx->kev[i][j]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -304,39 +312,45 @@ static int check_launch(hk_context* ctx) {
     return HK_OK;
 }
 
+struct KernelTimer {  // brackets one launch with events when pass timing is on
+    hk_context* c; int k;
+    KernelTimer(hk_context* ctx, int kernel) : c(ctx), k(kernel) {
+        c->launches += 1;
+        if (c->time_passes) { cudaEventRecord(c->kev[k][0], c->stream); c->kran[k] = true; }
+    }
+    ~KernelTimer() { if (c->time_passes) cudaEventRecord(c->kev[k][1], c->stream); }
+};
+
 static int run_prepass(hk_context* ctx, KParams& P) {
     rows(ctx, P, GHOST_TEMPORAL);
-    hk_launch_gbuffer(P, ctx->count_rays, ctx->stream);
-    ctx->launches += 1;
+    { KernelTimer t(ctx, HK_K_GBUFFER); hk_launch_gbuffer(P, ctx->count_rays, ctx->stream); }
     return check_launch(ctx);
 }
 static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, light.rs:645-699 (albedo is fused in the prepass)
     const hk_frame_uniform& f = P.in.frame;
     rows(ctx, P, GHOST_TEMPORAL);
-    hk_launch_direct(P, false, ctx->count_rays, ctx->stream);
-    hk_launch_direct(P, true, ctx->count_rays, ctx->stream);
-    ctx->launches += 2;
-    if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); hk_launch_spatial(P, true, ctx->stream); ctx->launches += 1; }
+    { KernelTimer t(ctx, HK_K_DIRECT); hk_launch_direct(P, false, ctx->count_rays, ctx->stream); }
+    { KernelTimer t(ctx, HK_K_EMISSIVE); hk_launch_direct(P, true, ctx->count_rays, ctx->stream); }
+    if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_EMISSIVE_SPATIAL); hk_launch_spatial(P, true, ctx->stream); }
     rows(ctx, P, GHOST_TEMPORAL);
-    hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
-    ctx->launches += 1;
-    if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); hk_launch_spatial(P, false, ctx->stream); ctx->launches += 1; }
+    { KernelTimer t(ctx, HK_K_INDIRECT); hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream); }
+    if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); hk_launch_spatial(P, false, ctx->stream); }
     return check_launch(ctx);
 }
 static int run_post(hk_context* ctx, KParams& P, bool fuse) {  // PostProcessNode::run, post_process.rs:1190-1234
     if (P.in.denoise) {
         const int signals = (P.in.frame.indirect_bounces == 0) ? 2 : 3;  // post_process.rs:949-954
-        rows(ctx, P, GHOST_DEMOD); hk_launch_demodulation(P, signals, ctx->stream);
-        rows(ctx, P, GHOST_L0); hk_launch_denoise_level(P, 0, signals, false, false, ctx->stream);
-        rows(ctx, P, GHOST_L1); hk_launch_denoise_level(P, 1, signals, false, false, ctx->stream);
-        rows(ctx, P, GHOST_L2); hk_launch_denoise_level(P, 2, signals, false, false, ctx->stream);
-        rows(ctx, P, 0); hk_launch_denoise_level(P, 3, signals, fuse, !fuse || ctx->keep_intermediates, ctx->stream);
-        ctx->launches += 5;
-        if (!fuse) { hk_launch_tone_mapping(P, ctx->stream); ctx->launches += 1; }
+        { rows(ctx, P, GHOST_DEMOD); KernelTimer t(ctx, HK_K_DEMODULATION); hk_launch_demodulation(P, signals, ctx->stream); }
+        { rows(ctx, P, GHOST_L0); KernelTimer t(ctx, HK_K_DENOISE_0); hk_launch_denoise_level(P, 0, signals, false, false, ctx->stream); }
+        { rows(ctx, P, GHOST_L1); KernelTimer t(ctx, HK_K_DENOISE_1); hk_launch_denoise_level(P, 1, signals, false, false, ctx->stream); }
+        { rows(ctx, P, GHOST_L2); KernelTimer t(ctx, HK_K_DENOISE_2); hk_launch_denoise_level(P, 2, signals, false, false, ctx->stream); }
+        { rows(ctx, P, 0); KernelTimer t(ctx, HK_K_DENOISE_3);
+          hk_launch_denoise_level(P, 3, signals, fuse, !fuse || ctx->keep_intermediates, ctx->stream); }
+        if (!fuse) { KernelTimer t(ctx, HK_K_TONE_MAPPING); hk_launch_tone_mapping(P, ctx->stream); }
     } else {
         rows(ctx, P, 0);
+        KernelTimer t(ctx, HK_K_TONE_MAPPING);
         hk_launch_tone_mapping(P, ctx->stream);
-        ctx->launches += 1;
     }
     return check_launch(ctx);
 }
@@ -359,6 +373,7 @@ int hk_post_process_run(hk_context* ctx, const hk_frame_inputs* in) {
 int hk_render_frame(hk_context* ctx, const hk_frame_inputs* in) {
     KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
     ctx->launches = 0;
+    for (int i = 0; i < HK_K_COUNT; ++i) ctx->kran[i] = false;
     const bool t = ctx->time_passes;
     if (ctx->count_rays) HK_CUDA(cudaMemsetAsync(ctx->counters, 0, sizeof(Counters), ctx->stream));
     if (t) cudaEventRecord(ctx->ev[0], ctx->stream);
@@ -405,6 +420,8 @@ int hk_get_stats(hk_context* ctx, hk_frame_stats* out) {
         cudaEventElapsedTime(&out->ms_light, ctx->ev[1], ctx->ev[2]);
         cudaEventElapsedTime(&out->ms_post_process, ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&out->ms_total, ctx->ev[0], ctx->ev[3]);
+        for (int i = 0; i < HK_K_COUNT; ++i)
+            if (ctx->kran[i]) cudaEventElapsedTime(&out->ms_kernel[i], ctx->kev[i][0], ctx->kev[i][1]);
     }
     out->kernel_launches = ctx->launches;
     return HK_OK;

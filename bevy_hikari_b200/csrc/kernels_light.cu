@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__
             P.planes.albedo[idx] = make_uint2(alb.x, alb.y);
         }
     }
+    if (y < P.band.r0 || y >= P.band.r1) n_primary = 0;   // ghost rows are redundant work: not counted
     flush_counters<COUNT>(P, n_primary, 0u, 0u);
 }
 
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_direct(const __grid_constant__ 
             P.planes.render[SIGNAL][idx] = make_uint2(o.x, o.y);
         }
     }
+    if (y < P.band.r0 || y >= P.band.r1) { n_tlas = 0; n_blas = 0; }   // ghost rows are redundant work: not counted
     flush_counters<COUNT>(P, 0u, n_tlas, n_blas);
 }
 
@@ -433,6 +435,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_indirect(const __grid_constant_
             P.planes.render[2][idx] = make_uint2(o.x, o.y);
         }
     }
+    if (y < P.band.r0 || y >= P.band.r1) { n_tlas = 0; n_blas = 0; }   // ghost rows are redundant work: not counted
     flush_counters<COUNT>(P, 0u, n_tlas, n_blas);
 }
 

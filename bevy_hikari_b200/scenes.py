@@ -137,11 +137,20 @@ def city():
             m[k] = 0xFFFFFFFF
         return m
 
-    # ground (city.rs: plane size 1 scaled 100, base colour 0.5 grey, perceptual_roughness 0.5) and the emissive sphere
-    meshes.append(_plane_mesh(1.0)); mat_list.append(std_material(base=(0.5, 0.5, 0.5, 1.0), rough=0.5))
+    # ground: shape::Plane::default() scaled (100,1,100), base colour rgb(0.8,0.7,0.6), perceptual_roughness 0.9 (city.rs:62-77)
+    meshes.append(_plane_mesh(1.0)); mat_list.append(std_material(base=(0.8, 0.7, 0.6, 1.0), rough=0.9))
     inst_mesh.append(0); inst_mat.append(0); inst_xf.append(_translation(0, 0, 0, (100.0, 1.0, 100.0)))
-    meshes.append(_uv_sphere_mesh(0.5, 36, 18)); mat_list.append(std_material(base=(1, 1, 1, 1), emissive=(1.0, 1.0, 1.0, 0.5)))
-    inst_mesh.append(1); inst_mat.append(1); inst_xf.append(_translation(0.0, 1.0, 0.0))
+    # emissive UV sphere r=0.5 at (0,1,0) rotated -90 deg about X; earth_daymap.jpg is both base-colour and emissive
+    # texture, emissive rgba(1,1,1,0.5) (city.rs:80-100).  The JPEG is shipped down-sampled to 512x256.
+    earth = np.load(os.path.join(SCENES, "earth.npz"))["rgba"]
+    textures.append({"rgba": earth, "address_mode_u": 1, "address_mode_v": 1, "filter_linear": 1, "srgb": 1})  # bevy default sampler: clamp
+    sphere_mat = std_material(base=(1, 1, 1, 1), emissive=(1.0, 1.0, 1.0, 0.5))
+    sphere_mat["base_color_texture"] = 0
+    sphere_mat["emissive_texture"] = 0
+    meshes.append(_uv_sphere_mesh(0.5, 36, 18)); mat_list.append(sphere_mat)
+    rot = np.zeros((4, 4), F)   # Quat::from_rotation_x(-pi/2): columns (1,0,0), (0,0,-1), (0,1,0)
+    rot[0, 0] = 1.0; rot[1, 2] = -1.0; rot[2, 1] = 1.0; rot[3, :] = (0.0, 1.0, 0.0, 1.0)
+    inst_mesh.append(1); inst_mat.append(1); inst_xf.append(rot.reshape(16))
 
     def add_house(name, positions):
         hm, hmat, htex, him, himat, hixf = _load_npz(name, texture_offset=len(textures))

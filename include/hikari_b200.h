@@ -110,7 +110,21 @@ typedef struct hk_frame_stats {
     float ms_prepass, ms_light, ms_post_process, ms_total;   /* CUDA-event times of the last frame, if enabled */
     uint32_t kernel_launches;    /* kernels launched by the last hk_render_frame */
     uint32_t _pad;
+    float ms_kernel[16];         /* per-kernel CUDA-event times of the last hk_render_frame, index = HK_K_*; 0 = not run */
 } hk_frame_stats;
+
+enum {   /* indices into hk_frame_stats.ms_kernel */
+    HK_K_GBUFFER = 0,            /* primary rays + albedo (replaces the raster prepass and full_screen_albedo) */
+    HK_K_DIRECT = 1,             /* direct_lit, sun */
+    HK_K_EMISSIVE = 2,           /* direct_lit, EMISSIVE_LIT */
+    HK_K_EMISSIVE_SPATIAL = 3,   /* spatial_reuse, EMISSIVE_LIT */
+    HK_K_INDIRECT = 4,           /* indirect_lit_ambient */
+    HK_K_INDIRECT_SPATIAL = 5,   /* spatial_reuse */
+    HK_K_DEMODULATION = 6,
+    HK_K_DENOISE_0 = 7, HK_K_DENOISE_1 = 8, HK_K_DENOISE_2 = 9, HK_K_DENOISE_3 = 10,   /* level 3 includes tone mapping when fused */
+    HK_K_TONE_MAPPING = 11,
+    HK_K_COUNT = 12
+};
 
 typedef struct hk_ray {   /* test hook input: a world-space ray exactly as traverse_top takes it */
     float origin[3];    float max_distance;

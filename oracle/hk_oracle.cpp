@@ -18,8 +18,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <omp.h>
+
 #include <algorithm>
-#include <atomic>
 #include <string>
 #include <vector>
 
@@ -105,7 +106,9 @@ struct hko_context {
     std::vector<uvec2> tone_mapping_output;
     // per-frame
     hk_frame_inputs in;
-    std::atomic<uint64_t> primary_rays{0}, tlas_rays{0}, blas_rays{0};
+    struct alignas(64) RayCounters { uint64_t primary = 0, tlas = 0, blas = 0; };
+    std::vector<RayCounters> rays;   // one slot per OpenMP thread (no shared atomics on the timed path)
+    RayCounters& cnt() { return rays[(size_t)omp_get_thread_num()]; }
     std::string error;
     int threads = 0;
 };
@@ -459,7 +462,7 @@ LightCandidate select_light_candidate(Ctx& c, vec4 rand, vec3 position, vec3 nor
 
         candidate.direction = ray.direction;
         bool front = dot(candidate.direction, normal) > 0.0f;
-        if (front) c.blas_rays.fetch_add(1, std::memory_order_relaxed);
+        if (front) c.cnt().blas += 1;
         if (front && traverse_bottom(c, hit, r, emissive_instance.mesh, 0.0f)) {
             hit.instance_index = emissive.instance;
             info = hit_info(c, ray, hit);
@@ -723,7 +726,7 @@ void pass_prepass(Ctx& c) {
     for_pixels(c, c.W, c.H, [&](int x, int y) {
         size_t idx = (size_t)y * c.W + x;
         Ray ray = primary_ray(c, (float)x, (float)y, jitter_ndc);
-        c.primary_rays.fetch_add(1, std::memory_order_relaxed);
+        c.cnt().primary += 1;
         Hit hit = traverse_top(c, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
         if (hit.instance_index == U32_MAX) {
             c.position[idx] = v4(0.0f); c.normal[idx] = 0u; c.depth_gradient[idx] = v2(0, 0);
@@ -878,7 +881,7 @@ void pass_direct_lit(Ctx& c, int signal) {  // light.wgsl:1044-1261
             trace_condition = trace_condition && candidate.p > 0.0f;
             if (EMISSIVE_LIT) trace_condition = trace_condition && candidate.emissive_instance != DONT_SAMPLE_EMISSIVE;
             if (trace_condition) {
-                c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                c.cnt().tlas += 1;
                 hit = traverse_top(c, ray, candidate.max_distance, candidate.min_distance, candidate.emissive_instance);
                 occlude_hit_info(ray, hit, info);
                 if (EMISSIVE_LIT) s.radiance = input_radiance(c, ray, info, false, candidate.emissive_instance, false);
@@ -901,7 +904,7 @@ void pass_direct_lit(Ctx& c, int signal) {  // light.wgsl:1044-1261
             trace_condition = trace_condition && candidate.p > 0.0f;
             if (EMISSIVE_LIT) trace_condition = trace_condition && candidate.emissive_instance != DONT_SAMPLE_EMISSIVE;
             if (trace_condition) {
-                c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                c.cnt().tlas += 1;
                 hit = traverse_top(c, ray, candidate.max_distance, candidate.min_distance, candidate.emissive_instance);
                 occlude_hit_info(ray, hit, info);
                 if (EMISSIVE_LIT) validate_radiance = input_radiance(c, ray, info, false, candidate.emissive_instance, false);
@@ -992,7 +995,7 @@ void pass_indirect(Ctx& c) {  // light.wgsl:1263-1498
                 ray.origin = xyz(bounce_sample.visible_position) + bounce_sample.visible_normal * RAY_BIAS;
                 ray.direction = mul(normal_basis(bounce_sample.visible_normal), xyz(rand_sample));
                 ray.inv_direction = 1.0f / ray.direction;
-                c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                c.cnt().tlas += 1;
                 hit = traverse_top(c, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
                 info = hit_info(c, ray, hit);
                 if (n == 0u) {
@@ -1014,7 +1017,7 @@ void pass_indirect(Ctx& c) {  // light.wgsl:1263-1498
                         ray.origin = xyz(bounce_sample.sample_position) + bounce_sample.sample_normal * RAY_BIAS;
                         ray.direction = candidate.direction;
                         ray.inv_direction = 1.0f / ray.direction;
-                        c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                        c.cnt().tlas += 1;
                         hit = traverse_top(c, ray, candidate.max_distance, candidate.min_distance, candidate.emissive_instance);
                         occlude_hit_info(ray, hit, info);
                         vec4 in_radiance = input_radiance(c, ray, info, sample_directional, candidate.emissive_instance, false);
@@ -1041,7 +1044,7 @@ void pass_indirect(Ctx& c) {  // light.wgsl:1263-1498
             ray.origin = xyz(s.visible_position) + s.visible_normal * RAY_BIAS;
             ray.direction = mul(normal_basis(s.visible_normal), xyz(rand_sample));
             ray.inv_direction = 1.0f / ray.direction;
-            c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+            c.cnt().tlas += 1;
             hit = traverse_top(c, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
             info = hit_info(c, ray, hit);
             s.sample_position = info.position;
@@ -1058,7 +1061,7 @@ void pass_indirect(Ctx& c) {  // light.wgsl:1263-1498
                     ray.origin = xyz(s.sample_position) + s.sample_normal * RAY_BIAS;
                     ray.direction = candidate.direction;
                     ray.inv_direction = 1.0f / ray.direction;
-                    c.tlas_rays.fetch_add(1, std::memory_order_relaxed);
+                    c.cnt().tlas += 1;
                     hit = traverse_top(c, ray, candidate.max_distance, candidate.min_distance, candidate.emissive_instance);
                     occlude_hit_info(ray, hit, info);
                     vec4 in_radiance = input_radiance(c, ray, info, sample_directional, candidate.emissive_instance, false);
@@ -1387,6 +1390,7 @@ int hko_context_create(hko_context** out, uint32_t width, uint32_t height, int t
     c->W = c->RW = (int)width;
     c->H = c->RH = (int)height;
     c->threads = threads > 0 ? threads : 1;
+    c->rays.assign((size_t)c->threads + 1, hko_context::RayCounters());
     size_t n = (size_t)width * height;
     c->position.assign(n, v4(0.0f)); c->normal.assign(n, 0u); c->depth_gradient.assign(n, v2(0, 0));
     c->instance_material.assign(n, v2(0, 0)); c->velocity_uv.assign(n, v4(0.0f));
@@ -1528,9 +1532,10 @@ int hko_trace_rays(hko_context* c, const hk_ray* rays, size_t n, hk_hit* hits) {
 }
 int hko_get_stats(hko_context* c, hk_frame_stats* out) {
     memset(out, 0, sizeof(*out));
-    out->primary_rays = c->primary_rays.exchange(0);
-    out->tlas_rays = c->tlas_rays.exchange(0);
-    out->blas_rays = c->blas_rays.exchange(0);
+    for (auto& r : c->rays) {
+        out->primary_rays += r.primary; out->tlas_rays += r.tlas; out->blas_rays += r.blas;
+        r = hko_context::RayCounters();
+    }
     return HK_OK;
 }
 const char* hko_last_error(hko_context* c) { return c ? c->error.c_str() : ""; }

@@ -1,0 +1,71 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_libraries():
+    """Both shared libraries must exist; build them if a fresh checkout has not yet (nvcc cross-compiles on CPU)."""
+    from bevy_hikari_b200 import _ffi
+    from oracle import oracle
+    if not os.path.exists(_ffi.LIB_PATH) or not os.path.exists(oracle.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return True
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+class Bench:
+    """A scene + camera + settings, ready to feed both the oracle and the CUDA path with identical inputs."""
+
+    def __init__(self, scene_name, width, height, config=None, **settings):
+        from bevy_hikari_b200 import plugin, scenes
+        self.scene = scenes.SCENE_BUILDERS[scene_name]()
+        self.width, self.height = width, height
+        self.world = self.scene.populate(plugin.World())
+        self.view, self.previous_view, self.lights = self.scene.view_inputs(width, height)
+        if config:
+            self.settings = scenes.config_settings(config, **settings)
+        else:
+            kw = dict(taa=plugin.TAA_NONE, upscale_kind=plugin.UPSCALE_SMAA_TU4X, upscale_ratio=1.0)
+            kw.update(settings)
+            self.settings = plugin.HikariSettings(**kw)
+
+    def inputs(self, frame):
+        from bevy_hikari_b200 import plugin
+        return plugin.make_frame_inputs(self.settings, frame, self.view, self.previous_view, self.lights)
+
+    def oracle(self, threads=None):
+        from bevy_hikari_b200 import plugin
+        from oracle import oracle
+        o = oracle.Oracle(self.width, self.height, plugin.load_noise(), threads)
+        o.upload_scene_desc(self.world.scene_desc())
+        return o
+
+    def device(self, row_begin=0, row_end=None):
+        from bevy_hikari_b200 import plugin
+        p = plugin.HikariPlugin(self.width, self.height, 0, row_begin, row_end)
+        p.upload_scene(self.world)
+        return p
+
+
+@pytest.fixture(scope="session")
+def cornell64():
+    return Bench("cornell", 64, 64, config="cornell_256")

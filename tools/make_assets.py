@@ -236,6 +236,9 @@ def main():
     print("cornell: meshes", int(c["mesh_count"]), "instances", len(c["inst_mesh"]),
           "tris", sum(len(c[f"m{i}_idx"]) // 3 for i in range(int(c["mesh_count"]))))
     if "--city" in sys.argv:
+        from PIL import Image
+        earth = Image.open(f"{REF}/assets/models/Earth/earth_daymap.jpg").convert("RGBA").resize((512, 256), Image.BOX)
+        np.savez_compressed(f"{ROOT}/scenes/earth.npz", rgba=np.asarray(earth, np.uint8))
         for name, fn in (("house", "Big House.glb"), ("house2", "Big House 2.glb"), ("house3", "Big House 3.glb")):
             h = convert_gltf(f"{REF}/assets/models/Low Poly/{fn}", max_tex=512)
             np.savez_compressed(f"{ROOT}/scenes/{name}.npz", **h)
