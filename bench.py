@@ -147,7 +147,10 @@ def run_ours(args):
 
     cfg, scene, world, W, H, view, pview, lights, settings = make_bench(args.config)
     r0, r1 = band(H, rank, world_size)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream, made torch's current stream so that torch.cuda.Event, NCCL and the context's
+    # kernels are all ordered on the same stream (the legacy default stream has handle 0 = "create your own" in the C ABI)
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     dev = plugin.HikariPlugin(W, H, cuda_device=local_rank, row_begin=r0, row_end=r1, cuda_stream=stream.cuda_stream)
     dev.upload_scene(world)
     own_px = (r1 - r0) * W
@@ -307,7 +310,59 @@ def run_ours(args):
 
 
 # ============================================================================================ CPU arms
-def oracle_for(config, width, height, threads=None):
+def host_threads():
+    """usable host cores: affinity mask, capped by the cgroup CPU quota (os.cpu_count() reports the whole machine)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+_BEST_THREADS = {}
+
+
+def best_threads(config, width, height):
+    """The host may expose more hardware threads than the container can actually use; time one oracle frame at
+    n, n/2, n/4 ... threads and keep the fastest, so the CPU arm is reported at its best."""
+    key = (config, width, height)
+    if key in _BEST_THREADS:
+        return _BEST_THREADS[key]
+    from bevy_hikari_b200 import plugin
+    n = host_threads()
+    cands = []
+    while n >= 1:
+        cands.append(n)
+        if n <= 4:
+            break
+        n //= 2
+    best, best_t = cands[-1], float("inf")
+    for t in cands:
+        orc, settings, view, pview, lights = oracle_for(config, width, height, threads=t, calibrate=False)
+        inp = plugin.make_frame_inputs(settings, 1, view, pview, lights)
+        orc.render_frame(inp)
+        t0 = time.perf_counter()
+        orc.render_frame(plugin.make_frame_inputs(settings, 2, view, pview, lights))
+        dt = time.perf_counter() - t0
+        orc.close()
+        if dt < best_t:
+            best, best_t = t, dt
+    _BEST_THREADS[key] = best
+    return best
+
+
+def oracle_for(config, width, height, threads=None, calibrate=True):
+    if threads is None:
+        threads = best_threads(config, width, height) if calibrate else host_threads()
     from bevy_hikari_b200 import plugin, scenes
     from oracle import oracle
     cfg = scenes.CONFIGS[config]

@@ -48,6 +48,9 @@ def _run(cmd):
 
 def build(force=False, verbose=False, ptxas_info=False):
     os.makedirs(OBJ, exist_ok=True)
+    extra_env = os.environ.get("HK_NVCC_EXTRA", "").split()   # tuning experiments, e.g. -DHK_MINB_INDIRECT=5
+    if extra_env:
+        force = True
     headers = [os.path.join(HERE, h) for h in HEADERS]
     jobs = []
     objs = []
@@ -56,7 +59,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         o = os.path.join(OBJ, os.path.basename(src) + ".o")
         objs.append(o)
         if force or _newer(o, [s] + headers):
-            extra = ["-Xptxas", "-v"] if ptxas_info else []
+            extra = (["-Xptxas", "-v"] if ptxas_info else []) + extra_env
             jobs.append([NVCC] + NVCC_FLAGS + extra + ["-c", s, "-o", o])
     for src in CPP:
         s = os.path.join(HERE, src)

@@ -92,6 +92,8 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     HK_CUDA(alloc_plane(ctx, &p.instance_material, n, L));
     HK_CUDA(alloc_plane(ctx, &p.velocity_uv, n, L));
     HK_CUDA(alloc_plane(ctx, &p.albedo, n, L));
+    HK_CUDA(alloc_plane(ctx, &p.dn_geometry, n, L));
+    HK_CUDA(alloc_plane(ctx, &p.dn_instance, n, L));
     for (int i = 0; i < 3; ++i) {
         HK_CUDA(alloc_plane(ctx, &p.render[i], n, L));
         HK_CUDA(alloc_plane(ctx, &p.variance[i], n, L));

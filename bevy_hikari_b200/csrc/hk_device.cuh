@@ -48,6 +48,8 @@ struct Planes {
     uint2* render[3];
     float* variance[3];
     ReservoirPlanes reservoir[10];
+    float4* dn_geometry;        // normalize(unpack(normal)).xyz | depth : what every a-trous tap needs, prepared once per frame
+    float* dn_instance;         // instance id + 0.5 (instance_material.x)
     uint2* dn_internal[4][3];   // [level][signal]; level 0 = demodulated input
     float* dn_variance[3];
     uint2* dn_render[3];
@@ -288,43 +290,87 @@ __device__ __forceinline__ void instance_ray(const hk_instance* inst, const Ray&
     vec4 c0 = f4v(ldg4(m)), c1 = f4v(ldg4(m + 1)), c2 = f4v(ldg4(m + 2)), c3 = f4v(ldg4(m + 3));
     vec4 o = v4(ray.origin, 1.0f), d = v4(ray.direction, 0.0f);
     vec4 po = v4(dot(c0, o), dot(c1, o), dot(c2, o), dot(c3, o));
-    r.origin = xyz(po) / po.w;
+    r.origin = (po.w == 1.0f) ? xyz(po) : xyz(po) / po.w;     // x / 1 == x exactly: affine instances skip three divisions
     r.direction = v3(dot(c0, d), dot(c1, d), dot(c2, d));
     r.inv_direction = 1.0f / r.direction;
 }
 
-// TLAS walk, light.wgsl:442-486.
+// TLAS + BLAS walk, light.wgsl:442-486 with traverse_bottom (:400-440) inlined as ONE loop ("if-if" instead of
+// "while-while"): every iteration performs one node step of whichever level the lane is in.  TLAS and BLAS records share
+// one format and one slab test, so lanes that are inside different instances' BLASes and lanes that are still walking
+// the TLAS execute the same interior-node code together instead of serialising inner against outer loop — the nested
+// form ran at ~4 active lanes per instruction on secondary rays (ncu, profiles/r1).  Visit order, the strict '<'
+// updates and both early-outs are unchanged, so hits are bit-identical to the nested walk.
 __device__ __forceinline__ Hit traverse_top(const DeviceScene& sc, const Ray& ray, float max_distance, float early_distance,
                                             uint32_t exclude_instance) {
     Hit hit;
     hit.u = 0.0f; hit.v = 0.0f; hit.distance = max_distance;
     hit.instance_index = U32_MAX; hit.primitive_index = U32_MAX;
     const hk_node* nodes = sc.instance_nodes;
-    const uint32_t count = sc.instance_node_count;
+    uint32_t count = sc.instance_node_count;
     uint32_t index = 0;
-    while (index < count) {
-        float4 n0 = ldg4(&nodes[index]);
-        uint32_t entry = __float_as_uint(n0.w);
-        if (entry >= BVH_LEAF_FLAG) {
-            uint32_t exit_index = __ldg(&nodes[index].exit_index);
-            uint32_t instance_index = entry - BVH_LEAF_FLAG;
-            const hk_instance* inst = sc.instances + instance_index;
-            if (instance_index != exclude_instance) {
-                float4 imin = ldg4(inst->min), imax = ldg4(inst->max);
+    Ray cur = ray;                 // world-space ray while in the TLAS, object-space ray while in a BLAS
+    bool in_blas = false, blas_hit = false;
+    uint32_t tlas_resume = 0, instance_index = 0, mesh_primitive = 0;
+    for (;;) {
+        // phase 1 — every lane steps over interior (navigator) records until it stands on a leaf record or its level is
+        // exhausted.  Lanes reconverge after this loop, so the expensive leaf work below (instance transform, triangle
+        // test) runs with all lanes that have a leaf pending instead of the 3-4 that happen to be in phase with each other.
+        uint32_t entry = 0;
+        float4 n0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        while (index < count) {
+            n0 = ldg4(&nodes[index]);                              // min.xyz | entry_index
+            entry = __float_as_uint(n0.w);
+            if (entry >= BVH_LEAF_FLAG) break;
+            const float4 n1 = ldg4(reinterpret_cast<const float4*>(&nodes[index]) + 1);  // max.xyz | exit_index
+            index = (slab(cur, f4xyz(n0), f4xyz(n1)) < hit.distance) ? entry : __float_as_uint(n1.w);
+        }
+        if (index >= count) {
+            if (!in_blas) break;
+            // traverse_bottom returned: back to the TLAS record after the instance leaf
+            in_blas = false;
+            if (blas_hit) {
+                hit.instance_index = instance_index;
+                if (hit.distance < early_distance) break;
+            }
+            nodes = sc.instance_nodes; count = sc.instance_node_count; index = tlas_resume;
+            cur = ray;
+            continue;
+        }
+        // phase 2 — leaf record
+        const uint32_t exit_index = __ldg(&nodes[index].exit_index);
+        index = exit_index;
+        if (!in_blas) {
+            const uint32_t candidate = entry - BVH_LEAF_FLAG;
+            if (candidate != exclude_instance) {
+                const hk_instance* inst = sc.instances + candidate;
+                const float4 imin = ldg4(inst->min), imax = ldg4(inst->max);
                 if (slab(ray, f4xyz(imin), f4xyz(imax)) < hit.distance) {
-                    Ray r;
-                    instance_ray(inst, ray, r);
-                    uint4 mesh = ldg4u(&inst->mesh);  // vertex, primitive, node_offset, node_count
-                    if (traverse_bottom(sc, hit, r, mesh.y, mesh.z, mesh.w, early_distance)) {
+                    instance_ray(inst, ray, cur);
+                    const uint4 mesh = ldg4u(&inst->mesh);     // vertex, primitive, node_offset, node_count
+                    in_blas = true; blas_hit = false;
+                    tlas_resume = exit_index; instance_index = candidate; mesh_primitive = mesh.y;
+                    nodes = sc.asset_nodes + mesh.z; count = mesh.w; index = 0;
+                }
+            }
+        } else {
+            const uint32_t primitive_index = mesh_primitive + entry - BVH_LEAF_FLAG;
+            const hk_primitive* prim = sc.primitives + primitive_index;
+            const float4 a = ldg4(&prim->vertices[0]), b = ldg4(&prim->vertices[1]), c = ldg4(&prim->vertices[2]);
+            const vec3 p0 = f4xyz(a), p1 = f4xyz(b), p2 = f4xyz(c);
+            if (slab(cur, vmin(p0, vmin(p1, p2)), vmax(p0, vmax(p1, p2))) < hit.distance) {
+                float u, v;
+                const float distance = triangle(cur, p0, p1, p2, u, v);
+                if (distance < hit.distance) {
+                    hit.u = u; hit.v = v; hit.distance = distance;
+                    hit.primitive_index = primitive_index;
+                    blas_hit = true;
+                    if (distance < early_distance) {           // traverse_bottom returns, traverse_top returns
                         hit.instance_index = instance_index;
-                        if (hit.distance < early_distance) return hit;
+                        break;
                     }
                 }
             }
-            index = exit_index;
-        } else {
-            float4 n1 = ldg4(reinterpret_cast<const float4*>(&nodes[index]) + 1);
-            index = (slab(ray, f4xyz(n0), f4xyz(n1)) < hit.distance) ? entry : __float_as_uint(n1.w);
         }
     }
     return hit;
@@ -488,23 +534,42 @@ __device__ __forceinline__ vec3 env_brdf(vec3 V, vec3 N, const Surface& s) {  //
     vec3 diffuse_color = base_color * (1.0f - s.metallic);
     return s.occlusion * env_terms(diffuse_color, F0, s.roughness, NdotV);
 }
-// shading = mix(lit, ambient, 1 - a), light.wgsl:796-888
-__device__ __forceinline__ vec3 shading(const ShadeEnv& e, vec3 V, vec3 N, vec3 Lv, const Surface& s, vec4 in_radiance) {
+// shading = mix(lit, ambient, 1 - a), light.wgsl:796-888, split in the part that depends only on (V, N, surface) and
+// the part that depends on the light direction and radiance: the spatial-reuse kernel shades up to 18 samples against
+// the same surface point, so the first part (two EnvBRDFApprox with an exp2 each, F0, f90, N.V) is evaluated once.
+// Operations and their order are exactly those of the single-call form, so results are bit-identical.
+struct ShadeCtx {
+    vec3 V, N, F0, diffuse_color, ambient_radiance;
+    float roughness, NdotV, f90;
+};
+__device__ __forceinline__ ShadeCtx make_shade_ctx(const ShadeEnv& e, vec3 V, vec3 N, const Surface& s) {
+    ShadeCtx c;
     vec3 base_color = xyz(s.base_color);
-    vec3 F0 = v3(0.16f * s.reflectance * s.reflectance * (1.0f - s.metallic)) + base_color * s.metallic;
-    vec3 diffuse_color = base_color * (1.0f - s.metallic);
+    c.V = V; c.N = N;
+    c.F0 = v3(0.16f * s.reflectance * s.reflectance * (1.0f - s.metallic)) + base_color * s.metallic;
+    c.diffuse_color = base_color * (1.0f - s.metallic);
+    c.roughness = s.roughness;
+    c.NdotV = fmax_(dot(N, V), 0.0001f);
+    c.f90 = saturate(dot(c.F0, v3(50.0f * 0.33f)));                                                  // fresnel()
+    c.ambient_radiance = s.occlusion * env_terms(c.diffuse_color, c.F0, s.roughness, c.NdotV) * e.ambient;  // ambient()
+    return c;
+}
+__device__ __forceinline__ vec3 shade(const ShadeCtx& c, vec3 Lv, vec4 in_radiance) {
     // lit()
-    vec3 Hv = normalize(Lv + V);
-    float NoL = saturate(dot(N, Lv));
-    float NoH = saturate(dot(N, Hv));
+    vec3 Hv = normalize(Lv + c.V);
+    float NoL = saturate(dot(c.N, Lv));
+    float NoH = saturate(dot(c.N, Hv));
     float LoH = saturate(dot(Lv, Hv));
-    float NdotV = fmax_(dot(N, V), 0.0001f);
-    vec3 diffuse = diffuse_color * Fd_Burley(s.roughness, NdotV, NoL, LoH);
-    vec3 specular_light = specular(F0, s.roughness, NdotV, NoL, NoH, LoH, 1.0f);
+    vec3 diffuse = c.diffuse_color * Fd_Burley(c.roughness, c.NdotV, NoL, LoH);
+    float D = D_GGX(c.roughness, NoH);
+    float Vis = V_SmithGGXCorrelated(c.roughness, c.NdotV, NoL);
+    vec3 F = F_Schlick_vec(c.F0, c.f90, LoH);
+    vec3 specular_light = (1.0f * D * Vis) * F;                                                       // specular(), intensity 1
     vec3 lit_radiance = (specular_light + diffuse) * xyz(in_radiance) * NoL;
-    // ambient()
-    vec3 ambient_radiance = s.occlusion * env_terms(diffuse_color, F0, s.roughness, NdotV) * e.ambient;
-    return mix(lit_radiance, ambient_radiance, 1.0f - in_radiance.w);
+    return mix(lit_radiance, c.ambient_radiance, 1.0f - in_radiance.w);
+}
+__device__ __forceinline__ vec3 shading(const ShadeEnv& e, vec3 V, vec3 N, vec3 Lv, const Surface& s, vec4 in_radiance) {
+    return shade(make_shade_ctx(e, V, N, s), Lv, in_radiance);
 }
 // input_radiance, light.wgsl:835-867
 __device__ __forceinline__ vec4 input_radiance(const DeviceScene& sc, const ShadeEnv& e, vec3 ray_direction, const HitInfo& info,
@@ -631,12 +696,22 @@ __device__ __forceinline__ vec4 noise_random(const KParams& P, int x, int y) {
     uint32_t noise_id = number % NOISE_TEXTURE_COUNT;
     uint32_t tx = ((uint32_t)x + number) & 63u, ty = ((uint32_t)y + number) & 63u;
     uchar4 t = __ldg(reinterpret_cast<const uchar4*>(P.noise) + ((noise_id * 64u + ty) * 64u + tx));
-    vec4 rnd = v4((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f, (float)t.w / 255.0f);
+    vec4 rnd = v4(unorm8(t.x), unorm8(t.y), unorm8(t.z), unorm8(t.w));
     return fract(rnd + (float)number * GOLDEN_RATIO);
 }
 
 // 8x4-pixel tiles per warp, 4 warps per CTA (16x8 pixels): ray coherence + whole-sector plane accesses.
 constexpr int TILE_W = 16, TILE_H = 8, CTA_THREADS = 128;
+#ifndef HK_MINB_INDIRECT
+#define HK_MINB_INDIRECT 8   // measured on B200 (tools/tune_launch_bounds.sh): these kernels are latency bound;
+                             // 8 CTAs/SM (<= 64 registers, some spills) beat 3-4 CTAs/SM at 130-160 registers by 20-25 %
+#endif
+#ifndef HK_MINB_DIRECT
+#define HK_MINB_DIRECT 8
+#endif
+#ifndef HK_MINB_SPATIAL
+#define HK_MINB_SPATIAL 8
+#endif
 __device__ __forceinline__ void tile_pixel(int& x, int& y, int row_lo) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     x = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);

@@ -180,7 +180,7 @@ __device__ __forceinline__ vec2 pixel_uv(const KParams& P, int x, int y) {  // c
 // --------------------------------------------------------------------------------------- P2: direct_lit
 // light.wgsl:1044-1261.  EMISSIVE_LIT=false is the sun pass (+RENDER_EMISSIVE), true is the emissive pass.
 template <bool EMISSIVE_LIT, bool COUNT>
-__global__ void __launch_bounds__(CTA_THREADS) k_direct(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __grid_constant__ KParams P) {
     constexpr int SIGNAL = EMISSIVE_LIT ? 1 : 0;
     constexpr bool RENDER_EMISSIVE = !EMISSIVE_LIT;
     int x, y;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_direct(const __grid_constant__ 
 // light.wgsl:1263-1498.  One kernel covers both the single-bounce and the MULTIPLE_BOUNCES variants: the reference's
 // single-bounce body is the loop body for n == 0 without the luminance clamp, so MULTI only switches those two bits.
 template <bool MULTI, bool COUNT>
-__global__ void __launch_bounds__(CTA_THREADS) k_indirect(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(const __grid_constant__ KParams P) {
     int x, y;
     tile_pixel(x, y, P.row_lo);
     const bool active = x < P.band.W && y < P.row_hi;
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_indirect(const __grid_constant_
 // light.wgsl:1500-1684.  The reference's 8x8 workgroup cache holds unpack(reservoir_buffer[..]) of this dispatch's
 // read-only input, so gathering neighbours straight from the planes (L1/L2-resident) is value-identical.
 template <bool EMISSIVE_LIT>
-__global__ void __launch_bounds__(CTA_THREADS) k_spatial(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const __grid_constant__ KParams P) {
     constexpr int SIGNAL = EMISSIVE_LIT ? 1 : 2;
     constexpr uint32_t SPATIAL_REUSE_COUNT = EMISSIVE_LIT ? 8u : 16u;   // light.wgsl:246-252
     constexpr float SPATIAL_REUSE_RANGE = EMISSIVE_LIT ? 10.0f : 20.0f;
@@ -483,11 +483,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_spatial(const __grid_constant__
         if (previous_pixel(P, previous_uv, false, pidx)) r = unpack_reservoir(load_quarters(B.previous_spatial_reservoir, pidx));
     }
     const vec3 view_direction = calculate_view(env, position);
+    const ShadeCtx shade_ctx = make_shade_ctx(env, view_direction, s.visible_normal, surface);   // shared by every shading below
     if (EMISSIVE_LIT) {
         merge_reservoir(r, q, luminance(xyz(q.s.radiance)));
     } else {
-        vec3 out_radiance = shading(env, view_direction, s.visible_normal, normalize(xyz(s.sample_position) - xyz(s.visible_position)),
-                                    surface, s.radiance);
+        vec3 out_radiance = shade(shade_ctx, normalize(xyz(s.sample_position) - xyz(s.visible_position)), s.radiance);
         merge_reservoir(r, q, luminance(out_radiance));
     }
     r.s.visible_position = s.visible_position;
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_spatial(const __grid_constant__
         if (EMISSIVE_LIT) {
             merge_reservoir(r, q, luminance(xyz(q.s.radiance)) / jacobian);
         } else {
-            vec3 out_radiance = shading(env, view_direction, s.visible_normal, sample_direction, surface, q.s.radiance);
+            vec3 out_radiance = shade(shade_ctx, sample_direction, q.s.radiance);
             merge_reservoir(r, q, luminance(out_radiance) / jacobian);
         }
     }
@@ -544,8 +544,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_spatial(const __grid_constant__
         r.w2_sum *= m / r.count;
         r.count = m;
     }
-    vec3 out_radiance = shading(env, view_direction, s.visible_normal, normalize(xyz(r.s.sample_position) - xyz(s.visible_position)),
-                                surface, r.s.radiance);
+    vec3 out_radiance = shade(shade_ctx, normalize(xyz(r.s.sample_position) - xyz(s.visible_position)), r.s.radiance);
     float total_lum = EMISSIVE_LIT ? r.count * luminance(xyz(r.s.radiance)) : r.count * luminance(out_radiance);
     r.w = (total_lum > 0.0f) ? r.w_sum / total_lum : 0.0f;
     r.lifetime += 1.0f;

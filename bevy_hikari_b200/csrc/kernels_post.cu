@@ -33,6 +33,12 @@ __global__ void __launch_bounds__(CTA_THREADS) k_demodulation(const __grid_const
     tile_pixel(x, y, P.row_lo);
     if (x >= P.band.W || y >= P.row_hi) return;
     const size_t idx = band_index(P.band, x, y);
+    {   // tap geometry for the four a-trous levels: the normalised normal, depth and instance id of this pixel are read
+        // by up to 36 taps; normalise once here instead of 36 times there (same operations, same values)
+        const vec3 n = normalize(xyz(unpack4x8snorm(P.planes.normal[idx])));
+        P.planes.dn_geometry[idx] = make_float4(n.x, n.y, n.z, P.planes.pos_depth[idx].w);
+        P.planes.dn_instance[idx] = P.planes.instance_material[idx].x;
+    }
     const vec3 albedo = xyz(load16(P.planes.albedo, idx));
     for (int sgl = 0; sgl < signals; ++sgl) {
         vec3 irradiance = xyz(load16(P.planes.render[sgl], idx));
@@ -69,14 +75,15 @@ __global__ void __launch_bounds__(CTA_THREADS) k_denoise(const __grid_constant__
     tile_pixel(x, y, P.row_lo);
     if (x >= P.band.W || y >= P.row_hi) return;
     const size_t idx = band_index(P.band, x, y);
-    const float depth = P.planes.pos_depth[idx].w;
+    const float4 geometry = P.planes.dn_geometry[idx];
+    const float depth = geometry.w;
     vec4 result[3];
     result[0] = result[1] = result[2] = v4(0.0f);
     if (!(depth < F32_EPSILON)) {
         const float2 dg = P.planes.depth_gradient[idx];
         const vec2 depth_gradient = v2(dg.x, dg.y);
-        const vec3 normal = normalize(xyz(unpack4x8snorm(P.planes.normal[idx])));
-        const float instance = P.planes.instance_material[idx].x;
+        const vec3 normal = f4xyz(geometry);
+        const float instance = P.planes.dn_instance[idx];
 
         SignalAcc acc[3];
 #pragma unroll
@@ -102,9 +109,10 @@ __global__ void __launch_bounds__(CTA_THREADS) k_denoise(const __grid_constant__
             if (sx < 0 || sy < 0 || sx >= P.band.W || sy >= P.band.H) continue;
             const size_t sidx = band_index(P.band, sx, sy);
             // geometric weights: once per tap for all signals
-            const vec3 sample_normal = normalize(xyz(unpack4x8snorm(P.planes.normal[sidx])));
-            const float sample_depth = P.planes.pos_depth[sidx].w;
-            const float sample_instance = P.planes.instance_material[sidx].x;
+            const float4 sample_geometry = P.planes.dn_geometry[sidx];
+            const vec3 sample_normal = f4xyz(sample_geometry);
+            const float sample_depth = sample_geometry.w;
+            const float sample_instance = P.planes.dn_instance[sidx];
             const float w_normal = pow16(fmax_(0.0f, dot(normal, sample_normal)));                                       // :44-47
             const float w_depth = exp_((-fabsf(depth - sample_depth)) / (fabsf(dot(depth_gradient, v2((float)ox, (float)oy))) + 0.01f));  // :50-53
             const float w_instance = fmax_(0.0f, 1.0f - fabsf(instance - sample_instance));                              // :63-65
@@ -148,12 +156,16 @@ __global__ void __launch_bounds__(CTA_THREADS) k_denoise(const __grid_constant__
     }
 
     if (LEVEL < 3) {
-        for (int sgl = 0; sgl < signals; ++sgl) store16(P.planes.dn_internal[LEVEL + 1][sgl], idx, result[sgl]);
+#pragma unroll
+        for (int sgl = 0; sgl < 3; ++sgl)
+            if (sgl < signals) store16(P.planes.dn_internal[LEVEL + 1][sgl], idx, result[sgl]);
         return;
     }
     // level 3 -> denoise_render (Rgba16Float), then tone_mapping.wgsl:21-32 on the f16-rounded values
     vec4 color = v4(0.0f);
-    for (int sgl = 0; sgl < signals; ++sgl) {
+#pragma unroll
+    for (int sgl = 0; sgl < 3; ++sgl) {
+        if (sgl >= signals) continue;
         uvec2 w = pack_rgba16f(result[sgl]);
         if (!FUSE_TONE_MAPPING || keep_denoised) P.planes.dn_render[sgl][idx] = make_uint2(w.x, w.y);
         if (FUSE_TONE_MAPPING) color = color + unpack_rgba16f(w);

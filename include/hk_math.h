@@ -72,6 +72,18 @@ HK_HD float pow16(float x) { x = x * x; x = x * x; x = x * x; return x * x; }
 HK_HD float pow025(float x) { return sqrtf(sqrtf(x)); }
 HK_HD bool is_nan(float v) { return !(v < 0.0f || 0.0f < v || v == 0.0f); }  // utils.wgsl:3-5
 
+// x / C, correctly rounded, for the three constants the unpack paths divide by (127, 255, 65535) and integer-valued x
+// with |x| <= C + 1: q = RN(x * RN(1/C)), one Newton correction with the exact remainder (Markstein).  Three
+// instructions instead of the ~12 of a general IEEE division — unpacking reservoirs was ~230 divisions per pixel in the
+// spatial pass.  tests/test_math.py checks EVERY possible input against IEEE division, so this is the same function.
+template <int C>
+HK_HD float div_const(float x) {
+    const float y = 1.0f / (float)C;
+    float q = x * y;
+    float r = fmaf(-q, (float)C, x);
+    return fmaf(r, y, q);
+}
+
 HK_HD uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 HK_HD float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
@@ -307,7 +319,8 @@ HK_HD uint32_t pack2x16unorm(float a, float b) {
     uint32_t y = (uint32_t)floorf(0.5f + 65535.0f * fmin_(1.0f, fmax_(0.0f, b)));
     return x | (y << 16);
 }
-HK_HD vec2 unpack2x16unorm(uint32_t u) { return v2((float)(u & 0xFFFFu) / 65535.0f, (float)(u >> 16) / 65535.0f); }
+HK_HD vec2 unpack2x16unorm(uint32_t u) { return v2(div_const<65535>((float)(u & 0xFFFFu)), div_const<65535>((float)(u >> 16))); }
+HK_HD float unorm8(uint32_t b) { return div_const<255>((float)(b & 0xFFu)); }   // Rgba8Unorm texel component
 // WGSL spec: floor(0.5 + 127 * min(1, max(-1, e))), two's complement byte
 HK_HD uint32_t snorm8(float e) {
     int32_t i = (int32_t)floorf(0.5f + 127.0f * fmin_(1.0f, fmax_(-1.0f, e)));
@@ -316,7 +329,7 @@ HK_HD uint32_t snorm8(float e) {
 HK_HD uint32_t pack4x8snorm(vec4 v) {
     return snorm8(v.x) | (snorm8(v.y) << 8) | (snorm8(v.z) << 16) | (snorm8(v.w) << 24);
 }
-HK_HD float unsnorm8(uint32_t b) { return fmax_((float)(int8_t)(b & 0xFFu) / 127.0f, -1.0f); }
+HK_HD float unsnorm8(uint32_t b) { return fmax_(div_const<127>((float)(int8_t)(b & 0xFFu)), -1.0f); }
 HK_HD vec4 unpack4x8snorm(uint32_t u) {
     return v4(unsnorm8(u), unsnorm8(u >> 8), unsnorm8(u >> 16), unsnorm8(u >> 24));
 }

@@ -686,7 +686,7 @@ inline vec4 noise_random(const Ctx& c, ivec2 coords) {  // light.wgsl:1075-1079
     int tx = (int)floorf(fract(noise_uv.x) * 64.0f), ty = (int)floorf(fract(noise_uv.y) * 64.0f);
     tx = std::min(tx, 63); ty = std::min(ty, 63);
     const uint8_t* t = &c.noise[(((size_t)noise_id * 64 + ty) * 64 + tx) * 4];
-    vec4 rnd = v4((float)t[0] / 255.0f, (float)t[1] / 255.0f, (float)t[2] / 255.0f, (float)t[3] / 255.0f);
+    vec4 rnd = v4(unorm8(t[0]), unorm8(t[1]), unorm8(t[2]), unorm8(t[3]));
     return fract(rnd + (float)number * GOLDEN_RATIO);
 }
 
@@ -1549,6 +1549,9 @@ float hko_math_f16_to_f32(uint16_t h) { return f16_bits_to_f32(h); }
 uint32_t hko_math_pack4x8snorm(float x, float y, float z, float w) { return pack4x8snorm(v4(x, y, z, w)); }
 uint32_t hko_math_pack2x16unorm(float a, float b) { return pack2x16unorm(a, b); }
 uint32_t hko_math_hash(uint32_t v) { return hash_u32(v); }
+float hko_math_unsnorm8(uint32_t b) { return unsnorm8(b); }
+float hko_math_unorm8(uint32_t b) { return unorm8(b); }
+float hko_math_unorm16(uint32_t u) { return unpack2x16unorm(u).x; }
 void hko_math_normal_basis(const float* n, float* out9) {
     mat3 m = normal_basis(v3(n[0], n[1], n[2]));
     for (int i = 0; i < 3; ++i) { out9[3 * i] = m.c[i].x; out9[3 * i + 1] = m.c[i].y; out9[3 * i + 2] = m.c[i].z; }

@@ -57,6 +57,9 @@ def lib():
             "hko_math_pack4x8snorm": (_U32, [C.c_float] * 4),
             "hko_math_pack2x16unorm": (_U32, [C.c_float, C.c_float]),
             "hko_math_hash": (_U32, [_U32]),
+            "hko_math_unsnorm8": (C.c_float, [_U32]),
+            "hko_math_unorm8": (C.c_float, [_U32]),
+            "hko_math_unorm16": (C.c_float, [_U32]),
             "hko_math_normal_basis": (None, [_P, _P]),
             "hko_pack_reservoir_roundtrip": (None, [_P, _P]),
         }

@@ -117,3 +117,16 @@ def test_reservoir_pack_unpack_is_idempotent_after_one_round_trip():
     d = (np.ascontiguousarray(once["visible_normal"]).view(np.int8).astype(int) -
          np.ascontiguousarray(twice["visible_normal"]).view(np.int8).astype(int))
     assert np.abs(d).max() <= 1
+
+
+def test_fast_division_by_constants_is_exactly_ieee_division_for_every_input():
+    """unsnorm8 / unorm8 / unorm16 use a 3-instruction correctly-rounded quotient (hk::div_const); exhaustive check."""
+    lib = oracle.lib()
+    for b in range(256):
+        i = b - 256 if b >= 128 else b
+        want = max(np.float32(i) / np.float32(127.0), np.float32(-1.0))
+        assert np.float32(lib.hko_math_unsnorm8(b)).view(np.uint32) == np.float32(want).view(np.uint32), b
+        assert np.float32(lib.hko_math_unorm8(b)).view(np.uint32) == (np.float32(b) / np.float32(255.0)).view(np.uint32), b
+    got = np.array([lib.hko_math_unorm16(u) for u in range(65536)], np.float32)
+    want = np.arange(65536, dtype=np.float32) / np.float32(65535.0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

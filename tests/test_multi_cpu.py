@@ -1,0 +1,60 @@
+"""N > 1 host logic on CPU (gloo, world_size 2): the row-band partition and the all-gather assembly bench.py uses.
+The CUDA side of sharding (ghost rows) is covered on the GPU by test_gpu_parity.py::test_row_bands_equal_unsharded."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.conftest import Bench
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, height, width, full_bytes, out_dir):
+    import bench
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r0, r1 = bench.band(height, rank, world)
+    full = torch.frombuffer(bytearray(full_bytes), dtype=torch.float16).reshape(height, width, 4)
+    tile = full[r0:r1].contiguous().reshape(-1)              # what hk_get_output(HK_OUT_TONE_MAPPED) holds on this rank
+    frame = torch.empty(world * tile.numel(), dtype=torch.float16)
+    dist.all_gather_into_tensor(frame, tile)                  # the one collective of the path
+    ok = torch.equal(frame.view(torch.int16), full.reshape(-1).view(torch.int16))
+    t = torch.tensor([1.0 if ok else 0.0, float(r1 - r0)])
+    dist.all_reduce(t)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "result.npy"), t.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_band_partition_and_all_gather_reassemble_the_frame(tmp_path):
+    import bench
+    # partition properties
+    for h, n in ((1080, 1), (1080, 2), (2160, 4), (4320, 8)):
+        bands = [bench.band(h, r, n) for r in range(n)]
+        assert bands[0][0] == 0 and bands[-1][1] == h
+        assert all(bands[i][1] == bands[i + 1][0] for i in range(n - 1))
+        assert len({b[1] - b[0] for b in bands}) == 1          # equal contributions for the all-gather
+    with pytest.raises(AssertionError):
+        bench.band(1080, 0, 7)
+    # a real frame from the oracle, split in two bands, reassembled over gloo
+    b = Bench("cornell", 48, 64, config="cornell_256")
+    orc = b.oracle(threads=2)
+    orc.render_frame(b.inputs(1))
+    from bevy_hikari_b200 import layout as L
+    full = np.ascontiguousarray(orc.readback(L.OUT_TONE_MAPPED))
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, 64, 48, full.tobytes(), str(tmp_path)), nprocs=2, join=True)
+    res = np.load(tmp_path / "result.npy")
+    assert res[0] == 2.0 and res[1] == 64.0
