@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "hikari_b200.h"
@@ -103,6 +104,8 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     }
     for (int r = 0; r < 10; ++r)
         for (int q = 0; q < 4; ++q) HK_CUDA(alloc_plane(ctx, &p.reservoir[r].q[q], n, L));
+    HK_CUDA(alloc_plane(ctx, &p.scatter_key, n, L));   // zero = no claim; k_scatter_resolve re-zeroes what it consumes
+    for (int q = 0; q < 4; ++q) HK_CUDA(alloc_plane(ctx, &p.scatter_value.q[q], n, L));
     HK_CUDA(alloc_plane(ctx, &p.tone_mapped, ctx->owned_pixels, L));
     return HK_OK;
 }
@@ -217,11 +220,43 @@ int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
         if (in.material >= s->material_count || (uint64_t)in.mesh.node_offset + in.mesh.node_count > s->asset_node_count)
             return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "instance references a material / node range out of bounds");
     }
+    // Does every leaf record sit right behind a navigator whose box is the shape's own AABB?  (true for bvh 0.7.1's
+    // flatten_custom, which is what the reference uploads; then the kernels skip the re-derived leaf box test.)
+    bool boxes_match = true;
+    auto same3 = [](const float* a, const float* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; };
+    for (uint32_t i = 1; i < s->instance_node_count && boxes_match; ++i) {
+        const hk_node& leaf = s->instance_nodes[i];
+        if (leaf.entry_index < 0x80000000u) continue;
+        const hk_node& nav = s->instance_nodes[i - 1];
+        uint32_t id = leaf.entry_index - 0x80000000u;
+        boxes_match = nav.entry_index == i && id < s->instance_count && same3(nav.min, s->instances[id].min) &&
+                      same3(nav.max, s->instances[id].max);
+    }
+    std::unordered_set<uint32_t> checked;   // mesh node ranges repeat across instances: check each once
+    for (uint32_t m = 0; m < s->instance_count && boxes_match; ++m) {
+        const hk_mesh_index& mi = s->instances[m].mesh;
+        if (!checked.insert(mi.node_offset).second) continue;
+        for (uint32_t i = 1; i < mi.node_count && boxes_match; ++i) {
+            const hk_node& leaf = s->asset_nodes[mi.node_offset + i];
+            if (leaf.entry_index < 0x80000000u) continue;
+            const hk_node& nav = s->asset_nodes[mi.node_offset + i - 1];
+            uint64_t pid = (uint64_t)mi.primitive + (leaf.entry_index - 0x80000000u);
+            if (nav.entry_index != i || pid >= s->primitive_count) { boxes_match = false; break; }
+            const hk_primitive& p = s->primitives[pid];
+            float mn[3], mx[3];
+            for (int c = 0; c < 3; ++c) {
+                mn[c] = fminf(p.vertices[0].position[c], fminf(p.vertices[1].position[c], p.vertices[2].position[c]));
+                mx[c] = fmaxf(p.vertices[0].position[c], fmaxf(p.vertices[1].position[c], p.vertices[2].position[c]));
+            }
+            boxes_match = same3(nav.min, mn) && same3(nav.max, mx);
+        }
+    }
     HK_CUDA(cudaSetDevice(ctx->device));
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
     free_list(ctx->scene_allocations);
     ctx->scene_ready = false;
     DeviceScene d{};
+    d.leaf_boxes_match = boxes_match ? 1u : 0u;
     HK_CUDA(upload(ctx, &d.vertices, s->vertices, s->vertex_count));
     HK_CUDA(upload(ctx, &d.primitives, s->primitives, s->primitive_count));
     HK_CUDA(upload(ctx, &d.asset_nodes, s->asset_nodes, s->asset_node_count));
@@ -331,11 +366,15 @@ static int run_prepass(hk_context* ctx, KParams& P) {
 static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, light.rs:645-699 (albedo is fused in the prepass)
     const hk_frame_uniform& f = P.in.frame;
     rows(ctx, P, GHOST_TEMPORAL);
-    { KernelTimer t(ctx, HK_K_DIRECT); hk_launch_direct(P, false, ctx->count_rays, ctx->stream); }
-    { KernelTimer t(ctx, HK_K_EMISSIVE); hk_launch_direct(P, true, ctx->count_rays, ctx->stream); }
+    // each temporal pass is followed by the resolve of its scatter writes (all allocated rows can be targets)
+    { KernelTimer t(ctx, HK_K_DIRECT); hk_launch_direct(P, false, ctx->count_rays, ctx->stream);
+      hk_launch_scatter_resolve(P, 0, ctx->stream); ctx->launches += 1; }
+    { KernelTimer t(ctx, HK_K_EMISSIVE); hk_launch_direct(P, true, ctx->count_rays, ctx->stream);
+      hk_launch_scatter_resolve(P, 1, ctx->stream); ctx->launches += 1; }
     if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_EMISSIVE_SPATIAL); hk_launch_spatial(P, true, ctx->stream); }
     rows(ctx, P, GHOST_TEMPORAL);
-    { KernelTimer t(ctx, HK_K_INDIRECT); hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream); }
+    { KernelTimer t(ctx, HK_K_INDIRECT); hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
+      hk_launch_scatter_resolve(P, 2, ctx->stream); ctx->launches += 1; }
     if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); hk_launch_spatial(P, false, ctx->stream); }
     return check_launch(ctx);
 }

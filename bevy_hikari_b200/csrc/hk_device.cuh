@@ -31,7 +31,8 @@ struct DeviceScene {
     const cudaTextureObject_t* textures;   // unused by the NO_TEXTURE variant
     const float4* texture_texels;          // decoded texels of all textures, concatenated
     const uint4* texture_info;             // per texture: (offset, width, height, flags: bit0-1 mode_u, 2-3 mode_v, 4 linear)
-    uint32_t instance_node_count, emissive_node_count, texture_count, _pad;
+    uint32_t instance_node_count, emissive_node_count, texture_count;
+    uint32_t leaf_boxes_match;   // 1 = every leaf's navigator box equals the shape's own AABB (validated at upload)
 };
 
 struct ReservoirPlanes {  // one PackedReservoir buffer as 4 planes
@@ -48,6 +49,10 @@ struct Planes {
     uint2* render[3];
     float* variance[3];
     ReservoirPlanes reservoir[10];
+    // deterministic resolution of store_previous_spatial_reservoir(previous_coords) (light.wgsl:1094,1201,1458): writers
+    // race for a target pixel in the reference; here the winner is the last writer in raster order (= the oracle's rule)
+    uint32_t* scatter_key;          // per target pixel: max over writers of ((writer_linear_index + 1) << 2 | kind), 0 = none
+    ReservoirPlanes scatter_value;  // per writer pixel: the reservoir a kind-2 (validation miss) write carries
     float4* dn_geometry;        // normalize(unpack(normal)).xyz | depth : what every a-trous tap needs, prepared once per frame
     float* dn_instance;         // instance id + 0.5 (instance_material.x)
     uint2* dn_internal[4][3];   // [level][signal]; level 0 = demodulated input
@@ -255,19 +260,18 @@ __device__ __forceinline__ bool traverse_bottom(const DeviceScene& sc, Hit& hit,
     const hk_node* nodes = sc.asset_nodes + node_offset;
     uint32_t index = 0;
     while (index < node_count) {
-        float4 n0 = ldg4(&nodes[index]);                 // min.xyz | entry_index
-        uint32_t entry = __float_as_uint(n0.w);
+        const float4 n0 = ldg4(&nodes[index]);                                           // min.xyz | entry_index
+        const float4 n1 = ldg4(reinterpret_cast<const float4*>(&nodes[index]) + 1);      // max.xyz | exit_index
+        const uint32_t entry = __float_as_uint(n0.w);
         if (entry >= BVH_LEAF_FLAG) {
-            uint32_t exit_index = __ldg(&nodes[index].exit_index);
-            uint32_t primitive_index = mesh_primitive + entry - BVH_LEAF_FLAG;
+            const bool via_navigator = index != 0u && sc.leaf_boxes_match != 0u;         // see traverse_top
+            const uint32_t primitive_index = mesh_primitive + entry - BVH_LEAF_FLAG;
             const hk_primitive* prim = sc.primitives + primitive_index;
-            float4 a = ldg4(&prim->vertices[0]), b = ldg4(&prim->vertices[1]), c = ldg4(&prim->vertices[2]);
-            vec3 p0 = f4xyz(a), p1 = f4xyz(b), p2 = f4xyz(c);
-            vec3 bmin = vmin(p0, vmin(p1, p2));
-            vec3 bmax = vmax(p0, vmax(p1, p2));
-            if (slab(ray, bmin, bmax) < hit.distance) {
+            const float4 a = ldg4(&prim->vertices[0]), b = ldg4(&prim->vertices[1]), c = ldg4(&prim->vertices[2]);
+            const vec3 p0 = f4xyz(a), p1 = f4xyz(b), p2 = f4xyz(c);
+            if (via_navigator || slab(ray, vmin(p0, vmin(p1, p2)), vmax(p0, vmax(p1, p2))) < hit.distance) {
                 float u, v;
-                float distance = triangle(ray, p0, p1, p2, u, v);
+                const float distance = triangle(ray, p0, p1, p2, u, v);
                 if (distance < hit.distance) {
                     hit.u = u; hit.v = v; hit.distance = distance;
                     hit.primitive_index = primitive_index;
@@ -275,9 +279,8 @@ __device__ __forceinline__ bool traverse_bottom(const DeviceScene& sc, Hit& hit,
                     if (distance < early_distance) return true;
                 }
             }
-            index = exit_index;
+            index = __float_as_uint(n1.w);
         } else {
-            float4 n1 = ldg4(reinterpret_cast<const float4*>(&nodes[index]) + 1);  // max.xyz | exit_index
             index = (slab(ray, f4xyz(n0), f4xyz(n1)) < hit.distance) ? entry : __float_as_uint(n1.w);
         }
     }
@@ -316,14 +319,15 @@ __device__ __forceinline__ Hit traverse_top(const DeviceScene& sc, const Ray& ra
         // phase 1 — every lane steps over interior (navigator) records until it stands on a leaf record or its level is
         // exhausted.  Lanes reconverge after this loop, so the expensive leaf work below (instance transform, triangle
         // test) runs with all lanes that have a leaf pending instead of the 3-4 that happen to be in phase with each other.
-        uint32_t entry = 0;
-        float4 n0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        uint32_t entry = 0, exit_index = 0;
         while (index < count) {
-            n0 = ldg4(&nodes[index]);                              // min.xyz | entry_index
+            // both halves of the record in one round trip (a leaf record only needs .w of each)
+            const float4 n0 = ldg4(&nodes[index]);                                           // min.xyz | entry_index
+            const float4 n1 = ldg4(reinterpret_cast<const float4*>(&nodes[index]) + 1);      // max.xyz | exit_index
             entry = __float_as_uint(n0.w);
+            exit_index = __float_as_uint(n1.w);
             if (entry >= BVH_LEAF_FLAG) break;
-            const float4 n1 = ldg4(reinterpret_cast<const float4*>(&nodes[index]) + 1);  // max.xyz | exit_index
-            index = (slab(cur, f4xyz(n0), f4xyz(n1)) < hit.distance) ? entry : __float_as_uint(n1.w);
+            index = (slab(cur, f4xyz(n0), f4xyz(n1)) < hit.distance) ? entry : exit_index;
         }
         if (index >= count) {
             if (!in_blas) break;
@@ -337,15 +341,23 @@ __device__ __forceinline__ Hit traverse_top(const DeviceScene& sc, const Ray& ra
             cur = ray;
             continue;
         }
-        // phase 2 — leaf record
-        const uint32_t exit_index = __ldg(&nodes[index].exit_index);
+        // phase 2 — leaf record.  A leaf record is only ever reached through its navigator (the record before it), whose
+        // box is the shape's own AABB (bvh 0.7.1 stores the child's joint AABB = min/max of the triangle's vertices, resp.
+        // the instance's min/max) and whose slab test against the same ray and the same hit.distance has just passed.
+        // The reference repeats that test on the re-derived box (light.wgsl:411-414, 456-459); it cannot fail, so it is
+        // skipped — except for the root of a single-shape BVH (index 0), which has no navigator.
+        const bool via_navigator = index != 0u && sc.leaf_boxes_match != 0u;
         index = exit_index;
         if (!in_blas) {
             const uint32_t candidate = entry - BVH_LEAF_FLAG;
             if (candidate != exclude_instance) {
                 const hk_instance* inst = sc.instances + candidate;
-                const float4 imin = ldg4(inst->min), imax = ldg4(inst->max);
-                if (slab(ray, f4xyz(imin), f4xyz(imax)) < hit.distance) {
+                bool pass = via_navigator;
+                if (!pass) {
+                    const float4 imin = ldg4(inst->min), imax = ldg4(inst->max);
+                    pass = slab(ray, f4xyz(imin), f4xyz(imax)) < hit.distance;
+                }
+                if (pass) {
                     instance_ray(inst, ray, cur);
                     const uint4 mesh = ldg4u(&inst->mesh);     // vertex, primitive, node_offset, node_count
                     in_blas = true; blas_hit = false;
@@ -358,7 +370,7 @@ __device__ __forceinline__ Hit traverse_top(const DeviceScene& sc, const Ray& ra
             const hk_primitive* prim = sc.primitives + primitive_index;
             const float4 a = ldg4(&prim->vertices[0]), b = ldg4(&prim->vertices[1]), c = ldg4(&prim->vertices[2]);
             const vec3 p0 = f4xyz(a), p1 = f4xyz(b), p2 = f4xyz(c);
-            if (slab(cur, vmin(p0, vmin(p1, p2)), vmax(p0, vmax(p1, p2))) < hit.distance) {
+            if (via_navigator || slab(cur, vmin(p0, vmin(p1, p2)), vmax(p0, vmax(p1, p2))) < hit.distance) {
                 float u, v;
                 const float distance = triangle(cur, p0, p1, p2, u, v);
                 if (distance < hit.distance) {
@@ -700,6 +712,13 @@ __device__ __forceinline__ vec4 noise_random(const KParams& P, int x, int y) {
     return fract(rnd + (float)number * GOLDEN_RATIO);
 }
 
+// kinds of writes to the previous-spatial buffer, in the order one pixel can issue them
+constexpr uint32_t SCATTER_BACKGROUND = 0u, SCATTER_MISS = 1u, SCATTER_VALIDATION = 2u;
+__device__ __forceinline__ void scatter_claim(const KParams& P, size_t target, int x, int y, uint32_t kind) {
+    uint32_t writer = (uint32_t)y * (uint32_t)P.band.W + (uint32_t)x;   // global raster index
+    atomicMax(&P.planes.scatter_key[target], ((writer + 1u) << 2) | kind);
+}
+
 // 8x4-pixel tiles per warp, 4 warps per CTA (16x8 pixels): ray coherence + whole-sector plane accesses.
 constexpr int TILE_W = 16, TILE_H = 8, CTA_THREADS = 128;
 #ifndef HK_MINB_INDIRECT
@@ -708,6 +727,9 @@ constexpr int TILE_W = 16, TILE_H = 8, CTA_THREADS = 128;
 #endif
 #ifndef HK_MINB_DIRECT
 #define HK_MINB_DIRECT 8
+#endif
+#ifndef HK_MINB_DENOISE
+#define HK_MINB_DENOISE 8
 #endif
 #ifndef HK_MINB_SPATIAL
 #define HK_MINB_SPATIAL 8

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
             PackedQuarters q = pack_reservoir(r);
             store_quarters(B.reservoir, idx, q);
             store_quarters(B.spatial_reservoir, idx, q);
-            store_quarters(B.previous_spatial_reservoir, idx, q);
+            scatter_claim(P, idx, x, y, SCATTER_BACKGROUND);
             P.planes.variance[SIGNAL][idx] = 0.0f;
             P.planes.render[SIGNAL][idx] = make_uint2(0u, 0u);
         } else {
@@ -224,9 +224,9 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
             size_t pidx = 0;
             Reservoir r = zero_reservoir();
             if (previous_pixel(P, previous_uv, false, pidx)) r = unpack_reservoir(load_quarters(B.previous_reservoir, pidx));
-            if (!check_previous_reservoir(r, s)) {
+            if (!check_previous_reservoir(r, s)) {   // r is now the zero reservoir: the write carries a constant
                 size_t sidx;
-                if (previous_pixel(P, previous_uv, true, sidx)) store_quarters(B.previous_spatial_reservoir, sidx, pack_reservoir(r));
+                if (previous_pixel(P, previous_uv, true, sidx)) scatter_claim(P, sidx, x, y, SCATTER_MISS);
             }
 
             const uint32_t validate_interval = EMISSIVE_LIT ? frame.emissive_validate_interval : frame.direct_validate_interval;
@@ -280,7 +280,10 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
                 float luminance_ratio = luminance(xyz(validate_radiance)) / fmax_(luminance(xyz(r.s.radiance)), 0.0001f);
                 if (luminance_ratio > 1.25f || luminance_ratio < 0.8f) {
                     size_t sidx;
-                    if (previous_pixel(P, previous_uv, true, sidx)) store_quarters(B.previous_spatial_reservoir, sidx, pack_reservoir(r));
+                    if (previous_pixel(P, previous_uv, true, sidx)) {
+                        store_quarters(P.planes.scatter_value, idx, pack_reservoir(r));
+                        scatter_claim(P, sidx, x, y, SCATTER_VALIDATION);
+                    }
                     float w_new = (cand.p > 0.0f) ? luminance(xyz(s.radiance)) / cand.p : 0.0f;
                     set_reservoir(r, s, w_new);
                 }
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
             PackedQuarters q = pack_reservoir(zero_reservoir());
             store_quarters(B.reservoir, idx, q);
             store_quarters(B.spatial_reservoir, idx, q);
-            store_quarters(B.previous_spatial_reservoir, idx, q);
+            scatter_claim(P, idx, x, y, SCATTER_BACKGROUND);
             P.planes.variance[2][idx] = 0.0f;
             P.planes.render[2][idx] = make_uint2(0u, 0u);
         } else {
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
             if (previous_pixel(P, previous_uv, false, pidx)) r = unpack_reservoir(load_quarters(B.previous_reservoir, pidx));
             if (!check_previous_reservoir(r, s)) {
                 size_t sidx;
-                if (previous_pixel(P, previous_uv, true, sidx)) store_quarters(B.previous_spatial_reservoir, sidx, pack_reservoir(r));
+                if (previous_pixel(P, previous_uv, true, sidx)) scatter_claim(P, sidx, x, y, SCATTER_MISS);
             }
             Surface surface = retreive_surface(sc, material_id, v2(vu.z, vu.w));
             vec3 view_direction = calculate_view(env, position);
@@ -555,6 +558,30 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
     P.planes.render[SIGNAL][idx] = make_uint2(o.x, o.y);
 }
 
+// ------------------------------------------------------------------------------------------- scatter resolve
+// Applies the winning write of each target pixel to the previous-spatial buffer of `signal` (see Planes::scatter_key).
+__global__ void __launch_bounds__(CTA_THREADS) k_scatter_resolve(const __grid_constant__ KParams P, int signal) {
+    int x, y;
+    tile_pixel(x, y, P.row_lo);
+    if (x >= P.band.W || y >= P.row_hi) return;
+    const size_t idx = band_index(P.band, x, y);
+    const uint32_t key = P.planes.scatter_key[idx];
+    if (key == 0u) return;
+    P.planes.scatter_key[idx] = 0u;   // leave the plane clean for the next pass
+    const uint32_t kind = key & 3u, writer = (key >> 2) - 1u;
+    const PassBuffers B = bind(P, signal);
+    PackedQuarters q;
+    if (kind == SCATTER_VALIDATION) {
+        const int wy = (int)(writer / (uint32_t)P.band.W), wx = (int)(writer % (uint32_t)P.band.W);
+        q = load_quarters(P.planes.scatter_value, band_index(P.band, wx, wy));
+    } else {
+        Reservoir r = zero_reservoir();
+        if (kind == SCATTER_BACKGROUND && signal != 2) set_reservoir(r, zero_sample(), 0.0f);   // light.wgsl:1059-1063 vs :1279-1282
+        q = pack_reservoir(r);
+    }
+    store_quarters(B.previous_spatial_reservoir, idx, q);
+}
+
 // ---------------------------------------------------------------------------------------------- ray-dump hook
 __global__ void k_trace_rays(DeviceScene sc, const hk_ray* rays, size_t n, hk_hit* hits) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -603,6 +630,10 @@ void hk_launch_spatial(const KParams& P, bool emissive, cudaStream_t st) {
     if (P.row_hi <= P.row_lo) return;
     if (emissive) k_spatial<true><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
     else k_spatial<false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+}
+void hk_launch_scatter_resolve(const KParams& P, int signal, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo) return;
+    k_scatter_resolve<<<grid_for(P), CTA_THREADS, 0, st>>>(P, signal);
 }
 void hk_launch_trace_rays(const DeviceScene& sc, const hk_ray* rays, size_t n, hk_hit* hits, cudaStream_t st) {
     if (n == 0) return;

@@ -65,11 +65,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_demodulation(const __grid_const
 // --------------------------------------------------------------------------------------------- denoise level
 struct SignalAcc {
     vec3 irradiance, sum_irradiance;
-    float sum_w, lum, variance, ff_moment_1, ff_moment_2, ff_count;
+    float sum_w, lum, lum_denominator, ff_moment_1, ff_moment_2, ff_count;
 };
 
 template <int LEVEL, bool FUSE_TONE_MAPPING>
-__global__ void __launch_bounds__(CTA_THREADS) k_denoise(const __grid_constant__ KParams P, int signals, int keep_denoised) {
+__global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const __grid_constant__ KParams P, int signals, int keep_denoised) {
     constexpr int STEP = 8 >> LEVEL;  // denoise.wgsl:101-114: coarse to fine
     int x, y;
     tile_pixel(x, y, P.row_lo);
@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_denoise(const __grid_constant__
         for (int sgl = 0; sgl < 3; ++sgl) {
             if (sgl >= signals) continue;
             SignalAcc& a = acc[sgl];
-            a.variance = P.planes.dn_variance[sgl][idx];
+            // denominator of luminance_weight (denoise.wgsl:56-61) depends on the centre pixel only: two sqrt per pixel
+            // instead of two per tap
+            a.lum_denominator = 4.0f * pow025(P.planes.dn_variance[sgl][idx]) + 0.001f;
             a.irradiance = xyz(load16(P.planes.dn_internal[LEVEL][sgl], idx));
             a.sum_irradiance = a.irradiance * kernel_at(P, 1, 1);
             a.sum_w = kernel_at(P, 1, 1);
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_denoise(const __grid_constant__
                 vec3 irr = xyz(load16(P.planes.dn_internal[LEVEL][sgl], sidx));
                 if (bad3(irr)) continue;
                 float sample_luminance = luminance(irr);
-                float w_luminance = exp_((-fabsf(a.lum - sample_luminance)) / (4.0f * pow025(a.variance) + 0.001f));    // :56-61
+                float w_luminance = exp_((-fabsf(a.lum - sample_luminance)) / a.lum_denominator);                       // :56-61
                 float w = clampf(w_geometry * w_luminance, 0.0f, 1.0f) * k;
                 a.sum_irradiance = a.sum_irradiance + irr * w;
                 a.sum_w += w;

@@ -72,6 +72,9 @@ HK_HD float pow16(float x) { x = x * x; x = x * x; x = x * x; return x * x; }
 HK_HD float pow025(float x) { return sqrtf(sqrtf(x)); }
 HK_HD bool is_nan(float v) { return !(v < 0.0f || 0.0f < v || v == 0.0f); }  // utils.wgsl:3-5
 
+// Exact integer -> float for 0 <= v < 2^23 by planting the integer in the mantissa of 2^23 (no I2F on the conversion pipe).
+HK_HD float u23_to_float(uint32_t v) { uint32_t b = 0x4B000000u | v; float f; memcpy(&f, &b, 4); return f - 8388608.0f; }
+
 // x / C, correctly rounded, for the three constants the unpack paths divide by (127, 255, 65535) and integer-valued x
 // with |x| <= C + 1: q = RN(x * RN(1/C)), one Newton correction with the exact remainder (Markstein).  Three
 // instructions instead of the ~12 of a general IEEE division — unpacking reservoirs was ~230 divisions per pixel in the
@@ -107,7 +110,10 @@ HK_HD float exp2_(float x) {
     if (x != x) return x;
     if (x < -126.0f) return 0.0f;
     if (x >= 128.0f) return u2f(0x7F800000u);
-    float n = rintf(x);
+    // round-to-nearest-even of x (|x| <= 128) with the 1.5*2^23 trick: two additions on the FMA pipe instead of
+    // FRND + F2I on the quarter-rate conversion pipe; the integer is read straight from the mantissa bits
+    float t = x + 12582912.0f;
+    float n = t - 12582912.0f;
     float f = x - n;  // [-0.5, 0.5]
     // exp(f ln2), Taylor to degree 7 (Horner, fused)
     float p = 1.5252733804e-5f;
@@ -118,7 +124,7 @@ HK_HD float exp2_(float x) {
     p = fmaf(p, f, 2.4022650696e-1f);
     p = fmaf(p, f, 6.9314718056e-1f);
     p = fmaf(p, f, 1.0f);
-    int32_t e = (int32_t)n;
+    int32_t e = (int32_t)f2u(t) - 0x4B400000;
     // p in [0.70, 1.42]; scale by 2^e in two steps so that e = 128 / -126 stay finite-normal where they must
     int32_t e1 = e / 2, e2 = e - e1;
     return p * u2f((uint32_t)(e1 + 127) << 23) * u2f((uint32_t)(e2 + 127) << 23);
@@ -127,7 +133,8 @@ HK_HD float exp_(float x) { return exp2_(x * 1.4426950408889634f); }
 
 // sin and cos together; intended range |x| <= ~1e3 (callers pass [0, 2*pi]).
 HK_HD void sincos_(float x, float* s_out, float* c_out) {
-    float k = rintf(x * 0.6366197723675814f);  // x * 2/pi
+    float kt = x * 0.6366197723675814f + 12582912.0f;   // x * 2/pi, rounded to nearest even (see exp2_)
+    float k = kt - 12582912.0f;
     float r = fmaf(-k, 1.5707962513e+0f, x);   // Cody-Waite, pi/2 split in three
     r = fmaf(-k, 7.5497894159e-8f, r);
     r = fmaf(-k, 5.3903029534e-15f, r);
@@ -140,7 +147,7 @@ HK_HD void sincos_(float x, float* s_out, float* c_out) {
     cp = fmaf(cp, r2, -1.388731625493765e-3f);
     cp = fmaf(cp, r2, 4.166664568298827e-2f);
     float c = fmaf(cp * r2, r2, fmaf(-0.5f, r2, 1.0f));
-    int32_t q = (int32_t)k & 3;
+    int32_t q = ((int32_t)f2u(kt) - 0x4B400000) & 3;
     float sr = (q & 1) ? c : s;
     float cr = (q & 1) ? s : c;
     if (q & 2) sr = -sr;
@@ -319,8 +326,8 @@ HK_HD uint32_t pack2x16unorm(float a, float b) {
     uint32_t y = (uint32_t)floorf(0.5f + 65535.0f * fmin_(1.0f, fmax_(0.0f, b)));
     return x | (y << 16);
 }
-HK_HD vec2 unpack2x16unorm(uint32_t u) { return v2(div_const<65535>((float)(u & 0xFFFFu)), div_const<65535>((float)(u >> 16))); }
-HK_HD float unorm8(uint32_t b) { return div_const<255>((float)(b & 0xFFu)); }   // Rgba8Unorm texel component
+HK_HD vec2 unpack2x16unorm(uint32_t u) { return v2(div_const<65535>(u23_to_float(u & 0xFFFFu)), div_const<65535>(u23_to_float(u >> 16))); }
+HK_HD float unorm8(uint32_t b) { return div_const<255>(u23_to_float(b & 0xFFu)); }   // Rgba8Unorm texel component
 // WGSL spec: floor(0.5 + 127 * min(1, max(-1, e))), two's complement byte
 HK_HD uint32_t snorm8(float e) {
     int32_t i = (int32_t)floorf(0.5f + 127.0f * fmin_(1.0f, fmax_(-1.0f, e)));
@@ -329,7 +336,10 @@ HK_HD uint32_t snorm8(float e) {
 HK_HD uint32_t pack4x8snorm(vec4 v) {
     return snorm8(v.x) | (snorm8(v.y) << 8) | (snorm8(v.z) << 16) | (snorm8(v.w) << 24);
 }
-HK_HD float unsnorm8(uint32_t b) { return fmax_(div_const<127>((float)(int8_t)(b & 0xFFu)), -1.0f); }
+HK_HD float unsnorm8(uint32_t b) {   // two's-complement byte -> [-128,127] -> /127, clamped at -1
+    float i = u23_to_float((b & 0xFFu) ^ 0x80u) - 128.0f;
+    return fmax_(div_const<127>(i), -1.0f);
+}
 HK_HD vec4 unpack4x8snorm(uint32_t u) {
     return v4(unsnorm8(u), unsnorm8(u >> 8), unsnorm8(u >> 16), unsnorm8(u >> 24));
 }

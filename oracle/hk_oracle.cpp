@@ -1530,6 +1530,59 @@ int hko_trace_rays(hko_context* c, const hk_ray* rays, size_t n, hk_hit* hits) {
     }
     return HK_OK;
 }
+// Diagnostic for kernel design (not a pass of the reference): number of TLAS and BLAS records each ray touches.
+static void count_steps(const Ctx& c, const Ray& ray, float max_distance, float early_distance, uint32_t exclude, uint32_t* out3) {
+    float best = max_distance;
+    uint32_t tlas = 0, blas = 0, leaves = 0;
+    uint32_t index = 0;
+    const uint32_t count = (uint32_t)c.instance_nodes.size();
+    bool done = false;
+    for (; index < count && !done;) {
+        const hk_node& node = c.instance_nodes[index];
+        ++tlas;
+        Aabb aabb;
+        if (node.entry_index >= BVH_LEAF_FLAG) {
+            uint32_t ii = node.entry_index - BVH_LEAF_FLAG;
+            const hk_instance& inst = c.instances[ii];
+            aabb.min = ld3(inst.min); aabb.max = ld3(inst.max);
+            if (ii != exclude && intersects_aabb(ray, aabb) < best) {
+                Ray r;
+                r.origin = instance_position_world_to_local(inst, ray.origin);
+                r.direction = instance_direction_world_to_local(inst, ray.direction);
+                r.inv_direction = 1.0f / r.direction;
+                uint32_t bi = 0;
+                while (bi < inst.mesh.node_count) {
+                    const hk_node& bn = c.asset_nodes[inst.mesh.node_offset + bi];
+                    ++blas;
+                    if (bn.entry_index >= BVH_LEAF_FLAG) {
+                        ++leaves;
+                        const hk_primitive& prim = c.primitives[inst.mesh.primitive + bn.entry_index - BVH_LEAF_FLAG];
+                        Intersection is = intersects_triangle(r, prim);
+                        if (is.distance < best) { best = is.distance; if (is.distance < early_distance) { done = true; break; } }
+                        bi = bn.exit_index;
+                    } else {
+                        aabb.min = ld3(bn.min); aabb.max = ld3(bn.max);
+                        bi = (intersects_aabb(r, aabb) < best) ? bn.entry_index : bn.exit_index;
+                    }
+                }
+            }
+            index = node.exit_index;
+        } else {
+            aabb.min = ld3(node.min); aabb.max = ld3(node.max);
+            index = (intersects_aabb(ray, aabb) < best) ? node.entry_index : node.exit_index;
+        }
+    }
+    out3[0] = tlas; out3[1] = blas; out3[2] = leaves;
+}
+int hko_trace_steps(hko_context* c, const hk_ray* rays, size_t n, uint32_t* steps3) {
+#pragma omp parallel for num_threads(c->threads)
+    for (long long i = 0; i < (long long)n; ++i) {
+        Ray r;
+        r.origin = ld3(rays[i].origin); r.direction = ld3(rays[i].direction); r.inv_direction = 1.0f / r.direction;
+        count_steps(*c, r, rays[i].max_distance, rays[i].early_distance, rays[i].exclude_instance, steps3 + 3 * i);
+    }
+    return HK_OK;
+}
 int hko_get_stats(hko_context* c, hk_frame_stats* out) {
     memset(out, 0, sizeof(*out));
     for (auto& r : c->rays) {

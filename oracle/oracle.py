@@ -48,6 +48,7 @@ def lib():
             "hko_upload_state": (_I, [_P, _I, _P, _SZ]),
             "hko_trace_rays": (_I, [_P, _P, _SZ, _P]),
             "hko_get_stats": (_I, [_P, C.POINTER(L.FrameStats)]),
+            "hko_trace_steps": (_I, [_P, _P, _SZ, _P]),
             "hko_last_error": (C.c_char_p, [_P]),
             "hko_math_exp2": (C.c_float, [C.c_float]),
             "hko_math_exp": (C.c_float, [C.c_float]),
@@ -119,6 +120,12 @@ class Oracle:
         hits = np.zeros(len(rays), L.HIT)
         self._check(lib().hko_trace_rays(self.ctx, rays.ctypes.data, len(rays), hits.ctypes.data))
         return hits
+
+    def trace_steps(self, rays):
+        rays = np.ascontiguousarray(rays, L.RAY)
+        steps = np.zeros((len(rays), 3), np.uint32)
+        self._check(lib().hko_trace_steps(self.ctx, rays.ctypes.data, len(rays), steps.ctypes.data))
+        return steps
 
     def stats(self):
         s = L.FrameStats()

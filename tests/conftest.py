@@ -52,6 +52,20 @@ class Bench:
         from bevy_hikari_b200 import plugin
         return plugin.make_frame_inputs(self.settings, frame, self.view, self.previous_view, self.lights)
 
+    def moving_inputs(self, frame, step=(0.03, 0.01, -0.02)):
+        """Camera translating by `step` per frame; previous_view = the view of frame - 1 (view.rs:47-73)."""
+        from bevy_hikari_b200 import camera as cam
+        from bevy_hikari_b200 import plugin
+
+        def view_at(f):
+            eye = tuple(e + s * (f - 1) for e, s in zip(self.scene.eye, step))
+            tgt = tuple(t + s * (f - 1) for t, s in zip(self.scene.target, step))
+            proj = cam.perspective_infinite_reverse_rh(self.scene.fov, self.width / self.height, self.scene.near)
+            return cam.make_view(cam.look_at(eye, tgt), proj, self.width, self.height)
+        view = view_at(frame)
+        prev = cam.make_previous_view(view_at(max(frame - 1, 1)))
+        return plugin.make_frame_inputs(self.settings, frame, view, prev, self.lights)
+
     def oracle(self, threads=None):
         from bevy_hikari_b200 import plugin
         from oracle import oracle
