@@ -34,6 +34,7 @@ struct hk_context {
     bool scene_ready = false, noise_ready = false;
     uint8_t* noise = nullptr;
     Counters* counters = nullptr;
+    SpatialTable* spatial_tables = nullptr;
     bool count_rays = false, time_passes = false, keep_intermediates = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[HK_K_COUNT][2] = {};   // per-kernel begin/end
@@ -143,6 +144,33 @@ int hk_context_create(hk_context** out, int cuda_device, uint32_t width, uint32_
         if (cudaMalloc(&p, sizeof(Counters)) != cudaSuccess) rc = set_error(c, HK_ERR_OUT_OF_MEMORY, "counters");
         else { c->counters = reinterpret_cast<Counters*>(p); cudaMemsetAsync(p, 0, sizeof(Counters), c->stream); }
     }
+    if (rc == HK_OK) {   // per-neighbour constants of spatial_reuse, light.wgsl:246-253,1566-1572,1609-1620
+        SpatialTable t[2];
+        memset(t, 0, sizeof(t));
+        for (int v = 0; v < 2; ++v) {
+            const uint32_t count = v ? 8u : 16u;
+            const float range = v ? 10.0f : 20.0f;
+            const uint32_t taps = 4u;
+            for (uint32_t i = 1; i <= count; ++i) {
+                t[v].phase[i] = (float)i * hk::GOLDEN_RATIO;
+                const float rad = sqrtf((float)i / (float)count) * range;
+                t[v].radius[i] = rad;
+                const float tap_interval = hk::fmax_(1.0f, rad / (float)(taps + 1u));
+                const uint32_t tap_count = hk::f32_to_u32(rad / tap_interval);
+                t[v].tap_count[i] = tap_count > 6u ? 6u : tap_count;   // never above 5 (radius / (radius / 5))
+                for (uint32_t j = 1; j <= t[v].tap_count[i]; ++j) {
+                    t[v].tap_dist[i][j - 1] = (float)j * tap_interval;
+                    t[v].tap_ratio[i][j - 1] = (float)j / (float)(tap_count + 1u);
+                }
+            }
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, sizeof(t)) != cudaSuccess) rc = set_error(c, HK_ERR_OUT_OF_MEMORY, "spatial tables");
+        else {
+            c->spatial_tables = reinterpret_cast<SpatialTable*>(p);
+            if (cudaMemcpy(p, t, sizeof(t), cudaMemcpyHostToDevice) != cudaSuccess) rc = set_error(c, HK_ERR_CUDA, "spatial tables upload");
+        }
+    }
     if (rc == HK_OK)
         for (int i = 0; i < 4; ++i)
             if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = set_error(c, HK_ERR_CUDA, "cudaEventCreate");
@@ -167,6 +195,7 @@ void hk_context_destroy(hk_context* ctx) {
     free_list(ctx->scene_allocations);
     if (ctx->noise) cudaFree(ctx->noise);
     if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->spatial_tables) cudaFree(ctx->spatial_tables);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < HK_K_COUNT; ++i)
         for (int j = 0; j < 2; ++j) if (ctx->kev[i][j]) cudaEventDestroy(ctx->kev[i][j]);
@@ -337,6 +366,7 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     hk::sincos_(in->frame.solar_angle, &s, &c);
     P.cos_solar_angle = c;
     P.random_frame = hk::random_float(in->frame.number);
+    P.spatial_tables = ctx->spatial_tables;
     return HK_OK;
 }
 static void rows(const hk_context* ctx, KParams& P, int ghost) {

@@ -69,6 +69,16 @@ struct Band {
 
 struct Counters { unsigned long long primary, tlas, blas; };
 
+// Per-neighbour constants of spatial_reuse (light.wgsl:1566-1572,1609-1620): they depend only on the neighbour index i,
+// so they are evaluated once on the host (same IEEE sqrt / division as the shader expression) instead of per pixel.
+struct SpatialTable {
+    float phase[17];        // f32(i) * GOLDEN_RATIO
+    float radius[17];       // sqrt(f32(i) / f32(COUNT)) * RANGE
+    uint32_t tap_count[17]; // u32(radius / max(1, radius / (TAPS + 1)))
+    float tap_dist[17][6];  // f32(j) * tap_interval, j = 1..tap_count  (tap_count is 5 when radius >= 5: r / (r/5))
+    float tap_ratio[17][6]; // f32(j) / f32(tap_count + 1)
+};
+
 struct KParams {
     hk_frame_inputs in;
     DeviceScene scene;
@@ -79,6 +89,7 @@ struct KParams {
     int row_lo, row_hi;     // rows this launch covers (global)
     float cos_solar_angle;  // cos(frame.solar_angle), hk::sincos_ evaluated once on the host with the same routine
     float random_frame;     // random_float(frame.number)
+    const SpatialTable* spatial_tables;   // [0] = indirect (16 neighbours, 20 px), [1] = emissive (8 neighbours, 10 px)
 };
 
 // --------------------------------------------------------------------------------------------- raw loads

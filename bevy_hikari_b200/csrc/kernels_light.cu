@@ -497,9 +497,11 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
     r.s.visible_normal = s.visible_normal;
 
     const vec2 size_f = v2((float)P.band.W, (float)P.band.H);
+    const SpatialTable& T = P.spatial_tables[EMISSIVE_LIT ? 1 : 0];
+    const float rotation = sum4(s.random);
     for (uint32_t i = 1u; i <= SPATIAL_REUSE_COUNT; i += 1u) {
-        float ang = TAU * fract((float)i * GOLDEN_RATIO + sum4(s.random) + P.random_frame);
-        float rad = sqrtf((float)i / (float)SPATIAL_REUSE_COUNT) * SPATIAL_REUSE_RANGE;
+        float ang = TAU * fract(T.phase[i] + rotation + P.random_frame);
+        const float rad = T.radius[i];
         float sn, cs;
         sincos_(ang, &sn, &cs);
         vec2 offset = rad * v2(cs, sn);
@@ -517,17 +519,16 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
         if (dot(sample_direction, s.visible_normal) < 0.0f) continue;
 
         // screen-space depth march towards the neighbour (light.wgsl:1608-1628)
-        float tap_interval = fmax_(1.0f, rad / (float)(SPATIAL_REUSE_TAPS + 1u));
-        uint32_t tap_count = f32_to_u32(rad / tap_interval);
+        const uint32_t tap_count = T.tap_count[i];
         bool occluded = false;
         vec2 unit = normalize(offset);
         for (uint32_t j = 1u; j <= tap_count; j += 1u) {
-            float tap_dist = (float)j * tap_interval;
+            float tap_dist = T.tap_dist[i][j - 1u];
             vec2 tap_uv = uv + (tap_dist * unit) / size_f;
             int tx = f32_to_i32(tap_uv.x * size_f.x), ty = f32_to_i32(tap_uv.y * size_f.y);
             float tap_depth = 0.0f;  // out-of-bounds textureLoad -> 0
             if (tx >= 0 && tx < P.band.W && ty >= 0 && ty < P.band.H) tap_depth = P.planes.pos_depth[band_index(P.band, tx, ty)].w;
-            float ref_depth = mixf(depth, sample_depth, (float)j / (float)(tap_count + 1u));
+            float ref_depth = mixf(depth, sample_depth, T.tap_ratio[i][j - 1u]);
             if (tap_depth > ref_depth + 0.00001f) { occluded = true; break; }
         }
         if (occluded) continue;

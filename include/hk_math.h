@@ -92,12 +92,18 @@ HK_HD float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 // WGSL u32(f32): truncate toward zero, clamped to the u32 range (negative / NaN -> 0).
 HK_HD uint32_t f32_to_u32(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float2uint_rz(f);   // cvt.rzi.u32.f32 already saturates and maps NaN to 0: same function, one instruction
+#endif
     if (!(f > 0.0f)) return 0u;
     if (f >= 4294967296.0f) return 0xFFFFFFFFu;
     return (uint32_t)f;
 }
 // WGSL i32(f32): truncate toward zero, clamped.
 HK_HD int32_t f32_to_i32(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rz(f);    // cvt.rzi.s32.f32: saturating, NaN -> 0
+#endif
     if (f != f) return 0;
     if (f >= 2147483648.0f) return 2147483647;
     if (f <= -2147483648.0f) return (int32_t)0x80000000;
