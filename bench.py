@@ -5,8 +5,8 @@
 
 N = 1: the workload is BASELINE.json configs[1] — cornell 1920x1080, 2 bounces, ReSTIR temporal + spatial (emissive
 and indirect), denoise on — unless --config says otherwise.  N > 1 (launched by torchrun, one rank per GPU): the frame is
-split in N horizontal row bands; every rank renders its band + ghost rows with no data-path exchange,
-then ONE NCCL all-gather assembles the tone-mapped frame on every rank ("scaling": "strong" — total work is fixed).
+split in N equal screen tiles (a columns x rows grid); every rank renders its tile + ghost pixels with no
+data-path exchange, then ONE NCCL all-gather collects the tone-mapped tiles on every rank (tile-major: [rank][row][col]) ("scaling": "strong" — total work is fixed).
 
 Timing: W warm-up frames, then exactly K frames bracketed by barrier + torch.cuda.synchronize(), CUDA events on the
 context's stream (which is torch's current stream), MAX over ranks.  Frames continue the temporal sequence
@@ -99,11 +99,40 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def band(height, rank, world):
-    """rows [r0, r1) owned by `rank`: contiguous bands, equal sizes (the all-gather needs equal contributions)."""
-    assert height % world == 0, "image height must be divisible by the number of GPUs"
-    rows = height // world
-    return rank * rows, (rank + 1) * rows
+GHOST = 36   # rows / columns a tile renders beyond its own rectangle (bevy_hikari_b200/csrc/context.cu GHOST_TEMPORAL)
+
+
+def tile_grid(width, height, world):
+    """(columns, rows) of the tile grid for `world` GPUs: equal tiles (the all-gather needs equal contributions), the
+    factorisation with the most columns among those within 5 % of the least rendered area (incl. ghost pixels): vertical
+    strips share sky / ground evenly, row bands do not."""
+    cands = []
+    for cx in range(1, world + 1):
+        if world % cx:
+            continue
+        cy = world // cx
+        if width % cx or height % cy:
+            continue
+        tw, th = width // cx, height // cy
+        area = 0
+        for j in range(cy):
+            for i in range(cx):
+                w = min(width, (i + 1) * tw + GHOST) - max(0, i * tw - GHOST)
+                h = min(height, (j + 1) * th + GHOST) - max(0, j * th - GHOST)
+                area += w * h
+        cands.append((area, cx, cy))
+    assert cands, "image size must be divisible by a factorisation of the number of GPUs"
+    least = min(a for a, _, _ in cands)
+    area, cx, cy = max((c for c in cands if c[0] <= 1.05 * least), key=lambda c: c[1])   # most columns within 5 % of the least area
+    return cx, cy
+
+
+def tile(width, height, rank, world):
+    """(x0, x1, y0, y1) owned by `rank`; ranks run left to right, then top to bottom."""
+    cx, cy = tile_grid(width, height, world)
+    tw, th = width // cx, height // cy
+    i, j = rank % cx, rank // cx
+    return i * tw, (i + 1) * tw, j * th, (j + 1) * th
 
 
 def make_bench(config):
@@ -124,7 +153,8 @@ def config_json(config, cfg, settings, world_size):
             "scene": cfg["scene"], "width": cfg["width"], "height": cfg["height"], "indirect_bounces": int(settings.indirect_bounces),
             "emissive_spatial_reuse": int(settings.emissive_spatial_reuse), "indirect_spatial_reuse": int(settings.indirect_spatial_reuse),
             "denoise": int(settings.denoise), "upscale": "SmaaTu4x{ratio:1.0}", "taa": "None",
-            "parallelism": f"row-bands x{world_size}" if world_size > 1 else "single GPU",
+            "parallelism": ("%dx%d screen tiles (+%d ghost px), one all-gather of the tone-mapped tiles" % (tile_grid(cfg["width"], cfg["height"], world_size) + (GHOST,)))
+                           if world_size > 1 else "single GPU",
             "l2": "per-frame working set (>1 GB of planes) exceeds L2; no explicit flush"}
 
 
@@ -146,22 +176,22 @@ def run_ours(args):
     assert world_size == args.gpus or world_size == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
     cfg, scene, world, W, H, view, pview, lights, settings = make_bench(args.config)
-    r0, r1 = band(H, rank, world_size)
+    x0, x1, r0, r1 = tile(W, H, rank, world_size)
     # a dedicated non-default stream, made torch's current stream so that torch.cuda.Event, NCCL and the context's
     # kernels are all ordered on the same stream (the legacy default stream has handle 0 = "create your own" in the C ABI)
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
-    dev = plugin.HikariPlugin(W, H, cuda_device=local_rank, row_begin=r0, row_end=r1, cuda_stream=stream.cuda_stream)
+    dev = plugin.HikariPlugin(W, H, cuda_device=local_rank, row_begin=r0, row_end=r1, cuda_stream=stream.cuda_stream,
+                              col_begin=x0, col_end=x1)
     dev.upload_scene(world)
-    own_px = (r1 - r0) * W
 
     # the context's tone-mapped band as a torch tensor (zero copy) for the all-gather
     ptr, nbytes = dev.output_device_pointer()
 
     class _Ext:  # __cuda_array_interface__ view of the context-owned buffer
         __cuda_array_interface__ = {"shape": (nbytes // 2,), "typestr": "<f2", "data": (ptr, False), "version": 3}
-    tile = torch.as_tensor(_Ext(), device=f"cuda:{local_rank}")
-    frame_buf = torch.empty(world_size * tile.numel(), dtype=torch.float16, device=tile.device) if world_size > 1 else None
+    tile_t = torch.as_tensor(_Ext(), device=f"cuda:{local_rank}")
+    frame_buf = torch.empty(world_size * tile_t.numel(), dtype=torch.float16, device=tile_t.device) if world_size > 1 else None
     pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
 
     def barrier():
@@ -172,14 +202,14 @@ def run_ours(args):
     def reduce_max(x):
         if world_size == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=tile.device)
+        t = torch.tensor([x], dtype=torch.float64, device=tile_t.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def reduce_sum(vals):
         if world_size == 1:
             return vals
-        t = torch.tensor(vals, dtype=torch.float64, device=tile.device)
+        t = torch.tensor(vals, dtype=torch.float64, device=tile_t.device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return [float(v) for v in t.tolist()]
 
@@ -195,7 +225,7 @@ def run_ours(args):
     for n in range(W_):
         dev.render_frame(inputs[n])
         if world_size > 1:
-            dist.all_gather_into_tensor(frame_buf, tile)
+            dist.all_gather_into_tensor(frame_buf, tile_t)
     kernel_ms = np.zeros(len(L.KERNEL_NAMES))
     launches = 0
     sampler = ClockSampler(local_rank)
@@ -207,7 +237,7 @@ def run_ours(args):
     for n in range(W_, W_ + K):
         dev.render_frame(inputs[n])
         if world_size > 1:
-            dist.all_gather_into_tensor(frame_buf, tile)
+            dist.all_gather_into_tensor(frame_buf, tile_t)
         # stats of the PREVIOUS frame would need a sync; collect per-kernel times after the loop from a replay below
     e1.record(stream)
     barrier()
@@ -272,8 +302,7 @@ def run_ours(args):
                      "demodulation": 15, "denoise_0": 7, "denoise_1": 3, "denoise_2": 1, "denoise_3": 0, "tone_mapping": 0}
     def launch_pixels(name):
         g = rows_launched[name]
-        lo, hi = max(0, r0 - g), min(H, r1 + g)
-        return (hi - lo) * W
+        return (min(H, r1 + g) - max(0, r0 - g)) * (min(W, x1 + g) - max(0, x0 - g))
     bpp = BYTES_PER_PIXEL[dom] * (signals if dom in PER_SIGNAL else 1)
     if dom == "denoise_3":
         bpp += BYTES_PER_PIXEL["tone_mapping"]      # fused tone mapping

@@ -30,8 +30,10 @@ class Settings(C.Structure):
 SYMBOLS = {
     # include/hikari_b200.h
     "hk_context_create": (_I, [C.POINTER(_P), _I, _U32, _U32, _U32, _U32, _P]),
+    "hk_context_create_tile": (_I, [C.POINTER(_P), _I, _U32, _U32, _U32, _U32, _U32, _U32, _P]),
     "hk_context_destroy": (None, [_P]),
     "hk_context_resize": (_I, [_P, _U32, _U32, _U32, _U32]),
+    "hk_context_resize_tile": (_I, [_P, _U32, _U32, _U32, _U32, _U32, _U32]),
     "hk_reset_temporal_state": (_I, [_P]),
     "hk_scene_upload": (_I, [_P, C.POINTER(L.SceneDesc)]),
     "hk_set_noise": (_I, [_P, _P]),
@@ -48,6 +50,7 @@ SYMBOLS = {
     "hk_set_keep_intermediates": (_I, [_P, _I]),
     "hk_get_stats": (_I, [_P, C.POINTER(L.FrameStats)]),
     "hk_band_rows": (_I, [_P, C.POINTER(_U32), C.POINTER(_U32)]),
+    "hk_tile_rect": (_I, [_P, C.POINTER(_U32 * 4), C.POINTER(_U32 * 4)]),
     "hk_last_error": (C.c_char_p, [_P]),
     "hk_version": (C.c_char_p, []),
     # include/hikari_host.h
@@ -68,6 +71,7 @@ SYMBOLS = {
     "hikari_plugin_create": (_P, []),
     "hikari_plugin_destroy": (None, [_P]),
     "hikari_plugin_build": (_I, [_P, _I, _U32, _U32, _U32, _U32, _P, _P]),
+    "hikari_plugin_build_tile": (_I, [_P, _I, _U32, _U32, _U32, _U32, _U32, _U32, _P, _P]),
     "hikari_plugin_upload_scene": (_I, [_P, _P]),
     "hikari_plugin_run_frame": (_I, [_P, C.POINTER(Settings), C.POINTER(L.View), C.POINTER(L.PreviousView), C.POINTER(L.Lights)]),
     "hikari_plugin_context": (_P, [_P]),

@@ -74,18 +74,22 @@ static void free_list(std::vector<void*>& list) {
     list.clear();
 }
 
-static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end) {
-    if (width == 0 || height == 0 || row_begin >= row_end || row_end > height)
-        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "bad size or row band");
+static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
+                           uint32_t row_begin, uint32_t row_end) {
+    if (width == 0 || height == 0 || row_begin >= row_end || row_end > height || col_begin >= col_end || col_end > width)
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "bad size or tile rectangle");
     free_list(ctx->allocations);
     Band b;
-    b.W = (int)width; b.H = (int)height; b.r0 = (int)row_begin; b.r1 = (int)row_end;
+    b.W = (int)width; b.H = (int)height; b.r0 = (int)row_begin; b.r1 = (int)row_end; b.cx0 = (int)col_begin; b.cx1 = (int)col_end;
     b.a0 = b.r0 - GHOST_TEMPORAL < 0 ? 0 : b.r0 - GHOST_TEMPORAL;
     b.a1 = b.r1 + GHOST_TEMPORAL > b.H ? b.H : b.r1 + GHOST_TEMPORAL;
+    b.ax0 = b.cx0 - GHOST_TEMPORAL < 0 ? 0 : b.cx0 - GHOST_TEMPORAL;
+    b.ax1 = b.cx1 + GHOST_TEMPORAL > b.W ? b.W : b.cx1 + GHOST_TEMPORAL;
+    b.AW = b.ax1 - b.ax0;
     ctx->band = b;
-    const size_t n = (size_t)b.W * (size_t)(b.a1 - b.a0);
+    const size_t n = (size_t)b.AW * (size_t)(b.a1 - b.a0);
     ctx->band_pixels = n;
-    ctx->owned_pixels = (size_t)b.W * (size_t)(b.r1 - b.r0);
+    ctx->owned_pixels = (size_t)(b.cx1 - b.cx0) * (size_t)(b.r1 - b.r0);
     Planes& p = ctx->planes;
     auto& L = ctx->allocations;
     HK_CUDA(alloc_plane(ctx, &p.pos_depth, n, L));
@@ -119,6 +123,11 @@ const char* hk_last_error(hk_context* ctx) { return ctx ? ctx->error.c_str() : g
 
 int hk_context_create(hk_context** out, int cuda_device, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end,
                       void* cuda_stream) {
+    return hk_context_create_tile(out, cuda_device, width, height, 0, width, row_begin, row_end, cuda_stream);
+}
+
+int hk_context_create_tile(hk_context** out, int cuda_device, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
+                           uint32_t row_begin, uint32_t row_end, void* cuda_stream) {
     hk_context* ctx = nullptr;
     if (!out) return set_error(nullptr, HK_ERR_INVALID_ARGUMENT, "out == NULL");
     *out = nullptr;
@@ -138,7 +147,7 @@ int hk_context_create(hk_context** out, int cuda_device, uint32_t width, uint32_
         if (e != cudaSuccess) { delete c; return set_error(nullptr, HK_ERR_CUDA, cudaGetErrorString(e)); }
         c->own_stream = true;
     }
-    int rc = allocate_planes(c, width, height, row_begin, row_end);
+    int rc = allocate_planes(c, width, height, col_begin, col_end, row_begin, row_end);
     if (rc == HK_OK) {
         void* p = nullptr;
         if (cudaMalloc(&p, sizeof(Counters)) != cudaSuccess) rc = set_error(c, HK_ERR_OUT_OF_MEMORY, "counters");
@@ -204,10 +213,14 @@ void hk_context_destroy(hk_context* ctx) {
 }
 
 int hk_context_resize(hk_context* ctx, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end) {
+    return hk_context_resize_tile(ctx, width, height, 0, width, row_begin, row_end);
+}
+int hk_context_resize_tile(hk_context* ctx, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
+                           uint32_t row_begin, uint32_t row_end) {
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;
     HK_CUDA(cudaSetDevice(ctx->device));
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
-    return allocate_planes(ctx, width, height, row_begin, row_end);  // planes come back zeroed (light.rs:342-363)
+    return allocate_planes(ctx, width, height, col_begin, col_end, row_begin, row_end);  // zeroed planes (light.rs:342-363)
 }
 
 int hk_reset_temporal_state(hk_context* ctx) {
@@ -369,9 +382,12 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     P.spatial_tables = ctx->spatial_tables;
     return HK_OK;
 }
-static void rows(const hk_context* ctx, KParams& P, int ghost) {
-    P.row_lo = ctx->band.r0 - ghost < ctx->band.a0 ? ctx->band.a0 : ctx->band.r0 - ghost;
-    P.row_hi = ctx->band.r1 + ghost > ctx->band.a1 ? ctx->band.a1 : ctx->band.r1 + ghost;
+static void rows(const hk_context* ctx, KParams& P, int ghost) {   // owned rectangle grown by `ghost`, clamped to the allocation
+    const Band& b = ctx->band;
+    P.row_lo = b.r0 - ghost < b.a0 ? b.a0 : b.r0 - ghost;
+    P.row_hi = b.r1 + ghost > b.a1 ? b.a1 : b.r1 + ghost;
+    P.col_lo = b.cx0 - ghost < b.ax0 ? b.ax0 : b.cx0 - ghost;
+    P.col_hi = b.cx1 + ghost > b.ax1 ? b.ax1 : b.cx1 + ghost;
 }
 static int check_launch(hk_context* ctx) {
     cudaError_t e = cudaGetLastError();
@@ -504,25 +520,38 @@ int hk_band_rows(hk_context* ctx, uint32_t* a0, uint32_t* a1) {
     if (a1) *a1 = (uint32_t)ctx->band.a1;
     return HK_OK;
 }
+int hk_tile_rect(hk_context* ctx, uint32_t allocated[4], uint32_t owned[4]) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    const Band& b = ctx->band;
+    if (allocated) { allocated[0] = b.ax0; allocated[1] = b.ax1; allocated[2] = b.a0; allocated[3] = b.a1; }
+    if (owned) { owned[0] = b.cx0; owned[1] = b.cx1; owned[2] = b.r0; owned[3] = b.r1; }
+    return HK_OK;
+}
 
 }  // extern "C"
 
 // ----------------------------------------------------------------------------------------- outputs / state
-__global__ void k_gather_reservoir(ReservoirPlanes b, size_t first, size_t n, uint4* out) {
+// owned rectangle of a reservoir buffer <-> the reference's AoS PackedReservoir layout
+__global__ void k_gather_reservoir(ReservoirPlanes b, Band band, size_t n, uint4* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for (int q = 0; q < 4; ++q) out[4 * i + q] = b.q[q][first + i];
+    const int ow = band.cx1 - band.cx0;
+    const size_t src = band_index(band, band.cx0 + (int)(i % (size_t)ow), band.r0 + (int)(i / (size_t)ow));
+    for (int q = 0; q < 4; ++q) out[4 * i + q] = b.q[q][src];
 }
-__global__ void k_scatter_reservoir(ReservoirPlanes b, size_t first, size_t n, const uint4* in) {
+__global__ void k_scatter_reservoir(ReservoirPlanes b, Band band, size_t n, const uint4* in) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for (int q = 0; q < 4; ++q) b.q[q][first + i] = in[4 * i + q];
+    const int ow = band.cx1 - band.cx0;
+    const size_t dst = band_index(band, band.cx0 + (int)(i % (size_t)ow), band.r0 + (int)(i / (size_t)ow));
+    for (int q = 0; q < 4; ++q) b.q[q][dst] = in[4 * i + q];
 }
 
-// device pointer of the owned rows of a plane + bytes per pixel; reservoirs are handled separately
+// device pointer of the first owned pixel of a plane + bytes per pixel (row pitch = AW pixels, except the tightly packed
+// tone-mapped plane); reservoirs are handled separately
 static void* owned_plane(hk_context* ctx, int which, size_t* bpp) {
     const Planes& p = ctx->planes;
-    const size_t first = (size_t)(ctx->band.r0 - ctx->band.a0) * (size_t)ctx->band.W;
+    const size_t first = (size_t)(ctx->band.r0 - ctx->band.a0) * (size_t)ctx->band.AW + (size_t)(ctx->band.cx0 - ctx->band.ax0);
     switch (which) {
         case HK_OUT_TONE_MAPPED: *bpp = 8; return p.tone_mapped;
         case HK_OUT_RENDER_DIRECT: case HK_OUT_RENDER_EMISSIVE: case HK_OUT_RENDER_INDIRECT:
@@ -559,15 +588,14 @@ static int transfer(hk_context* ctx, int which, void* host, size_t bytes, bool t
         if (bytes != n * 64) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
         uint4* tmp = nullptr;
         HK_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), bytes));
-        const size_t first = (size_t)(ctx->band.r0 - ctx->band.a0) * (size_t)ctx->band.W;
         const unsigned blocks = (unsigned)((n + 255) / 256);
         cudaError_t e;
         if (to_host) {
-            k_gather_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], first, n, tmp);
+            k_gather_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], ctx->band, n, tmp);
             e = cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream);
         } else {
             e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
-            k_scatter_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], first, n, tmp);
+            k_scatter_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], ctx->band, n, tmp);
         }
         cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
         cudaFree(tmp);
@@ -579,8 +607,10 @@ static int transfer(hk_context* ctx, int which, void* host, size_t bytes, bool t
     void* dev = owned_plane(ctx, which, &bpp);
     if (!dev) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown plane id");
     if (bytes != n * bpp) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
-    if (to_host) HK_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    else HK_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t ow = (size_t)(ctx->band.cx1 - ctx->band.cx0), oh = (size_t)(ctx->band.r1 - ctx->band.r0);
+    const size_t dev_pitch = (which == HK_OUT_TONE_MAPPED ? ow : (size_t)ctx->band.AW) * bpp;
+    if (to_host) HK_CUDA(cudaMemcpy2DAsync(host, ow * bpp, dev, dev_pitch, ow * bpp, oh, cudaMemcpyDeviceToHost, ctx->stream));
+    else HK_CUDA(cudaMemcpy2DAsync(dev, dev_pitch, host, ow * bpp, ow * bpp, oh, cudaMemcpyHostToDevice, ctx->stream));
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }

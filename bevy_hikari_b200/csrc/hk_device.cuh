@@ -61,10 +61,11 @@ struct Planes {
     uint2* tone_mapped;         // owned rows only, tightly packed (row_begin is row 0)
 };
 
-struct Band {
-    int W, H;            // full image
-    int a0, a1;          // allocated rows [a0,a1)
-    int r0, r1;          // owned rows
+struct Band {             // the tile of the frame one context renders (whole frame: everything 0..W, 0..H)
+    int W, H;             // full image
+    int ax0, ax1, a0, a1; // allocated rectangle: columns [ax0,ax1), rows [a0,a1) = owned +- ghost, clamped to the image
+    int cx0, cx1, r0, r1; // owned rectangle: columns [cx0,cx1), rows [r0,r1)
+    int AW;               // ax1 - ax0: row stride of every plane
 };
 
 struct Counters { unsigned long long primary, tlas, blas; };
@@ -87,6 +88,7 @@ struct KParams {
     Counters* counters;     // nullptr = counting compiled in but disabled at run time
     const uint8_t* noise;   // 16 x 64 x 64 x 4
     int row_lo, row_hi;     // rows this launch covers (global)
+    int col_lo, col_hi;     // columns this launch covers (global)
     float cos_solar_angle;  // cos(frame.solar_angle), hk::sincos_ evaluated once on the host with the same routine
     float random_frame;     // random_float(frame.number)
     const SpatialTable* spatial_tables;   // [0] = indirect (16 neighbours, 20 px), [1] = emissive (8 neighbours, 10 px)
@@ -711,7 +713,10 @@ __device__ __forceinline__ LightCandidate select_light_candidate(const DeviceSce
 }
 
 // -------------------------------------------------------------------------------------------- pixel helpers
-__device__ __forceinline__ size_t band_index(const Band& b, int x, int y) { return (size_t)(y - b.a0) * (size_t)b.W + (size_t)x; }
+__device__ __forceinline__ size_t band_index(const Band& b, int x, int y) { return (size_t)(y - b.a0) * (size_t)b.AW + (size_t)(x - b.ax0); }
+__device__ __forceinline__ bool band_allocated(const Band& b, int x, int y) { return x >= b.ax0 && x < b.ax1 && y >= b.a0 && y < b.a1; }
+__device__ __forceinline__ bool band_owned(const Band& b, int x, int y) { return x >= b.cx0 && x < b.cx1 && y >= b.r0 && y < b.r1; }
+__device__ __forceinline__ size_t owned_index(const Band& b, int x, int y) { return (size_t)(y - b.r0) * (size_t)(b.cx1 - b.cx0) + (size_t)(x - b.cx0); }
 
 // blue-noise fetch, light.wgsl:1075-1079 (nearest + repeat on a 64x64 texture == integer wrap)
 __device__ __forceinline__ vec4 noise_random(const KParams& P, int x, int y) {
@@ -745,10 +750,11 @@ constexpr int TILE_W = 16, TILE_H = 8, CTA_THREADS = 128;
 #ifndef HK_MINB_SPATIAL
 #define HK_MINB_SPATIAL 8
 #endif
-__device__ __forceinline__ void tile_pixel(int& x, int& y, int row_lo) {
+__device__ __forceinline__ void tile_pixel(int& x, int& y, const KParams& P) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    x = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
-    y = row_lo + blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    x = P.col_lo + blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
+    y = P.row_lo + blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
 }
+__device__ __forceinline__ bool tile_active(const KParams& P, int x, int y) { return x < P.col_hi && y < P.row_hi; }
 
 }  // namespace hkd

@@ -44,8 +44,8 @@ __device__ __forceinline__ Ray primary_ray(const KParams& P, const mat4& inv_vie
 template <bool COUNT>
 __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__ KParams P) {
     int x, y;
-    tile_pixel(x, y, P.row_lo);
-    const bool active = x < P.band.W && y < P.row_hi;
+    tile_pixel(x, y, P);
+    const bool active = tile_active(P, x, y);
     uint32_t n_primary = 0;
     if (active) {
         const size_t idx = band_index(P.band, x, y);
@@ -127,15 +127,15 @@ __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__
             P.planes.albedo[idx] = make_uint2(alb.x, alb.y);
         }
     }
-    if (y < P.band.r0 || y >= P.band.r1) n_primary = 0;   // ghost rows are redundant work: not counted
+    if (!band_owned(P.band, x, y)) n_primary = 0;   // ghost pixels are redundant work: not counted
     flush_counters<COUNT>(P, n_primary, 0u, 0u);
 }
 
 // stand-alone full_screen_albedo for externally supplied G-buffers
 __global__ void __launch_bounds__(CTA_THREADS) k_albedo(const __grid_constant__ KParams P) {
     int x, y;
-    tile_pixel(x, y, P.row_lo);
-    if (x >= P.band.W || y >= P.row_hi) return;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
     const size_t idx = band_index(P.band, x, y);
     float4 pd = P.planes.pos_depth[idx];
     if (pd.w < F32_EPSILON) { P.planes.albedo[idx] = make_uint2(0u, 0u); return; }
@@ -169,7 +169,7 @@ __device__ __forceinline__ bool previous_pixel(const KParams& P, vec2 previous_u
     bool inside = inclusive ? (ax <= 0.5f && ay <= 0.5f) : (ax < 0.5f && ay < 0.5f);
     if (!inside) return false;
     int px = f32_to_i32(previous_uv.x * (float)P.band.W), py = f32_to_i32(previous_uv.y * (float)P.band.H);
-    if (px < 0 || px >= P.band.W || py < P.band.a0 || py >= P.band.a1) return false;
+    if (!band_allocated(P.band, px, py)) return false;
     pidx = band_index(P.band, px, py);
     return true;
 }
@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
     constexpr int SIGNAL = EMISSIVE_LIT ? 1 : 0;
     constexpr bool RENDER_EMISSIVE = !EMISSIVE_LIT;
     int x, y;
-    tile_pixel(x, y, P.row_lo);
-    const bool active = x < P.band.W && y < P.row_hi;
+    tile_pixel(x, y, P);
+    const bool active = tile_active(P, x, y);
     uint32_t n_tlas = 0, n_blas = 0;
     if (active) {
         const DeviceScene& sc = P.scene;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
             P.planes.render[SIGNAL][idx] = make_uint2(o.x, o.y);
         }
     }
-    if (y < P.band.r0 || y >= P.band.r1) { n_tlas = 0; n_blas = 0; }   // ghost rows are redundant work: not counted
+    if (!band_owned(P.band, x, y)) { n_tlas = 0; n_blas = 0; }   // ghost pixels are redundant work: not counted
     flush_counters<COUNT>(P, 0u, n_tlas, n_blas);
 }
 
@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
 template <bool MULTI, bool COUNT>
 __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(const __grid_constant__ KParams P) {
     int x, y;
-    tile_pixel(x, y, P.row_lo);
-    const bool active = x < P.band.W && y < P.row_hi;
+    tile_pixel(x, y, P);
+    const bool active = tile_active(P, x, y);
     uint32_t n_tlas = 0, n_blas = 0;
     if (active) {
         const DeviceScene& sc = P.scene;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
             P.planes.render[2][idx] = make_uint2(o.x, o.y);
         }
     }
-    if (y < P.band.r0 || y >= P.band.r1) { n_tlas = 0; n_blas = 0; }   // ghost rows are redundant work: not counted
+    if (!band_owned(P.band, x, y)) { n_tlas = 0; n_blas = 0; }   // ghost pixels are redundant work: not counted
     flush_counters<COUNT>(P, 0u, n_tlas, n_blas);
 }
 
@@ -452,8 +452,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
     constexpr float SPATIAL_REUSE_RANGE = EMISSIVE_LIT ? 10.0f : 20.0f;
     constexpr uint32_t SPATIAL_REUSE_TAPS = 4u;
     int x, y;
-    tile_pixel(x, y, P.row_lo);
-    if (x >= P.band.W || y >= P.row_hi) return;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
     const DeviceScene& sc = P.scene;
     const hk_frame_uniform& frame = P.in.frame;
     const size_t idx = band_index(P.band, x, y);
@@ -563,8 +563,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
 // Applies the winning write of each target pixel to the previous-spatial buffer of `signal` (see Planes::scatter_key).
 __global__ void __launch_bounds__(CTA_THREADS) k_scatter_resolve(const __grid_constant__ KParams P, int signal) {
     int x, y;
-    tile_pixel(x, y, P.row_lo);
-    if (x >= P.band.W || y >= P.row_hi) return;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
     const size_t idx = band_index(P.band, x, y);
     const uint32_t key = P.planes.scatter_key[idx];
     if (key == 0u) return;
@@ -598,8 +598,8 @@ __global__ void k_trace_rays(DeviceScene sc, const hk_ray* rays, size_t n, hk_hi
 
 // ------------------------------------------------------------------------------------------------ launchers
 static dim3 grid_for(const KParams& P) {
-    int rows = P.row_hi - P.row_lo;
-    return dim3((unsigned)((P.band.W + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
+    int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
+    return dim3((unsigned)((cols + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
 }
 
 }  // namespace hkd
@@ -607,33 +607,33 @@ static dim3 grid_for(const KParams& P) {
 using namespace hkd;
 
 void hk_launch_gbuffer(const KParams& P, bool count, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo) return;
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     if (count) k_gbuffer<true><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
     else k_gbuffer<false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }
 void hk_launch_albedo(const KParams& P, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo) return;
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_albedo<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }
 void hk_launch_direct(const KParams& P, bool emissive, bool count, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo) return;
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     dim3 g = grid_for(P);
     if (emissive) { if (count) k_direct<true, true><<<g, CTA_THREADS, 0, st>>>(P); else k_direct<true, false><<<g, CTA_THREADS, 0, st>>>(P); }
     else { if (count) k_direct<false, true><<<g, CTA_THREADS, 0, st>>>(P); else k_direct<false, false><<<g, CTA_THREADS, 0, st>>>(P); }
 }
 void hk_launch_indirect(const KParams& P, bool multi, bool count, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo) return;
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     dim3 g = grid_for(P);
     if (multi) { if (count) k_indirect<true, true><<<g, CTA_THREADS, 0, st>>>(P); else k_indirect<true, false><<<g, CTA_THREADS, 0, st>>>(P); }
     else { if (count) k_indirect<false, true><<<g, CTA_THREADS, 0, st>>>(P); else k_indirect<false, false><<<g, CTA_THREADS, 0, st>>>(P); }
 }
 void hk_launch_spatial(const KParams& P, bool emissive, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo) return;
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     if (emissive) k_spatial<true><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
     else k_spatial<false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }
 void hk_launch_scatter_resolve(const KParams& P, int signal, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo) return;
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_scatter_resolve<<<grid_for(P), CTA_THREADS, 0, st>>>(P, signal);
 }
 void hk_launch_trace_rays(const DeviceScene& sc, const hk_ray* rays, size_t n, hk_hit* hits, cudaStream_t st) {

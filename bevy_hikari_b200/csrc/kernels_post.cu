@@ -30,8 +30,8 @@ __device__ __forceinline__ float kernel_at(const KParams& P, int a, int b) { ret
 // denoise.wgsl:135-162 for all signals of a pixel.
 __global__ void __launch_bounds__(CTA_THREADS) k_demodulation(const __grid_constant__ KParams P, int signals) {
     int x, y;
-    tile_pixel(x, y, P.row_lo);
-    if (x >= P.band.W || y >= P.row_hi) return;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
     const size_t idx = band_index(P.band, x, y);
     {   // tap geometry for the four a-trous levels: the normalised normal, depth and instance id of this pixel are read
         // by up to 36 taps; normalise once here instead of 36 times there (same operations, same values)
@@ -72,8 +72,8 @@ template <int LEVEL, bool FUSE_TONE_MAPPING>
 __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const __grid_constant__ KParams P, int signals, int keep_denoised) {
     constexpr int STEP = 8 >> LEVEL;  // denoise.wgsl:101-114: coarse to fine
     int x, y;
-    tile_pixel(x, y, P.row_lo);
-    if (x >= P.band.W || y >= P.row_hi) return;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
     const size_t idx = band_index(P.band, x, y);
     const float4 geometry = P.planes.dn_geometry[idx];
     const float depth = geometry.w;
@@ -172,12 +172,12 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
         if (!FUSE_TONE_MAPPING || keep_denoised) P.planes.dn_render[sgl][idx] = make_uint2(w.x, w.y);
         if (FUSE_TONE_MAPPING) color = color + unpack_rgba16f(w);
     }
-    if (FUSE_TONE_MAPPING && y >= P.band.r0 && y < P.band.r1) {
+    if (FUSE_TONE_MAPPING && band_owned(P.band, x, y)) {
         vec3 rgb = reinhard_luminance(vmax(xyz(color), 0.0039f));
         color = v4(rgb, color.w);
         if (!(color.w > 0.0f))
             color = v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]);
-        store16(P.planes.tone_mapped, (size_t)(y - P.band.r0) * (size_t)P.band.W + (size_t)x, color);
+        store16(P.planes.tone_mapped, owned_index(P.band, x, y), color);
     }
 }
 
@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
 // tone_mapping.wgsl:21-32 stand-alone (denoise off, or nodes run one by one); inputs per post_process.rs:940-954.
 __global__ void __launch_bounds__(CTA_THREADS) k_tone_mapping(const __grid_constant__ KParams P) {
     int x, y;
-    tile_pixel(x, y, P.row_lo);
-    if (x >= P.band.W || y >= P.row_hi) return;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
     const size_t idx = band_index(P.band, x, y);
     const bool dn = P.in.denoise != 0u;
     uint2* const* src = dn ? P.planes.dn_render : P.planes.render;
@@ -197,12 +197,12 @@ __global__ void __launch_bounds__(CTA_THREADS) k_tone_mapping(const __grid_const
     color = v4(rgb, color.w);
     if (!(color.w > 0.0f))
         color = v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]);
-    store16(P.planes.tone_mapped, (size_t)(y - P.band.r0) * (size_t)P.band.W + (size_t)x, color);
+    store16(P.planes.tone_mapped, owned_index(P.band, x, y), color);
 }
 
 static dim3 grid_for(const KParams& P) {
-    int rows = P.row_hi - P.row_lo;
-    return dim3((unsigned)((P.band.W + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
+    int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
+    return dim3((unsigned)((cols + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
 }
 
 }  // namespace hkd
@@ -210,11 +210,11 @@ static dim3 grid_for(const KParams& P) {
 using namespace hkd;
 
 void hk_launch_demodulation(const KParams& P, int signals, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo) return;
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_demodulation<<<grid_for(P), CTA_THREADS, 0, st>>>(P, signals);
 }
 void hk_launch_denoise_level(const KParams& P, int level, int signals, bool fuse_tone_mapping, bool keep_denoised, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo) return;
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     dim3 g = grid_for(P);
     int keep = keep_denoised ? 1 : 0;
     switch (level) {
@@ -227,6 +227,6 @@ void hk_launch_denoise_level(const KParams& P, int level, int signals, bool fuse
     }
 }
 void hk_launch_tone_mapping(const KParams& P, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo) return;
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_tone_mapping<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }

@@ -516,8 +516,12 @@ int PostProcessNode::run(hk_context* ctx, const hk_frame_inputs& in) { return hk
 HikariPlugin::~HikariPlugin() { if (ctx_) hk_context_destroy(ctx_); }
 int HikariPlugin::build(int cuda_device, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end,
                         const uint8_t* noise, void* cuda_stream) {
+    return build_tile(cuda_device, width, height, 0, width, row_begin, row_end, noise, cuda_stream);
+}
+int HikariPlugin::build_tile(int cuda_device, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
+                             uint32_t row_begin, uint32_t row_end, const uint8_t* noise, void* cuda_stream) {
     if (ctx_) { hk_context_destroy(ctx_); ctx_ = nullptr; }
-    int e = hk_context_create(&ctx_, cuda_device, width, height, row_begin, row_end, cuda_stream);
+    int e = hk_context_create_tile(&ctx_, cuda_device, width, height, col_begin, col_end, row_begin, row_end, cuda_stream);
     if (e != HK_OK) return e;
     counter.value = 0;
     return hk_set_noise(ctx_, noise);

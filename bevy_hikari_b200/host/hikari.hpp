@@ -182,6 +182,9 @@ public:
     HikariPlugin& operator=(const HikariPlugin&) = delete;
     int build(int cuda_device, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end,
               const uint8_t* noise_rgba8_64x64x16, void* cuda_stream);
+    // same for a rectangular tile of the camera target (multi-GPU sharding in two dimensions)
+    int build_tile(int cuda_device, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end, uint32_t row_begin,
+                   uint32_t row_end, const uint8_t* noise_rgba8_64x64x16, void* cuda_stream);
     int upload_scene(const MeshMaterialWorld& world);
     // One frame of the camera's sub-graph: PREPASS -> LIGHT -> POST_PROCESS (lib.rs:258-365).  Increments the counter
     // first, as frame_counter_system does in PostUpdate (view.rs:89-103).

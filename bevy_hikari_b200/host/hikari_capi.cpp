@@ -113,6 +113,10 @@ int hikari_plugin_build(hikari_plugin* p, int cuda_device, uint32_t width, uint3
                         uint32_t row_end, const uint8_t* noise, void* cuda_stream) {
     return P(p)->build(cuda_device, width, height, row_begin, row_end, noise, cuda_stream);
 }
+int hikari_plugin_build_tile(hikari_plugin* p, int cuda_device, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
+                             uint32_t row_begin, uint32_t row_end, const uint8_t* noise, void* cuda_stream) {
+    return P(p)->build_tile(cuda_device, width, height, col_begin, col_end, row_begin, row_end, noise, cuda_stream);
+}
 int hikari_plugin_upload_scene(hikari_plugin* p, hikari_world* w) { return P(p)->upload_scene(*W(w)); }
 int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk_view* view,
                             const hk_previous_view* previous_view, const hk_lights* lights) {

@@ -137,13 +137,14 @@ def scene_desc_from_buffers(buffers, textures=()):
 class HikariPlugin:
     """HikariPlugin + one camera with `CameraRenderGraph::new(graph::NAME)` (src/lib.rs:95-370)."""
 
-    def __init__(self, width, height, cuda_device=0, row_begin=0, row_end=None, cuda_stream=None):
+    def __init__(self, width, height, cuda_device=0, row_begin=0, row_end=None, cuda_stream=None, col_begin=0, col_end=None):
         self.width, self.height = width, height
         self.row_begin, self.row_end = row_begin, height if row_end is None else row_end
+        self.col_begin, self.col_end = col_begin, width if col_end is None else col_end
         self._p = lib().hikari_plugin_create()
         noise = load_noise()
-        rc = lib().hikari_plugin_build(self._p, cuda_device, width, height, self.row_begin, self.row_end, noise.ctypes.data,
-                                       cuda_stream)
+        rc = lib().hikari_plugin_build_tile(self._p, cuda_device, width, height, self.col_begin, self.col_end, self.row_begin,
+                                            self.row_end, noise.ctypes.data, cuda_stream)
         if rc != _ffi.HK_OK:
             msg = lib().hk_last_error(None).decode()
             lib().hikari_plugin_destroy(self._p)
@@ -162,6 +163,10 @@ class HikariPlugin:
     @property
     def owned_rows(self):
         return self.row_end - self.row_begin
+
+    @property
+    def owned_cols(self):
+        return self.col_end - self.col_begin
 
     def upload_scene(self, world):
         check(lib().hikari_plugin_upload_scene(self._p, world._w), self.ctx)
@@ -198,11 +203,11 @@ class HikariPlugin:
 
     def readback(self, which, out=None):
         bpp, dt, comps = L.OUT_FORMATS[which]
-        n = self.owned_rows * self.width
+        n = self.owned_rows * self.owned_cols
         if out is None:
             out = np.empty(n * bpp, np.uint8)
         check(lib().hk_readback(self.ctx, which, out.ctypes.data, n * bpp), self.ctx)
-        return view_plane(out, which, self.owned_rows, self.width)
+        return view_plane(out, which, self.owned_rows, self.owned_cols)
 
     def readback_into(self, which, host_ptr, nbytes):
         check(lib().hk_readback(self.ctx, which, host_ptr, nbytes), self.ctx)

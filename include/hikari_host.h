@@ -59,6 +59,8 @@ hikari_plugin* hikari_plugin_create(void);
 void hikari_plugin_destroy(hikari_plugin* p);
 int hikari_plugin_build(hikari_plugin* p, int cuda_device, uint32_t width, uint32_t height, uint32_t row_begin,
                         uint32_t row_end, const uint8_t* noise_rgba8_64x64x16, void* cuda_stream);
+int hikari_plugin_build_tile(hikari_plugin* p, int cuda_device, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
+                             uint32_t row_begin, uint32_t row_end, const uint8_t* noise_rgba8_64x64x16, void* cuda_stream);
 int hikari_plugin_upload_scene(hikari_plugin* p, hikari_world* w);
 int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk_view* view,
                             const hk_previous_view* previous_view, const hk_lights* lights);

@@ -73,9 +73,9 @@ class Bench:
         o.upload_scene_desc(self.world.scene_desc())
         return o
 
-    def device(self, row_begin=0, row_end=None):
+    def device(self, row_begin=0, row_end=None, col_begin=0, col_end=None):
         from bevy_hikari_b200 import plugin
-        p = plugin.HikariPlugin(self.width, self.height, 0, row_begin, row_end)
+        p = plugin.HikariPlugin(self.width, self.height, 0, row_begin, row_end, None, col_begin, col_end)
         p.upload_scene(self.world)
         return p
 

@@ -34,7 +34,7 @@ def compare_all(dev, orc, planes, frame, allow=0):
         n = mismatch(dev.readback(k), orc.readback(k))
         if n > allow:
             bad[k] = n
-    assert not bad, f"frame {frame}: planes with differing pixels {bad} (of {dev.width * dev.owned_rows})"
+    assert not bad, f"frame {frame}: planes with differing pixels {bad} (of {dev.owned_cols * dev.owned_rows})"
 
 
 def random_rays(n, seed, any_hit_fraction=0.3):
@@ -168,6 +168,27 @@ def test_row_bands_equal_unsharded():
             whole = full.readback(k)
             parts = np.concatenate([top.readback(k), bot.readback(k)], axis=0)
             assert mismatch(whole, parts) == 0, (f, k)
+
+
+def test_2d_tiles_equal_unsharded():
+    """Four contexts owning a 2x2 grid of tiles (plus ghost rows AND ghost columns) reproduce the unsharded frame."""
+    b = Bench("cornell", 176, 144, config="cornell_1080p")
+    full = b.device()
+    tiles = [b.device(0, 72, 0, 88), b.device(0, 72, 88, 176), b.device(72, 144, 0, 88), b.device(72, 144, 88, 176)]
+    for d in tiles + [full]:
+        d.set_profiling(True, False)
+    for f in range(1, 7):
+        inp = b.inputs(f)
+        for d in tiles + [full]:
+            d.render_frame(inp)
+        for k in (L.OUT_TONE_MAPPED, L.OUT_RENDER_INDIRECT, L.OUT_RESERVOIR_0 + 4, L.OUT_RESERVOIR_0 + 8, L.OUT_GBUFFER_POSITION):
+            whole = full.readback(k)
+            t = [d.readback(k) for d in tiles]
+            parts = np.concatenate([np.concatenate(t[:2], axis=1), np.concatenate(t[2:], axis=1)], axis=0)
+            assert mismatch(whole, parts) == 0, (f, k)
+        sw = full.stats()
+        st = [d.stats() for d in tiles]
+        assert sum(s.tlas_rays for s in st) == sw.tlas_rays and sum(s.blas_rays for s in st) == sw.blas_rays   # ghosts not counted
 
 
 def test_ray_counts_match_oracle():

@@ -113,7 +113,7 @@ def test_resize_and_reset_zero_the_temporal_state():
     assert not any(dev.readback(L.OUT_RESERVOIR_0 + i).tobytes().strip(b"\0") for i in range(10))
     # resize: planes re-allocated and zeroed like ReservoirCache does when size.x*size.y changes (light.rs:342-363)
     _ffi.check(_ffi.lib().hk_context_resize(dev.ctx, 32, 24, 0, 24), dev.ctx)
-    dev.width, dev.height, dev.row_begin, dev.row_end = 32, 24, 0, 24
+    dev.width, dev.height, dev.row_begin, dev.row_end, dev.col_begin, dev.col_end = 32, 24, 0, 24, 0, 32
     b2 = Bench("cornell", 32, 24, config="cornell_1080p")
     fresh = b2.device()
     for f in range(1, 4):

@@ -24,13 +24,19 @@ def _worker(rank, world, port, height, width, full_bytes, out_dir):
     import bench
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    r0, r1 = bench.band(height, rank, world)
+    x0, x1, r0, r1 = bench.tile(width, height, rank, world)
     full = torch.frombuffer(bytearray(full_bytes), dtype=torch.float16).reshape(height, width, 4)
-    tile = full[r0:r1].contiguous().reshape(-1)              # what hk_get_output(HK_OUT_TONE_MAPPED) holds on this rank
+    tile = full[r0:r1, x0:x1].contiguous().reshape(-1)       # what hk_get_output(HK_OUT_TONE_MAPPED) holds on this rank
     frame = torch.empty(world * tile.numel(), dtype=torch.float16)
     dist.all_gather_into_tensor(frame, tile)                  # the one collective of the path
-    ok = torch.equal(frame.view(torch.int16), full.reshape(-1).view(torch.int16))
-    t = torch.tensor([1.0 if ok else 0.0, float(r1 - r0)])
+    # the gathered buffer is tile-major: [rank][row][col]; re-assemble and compare with the unsharded frame
+    tiles = frame.reshape(world, r1 - r0, x1 - x0, 4)
+    rebuilt = torch.empty_like(full)
+    for r in range(world):
+        a0, a1, b0, b1 = bench.tile(width, height, r, world)
+        rebuilt[b0:b1, a0:a1] = tiles[r]
+    ok = torch.equal(rebuilt.view(torch.int16), full.view(torch.int16))
+    t = torch.tensor([1.0 if ok else 0.0, float((r1 - r0) * (x1 - x0))])
     dist.all_reduce(t)
     if rank == 0:
         np.save(os.path.join(out_dir, "result.npy"), t.numpy())
@@ -41,13 +47,16 @@ def _worker(rank, world, port, height, width, full_bytes, out_dir):
 def test_band_partition_and_all_gather_reassemble_the_frame(tmp_path):
     import bench
     # partition properties
-    for h, n in ((1080, 1), (1080, 2), (2160, 4), (4320, 8)):
-        bands = [bench.band(h, r, n) for r in range(n)]
-        assert bands[0][0] == 0 and bands[-1][1] == h
-        assert all(bands[i][1] == bands[i + 1][0] for i in range(n - 1))
-        assert len({b[1] - b[0] for b in bands}) == 1          # equal contributions for the all-gather
+    for w, h, n in ((1920, 1080, 1), (1920, 1080, 2), (3840, 2160, 4), (7680, 4320, 8), (1920, 1080, 8), (1920, 1080, 4)):
+        tiles = [bench.tile(w, h, r, n) for r in range(n)]
+        cover = np.zeros((h, w), np.uint8)                    # every pixel owned exactly once
+        for x0, x1, y0, y1 in tiles:
+            cover[y0:y1, x0:x1] += 1
+        assert (cover == 1).all()
+        assert len({(t[1] - t[0], t[3] - t[2]) for t in tiles}) == 1     # equal contributions for the all-gather
+    assert bench.tile_grid(1920, 1080, 2) == (2, 1) and bench.tile_grid(1920, 1080, 8) == (4, 2)
     with pytest.raises(AssertionError):
-        bench.band(1080, 0, 7)
+        bench.tile(1920, 1080, 0, 7)
     # a real frame from the oracle, split in two bands, reassembled over gloo
     b = Bench("cornell", 48, 64, config="cornell_256")
     orc = b.oracle(threads=2)
@@ -57,4 +66,4 @@ def test_band_partition_and_all_gather_reassemble_the_frame(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 64, 48, full.tobytes(), str(tmp_path)), nprocs=2, join=True)
     res = np.load(tmp_path / "result.npy")
-    assert res[0] == 2.0 and res[1] == 64.0
+    assert res[0] == 2.0 and res[1] == 2 * 24 * 64.0
