@@ -135,6 +135,53 @@ def tile(width, height, rank, world):
     return i * tw, (i + 1) * tw, j * th, (j + 1) * th
 
 
+def balanced_cuts(cost, n, align=8):
+    """cut positions (n + 1 of them, multiples of `align` except the last) splitting `cost` (per line) into n parts of
+    nearly equal sum"""
+    L = len(cost)
+    pre = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for k in range(1, n):
+        pos = int(np.searchsorted(pre, pre[-1] * k / n))
+        pos = int(round(pos / align)) * align
+        pos = max(cuts[-1] + align, min(pos, L - align * (n - k)))
+        cuts.append(pos)
+    cuts.append(L)
+    return cuts
+
+
+def plan_tiles(width, height, world, coverage=None, background_weight=0.15):
+    """One (x0, x1, y0, y1) per rank.  Without a coverage map: the equal grid of tile().  With one (H' x W' booleans from
+    a low-resolution primary-ray pass, identical on every rank): vertical OR horizontal strips whose cuts equalise the
+    estimated cost (covered pixels + `background_weight` per pixel, ghost pixels included); the direction with the smaller
+    maximum wins.  Tiles then differ in size; the all-gather pads every contribution to the largest tile."""
+    if world == 1:
+        return [(0, width, 0, height)]
+    if coverage is None:
+        return [tile(width, height, r, world) for r in range(world)]
+    cov = np.asarray(coverage, np.float64)
+    sy, sx = height / cov.shape[0], width / cov.shape[1]
+    cost_map = cov + background_weight                      # per low-res pixel
+    best = None
+    for axis, full, scale in ((1, width, sx), (0, height, sy)):
+        line = np.repeat(cost_map.sum(axis=0 if axis == 1 else 1), int(round(scale)))[:full] / scale
+        if len(line) < full:
+            line = np.pad(line, (0, full - len(line)), mode="edge")
+        if full < world * 2 * GHOST:
+            continue
+        cuts = balanced_cuts(line, world)
+        pre = np.concatenate([[0.0], np.cumsum(line)])
+        worst = max(pre[min(full, cuts[r + 1] + GHOST)] - pre[max(0, cuts[r] - GHOST)] for r in range(world))
+        if best is None or worst < best[0]:
+            best = (worst, axis, cuts)
+    if best is None:
+        return [tile(width, height, r, world) for r in range(world)]
+    _, axis, cuts = best
+    if axis == 1:
+        return [(cuts[r], cuts[r + 1], 0, height) for r in range(world)]
+    return [(0, width, cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def make_bench(config):
     from bevy_hikari_b200 import plugin, scenes
     cfg = scenes.CONFIGS[config]
@@ -153,8 +200,8 @@ def config_json(config, cfg, settings, world_size):
             "scene": cfg["scene"], "width": cfg["width"], "height": cfg["height"], "indirect_bounces": int(settings.indirect_bounces),
             "emissive_spatial_reuse": int(settings.emissive_spatial_reuse), "indirect_spatial_reuse": int(settings.indirect_spatial_reuse),
             "denoise": int(settings.denoise), "upscale": "SmaaTu4x{ratio:1.0}", "taa": "None",
-            "parallelism": ("%dx%d screen tiles (+%d ghost px), one all-gather of the tone-mapped tiles" % (tile_grid(cfg["width"], cfg["height"], world_size) + (GHOST,)))
-                           if world_size > 1 else "single GPU",
+            "parallelism": (f"{world_size} screen tiles (+{GHOST} ghost px each side, cuts balanced on a coverage probe unless "
+                            "--equal-tiles), one all-gather of the tone-mapped tiles") if world_size > 1 else "single GPU",
             "l2": "per-frame working set (>1 GB of planes) exceeds L2; no explicit flush"}
 
 
@@ -176,7 +223,21 @@ def run_ours(args):
     assert world_size == args.gpus or world_size == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
     cfg, scene, world, W, H, view, pview, lights, settings = make_bench(args.config)
-    x0, x1, r0, r1 = tile(W, H, rank, world_size)
+    tiles = None
+    if world_size > 1 and not args.equal_tiles:
+        # coverage map from a quarter-resolution primary-ray pass on this rank's own GPU (bit-identical on every rank,
+        # so every rank derives the same plan without communicating)
+        cw, ch = max(W // 4, 1), max(H // 4, 1)
+        probe = plugin.HikariPlugin(cw, ch, cuda_device=local_rank)
+        probe.upload_scene(world)
+        pv, ppv, pl = scene.view_inputs(cw, ch)
+        probe.prepass(plugin.make_frame_inputs(settings, 1, pv, ppv, pl))
+        coverage = probe.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)[..., 0] > 0
+        probe.close()
+        tiles = plan_tiles(W, H, world_size, coverage)
+    else:
+        tiles = plan_tiles(W, H, world_size)
+    x0, x1, r0, r1 = tiles[rank]
     # a dedicated non-default stream, made torch's current stream so that torch.cuda.Event, NCCL and the context's
     # kernels are all ordered on the same stream (the legacy default stream has handle 0 = "create your own" in the C ABI)
     stream = torch.cuda.Stream(device=local_rank)
@@ -191,7 +252,14 @@ def run_ours(args):
     class _Ext:  # __cuda_array_interface__ view of the context-owned buffer
         __cuda_array_interface__ = {"shape": (nbytes // 2,), "typestr": "<f2", "data": (ptr, False), "version": 3}
     tile_t = torch.as_tensor(_Ext(), device=f"cuda:{local_rank}")
-    frame_buf = torch.empty(world_size * tile_t.numel(), dtype=torch.float16, device=tile_t.device) if world_size > 1 else None
+    # tiles may differ in size (balanced cuts): every rank contributes a buffer padded to the largest tile
+    max_elems = max((t[1] - t[0]) * (t[3] - t[2]) for t in tiles) * 4
+    send_buf = torch.zeros(max_elems, dtype=torch.float16, device=tile_t.device) if world_size > 1 else None
+    frame_buf = torch.empty(world_size * max_elems, dtype=torch.float16, device=tile_t.device) if world_size > 1 else None
+
+    def gather_frame():
+        send_buf[:tile_t.numel()].copy_(tile_t)
+        dist.all_gather_into_tensor(frame_buf, send_buf)
     pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
 
     def barrier():
@@ -225,7 +293,7 @@ def run_ours(args):
     for n in range(W_):
         dev.render_frame(inputs[n])
         if world_size > 1:
-            dist.all_gather_into_tensor(frame_buf, tile_t)
+            gather_frame()
     kernel_ms = np.zeros(len(L.KERNEL_NAMES))
     launches = 0
     sampler = ClockSampler(local_rank)
@@ -237,7 +305,7 @@ def run_ours(args):
     for n in range(W_, W_ + K):
         dev.render_frame(inputs[n])
         if world_size > 1:
-            dist.all_gather_into_tensor(frame_buf, tile_t)
+            gather_frame()
         # stats of the PREVIOUS frame would need a sync; collect per-kernel times after the loop from a replay below
     e1.record(stream)
     barrier()
@@ -313,11 +381,18 @@ def run_ours(args):
         frame_bpp += BYTES_PER_PIXEL["tone_mapping"]
     frame_achieved = frame_bpp * W * H / (ms_per_step * 1e-3) / 1e9
 
+    traffic = None   # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this workload
+    try:
+        if world_size == 1:
+            with open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")) as f:
+                traffic = json.load(f).get(args.config, {}).get(dom)
+    except Exception:
+        traffic = None
     out = {
         "metric": "Mrays/s", "value": round(value, 3), "unit": "Mrays/s", "n_gpus": world_size, "steps": K, "warmup": W_,
         "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "reference asset cornell.glb + blue-noise seed (no synthetic inputs exist for this path)",
-        "config": config_json(args.config, cfg, settings, world_size),
+        "config": dict(config_json(args.config, cfg, settings, world_size), tiles=[list(t) for t in tiles]),
         "rays_per_frame": {"light_tlas": rays[1] / K, "light_blas": rays[2] / K, "primary": rays[0] / K},
         "fps": round(1e3 / ms_per_step, 2),
         "e2e": {"value": round(e2e_value, 3), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / K, 5),
@@ -325,7 +400,7 @@ def run_ours(args):
         "gpu_launches": int(launches_per_frame * K),
         "kernel_ms": {name: round(float(kernel_ms[i]), 5) for i, name in enumerate(L.KERNEL_NAMES) if kernel_ms[i] > 0},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 5), "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                     "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "frame": {"bytes_per_pixel": frame_bpp, "achieved": round(frame_achieved, 2),
                                "frac": round(frame_achieved / peak, 5)}},
@@ -471,6 +546,7 @@ def main():
     ap.add_argument("--config", default="cornell_1080p")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--equal-tiles", action="store_true", help="N > 1: equal grid of tiles instead of cost-balanced strips")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
