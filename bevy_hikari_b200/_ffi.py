@@ -42,6 +42,7 @@ SYMBOLS = {
     "hk_post_process_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
     "hk_render_frame": (_I, [_P, C.POINTER(L.FrameInputs)]),
     "hk_get_output": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_SZ)]),
+    "hk_output_extent": (_I, [_P, _I, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "hk_readback": (_I, [_P, _I, _P, _SZ]),
     "hk_upload_state": (_I, [_P, _I, _P, _SZ]),
     "hk_sync": (_I, [_P]),
@@ -77,6 +78,7 @@ SYMBOLS = {
     "hikari_plugin_context": (_P, [_P]),
     "hikari_plugin_frame_counter": (_U64, [_P]),
     "hikari_plugin_set_frame_counter": (None, [_P, _U64]),
+    "hikari_plugin_set_temporal_upscalers": (None, [_P, _I]),
 }
 
 _lib = None

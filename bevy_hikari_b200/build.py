@@ -22,7 +22,7 @@ LIB = os.path.join(HERE, "libhikari_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 
-CU = ["csrc/context.cu", "csrc/kernels_light.cu", "csrc/kernels_post.cu"]
+CU = ["csrc/context.cu", "csrc/kernels_light.cu", "csrc/kernels_post.cu", "csrc/kernels_upscale.cu"]
 CPP = ["host/hikari.cpp", "host/hikari_capi.cpp"]
 HEADERS = ["csrc/hk_device.cuh", "csrc/hk_kernels.h", "host/hikari.hpp", "../include/hk_math.h", "../include/hk_layout.h",
            "../include/hikari_b200.h", "../include/hikari_host.h"]

@@ -32,6 +32,9 @@ struct hk_context {
     Planes planes{};
     DeviceScene scene{};
     bool scene_ready = false, noise_ready = false;
+    bool full_frame = true;            // the context owns the whole frame (no tile): upscale_ratio > 1 and the upscalers need it
+    int last_render_w = 0, last_render_h = 0; bool last_smaa = false, last_upscalers = false; uint32_t last_number = 0;   // of the last frame, for read-back sizes
+    int gbuffer_current = 0;           // index of the "current" position / velocity_uv planes; toggled by every prepass
     uint8_t* noise = nullptr;
     Counters* counters = nullptr;
     SpatialTable* spatial_tables = nullptr;
@@ -86,17 +89,24 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     b.ax0 = b.cx0 - GHOST_TEMPORAL < 0 ? 0 : b.cx0 - GHOST_TEMPORAL;
     b.ax1 = b.cx1 + GHOST_TEMPORAL > b.W ? b.W : b.cx1 + GHOST_TEMPORAL;
     b.AW = b.ax1 - b.ax0;
+    b.RW = b.W; b.RH = b.H; b.RS = b.AW;
     ctx->band = b;
     const size_t n = (size_t)b.AW * (size_t)(b.a1 - b.a0);
     ctx->band_pixels = n;
     ctx->owned_pixels = (size_t)(b.cx1 - b.cx0) * (size_t)(b.r1 - b.r0);
     Planes& p = ctx->planes;
     auto& L = ctx->allocations;
-    HK_CUDA(alloc_plane(ctx, &p.pos_depth, n, L));
+    ctx->full_frame = (b.cx0 == 0 && b.cx1 == b.W && b.r0 == 0 && b.r1 == b.H);
+    ctx->gbuffer_current = 0;
+    HK_CUDA(alloc_plane(ctx, &p.pos_depth_db[0], n, L));
+    HK_CUDA(alloc_plane(ctx, &p.pos_depth_db[1], n, L));
+    HK_CUDA(alloc_plane(ctx, &p.velocity_uv_db[0], n, L));
+    HK_CUDA(alloc_plane(ctx, &p.velocity_uv_db[1], n, L));
+    p.pos_depth = p.pos_depth_db[0];
+    p.velocity_uv = p.velocity_uv_db[0];
     HK_CUDA(alloc_plane(ctx, &p.normal, n, L));
     HK_CUDA(alloc_plane(ctx, &p.depth_gradient, n, L));
     HK_CUDA(alloc_plane(ctx, &p.instance_material, n, L));
-    HK_CUDA(alloc_plane(ctx, &p.velocity_uv, n, L));
     HK_CUDA(alloc_plane(ctx, &p.albedo, n, L));
     HK_CUDA(alloc_plane(ctx, &p.dn_geometry, n, L));
     HK_CUDA(alloc_plane(ctx, &p.dn_instance, n, L));
@@ -111,7 +121,15 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
         for (int q = 0; q < 4; ++q) HK_CUDA(alloc_plane(ctx, &p.reservoir[r].q[q], n, L));
     HK_CUDA(alloc_plane(ctx, &p.scatter_key, n, L));   // zero = no claim; k_scatter_resolve re-zeroes what it consumes
     for (int q = 0; q < 4; ++q) HK_CUDA(alloc_plane(ctx, &p.scatter_value.q[q], n, L));
-    HK_CUDA(alloc_plane(ctx, &p.tone_mapped, ctx->owned_pixels, L));
+    HK_CUDA(alloc_plane(ctx, &p.tone_mapped_db[0], ctx->owned_pixels, L));
+    HK_CUDA(alloc_plane(ctx, &p.tone_mapped_db[1], ctx->owned_pixels, L));
+    p.tone_mapped = p.tone_mapped_db[0];
+    p.upscale_output = nullptr; p.taa_output[0] = p.taa_output[1] = nullptr;
+    if (ctx->full_frame) {   // temporal upscalers (K11/K12) run on whole frames only
+        HK_CUDA(alloc_plane(ctx, &p.upscale_output, 4 * n, L));
+        HK_CUDA(alloc_plane(ctx, &p.taa_output[0], 4 * n, L));
+        HK_CUDA(alloc_plane(ctx, &p.taa_output[1], 4 * n, L));
+    }
     return HK_OK;
 }
 
@@ -364,15 +382,35 @@ int hk_set_noise(hk_context* ctx, const uint8_t* rgba) {
 static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     if (!ctx || !in) return HK_ERR_INVALID_ARGUMENT;
     if (!ctx->scene_ready || !ctx->noise_ready) return set_error(ctx, HK_ERR_NOT_READY, "scene or noise not uploaded");
-    if (in->frame.upscale_ratio != 1.0f)
-        return set_error(ctx, HK_ERR_UNSUPPORTED, "upscale_ratio != 1 (render size must equal target size in this build)");
+    const bool ratio1 = in->frame.upscale_ratio == 1.0f;
+    if (!(in->frame.upscale_ratio >= 1.0f && in->frame.upscale_ratio <= 2.0f))
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "upscale_ratio must be in [1, 2] (Upscale::ratio clamps, lib.rs:501-505)");
+    if ((!ratio1 || in->temporal_upscalers) && !ctx->full_frame)
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "upscale_ratio != 1 and the temporal upscalers need a full-frame context (no tile)");
     if (in->frame.direct_validate_interval == 0 || in->frame.emissive_validate_interval == 0)
         return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "validate interval must be >= 1");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return set_error(ctx, HK_ERR_CUDA, "cudaSetDevice");
     P.in = *in;
     P.scene = ctx->scene;
     P.planes = ctx->planes;
+    P.planes.pos_depth = ctx->planes.pos_depth_db[ctx->gbuffer_current];
+    P.planes.velocity_uv = ctx->planes.velocity_uv_db[ctx->gbuffer_current];
+    // tone_mapping_output alternates every frame in the reference (post_process.rs:979); only smaa_tu4x reads the other one,
+    // so the pointer hk_get_output hands out stays fixed unless the temporal upscalers are on
+    P.planes.tone_mapped = ctx->planes.tone_mapped_db[in->temporal_upscalers ? (in->frame.number % 2u) : 0u];
+    ctx->last_upscalers = in->temporal_upscalers != 0;
     P.band = ctx->band;
+    P.ratio1 = ratio1 ? 1 : 0;
+    P.jitter_sign = ((in->frame.number & 1u) == 0u) ? -1.0f : 1.0f;
+    P.ratio_m1 = in->frame.upscale_ratio - 1.0f;
+    P.gbuffer_current = ctx->gbuffer_current;
+    if (!ratio1) {   // scaled_size = (ratio.recip() * size).ceil(), light.rs:622-624; render-size planes use stride RW
+        const float scale = 1.0f / in->frame.upscale_ratio;
+        P.band.RW = (int)ceilf(scale * (float)P.band.W);
+        P.band.RH = (int)ceilf(scale * (float)P.band.H);
+        P.band.RS = P.band.RW;
+    }
+    ctx->last_render_w = P.band.RW; ctx->last_render_h = P.band.RH; ctx->last_smaa = in->smaa_tu4x != 0; ctx->last_number = in->frame.number;
     P.counters = ctx->count_rays ? ctx->counters : nullptr;
     P.noise = ctx->noise;
     float s, c;
@@ -382,7 +420,20 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     P.spatial_tables = ctx->spatial_tables;
     return HK_OK;
 }
+static void rows_deferred(const hk_context* ctx, KParams& P, int ghost) {   // deferred-space launches (G-buffer, albedo)
+    const Band& b = ctx->band;
+    P.band.cx0 = b.cx0; P.band.cx1 = b.cx1; P.band.r0 = b.r0; P.band.r1 = b.r1;
+    P.row_lo = b.r0 - ghost < b.a0 ? b.a0 : b.r0 - ghost;
+    P.row_hi = b.r1 + ghost > b.a1 ? b.a1 : b.r1 + ghost;
+    P.col_lo = b.cx0 - ghost < b.ax0 ? b.ax0 : b.cx0 - ghost;
+    P.col_hi = b.cx1 + ghost > b.ax1 ? b.ax1 : b.cx1 + ghost;
+}
 static void rows(const hk_context* ctx, KParams& P, int ghost) {   // owned rectangle grown by `ghost`, clamped to the allocation
+    if (!P.ratio1) {   // full-frame context at render size: no ghosts, the owned rectangle is the render rectangle
+        P.band.cx0 = 0; P.band.cx1 = P.band.RW; P.band.r0 = 0; P.band.r1 = P.band.RH;
+        P.row_lo = 0; P.row_hi = P.band.RH; P.col_lo = 0; P.col_hi = P.band.RW;
+        return;
+    }
     const Band& b = ctx->band;
     P.row_lo = b.r0 - ghost < b.a0 ? b.a0 : b.r0 - ghost;
     P.row_hi = b.r1 + ghost > b.a1 ? b.a1 : b.r1 + ghost;
@@ -405,7 +456,12 @@ struct KernelTimer {  // brackets one launch with events when pass timing is on
 };
 
 static int run_prepass(hk_context* ctx, KParams& P) {
-    rows(ctx, P, GHOST_TEMPORAL);
+    // prepass_textures_system swaps current <-> previous before rendering (prepass.rs:427)
+    ctx->gbuffer_current ^= 1;
+    P.gbuffer_current = ctx->gbuffer_current;
+    P.planes.pos_depth = ctx->planes.pos_depth_db[ctx->gbuffer_current];
+    P.planes.velocity_uv = ctx->planes.velocity_uv_db[ctx->gbuffer_current];
+    rows_deferred(ctx, P, GHOST_TEMPORAL);
     { KernelTimer t(ctx, HK_K_GBUFFER); hk_launch_gbuffer(P, ctx->count_rays, ctx->stream); }
     return check_launch(ctx);
 }
@@ -438,6 +494,16 @@ static int run_post(hk_context* ctx, KParams& P, bool fuse) {  // PostProcessNod
         rows(ctx, P, 0);
         KernelTimer t(ctx, HK_K_TONE_MAPPING);
         hk_launch_tone_mapping(P, ctx->stream);
+    }
+    if (P.in.temporal_upscalers) {   // post_process.rs:1236-1277; make_params guarantees a full-frame context
+        rows(ctx, P, 0);
+        const bool smaa = P.in.smaa_tu4x != 0;
+        if (smaa) { KernelTimer t(ctx, HK_K_SMAA_TU4X); hk_launch_smaa_tu4x(P, ctx->stream); ctx->launches += 1; }
+        if (P.in.taa_jitter) {
+            P.row_lo = 0; P.col_lo = 0;
+            P.col_hi = smaa ? 2 * P.band.RW : P.band.RW; P.row_hi = smaa ? 2 * P.band.RH : P.band.RH;
+            KernelTimer t(ctx, HK_K_TAA); hk_launch_taa_jasmine(P, smaa, ctx->stream);
+        }
     }
     return check_launch(ctx);
 }
@@ -547,55 +613,87 @@ __global__ void k_scatter_reservoir(ReservoirPlanes b, Band band, size_t n, cons
     for (int q = 0; q < 4; ++q) b.q[q][dst] = in[4 * i + q];
 }
 
-// device pointer of the first owned pixel of a plane + bytes per pixel (row pitch = AW pixels, except the tightly packed
-// tone-mapped plane); reservoirs are handled separately
-static void* owned_plane(hk_context* ctx, int which, size_t* bpp) {
+// Where a read-back / upload plane lives: device pointer of its first transferred pixel, bytes per pixel, the
+// rectangle (width x height, in pixels) that is transferred and the row pitch of the plane in pixels.
+struct PlaneView { void* ptr; size_t bpp, w, h, pitch; };
+static bool plane_view(hk_context* ctx, int which, PlaneView* v) {
     const Planes& p = ctx->planes;
-    const size_t first = (size_t)(ctx->band.r0 - ctx->band.a0) * (size_t)ctx->band.AW + (size_t)(ctx->band.cx0 - ctx->band.ax0);
+    const Band& b = ctx->band;
+    const size_t ow = (size_t)(b.cx1 - b.cx0), oh = (size_t)(b.r1 - b.r0);
+    const bool scaled = ctx->last_render_w != 0 && (ctx->last_render_w != b.W || ctx->last_render_h != b.H);   // ratio > 1 (full frame)
+    const size_t rw = scaled ? (size_t)ctx->last_render_w : ow, rh = scaled ? (size_t)ctx->last_render_h : oh;
+    const size_t first_def = (size_t)(b.r0 - b.a0) * (size_t)b.AW + (size_t)(b.cx0 - b.ax0);
+    const size_t first_ren = scaled ? 0 : first_def;
+    const size_t pitch_ren = scaled ? rw : (size_t)b.AW;
+    auto deferred = [&](void* base, size_t bpp) { *v = PlaneView{(char*)base + first_def * bpp, bpp, ow, oh, (size_t)b.AW}; return true; };
+    auto render = [&](void* base, size_t bpp) { *v = PlaneView{(char*)base + first_ren * bpp, bpp, rw, rh, pitch_ren}; return true; };
+    const uint32_t cur = ctx->last_number % 2u;
     switch (which) {
-        case HK_OUT_TONE_MAPPED: *bpp = 8; return p.tone_mapped;
-        case HK_OUT_RENDER_DIRECT: case HK_OUT_RENDER_EMISSIVE: case HK_OUT_RENDER_INDIRECT:
-            *bpp = 8; return p.render[which - HK_OUT_RENDER_DIRECT] + first;
-        case HK_OUT_VARIANCE_DIRECT: case HK_OUT_VARIANCE_EMISSIVE: case HK_OUT_VARIANCE_INDIRECT:
-            *bpp = 4; return p.variance[which - HK_OUT_VARIANCE_DIRECT] + first;
-        case HK_OUT_ALBEDO: *bpp = 8; return p.albedo + first;
-        case HK_OUT_DENOISED_DIRECT: case HK_OUT_DENOISED_EMISSIVE: case HK_OUT_DENOISED_INDIRECT:
-            *bpp = 8; return p.dn_render[which - HK_OUT_DENOISED_DIRECT] + first;
-        case HK_OUT_GBUFFER_POSITION: *bpp = 16; return p.pos_depth + first;
-        case HK_OUT_GBUFFER_NORMAL: *bpp = 4; return p.normal + first;
-        case HK_OUT_GBUFFER_DEPTH_GRADIENT: *bpp = 8; return p.depth_gradient + first;
-        case HK_OUT_GBUFFER_INSTANCE_MATERIAL: *bpp = 8; return p.instance_material + first;
-        case HK_OUT_GBUFFER_VELOCITY_UV: *bpp = 16; return p.velocity_uv + first;
+        case HK_OUT_TONE_MAPPED: *v = PlaneView{p.tone_mapped_db[ctx->last_upscalers ? cur : 0u], 8, rw, rh, rw}; return true;
+        case HK_OUT_UPSCALED: if (!p.upscale_output) return false; *v = PlaneView{p.upscale_output, 8, 2 * rw, 2 * rh, 2 * rw}; return true;
+        case HK_OUT_TAA: {
+            if (!p.taa_output[0]) return false;
+            const size_t k = ctx->last_smaa ? 2 : 1;
+            *v = PlaneView{p.taa_output[cur], 8, k * rw, k * rh, k * rw};
+            return true;
+        }
+        case HK_OUT_RENDER_DIRECT: case HK_OUT_RENDER_EMISSIVE: case HK_OUT_RENDER_INDIRECT: return render(p.render[which - HK_OUT_RENDER_DIRECT], 8);
+        case HK_OUT_VARIANCE_DIRECT: case HK_OUT_VARIANCE_EMISSIVE: case HK_OUT_VARIANCE_INDIRECT: return render(p.variance[which - HK_OUT_VARIANCE_DIRECT], 4);
+        case HK_OUT_DENOISED_DIRECT: case HK_OUT_DENOISED_EMISSIVE: case HK_OUT_DENOISED_INDIRECT: return render(p.dn_render[which - HK_OUT_DENOISED_DIRECT], 8);
+        case HK_OUT_ALBEDO: return deferred(p.albedo, 8);
+        case HK_OUT_GBUFFER_POSITION: return deferred(p.pos_depth_db[ctx->gbuffer_current], 16);
+        case HK_OUT_GBUFFER_NORMAL: return deferred(p.normal, 4);
+        case HK_OUT_GBUFFER_DEPTH_GRADIENT: return deferred(p.depth_gradient, 8);
+        case HK_OUT_GBUFFER_INSTANCE_MATERIAL: return deferred(p.instance_material, 8);
+        case HK_OUT_GBUFFER_VELOCITY_UV: return deferred(p.velocity_uv_db[ctx->gbuffer_current], 16);
     }
-    return nullptr;
+    return false;
 }
 
 extern "C" {
 
 int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes) {
     if (!ctx || !device_ptr) return HK_ERR_INVALID_ARGUMENT;
-    if (which != HK_OUT_TONE_MAPPED) return set_error(ctx, HK_ERR_UNSUPPORTED, "only HK_OUT_TONE_MAPPED is exposed as a device pointer");
-    *device_ptr = ctx->planes.tone_mapped;
-    if (bytes) *bytes = ctx->owned_pixels * 8;
+    PlaneView v;
+    if ((which != HK_OUT_TONE_MAPPED && which != HK_OUT_UPSCALED && which != HK_OUT_TAA) || !plane_view(ctx, which, &v))
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "only the final images (tone-mapped, upscaled, TAA) are exposed as device pointers");
+    *device_ptr = v.ptr;
+    if (bytes) *bytes = v.w * v.h * v.bpp;
+    return HK_OK;
+}
+
+int hk_output_extent(hk_context* ctx, int which, uint32_t* width, uint32_t* height) {
+    if (!ctx || !width || !height) return HK_ERR_INVALID_ARGUMENT;
+    PlaneView v;
+    if (which >= HK_OUT_RESERVOIR_0 && which < HK_OUT_RESERVOIR_0 + 10) {
+        if (!plane_view(ctx, HK_OUT_RENDER_DIRECT, &v)) return HK_ERR_INVALID_ARGUMENT;
+    } else if (!plane_view(ctx, which, &v)) {
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown plane id");
+    }
+    *width = (uint32_t)v.w; *height = (uint32_t)v.h;
     return HK_OK;
 }
 
 static int transfer(hk_context* ctx, int which, void* host, size_t bytes, bool to_host) {
     if (!ctx || !host) return HK_ERR_INVALID_ARGUMENT;
     HK_CUDA(cudaSetDevice(ctx->device));
-    const size_t n = ctx->owned_pixels;
     if (which >= HK_OUT_RESERVOIR_0 && which < HK_OUT_RESERVOIR_0 + 10) {
+        Band rb = ctx->band;   // rectangle of the reservoir buffer in render space
+        if (ctx->last_render_w != 0 && (ctx->last_render_w != rb.W || ctx->last_render_h != rb.H)) {
+            rb.cx0 = 0; rb.cx1 = ctx->last_render_w; rb.r0 = 0; rb.r1 = ctx->last_render_h; rb.a0 = 0; rb.ax0 = 0; rb.AW = ctx->last_render_w;
+        }
+        const size_t n = (size_t)(rb.cx1 - rb.cx0) * (size_t)(rb.r1 - rb.r0);
         if (bytes != n * 64) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
         uint4* tmp = nullptr;
         HK_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), bytes));
         const unsigned blocks = (unsigned)((n + 255) / 256);
         cudaError_t e;
         if (to_host) {
-            k_gather_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], ctx->band, n, tmp);
+            k_gather_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], rb, n, tmp);
             e = cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream);
         } else {
             e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
-            k_scatter_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], ctx->band, n, tmp);
+            k_scatter_reservoir<<<blocks, 256, 0, ctx->stream>>>(ctx->planes.reservoir[which - HK_OUT_RESERVOIR_0], rb, n, tmp);
         }
         cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
         cudaFree(tmp);
@@ -603,14 +701,11 @@ static int transfer(hk_context* ctx, int which, void* host, size_t bytes, bool t
         HK_CUDA(e2);
         return HK_OK;
     }
-    size_t bpp = 0;
-    void* dev = owned_plane(ctx, which, &bpp);
-    if (!dev) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown plane id");
-    if (bytes != n * bpp) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
-    const size_t ow = (size_t)(ctx->band.cx1 - ctx->band.cx0), oh = (size_t)(ctx->band.r1 - ctx->band.r0);
-    const size_t dev_pitch = (which == HK_OUT_TONE_MAPPED ? ow : (size_t)ctx->band.AW) * bpp;
-    if (to_host) HK_CUDA(cudaMemcpy2DAsync(host, ow * bpp, dev, dev_pitch, ow * bpp, oh, cudaMemcpyDeviceToHost, ctx->stream));
-    else HK_CUDA(cudaMemcpy2DAsync(dev, dev_pitch, host, ow * bpp, ow * bpp, oh, cudaMemcpyHostToDevice, ctx->stream));
+    PlaneView v;
+    if (!plane_view(ctx, which, &v)) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown plane id");
+    if (bytes != v.w * v.h * v.bpp) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
+    if (to_host) HK_CUDA(cudaMemcpy2DAsync(host, v.w * v.bpp, v.ptr, v.pitch * v.bpp, v.w * v.bpp, v.h, cudaMemcpyDeviceToHost, ctx->stream));
+    else HK_CUDA(cudaMemcpy2DAsync(v.ptr, v.pitch * v.bpp, host, v.w * v.bpp, v.w * v.bpp, v.h, cudaMemcpyHostToDevice, ctx->stream));
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }

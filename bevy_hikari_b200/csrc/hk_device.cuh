@@ -40,11 +40,13 @@ struct ReservoirPlanes {  // one PackedReservoir buffer as 4 planes
 };
 
 struct Planes {
-    float4* pos_depth;
+    float4* pos_depth;          // current frame (= pos_depth_db[gbuffer_current]); previous frame = the other one (prepass.rs:312-321)
     uint32_t* normal;
     float2* depth_gradient;
     float2* instance_material;
     float4* velocity_uv;
+    float4* pos_depth_db[2];
+    float4* velocity_uv_db[2];
     uint2* albedo;
     uint2* render[3];
     float* variance[3];
@@ -58,14 +60,20 @@ struct Planes {
     uint2* dn_internal[4][3];   // [level][signal]; level 0 = demodulated input
     float* dn_variance[3];
     uint2* dn_render[3];
-    uint2* tone_mapped;         // owned rows only, tightly packed (row_begin is row 0)
+    uint2* tone_mapped;         // owned rectangle only, tightly packed; = tone_mapped_db[frame.number % 2] (post_process.rs:716,979)
+    uint2* tone_mapped_db[2];
+    uint2* upscale_output;      // 2 RW x 2 RH (SMAA TU4x), full-frame contexts only
+    uint2* taa_output[2];       // [frame.number % 2] is written
 };
 
 struct Band {             // the tile of the frame one context renders (whole frame: everything 0..W, 0..H)
     int W, H;             // full image
     int ax0, ax1, a0, a1; // allocated rectangle: columns [ax0,ax1), rows [a0,a1) = owned +- ghost, clamped to the image
     int cx0, cx1, r0, r1; // owned rectangle: columns [cx0,cx1), rows [r0,r1)
-    int AW;               // ax1 - ax0: row stride of every plane
+    int AW;               // ax1 - ax0: row stride of the deferred-size planes (G-buffer, albedo)
+    // render size = ceil(size / upscale_ratio) (light.rs:622-624).  At ratio 1 (every tiled / benchmark configuration)
+    // render space == deferred space and RS == AW; at ratio > 1 (full-frame contexts only) render-size planes use stride RW.
+    int RW, RH, RS;
 };
 
 struct Counters { unsigned long long primary, tlas, blas; };
@@ -92,6 +100,10 @@ struct KParams {
     float cos_solar_angle;  // cos(frame.solar_angle), hk::sincos_ evaluated once on the host with the same routine
     float random_frame;     // random_float(frame.number)
     const SpatialTable* spatial_tables;   // [0] = indirect (16 neighbours, 20 px), [1] = emissive (8 neighbours, 10 px)
+    int ratio1;             // upscale_ratio == 1: deferred coordinates are the render coordinates
+    float jitter_sign;      // -1 on even frames, +1 on odd frames (light.wgsl:1010, denoise.wgsl:40)
+    float ratio_m1;         // upscale_ratio - 1
+    int gbuffer_current;    // which of the double-buffered position / velocity_uv planes is "current" this frame
 };
 
 // --------------------------------------------------------------------------------------------- raw loads
@@ -716,6 +728,7 @@ __device__ __forceinline__ LightCandidate select_light_candidate(const DeviceSce
 __device__ __forceinline__ size_t band_index(const Band& b, int x, int y) { return (size_t)(y - b.a0) * (size_t)b.AW + (size_t)(x - b.ax0); }
 __device__ __forceinline__ bool band_allocated(const Band& b, int x, int y) { return x >= b.ax0 && x < b.ax1 && y >= b.a0 && y < b.a1; }
 __device__ __forceinline__ bool band_owned(const Band& b, int x, int y) { return x >= b.cx0 && x < b.cx1 && y >= b.r0 && y < b.r1; }
+__device__ __forceinline__ size_t render_index(const Band& b, int x, int y) { return (size_t)(y - b.a0) * (size_t)b.RS + (size_t)(x - b.ax0); }
 __device__ __forceinline__ size_t owned_index(const Band& b, int x, int y) { return (size_t)(y - b.r0) * (size_t)(b.cx1 - b.cx0) + (size_t)(x - b.cx0); }
 
 // blue-noise fetch, light.wgsl:1075-1079 (nearest + repeat on a 64x64 texture == integer wrap)
@@ -728,10 +741,36 @@ __device__ __forceinline__ vec4 noise_random(const KParams& P, int x, int y) {
     return fract(rnd + (float)number * GOLDEN_RATIO);
 }
 
+// ---- render space <-> deferred (G-buffer) space, light.wgsl:1007-1017 and denoise.wgsl:37-41
+__device__ __forceinline__ vec2 render_uv(const KParams& P, int x, int y) {   // coords_to_uv(coords, render_size)
+    return (v2((float)x, (float)y) + 0.5f) / v2((float)P.band.RW, (float)P.band.RH);
+}
+__device__ __forceinline__ vec2 jittered_deferred_uv(const KParams& P, vec2 uv, float amount) {
+    if (P.ratio1) return uv;   // + (+-amount) * texel * 0
+    vec2 texel_size = v2(1.0f, 1.0f) / v2((float)P.band.W, (float)P.band.H);
+    return uv + (P.jitter_sign * amount) * texel_size * P.ratio_m1;
+}
+// jittered_deferred_coords (light passes: +-0.25 texel, truncation); (x, y) is the render pixel whose uv is `uv`
+__device__ __forceinline__ void light_deferred_coords(const KParams& P, vec2 uv, int x, int y, int& dx, int& dy) {
+    if (P.ratio1) { dx = x; dy = y; return; }   // trunc(((x + 0.5) / W) * W) == x
+    vec2 d = jittered_deferred_uv(P, uv, 0.25f);
+    dx = f32_to_i32(d.x * (float)P.band.W); dy = f32_to_i32(d.y * (float)P.band.H);
+}
+// textureSampleLevel(<deferred texture>, nearest_sampler, jittered_deferred_uv(uv)) of the denoise passes: +-0.5 texel, floor, clamp
+__device__ __forceinline__ void denoise_deferred_coords(const KParams& P, vec2 uv, int x, int y, int& dx, int& dy) {
+    if (P.ratio1) { dx = x; dy = y; return; }
+    vec2 d = jittered_deferred_uv(P, uv, 0.5f);
+    dx = min(max((int)floorf(d.x * (float)P.band.W), 0), P.band.W - 1);
+    dy = min(max((int)floorf(d.y * (float)P.band.H), 0), P.band.H - 1);
+}
+__device__ __forceinline__ bool render_allocated(const KParams& P, int x, int y) {
+    return P.ratio1 ? band_allocated(P.band, x, y) : (x >= 0 && x < P.band.RW && y >= 0 && y < P.band.RH);
+}
+
 // kinds of writes to the previous-spatial buffer, in the order one pixel can issue them
 constexpr uint32_t SCATTER_BACKGROUND = 0u, SCATTER_MISS = 1u, SCATTER_VALIDATION = 2u;
 __device__ __forceinline__ void scatter_claim(const KParams& P, size_t target, int x, int y, uint32_t kind) {
-    uint32_t writer = (uint32_t)y * (uint32_t)P.band.W + (uint32_t)x;   // global raster index
+    uint32_t writer = (uint32_t)y * (uint32_t)P.band.RW + (uint32_t)x;   // global raster index in render space
     atomicMax(&P.planes.scatter_key[target], ((writer + 1u) << 2) | kind);
 }
 

@@ -1,4 +1,4 @@
-// hk_kernels.h — host-callable launchers of the CUDA kernels (implemented in kernels_light.cu / kernels_post.cu).
+// hk_kernels.h — host-callable launchers of the CUDA kernels (implemented in kernels_light.cu / kernels_post.cu / kernels_upscale.cu).
 #pragma once
 #include "hk_device.cuh"
 
@@ -14,3 +14,7 @@ void hk_launch_trace_rays(const hkd::DeviceScene& sc, const hk_ray* rays, size_t
 void hk_launch_demodulation(const hkd::KParams& P, int signals, cudaStream_t st);
 void hk_launch_denoise_level(const hkd::KParams& P, int level, int signals, bool fuse_tone_mapping, bool keep_denoised, cudaStream_t st);
 void hk_launch_tone_mapping(const hkd::KParams& P, cudaStream_t st);
+
+// temporal upscalers (kernels_upscale.cu); full-frame contexts only
+void hk_launch_smaa_tu4x(const hkd::KParams& P, cudaStream_t st);               // smaa_tu4x + smaa_tu4x_extrapolate over the render rectangle
+void hk_launch_taa_jasmine(const hkd::KParams& P, bool smaa, cudaStream_t st);  // over col_lo..col_hi x row_lo..row_hi = the output size

@@ -168,13 +168,18 @@ __device__ __forceinline__ bool previous_pixel(const KParams& P, vec2 previous_u
     float ax = fabsf(previous_uv.x - 0.5f), ay = fabsf(previous_uv.y - 0.5f);
     bool inside = inclusive ? (ax <= 0.5f && ay <= 0.5f) : (ax < 0.5f && ay < 0.5f);
     if (!inside) return false;
-    int px = f32_to_i32(previous_uv.x * (float)P.band.W), py = f32_to_i32(previous_uv.y * (float)P.band.H);
-    if (!band_allocated(P.band, px, py)) return false;
-    pidx = band_index(P.band, px, py);
+    int px = f32_to_i32(previous_uv.x * (float)P.band.RW), py = f32_to_i32(previous_uv.y * (float)P.band.RH);
+    if (!render_allocated(P, px, py)) return false;
+    pidx = render_index(P.band, px, py);
     return true;
 }
-__device__ __forceinline__ vec2 pixel_uv(const KParams& P, int x, int y) {  // coords_to_uv, utils.wgsl:37-39
-    return (v2((float)x, (float)y) + 0.5f) / v2((float)P.band.W, (float)P.band.H);
+__device__ __forceinline__ vec2 pixel_uv(const KParams& P, int x, int y) { return render_uv(P, x, y); }  // coords_to_uv, utils.wgsl:37-39
+// index of the G-buffer texel a light pass reads for render pixel (x, y): jittered_deferred_coords(uv)
+__device__ __forceinline__ size_t light_gbuffer_index(const KParams& P, int x, int y, size_t render_idx) {
+    if (P.ratio1) return render_idx;
+    int dx, dy;
+    light_deferred_coords(P, render_uv(P, x, y), x, y, dx, dy);
+    return band_index(P.band, dx, dy);
 }
 
 // --------------------------------------------------------------------------------------- P2: direct_lit
@@ -190,9 +195,10 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
     if (active) {
         const DeviceScene& sc = P.scene;
         const hk_frame_uniform& frame = P.in.frame;
-        const size_t idx = band_index(P.band, x, y);
+        const size_t idx = render_index(P.band, x, y);
+        const size_t gidx = light_gbuffer_index(P, x, y, idx);
         const PassBuffers B = bind(P, SIGNAL);
-        const float4 pd = P.planes.pos_depth[idx];
+        const float4 pd = P.planes.pos_depth[gidx];
         const float depth = pd.w;
         if (depth < F32_EPSILON) {
             Reservoir r = zero_reservoir();
@@ -206,10 +212,10 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
         } else {
             const ShadeEnv env = make_env(P);
             const vec3 position = f4xyz(pd);
-            const vec3 normal = xyz(unpack4x8snorm(P.planes.normal[idx]));  // NOT normalised (light.wgsl:1071)
-            const float2 imf = P.planes.instance_material[idx];
+            const vec3 normal = xyz(unpack4x8snorm(P.planes.normal[gidx]));  // NOT normalised (light.wgsl:1071)
+            const float2 imf = P.planes.instance_material[gidx];
             const uint32_t instance_id = f32_to_u32(imf.x), material_id = f32_to_u32(imf.y);
-            const float4 vu = P.planes.velocity_uv[idx];
+            const float4 vu = P.planes.velocity_uv[gidx];
 
             Sample s = zero_sample();
             s.random = noise_random(P, x, y);
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
             HitInfo info = empty_hit_info(v3(0.0f), v3(0.0f));
             info.instance_index = 0u; info.material_index = 0u; info.position = v4(0.0f);
 
-            const vec2 previous_uv = pixel_uv(P, x, y) - v2(vu.x, vu.y);
+            const vec2 previous_uv = jittered_deferred_uv(P, pixel_uv(P, x, y), 0.25f) - v2(vu.x, vu.y);
             size_t pidx = 0;
             Reservoir r = zero_reservoir();
             if (previous_pixel(P, previous_uv, false, pidx)) r = unpack_reservoir(load_quarters(B.previous_reservoir, pidx));
@@ -323,9 +329,10 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
     if (active) {
         const DeviceScene& sc = P.scene;
         const hk_frame_uniform& frame = P.in.frame;
-        const size_t idx = band_index(P.band, x, y);
+        const size_t idx = render_index(P.band, x, y);
+        const size_t gidx = light_gbuffer_index(P, x, y, idx);
         const PassBuffers B = bind(P, 2);
-        const float4 pd = P.planes.pos_depth[idx];
+        const float4 pd = P.planes.pos_depth[gidx];
         const float depth = pd.w;
         if (frame.indirect_bounces == 0u || depth < F32_EPSILON) {
             PackedQuarters q = pack_reservoir(zero_reservoir());
@@ -337,10 +344,10 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
         } else {
             const ShadeEnv env = make_env(P);
             const vec3 position = f4xyz(pd);
-            const vec3 normal = normalize(xyz(unpack4x8snorm(P.planes.normal[idx])));  // normalised here (light.wgsl:1289)
-            const float2 imf = P.planes.instance_material[idx];
+            const vec3 normal = normalize(xyz(unpack4x8snorm(P.planes.normal[gidx])));  // normalised here (light.wgsl:1289)
+            const float2 imf = P.planes.instance_material[gidx];
             const uint32_t instance_id = f32_to_u32(imf.x), material_id = f32_to_u32(imf.y);
-            const float4 vu = P.planes.velocity_uv[idx];
+            const float4 vu = P.planes.velocity_uv[gidx];
 
             Sample s = zero_sample();
             s.random = noise_random(P, x, y);
@@ -410,7 +417,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
             }
 
             // ReSTIR: temporal
-            const vec2 previous_uv = pixel_uv(P, x, y) - v2(vu.x, vu.y);
+            const vec2 previous_uv = jittered_deferred_uv(P, pixel_uv(P, x, y), 0.25f) - v2(vu.x, vu.y);
             size_t pidx = 0;
             Reservoir r = zero_reservoir();
             if (previous_pixel(P, previous_uv, false, pidx)) r = unpack_reservoir(load_quarters(B.previous_reservoir, pidx));
@@ -456,9 +463,10 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
     if (!tile_active(P, x, y)) return;
     const DeviceScene& sc = P.scene;
     const hk_frame_uniform& frame = P.in.frame;
-    const size_t idx = band_index(P.band, x, y);
+    const size_t idx = render_index(P.band, x, y);
+    const size_t gidx = light_gbuffer_index(P, x, y, idx);
     const PassBuffers B = bind(P, SIGNAL);
-    const float4 pd = P.planes.pos_depth[idx];
+    const float4 pd = P.planes.pos_depth[gidx];
     const float depth = pd.w;
     const PackedQuarters own = load_quarters(B.reservoir, idx);
     if (depth < F32_EPSILON) {
@@ -470,12 +478,12 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
     Reservoir r = unpack_reservoir(own);
     const ShadeEnv env = make_env(P);
     const vec3 position = f4xyz(pd);
-    const float2 imf = P.planes.instance_material[idx];
-    const float4 vu = P.planes.velocity_uv[idx];
+    const float2 imf = P.planes.instance_material[gidx];
+    const float4 vu = P.planes.velocity_uv[gidx];
     const Surface surface = retreive_surface(sc, f32_to_u32(imf.y), v2(vu.z, vu.w));
     const bool use_spatial_variance = r.count <= 4.0f;
     const vec2 uv = pixel_uv(P, x, y);
-    const vec2 previous_uv = uv - v2(vu.x, vu.y);
+    const vec2 previous_uv = jittered_deferred_uv(P, uv, 0.25f) - v2(vu.x, vu.y);
 
     Reservoir q = r;
     const Sample s = q.s;
@@ -496,7 +504,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
     r.s.visible_position = s.visible_position;
     r.s.visible_normal = s.visible_normal;
 
-    const vec2 size_f = v2((float)P.band.W, (float)P.band.H);
+    const vec2 size_f = v2((float)P.band.RW, (float)P.band.RH);
     const SpatialTable& T = P.spatial_tables[EMISSIVE_LIT ? 1 : 0];
     const float rotation = sum4(s.random);
     for (uint32_t i = 1u; i <= SPATIAL_REUSE_COUNT; i += 1u) {
@@ -508,8 +516,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
         int sx = f32_to_i32(offset.x + (float)x), sy = f32_to_i32(offset.y + (float)y);
         vec2 sample_uv = (v2((float)sx, (float)sy) + 0.5f) / size_f;
         if (sample_uv.x < 0.0f || sample_uv.y < 0.0f || sample_uv.x > 1.0f || sample_uv.y > 1.0f) continue;
-        const size_t sidx = band_index(P.band, sx, sy);
-        const float sample_depth = P.planes.pos_depth[sidx].w;
+        const size_t sidx = render_index(P.band, sx, sy);
+        const float sample_depth = P.planes.pos_depth[light_gbuffer_index(P, sx, sy, sidx)].w;
         float depth_ratio = depth / sample_depth;
         if (depth_ratio < 0.9f || depth_ratio > 1.1f) continue;
         q = unpack_reservoir(load_quarters(B.reservoir, sidx));
@@ -525,7 +533,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
         for (uint32_t j = 1u; j <= tap_count; j += 1u) {
             float tap_dist = T.tap_dist[i][j - 1u];
             vec2 tap_uv = uv + (tap_dist * unit) / size_f;
-            int tx = f32_to_i32(tap_uv.x * size_f.x), ty = f32_to_i32(tap_uv.y * size_f.y);
+            vec2 tap_deferred_uv = jittered_deferred_uv(P, tap_uv, 0.25f);
+            int tx = f32_to_i32(tap_deferred_uv.x * (float)P.band.W), ty = f32_to_i32(tap_deferred_uv.y * (float)P.band.H);
             float tap_depth = 0.0f;  // out-of-bounds textureLoad -> 0
             if (tx >= 0 && tx < P.band.W && ty >= 0 && ty < P.band.H) tap_depth = P.planes.pos_depth[band_index(P.band, tx, ty)].w;
             float ref_depth = mixf(depth, sample_depth, T.tap_ratio[i][j - 1u]);
@@ -565,7 +574,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_scatter_resolve(const __grid_co
     int x, y;
     tile_pixel(x, y, P);
     if (!tile_active(P, x, y)) return;
-    const size_t idx = band_index(P.band, x, y);
+    const size_t idx = render_index(P.band, x, y);
     const uint32_t key = P.planes.scatter_key[idx];
     if (key == 0u) return;
     P.planes.scatter_key[idx] = 0u;   // leave the plane clean for the next pass
@@ -573,8 +582,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_scatter_resolve(const __grid_co
     const PassBuffers B = bind(P, signal);
     PackedQuarters q;
     if (kind == SCATTER_VALIDATION) {
-        const int wy = (int)(writer / (uint32_t)P.band.W), wx = (int)(writer % (uint32_t)P.band.W);
-        q = load_quarters(P.planes.scatter_value, band_index(P.band, wx, wy));
+        const int wy = (int)(writer / (uint32_t)P.band.RW), wx = (int)(writer % (uint32_t)P.band.RW);
+        q = load_quarters(P.planes.scatter_value, render_index(P.band, wx, wy));
     } else {
         Reservoir r = zero_reservoir();
         if (kind == SCATTER_BACKGROUND && signal != 2) set_reservoir(r, zero_sample(), 0.0f);   // light.wgsl:1059-1063 vs :1279-1282

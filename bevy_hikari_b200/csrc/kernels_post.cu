@@ -32,14 +32,20 @@ __global__ void __launch_bounds__(CTA_THREADS) k_demodulation(const __grid_const
     int x, y;
     tile_pixel(x, y, P);
     if (!tile_active(P, x, y)) return;
-    const size_t idx = band_index(P.band, x, y);
+    const size_t idx = render_index(P.band, x, y);
+    size_t gidx = idx;   // the G-buffer / albedo texel this render pixel samples (nearest at the +-0.5-texel jittered uv)
+    if (!P.ratio1) {
+        int dx, dy;
+        denoise_deferred_coords(P, render_uv(P, x, y), x, y, dx, dy);
+        gidx = band_index(P.band, dx, dy);
+    }
     {   // tap geometry for the four a-trous levels: the normalised normal, depth and instance id of this pixel are read
         // by up to 36 taps; normalise once here instead of 36 times there (same operations, same values)
-        const vec3 n = normalize(xyz(unpack4x8snorm(P.planes.normal[idx])));
-        P.planes.dn_geometry[idx] = make_float4(n.x, n.y, n.z, P.planes.pos_depth[idx].w);
-        P.planes.dn_instance[idx] = P.planes.instance_material[idx].x;
+        const vec3 n = normalize(xyz(unpack4x8snorm(P.planes.normal[gidx])));
+        P.planes.dn_geometry[idx] = make_float4(n.x, n.y, n.z, P.planes.pos_depth[gidx].w);
+        P.planes.dn_instance[idx] = P.planes.instance_material[gidx].x;
     }
-    const vec3 albedo = xyz(load16(P.planes.albedo, idx));
+    const vec3 albedo = xyz(load16(P.planes.albedo, gidx));
     for (int sgl = 0; sgl < signals; ++sgl) {
         vec3 irradiance = xyz(load16(P.planes.render[sgl], idx));
         vec3 q = irradiance / albedo;
@@ -52,8 +58,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_demodulation(const __grid_const
 #pragma unroll
             for (int oy = -1; oy <= 1; ++oy) {
                 int sx = x + ox, sy = y + oy;
-                if (sx < 0 || sy < 0 || sx >= P.band.W || sy >= P.band.H) continue;
-                float variance = P.planes.variance[sgl][band_index(P.band, sx, sy)];
+                if (sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH) continue;
+                float variance = P.planes.variance[sgl][render_index(P.band, sx, sy)];
                 if (variance > F32_MAX) continue;
                 sum_variance += kernel_at(P, oy + 1, ox + 1) * fmax_(variance, 0.0f);
             }
@@ -74,13 +80,19 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
     int x, y;
     tile_pixel(x, y, P);
     if (!tile_active(P, x, y)) return;
-    const size_t idx = band_index(P.band, x, y);
+    const size_t idx = render_index(P.band, x, y);
+    size_t gidx = idx;
+    if (!P.ratio1) {
+        int dx, dy;
+        denoise_deferred_coords(P, render_uv(P, x, y), x, y, dx, dy);
+        gidx = band_index(P.band, dx, dy);
+    }
     const float4 geometry = P.planes.dn_geometry[idx];
     const float depth = geometry.w;
     vec4 result[3];
     result[0] = result[1] = result[2] = v4(0.0f);
     if (!(depth < F32_EPSILON)) {
-        const float2 dg = P.planes.depth_gradient[idx];
+        const float2 dg = P.planes.depth_gradient[gidx];
         const vec2 depth_gradient = v2(dg.x, dg.y);
         const vec3 normal = f4xyz(geometry);
         const float instance = P.planes.dn_instance[idx];
@@ -108,8 +120,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
         for (int t = 0; t < 8; ++t) {
             const int ox = OX[t], oy = OY[t];
             const int sx = x + ox * STEP, sy = y + oy * STEP;
-            if (sx < 0 || sy < 0 || sx >= P.band.W || sy >= P.band.H) continue;
-            const size_t sidx = band_index(P.band, sx, sy);
+            if (sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH) continue;
+            const size_t sidx = render_index(P.band, sx, sy);
             // geometric weights: once per tap for all signals
             const float4 sample_geometry = P.planes.dn_geometry[sidx];
             const vec3 sample_normal = f4xyz(sample_geometry);
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
         }
 
         vec4 albedo = v4(1.0f);
-        if (LEVEL == 3) albedo = load16(P.planes.albedo, idx);
+        if (LEVEL == 3) albedo = load16(P.planes.albedo, gidx);
 #pragma unroll
         for (int sgl = 0; sgl < 3; ++sgl) {
             if (sgl >= signals) continue;
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_tone_mapping(const __grid_const
     int x, y;
     tile_pixel(x, y, P);
     if (!tile_active(P, x, y)) return;
-    const size_t idx = band_index(P.band, x, y);
+    const size_t idx = render_index(P.band, x, y);
     const bool dn = P.in.denoise != 0u;
     uint2* const* src = dn ? P.planes.dn_render : P.planes.render;
     vec4 color = load16(src[0], idx);

@@ -1,0 +1,302 @@
+// kernels_upscale.cu — the temporal upscalers that follow tone mapping in the default HikariSettings pipeline
+// (SURVEY.md 8(f) rank 1): smaa_tu4x + smaa_tu4x_extrapolate (src/shaders/smaa.wgsl:81-271) and taa_jasmine
+// (src/shaders/taa.wgsl:79-170), dispatched by PostProcessNode::run (src/post_process.rs:1236-1277).
+// Full-frame contexts only.  Texture addressing (both samplers clamp-to-edge, post_process.rs:697-708):
+//   nearest: texel floor(uv * size);  linear: bilinear around uv * size - 0.5 with fp32 weights;
+//   textureGather: the 2x2 bilinear footprint as (x: (i0,j1), y: (i1,j1), z: (i1,j0), w: (i0,j0)).
+#include "hk_device.cuh"
+#include "hk_kernels.h"
+
+namespace hkd {
+
+struct Image16 {   // Rgba16Float, tightly packed w x h
+    const uint2* t; int w, h;
+    __device__ __forceinline__ vec4 texel(int x, int y) const {
+        x = min(max(x, 0), w - 1); y = min(max(y, 0), h - 1);
+        uint2 u = t[(size_t)y * w + x];
+        uvec2 q; q.x = u.x; q.y = u.y;
+        return unpack_rgba16f(q);
+    }
+    __device__ __forceinline__ vec4 load(int x, int y) const {   // textureLoad: zero outside
+        if (x < 0 || y < 0 || x >= w || y >= h) return v4(0.0f);
+        uint2 u = t[(size_t)y * w + x];
+        uvec2 q; q.x = u.x; q.y = u.y;
+        return unpack_rgba16f(q);
+    }
+    __device__ __forceinline__ vec4 nearest(vec2 uv) const { return texel((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
+    __device__ __forceinline__ vec4 linear(vec2 uv) const {
+        float fx = uv.x * (float)w - 0.5f, fy = uv.y * (float)h - 0.5f;
+        float x0 = floorf(fx), y0 = floorf(fy), ax = fx - x0, ay = fy - y0;
+        vec4 t00 = texel((int)x0, (int)y0), t10 = texel((int)x0 + 1, (int)y0), t01 = texel((int)x0, (int)y0 + 1), t11 = texel((int)x0 + 1, (int)y0 + 1);
+        vec4 top = t00 * (1.0f - ax) + t10 * ax, bot = t01 * (1.0f - ax) + t11 * ax;
+        return top * (1.0f - ay) + bot * ay;
+    }
+    __device__ __forceinline__ void gather(vec2 uv, vec4 out[4]) const {
+        float fx = uv.x * (float)w - 0.5f, fy = uv.y * (float)h - 0.5f;
+        int i0 = (int)floorf(fx), j0 = (int)floorf(fy);
+        out[0] = texel(i0, j0 + 1); out[1] = texel(i0 + 1, j0 + 1); out[2] = texel(i0 + 1, j0); out[3] = texel(i0, j0);
+    }
+};
+struct Image32 {   // a float4 plane of the (full-frame) G-buffer
+    const float4* t; int w, h;
+    __device__ __forceinline__ vec4 texel(int x, int y) const {
+        x = min(max(x, 0), w - 1); y = min(max(y, 0), h - 1);
+        return f4v(t[(size_t)y * w + x]);
+    }
+    __device__ __forceinline__ vec4 nearest(vec2 uv) const { return texel((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
+    __device__ __forceinline__ vec4 gather_w(vec2 uv) const {
+        float fx = uv.x * (float)w - 0.5f, fy = uv.y * (float)h - 0.5f;
+        int i0 = (int)floorf(fx), j0 = (int)floorf(fy);
+        return v4(texel(i0, j0 + 1).w, texel(i0 + 1, j0 + 1).w, texel(i0 + 1, j0).w, texel(i0, j0).w);
+    }
+};
+
+__device__ __forceinline__ vec3 RGB_to_YCoCg(vec3 rgb) {  // smaa.wgsl:23-28
+    float y = (rgb.x / 4.0f) + (rgb.y / 2.0f) + (rgb.z / 4.0f);
+    float co = (rgb.x / 2.0f) - (rgb.z / 2.0f);
+    float cg = (-rgb.x / 4.0f) + (rgb.y / 2.0f) - (rgb.z / 4.0f);
+    return v3(y, co, cg);
+}
+__device__ __forceinline__ vec3 clamp01(vec3 v) { return v3(clampf(v.x, 0.0f, 1.0f), clampf(v.y, 0.0f, 1.0f), clampf(v.z, 0.0f, 1.0f)); }
+__device__ __forceinline__ vec3 YCoCg_to_RGB(vec3 c) { return clamp01(v3(c.x + c.y - c.z, c.x + c.z, c.x - c.y - c.z)); }  // :30-35
+__device__ __forceinline__ vec3 vabs(vec3 a) { return v3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+__device__ __forceinline__ vec3 vsqrt(vec3 a) { return v3(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z)); }
+__device__ __forceinline__ vec3 clip_towards_aabb_center(vec3 previous_color, vec3 aabb_min, vec3 aabb_max) {  // smaa.wgsl:37-45
+    vec3 p_clip = 0.5f * (aabb_max + aabb_min);
+    vec3 e_clip = 0.5f * (aabb_max - aabb_min);
+    vec3 v_clip = previous_color - p_clip;
+    vec3 v_unit = v_clip / e_clip;
+    vec3 a_unit = vabs(v_unit);
+    float ma_unit = fmax_(a_unit.x, fmax_(a_unit.y, a_unit.z));
+    return (ma_unit > 1.0f) ? p_clip + v_clip / ma_unit : previous_color;
+}
+// smaa.wgsl:52-72 / taa.wgsl:57-77
+__device__ __forceinline__ vec2 nearest_velocity(const Image32& position, const Image32& velocity_uv, vec2 uv, vec2 texel_size) {
+    vec4 depths;
+    depths.x = position.nearest(uv + v2(texel_size.x, texel_size.y)).w;
+    depths.y = position.nearest(uv + v2(-texel_size.x, texel_size.y)).w;
+    depths.z = position.nearest(uv + v2(texel_size.x, -texel_size.y)).w;
+    depths.w = position.nearest(uv + v2(-texel_size.x, -texel_size.y)).w;
+    float max_depth = fmax_(fmax_(depths.x, depths.y), fmax_(depths.z, depths.w));
+    float depth = position.nearest(uv).w;
+    vec2 offset = v2(0.0f, 0.0f);
+    if (depth < max_depth) {
+        vec4 sx = v4(depths.x == max_depth ? 1.0f : 0.0f, depths.y == max_depth ? -1.0f : 0.0f, depths.z == max_depth ? 1.0f : 0.0f,
+                     depths.w == max_depth ? -1.0f : 0.0f);
+        vec4 sy = v4(depths.x == max_depth ? 1.0f : 0.0f, depths.y == max_depth ? 1.0f : 0.0f, depths.z == max_depth ? -1.0f : 0.0f,
+                     depths.w == max_depth ? -1.0f : 0.0f);
+        offset = v2(dot(v4(texel_size.x), sx), dot(v4(texel_size.y), sy));
+    }
+    vec4 v = velocity_uv.nearest(uv + offset);
+    return v2(v.x, v.y);
+}
+__device__ __forceinline__ float distance4(vec4 a, vec4 b) { vec4 d = a - b; return sqrtf(dot(d, d)); }
+__device__ __forceinline__ float distance2(vec2 a, vec2 b) { vec2 d = a - b; return sqrtf(dot(d, d)); }
+__device__ __forceinline__ bool any_lt(vec4 a, float t) { return a.x < t || a.y < t || a.z < t || a.w < t; }
+__device__ __forceinline__ vec4 depth_ratio_of(float current, vec4 previous) {   // select(current / previous, 1.0, previous == 0.0)
+    return v4(previous.x == 0.0f ? 1.0f : current / previous.x, previous.y == 0.0f ? 1.0f : current / previous.y,
+              previous.z == 0.0f ? 1.0f : current / previous.z, previous.w == 0.0f ? 1.0f : current / previous.w);
+}
+__device__ __forceinline__ void store16(uint2* plane, size_t i, vec4 v) {
+    uvec2 w = pack_rgba16f(v);
+    plane[i] = make_uint2(w.x, w.y);
+}
+
+// --------------------------------------------------------------------------------------------- smaa_tu4x
+__global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x(const __grid_constant__ KParams P) {  // smaa.wgsl:81-199
+    int x, y;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
+    const int RW = P.band.RW, RH = P.band.RH, OW = 2 * RW, OH = 2 * RH, W = P.band.W, H = P.band.H;
+    const uint32_t cur = P.in.frame.number % 2u, prv = 1u - cur;
+    const Image16 render{P.planes.tone_mapped_db[cur], RW, RH}, previous_render{P.planes.tone_mapped_db[prv], RW, RH};
+    const Image32 position{P.planes.pos_depth_db[P.gbuffer_current], W, H}, previous_position{P.planes.pos_depth_db[P.gbuffer_current ^ 1], W, H};
+    const Image32 velocity_uv{P.planes.velocity_uv_db[P.gbuffer_current], W, H}, previous_velocity_uv{P.planes.velocity_uv_db[P.gbuffer_current ^ 1], W, H};
+    const int current_jitter = ((P.in.frame.number & 1u) == 0u) ? 0 : 1;
+    const int previous_jitter = 1 - current_jitter;
+    const vec2 uv = render_uv(P, x, y);
+    const vec2 texel_size = v2(1.0f, 1.0f) / v2((float)OW, (float)OH);
+    const vec2 uv_biases[5] = {v2(0.0f, 0.0f), v2(2.5f, 2.5f) * texel_size, v2(-2.5f, 2.5f) * texel_size, v2(2.5f, -2.5f) * texel_size,
+                               v2(-2.5f, -2.5f) * texel_size};
+    const int cox = 2 * x + current_jitter, coy = 2 * y + current_jitter;
+    const vec3 current_color = xyz(render.nearest(uv));
+    const int pox = 2 * x + previous_jitter, poy = 2 * y + previous_jitter;
+    const vec2 previous_output_uv = (v2((float)pox, (float)poy) + 0.5f) / v2((float)OW, (float)OH);
+    const vec2 deferred_texel = v2(1.0f, 1.0f) / v2((float)W, (float)H);
+    const vec2 velocity = nearest_velocity(position, velocity_uv, previous_output_uv, deferred_texel);
+    const vec2 previous_reprojected_uv = previous_output_uv - velocity;
+    vec3 previous_color = xyz(previous_render.nearest(previous_reprojected_uv));
+    const bool boundary_miss = fabsf(previous_reprojected_uv.x - 0.5f) > 0.5f || fabsf(previous_reprojected_uv.y - 0.5f) > 0.5f;
+    auto instance_at = [&](vec2 u) {
+        int px = min(max((int)floorf(u.x * (float)W), 0), W - 1), py = min(max((int)floorf(u.y * (float)H), 0), H - 1);
+        return P.planes.instance_material[(size_t)py * W + px].x;
+    };
+    const float current_instance = instance_at(previous_output_uv);
+    bool instance_miss = false;
+    const float current_depth = position.nearest(previous_output_uv).w;
+    bool depth_miss = current_depth == 0.0f;
+    for (uint32_t i = 0u; i < 5u; i += 1u) {
+        vec4 depth_ratio = depth_ratio_of(current_depth, previous_position.gather_w(previous_reprojected_uv + uv_biases[i]));
+        depth_miss = depth_miss || any_lt(depth_ratio, 0.95f);
+        float previous_instance = instance_at(previous_reprojected_uv + uv_biases[i]);
+        instance_miss = instance_miss || (any_lt(depth_ratio, 0.95f) && fabsf(previous_instance - current_instance) > 1.0f);
+    }
+    vec4 pv = previous_velocity_uv.nearest(previous_reprojected_uv);
+    const bool velocity_miss = distance2(velocity, v2(pv.x, pv.y)) > 0.0001f;
+    if (boundary_miss || ((depth_miss || instance_miss) && velocity_miss)) {
+        vec2 uv_bias = v2(0.0f, 0.0f);
+        float min_ds = 10.0f;
+        for (uint32_t i = 0u; i < 5u; i += 1u) {
+            float dds = distance4(v4(current_depth), position.gather_w(previous_output_uv + uv_biases[i]));
+            if (dds < min_ds) uv_bias = uv_biases[i];
+            min_ds = fmin_(min_ds, dds);
+        }
+        vec4 g[4];
+        render.gather(previous_output_uv + uv_bias, g);
+        vec3 s1 = RGB_to_YCoCg(xyz(g[0])), s2 = RGB_to_YCoCg(xyz(g[1])), s3 = RGB_to_YCoCg(xyz(g[2])), s4 = RGB_to_YCoCg(xyz(g[3]));
+        vec3 moment_1 = s1 + s2 + s3 + s4;
+        vec3 moment_2 = s1 * s1 + s2 * s2 + s3 * s3 + s4 * s4;
+        vec3 mean = moment_1 / 4.0f;
+        vec3 variance = vsqrt((moment_2 / 4.0f) - (mean * mean));
+        previous_color = RGB_to_YCoCg(previous_color);
+        previous_color = clip_towards_aabb_center(previous_color, mean - variance, mean + variance);
+        previous_color = YCoCg_to_RGB(previous_color);
+    }
+    vec2 sv = velocity / (2.0f * texel_size);
+    float blend_factor = fmax_(fract(sv.x), fract(sv.y));
+    float sn, cs;
+    sincos_(blend_factor * TAU, &sn, &cs);
+    blend_factor = clampf(-cs, 0.0f, 1.0f);
+    vec3 remix_color = xyz(render.linear(previous_output_uv));
+    previous_color = mix(previous_color, remix_color, blend_factor);
+    store16(P.planes.upscale_output, (size_t)coy * OW + cox, v4(current_color, 1.0f));
+    store16(P.planes.upscale_output, (size_t)poy * OW + pox, v4(previous_color, 1.0f));
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x_extrapolate(const __grid_constant__ KParams P) {  // smaa.wgsl:201-271
+    int x, y;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
+    const int OW = 2 * P.band.RW, OH = 2 * P.band.RH;
+    const Image16 out{P.planes.upscale_output, OW, OH};
+    vec4 t = out.load(2 * x, 2 * y), b = out.load(2 * x + 1, 2 * y + 1), n = out.load(2 * x + 1, 2 * y - 1), e = out.load(2 * x + 2, 2 * y);
+    vec4 s_ = out.load(2 * x, 2 * y + 2), w = out.load(2 * x - 1, 2 * y + 1);
+    auto lum3 = [](vec4 a, vec4 c) { return luminance(vabs(xyz(a) - xyz(c))); };
+    vec2 dh = v2(lum3(w, b), lum3(t, e));
+    vec2 dv = v2(lum3(t, s_), lum3(n, b));
+    vec2 factor_xy = v2(fmax_(dv.x, 0.001f) * fmax_(dv.y, 0.001f), fmax_(dh.x, 0.001f) * fmax_(dh.y, 0.001f));
+    float factor_z = 1.0f / (factor_xy.x + factor_xy.y);
+    auto blend = [&](vec4 tt, vec4 bb, vec4 ll, vec4 rr) {
+        vec4 color = v4(0.0f);
+        color = color + (ll + rr) * factor_xy.x;
+        color = color + (tt + bb) * factor_xy.y;
+        return color * (0.5f * factor_z);
+    };
+    store16(P.planes.upscale_output, (size_t)(2 * y + 1) * OW + 2 * x, blend(t, s_, w, b));
+    store16(P.planes.upscale_output, (size_t)(2 * y) * OW + 2 * x + 1, blend(n, b, t, e));
+}
+
+// ------------------------------------------------------------------------------------------- taa_jasmine
+// launched over the OUTPUT size (2 RW x 2 RH after SMAA TU4x, else RW x RH): col_hi / row_hi carry it
+__global__ void __launch_bounds__(CTA_THREADS) k_taa_jasmine(const __grid_constant__ KParams P, int smaa) {  // taa.wgsl:79-170
+    int x, y;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
+    const int OW = smaa ? 2 * P.band.RW : P.band.RW, OH = smaa ? 2 * P.band.RH : P.band.RH, W = P.band.W, H = P.band.H;
+    const uint32_t cur = P.in.frame.number % 2u, prv = 1u - cur;
+    const Image16 render{smaa ? P.planes.upscale_output : P.planes.tone_mapped_db[cur], OW, OH};
+    const Image16 previous_render{P.planes.taa_output[prv], OW, OH};
+    const Image32 position{P.planes.pos_depth_db[P.gbuffer_current], W, H}, previous_position{P.planes.pos_depth_db[P.gbuffer_current ^ 1], W, H};
+    const Image32 velocity_uv{P.planes.velocity_uv_db[P.gbuffer_current], W, H}, previous_velocity_uv{P.planes.velocity_uv_db[P.gbuffer_current ^ 1], W, H};
+    auto sample_previous = [&](vec2 u) { return clamp01(xyz(previous_render.linear(u))); };
+    auto sample_render = [&](vec2 u) { return RGB_to_YCoCg(clamp01(xyz(render.nearest(u)))); };
+    const vec2 size = v2((float)OW, (float)OH);
+    const vec2 texel_size = v2(1.0f, 1.0f) / size;
+    const vec2 uv = (v2((float)x, (float)y) + 0.5f) / size;
+    const vec4 original_color = render.nearest(uv);
+    const vec3 current_color = xyz(original_color);
+    const vec2 velocity = nearest_velocity(position, velocity_uv, uv, texel_size);
+    const vec2 previous_uv = uv - velocity;
+    const bool boundary_miss = fabsf(previous_uv.x - 0.5f) > 0.5f || fabsf(previous_uv.y - 0.5f) > 0.5f;
+    const vec2 uv_biases[5] = {v2(0.0f, 0.0f), v2(1.5f, 1.5f) * texel_size, v2(-1.5f, 1.5f) * texel_size, v2(1.5f, -1.5f) * texel_size,
+                               v2(-1.5f, -1.5f) * texel_size};
+    const vec4 current_position_depth = position.nearest(uv);
+    bool has_content = current_position_depth.w > 0.0f;
+    bool depth_miss = current_position_depth.w == 0.0f;
+    bool position_miss = current_position_depth.w == 0.0f;
+    for (uint32_t i = 0u; i < 5u; i += 1u) {
+        vec4 pd = previous_position.gather_w(previous_uv + uv_biases[i]);
+        vec4 depth_ratio = depth_ratio_of(current_position_depth.w, pd);
+        has_content = has_content || pd.x > 0.0f || pd.y > 0.0f || pd.z > 0.0f || pd.w > 0.0f;
+        depth_miss = depth_miss || any_lt(depth_ratio, 0.95f);
+        vec3 previous_pos = xyz(previous_position.nearest(previous_uv + uv_biases[i]));
+        position_miss = position_miss || length(xyz(current_position_depth) - previous_pos) > 0.5f;
+    }
+    const size_t oidx = (size_t)y * OW + x;
+    if (!has_content) {
+        store16(P.planes.taa_output[cur], oidx, v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]));
+        return;
+    }
+    vec4 pv = previous_velocity_uv.nearest(previous_uv);
+    const bool velocity_miss = distance2(velocity, v2(pv.x, pv.y)) > 0.00005f;
+    // 5-tap Catmull-Rom, taa.wgsl:121-139
+    vec2 sample_position = (uv - velocity) * size;
+    vec2 tp1 = v2(floorf(sample_position.x - 0.5f), floorf(sample_position.y - 0.5f)) + 0.5f;
+    vec2 f = sample_position - tp1;
+    auto W0 = [](float f_) { return f_ * (-0.5f + f_ * (1.0f - 0.5f * f_)); };
+    auto W1 = [](float f_) { return 1.0f + f_ * f_ * (-2.5f + 1.5f * f_); };
+    auto W2 = [](float f_) { return f_ * (0.5f + f_ * (2.0f - 1.5f * f_)); };
+    auto W3 = [](float f_) { return f_ * f_ * (-0.5f + 0.5f * f_); };
+    vec2 w0 = v2(W0(f.x), W0(f.y)), w1 = v2(W1(f.x), W1(f.y)), w2 = v2(W2(f.x), W2(f.y)), w3 = v2(W3(f.x), W3(f.y));
+    vec2 w12 = w1 + w2;
+    vec2 offset12 = w2 / (w1 + w2);
+    vec2 tp0 = (tp1 - 1.0f) * texel_size;
+    vec2 tp3 = (tp1 + 2.0f) * texel_size;
+    vec2 tp12 = (tp1 + offset12) * texel_size;
+    vec3 previous_color = v3(0.0f);
+    previous_color = previous_color + sample_previous(v2(tp12.x, tp0.y)) * w12.x * w0.y;
+    previous_color = previous_color + sample_previous(v2(tp0.x, tp12.y)) * w0.x * w12.y;
+    previous_color = previous_color + sample_previous(v2(tp12.x, tp12.y)) * w12.x * w12.y;
+    previous_color = previous_color + sample_previous(v2(tp3.x, tp12.y)) * w3.x * w12.y;
+    previous_color = previous_color + sample_previous(v2(tp12.x, tp3.y)) * w12.x * w3.y;
+    if (boundary_miss || (position_miss && velocity_miss && depth_miss)) {
+        vec3 s_tl = sample_render(uv + v2(-texel_size.x, texel_size.y));
+        vec3 s_tm = sample_render(uv + v2(0.0f, texel_size.y));
+        vec3 s_tr = sample_render(uv + texel_size);
+        vec3 s_ml = sample_render(uv - v2(texel_size.x, 0.0f));
+        vec3 s_mm = RGB_to_YCoCg(current_color);
+        vec3 s_mr = sample_render(uv + v2(texel_size.x, 0.0f));
+        vec3 s_bl = sample_render(uv - texel_size);
+        vec3 s_bm = sample_render(uv - v2(0.0f, texel_size.y));
+        vec3 s_br = sample_render(uv + v2(texel_size.x, -texel_size.y));
+        vec3 moment_1 = s_tl + s_tm + s_tr + s_ml + s_mm + s_mr + s_bl + s_bm + s_br;
+        vec3 moment_2 = (s_tl * s_tl) + (s_tm * s_tm) + (s_tr * s_tr) + (s_ml * s_ml) + (s_mm * s_mm) + (s_mr * s_mr) + (s_bl * s_bl) +
+                        (s_bm * s_bm) + (s_br * s_br);
+        vec3 mean = moment_1 / 9.0f;
+        vec3 variance = vsqrt((moment_2 / 9.0f) - (mean * mean));
+        previous_color = RGB_to_YCoCg(previous_color);
+        previous_color = clip_towards_aabb_center(previous_color, mean - variance, mean + variance);
+        previous_color = YCoCg_to_RGB(previous_color);
+    }
+    vec3 output = mix(previous_color, current_color, 0.1f / P.in.frame.upscale_ratio);
+    store16(P.planes.taa_output[cur], oidx, v4(output, original_color.w));
+}
+
+static dim3 grid_for(const KParams& P) {
+    int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
+    return dim3((unsigned)((cols + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
+}
+
+}  // namespace hkd
+
+using namespace hkd;
+
+void hk_launch_smaa_tu4x(const KParams& P, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+    k_smaa_tu4x<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+    k_smaa_tu4x_extrapolate<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+}
+void hk_launch_taa_jasmine(const KParams& P, bool smaa, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+    k_taa_jasmine<<<grid_for(P), CTA_THREADS, 0, st>>>(P, smaa ? 1 : 0);
+}

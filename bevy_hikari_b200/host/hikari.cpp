@@ -535,6 +535,7 @@ int HikariPlugin::run_frame(const HikariSettings& settings, const ViewInputs& vi
     if (!ctx_) return HK_ERR_NOT_READY;
     counter.value += 1;
     hk_frame_inputs in = make_frame_inputs(settings, counter, view);
+    in.temporal_upscalers = temporal_upscalers ? 1u : 0u;
     return hk_render_frame(ctx_, &in);
 }
 std::string HikariPlugin::last_error() const { return hk_last_error(ctx_); }

@@ -191,6 +191,9 @@ public:
     int run_frame(const HikariSettings& settings, const ViewInputs& view);
     hk_context* context() const { return ctx_; }
     FrameCounter counter;
+    // run the temporal upscalers after tone mapping (smaa_tu4x / taa_jasmine as `settings` select them,
+    // post_process.rs:1236-1277).  Off by default: the sharded / benchmarked path ends at the tone-mapped image.
+    bool temporal_upscalers = false;
     std::string last_error() const;
 
 private:

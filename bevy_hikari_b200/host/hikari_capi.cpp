@@ -127,5 +127,6 @@ int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk
 hk_context* hikari_plugin_context(hikari_plugin* p) { return P(p)->context(); }
 uint64_t hikari_plugin_frame_counter(hikari_plugin* p) { return P(p)->counter.value; }
 void hikari_plugin_set_frame_counter(hikari_plugin* p, uint64_t v) { P(p)->counter.value = (size_t)v; }
+void hikari_plugin_set_temporal_upscalers(hikari_plugin* p, int enabled) { P(p)->temporal_upscalers = enabled != 0; }
 
 }  // extern "C"

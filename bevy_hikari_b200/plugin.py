@@ -33,10 +33,11 @@ def HikariSettings(**overrides):
     return s
 
 
-def make_frame_inputs(settings, frame_counter, view, previous_view, lights):
+def make_frame_inputs(settings, frame_counter, view, previous_view, lights, temporal_upscalers=False):
     out = L.FrameInputs()
     lib().hikari_make_frame_inputs(C.byref(settings), int(frame_counter), C.byref(view), C.byref(previous_view),
                                    C.byref(lights), C.byref(out))
+    out.temporal_upscalers = 1 if temporal_upscalers else 0
     return out
 
 
@@ -182,6 +183,9 @@ class HikariPlugin:
     def frame_counter(self, v):
         lib().hikari_plugin_set_frame_counter(self._p, int(v))
 
+    def set_temporal_upscalers(self, enabled):
+        lib().hikari_plugin_set_temporal_upscalers(self._p, 1 if enabled else 0)
+
     def run_frame(self, settings, view, previous_view, lights):
         check(lib().hikari_plugin_run_frame(self._p, C.byref(settings), C.byref(view), C.byref(previous_view), C.byref(lights)),
               self.ctx)
@@ -201,13 +205,19 @@ class HikariPlugin:
         check(lib().hk_get_stats(self.ctx, C.byref(s)), self.ctx)
         return s
 
+    def output_extent(self, which):
+        w, h = C.c_uint32(), C.c_uint32()
+        check(lib().hk_output_extent(self.ctx, which, C.byref(w), C.byref(h)), self.ctx)
+        return w.value, h.value
+
     def readback(self, which, out=None):
         bpp, dt, comps = L.OUT_FORMATS[which]
-        n = self.owned_rows * self.owned_cols
+        w, h = self.output_extent(which)
+        n = w * h
         if out is None:
             out = np.empty(n * bpp, np.uint8)
         check(lib().hk_readback(self.ctx, which, out.ctypes.data, n * bpp), self.ctx)
-        return view_plane(out, which, self.owned_rows, self.owned_cols)
+        return view_plane(out[:n * bpp], which, h, w)
 
     def readback_into(self, which, host_ptr, nbytes):
         check(lib().hk_readback(self.ctx, which, host_ptr, nbytes), self.ctx)
@@ -216,9 +226,9 @@ class HikariPlugin:
         a = np.ascontiguousarray(array)
         check(lib().hk_upload_state(self.ctx, which, a.ctypes.data, a.nbytes), self.ctx)
 
-    def output_device_pointer(self):
+    def output_device_pointer(self, which=L.OUT_TONE_MAPPED):
         p, b = C.c_void_p(), C.c_size_t()
-        check(lib().hk_get_output(self.ctx, L.OUT_TONE_MAPPED, C.byref(p), C.byref(b)), self.ctx)
+        check(lib().hk_get_output(self.ctx, which, C.byref(p), C.byref(b)), self.ctx)
         return p.value, b.value
 
     def trace_rays(self, rays):

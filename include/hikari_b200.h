@@ -75,8 +75,10 @@ typedef struct hk_frame_inputs {
     hk_lights lights;
     uint32_t denoise;                /* HikariSettings::denoise (src/lib.rs:428) */
     uint32_t taa_jitter;             /* 1 = TEMPORAL_ANTI_ALIASING jitter in the prepass (prepass.wgsl:52-54) */
-    uint32_t smaa_tu4x;              /* 1 = SMAA_TU4X jitter index rule (prepass.wgsl:31-35) */
-    uint32_t _pad;
+    uint32_t smaa_tu4x;              /* 1 = Upscale::SmaaTu4x: SMAA_TU4X jitter index rule (prepass.wgsl:31-35) */
+    uint32_t temporal_upscalers;     /* 1 = hk_post_process_run continues past tone mapping with smaa_tu4x + smaa_tu4x_extrapolate
+                                        (when smaa_tu4x) and taa_jasmine (when taa_jitter) — post_process.rs:1236-1277, the
+                                        "next" rows K11/K12 of SURVEY.md 8(f).  0 = the hot path ends at tone mapping. */
 } hk_frame_inputs;
 
 /* Identifiers for hk_get_output / hk_readback / hk_upload_state.  Read-back formats are the reference's texture /
@@ -94,6 +96,8 @@ enum {
     HK_OUT_DENOISED_DIRECT = 8,  /* Rgba16Float           post_process.rs:714 denoise_render[0] */
     HK_OUT_DENOISED_EMISSIVE = 9,
     HK_OUT_DENOISED_INDIRECT = 10,
+    HK_OUT_UPSCALED = 11,        /* Rgba16Float, 2x render size   post_process.rs:718-722 upscale_output[0] (SMAA TU4x) */
+    HK_OUT_TAA = 12,             /* Rgba16Float, 2x render size with SMAA TU4x else render size   post_process.rs:726-731 taa_output[current] */
     HK_OUT_GBUFFER_POSITION = 16,           /* Rgba32Float 16 B/px */
     HK_OUT_GBUFFER_NORMAL = 17,             /* Rgba8Snorm   4 B/px */
     HK_OUT_GBUFFER_DEPTH_GRADIENT = 18,     /* Rg32Float    8 B/px */
@@ -123,7 +127,9 @@ enum {   /* indices into hk_frame_stats.ms_kernel */
     HK_K_DEMODULATION = 6,
     HK_K_DENOISE_0 = 7, HK_K_DENOISE_1 = 8, HK_K_DENOISE_2 = 9, HK_K_DENOISE_3 = 10,   /* level 3 includes tone mapping when fused */
     HK_K_TONE_MAPPING = 11,
-    HK_K_COUNT = 12
+    HK_K_SMAA_TU4X = 12,         /* smaa_tu4x + smaa_tu4x_extrapolate (only with temporal_upscalers) */
+    HK_K_TAA = 13,               /* taa_jasmine (only with temporal_upscalers) */
+    HK_K_COUNT = 14
 };
 
 typedef struct hk_ray {   /* test hook input: a world-space ray exactly as traverse_top takes it */
@@ -160,7 +166,12 @@ int hk_light_run(hk_context* ctx, const hk_frame_inputs* in);
 int hk_post_process_run(hk_context* ctx, const hk_frame_inputs* in);
 int hk_render_frame(hk_context* ctx, const hk_frame_inputs* in);     /* prepass -> light -> post process */
 
-int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes);  /* HK_OUT_TONE_MAPPED only: owned rows */
+int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes);  /* final images only: HK_OUT_TONE_MAPPED (owned
+                                                                                     rectangle), HK_OUT_UPSCALED, HK_OUT_TAA */
+/* Pixels of the rectangle hk_readback / hk_get_output transfer for `which`, under the settings of the last frame run:
+ * deferred-size planes (G-buffer, albedo) = the owned rectangle; render-size planes = ceil(size / upscale_ratio)
+ * (light.rs:622-624); HK_OUT_UPSCALED (and HK_OUT_TAA after smaa_tu4x) = twice the render size (post_process.rs:718-731). */
+int hk_output_extent(hk_context* ctx, int which, uint32_t* width, uint32_t* height);
 int hk_readback(hk_context* ctx, int which, void* host, size_t bytes);            /* synchronises */
 int hk_upload_state(hk_context* ctx, int which, const void* host, size_t bytes);  /* inverse of hk_readback (tests) */
 int hk_sync(hk_context* ctx);

@@ -67,6 +67,8 @@ int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk
 hk_context* hikari_plugin_context(hikari_plugin* p);
 uint64_t hikari_plugin_frame_counter(hikari_plugin* p);
 void hikari_plugin_set_frame_counter(hikari_plugin* p, uint64_t v);
+/* 1 = run_frame continues past tone mapping with smaa_tu4x / taa_jasmine as the settings select (post_process.rs:1236-1277) */
+void hikari_plugin_set_temporal_upscalers(hikari_plugin* p, int enabled);
 
 #ifdef __cplusplus
 }

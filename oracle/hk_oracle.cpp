@@ -94,6 +94,7 @@ struct hko_context {
     std::vector<vec2> depth_gradient;      // Rg32Float
     std::vector<vec2> instance_material;   // Rg32Float
     std::vector<vec4> velocity_uv;         // Rgba32Float
+    std::vector<vec4> previous_position, previous_velocity_uv;   // swapped with the current ones every frame (prepass.rs:312-321,427)
     // light textures (bind group 5) and reservoirs (bind group 6)
     std::vector<uvec2> albedo;             // Rgba16Float, full size
     std::vector<uvec2> render[3];          // Rgba16Float
@@ -103,7 +104,9 @@ struct hko_context {
     std::vector<uvec2> denoise_internal[4];
     std::vector<float> denoise_internal_variance;
     std::vector<uvec2> denoise_render[3];
-    std::vector<uvec2> tone_mapping_output;
+    std::vector<uvec2> tone_mapping_output[2];   // [frame.number % 2] is written (post_process.rs:716,979)
+    std::vector<uvec2> upscale_output;           // 2 RW x 2 RH (post_process.rs:718-722)
+    std::vector<uvec2> taa_output[2];            // 2 RW x 2 RH with SMAA TU4x, else RW x RH (post_process.rs:726-731)
     // per-frame
     hk_frame_inputs in;
     struct alignas(64) RayCounters { uint64_t primary = 0, tlas = 0, blas = 0; };
@@ -716,6 +719,9 @@ Ray primary_ray(const Ctx& c, float px, float py, vec2 jitter_ndc) {
     return ray;
 }
 void pass_prepass(Ctx& c) {
+    // prepass_textures_system swaps current <-> previous every frame before the pass renders (prepass.rs:427)
+    c.position.swap(c.previous_position);
+    c.velocity_uv.swap(c.previous_velocity_uv);
     const mat4 view_proj = ldm(c.in.view.view_proj);
     const mat4 prev_view_proj = ldm(c.in.previous_view.view_proj);
     vec2 jitter_ndc = v2(0.0f, 0.0f);
@@ -1344,7 +1350,280 @@ void pass_tone_mapping(Ctx& c) {  // tone_mapping.wgsl:21-32 ; inputs per post_p
         vec3 rgb = reinhard_luminance(vmax(xyz(color), 0.0039f));
         color = v4(rgb, color.w);
         if (!(color.w > 0.0f)) color = ld4(c.in.frame.clear_color);
-        c.tone_mapping_output[idx] = pack_rgba16f(color);
+        c.tone_mapping_output[c.in.frame.number % 2u][idx] = pack_rgba16f(color);
+    });
+}
+
+
+// ----------------------------------------------------------------------------- K11/K12: SMAA TU4x and TAA
+// Texture addressing used by smaa.wgsl / taa.wgsl, both samplers clamp-to-edge (post_process.rs:697-708):
+//   nearest: texel floor(uv * size);  linear: bilinear around uv * size - 0.5 with fp32 weights;
+//   textureGather: the 2x2 bilinear footprint as (x: (i0,j1), y: (i1,j1), z: (i1,j0), w: (i0,j0)).
+struct Image16 {   // an Rgba16Float texture
+    const std::vector<uvec2>* t; int w, h;
+    vec4 texel(int x, int y) const {
+        x = std::min(std::max(x, 0), w - 1); y = std::min(std::max(y, 0), h - 1);
+        return unpack_rgba16f((*t)[(size_t)y * w + x]);
+    }
+    vec4 load(ivec2 p) const { return (p.x < 0 || p.y < 0 || p.x >= w || p.y >= h) ? v4(0.0f) : unpack_rgba16f((*t)[(size_t)p.y * w + p.x]); }
+    vec4 nearest(vec2 uv) const { return texel((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
+    vec4 linear(vec2 uv) const {
+        float fx = uv.x * (float)w - 0.5f, fy = uv.y * (float)h - 0.5f;
+        float x0 = floorf(fx), y0 = floorf(fy), ax = fx - x0, ay = fy - y0;
+        vec4 t00 = texel((int)x0, (int)y0), t10 = texel((int)x0 + 1, (int)y0), t01 = texel((int)x0, (int)y0 + 1), t11 = texel((int)x0 + 1, (int)y0 + 1);
+        vec4 top = t00 * (1.0f - ax) + t10 * ax, bot = t01 * (1.0f - ax) + t11 * ax;
+        return top * (1.0f - ay) + bot * ay;
+    }
+    void gather(vec2 uv, vec4 out[4]) const {   // out[k] = texel k of the footprint in gather order
+        float fx = uv.x * (float)w - 0.5f, fy = uv.y * (float)h - 0.5f;
+        int i0 = (int)floorf(fx), j0 = (int)floorf(fy);
+        out[0] = texel(i0, j0 + 1); out[1] = texel(i0 + 1, j0 + 1); out[2] = texel(i0 + 1, j0); out[3] = texel(i0, j0);
+    }
+};
+struct Image32 {   // an Rgba32Float texture (position / velocity_uv planes)
+    const std::vector<vec4>* t; int w, h;
+    vec4 texel(int x, int y) const {
+        x = std::min(std::max(x, 0), w - 1); y = std::min(std::max(y, 0), h - 1);
+        return (*t)[(size_t)y * w + x];
+    }
+    vec4 nearest(vec2 uv) const { return texel((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
+    vec4 gather_w(vec2 uv) const {
+        float fx = uv.x * (float)w - 0.5f, fy = uv.y * (float)h - 0.5f;
+        int i0 = (int)floorf(fx), j0 = (int)floorf(fy);
+        return v4(texel(i0, j0 + 1).w, texel(i0 + 1, j0 + 1).w, texel(i0 + 1, j0).w, texel(i0, j0).w);
+    }
+};
+inline vec3 RGB_to_YCoCg(vec3 rgb) {  // smaa.wgsl:23-28
+    float y = (rgb.x / 4.0f) + (rgb.y / 2.0f) + (rgb.z / 4.0f);
+    float co = (rgb.x / 2.0f) - (rgb.z / 2.0f);
+    float cg = (-rgb.x / 4.0f) + (rgb.y / 2.0f) - (rgb.z / 4.0f);
+    return v3(y, co, cg);
+}
+inline vec3 clamp01(vec3 v) { return v3(clampf(v.x, 0.0f, 1.0f), clampf(v.y, 0.0f, 1.0f), clampf(v.z, 0.0f, 1.0f)); }
+inline vec3 YCoCg_to_RGB(vec3 c) {  // smaa.wgsl:30-35
+    return clamp01(v3(c.x + c.y - c.z, c.x + c.z, c.x - c.y - c.z));
+}
+inline vec3 vabs(vec3 a) { return v3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+inline vec3 vsqrt(vec3 a) { return v3(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z)); }
+inline vec3 clip_towards_aabb_center(vec3 previous_color, vec3 current_color, vec3 aabb_min, vec3 aabb_max) {  // smaa.wgsl:37-45
+    (void)current_color;
+    vec3 p_clip = 0.5f * (aabb_max + aabb_min);
+    vec3 e_clip = 0.5f * (aabb_max - aabb_min);
+    vec3 v_clip = previous_color - p_clip;
+    vec3 v_unit = v_clip / e_clip;
+    vec3 a_unit = vabs(v_unit);
+    float ma_unit = fmax_(a_unit.x, fmax_(a_unit.y, a_unit.z));
+    return (ma_unit > 1.0f) ? p_clip + v_clip / ma_unit : previous_color;
+}
+// smaa.wgsl:52-72 / taa.wgsl:57-77; `texel_size` differs between the two callers
+vec2 nearest_velocity(const Image32& position, const Image32& velocity_uv, vec2 uv, vec2 texel_size) {
+    vec4 depths;
+    depths.x = position.nearest(uv + v2(texel_size.x, texel_size.y)).w;
+    depths.y = position.nearest(uv + v2(-texel_size.x, texel_size.y)).w;
+    depths.z = position.nearest(uv + v2(texel_size.x, -texel_size.y)).w;
+    depths.w = position.nearest(uv + v2(-texel_size.x, -texel_size.y)).w;
+    float max_depth = fmax_(fmax_(depths.x, depths.y), fmax_(depths.z, depths.w));
+    float depth = position.nearest(uv).w;
+    vec2 offset = v2(0.0f, 0.0f);
+    if (depth < max_depth) {
+        vec4 sx = v4(depths.x == max_depth ? 1.0f : 0.0f, depths.y == max_depth ? -1.0f : 0.0f, depths.z == max_depth ? 1.0f : 0.0f,
+                     depths.w == max_depth ? -1.0f : 0.0f);
+        vec4 sy = v4(depths.x == max_depth ? 1.0f : 0.0f, depths.y == max_depth ? 1.0f : 0.0f, depths.z == max_depth ? -1.0f : 0.0f,
+                     depths.w == max_depth ? -1.0f : 0.0f);
+        offset = v2(dot(v4(texel_size.x), sx), dot(v4(texel_size.y), sy));
+    }
+    vec4 v = velocity_uv.nearest(uv + offset);
+    return v2(v.x, v.y);
+}
+inline float distance4(vec4 a, vec4 b) { vec4 d = a - b; return sqrtf(dot(d, d)); }
+inline float distance2(vec2 a, vec2 b) { vec2 d = a - b; return sqrtf(dot(d, d)); }
+inline bool any_lt(vec4 a, float t) { return a.x < t || a.y < t || a.z < t || a.w < t; }
+
+void pass_smaa_tu4x(Ctx& c) {  // smaa.wgsl:81-199
+    const uint32_t cur = c.in.frame.number % 2u, prev = 1u - cur;
+    Image16 render{&c.tone_mapping_output[cur], c.RW, c.RH}, previous_render{&c.tone_mapping_output[prev], c.RW, c.RH};
+    Image32 position{&c.position, c.W, c.H}, previous_position{&c.previous_position, c.W, c.H};
+    Image32 velocity_uv{&c.velocity_uv, c.W, c.H}, previous_velocity_uv{&c.previous_velocity_uv, c.W, c.H};
+    const int OW = 2 * c.RW, OH = 2 * c.RH;
+    ivec2 input_size; input_size.x = c.RW; input_size.y = c.RH;
+    ivec2 output_size; output_size.x = OW; output_size.y = OH;
+    const int current_jitter = ((c.in.frame.number & 1u) == 0u) ? 0 : 1;     // current_smaa_jitter :74-76
+    const int previous_jitter = ((c.in.frame.number & 1u) == 0u) ? 1 : 0;    // previous_smaa_jitter :78-80
+    for_pixels(c, c.RW, c.RH, [&](int x, int y) {
+        ivec2 coords; coords.x = x; coords.y = y;
+        vec2 uv = coords_to_uv(coords, input_size);
+        vec2 texel_size = v2(1.0f, 1.0f) / v2((float)OW, (float)OH);
+        vec2 uv_biases[5] = {v2(0.0f, 0.0f), v2(2.5f, 2.5f) * texel_size, v2(-2.5f, 2.5f) * texel_size, v2(2.5f, -2.5f) * texel_size,
+                             v2(-2.5f, -2.5f) * texel_size};
+        ivec2 current_output_coords; current_output_coords.x = 2 * x + current_jitter; current_output_coords.y = 2 * y + current_jitter;
+        vec3 current_color = xyz(render.nearest(uv));
+        ivec2 previous_output_coords; previous_output_coords.x = 2 * x + previous_jitter; previous_output_coords.y = 2 * y + previous_jitter;
+        vec2 previous_output_uv = coords_to_uv(previous_output_coords, output_size);
+        vec2 deferred_texel = v2(1.0f, 1.0f) / v2((float)c.W, (float)c.H);
+        vec2 velocity = nearest_velocity(position, velocity_uv, previous_output_uv, deferred_texel);
+        vec2 previous_reprojected_uv = previous_output_uv - velocity;
+        vec3 previous_color = xyz(previous_render.nearest(previous_reprojected_uv));
+        bool boundary_miss = fabsf(previous_reprojected_uv.x - 0.5f) > 0.5f || fabsf(previous_reprojected_uv.y - 0.5f) > 0.5f;
+        Image32 instance_material_dummy{nullptr, 0, 0}; (void)instance_material_dummy;
+        auto instance_at = [&](vec2 u) {
+            int px = std::min(std::max((int)floorf(u.x * (float)c.W), 0), c.W - 1), py = std::min(std::max((int)floorf(u.y * (float)c.H), 0), c.H - 1);
+            return c.instance_material[(size_t)py * c.W + px].x;
+        };
+        float current_instance = instance_at(previous_output_uv);
+        bool instance_miss = false;
+        float current_depth = position.nearest(previous_output_uv).w;
+        bool depth_miss = current_depth == 0.0f;
+        for (uint32_t i = 0u; i < 5u; i += 1u) {
+            vec4 previous_depths = previous_position.gather_w(previous_reprojected_uv + uv_biases[i]);
+            vec4 q = v4(current_depth) ;
+            vec4 depth_ratio = v4(previous_depths.x == 0.0f ? 1.0f : q.x / previous_depths.x, previous_depths.y == 0.0f ? 1.0f : q.y / previous_depths.y,
+                                  previous_depths.z == 0.0f ? 1.0f : q.z / previous_depths.z, previous_depths.w == 0.0f ? 1.0f : q.w / previous_depths.w);
+            depth_miss = depth_miss || any_lt(depth_ratio, 0.95f);
+            float previous_instance = instance_at(previous_reprojected_uv + uv_biases[i]);
+            instance_miss = instance_miss || (any_lt(depth_ratio, 0.95f) && fabsf(previous_instance - current_instance) > 1.0f);
+        }
+        vec4 pv = previous_velocity_uv.nearest(previous_reprojected_uv);
+        bool velocity_miss = distance2(velocity, v2(pv.x, pv.y)) > 0.0001f;
+        if (boundary_miss || ((depth_miss || instance_miss) && velocity_miss)) {
+            vec2 uv_bias = v2(0.0f, 0.0f);
+            float min_ds = 10.0f;
+            for (uint32_t i = 0u; i < 5u; i += 1u) {
+                vec4 ds = position.gather_w(previous_output_uv + uv_biases[i]);
+                float dds = distance4(v4(current_depth), ds);
+                if (dds < min_ds) uv_bias = uv_biases[i];
+                min_ds = fmin_(min_ds, dds);
+            }
+            vec4 g[4];
+            render.gather(previous_output_uv + uv_bias, g);
+            vec3 s1 = RGB_to_YCoCg(xyz(g[0])), s2 = RGB_to_YCoCg(xyz(g[1])), s3 = RGB_to_YCoCg(xyz(g[2])), s4 = RGB_to_YCoCg(xyz(g[3]));
+            vec3 s_mm = RGB_to_YCoCg(current_color);
+            vec3 moment_1 = s1 + s2 + s3 + s4;
+            vec3 moment_2 = s1 * s1 + s2 * s2 + s3 * s3 + s4 * s4;
+            vec3 mean = moment_1 / 4.0f;
+            vec3 variance = vsqrt((moment_2 / 4.0f) - (mean * mean));
+            previous_color = RGB_to_YCoCg(previous_color);
+            previous_color = clip_towards_aabb_center(previous_color, s_mm, mean - variance, mean + variance);
+            previous_color = YCoCg_to_RGB(previous_color);
+        }
+        vec2 sv = velocity / (2.0f * texel_size);
+        vec2 subpixel_velocity = v2(fract(sv.x), fract(sv.y));
+        float blend_factor = fmax_(subpixel_velocity.x, subpixel_velocity.y);
+        float sn, cs; sincos_(blend_factor * TAU, &sn, &cs);
+        blend_factor = clampf(-cs, 0.0f, 1.0f);
+        vec3 remix_color = xyz(render.linear(previous_output_uv));
+        previous_color = mix(previous_color, remix_color, blend_factor);
+        c.upscale_output[(size_t)current_output_coords.y * OW + current_output_coords.x] = pack_rgba16f(v4(current_color, 1.0f));
+        c.upscale_output[(size_t)previous_output_coords.y * OW + previous_output_coords.x] = pack_rgba16f(v4(previous_color, 1.0f));
+    });
+}
+
+void pass_smaa_tu4x_extrapolate(Ctx& c) {  // smaa.wgsl:201-271
+    const int OW = 2 * c.RW, OH = 2 * c.RH;
+    Image16 out{&c.upscale_output, OW, OH};
+    auto lum3 = [](vec4 a, vec4 b) { return luminance(vabs(xyz(a) - xyz(b))); };
+    for_pixels(c, c.RW, c.RH, [&](int x, int y) {
+        auto L = [&](int dx, int dy) { ivec2 p; p.x = 2 * x + dx; p.y = 2 * y + dy; return out.load(p); };
+        vec4 t = L(0, 0), b = L(1, 1), n = L(1, -1), e = L(2, 0), s_ = L(0, 2), w = L(-1, 1);
+        // differential_blend_factor :201-222
+        vec2 dh = v2(lum3(w, b), lum3(t, e));
+        vec2 dv = v2(lum3(t, s_), lum3(n, b));
+        vec2 factor_xy = v2(fmax_(dv.x, 0.001f) * fmax_(dv.y, 0.001f), fmax_(dh.x, 0.001f) * fmax_(dh.y, 0.001f));
+        float factor_z = 1.0f / (factor_xy.x + factor_xy.y);
+        auto blend = [&](vec4 tt, vec4 bb, vec4 ll, vec4 rr) {  // differential_blend :224-235
+            vec4 color = v4(0.0f);
+            color = color + (ll + rr) * factor_xy.x;
+            color = color + (tt + bb) * factor_xy.y;
+            return color * (0.5f * factor_z);
+        };
+        vec4 x_color = blend(t, s_, w, b);
+        vec4 y_color = blend(n, b, t, e);
+        c.upscale_output[(size_t)(2 * y + 1) * OW + 2 * x] = pack_rgba16f(x_color);
+        c.upscale_output[(size_t)(2 * y) * OW + 2 * x + 1] = pack_rgba16f(y_color);
+    });
+}
+
+void pass_taa_jasmine(Ctx& c) {  // taa.wgsl:79-170
+    const uint32_t cur = c.in.frame.number % 2u, prev = 1u - cur;
+    const bool smaa = c.in.smaa_tu4x != 0;
+    const int OW = smaa ? 2 * c.RW : c.RW, OH = smaa ? 2 * c.RH : c.RH;      // post_process.rs:718-731,1257
+    Image16 render{smaa ? &c.upscale_output : &c.tone_mapping_output[cur], OW, OH};   // taa_input_texture, post_process.rs:1011-1014
+    Image16 previous_render{&c.taa_output[prev], OW, OH};
+    Image32 position{&c.position, c.W, c.H}, previous_position{&c.previous_position, c.W, c.H};
+    Image32 velocity_uv{&c.velocity_uv, c.W, c.H}, previous_velocity_uv{&c.previous_velocity_uv, c.W, c.H};
+    ivec2 output_size; output_size.x = OW; output_size.y = OH;
+    auto sample_previous = [&](vec2 u) { return clamp01(xyz(previous_render.linear(u))); };          // :47-50
+    auto sample_render = [&](vec2 u) { return RGB_to_YCoCg(clamp01(xyz(render.nearest(u)))); };      // :52-55
+    for_pixels(c, OW, OH, [&](int x, int y) {
+        ivec2 coords; coords.x = x; coords.y = y;
+        vec2 size = v2((float)OW, (float)OH);
+        vec2 texel_size = v2(1.0f, 1.0f) / size;
+        vec2 uv = coords_to_uv(coords, output_size);
+        vec4 original_color = render.nearest(uv);
+        vec3 current_color = xyz(original_color);
+        vec2 velocity = nearest_velocity(position, velocity_uv, uv, texel_size);   // texel of render_texture here (taa.wgsl:58)
+        vec2 previous_uv = uv - velocity;
+        bool boundary_miss = fabsf(previous_uv.x - 0.5f) > 0.5f || fabsf(previous_uv.y - 0.5f) > 0.5f;
+        vec2 uv_biases[5] = {v2(0.0f, 0.0f), v2(1.5f, 1.5f) * texel_size, v2(-1.5f, 1.5f) * texel_size, v2(1.5f, -1.5f) * texel_size,
+                             v2(-1.5f, -1.5f) * texel_size};
+        vec4 current_position_depth = position.nearest(uv);
+        bool has_content = current_position_depth.w > 0.0f;
+        bool depth_miss = current_position_depth.w == 0.0f;
+        bool position_miss = current_position_depth.w == 0.0f;
+        for (uint32_t i = 0u; i < 5u; i += 1u) {
+            vec4 pd = previous_position.gather_w(previous_uv + uv_biases[i]);
+            float cd = current_position_depth.w;
+            vec4 depth_ratio = v4(pd.x == 0.0f ? 1.0f : cd / pd.x, pd.y == 0.0f ? 1.0f : cd / pd.y, pd.z == 0.0f ? 1.0f : cd / pd.z,
+                                  pd.w == 0.0f ? 1.0f : cd / pd.w);
+            has_content = has_content || pd.x > 0.0f || pd.y > 0.0f || pd.z > 0.0f || pd.w > 0.0f;
+            depth_miss = depth_miss || any_lt(depth_ratio, 0.95f);
+            vec3 previous_pos = xyz(previous_position.nearest(previous_uv + uv_biases[i]));
+            position_miss = position_miss || length(xyz(current_position_depth) - previous_pos) > 0.5f;
+        }
+        size_t oidx = (size_t)y * OW + x;
+        if (!has_content) { c.taa_output[cur][oidx] = pack_rgba16f(ld4(c.in.frame.clear_color)); return; }
+        vec4 pv = previous_velocity_uv.nearest(previous_uv);
+        bool velocity_miss = distance2(velocity, v2(pv.x, pv.y)) > 0.00005f;
+        // 5-tap Catmull-Rom (taa.wgsl:121-139)
+        vec2 sample_position = (uv - velocity) * size;
+        vec2 tp1 = v2(floorf(sample_position.x - 0.5f), floorf(sample_position.y - 0.5f)) + 0.5f;
+        vec2 f = sample_position - tp1;
+        auto W0 = [](float f_) { return f_ * (-0.5f + f_ * (1.0f - 0.5f * f_)); };
+        auto W1 = [](float f_) { return 1.0f + f_ * f_ * (-2.5f + 1.5f * f_); };
+        auto W2 = [](float f_) { return f_ * (0.5f + f_ * (2.0f - 1.5f * f_)); };
+        auto W3 = [](float f_) { return f_ * f_ * (-0.5f + 0.5f * f_); };
+        vec2 w0 = v2(W0(f.x), W0(f.y)), w1 = v2(W1(f.x), W1(f.y)), w2 = v2(W2(f.x), W2(f.y)), w3 = v2(W3(f.x), W3(f.y));
+        vec2 w12 = w1 + w2;
+        vec2 offset12 = w2 / (w1 + w2);
+        vec2 tp0 = (tp1 - 1.0f) * texel_size;
+        vec2 tp3 = (tp1 + 2.0f) * texel_size;
+        vec2 tp12 = (tp1 + offset12) * texel_size;
+        vec3 previous_color = v3(0.0f);
+        previous_color = previous_color + sample_previous(v2(tp12.x, tp0.y)) * w12.x * w0.y;
+        previous_color = previous_color + sample_previous(v2(tp0.x, tp12.y)) * w0.x * w12.y;
+        previous_color = previous_color + sample_previous(v2(tp12.x, tp12.y)) * w12.x * w12.y;
+        previous_color = previous_color + sample_previous(v2(tp3.x, tp12.y)) * w3.x * w12.y;
+        previous_color = previous_color + sample_previous(v2(tp12.x, tp3.y)) * w12.x * w3.y;
+        if (boundary_miss || (position_miss && velocity_miss && depth_miss)) {
+            vec3 s_tl = sample_render(uv + v2(-texel_size.x, texel_size.y));
+            vec3 s_tm = sample_render(uv + v2(0.0f, texel_size.y));
+            vec3 s_tr = sample_render(uv + texel_size);
+            vec3 s_ml = sample_render(uv - v2(texel_size.x, 0.0f));
+            vec3 s_mm = RGB_to_YCoCg(current_color);
+            vec3 s_mr = sample_render(uv + v2(texel_size.x, 0.0f));
+            vec3 s_bl = sample_render(uv - texel_size);
+            vec3 s_bm = sample_render(uv - v2(0.0f, texel_size.y));
+            vec3 s_br = sample_render(uv + v2(texel_size.x, -texel_size.y));
+            vec3 moment_1 = s_tl + s_tm + s_tr + s_ml + s_mm + s_mr + s_bl + s_bm + s_br;
+            vec3 moment_2 = (s_tl * s_tl) + (s_tm * s_tm) + (s_tr * s_tr) + (s_ml * s_ml) + (s_mm * s_mm) + (s_mr * s_mr) + (s_bl * s_bl) +
+                            (s_bm * s_bm) + (s_br * s_br);
+            vec3 mean = moment_1 / 9.0f;
+            vec3 variance = vsqrt((moment_2 / 9.0f) - (mean * mean));
+            previous_color = RGB_to_YCoCg(previous_color);
+            previous_color = clip_towards_aabb_center(previous_color, s_mm, mean - variance, mean + variance);
+            previous_color = YCoCg_to_RGB(previous_color);
+        }
+        vec3 output = mix(previous_color, current_color, 0.1f / c.in.frame.upscale_ratio);
+        c.taa_output[cur][oidx] = pack_rgba16f(v4(output, original_color.w));
     });
 }
 
@@ -1372,6 +1651,10 @@ void post_process_node(Ctx& c) {  // PostProcessNode::run, post_process.rs:1140-
         }
     }
     pass_tone_mapping(c);
+    if (c.in.temporal_upscalers) {   // post_process.rs:1236-1277 (K11/K12); FSR1 blobs are out of scope
+        if (c.in.smaa_tu4x) { pass_smaa_tu4x(c); pass_smaa_tu4x_extrapolate(c); }
+        if (c.in.taa_jitter) pass_taa_jasmine(c);
+    }
 }
 
 int fail(Ctx* c, int code, const char* msg) { if (c) c->error = msg; return code; }
@@ -1401,7 +1684,9 @@ int hko_context_create(hko_context** out, uint32_t width, uint32_t height, int t
     for (int i = 0; i < 10; ++i) c->reservoir[i].assign(n, zr);
     for (int i = 0; i < 4; ++i) c->denoise_internal[i].assign(n, z2);
     c->denoise_internal_variance.assign(n, 0.0f);
-    c->tone_mapping_output.assign(n, z2);
+    for (int i = 0; i < 2; ++i) { c->tone_mapping_output[i].assign(n, z2); c->taa_output[i].assign(4 * n, z2); }
+    c->upscale_output.assign(4 * n, z2);
+    c->previous_position.assign(n, v4(0.0f)); c->previous_velocity_uv.assign(n, v4(0.0f));
     memset(&c->in, 0, sizeof(c->in));
     *out = c;
     return HK_OK;
@@ -1451,8 +1736,12 @@ int hko_set_noise(hko_context* c, const uint8_t* rgba) {
 static int begin(hko_context* c, const hk_frame_inputs* in) {
     if (!c || !in) return HK_ERR_INVALID_ARGUMENT;
     if (!c->scene_ready || !c->noise_ready) return fail(c, HK_ERR_NOT_READY, "scene or noise not uploaded");
-    if (in->frame.upscale_ratio != 1.0f) return fail(c, HK_ERR_UNSUPPORTED, "upscale_ratio != 1");
     c->in = *in;
+    // scaled_size = (ratio.recip() * size.as_vec2()).ceil() (light.rs:622-624)
+    const float scale = 1.0f / in->frame.upscale_ratio;
+    c->RW = (int)ceilf(scale * (float)c->W);
+    c->RH = (int)ceilf(scale * (float)c->H);
+    if (c->RW < 1 || c->RH < 1 || c->RW > c->W || c->RH > c->H) return fail(c, HK_ERR_INVALID_ARGUMENT, "upscale_ratio out of range");
     return HK_OK;
 }
 int hko_prepass_run(hko_context* c, const hk_frame_inputs* in) { int e = begin(c, in); if (e) return e; pass_prepass(*c); return HK_OK; }
@@ -1485,26 +1774,39 @@ int hko_run_pass(hko_context* c, const hk_frame_inputs* in, int pass, int arg) {
     return HK_OK;
 }
 static void* plane(hko_context* c, int which, size_t* bytes) {
-    size_t n = (size_t)c->W * c->H;
+    size_t n = (size_t)c->W * c->H;                   // deferred (full) size planes
+    const size_t nr = (size_t)c->RW * c->RH;          // render-size planes (row stride RW, so the first RW*RH entries)
+    const bool smaa = c->in.smaa_tu4x != 0;
     auto R = [&](void* p, size_t b) { *bytes = b * n; return p; };
+    auto RR = [&](void* p, size_t b, size_t count) { *bytes = b * count; return p; };
     switch (which) {
-        case HK_OUT_TONE_MAPPED: return R(c->tone_mapping_output.data(), 8);
+        case HK_OUT_TONE_MAPPED: return RR(c->tone_mapping_output[c->in.frame.number % 2u].data(), 8, nr);
+        case HK_OUT_UPSCALED: return RR(c->upscale_output.data(), 8, 4 * nr);
+        case HK_OUT_TAA: return RR(c->taa_output[c->in.frame.number % 2u].data(), 8, smaa ? 4 * nr : nr);
         case HK_OUT_RENDER_DIRECT: case HK_OUT_RENDER_EMISSIVE: case HK_OUT_RENDER_INDIRECT:
-            return R(c->render[which - HK_OUT_RENDER_DIRECT].data(), 8);
+            return RR(c->render[which - HK_OUT_RENDER_DIRECT].data(), 8, nr);
         case HK_OUT_VARIANCE_DIRECT: case HK_OUT_VARIANCE_EMISSIVE: case HK_OUT_VARIANCE_INDIRECT:
-            return R(c->variance[which - HK_OUT_VARIANCE_DIRECT].data(), 4);
+            return RR(c->variance[which - HK_OUT_VARIANCE_DIRECT].data(), 4, nr);
         case HK_OUT_ALBEDO: return R(c->albedo.data(), 8);
         case HK_OUT_DENOISED_DIRECT: case HK_OUT_DENOISED_EMISSIVE: case HK_OUT_DENOISED_INDIRECT:
-            return R(c->denoise_render[which - HK_OUT_DENOISED_DIRECT].data(), 8);
+            return RR(c->denoise_render[which - HK_OUT_DENOISED_DIRECT].data(), 8, nr);
         case HK_OUT_GBUFFER_POSITION: return R(c->position.data(), 16);
         case HK_OUT_GBUFFER_NORMAL: return R(c->normal.data(), 4);
         case HK_OUT_GBUFFER_DEPTH_GRADIENT: return R(c->depth_gradient.data(), 8);
         case HK_OUT_GBUFFER_INSTANCE_MATERIAL: return R(c->instance_material.data(), 8);
         case HK_OUT_GBUFFER_VELOCITY_UV: return R(c->velocity_uv.data(), 16);
         default:
-            if (which >= HK_OUT_RESERVOIR_0 && which < HK_OUT_RESERVOIR_0 + 10) return R(c->reservoir[which - HK_OUT_RESERVOIR_0].data(), 64);
+            if (which >= HK_OUT_RESERVOIR_0 && which < HK_OUT_RESERVOIR_0 + 10) return RR(c->reservoir[which - HK_OUT_RESERVOIR_0].data(), 64, nr);
     }
     return nullptr;
+}
+int hko_output_extent(hko_context* c, int which, uint32_t* width, uint32_t* height) {   // pixels of a read-back plane, last frame's settings
+    size_t b = 0;
+    if (!plane(c, which, &b)) return fail(c, HK_ERR_INVALID_ARGUMENT, "bad plane id");
+    const bool deferred = which == HK_OUT_ALBEDO || (which >= HK_OUT_GBUFFER_POSITION && which <= HK_OUT_GBUFFER_VELOCITY_UV);
+    const int k = (which == HK_OUT_UPSCALED || (which == HK_OUT_TAA && c->in.smaa_tu4x)) ? 2 : 1;
+    *width = (uint32_t)(deferred ? c->W : k * c->RW); *height = (uint32_t)(deferred ? c->H : k * c->RH);
+    return HK_OK;
 }
 int hko_readback(hko_context* c, int which, void* host, size_t bytes) {
     size_t b = 0; void* p = plane(c, which, &b);

@@ -44,6 +44,7 @@ def lib():
             "hko_post_process_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
             "hko_render_frame": (_I, [_P, C.POINTER(L.FrameInputs)]),
             "hko_run_pass": (_I, [_P, C.POINTER(L.FrameInputs), _I, _I]),
+            "hko_output_extent": (_I, [_P, _I, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
             "hko_readback": (_I, [_P, _I, _P, _SZ]),
             "hko_upload_state": (_I, [_P, _I, _P, _SZ]),
             "hko_trace_rays": (_I, [_P, _P, _SZ, _P]),
@@ -107,9 +108,11 @@ class Oracle:
     def readback(self, which):
         from bevy_hikari_b200.plugin import view_plane
         bpp, dt, comps = L.OUT_FORMATS[which]
-        raw = np.empty(self.width * self.height * bpp, np.uint8)
+        w, h = C.c_uint32(), C.c_uint32()
+        self._check(lib().hko_output_extent(self.ctx, which, C.byref(w), C.byref(h)))
+        raw = np.empty(w.value * h.value * bpp, np.uint8)
         self._check(lib().hko_readback(self.ctx, which, raw.ctypes.data, raw.size))
-        return view_plane(raw, which, self.height, self.width)
+        return view_plane(raw, which, h.value, w.value)
 
     def upload_state(self, which, array):
         a = np.ascontiguousarray(array)

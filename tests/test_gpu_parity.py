@@ -210,8 +210,9 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(_ffi.HikariError, match="not uploaded"):
         p.render_frame(b.inputs(1))          # scene missing -> HK_ERR_NOT_READY (reference: node silently skips)
     p.upload_scene(b.world)
-    bad = plugin.HikariSettings(upscale_ratio=2.0)
+    bad = b.inputs(1)
+    bad.frame.upscale_ratio = 0.5            # Upscale::ratio() clamps to [1, 2] (lib.rs:501-505); raw inputs outside are refused
     with pytest.raises(_ffi.HikariError, match="upscale_ratio"):
-        p.run_frame(bad, b.view, b.previous_view, b.lights)
+        p.render_frame(bad)
     p.run_frame(b.settings, b.view, b.previous_view, b.lights)
     assert p.frame_counter == 2              # frame_counter_system increments before extraction (view.rs:89-103)
