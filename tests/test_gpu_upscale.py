@@ -118,3 +118,27 @@ def test_tiles_reject_scaled_rendering():
     inp.frame.upscale_ratio = 2.5
     with pytest.raises(_ffi.HikariError, match="upscale_ratio"):
         b.device().render_frame(inp)
+
+
+def test_committed_fixtures_from_cuda():
+    """The CUDA path reproduces both committed fixtures (tests/golden/, written by tools/make_golden.py from the oracle)
+    byte for byte — the check that needs nothing but the repository on the GPU box."""
+    import os
+    from tests.conftest import ROOT
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cornell_48x48_cfg2_frames1-6.npz"))
+    b = Bench("cornell", 48, 48, config="cornell_1080p")
+    dev = b.device()
+    for f in range(1, 7):
+        dev.render_frame(b.inputs(f))
+    for name, which in (("tone_mapped", L.OUT_TONE_MAPPED), ("position", L.OUT_GBUFFER_POSITION), ("instance_material", L.OUT_GBUFFER_INSTANCE_MATERIAL),
+                        ("reservoir9", L.OUT_RESERVOIR_0 + 9), ("render_indirect", L.OUT_RENDER_INDIRECT)):
+        assert np.array_equal(np.ascontiguousarray(dev.readback(which)).view(np.uint8).reshape(-1), z[name]), name
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cornell_48x40_ratio1.5_smaa_taa_frames1-6.npz"))
+    b = Bench("cornell", 48, 40, config="cornell_1080p", taa=plugin.TAA_JASMINE, upscale_ratio=1.5)
+    dev = b.device()
+    for f in range(1, 7):
+        inp = b.moving_inputs(f)
+        inp.temporal_upscalers = 1
+        dev.render_frame(inp)
+    for name, which in (("tone_mapped", L.OUT_TONE_MAPPED), ("upscaled", L.OUT_UPSCALED), ("taa", L.OUT_TAA), ("reservoir9", L.OUT_RESERVOIR_0 + 9)):
+        assert np.array_equal(np.ascontiguousarray(dev.readback(which)).view(np.uint8).reshape(-1), z[name]), name
