@@ -356,6 +356,29 @@ def run_ours(args):
     e2e_ms = reduce_max(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
     e2e_value = light_rays / (e2e_ms * 1e-3) / 1e6
 
+    # ------------------------------------------------ animated scene: cost of the per-frame scene half (not in `value`)
+    # one instance moves -> previous_transform_system + prepare_instances on the host (TLAS, emissive BVH, alias tables;
+    # instance.rs:352-437) and hk_scene_update_instances (H2D of the instance-level buffers)
+    scene_update = None
+    if world_size == 1:
+        base = np.array(scene.inst_transform[len(scene.inst_transform) - 1], np.float32)
+        host_ms, upload_ms = [], []
+        for n in range(12):
+            moved = base.copy()
+            moved[12] += 0.001 * (n + 1)
+            t0 = time.perf_counter()
+            world.set_instance_transform(len(scene.inst_transform) - 1, moved)
+            world.previous_transform_system()
+            world.prepare_instances()
+            t1 = time.perf_counter()
+            dev.update_instances(world)
+            t2 = time.perf_counter()
+            host_ms.append((t1 - t0) * 1e3); upload_ms.append((t2 - t1) * 1e3)
+        d = world.scene_desc()
+        scene_update = {"host_rebuild_ms": round(float(np.median(host_ms[2:])), 4), "upload_ms": round(float(np.median(upload_ms[2:])), 4),
+                        "instances": int(d.instance_count), "tlas_nodes": int(d.instance_node_count), "alias_entries": int(d.alias_count),
+                        "note": "per-frame cost when instances move; outside the timed region of value / e2e (static benchmark scene)"}
+
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()
@@ -406,6 +429,8 @@ def run_ours(args):
                                "frac": round(frame_achieved / peak, 5)}},
         "clocks": clocks,
     }
+    if scene_update:
+        out["scene_update"] = scene_update
     if world_size == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(args.config, seconds_budget=25.0)
     print(json.dumps(out), flush=True)

@@ -36,6 +36,7 @@ SYMBOLS = {
     "hk_context_resize_tile": (_I, [_P, _U32, _U32, _U32, _U32, _U32, _U32]),
     "hk_reset_temporal_state": (_I, [_P]),
     "hk_scene_upload": (_I, [_P, C.POINTER(L.SceneDesc)]),
+    "hk_scene_update_instances": (_I, [_P, C.POINTER(L.SceneDesc)]),
     "hk_set_noise": (_I, [_P, _P]),
     "hk_prepass_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
     "hk_light_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
@@ -67,6 +68,10 @@ SYMBOLS = {
     "hikari_world_add_texture": (_U32, [_P, C.POINTER(L.TextureDesc)]),
     "hikari_world_add_instance": (_U32, [_P, _U32, _U32, _P, _U32]),
     "hikari_world_prepare": (None, [_P]),
+    "hikari_world_prepare_instances": (None, [_P]),
+    "hikari_world_set_instance_transform": (None, [_P, _U32, _P]),
+    "hikari_world_set_instance_visible": (None, [_P, _U32, _U32]),
+    "hikari_world_previous_transform_system": (None, [_P]),
     "hikari_world_scene_desc": (None, [_P, C.POINTER(L.SceneDesc)]),
     "hikari_world_mesh_error": (_I, [_P, _U32]),
     "hikari_plugin_create": (_P, []),
@@ -74,6 +79,7 @@ SYMBOLS = {
     "hikari_plugin_build": (_I, [_P, _I, _U32, _U32, _U32, _U32, _P, _P]),
     "hikari_plugin_build_tile": (_I, [_P, _I, _U32, _U32, _U32, _U32, _U32, _U32, _P, _P]),
     "hikari_plugin_upload_scene": (_I, [_P, _P]),
+    "hikari_plugin_update_instances": (_I, [_P, _P]),
     "hikari_plugin_run_frame": (_I, [_P, C.POINTER(Settings), C.POINTER(L.View), C.POINTER(L.PreviousView), C.POINTER(L.Lights)]),
     "hikari_plugin_context": (_P, [_P]),
     "hikari_plugin_frame_counter": (_U64, [_P]),

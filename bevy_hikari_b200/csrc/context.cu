@@ -28,7 +28,10 @@ struct hk_context {
     Band band{};
     size_t band_pixels = 0, owned_pixels = 0;
     std::vector<void*> allocations;        // per-pixel planes
-    std::vector<void*> scene_allocations;  // scene buffers
+    std::vector<void*> scene_allocations;  // scene buffers: meshes, BLAS nodes, materials, textures
+    struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[7];   // scene buffers rewritten by hk_scene_update_instances (grow-only)
+    bool mesh_boxes_match = false;         // BLAS half of DeviceScene::leaf_boxes_match
+    uint32_t scene_material_count = 0, scene_asset_node_count = 0, scene_primitive_count = 0;
     Planes planes{};
     DeviceScene scene{};
     bool scene_ready = false, noise_ready = false;
@@ -220,6 +223,7 @@ void hk_context_destroy(hk_context* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_list(ctx->allocations);
     free_list(ctx->scene_allocations);
+    for (auto& b : ctx->ibuf) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     if (ctx->noise) cudaFree(ctx->noise);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->spatial_tables) cudaFree(ctx->spatial_tables);
@@ -265,24 +269,41 @@ static cudaError_t upload(hk_context* ctx, const T** dst, const T* src, uint32_t
     return e;
 }
 
-extern "C" {
 
-int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
-    if (!ctx || !s) return HK_ERR_INVALID_ARGUMENT;
-    if ((s->vertex_count && !s->vertices) || (s->primitive_count && !s->primitives) || (s->instance_count && !s->instances) ||
-        (s->material_count && !s->materials) || (s->asset_node_count && !s->asset_nodes) ||
-        (s->instance_node_count && !s->instance_nodes) || (s->emissive_node_count && !s->emissive_nodes) ||
-        (s->emissive_count && !s->emissives) || (s->alias_count && !s->alias_table) || (s->texture_count && !s->textures))
+// copy into a grow-only device buffer (per-frame updates must not pay cudaMalloc/cudaFree)
+template <class T>
+static cudaError_t upload_into(hk_context* ctx, hk_context::DevBuf& b, const T** dst, const T* src, size_t count) {
+    const size_t bytes = count * sizeof(T), need = bytes + 64;   // +64: 16-byte vector loads at the tail stay in bounds
+    cudaError_t e = cudaSuccess;
+    if (b.cap < need) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr; b.cap = 0;
+        const size_t cap = need + need / 2;
+        e = cudaMalloc(&b.p, cap);
+        if (e != cudaSuccess) return e;
+        b.cap = cap;
+    }
+    if (bytes) e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(static_cast<char*>(b.p) + bytes, 0, 64, ctx->stream);
+    *dst = reinterpret_cast<const T*>(b.p);
+    return e;
+}
+
+// Validation + upload of the per-frame half of the scene (instances, TLAS, emissives, emissive BVH, alias tables,
+// previous model matrices) into `d`.  Frees the previous copies.
+static int upload_instances(hk_context* ctx, const hk_scene_desc* s, DeviceScene& d) {
+    if ((s->instance_count && !s->instances) || (s->instance_node_count && !s->instance_nodes) ||
+        (s->emissive_node_count && !s->emissive_nodes) || (s->emissive_count && !s->emissives) || (s->alias_count && !s->alias_table))
         return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "scene buffer pointer is NULL with a non-zero count");
     // validate indices once so that kernels can skip bounds checks
     for (uint32_t i = 0; i < s->instance_count; ++i) {
         const hk_instance& in = s->instances[i];
-        if (in.material >= s->material_count || (uint64_t)in.mesh.node_offset + in.mesh.node_count > s->asset_node_count)
+        if (in.material >= ctx->scene_material_count || (uint64_t)in.mesh.node_offset + in.mesh.node_count > ctx->scene_asset_node_count)
             return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "instance references a material / node range out of bounds");
     }
     // Does every leaf record sit right behind a navigator whose box is the shape's own AABB?  (true for bvh 0.7.1's
     // flatten_custom, which is what the reference uploads; then the kernels skip the re-derived leaf box test.)
-    bool boxes_match = true;
+    bool boxes_match = ctx->mesh_boxes_match;
     auto same3 = [](const float* a, const float* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; };
     for (uint32_t i = 1; i < s->instance_node_count && boxes_match; ++i) {
         const hk_node& leaf = s->instance_nodes[i];
@@ -292,9 +313,47 @@ int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
         boxes_match = nav.entry_index == i && id < s->instance_count && same3(nav.min, s->instances[id].min) &&
                       same3(nav.max, s->instances[id].max);
     }
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));   // frames in flight still read the buffers that are overwritten below
+    d.leaf_boxes_match = boxes_match ? 1u : 0u;
+    HK_CUDA(upload_into(ctx, ctx->ibuf[0], &d.alias_table, s->alias_table, s->alias_count));
+    HK_CUDA(upload_into(ctx, ctx->ibuf[1], &d.instances, s->instances, s->instance_count));
+    HK_CUDA(upload_into(ctx, ctx->ibuf[2], &d.instance_nodes, s->instance_nodes, s->instance_node_count));
+    HK_CUDA(upload_into(ctx, ctx->ibuf[3], &d.emissive_nodes, s->emissive_nodes, s->emissive_node_count));
+    HK_CUDA(upload_into(ctx, ctx->ibuf[4], &d.emissives, s->emissives, s->emissive_count));
+    d.instance_node_count = s->instance_node_count;
+    d.emissive_node_count = s->emissive_node_count;
+    d.previous_models = nullptr;
+    d.instance_moved = nullptr;
+    std::vector<uint32_t> moved;
+    if (s->previous_instance_models && s->instance_count) {
+        moved.resize(s->instance_count);
+        bool any = false;
+        for (uint32_t i = 0; i < s->instance_count; ++i) {
+            moved[i] = memcmp(s->previous_instance_models + 16 * (size_t)i, s->instances[i].model, 64) != 0 ? 1u : 0u;
+            any = any || moved[i];
+        }
+        if (any) {
+            HK_CUDA(upload_into(ctx, ctx->ibuf[5], &d.previous_models, reinterpret_cast<const float4*>(s->previous_instance_models), 4 * (size_t)s->instance_count));
+            HK_CUDA(upload_into(ctx, ctx->ibuf[6], &d.instance_moved, moved.data(), s->instance_count));
+        }
+    }
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));      // caller's arrays (and `moved`) may be freed after return
+    return HK_OK;
+}
+
+extern "C" {
+
+int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
+    if (!ctx || !s) return HK_ERR_INVALID_ARGUMENT;
+    if ((s->vertex_count && !s->vertices) || (s->primitive_count && !s->primitives) ||
+        (s->material_count && !s->materials) || (s->asset_node_count && !s->asset_nodes) || (s->texture_count && !s->textures))
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "scene buffer pointer is NULL with a non-zero count");
+    bool boxes_match = true;
+    auto same3 = [](const float* a, const float* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; };
     std::unordered_set<uint32_t> checked;   // mesh node ranges repeat across instances: check each once
-    for (uint32_t m = 0; m < s->instance_count && boxes_match; ++m) {
+    for (uint32_t m = 0; m < s->instance_count && boxes_match && s->instances; ++m) {
         const hk_mesh_index& mi = s->instances[m].mesh;
+        if ((uint64_t)mi.node_offset + mi.node_count > s->asset_node_count) break;   // reported by upload_instances
         if (!checked.insert(mi.node_offset).second) continue;
         for (uint32_t i = 1; i < mi.node_count && boxes_match; ++i) {
             const hk_node& leaf = s->asset_nodes[mi.node_offset + i];
@@ -315,19 +374,15 @@ int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
     free_list(ctx->scene_allocations);
     ctx->scene_ready = false;
+    ctx->mesh_boxes_match = boxes_match;
+    ctx->scene_material_count = s->material_count;
+    ctx->scene_asset_node_count = s->asset_node_count;
+    ctx->scene_primitive_count = s->primitive_count;
     DeviceScene d{};
-    d.leaf_boxes_match = boxes_match ? 1u : 0u;
     HK_CUDA(upload(ctx, &d.vertices, s->vertices, s->vertex_count));
     HK_CUDA(upload(ctx, &d.primitives, s->primitives, s->primitive_count));
     HK_CUDA(upload(ctx, &d.asset_nodes, s->asset_nodes, s->asset_node_count));
-    HK_CUDA(upload(ctx, &d.alias_table, s->alias_table, s->alias_count));
-    HK_CUDA(upload(ctx, &d.instances, s->instances, s->instance_count));
-    HK_CUDA(upload(ctx, &d.instance_nodes, s->instance_nodes, s->instance_node_count));
     HK_CUDA(upload(ctx, &d.materials, s->materials, s->material_count));
-    HK_CUDA(upload(ctx, &d.emissive_nodes, s->emissive_nodes, s->emissive_node_count));
-    HK_CUDA(upload(ctx, &d.emissives, s->emissives, s->emissive_count));
-    d.instance_node_count = s->instance_node_count;
-    d.emissive_node_count = s->emissive_node_count;
     d.texture_count = s->texture_count;
     d.textures = nullptr;
     if (s->texture_count) {
@@ -361,9 +416,24 @@ int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
         HK_CUDA(upload(ctx, &d.texture_info, info.data(), s->texture_count));
         HK_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging vectors die at scope exit
     }
-    HK_CUDA(cudaStreamSynchronize(ctx->stream));      // caller's arrays may be freed after return
+    int rc = upload_instances(ctx, s, d);
+    if (rc != HK_OK) return rc;
     ctx->scene = d;
     ctx->scene_ready = true;
+    return HK_OK;
+}
+
+int hk_scene_update_instances(hk_context* ctx, const hk_scene_desc* s) {
+    if (!ctx || !s) return HK_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene_ready) return set_error(ctx, HK_ERR_NOT_READY, "hk_scene_update_instances needs a scene from hk_scene_upload");
+    HK_CUDA(cudaSetDevice(ctx->device));
+    DeviceScene d = ctx->scene;
+    int rc = upload_instances(ctx, s, d);
+    if (rc != HK_OK) {   // validation fails before anything is freed; a CUDA failure may leave freed buffers behind
+        if (rc != HK_ERR_INVALID_ARGUMENT) ctx->scene_ready = false;
+        return rc;
+    }
+    ctx->scene = d;
     return HK_OK;
 }
 

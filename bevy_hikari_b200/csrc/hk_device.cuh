@@ -33,6 +33,10 @@ struct DeviceScene {
     const uint4* texture_info;             // per texture: (offset, width, height, flags: bit0-1 mode_u, 2-3 mode_v, 4 linear)
     uint32_t instance_node_count, emissive_node_count, texture_count;
     uint32_t leaf_boxes_match;   // 1 = every leaf's navigator box equals the shape's own AABB (validated at upload)
+    // previous-frame model matrices (4 float4 columns per instance) and a per-instance "moved" flag (previous != current,
+    // compared bitwise on the host); both nullptr when no instance moved
+    const float4* previous_models;
+    const uint32_t* instance_moved;
 };
 
 struct ReservoirPlanes {  // one PackedReservoir buffer as 4 planes

@@ -104,8 +104,18 @@ __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__
             float ty = dot(P0 - ry.origin, Ng) / dot(ry.direction, Ng);
             vec4 cy = mul(view_proj, v4(ry.origin + ry.direction * ty, 1.0f));
             vec2 grad = v2(cx.z / cx.w - depth, cy.z / cy.w - depth);
-            // velocity = clip_to_uv(view_proj * p) - clip_to_uv(previous_view_proj * p)   (static instances)
-            vec4 pclip = mul(load_mat4(P.in.previous_view.view_proj), v4(world_position, 1.0f));
+            // velocity = clip_to_uv(view_proj * world_position) - clip_to_uv(previous_view_proj * previous_world_position)
+            // (prepass.wgsl:52,99): previous_world_position = previous_mesh.model * local position for instances whose
+            // model matrix changed since the last frame, the world position itself otherwise
+            vec3 previous_world_position = world_position;
+            if (sc.instance_moved != nullptr && __ldg(&sc.instance_moved[hit.instance_index]) != 0u) {
+                const float4* pm = sc.previous_models + 4u * (size_t)hit.instance_index;
+                mat4 previous_model;
+                for (int c = 0; c < 4; ++c) previous_model.c[c] = f4v(ldg4(pm + c));
+                vec3 local_position = f4xyz(pa) + hit.u * (f4xyz(pb) - f4xyz(pa)) + hit.v * (f4xyz(pc) - f4xyz(pa));
+                previous_world_position = xyz(mul(previous_model, v4(local_position, 1.0f)));
+            }
+            vec4 pclip = mul(load_mat4(P.in.previous_view.view_proj), v4(previous_world_position, 1.0f));
             vec2 uva = v2(clip.x, clip.y) / clip.w; uva = (uva + 1.0f) * 0.5f; uva.y = 1.0f - uva.y;
             vec2 uvb = v2(pclip.x, pclip.y) / pclip.w; uvb = (uvb + 1.0f) * 0.5f; uvb.y = 1.0f - uvb.y;
             vec2 velocity = uva - uvb;

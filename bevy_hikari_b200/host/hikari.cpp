@@ -360,6 +360,20 @@ std::vector<hk_alias_entry> GpuMesh::build_alias_table(const float transform[16]
 uint32_t MeshMaterialWorld::add_mesh(const Mesh& mesh) { meshes_.push_back(mesh); return (uint32_t)meshes_.size() - 1; }
 uint32_t MeshMaterialWorld::add_material(const StandardMaterial& m) { materials_in_.push_back(m); return (uint32_t)materials_in_.size() - 1; }
 uint32_t MeshMaterialWorld::add_instance(const InstanceDesc& i) { instances_in_.push_back(i); return (uint32_t)instances_in_.size() - 1; }
+void MeshMaterialWorld::set_instance_transform(uint32_t instance, const float transform[16]) {
+    if (instance < instances_in_.size()) memcpy(instances_in_[instance].transform, transform, 64);
+}
+void MeshMaterialWorld::set_instance_visible(uint32_t instance, bool visible) {
+    if (instance < instances_in_.size()) instances_in_[instance].visible = visible;
+}
+void MeshMaterialWorld::previous_transform_system() {  // transform.rs:31-44
+    for (InstanceDesc& d : instances_in_) {
+        if (d.has_queue) memcpy(d.queue[1], d.queue[0], 64);
+        else memcpy(d.queue[1], d.transform, 64);
+        memcpy(d.queue[0], d.transform, 64);
+        d.has_queue = true;
+    }
+}
 uint32_t MeshMaterialWorld::add_texture(const hk_texture_desc& t, const uint8_t* pixels) {
     texture_pixels_.emplace_back(pixels, pixels + (size_t)t.width * t.height * 4);
     hk_texture_desc d = t;
@@ -412,11 +426,15 @@ void MeshMaterialWorld::prepare_material_assets() {  // material.rs:139-203
 void MeshMaterialWorld::prepare_instances() {  // instance.rs:245-444
     if (!universal_settings.build_instance_acceleration_structure) return;
     instances.clear(); emissives.clear(); alias_table.clear(); instance_nodes.clear(); emissive_nodes.clear();
+    previous_models.clear();
+    alias_table_cache_.resize(instances_in_.size());
     std::vector<const InstanceDesc*> kept;
     for (const InstanceDesc& d : instances_in_) {
         if (!d.visible) continue;                                              // instance.rs:357
         if (d.mesh >= meshes_.size() || !mesh_ok_[d.mesh] || d.material >= materials.size()) continue;  // instance.rs:275-283
         kept.push_back(&d);
+        const float* previous = d.has_queue ? d.queue[1] : d.transform;        // PreviousMeshUniform::transform = queue[1]
+        previous_models.insert(previous_models.end(), previous, previous + 16);
     }
     for (const InstanceDesc* d : kept) {
         const GpuMesh& g = gpu_meshes_[d->mesh];
@@ -461,7 +479,25 @@ void MeshMaterialWorld::prepare_instances() {  // instance.rs:245-444
         float intensity = 255.0f * e[3] * length3(e);
         if (intensity > 0.0f) {
             const GpuMesh& g = gpu_meshes_[kept[id]->mesh];
-            std::vector<hk_alias_entry> table = g.build_alias_table(inst.model);
+            // alias table cached per entity while the scale stays within 0.01 (instance.rs:385-397): a rotating or
+            // translating light keeps the table computed for the transform it was first seen with
+            float scale[3];
+            {   // glam Mat4::to_scale_rotation_translation().0 = (|x_axis| * signum(det), |y_axis|, |z_axis|)
+                const float* m = inst.model;
+                float det3 = m[0] * (m[5] * m[10] - m[6] * m[9]) - m[4] * (m[1] * m[10] - m[2] * m[9]) + m[8] * (m[1] * m[6] - m[2] * m[5]);
+                scale[0] = length3(m) * (det3 < 0.0f ? -1.0f : 1.0f);
+                scale[1] = length3(m + 4);
+                scale[2] = length3(m + 8);
+            }
+            CachedAliasTable& cache = alias_table_cache_[(size_t)(kept[id] - instances_in_.data())];
+            const bool cache_hit = cache.valid && fabsf(cache.scale[0] - scale[0]) <= 0.01f && fabsf(cache.scale[1] - scale[1]) <= 0.01f &&
+                                   fabsf(cache.scale[2] - scale[2]) <= 0.01f;
+            if (!cache_hit) {
+                cache.valid = true;
+                memcpy(cache.scale, scale, 12);
+                cache.table = g.build_alias_table(inst.model);
+            }
+            const std::vector<hk_alias_entry>& table = cache.table;
             hk_emissive em;
             memset(&em, 0, sizeof(em));
             em.alias_table_offset = (uint32_t)alias_table.size();
@@ -505,6 +541,7 @@ hk_scene_desc MeshMaterialWorld::scene_desc() const {
     auto* self = const_cast<MeshMaterialWorld*>(this);
     for (size_t i = 0; i < textures_.size(); ++i) self->textures_[i].rgba8 = texture_pixels_[i].data();
     d.textures = textures_.data(); d.texture_count = (uint32_t)textures_.size();
+    d.previous_instance_models = previous_models.size() == 16 * instances.size() && !instances.empty() ? previous_models.data() : nullptr;
     return d;
 }
 
@@ -530,6 +567,11 @@ int HikariPlugin::upload_scene(const MeshMaterialWorld& world) {
     if (!ctx_) return HK_ERR_NOT_READY;
     hk_scene_desc d = world.scene_desc();
     return hk_scene_upload(ctx_, &d);
+}
+int HikariPlugin::update_instances(const MeshMaterialWorld& world) {
+    if (!ctx_) return HK_ERR_NOT_READY;
+    hk_scene_desc d = world.scene_desc();
+    return hk_scene_update_instances(ctx_, &d);
 }
 int HikariPlugin::run_frame(const HikariSettings& settings, const ViewInputs& view) {
     if (!ctx_) return HK_ERR_NOT_READY;

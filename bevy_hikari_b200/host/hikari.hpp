@@ -117,6 +117,9 @@ struct InstanceDesc {                         // one (Entity, Handle<Mesh>, Hand
     uint32_t mesh = 0, material = 0;
     float transform[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     bool visible = true;
+    // GlobalTransformQueue([current, previous]) (transform.rs:19-20); absent until previous_transform_system has seen the entity
+    bool has_queue = false;
+    float queue[2][16] = {};
 };
 
 // Flattened skip-link BVH over boxes (bvh 0.7.1 BVH::build + flatten_custom(&GpuNode::pack); mod.rs:458-459).
@@ -136,6 +139,14 @@ public:
     void prepare_material_assets();                        // material.rs:139-203
     void prepare_instances();                              // instance.rs:245-444
     void prepare();                                        // the three, in RenderStage::Prepare order (mod.rs:42-55)
+    // Animated instances.  set_instance_transform changes an entity's GlobalTransform (a user system in Update);
+    // previous_transform_system is the PostUpdate system of transform.rs:31-44, run once per frame: every entity's queue
+    // becomes [current matrix, former queue[0]] ([m, m] the first time).  prepare_instances then rebuilds instances, TLAS,
+    // emissives and alias tables (instance.rs:352-437) and PreviousMeshUniform (instance.rs:111-128).
+    void set_instance_transform(uint32_t instance, const float transform[16]);
+    void set_instance_visible(uint32_t instance, bool visible);
+    void previous_transform_system();
+    std::vector<float> previous_models;                    // 16 floats per entry of `instances`, queue[1] (or the model itself)
     hk_scene_desc scene_desc() const;                      // views into the vectors below; valid until the next prepare()
     const std::vector<PrepareMeshError>& mesh_errors() const { return mesh_errors_; }
 
@@ -157,6 +168,8 @@ private:
     std::vector<hk_mesh_index> mesh_index_;
     std::vector<StandardMaterial> materials_in_;
     std::vector<InstanceDesc> instances_in_;
+    struct CachedAliasTable { bool valid = false; float scale[3] = {0, 0, 0}; std::vector<hk_alias_entry> table; };
+    std::vector<CachedAliasTable> alias_table_cache_;      // per entity: Local<HashMap<Entity, (Vec3, Vec<GpuAliasEntry>)>>, instance.rs:253,386-397
     std::vector<hk_texture_desc> textures_;
     std::vector<std::vector<uint8_t>> texture_pixels_;
 };
@@ -186,6 +199,8 @@ public:
     int build_tile(int cuda_device, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end, uint32_t row_begin,
                    uint32_t row_end, const uint8_t* noise_rgba8_64x64x16, void* cuda_stream);
     int upload_scene(const MeshMaterialWorld& world);
+    // instance-level buffers only (hk_scene_update_instances): what instance.rs:427-435 rewrites when instances change
+    int update_instances(const MeshMaterialWorld& world);
     // One frame of the camera's sub-graph: PREPASS -> LIGHT -> POST_PROCESS (lib.rs:258-365).  Increments the counter
     // first, as frame_counter_system does in PostUpdate (view.rs:89-103).
     int run_frame(const HikariSettings& settings, const ViewInputs& view);

@@ -99,6 +99,10 @@ uint32_t hikari_world_add_instance(hikari_world* w, uint32_t mesh, uint32_t mate
     return W(w)->add_instance(d);
 }
 void hikari_world_prepare(hikari_world* w) { W(w)->prepare(); }
+void hikari_world_prepare_instances(hikari_world* w) { W(w)->prepare_instances(); }
+void hikari_world_set_instance_transform(hikari_world* w, uint32_t instance, const float* transform16) { W(w)->set_instance_transform(instance, transform16); }
+void hikari_world_set_instance_visible(hikari_world* w, uint32_t instance, uint32_t visible) { W(w)->set_instance_visible(instance, visible != 0); }
+void hikari_world_previous_transform_system(hikari_world* w) { W(w)->previous_transform_system(); }
 void hikari_world_scene_desc(hikari_world* w, hk_scene_desc* out) { *out = W(w)->scene_desc(); }
 int hikari_world_mesh_error(hikari_world* w, uint32_t mesh) {
     const auto& e = W(w)->mesh_errors();
@@ -118,6 +122,7 @@ int hikari_plugin_build_tile(hikari_plugin* p, int cuda_device, uint32_t width, 
     return P(p)->build_tile(cuda_device, width, height, col_begin, col_end, row_begin, row_end, noise, cuda_stream);
 }
 int hikari_plugin_upload_scene(hikari_plugin* p, hikari_world* w) { return P(p)->upload_scene(*W(w)); }
+int hikari_plugin_update_instances(hikari_plugin* p, hikari_world* w) { return P(p)->update_instances(*W(w)); }
 int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk_view* view,
                             const hk_previous_view* previous_view, const hk_lights* lights) {
     ViewInputs v;

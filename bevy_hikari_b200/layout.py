@@ -86,7 +86,8 @@ class SceneDesc(C.Structure):
                 ("materials", C.c_void_p), ("material_count", C.c_uint32),
                 ("emissive_nodes", C.c_void_p), ("emissive_node_count", C.c_uint32),
                 ("emissives", C.c_void_p), ("emissive_count", C.c_uint32),
-                ("textures", C.c_void_p), ("texture_count", C.c_uint32)]
+                ("textures", C.c_void_p), ("texture_count", C.c_uint32),
+                ("previous_instance_models", C.c_void_p)]
 
 
 class FrameStats(C.Structure):

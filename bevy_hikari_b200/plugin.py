@@ -84,6 +84,26 @@ class World:
     def prepare(self):
         lib().hikari_world_prepare(self._w)
 
+    # animated instances (transform.rs:31-44, instance.rs:352-437)
+    def set_instance_transform(self, instance, transform16):
+        t = np.ascontiguousarray(transform16, np.float32).reshape(16)
+        lib().hikari_world_set_instance_transform(self._w, instance, t.ctypes.data)
+
+    def set_instance_visible(self, instance, visible):
+        lib().hikari_world_set_instance_visible(self._w, instance, 1 if visible else 0)
+
+    def previous_transform_system(self):
+        lib().hikari_world_previous_transform_system(self._w)
+
+    def prepare_instances(self):
+        lib().hikari_world_prepare_instances(self._w)
+
+    def previous_models(self):
+        d = self.scene_desc()
+        if not d.previous_instance_models or d.instance_count == 0:
+            return np.zeros((0, 16), np.float32)
+        return np.frombuffer(C.string_at(d.previous_instance_models, d.instance_count * 64), np.float32).reshape(-1, 16).copy()
+
     def mesh_error(self, mesh):
         return lib().hikari_world_mesh_error(self._w, mesh)
 
@@ -174,6 +194,12 @@ class HikariPlugin:
 
     def upload_scene_desc(self, desc):
         check(lib().hk_scene_upload(self.ctx, C.byref(desc)), self.ctx)
+
+    def update_instances(self, world):
+        check(lib().hikari_plugin_update_instances(self._p, world._w), self.ctx)
+
+    def update_instances_desc(self, desc):
+        check(lib().hk_scene_update_instances(self.ctx, C.byref(desc)), self.ctx)
 
     @property
     def frame_counter(self):

@@ -65,6 +65,10 @@ typedef struct hk_scene_desc {
     const hk_node* emissive_nodes;       uint32_t emissive_node_count;   /* Nodes.count (instance.rs:97) */
     const hk_emissive* emissives;        uint32_t emissive_count;
     const hk_texture_desc* textures;     uint32_t texture_count;         /* 0 => NO_TEXTURE variant (light.rs:141-143) */
+    /* PreviousMeshUniform::transform of every instance (instance.rs:111-128, bound as `previous_mesh` in prepass.wgsl:7-8):
+     * instance_count column-major mat4 (16 floats each), the model matrix of the previous frame.  NULL = nothing moved.
+     * Only feeds the motion vectors of the G-buffer (prepass.wgsl:52,99). */
+    const float* previous_instance_models;
 } hk_scene_desc;
 
 /* What bind group 0 carries each frame (src/prepass.rs:81-125, src/light.rs:630-639) + the settings that pick passes. */
@@ -159,6 +163,11 @@ int hk_context_resize_tile(hk_context* ctx, uint32_t width, uint32_t height, uin
 int hk_reset_temporal_state(hk_context* ctx);   /* zero reservoirs, as re-allocation does in light.rs:342-363 */
 
 int hk_scene_upload(hk_context* ctx, const hk_scene_desc* scene);
+/* The per-frame part of the scene, for animated instances: replaces instances, instance_nodes (TLAS), emissives,
+ * emissive_nodes, alias_table and previous_instance_models — what MeshMaterialRenderAssets / InstanceRenderAssets::set +
+ * write_buffer rewrite when an instance event fires (instance.rs:352-437) — and leaves meshes, BLAS nodes, materials and
+ * textures of the last hk_scene_upload in place.  Only those members of `scene` are read. */
+int hk_scene_update_instances(hk_context* ctx, const hk_scene_desc* scene);
 int hk_set_noise(hk_context* ctx, const uint8_t* rgba8_64x64x16);   /* 16 textures of 64x64 RGBA8, lib.rs:189-219 */
 
 int hk_prepass_run(hk_context* ctx, const hk_frame_inputs* in);

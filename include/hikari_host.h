@@ -52,6 +52,13 @@ uint32_t hikari_world_add_material(hikari_world* w, const hk_material* m);
 uint32_t hikari_world_add_texture(hikari_world* w, const hk_texture_desc* t);
 uint32_t hikari_world_add_instance(hikari_world* w, uint32_t mesh, uint32_t material, const float* transform16, uint32_t visible);
 void hikari_world_prepare(hikari_world* w);                               /* prepare_mesh_assets -> materials -> instances */
+/* animated instances: a user system moving an entity (Update), previous_transform_system (transform.rs:31-44, once per
+ * frame in PostUpdate), then prepare_instances (instance.rs:245-444) which rebuilds instances / TLAS / emissives / alias
+ * tables (cached per entity while the scale stays within 0.01, instance.rs:385-397) and PreviousMeshUniform */
+void hikari_world_set_instance_transform(hikari_world* w, uint32_t instance, const float* transform16);
+void hikari_world_set_instance_visible(hikari_world* w, uint32_t instance, uint32_t visible);
+void hikari_world_previous_transform_system(hikari_world* w);
+void hikari_world_prepare_instances(hikari_world* w);
 void hikari_world_scene_desc(hikari_world* w, hk_scene_desc* out);        /* pointers valid until the next prepare */
 int hikari_world_mesh_error(hikari_world* w, uint32_t mesh);              /* PrepareMeshError as int, 0 = ok */
 
@@ -62,6 +69,7 @@ int hikari_plugin_build(hikari_plugin* p, int cuda_device, uint32_t width, uint3
 int hikari_plugin_build_tile(hikari_plugin* p, int cuda_device, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
                              uint32_t row_begin, uint32_t row_end, const uint8_t* noise_rgba8_64x64x16, void* cuda_stream);
 int hikari_plugin_upload_scene(hikari_plugin* p, hikari_world* w);
+int hikari_plugin_update_instances(hikari_plugin* p, hikari_world* w);   /* hk_scene_update_instances: instance-level buffers only */
 int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk_view* view,
                             const hk_previous_view* previous_view, const hk_lights* lights);
 hk_context* hikari_plugin_context(hikari_plugin* p);

@@ -81,6 +81,7 @@ struct hko_context {
     std::vector<hk_node> asset_nodes;
     std::vector<hk_alias_entry> alias_table;
     std::vector<hk_instance> instances;
+    std::vector<float> previous_models;     // instance_count x 16, empty = no instance moved (prepass.wgsl:7-8 previous_mesh)
     std::vector<hk_node> instance_nodes;
     std::vector<hk_material> materials;
     std::vector<hk_node> emissive_nodes;
@@ -768,7 +769,18 @@ void pass_prepass(Ctx& c) {
             return cl.z / cl.w;
         };
         vec2 grad = v2(plane_depth((float)x + 1.0f, (float)y) - depth, plane_depth((float)x, (float)y + 1.0f) - depth);
-        vec2 velocity = clip_to_uv(clip) - clip_to_uv(mul(prev_view_proj, v4(world_position, 1.0f)));
+        // prepass.wgsl:52,99: previous_world_position = previous_mesh.model * vertex position, interpolated.  Here: the model
+        // of the previous frame applied to the hit's object-space point when the instance moved, else the hit point itself.
+        vec3 previous_world_position = world_position;
+        if (!c.previous_models.empty()) {
+            const float* pm = &c.previous_models[16 * (size_t)hit.instance_index];
+            if (memcmp(pm, inst.model, 64) != 0) {
+                vec3 p0 = ld3(prim.vertices[0].position), p1 = ld3(prim.vertices[1].position), p2 = ld3(prim.vertices[2].position);
+                vec3 local_position = p0 + u * (p1 - p0) + v * (p2 - p0);
+                previous_world_position = xyz(mul(ldm(pm), v4(local_position, 1.0f)));
+            }
+        }
+        vec2 velocity = clip_to_uv(clip) - clip_to_uv(mul(prev_view_proj, v4(previous_world_position, 1.0f)));
         c.position[idx] = v4(world_position, depth);
         c.normal[idx] = pack4x8snorm(v4(world_normal, 1.0f));
         c.depth_gradient[idx] = grad;
@@ -1697,17 +1709,24 @@ int hko_reset_temporal_state(hko_context* c) {
     for (int i = 0; i < 10; ++i) std::fill(c->reservoir[i].begin(), c->reservoir[i].end(), zr);
     return HK_OK;
 }
+int hko_scene_update_instances(hko_context* c, const hk_scene_desc* s) {   // instance.rs:427-435 (set + write_buffer)
+    if (!c || !s) return HK_ERR_INVALID_ARGUMENT;
+    assign(c->alias_table, s->alias_table, s->alias_count);
+    assign(c->instances, s->instances, s->instance_count);
+    assign(c->instance_nodes, s->instance_nodes, s->instance_node_count);
+    assign(c->emissive_nodes, s->emissive_nodes, s->emissive_node_count);
+    assign(c->emissives, s->emissives, s->emissive_count);
+    c->previous_models.clear();
+    if (s->previous_instance_models) c->previous_models.assign(s->previous_instance_models, s->previous_instance_models + 16 * (size_t)s->instance_count);
+    return HK_OK;
+}
 int hko_scene_upload(hko_context* c, const hk_scene_desc* s) {
     if (!c || !s) return HK_ERR_INVALID_ARGUMENT;
     assign(c->vertices, s->vertices, s->vertex_count);
     assign(c->primitives, s->primitives, s->primitive_count);
     assign(c->asset_nodes, s->asset_nodes, s->asset_node_count);
-    assign(c->alias_table, s->alias_table, s->alias_count);
-    assign(c->instances, s->instances, s->instance_count);
-    assign(c->instance_nodes, s->instance_nodes, s->instance_node_count);
     assign(c->materials, s->materials, s->material_count);
-    assign(c->emissive_nodes, s->emissive_nodes, s->emissive_node_count);
-    assign(c->emissives, s->emissives, s->emissive_count);
+    hko_scene_update_instances(c, s);
     c->textures.clear();
     float srgb_lut[256], lin_lut[256];
     for (int i = 0; i < 256; ++i) {

@@ -38,6 +38,7 @@ def lib():
             "hko_context_destroy": (None, [_P]),
             "hko_reset_temporal_state": (_I, [_P]),
             "hko_scene_upload": (_I, [_P, C.POINTER(L.SceneDesc)]),
+            "hko_scene_update_instances": (_I, [_P, C.POINTER(L.SceneDesc)]),
             "hko_set_noise": (_I, [_P, _P]),
             "hko_prepass_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
             "hko_light_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
@@ -98,6 +99,7 @@ class Oracle:
             raise RuntimeError(f"oracle error {rc}: {lib().hko_last_error(self.ctx).decode()}")
 
     def upload_scene_desc(self, desc): self._check(lib().hko_scene_upload(self.ctx, C.byref(desc)))
+    def update_instances_desc(self, desc): self._check(lib().hko_scene_update_instances(self.ctx, C.byref(desc)))
     def reset_temporal_state(self): self._check(lib().hko_reset_temporal_state(self.ctx))
     def prepass(self, inputs): self._check(lib().hko_prepass_run(self.ctx, C.byref(inputs)))
     def light(self, inputs): self._check(lib().hko_light_run(self.ctx, C.byref(inputs)))

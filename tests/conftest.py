@@ -83,3 +83,45 @@ class Bench:
 @pytest.fixture(scope="session")
 def cornell64():
     return Bench("cornell", 64, 64, config="cornell_256")
+
+
+def rotation_y_about(angle, center, translate=(0.0, 0.0, 0.0)):
+    """Column-major mat4 (16 floats): rotate by `angle` about the vertical axis through `center`, then translate."""
+    c, s = np.float32(np.cos(angle)), np.float32(np.sin(angle))
+    r = np.array([[c, 0, -s, 0], [0, 1, 0, 0], [s, 0, c, 0], [0, 0, 0, 1]], np.float64)   # rows = columns of the matrix
+    cx = np.array(center, np.float64)
+    t = cx - cx @ r[:3, :3] + np.array(translate, np.float64)
+    r[3, :3] = t
+    return r.astype(np.float32).reshape(16)
+
+
+class Animation:
+    """A user system moving entities every frame + the per-frame part of MeshMaterialPlugin (transform.rs:31-44,
+    instance.rs:352-437) on a Bench's world.  `tracks` maps instance id -> f(frame) -> world-space mat4 applied on top
+    of the instance's original transform."""
+
+    def __init__(self, bench, tracks):
+        from bevy_hikari_b200 import scenes
+        self.bench, self.tracks = bench, tracks
+        self.compose = scenes._compose
+        self.base = {i: np.array(bench.scene.inst_transform[i], np.float32) for i in tracks}
+
+    def step(self, frame):
+        w = self.bench.world
+        for i, f in self.tracks.items():
+            w.set_instance_transform(i, self.compose(f(frame), self.base[i]))
+        w.previous_transform_system()
+        w.prepare_instances()
+        return w
+
+
+def cornell_animation(bench):
+    """the short box spins and drifts, the ceiling light slides"""
+    return Animation(bench, {6: lambda f: rotation_y_about(0.06 * f, (0.33, 0.3, -0.37), (0.01 * f, 0.0, 0.0)),
+                             4: lambda f: rotation_y_about(0.0, (0, 0, 0), (0.03 * np.sin(0.7 * f), 0.0, 0.02 * f))})
+
+
+def city_animation(bench):
+    """the emissive earth sphere rotates and bobs (the reference's animated light), one house part slides"""
+    return Animation(bench, {1: lambda f: rotation_y_about(0.1 * f, (0.0, 1.0, 0.0), (0.0, 0.05 * np.sin(0.5 * f), 0.0)),
+                             2: lambda f: rotation_y_about(0.0, (0, 0, 0), (0.02 * f, 0.0, 0.0))})
