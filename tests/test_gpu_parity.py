@@ -215,4 +215,4 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(_ffi.HikariError, match="upscale_ratio"):
         p.render_frame(bad)
     p.run_frame(b.settings, b.view, b.previous_view, b.lights)
-    assert p.frame_counter == 2              # frame_counter_system increments before extraction (view.rs:89-103)
+    assert p.frame_counter == 1              # frame_counter_system increments before extraction (view.rs:89-103)
