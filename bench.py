@@ -17,7 +17,9 @@ value      Mrays/s, device-resident: rays = traverse_top calls + stand-alone tra
            (SURVEY.md 8(d)), counted exactly by replaying the same frames with the counting kernel variants AFTER the timed
            region (counters are compiled out of the timed kernels); primary (G-buffer) rays are reported separately.
 e2e        same metric through the public plugin API with host buffers: HikariPlugin.run_frame(settings, view, lights)
-           (host structs -> kernel parameters) + read-back of the tone-mapped band into pinned host memory every frame.
+           (host structs -> kernel parameters) + read-back of the tone-mapped tile into pinned host memory every frame,
+           pipelined like a presentation loop: hk_readback_async copies frame n on the context's copy stream while frame
+           n + 1 renders; the host waits for (and so observes) every frame's image, the last one inside the timed region.
 roofline   dominant kernel (largest share of the frame): algorithmic bytes/pixel x pixels / its mean
            CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline / --impl reference: the oracle (CPU restatement of the reference's WGSL; the reference itself is Rust + wgpu
@@ -342,15 +344,23 @@ def run_ours(args):
     dev.reset_temporal_state()
     dev.frame_counter = 0
     h2d = ctypes.sizeof(L.FrameInputs)
+    # Presentation-loop form: frame n's tile is copied to pinned host memory on the context's copy stream while frame
+    # n + 1 renders (hk_readback_async); the host sees every frame's result, one frame later.  Two pinned buffers alternate.
+    pinned2 = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host_bufs = [pinned.data_ptr(), pinned2.data_ptr()]
     for n in range(W_):
         dev.run_frame(settings, view, pview, lights)
-        dev.readback_into(L.OUT_TONE_MAPPED, pinned.data_ptr(), nbytes)
+        dev.readback_wait()
+        dev.readback_async(L.OUT_TONE_MAPPED, host_bufs[n & 1], nbytes)
+    dev.readback_wait()
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
     for n in range(K):
         dev.run_frame(settings, view, pview, lights)                      # host structs -> kernel parameters
-        dev.readback_into(L.OUT_TONE_MAPPED, pinned.data_ptr(), nbytes)   # D2H of the band into pinned memory (syncs)
+        dev.readback_wait()                                               # frame n - 1 has landed in host memory
+        dev.readback_async(L.OUT_TONE_MAPPED, host_bufs[n & 1], nbytes)   # D2H of this frame's tile, overlapping the next frame
+    dev.readback_wait()                                                   # the last frame's result too
     e1.record(stream)
     barrier()
     e2e_ms = reduce_max(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))

@@ -45,6 +45,8 @@ SYMBOLS = {
     "hk_get_output": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_SZ)]),
     "hk_output_extent": (_I, [_P, _I, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "hk_readback": (_I, [_P, _I, _P, _SZ]),
+    "hk_readback_async": (_I, [_P, _I, _P, _SZ]),
+    "hk_readback_wait": (_I, [_P]),
     "hk_upload_state": (_I, [_P, _I, _P, _SZ]),
     "hk_sync": (_I, [_P]),
     "hk_trace_rays": (_I, [_P, _P, _SZ, _P]),

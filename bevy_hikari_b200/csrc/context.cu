@@ -42,6 +42,11 @@ struct hk_context {
     Counters* counters = nullptr;
     SpatialTable* spatial_tables = nullptr;
     bool count_rays = false, time_passes = false, keep_intermediates = false;
+    // pipelined read-back (hk_readback_async): copy stream + "frame submitted" / "copy landed" events
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_submitted = nullptr, ev_copied = nullptr;
+    bool copy_in_flight = false;      // a copy has been queued and the compute stream has not yet been ordered behind it
+    bool copy_unwaited = false;       // ... and the host has not waited for it
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[HK_K_COUNT][2] = {};   // per-kernel begin/end
     bool kran[HK_K_COUNT] = {};
@@ -221,6 +226,9 @@ void hk_context_destroy(hk_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_submitted) cudaEventDestroy(ctx->ev_submitted);
+    if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     free_list(ctx->allocations);
     free_list(ctx->scene_allocations);
     for (auto& b : ctx->ibuf) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
@@ -242,6 +250,8 @@ int hk_context_resize_tile(hk_context* ctx, uint32_t width, uint32_t height, uin
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;
     HK_CUDA(cudaSetDevice(ctx->device));
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) HK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copy_in_flight = ctx->copy_unwaited = false;
     return allocate_planes(ctx, width, height, col_begin, col_end, row_begin, row_end);  // zeroed planes (light.rs:342-363)
 }
 
@@ -550,6 +560,12 @@ static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, li
     if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); hk_launch_spatial(P, false, ctx->stream); }
     return check_launch(ctx);
 }
+// the kernels below overwrite the final images: a pipelined read-back of the previous frame must have left them first
+static void order_behind_copy(hk_context* ctx) {
+    if (!ctx->copy_in_flight) return;
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0);
+    ctx->copy_in_flight = false;
+}
 static int run_post(hk_context* ctx, KParams& P, bool fuse) {  // PostProcessNode::run, post_process.rs:1190-1234
     if (P.in.denoise) {
         const int signals = (P.in.frame.indirect_bounces == 0) ? 2 : 3;  // post_process.rs:949-954
@@ -557,11 +573,13 @@ static int run_post(hk_context* ctx, KParams& P, bool fuse) {  // PostProcessNod
         { rows(ctx, P, GHOST_L0); KernelTimer t(ctx, HK_K_DENOISE_0); hk_launch_denoise_level(P, 0, signals, false, false, ctx->stream); }
         { rows(ctx, P, GHOST_L1); KernelTimer t(ctx, HK_K_DENOISE_1); hk_launch_denoise_level(P, 1, signals, false, false, ctx->stream); }
         { rows(ctx, P, GHOST_L2); KernelTimer t(ctx, HK_K_DENOISE_2); hk_launch_denoise_level(P, 2, signals, false, false, ctx->stream); }
+        if (fuse) order_behind_copy(ctx);
         { rows(ctx, P, 0); KernelTimer t(ctx, HK_K_DENOISE_3);
           hk_launch_denoise_level(P, 3, signals, fuse, !fuse || ctx->keep_intermediates, ctx->stream); }
-        if (!fuse) { KernelTimer t(ctx, HK_K_TONE_MAPPING); hk_launch_tone_mapping(P, ctx->stream); }
+        if (!fuse) { order_behind_copy(ctx); KernelTimer t(ctx, HK_K_TONE_MAPPING); hk_launch_tone_mapping(P, ctx->stream); }
     } else {
         rows(ctx, P, 0);
+        order_behind_copy(ctx);
         KernelTimer t(ctx, HK_K_TONE_MAPPING);
         hk_launch_tone_mapping(P, ctx->stream);
     }
@@ -613,6 +631,7 @@ int hk_sync(hk_context* ctx) {
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;
     HK_CUDA(cudaSetDevice(ctx->device));
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_unwaited) { HK_CUDA(cudaEventSynchronize(ctx->ev_copied)); ctx->copy_unwaited = false; }
     return HK_OK;
 }
 
@@ -780,6 +799,36 @@ static int transfer(hk_context* ctx, int which, void* host, size_t bytes, bool t
     return HK_OK;
 }
 int hk_readback(hk_context* ctx, int which, void* host, size_t bytes) { return transfer(ctx, which, host, bytes, true); }
+
+int hk_readback_async(hk_context* ctx, int which, void* pinned_host, size_t bytes) {
+    if (!ctx || !pinned_host) return HK_ERR_INVALID_ARGUMENT;
+    PlaneView v;
+    if ((which != HK_OUT_TONE_MAPPED && which != HK_OUT_UPSCALED && which != HK_OUT_TAA) || !plane_view(ctx, which, &v))
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "hk_readback_async serves the final images (tone-mapped, upscaled, TAA)");
+    if (bytes != v.w * v.h * v.bpp) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
+    HK_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        HK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        HK_CUDA(cudaEventCreateWithFlags(&ctx->ev_submitted, cudaEventDisableTiming));
+        HK_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+    }
+    if (ctx->copy_unwaited) HK_CUDA(cudaEventSynchronize(ctx->ev_copied));   // one copy in flight: the previous one must have landed
+    HK_CUDA(cudaEventRecord(ctx->ev_submitted, ctx->stream));
+    HK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_submitted, 0));
+    HK_CUDA(cudaMemcpy2DAsync(pinned_host, v.w * v.bpp, v.ptr, v.pitch * v.bpp, v.w * v.bpp, v.h, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    HK_CUDA(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    ctx->copy_in_flight = true;
+    ctx->copy_unwaited = true;
+    return HK_OK;
+}
+int hk_readback_wait(hk_context* ctx) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    if (!ctx->copy_unwaited) return HK_OK;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    HK_CUDA(cudaEventSynchronize(ctx->ev_copied));
+    ctx->copy_unwaited = false;
+    return HK_OK;
+}
 int hk_upload_state(hk_context* ctx, int which, const void* host, size_t bytes) {
     return transfer(ctx, which, const_cast<void*>(host), bytes, false);
 }

@@ -524,8 +524,10 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
         sincos_(ang, &sn, &cs);
         vec2 offset = rad * v2(cs, sn);
         int sx = f32_to_i32(offset.x + (float)x), sy = f32_to_i32(offset.y + (float)y);
-        vec2 sample_uv = (v2((float)sx, (float)sy) + 0.5f) / size_f;
-        if (sample_uv.x < 0.0f || sample_uv.y < 0.0f || sample_uv.x > 1.0f || sample_uv.y > 1.0f) continue;
+        // light.wgsl:1577-1580 tests sample_uv = (coords + 0.5) / size against [0, 1].  For integer coords and size < 2^22
+        // the correctly rounded quotient is < 0 iff coords < 0 and > 1 iff coords >= size ((size - 0.5) / size < 1 and
+        // (size + 0.5) / size >= 1 + 2^-23 survive rounding), so the two IEEE divisions per neighbour are not needed.
+        if (sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH) continue;
         const size_t sidx = render_index(P.band, sx, sy);
         const float sample_depth = P.planes.pos_depth[light_gbuffer_index(P, sx, sy, sidx)].w;
         float depth_ratio = depth / sample_depth;

@@ -248,6 +248,12 @@ class HikariPlugin:
     def readback_into(self, which, host_ptr, nbytes):
         check(lib().hk_readback(self.ctx, which, host_ptr, nbytes), self.ctx)
 
+    def readback_async(self, which, pinned_host_ptr, nbytes):
+        check(lib().hk_readback_async(self.ctx, which, pinned_host_ptr, nbytes), self.ctx)
+
+    def readback_wait(self):
+        check(lib().hk_readback_wait(self.ctx), self.ctx)
+
     def upload_state(self, which, array):
         a = np.ascontiguousarray(array)
         check(lib().hk_upload_state(self.ctx, which, a.ctypes.data, a.nbytes), self.ctx)

@@ -170,7 +170,39 @@ def city():
                      sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 4.0, math.pi / 4.0, 0.0)))
 
 
-SCENE_BUILDERS = {"cornell": cornell, "city": city}
+def terrain(n=224, seed=7):
+    """Stress scene, not a reference example: one n x n-quad displaced grid (2 n^2 triangles — 100 352 at n = 224, the size
+    class of the reference's scene.gltf) under a small emissive sphere and the sun; exercises a deep
+    BLAS (3 * 100 352 - 2 records) in the host builder and in traversal."""
+    rng = np.random.default_rng(seed)
+    g = np.linspace(-6.0, 6.0, n + 1, dtype=np.float64)
+    x, z = np.meshgrid(g, g, indexing="xy")
+    y = 0.35 * np.sin(1.3 * x) * np.cos(0.9 * z) + 0.15 * np.sin(3.1 * x + 1.0) + 0.03 * rng.standard_normal(x.shape)
+    pos = np.stack([x, y, z], axis=2).reshape(-1, 3).astype(F)
+    gy, gx = np.gradient(y, g, g)                      # d/dz (rows), d/dx (cols)
+    nrm = np.stack([-gx, np.ones_like(y), -gy], axis=2)
+    nrm = (nrm / np.linalg.norm(nrm, axis=2, keepdims=True)).reshape(-1, 3).astype(F)
+    uv = np.stack([(x + 6.0) / 12.0, (z + 6.0) / 12.0], axis=2).reshape(-1, 2).astype(F)
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    a = (j * (n + 1) + i).reshape(-1); b = a + 1; c = a + (n + 1); d = c + 1
+    idx = np.stack([a, c, b, b, c, d], axis=1).reshape(-1).astype(np.uint32)
+
+    def std_material(base, emissive=(0, 0, 0, 1), rough=0.6):
+        m = np.zeros((), L.MATERIAL)
+        m["base_color"], m["emissive"] = base, emissive
+        m["perceptual_roughness"], m["metallic"], m["reflectance"] = rough, 0.01, 0.5
+        for k in ("base_color_texture", "emissive_texture", "metallic_roughness_texture", "normal_map_texture", "occlusion_texture"):
+            m[k] = 0xFFFFFFFF
+        return m
+
+    meshes = [(pos, nrm, uv, idx), _uv_sphere_mesh(0.5, 24, 12)]
+    mats = np.array([std_material((0.55, 0.7, 0.45, 1.0)), std_material((1, 1, 1, 1), emissive=(1.0, 0.8, 0.5, 0.6))], L.MATERIAL)
+    return SceneData(meshes, mats, [], [0, 1], [0, 1], [_translation(0, 0, 0), _translation(0.5, 1.6, 0.0)],
+                     eye=(0.0, 3.0, 9.0), target=(0.0, 0.0, 0.0), sun_illuminance=8000.0,
+                     sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 3.0, math.pi / 5.0, 0.0)))
+
+
+SCENE_BUILDERS = {"cornell": cornell, "city": city, "terrain": terrain}
 
 # BASELINE.json configs (SURVEY.md 8(d)).  All run with Upscale::SmaaTu4x{ratio 1.0}, Taa::None so that the render
 # resolution equals the stated resolution.

@@ -182,6 +182,13 @@ int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes);
  * (light.rs:622-624); HK_OUT_UPSCALED (and HK_OUT_TAA after smaa_tu4x) = twice the render size (post_process.rs:718-731). */
 int hk_output_extent(hk_context* ctx, int which, uint32_t* width, uint32_t* height);
 int hk_readback(hk_context* ctx, int which, void* host, size_t bytes);            /* synchronises */
+/* Pipelined read-back of a final image (HK_OUT_TONE_MAPPED / HK_OUT_UPSCALED / HK_OUT_TAA) for a presentation loop: the
+ * copy into `pinned_host` (page-locked memory) is queued on an internal copy stream behind all work submitted so far and
+ * the call returns at once.  The next frame can be submitted immediately — on the device, its first write to a final
+ * image waits for the copy.  hk_readback_wait blocks the host until the last queued copy has landed.  One copy may be
+ * in flight per context. */
+int hk_readback_async(hk_context* ctx, int which, void* pinned_host, size_t bytes);
+int hk_readback_wait(hk_context* ctx);
 int hk_upload_state(hk_context* ctx, int which, const void* host, size_t bytes);  /* inverse of hk_readback (tests) */
 int hk_sync(hk_context* ctx);
 

@@ -216,3 +216,22 @@ def test_errors_are_reported_not_fatal():
         p.render_frame(bad)
     p.run_frame(b.settings, b.view, b.previous_view, b.lights)
     assert p.frame_counter == 1              # frame_counter_system increments before extraction (view.rs:89-103)
+
+
+def test_large_mesh_bit_exact():
+    """100 352-triangle BLAS (302 k records — the size class of the reference's scene.gltf): host builder, upload and deep
+    traversal, static then moving camera."""
+    b = Bench("terrain", 128, 80, config="city_4k")
+    assert b.world.scene_desc().primitive_count > 100000
+    dev, orc = b.device(), b.oracle()
+    dev.set_keep_intermediates(True)
+    for f in range(1, 7):
+        inp = b.inputs(f) if f < 4 else b.moving_inputs(f)
+        dev.render_frame(inp)
+        orc.render_frame(inp)
+        compare_all(dev, orc, ALL_PLANES + DENOISED, f)
+    rays = random_rays(4096, 5)
+    rays["origin"] = rays["origin"] * np.float32(3.0) + np.array([0, 1.0, 0], np.float32)
+    hd, ho = dev.trace_rays(rays), orc.trace_rays(rays)
+    assert hd.tobytes() == ho.tobytes()
+    assert (hd["instance_index"] != 0xFFFFFFFF).mean() > 0.3

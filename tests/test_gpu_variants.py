@@ -134,3 +134,30 @@ def test_scene_upload_rejects_out_of_range_references():
     assert _ffi.lib().hk_readback(dev.ctx, L.OUT_TONE_MAPPED, bad_size.ctypes.data, bad_size.size) == _ffi.HK_ERR_INVALID_ARGUMENT
     assert _ffi.lib().hk_readback(dev.ctx, 999, bad_size.ctypes.data, bad_size.size) == _ffi.HK_ERR_INVALID_ARGUMENT
     assert _ffi.lib().hk_render_frame(dev.ctx, None) == _ffi.HK_ERR_INVALID_ARGUMENT
+
+
+def test_pipelined_readback_equals_blocking():
+    """hk_readback_async / hk_readback_wait: frame n's image lands in pinned host memory while frame n + 1 renders, and is
+    byte-identical to the blocking read-back of the same frame; the next frame's tone-map write waits for the copy."""
+    import torch
+    b = Bench("cornell", 160, 96, config="cornell_1080p")
+    a, c = b.device(), b.device()
+    nbytes = 160 * 96 * 8
+    bufs = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    expected = []
+    for f in range(1, 8):
+        inp = b.inputs(f)
+        c.render_frame(inp)
+        expected.append(np.ascontiguousarray(c.readback(L.OUT_TONE_MAPPED)).view(np.uint8).reshape(-1).copy())
+        a.render_frame(inp)
+        a.readback_wait()                                   # frame f - 1 is complete on the host ...
+        if f > 1:
+            assert np.array_equal(bufs[f & 1].numpy(), expected[f - 2]), f - 1
+        a.readback_async(L.OUT_TONE_MAPPED, bufs[(f + 1) & 1].data_ptr(), nbytes)   # ... while frame f is being copied
+    a.readback_wait()
+    assert np.array_equal(bufs[(7 + 1) & 1].numpy(), expected[6])
+    from bevy_hikari_b200 import _ffi
+    with pytest.raises(_ffi.HikariError, match="final images"):
+        a.readback_async(L.OUT_ALBEDO, bufs[0].data_ptr(), nbytes)
+    with pytest.raises(_ffi.HikariError, match="size mismatch"):
+        a.readback_async(L.OUT_TONE_MAPPED, bufs[0].data_ptr(), nbytes - 8)

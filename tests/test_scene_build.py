@@ -141,3 +141,29 @@ def test_city_scene_builds_and_matches_oracle_builder():
     assert len(pb["instances"]) == 54 and len(pb["instance_nodes"]) == 3 * 54 - 2
     assert len(pb["primitives"]) == 19136
     assert len(pb["emissives"]) == 1
+
+
+def test_large_mesh_builder_invariants():
+    """bvh 0.7.1 restatement on 100 352 triangles: record count 3N - 2, every leaf reachable exactly once, navigator boxes
+    contain their subtrees (checked on a sample), build time bounded."""
+    import time
+    from bevy_hikari_b200 import scenes
+    t0 = time.time()
+    w = scenes.terrain().populate(plugin.World())
+    assert time.time() - t0 < 20.0
+    bufs = w.buffers()
+    inst = bufs["instances"][0]
+    n_tris = 2 * 224 * 224
+    nodes = bufs["asset_nodes"][inst["mesh"]["node_offset"]:inst["mesh"]["node_offset"] + inst["mesh"]["node_count"]]
+    assert len(nodes) == 3 * n_tris - 2
+    leaves = walk_all_leaves(nodes)
+    assert sorted(leaves) == list(range(n_tris))
+    prim = bufs["primitives"]["vertices"]["position"][inst["mesh"]["primitive"]:inst["mesh"]["primitive"] + n_tris]
+    mn, mx = prim.min(axis=1), prim.max(axis=1)
+    rng = np.random.default_rng(0)
+    nav = np.flatnonzero(nodes["entry_index"] < 0x80000000)
+    for i in rng.choice(nav, 200, replace=False):
+        n = nodes[i]
+        sub = nodes[i + 1:int(n["exit_index"])]
+        ids = sub["entry_index"][sub["entry_index"] >= 0x80000000] - 0x80000000
+        assert np.all(mn[ids] >= n["min"]) and np.all(mx[ids] <= n["max"])
