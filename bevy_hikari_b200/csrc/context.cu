@@ -47,6 +47,7 @@ struct hk_context {
     cudaEvent_t ev_submitted = nullptr, ev_copied = nullptr;
     bool copy_in_flight = false;      // a copy has been queued and the compute stream has not yet been ordered behind it
     bool copy_unwaited = false;       // ... and the host has not waited for it
+    float trace_ms = 0.0f;            // kernel time of the last hk_trace_rays (ms_kernel[HK_K_TRACE_RAYS])
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[HK_K_COUNT][2] = {};   // per-kernel begin/end
     bool kran[HK_K_COUNT] = {};
@@ -665,6 +666,7 @@ int hk_get_stats(hk_context* ctx, hk_frame_stats* out) {
         for (int i = 0; i < HK_K_COUNT; ++i)
             if (ctx->kran[i]) cudaEventElapsedTime(&out->ms_kernel[i], ctx->kev[i][0], ctx->kev[i][1]);
     }
+    out->ms_kernel[HK_K_TRACE_RAYS] = ctx->trace_ms;
     out->kernel_launches = ctx->launches;
     return HK_OK;
 }
@@ -842,9 +844,15 @@ int hk_trace_rays(hk_context* ctx, const hk_ray* rays, size_t n, hk_hit* hits) {
     HK_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_rays), n * sizeof(hk_ray)));
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_hits), n * sizeof(hk_hit));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(hk_ray), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) { hk_launch_trace_rays(ctx->scene, d_rays, n, d_hits, ctx->stream); e = cudaGetLastError(); }
+    if (e == cudaSuccess) {
+        cudaEventRecord(ctx->ev[0], ctx->stream);
+        hk_launch_trace_rays(ctx->scene, d_rays, n, d_hits, ctx->stream);
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_hits, n * sizeof(hk_hit), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) cudaEventElapsedTime(&ctx->trace_ms, ctx->ev[0], ctx->ev[1]);
     cudaFree(d_rays); cudaFree(d_hits);
     HK_CUDA(e);
     return HK_OK;

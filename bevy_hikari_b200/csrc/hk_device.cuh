@@ -15,6 +15,33 @@
 #include "hikari_b200.h"
 #include "hk_math.h"
 
+// Inlining policy of the large device functions (code size vs call overhead; see DESIGN.md 4: the light kernels are
+// instruction-fetch bound).  Override per function group with -DHK_INL_<GROUP>=__noinline__.
+#ifndef HK_INL_PACK
+#define HK_INL_PACK __forceinline__
+#endif
+#ifndef HK_INL_TRAVERSE
+#define HK_INL_TRAVERSE __forceinline__
+#endif
+#ifndef HK_INL_HITINFO
+#define HK_INL_HITINFO __forceinline__
+#endif
+#ifndef HK_INL_TEXTURE
+#define HK_INL_TEXTURE __forceinline__
+#endif
+#ifndef HK_INL_SURFACE
+#define HK_INL_SURFACE __forceinline__
+#endif
+#ifndef HK_INL_SHADE
+#define HK_INL_SHADE __forceinline__
+#endif
+#ifndef HK_INL_RADIANCE
+#define HK_INL_RADIANCE __forceinline__
+#endif
+#ifndef HK_INL_SELECT
+#define HK_INL_SELECT __forceinline__
+#endif
+
 namespace hkd {
 using namespace hk;
 
@@ -148,7 +175,7 @@ __device__ __forceinline__ Reservoir zero_reservoir() {
 // light.wgsl:77-136 on the planar layout.
 struct PackedQuarters { uint4 q0, q1, q2, q3; };
 
-__device__ __forceinline__ Reservoir unpack_reservoir(const PackedQuarters& p) {
+static __device__ HK_INL_PACK Reservoir unpack_reservoir(const PackedQuarters& p) {
     Reservoir r;
     vec2 t0 = unpack2x16float(p.q3.z), t1 = unpack2x16float(p.q3.w);
     r.count = t0.x; r.w = t0.y; r.w_sum = t1.x; r.w2_sum = t1.y;
@@ -166,7 +193,7 @@ __device__ __forceinline__ Reservoir unpack_reservoir(const PackedQuarters& p) {
     r.s.visible_instance = f32_to_u32(__uint_as_float(p.q2.w));
     return r;
 }
-__device__ __forceinline__ PackedQuarters pack_reservoir(const Reservoir& r) {
+static __device__ HK_INL_PACK PackedQuarters pack_reservoir(const Reservoir& r) {
     PackedQuarters p;
     p.q0.x = pack2x16float(r.s.radiance.x, r.s.radiance.y);
     p.q0.y = pack2x16float(r.s.radiance.z, r.s.radiance.w);
@@ -333,7 +360,7 @@ __device__ __forceinline__ void instance_ray(const hk_instance* inst, const Ray&
 // the TLAS execute the same interior-node code together instead of serialising inner against outer loop — the nested
 // form ran at ~4 active lanes per instruction on secondary rays (ncu, profiles/r1).  Visit order, the strict '<'
 // updates and both early-outs are unchanged, so hits are bit-identical to the nested walk.
-__device__ __forceinline__ Hit traverse_top(const DeviceScene& sc, const Ray& ray, float max_distance, float early_distance,
+static __device__ HK_INL_TRAVERSE Hit traverse_top(const DeviceScene& sc, const Ray& ray, float max_distance, float early_distance,
                                             uint32_t exclude_instance) {
     Hit hit;
     hit.u = 0.0f; hit.v = 0.0f; hit.distance = max_distance;
@@ -430,7 +457,7 @@ __device__ __forceinline__ HitInfo empty_hit_info(vec3 position, vec3 direction)
     info.normal = v3(0.0f); info.uv = v2(0.0f, 0.0f);
     return info;
 }
-__device__ __forceinline__ HitInfo hit_info(const DeviceScene& sc, const Ray& ray, const Hit& hit) {  // light.wgsl:496-523
+static __device__ HK_INL_HITINFO HitInfo hit_info(const DeviceScene& sc, const Ray& ray, const Hit& hit) {  // light.wgsl:496-523
     HitInfo info;
     info.instance_index = hit.instance_index;
     info.material_index = U32_MAX;
@@ -492,7 +519,7 @@ __device__ __forceinline__ int wrap_coord(int i, int n, uint32_t mode) {
     int period = 2 * n; i %= period; if (i < 0) i += period;
     return (i < n) ? i : period - 1 - i;
 }
-__device__ __forceinline__ vec4 sample_texture(const DeviceScene& sc, uint32_t id, vec2 uv) {
+static __device__ HK_INL_TEXTURE vec4 sample_texture(const DeviceScene& sc, uint32_t id, vec2 uv) {
     uint4 ti = __ldg(&sc.texture_info[id]);
     const float4* tex = sc.texture_texels + ti.x;
     int w = (int)ti.y, h = (int)ti.z;
@@ -515,7 +542,7 @@ __device__ __forceinline__ vec4 sample_texture(const DeviceScene& sc, uint32_t i
 }
 
 // retreive_surface, light.wgsl:730-742 (NO_TEXTURE) / 749-781
-__device__ __forceinline__ Surface retreive_surface(const DeviceScene& sc, uint32_t material_index, vec2 uv) {
+static __device__ HK_INL_SURFACE Surface retreive_surface(const DeviceScene& sc, uint32_t material_index, vec2 uv) {
     const float4* m = reinterpret_cast<const float4*>(sc.materials + material_index);
     float4 base = ldg4(m), t0 = ldg4(m + 1), emis = ldg4(m + 2), t1 = ldg4(m + 3), t2 = ldg4(m + 4);
     Surface s;
@@ -537,7 +564,7 @@ __device__ __forceinline__ Surface retreive_surface(const DeviceScene& sc, uint3
     s.reflectance = t2.x;
     return s;
 }
-__device__ __forceinline__ vec4 retreive_emissive(const DeviceScene& sc, uint32_t material_index, vec2 uv) {  // light.wgsl:744-747 / 783-793
+static __device__ HK_INL_SURFACE vec4 retreive_emissive(const DeviceScene& sc, uint32_t material_index, vec2 uv) {  // light.wgsl:744-747 / 783-793
     const float4* m = reinterpret_cast<const float4*>(sc.materials + material_index);
     vec4 emissive = f4v(ldg4(m + 2));
     if (sc.texture_count != 0u) {
@@ -568,7 +595,7 @@ __device__ __forceinline__ vec3 calculate_view(const ShadeEnv& e, vec3 world_pos
 __device__ __forceinline__ vec3 env_terms(vec3 diffuse_color, vec3 F0, float roughness, float NdotV) {
     return EnvBRDFApprox(diffuse_color, 1.0f, NdotV) + EnvBRDFApprox(F0, roughness, NdotV);
 }
-__device__ __forceinline__ vec3 env_brdf(vec3 V, vec3 N, const Surface& s) {  // light.wgsl:890-908
+static __device__ HK_INL_SHADE vec3 env_brdf(vec3 V, vec3 N, const Surface& s) {  // light.wgsl:890-908
     vec3 base_color = xyz(s.base_color);
     float NdotV = fmax_(dot(N, V), 0.0001f);
     vec3 F0 = v3(0.16f * s.reflectance * s.reflectance * (1.0f - s.metallic)) + base_color * s.metallic;
@@ -609,11 +636,11 @@ __device__ __forceinline__ vec3 shade(const ShadeCtx& c, vec3 Lv, vec4 in_radian
     vec3 lit_radiance = (specular_light + diffuse) * xyz(in_radiance) * NoL;
     return mix(lit_radiance, c.ambient_radiance, 1.0f - in_radiance.w);
 }
-__device__ __forceinline__ vec3 shading(const ShadeEnv& e, vec3 V, vec3 N, vec3 Lv, const Surface& s, vec4 in_radiance) {
+static __device__ HK_INL_SHADE vec3 shading(const ShadeEnv& e, vec3 V, vec3 N, vec3 Lv, const Surface& s, vec4 in_radiance) {
     return shade(make_shade_ctx(e, V, N, s), Lv, in_radiance);
 }
 // input_radiance, light.wgsl:835-867
-__device__ __forceinline__ vec4 input_radiance(const DeviceScene& sc, const ShadeEnv& e, vec3 ray_direction, const HitInfo& info,
+static __device__ HK_INL_RADIANCE vec4 input_radiance(const DeviceScene& sc, const ShadeEnv& e, vec3 ray_direction, const HitInfo& info,
                                                bool sample_directional, uint32_t sample_emissive, bool sample_ambient) {
     vec3 radiance = v3(0.0f);
     float amb = 0.0f;
@@ -633,7 +660,7 @@ __device__ __forceinline__ vec4 input_radiance(const DeviceScene& sc, const Shad
 
 // select_light_candidate, light.wgsl:599-708.  COUNT_RAYS adds the stand-alone BLAS ray to *blas_rays.
 template <bool COUNT_RAYS>
-__device__ __forceinline__ LightCandidate select_light_candidate(const DeviceScene& sc, const ShadeEnv& e, vec4 rnd, vec3 position,
+static __device__ HK_INL_SELECT LightCandidate select_light_candidate(const DeviceScene& sc, const ShadeEnv& e, vec4 rnd, vec3 position,
                                                                  vec3 normal, uint32_t instance, HitInfo& info, uint32_t& blas_rays) {
     LightCandidate cand;
     cand.max_distance = F32_MAX;

@@ -39,15 +39,47 @@ __global__ void __launch_bounds__(CTA_THREADS) k_demodulation(const __grid_const
         denoise_deferred_coords(P, render_uv(P, x, y), x, y, dx, dy);
         gidx = band_index(P.band, dx, dy);
     }
+    // Every input of this kernel is read-only here, so all loads are issued before the first store (ld.global.nc): the
+    // kernel is a latency chain otherwise (ncu: 15 warps stalled on long scoreboard per issue, 33 % issue utilisation).
+    const uint32_t packed_normal = __ldg(&P.planes.normal[gidx]);
+    const float depth = __ldg(&P.planes.pos_depth[gidx].w);
+    const float instance = __ldg(&P.planes.instance_material[gidx].x);
+    const uint2 albedo_bits = __ldg(&P.planes.albedo[gidx]);
+    uint2 render_bits[3];
+    float variance[3][9];
+    bool tap_inside[9];
+#pragma unroll
+    for (int ox = -1; ox <= 1; ++ox)
+#pragma unroll
+        for (int oy = -1; oy <= 1; ++oy) {
+            const int sx = x + ox, sy = y + oy;
+            tap_inside[(ox + 1) * 3 + (oy + 1)] = !(sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH);
+        }
+#pragma unroll
+    for (int sgl = 0; sgl < 3; ++sgl) {
+        if (sgl >= signals) continue;
+        render_bits[sgl] = __ldg(&P.planes.render[sgl][idx]);
+#pragma unroll
+        for (int ox = -1; ox <= 1; ++ox)
+#pragma unroll
+            for (int oy = -1; oy <= 1; ++oy) {
+                const int t = (ox + 1) * 3 + (oy + 1);
+                variance[sgl][t] = tap_inside[t] ? __ldg(&P.planes.variance[sgl][render_index(P.band, x + ox, y + oy)]) : 0.0f;
+            }
+    }
     {   // tap geometry for the four a-trous levels: the normalised normal, depth and instance id of this pixel are read
         // by up to 36 taps; normalise once here instead of 36 times there (same operations, same values)
-        const vec3 n = normalize(xyz(unpack4x8snorm(P.planes.normal[gidx])));
-        P.planes.dn_geometry[idx] = make_float4(n.x, n.y, n.z, P.planes.pos_depth[gidx].w);
-        P.planes.dn_instance[idx] = P.planes.instance_material[gidx].x;
+        const vec3 n = normalize(xyz(unpack4x8snorm(packed_normal)));
+        P.planes.dn_geometry[idx] = make_float4(n.x, n.y, n.z, depth);
+        P.planes.dn_instance[idx] = instance;
     }
-    const vec3 albedo = xyz(load16(P.planes.albedo, gidx));
-    for (int sgl = 0; sgl < signals; ++sgl) {
-        vec3 irradiance = xyz(load16(P.planes.render[sgl], idx));
+    uvec2 ab; ab.x = albedo_bits.x; ab.y = albedo_bits.y;
+    const vec3 albedo = xyz(unpack_rgba16f(ab));
+#pragma unroll
+    for (int sgl = 0; sgl < 3; ++sgl) {
+        if (sgl >= signals) continue;
+        uvec2 rb; rb.x = render_bits[sgl].x; rb.y = render_bits[sgl].y;
+        vec3 irradiance = xyz(unpack_rgba16f(rb));
         vec3 q = irradiance / albedo;
         irradiance = v3(albedo.x < 0.01f ? 0.0f : q.x, albedo.y < 0.01f ? 0.0f : q.y, albedo.z < 0.01f ? 0.0f : q.z);
         store16(P.planes.dn_internal[0][sgl], idx, v4(irradiance, 1.0f));
@@ -57,11 +89,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_demodulation(const __grid_const
         for (int ox = -1; ox <= 1; ++ox) {
 #pragma unroll
             for (int oy = -1; oy <= 1; ++oy) {
-                int sx = x + ox, sy = y + oy;
-                if (sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH) continue;
-                float variance = P.planes.variance[sgl][render_index(P.band, sx, sy)];
-                if (variance > F32_MAX) continue;
-                sum_variance += kernel_at(P, oy + 1, ox + 1) * fmax_(variance, 0.0f);
+                const int t = (ox + 1) * 3 + (oy + 1);
+                if (!tap_inside[t]) continue;
+                const float v = variance[sgl][t];
+                if (v > F32_MAX) continue;
+                sum_variance += kernel_at(P, oy + 1, ox + 1) * fmax_(v, 0.0f);
             }
         }
         P.planes.dn_variance[sgl][idx] = sum_variance;

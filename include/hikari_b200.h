@@ -133,7 +133,8 @@ enum {   /* indices into hk_frame_stats.ms_kernel */
     HK_K_TONE_MAPPING = 11,
     HK_K_SMAA_TU4X = 12,         /* smaa_tu4x + smaa_tu4x_extrapolate (only with temporal_upscalers) */
     HK_K_TAA = 13,               /* taa_jasmine (only with temporal_upscalers) */
-    HK_K_COUNT = 14
+    HK_K_COUNT = 14,
+    HK_K_TRACE_RAYS = 15         /* kernel time of the last hk_trace_rays call (always filled) */
 };
 
 typedef struct hk_ray {   /* test hook input: a world-space ray exactly as traverse_top takes it */
