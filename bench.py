@@ -195,7 +195,7 @@ def make_bench(config):
     return cfg, scene, world, W, H, view, pview, lights, settings
 
 
-def config_json(config, cfg, settings, world_size):
+def config_json(config, cfg, settings, world_size, gather="peer"):
     return {"workload": f"{config}: {cfg['scene']} {cfg['width']}x{cfg['height']}, {settings.indirect_bounces} bounces, "
                         f"temporal+{'emissive+' if settings.emissive_spatial_reuse else ''}"
                         f"{'indirect ' if settings.indirect_spatial_reuse else ''}spatial ReSTIR, denoise {'on' if settings.denoise else 'off'}",
@@ -203,7 +203,9 @@ def config_json(config, cfg, settings, world_size):
             "emissive_spatial_reuse": int(settings.emissive_spatial_reuse), "indirect_spatial_reuse": int(settings.indirect_spatial_reuse),
             "denoise": int(settings.denoise), "upscale": "SmaaTu4x{ratio:1.0}", "taa": "None",
             "parallelism": (f"{world_size} screen tiles (+{GHOST} ghost px each side, cuts balanced on a coverage probe unless "
-                            "--equal-tiles), one all-gather of the tone-mapped tiles") if world_size > 1 else "single GPU",
+                            "--equal-tiles), " + ("tiles stored by the tone-map kernel into rank 0's frame over NVLink (CUDA IPC) + a 4-byte "
+                                                 "all-reduce as the frame barrier" if gather == "peer" else
+                                                 "one all-gather of the tone-mapped tiles")) if world_size > 1 else "single GPU",
             "l2": "per-frame working set (>1 GB of planes) exceeds L2; no explicit flush"}
 
 
@@ -259,9 +261,34 @@ def run_ours(args):
     send_buf = torch.zeros(max_elems, dtype=torch.float16, device=tile_t.device) if world_size > 1 else None
     frame_buf = torch.empty(world_size * max_elems, dtype=torch.float16, device=tile_t.device) if world_size > 1 else None
 
+    # Frame assembly (N > 1).  Default: rank 0 owns two full-frame buffers (double-buffered); every rank maps them through
+    # CUDA IPC and its last kernel stores the tile's pixels straight into the frame over NVLink (hk_set_frame_target) —
+    # the store is the transfer; the only collective is a 4-byte all-reduce that tells rank 0 that every tile has landed.
+    # --gather nccl keeps the earlier form (copy + all_gather_into_tensor of padded tiles) for comparison.
+    frame_targets = None
+    landed = torch.zeros(1, dtype=torch.int32, device=tile_t.device) if world_size > 1 else None
+    if world_size > 1 and args.gather == "peer":
+        handles = [None, None]
+        if rank == 0:
+            own = [dev.frame_alloc(), dev.frame_alloc()]
+            frame_targets = [own[0][0], own[1][0]]
+            handles = [own[0][1], own[1][1]]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            frame_targets = [dev.frame_open(handles[0]), dev.frame_open(handles[1])]
+    frame_no = [0]
+
+    def begin_frame():
+        if frame_targets:
+            dev.set_frame_target(frame_targets[frame_no[0] & 1], W)
+        frame_no[0] += 1
+
     def gather_frame():
-        send_buf[:tile_t.numel()].copy_(tile_t)
-        dist.all_gather_into_tensor(frame_buf, send_buf)
+        if frame_targets:
+            dist.all_reduce(landed)          # stream-ordered behind this rank's tone-map stores: "all tiles have landed"
+        else:
+            send_buf[:tile_t.numel()].copy_(tile_t)
+            dist.all_gather_into_tensor(frame_buf, send_buf)
     pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
 
     def barrier():
@@ -293,6 +320,7 @@ def run_ours(args):
     dev.set_profiling(False, True)        # per-kernel CUDA events on, ray counters off
     inputs = [frame_inputs(n) for n in range(1, W_ + K + 1)]
     for n in range(W_):
+        begin_frame()
         dev.render_frame(inputs[n])
         if world_size > 1:
             gather_frame()
@@ -305,6 +333,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for n in range(W_, W_ + K):
+        begin_frame()
         dev.render_frame(inputs[n])
         if world_size > 1:
             gather_frame()
@@ -348,19 +377,58 @@ def run_ours(args):
     # n + 1 renders (hk_readback_async); the host sees every frame's result, one frame later.  Two pinned buffers alternate.
     pinned2 = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
     host_bufs = [pinned.data_ptr(), pinned2.data_ptr()]
+    d2h_bytes = nbytes
+    if frame_targets:
+        # N > 1: the tiles land in rank 0's frame over NVLink; rank 0 reads the ASSEMBLED frame back to pinned host memory
+        # on a copy stream while the next frame renders.  Buffer (n & 1) is rewritten by frame n + 2: rank 0 orders its
+        # frame barrier n + 1 behind copy n, so no rank can store frame n + 2 before that copy has finished.
+        frame_bytes = W * H * 8
+        d2h_bytes = frame_bytes if rank == 0 else 0
+        copy_stream = torch.cuda.Stream(device=local_rank)
+        copied = torch.cuda.Event()
+        if rank == 0:
+            class _Frame:
+                def __init__(self, ptr):
+                    self.__cuda_array_interface__ = {"shape": (frame_bytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+            frame_views = [torch.as_tensor(_Frame(p), device=f"cuda:{local_rank}") for p in frame_targets]
+            host_frames = [torch.empty(frame_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+
+        def e2e_step(n, first):
+            begin_frame()
+            dev.run_frame(settings, view, pview, lights)
+            if rank == 0 and not first:
+                stream.wait_event(copied)            # frame barrier n is ordered behind copy n - 1
+            dist.all_reduce(landed)
+            if rank == 0:
+                ready = torch.cuda.Event()
+                ready.record(stream)
+                if not first:
+                    copied.synchronize()             # the host observes frame n - 1
+                copy_stream.wait_event(ready)
+                with torch.cuda.stream(copy_stream):
+                    host_frames[n & 1].copy_(frame_views[(frame_no[0] - 1) & 1], non_blocking=True)
+                    copied.record(copy_stream)
+
+        def e2e_finish():
+            if rank == 0:
+                copied.synchronize()
+    else:
+        def e2e_step(n, first):
+            dev.run_frame(settings, view, pview, lights)                      # host structs -> kernel parameters
+            dev.readback_wait()                                               # frame n - 1 has landed in host memory
+            dev.readback_async(L.OUT_TONE_MAPPED, host_bufs[n & 1], nbytes)   # D2H of this frame's tile, overlapping the next frame
+
+        def e2e_finish():
+            dev.readback_wait()                                               # the last frame's result too
     for n in range(W_):
-        dev.run_frame(settings, view, pview, lights)
-        dev.readback_wait()
-        dev.readback_async(L.OUT_TONE_MAPPED, host_bufs[n & 1], nbytes)
-    dev.readback_wait()
+        e2e_step(n, n == 0)
+    e2e_finish()
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
     for n in range(K):
-        dev.run_frame(settings, view, pview, lights)                      # host structs -> kernel parameters
-        dev.readback_wait()                                               # frame n - 1 has landed in host memory
-        dev.readback_async(L.OUT_TONE_MAPPED, host_bufs[n & 1], nbytes)   # D2H of this frame's tile, overlapping the next frame
-    dev.readback_wait()                                                   # the last frame's result too
+        e2e_step(n, n == 0)
+    e2e_finish()
     e1.record(stream)
     barrier()
     e2e_ms = reduce_max(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
@@ -425,11 +493,11 @@ def run_ours(args):
         "metric": "Mrays/s", "value": round(value, 3), "unit": "Mrays/s", "n_gpus": world_size, "steps": K, "warmup": W_,
         "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "reference asset cornell.glb + blue-noise seed (no synthetic inputs exist for this path)",
-        "config": dict(config_json(args.config, cfg, settings, world_size), tiles=[list(t) for t in tiles]),
+        "config": dict(config_json(args.config, cfg, settings, world_size, args.gather), tiles=[list(t) for t in tiles]),
         "rays_per_frame": {"light_tlas": rays[1] / K, "light_blas": rays[2] / K, "primary": rays[0] / K},
         "fps": round(1e3 / ms_per_step, 2),
         "e2e": {"value": round(e2e_value, 3), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / K, 5),
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": nbytes},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(launches_per_frame * K),
         "kernel_ms": {name: round(float(kernel_ms[i]), 5) for i, name in enumerate(L.KERNEL_NAMES) if kernel_ms[i] > 0},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
@@ -582,6 +650,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--equal-tiles", action="store_true", help="N > 1: equal grid of tiles instead of cost-balanced strips")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = tiles stored straight into rank 0's frame over NVLink (CUDA IPC); nccl = all_gather of tiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -47,6 +47,8 @@ struct hk_context {
     cudaEvent_t ev_submitted = nullptr, ev_copied = nullptr;
     bool copy_in_flight = false;      // a copy has been queued and the compute stream has not yet been ordered behind it
     bool copy_unwaited = false;       // ... and the host has not waited for it
+    uint2* frame_target = nullptr; uint32_t frame_pitch = 0;   // hk_set_frame_target
+    std::vector<void*> frames_owned, frames_opened;            // hk_frame_alloc / hk_frame_open
     float trace_ms = 0.0f;            // kernel time of the last hk_trace_rays (ms_kernel[HK_K_TRACE_RAYS])
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[HK_K_COUNT][2] = {};   // per-kernel begin/end
@@ -228,6 +230,8 @@ void hk_context_destroy(hk_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (void* p : ctx->frames_opened) cudaIpcCloseMemHandle(p);
+    for (void* p : ctx->frames_owned) cudaFree(p);
     if (ctx->ev_submitted) cudaEventDestroy(ctx->ev_submitted);
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     free_list(ctx->allocations);
@@ -485,6 +489,8 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     P.jitter_sign = ((in->frame.number & 1u) == 0u) ? -1.0f : 1.0f;
     P.ratio_m1 = in->frame.upscale_ratio - 1.0f;
     P.gbuffer_current = ctx->gbuffer_current;
+    P.frame_target = ratio1 ? ctx->frame_target : nullptr;   // the assembled frame has the output size = render size at ratio 1
+    P.frame_pitch = ctx->frame_pitch;
     if (!ratio1) {   // scaled_size = (ratio.recip() * size).ceil(), light.rs:622-624; render-size planes use stride RW
         const float scale = 1.0f / in->frame.upscale_ratio;
         P.band.RW = (int)ceilf(scale * (float)P.band.W);
@@ -823,6 +829,66 @@ int hk_readback_async(hk_context* ctx, int which, void* pinned_host, size_t byte
     ctx->copy_unwaited = true;
     return HK_OK;
 }
+// ------------------------------------------------------------------------------------------ frame assembly
+int hk_set_frame_target(hk_context* ctx, void* frame_device_ptr, uint32_t pitch_pixels) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    if (!frame_device_ptr) { ctx->frame_target = nullptr; ctx->frame_pitch = 0; return HK_OK; }
+    if (pitch_pixels < (uint32_t)ctx->band.W) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "frame target pitch is smaller than the frame width");
+    HK_CUDA(cudaSetDevice(ctx->device));
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, frame_device_ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "frame target is not device memory");
+    }
+    if (attr.device != ctx->device) {   // same-process peer (cross-process mappings from hk_frame_open are already accessible)
+        int can = 0;
+        HK_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, attr.device));
+        if (!can) return set_error(ctx, HK_ERR_UNSUPPORTED, "no peer access between the context's GPU and the frame target's GPU");
+        cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) HK_CUDA(e);
+        cudaGetLastError();
+    }
+    ctx->frame_target = static_cast<uint2*>(frame_device_ptr);
+    ctx->frame_pitch = pitch_pixels;
+    return HK_OK;
+}
+int hk_frame_alloc(hk_context* ctx, void** device_ptr, uint8_t ipc_handle[64]) {
+    if (!ctx || !device_ptr) return HK_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    HK_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ctx->band.W * (size_t)ctx->band.H * 8u;
+    void* p = nullptr;
+    HK_CUDA(cudaMalloc(&p, bytes));
+    ctx->frames_owned.push_back(p);
+    HK_CUDA(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ipc_handle) {
+        cudaIpcMemHandle_t h;
+        HK_CUDA(cudaIpcGetMemHandle(&h, p));
+        memcpy(ipc_handle, &h, 64);
+    }
+    *device_ptr = p;
+    return HK_OK;
+}
+int hk_frame_open(hk_context* ctx, const uint8_t ipc_handle[64], void** device_ptr) {
+    if (!ctx || !ipc_handle || !device_ptr) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    void* p = nullptr;
+    HK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->frames_opened.push_back(p);
+    *device_ptr = p;
+    return HK_OK;
+}
+int hk_frame_read(hk_context* ctx, const void* frame_device_ptr, void* host, size_t bytes) {
+    if (!ctx || !frame_device_ptr || !host) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    HK_CUDA(cudaMemcpyAsync(host, frame_device_ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HK_OK;
+}
+
 int hk_readback_wait(hk_context* ctx) {
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;
     if (!ctx->copy_unwaited) return HK_OK;

@@ -135,6 +135,10 @@ struct KParams {
     float jitter_sign;      // -1 on even frames, +1 on odd frames (light.wgsl:1010, denoise.wgsl:40)
     float ratio_m1;         // upscale_ratio - 1
     int gbuffer_current;    // which of the double-buffered position / velocity_uv planes is "current" this frame
+    // frame assembly (hk_set_frame_target): a full-frame Rgba16Float image, possibly in a peer GPU's memory (NVLink), that
+    // receives this context's owned pixels at their global position; nullptr = none
+    uint2* frame_target;
+    uint32_t frame_pitch;   // pixels
 };
 
 // --------------------------------------------------------------------------------------------- raw loads

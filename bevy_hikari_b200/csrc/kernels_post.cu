@@ -21,6 +21,14 @@ __device__ __forceinline__ void store16(uint2* plane, size_t i, vec4 v) {
     uvec2 w = pack_rgba16f(v);
     plane[i] = make_uint2(w.x, w.y);
 }
+// the tone-mapped pixel: into the context's own tile and, when a frame target is set, into the assembled frame — for a
+// remote target this store over NVLink *is* the transfer (no gather kernel, no collective on the data path)
+__device__ __forceinline__ void store_final(const KParams& P, int x, int y, vec4 color) {
+    uvec2 w = pack_rgba16f(color);
+    const uint2 bits = make_uint2(w.x, w.y);
+    P.planes.tone_mapped[owned_index(P.band, x, y)] = bits;
+    if (P.frame_target) P.frame_target[(size_t)y * P.frame_pitch + (size_t)x] = bits;
+}
 __device__ __forceinline__ bool bad3(vec3 v) {  // any_is_nan_vec3(v) || any(v > F32_MAX), denoise.wgsl:190,239
     return is_nan(v.x) || is_nan(v.y) || is_nan(v.z) || v.x > F32_MAX || v.y > F32_MAX || v.z > F32_MAX;
 }
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
         color = v4(rgb, color.w);
         if (!(color.w > 0.0f))
             color = v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]);
-        store16(P.planes.tone_mapped, owned_index(P.band, x, y), color);
+        store_final(P, x, y, color);
     }
 }
 
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_tone_mapping(const __grid_const
     color = v4(rgb, color.w);
     if (!(color.w > 0.0f))
         color = v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]);
-    store16(P.planes.tone_mapped, owned_index(P.band, x, y), color);
+    store_final(P, x, y, color);
 }
 
 static dim3 grid_for(const KParams& P) {

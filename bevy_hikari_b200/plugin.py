@@ -254,6 +254,27 @@ class HikariPlugin:
     def readback_wait(self):
         check(lib().hk_readback_wait(self.ctx), self.ctx)
 
+    # frame assembly across tiles / GPUs (hk_set_frame_target)
+    def frame_alloc(self):
+        p = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        check(lib().hk_frame_alloc(self.ctx, C.byref(p), handle), self.ctx)
+        return p.value, bytes(handle)
+
+    def frame_open(self, handle):
+        p = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        check(lib().hk_frame_open(self.ctx, buf, C.byref(p)), self.ctx)
+        return p.value
+
+    def set_frame_target(self, device_ptr, pitch_pixels=None):
+        check(lib().hk_set_frame_target(self.ctx, device_ptr, self.width if pitch_pixels is None else pitch_pixels), self.ctx)
+
+    def frame_read(self, device_ptr):
+        out = np.empty(self.width * self.height * 8, np.uint8)
+        check(lib().hk_frame_read(self.ctx, device_ptr, out.ctypes.data, out.size), self.ctx)
+        return view_plane(out, L.OUT_TONE_MAPPED, self.height, self.width)
+
     def upload_state(self, which, array):
         a = np.ascontiguousarray(array)
         check(lib().hk_upload_state(self.ctx, which, a.ctypes.data, a.nbytes), self.ctx)

@@ -193,6 +193,17 @@ int hk_readback_wait(hk_context* ctx);
 int hk_upload_state(hk_context* ctx, int which, const void* host, size_t bytes);  /* inverse of hk_readback (tests) */
 int hk_sync(hk_context* ctx);
 
+/* Frame assembly for tiled (multi-GPU) rendering.  With a frame target set, every owned pixel of the tone-mapped image is
+ * also stored into the full-frame Rgba16Float buffer `frame` (pitch in pixels) at its position in the frame, by the last
+ * kernel of hk_render_frame / hk_post_process_run itself.  `frame` may live on another GPU — same process (peer access is
+ * enabled on demand) or another process (hk_frame_open of a handle from hk_frame_alloc; CUDA IPC) — so that the store
+ * over NVLink is the transfer and no gather pass or collective touches the pixels.  The caller orders "all tiles have
+ * landed" (an event, or a barrier across ranks) before consuming the frame.  NULL clears the target.  upscale_ratio 1 only. */
+int hk_set_frame_target(hk_context* ctx, void* frame_device_ptr, uint32_t pitch_pixels);
+int hk_frame_alloc(hk_context* ctx, void** device_ptr, uint8_t ipc_handle[64]);        /* width x height x 8 B, zeroed; freed with the context */
+int hk_frame_open(hk_context* ctx, const uint8_t ipc_handle[64], void** device_ptr);   /* map a frame of another process; closed with the context */
+int hk_frame_read(hk_context* ctx, const void* frame_device_ptr, void* host, size_t bytes);   /* synchronous D2H of an assembled frame */
+
 int hk_trace_rays(hk_context* ctx, const hk_ray* rays, size_t n, hk_hit* hits);   /* F3/F4 parity hook */
 int hk_set_profiling(hk_context* ctx, int count_rays, int time_passes);
 int hk_set_keep_intermediates(hk_context* ctx, int keep);   /* 1: hk_render_frame also writes HK_OUT_DENOISED_* */
