@@ -170,6 +170,77 @@ def city():
                      sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 4.0, math.pi / 4.0, 0.0)))
 
 
+def _box_mesh(sx=1.0, sy=1.0, sz=1.0):
+    """bevy shape::Box::new(sx, sy, sz) (shape::Cube { size } = Box::new(size, size, size)): 24 vertices, 6 faces in
+    bevy's order (+z, -z, +x, -x, +y, -y), two triangles per face."""
+    x0, x1, y0, y1, z0, z1 = -sx / 2, sx / 2, -sy / 2, sy / 2, -sz / 2, sz / 2
+    v = [
+        ((x0, y0, z1), (0, 0, 1), (0, 0)), ((x1, y0, z1), (0, 0, 1), (1, 0)), ((x1, y1, z1), (0, 0, 1), (1, 1)), ((x0, y1, z1), (0, 0, 1), (0, 1)),
+        ((x0, y1, z0), (0, 0, -1), (1, 0)), ((x1, y1, z0), (0, 0, -1), (0, 0)), ((x1, y0, z0), (0, 0, -1), (0, 1)), ((x0, y0, z0), (0, 0, -1), (1, 1)),
+        ((x1, y0, z0), (1, 0, 0), (0, 0)), ((x1, y1, z0), (1, 0, 0), (1, 0)), ((x1, y1, z1), (1, 0, 0), (1, 1)), ((x1, y0, z1), (1, 0, 0), (0, 1)),
+        ((x0, y0, z1), (-1, 0, 0), (1, 0)), ((x0, y1, z1), (-1, 0, 0), (0, 0)), ((x0, y1, z0), (-1, 0, 0), (0, 1)), ((x0, y0, z0), (-1, 0, 0), (1, 1)),
+        ((x1, y1, z0), (0, 1, 0), (1, 0)), ((x0, y1, z0), (0, 1, 0), (0, 0)), ((x0, y1, z1), (0, 1, 0), (0, 1)), ((x1, y1, z1), (0, 1, 0), (1, 1)),
+        ((x1, y0, z1), (0, -1, 0), (0, 0)), ((x0, y0, z1), (0, -1, 0), (1, 0)), ((x0, y0, z0), (0, -1, 0), (1, 1)), ((x1, y0, z0), (0, -1, 0), (0, 1)),
+    ]
+    pos = np.array([a for a, _, _ in v], F); nrm = np.array([b for _, b, _ in v], F); uv = np.array([c for _, _, c in v], F)
+    idx = np.array([k + o for k in range(0, 24, 4) for o in (0, 1, 2, 2, 3, 0)], np.uint32)
+    return pos, nrm, uv, idx
+
+
+def _std_material(base=(1, 1, 1, 1), emissive=(0, 0, 0, 1), rough=0.089, metallic=0.01, refl=0.5):
+    """bevy 0.9 StandardMaterial::default() with overrides; Color::rgb values are passed through as_rgba_f32 (material.rs:168)."""
+    m = np.zeros((), L.MATERIAL)
+    m["base_color"], m["emissive"] = base, emissive
+    m["perceptual_roughness"], m["metallic"], m["reflectance"] = rough, metallic, refl
+    for k in ("base_color_texture", "emissive_texture", "metallic_roughness_texture", "normal_map_texture", "occlusion_texture"):
+        m[k] = 0xFFFFFFFF
+    return m
+
+
+_ROT_X_NEG_90 = np.array([[1, 0, 0, 0], [0, 0, -1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], F)   # Quat::from_rotation_x(-pi/2), rows = columns
+
+
+def minimal():
+    """examples/minimal.rs:20-66: Plane { size: 5 } rgb(0.3,0.5,0.3), Cube { size: 1 } rgb(0.8,0.7,0.6) at (0,0.5,0), sun
+    10 klx with rotation XYZ(-pi/4, pi/4, 0), camera (-2,2.5,5) -> origin, HikariSettings::default().  No emissive at all."""
+    meshes = [_plane_mesh(5.0), _box_mesh(1.0, 1.0, 1.0)]
+    mats = np.array([_std_material((0.3, 0.5, 0.3, 1.0)), _std_material((0.8, 0.7, 0.6, 1.0))], L.MATERIAL)
+    return SceneData(meshes, mats, [], [0, 1], [0, 1], [_translation(0, 0, 0), _translation(0.0, 0.5, 0.0)],
+                     eye=(-2.0, 2.5, 5.0), target=(0.0, 0.0, 0.0), sun_illuminance=10000.0,
+                     sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 4.0, math.pi / 4.0, 0.0)))
+
+
+def simple():
+    """examples/simple.rs:54-262 without the two extinguisher.glb instances: a room of scaled unit cubes (ground, left,
+    right, back, top), a 400 x 400 ground plane, TWO emissive earth spheres (emissive alpha 0.5 and 0.1) that the example
+    rotates about their local z (sphere_rotate_system, :385-389), sun 10 klx, camera (-10,2.5,20) -> origin."""
+    earth = np.load(os.path.join(SCENES, "earth.npz"))["rgba"]
+    textures = [{"rgba": earth, "address_mode_u": 1, "address_mode_v": 1, "filter_linear": 1, "srgb": 1}]
+    meshes = [_box_mesh(1.0, 1.0, 1.0), _plane_mesh(1.0), _uv_sphere_mesh(0.5, 36, 18), _uv_sphere_mesh(0.5, 36, 18)]
+    mat = [_std_material((0.3, 0.5, 0.3, 1.0), rough=0.9), _std_material((1, 1, 1, 1), rough=0.9),
+           _std_material((1.0, 0.08, 0.58, 1.0), rough=0.9),       # Color::PINK
+           _std_material((1, 1, 1, 1), rough=0.9),
+           _std_material((0.49, 1.0, 0.83, 1.0), rough=0.9),       # Color::AQUAMARINE
+           _std_material((1, 1, 1, 1), rough=0.9)]
+    for alpha in (0.5, 0.1):
+        m = _std_material((1, 1, 1, 1), emissive=(1.0, 1.0, 1.0, alpha))
+        m["base_color_texture"] = 0
+        m["emissive_texture"] = 0
+        mat.append(m)
+    inst_mesh = [0, 1, 0, 0, 0, 0, 2, 3]
+    inst_mat = [0, 1, 2, 3, 4, 5, 6, 7]
+    xf = [_translation(0.0, -0.5, 0.0, (8.0, 1.0, 8.0)), _translation(0.0, -1.0, 0.0, (400.0, 1.0, 400.0)),
+          _translation(-3.5, 3.0, 0.0, (1.0, 6.0, 8.0)), _translation(3.5, 3.0, 0.0, (1.0, 6.0, 8.0)),
+          _translation(0.0, 3.0, -3.5, (6.0, 6.0, 1.0)), _translation(0.0, 6.5, 0.0, (8.0, 1.0, 8.0))]
+    for x in (2.0, -2.0):
+        m = _ROT_X_NEG_90.copy()
+        m[3, :3] = (x, 1.0, 0.0)
+        xf.append(m.reshape(16))
+    return SceneData(meshes, np.array(mat, L.MATERIAL), textures, inst_mesh, inst_mat, xf,
+                     eye=(-10.0, 2.5, 20.0), target=(0.0, 0.0, 0.0), sun_illuminance=10000.0,
+                     sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 4.0, math.pi / 4.0, 0.0)))
+
+
 def terrain(n=224, seed=7):
     """Stress scene, not a reference example: one n x n-quad displaced grid (2 n^2 triangles — 100 352 at n = 224, the size
     class of the reference's scene.gltf) under a small emissive sphere and the sun; exercises a deep
@@ -202,7 +273,7 @@ def terrain(n=224, seed=7):
                      sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 3.0, math.pi / 5.0, 0.0)))
 
 
-SCENE_BUILDERS = {"cornell": cornell, "city": city, "terrain": terrain}
+SCENE_BUILDERS = {"cornell": cornell, "city": city, "terrain": terrain, "minimal": minimal, "simple": simple}
 
 # BASELINE.json configs.  All run with Upscale::SmaaTu4x{ratio 1.0}, Taa::None so that the render
 # resolution equals the stated resolution.

@@ -49,9 +49,9 @@ def test_upscale_ratio_city_textured():
 UPSCALER_CASES = [
     # scene, config, size, settings, planes produced
     ("cornell", "cornell_1080p", (112, 80), dict(taa=plugin.TAA_JASMINE, upscale_kind=plugin.UPSCALE_SMAA_TU4X, upscale_ratio=1.0),
-     [L.OUT_UPSCALED, L.OUT_TAA]),                                           # HikariSettings::default()
+     [L.OUT_UPSCALED, L.OUT_TAA]),                                           # Upscale::SMAA_TU_1_0 + Taa::Jasmine
     ("cornell", "cornell_1080p", (112, 80), dict(taa=plugin.TAA_JASMINE, upscale_kind=plugin.UPSCALE_SMAA_TU4X, upscale_ratio=2.0),
-     [L.OUT_UPSCALED, L.OUT_TAA]),                                           # Upscale::SMAA_TU_2_0
+     [L.OUT_UPSCALED, L.OUT_TAA]),                                           # HikariSettings::default(): Upscale::SMAA_TU_2_0 + Taa::Jasmine (lib.rs:435-455,494-497)
     ("cornell", "cornell_1080p", (90, 50), dict(taa=plugin.TAA_NONE, upscale_kind=plugin.UPSCALE_SMAA_TU4X, upscale_ratio=1.5),
      [L.OUT_UPSCALED]),
     ("cornell", "cornell_1080p", (90, 50), dict(taa=plugin.TAA_JASMINE, upscale_kind=plugin.UPSCALE_FSR1, upscale_ratio=1.0),
