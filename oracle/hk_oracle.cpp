@@ -1926,6 +1926,18 @@ uint32_t hko_math_hash(uint32_t v) { return hash_u32(v); }
 float hko_math_unsnorm8(uint32_t b) { return unsnorm8(b); }
 float hko_math_unorm8(uint32_t b) { return unorm8(b); }
 float hko_math_unorm16(uint32_t u) { return unpack2x16unorm(u).x; }
+// BRDF pieces of light.wgsl:796-833 (imported from bevy_pbr::pbr_lighting) for tests/test_math.py, which checks them
+// against a float64 restatement of the published Filament / Karis formulas
+void hko_math_lit(const float* radiance, const float* diffuse_color, float roughness, const float* F0, const float* Lv, const float* N,
+                  const float* V, float* out3) {
+    vec3 r = lit(ld3(radiance), ld3(diffuse_color), roughness, ld3(F0), ld3(Lv), ld3(N), ld3(V));
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+void hko_math_env_brdf_approx(const float* f0, float perceptual_roughness, float NoV, float* out3) {
+    vec3 r = EnvBRDFApprox(ld3(f0), perceptual_roughness, NoV);
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+float hko_math_perceptual_roughness_to_roughness(float pr) { return perceptualRoughnessToRoughness(pr); }
 void hko_math_normal_basis(const float* n, float* out9) {
     mat3 m = normal_basis(v3(n[0], n[1], n[2]));
     for (int i = 0; i < 3; ++i) { out9[3 * i] = m.c[i].x; out9[3 * i + 1] = m.c[i].y; out9[3 * i + 2] = m.c[i].z; }

@@ -52,6 +52,9 @@ def lib():
             "hko_get_stats": (_I, [_P, C.POINTER(L.FrameStats)]),
             "hko_trace_steps": (_I, [_P, _P, _SZ, _P]),
             "hko_last_error": (C.c_char_p, [_P]),
+            "hko_math_lit": (None, [_P, _P, C.c_float, _P, _P, _P, _P, _P]),
+            "hko_math_env_brdf_approx": (None, [_P, C.c_float, C.c_float, _P]),
+            "hko_math_perceptual_roughness_to_roughness": (C.c_float, [C.c_float]),
             "hko_math_exp2": (C.c_float, [C.c_float]),
             "hko_math_exp": (C.c_float, [C.c_float]),
             "hko_math_sincos": (None, [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

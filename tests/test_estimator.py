@@ -1,0 +1,191 @@
+"""A physical anchor for the oracle that needs no reference output: with temporal and spatial reuse off, the emissive
+direct pass is a one-sample Monte-Carlo estimator of the direct illumination from the area light,
+    E[out] = integral over the light of  f_r(x, V, L) * NoL * L_e * visibility * |cos(theta_y)| / d^2  dA,
+so its average over many frames and pixels must converge to that integral.  The integral is evaluated here by quadrature
+in float64 numpy with brute-force visibility and an independent restatement of the BRDF.  This checks the whole chain the
+parity tests take for granted: alias-table area sampling, the area-to-solid-angle pdf (light.wgsl:683-686), shadow rays,
+the RIS weight w_sum / (count * luminance) and the BRDF.
+
+Two properties of the reference's algorithm are modelled rather than hidden:
+  * the ray towards the sampled light point starts at position + RAY_BIAS * normal but keeps the direction computed from
+    the unbiased position (light.wgsl:664-670), so it lands up to 1 cm beside the sampled point and misses the light when
+    that point is within 1 cm of the far edge: a few per cent of the light's contribution are lost on surfaces whose
+    normal is parallel to the light's plane (the three walls: measured 4-6 % below the integral), < 1 % on the floor and the
+    boxes.  The assertions state exactly that: unbiased within 3 % on floor and boxes, 0-7 % low on the walls;
+  * all four random channels advance by the same golden-ratio step per frame (light.wgsl:1079), so one pixel's samples
+    lie on a line of the sample square and a single pixel's time average does not converge to its integral; averages over
+    many pixels (independent blue-noise offsets) do.  The assertions are therefore per surface, not per pixel.
+CPU only."""
+import numpy as np
+
+from bevy_hikari_b200 import layout as L
+from bevy_hikari_b200 import plugin
+from tests.conftest import Bench
+from tests.test_oracle import world_triangles
+
+
+def brdf_times_nol(N, V, Lv, base, rough, metallic, reflectance):
+    sat = lambda x: np.clip(x, 0.0, 1.0)
+    H = Lv + V
+    H /= np.linalg.norm(H, axis=1, keepdims=True)
+    NoL, NoH, LoH = sat((N * Lv).sum(1)), sat((N * H).sum(1)), sat((Lv * H).sum(1))
+    NoV = max(float(N[0] @ V[0]), 1e-4)
+    F0 = 0.16 * reflectance * reflectance * (1.0 - metallic) + base * metallic
+    diffuse = base * (1.0 - metallic)
+    f90 = 0.5 + 2.0 * rough * LoH * LoH
+    fd = (1 + (f90 - 1) * (1 - NoL) ** 5) * (1 + (f90 - 1) * (1 - NoV) ** 5) / np.pi
+    a = NoH * rough
+    k = rough / (1.0 - NoH * NoH + a * a)
+    D = k * k / np.pi
+    a2 = rough * rough
+    Vis = 0.5 / (NoL * np.sqrt((NoV - a2 * NoV) * NoV + a2) + NoV * np.sqrt((NoL - a2 * NoL) * NoL + a2) + 1e-30)
+    F = F0[None, :] + (sat(F0.sum() * 50.0 * 0.33) - F0[None, :]) * ((1 - LoH) ** 5)[:, None]
+    return ((D * Vis)[:, None] * F + diffuse[None, :] * fd[:, None]) * NoL[:, None]
+
+
+def occluded(tris, origin, targets):
+    """any triangle strictly between origin and each target point (Moeller-Trumbore, float64)"""
+    d = targets - origin
+    dist = np.linalg.norm(d, axis=1)
+    d = d / dist[:, None]
+    a, b, c = tris[:, 0], tris[:, 1], tris[:, 2]
+    ab, ac = b - a, c - a
+    blocked = np.zeros(len(targets), bool)
+    for i in range(len(targets)):
+        u_vec = np.cross(d[i], ac)
+        det = (ab * u_vec).sum(1)
+        ok = np.abs(det) > 1e-12
+        inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        ao = origin - a
+        u = (ao * u_vec).sum(1) * inv
+        v_vec = np.cross(ao, ab)
+        v = (d[i] * v_vec).sum(1) * inv
+        t = (ac * v_vec).sum(1) * inv
+        hit = ok & (u >= 0) & (u <= 1) & (v >= 0) & (u + v <= 1) & (t > 1e-6) & (t < dist[i] - 1e-3)
+        blocked[i] = hit.any()
+    return blocked
+
+
+def test_emissive_direct_pass_converges_to_the_area_light_integral():
+    size, frames = 32, 600
+    b = Bench("cornell", size, size, indirect_bounces=0, temporal_reuse=0, emissive_spatial_reuse=0, indirect_spatial_reuse=0, denoise=0,
+              emissive_validate_interval=1000000, direct_validate_interval=1000000, taa=plugin.TAA_NONE, upscale_ratio=1.0)
+    orc = b.oracle()
+    acc = np.zeros((size, size, 3))
+    for f in range(1, frames + 1):
+        orc.render_frame(b.inputs(f))
+        acc += orc.readback(L.OUT_RENDER_EMISSIVE).astype(np.float64)[..., :3]
+    acc /= frames
+    pos = orc.readback(L.OUT_GBUFFER_POSITION).astype(np.float64)
+    nrm = orc.readback(L.OUT_GBUFFER_NORMAL).astype(np.float64)[..., :3] / 127.0
+    im = np.floor(orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)).astype(int)
+
+    bufs = b.world.buffers()
+    tris, owner = world_triangles(bufs)
+    light_instance = int(bufs["emissives"][0]["instance"])
+    light_tris = tris[owner == light_instance]
+    blockers = tris[owner != light_instance]
+    emissive = bufs["materials"][bufs["instances"][light_instance]["material"]]["emissive"].astype(np.float64)
+    emission = 255.0 * emissive[3] * emissive[:3]                       # compute_emissive_radiance, light.wgsl:729-731
+    # quadrature points on the light: uniform barycentric grid per triangle
+    n = 14
+    pts, weights, normals = [], [], []
+    for t in light_tris:
+        e1, e2 = t[1] - t[0], t[2] - t[0]
+        area = 0.5 * np.linalg.norm(np.cross(e1, e2))
+        ng = np.cross(e1, e2); ng /= np.linalg.norm(ng)
+        cells = [(i, j, k) for i in range(n) for j in range(n - i) for k in (0, 1) if not (k == 1 and i + j >= n - 1)]
+        for i, j, k in cells:       # centroids of the n^2 congruent sub-triangles
+            u, v = ((i + 1 / 3) / n, (j + 1 / 3) / n) if k == 0 else ((i + 2 / 3) / n, (j + 2 / 3) / n)
+            pts.append(t[0] + u * e1 + v * e2); weights.append(area / (n * n)); normals.append(ng)
+    pts, weights, normals = np.array(pts), np.array(weights), np.array(normals)
+    assert abs(weights.sum() - float(bufs["emissives"][0]["surface_area"])) < 1e-4
+
+    eye = np.array(b.scene.eye, np.float64)
+    light_y = light_tris[0, 0, 1]
+    chosen = np.argwhere((pos[..., 3] > 0) & (im[..., 0] != light_instance) & (np.abs(pos[..., 1] - light_y) > 0.05))
+    got, ideal = [], []
+    for y, x in chosen:
+        p = pos[y, x, :3]
+        N = nrm[y, x] / np.linalg.norm(nrm[y, x])
+        mat = bufs["materials"][im[y, x, 1]]
+        rough = float(np.clip(mat["perceptual_roughness"], 0.089, 1.0)) ** 2
+        origin = p + N * 0.01                                           # RAY_BIAS
+        d = pts - p
+        d2 = (d * d).sum(1)
+        Lv = d / np.sqrt(d2)[:, None]
+        cos_y = np.abs((Lv * normals).sum(1))
+        V = (eye - p) / np.linalg.norm(eye - p)
+        f = brdf_times_nol(np.tile(N, (len(pts), 1)), np.tile(V, (len(pts), 1)), Lv, mat["base_color"][:3].astype(np.float64), rough,
+                           float(mat["metallic"]), float(mat["reflectance"]))
+        vis = ~occluded(blockers, origin, pts)
+        ideal.append((f * (cos_y / d2 * weights * vis)[:, None]).sum(0) * emission)
+        got.append(acc[y, x])
+    got, ideal = np.array(got), np.array(ideal)
+    surface = im[chosen[:, 0], chosen[:, 1], 0]
+    lum = lambda a: a @ np.array([0.2126, 0.7152, 0.0722])
+    g, e = lum(got), lum(ideal)
+    ratios = {}
+    for k in np.unique(surface):
+        m = (surface == k) & (e > 0.02 * e.max())
+        if m.sum() < 30:
+            continue
+        ratios[int(k)] = g[m].sum() / e[m].sum()
+        per_channel = got[m].sum(0) / ideal[m].sum(0)
+        assert np.all(np.abs(per_channel - ratios[int(k)]) < 0.01), (k, per_channel)          # base colours carried correctly
+    assert len(ratios) >= 5, ratios                           # back wall, floor, left wall, right wall, tall box
+    normals_of = {int(k): nrm[chosen[surface == k][0][0], chosen[surface == k][0][1]] for k in ratios}
+    for k, r in ratios.items():
+        facing_sideways = abs(normals_of[k][1]) < 0.5         # surface normal (nearly) parallel to the light's plane
+        if facing_sideways and abs(normals_of[k][0]) + abs(normals_of[k][2]) > 0.99 and min(abs(normals_of[k][0]), abs(normals_of[k][2])) < 0.05:
+            assert 0.93 < r < 1.0, (k, r)                     # the three walls: the ray-bias loss described above
+        else:
+            assert abs(r - 1.0) < 0.03, (k, r)                # floor and boxes: unbiased
+    lit = e > 0.02 * e.max()
+    assert 0.94 < g[lit].sum() / e[lit].sum() < 1.0
+    assert np.corrcoef(g[lit], e[lit])[0, 1] > 0.97           # pixel by pixel: shadows, distance fall-off, BRDF lobes
+
+
+def test_sun_pass_equals_the_brdf_times_the_sun_where_unshadowed():
+    """examples/minimal.rs under the sun only: the directional pass samples the solar cone (half angle 0.046 rad) with
+    p = 1, so away from shadow edges its output is lit(directional_colour, L ~ sun) and inside the cube's shadow it is 0."""
+    size, frames = 48, 60
+    b = Bench("minimal", size, size, indirect_bounces=0, temporal_reuse=0, emissive_spatial_reuse=0, indirect_spatial_reuse=0, denoise=0,
+              emissive_validate_interval=1000000, direct_validate_interval=1000000, taa=plugin.TAA_NONE, upscale_ratio=1.0)
+    orc = b.oracle()
+    acc = np.zeros((size, size, 3))
+    for f in range(1, frames + 1):
+        orc.render_frame(b.inputs(f))
+        acc += orc.readback(L.OUT_RENDER_DIRECT).astype(np.float64)[..., :3]
+    acc /= frames
+    pos = orc.readback(L.OUT_GBUFFER_POSITION).astype(np.float64)
+    nrm = orc.readback(L.OUT_GBUFFER_NORMAL).astype(np.float64)[..., :3] / 127.0
+    im = np.floor(orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)).astype(int)
+    bufs = b.world.buffers()
+    tris, _ = world_triangles(bufs)
+    sun = np.array(b.lights.direction_to_light[:], np.float64)
+    colour = np.array(b.lights.directional_color[:3], np.float64)
+    eye = np.array(b.scene.eye, np.float64)
+    # a ring of directions on the rim of the solar cone: a pixel is "clear" when the whole cone is visible, "dark" when none of it is
+    t1 = np.cross(sun, [0.0, 1.0, 0.0]); t1 /= np.linalg.norm(t1); t2 = np.cross(sun, t1)
+    rim = [sun] + [np.cos(0.06) * sun + np.sin(0.06) * (np.cos(a) * t1 + np.sin(a) * t2) for a in np.linspace(0, 2 * np.pi, 6, endpoint=False)]
+    lit_px = dark_px = 0
+    for y, x in np.argwhere(pos[..., 3] > 0):
+        p = pos[y, x, :3]
+        N = nrm[y, x] / np.linalg.norm(nrm[y, x])
+        if N @ sun < 0.15:
+            continue
+        origin = p + N * 0.01
+        blocked = occluded(tris, origin, np.array([origin + 100.0 * d for d in rim]))
+        mat = bufs["materials"][im[y, x, 1]]
+        rough = float(np.clip(mat["perceptual_roughness"], 0.089, 1.0)) ** 2
+        if not blocked.any():
+            V = (eye - p) / np.linalg.norm(eye - p)
+            expect = brdf_times_nol(N[None, :], V[None, :], sun[None, :], mat["base_color"][:3].astype(np.float64), rough,
+                                    float(mat["metallic"]), float(mat["reflectance"]))[0] * colour
+            assert np.allclose(acc[y, x], expect, rtol=0.03, atol=1e-3), (y, x, acc[y, x], expect)
+            lit_px += 1
+        elif blocked.all():
+            assert np.all(acc[y, x] == 0.0), (y, x, acc[y, x])
+            dark_px += 1
+    assert lit_px > 300 and dark_px > 20, (lit_px, dark_px)

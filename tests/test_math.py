@@ -130,3 +130,59 @@ def test_fast_division_by_constants_is_exactly_ieee_division_for_every_input():
     got = np.array([lib.hko_math_unorm16(u) for u in range(65536)], np.float32)
     want = np.arange(65536, dtype=np.float32) / np.float32(65535.0)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_brdf_matches_float64_restatement_of_the_published_formulas():
+    """lit() (light.wgsl:796-818) = (Fr + Fd) * radiance * NoL with bevy_pbr 0.9's pbr_lighting functions, which are
+    Filament's: D_GGX, V_SmithGGXCorrelated, F_Schlick with f90 = saturate(dot(f0, 50 * 0.33)), Fd_Burley; EnvBRDFApprox is
+    Karis' mobile approximation.  Restated here in float64 from the published formulas, independent of include/hk_math.h."""
+    lib = oracle.lib()
+    rng = np.random.default_rng(3)
+    f3 = lambda a: np.ascontiguousarray(a, np.float32)
+
+    def unit(v):
+        return v / np.linalg.norm(v)
+
+    worst = 0.0
+    for _ in range(400):
+        N = unit(rng.normal(size=3))
+        V = unit(N + 0.9 * rng.normal(size=3))
+        Lv = unit(N + 0.9 * rng.normal(size=3))
+        rough = float(np.float32(rng.uniform(0.089, 1.0) ** 2))
+        F0 = rng.uniform(0.02, 0.9, 3); diffuse = rng.uniform(0, 1, 3); radiance = rng.uniform(0, 20, 3)
+        args = [f3(radiance), f3(diffuse), f3(F0), f3(Lv), f3(N), f3(V)]
+        radiance, diffuse, F0, Lv, N, V = [a.astype(np.float64) for a in args]
+        out = np.zeros(3, np.float32)
+        lib.hko_math_lit(args[0].ctypes.data, args[1].ctypes.data, C.c_float(rough), args[2].ctypes.data, args[3].ctypes.data,
+                         args[4].ctypes.data, args[5].ctypes.data, out.ctypes.data)
+        H = unit(Lv + V)
+        sat = lambda x: min(max(x, 0.0), 1.0)
+        NoL, NoH, LoH, NoV = sat(N @ Lv), sat(N @ H), sat(Lv @ H), max(N @ V, 1e-4)
+        f90 = 0.5 + 2.0 * rough * LoH * LoH
+        fd = (1 + (f90 - 1) * (1 - NoL) ** 5) * (1 + (f90 - 1) * (1 - NoV) ** 5) / np.pi
+        a = NoH * rough
+        k = rough / (1.0 - NoH * NoH + a * a)
+        D = k * k / np.pi
+        a2 = rough * rough
+        Vis = 0.5 / (NoL * np.sqrt((NoV - a2 * NoV) * NoV + a2) + NoV * np.sqrt((NoL - a2 * NoL) * NoL + a2))
+        F = F0 + (sat(F0.sum() * 50.0 * 0.33) - F0) * (1 - LoH) ** 5
+        expect = (D * Vis * F + diffuse * fd) * radiance * NoL
+        if np.abs(expect).max() > 1e-6:
+            worst = max(worst, float(np.abs(out - expect).max() / max(np.abs(expect).max(), 1e-3)))
+    assert worst < 2e-4, worst
+
+    worst = 0.0
+    for _ in range(400):
+        f0 = rng.uniform(0.0, 1.0, 3); pr = float(rng.uniform(0.0, 1.0)); nov = float(rng.uniform(1e-4, 1.0))
+        out = np.zeros(3, np.float32)
+        f0_32 = f3(f0)
+        lib.hko_math_env_brdf_approx(f0_32.ctypes.data, C.c_float(pr), C.c_float(nov), out.ctypes.data)
+        pr, nov = float(np.float32(pr)), float(np.float32(nov))
+        r = pr * np.array([-1.0, -0.0275, -0.572, 0.022]) + np.array([1.0, 0.0425, 1.04, -0.04])
+        a004 = min(r[0] * r[0], 2.0 ** (-9.28 * nov)) * r[0] + r[1]
+        ab = np.array([-1.04, 1.04]) * a004 + r[2:]
+        expect = f0_32.astype(np.float64) * ab[0] + ab[1]
+        worst = max(worst, float(np.abs(out - expect).max()))
+    assert worst < 2e-5, worst
+    assert lib.hko_math_perceptual_roughness_to_roughness(C.c_float(0.5)) == np.float32(0.25)
+    assert lib.hko_math_perceptual_roughness_to_roughness(C.c_float(0.01)) == np.float32(np.float32(0.089) * np.float32(0.089))
