@@ -66,9 +66,15 @@ def occluded(tris, origin, targets):
     return blocked
 
 
-def test_emissive_direct_pass_converges_to_the_area_light_integral():
+import pytest
+
+
+@pytest.mark.parametrize("temporal_reuse", [0, 1])
+def test_emissive_direct_pass_converges_to_the_area_light_integral(temporal_reuse):
+    """temporal_reuse = 0: plain one-sample estimator.  temporal_reuse = 1: temporal ReSTIR (reservoir merge, M cap 50, f16
+    storage of the weights) must leave the expectation unchanged in a static scene."""
     size, frames = 32, 600
-    b = Bench("cornell", size, size, indirect_bounces=0, temporal_reuse=0, emissive_spatial_reuse=0, indirect_spatial_reuse=0, denoise=0,
+    b = Bench("cornell", size, size, indirect_bounces=0, temporal_reuse=temporal_reuse, emissive_spatial_reuse=0, indirect_spatial_reuse=0, denoise=0,
               emissive_validate_interval=1000000, direct_validate_interval=1000000, taa=plugin.TAA_NONE, upscale_ratio=1.0)
     orc = b.oracle()
     acc = np.zeros((size, size, 3))
