@@ -663,10 +663,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--equal-tiles", action="store_true", help="N > 1: equal grid of tiles instead of cost-balanced strips")
+    ap.add_argument("--lib", default=None, help="tuning: load this build of libhikari_b200.so (tools/build_variants.py) instead of the in-tree one")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = tiles stored straight into rank 0's frame over NVLink (CUDA IPC); nccl = all_gather of tiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.lib:
+        from bevy_hikari_b200 import _ffi
+        _ffi.LIB_PATH = os.path.abspath(args.lib)
     if args.impl == "reference":
         run_reference(args)
     else:

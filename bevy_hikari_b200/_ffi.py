@@ -7,7 +7,7 @@ import os
 from . import layout as L
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("HK_LIB") or os.path.join(HERE, "libhikari_b200.so")   # HK_LIB: tuning builds (tools/build_variants.py)
+LIB_PATH = os.path.join(HERE, "libhikari_b200.so")   # the one product library; there is no fallback if it is missing
 
 HK_OK = 0
 HK_ERR_INVALID_ARGUMENT, HK_ERR_CUDA, HK_ERR_NOT_READY, HK_ERR_OUT_OF_MEMORY, HK_ERR_UNSUPPORTED = -1, -2, -3, -4, -5

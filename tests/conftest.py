@@ -9,8 +9,24 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+EMULATED = bool(os.environ.get("HK_EMULATE_KERNELS"))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if EMULATED:
+        # Development / CI aid (tests/emu/): run the `-m gpu` parity tests against the kernel SOURCES compiled for the host,
+        # to check kernel logic without a GPU.  Only ever enabled by this environment variable, only from tests.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emu
+        from bevy_hikari_b200 import _ffi
+        _ffi.LIB_PATH = build_emu.build()
+
+
+def needs_real_gpu():
+    """for the few tests that exercise the CUDA runtime itself (pinned memory, IPC) rather than kernel logic"""
+    if EMULATED:
+        pytest.skip("needs a real CUDA device (kernel-logic emulation is active)")
 
 
 @pytest.fixture(scope="session", autouse=True)

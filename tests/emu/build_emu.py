@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE: build tests/emu/_build/libhikari_emu.so — the kernel sources of bevy_hikari_b200/csrc compiled for
+the host through tests/emu/cuda_emu.h, behind the same C ABI, so that the kernels' logic can be compared with the oracle
+without a GPU (tests/test_emulated_kernels.py; HK_LIB=<this library> runs any `-m gpu` test on the CPU during development).
+The only source transformations are
+  * `kernel<<<grid, block, 0, stream>>>(args)`  ->  `EMU_LAUNCH(grid, block, kernel(args))`
+  * flush_counters' warp reduction (shuffles) -> one atomic add per thread (same totals)."""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SRC = os.path.join(ROOT, "bevy_hikari_b200", "csrc")
+HOST = os.path.join(ROOT, "bevy_hikari_b200", "host")
+GEN, OUT = os.path.join(HERE, "_gen"), os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libhikari_emu.so")
+CU = ["context.cu", "kernels_light.cu", "kernels_post.cu", "kernels_upscale.cu"]
+CPP = ["hikari.cpp", "hikari_capi.cpp"]
+CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
+FLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-std=c++17", "-w",
+         "-I" + os.path.join(HERE, "include"), "-I" + SRC, "-I" + HOST, "-I" + os.path.join(ROOT, "include")]
+
+LAUNCH = re.compile(r"([A-Za-z_][A-Za-z_0-9]*(?:<[^<>;]*>)?)<<<([^;]*?)>>>\(([^;]*)\);")
+FLUSH_OLD = re.compile(r"for \(int o = 16; o > 0; o >>= 1\) \{.*?\n    \}\n    if \(\(threadIdx\.x & 31\) == 0\) \{", re.S)
+
+
+def transform(text, name):
+    def launch(m):
+        kernel, cfg, args = m.group(1), m.group(2), m.group(3)
+        parts = [p.strip() for p in split_top(cfg)]
+        return f"EMU_LAUNCH(dim3({parts[0]}), dim3({parts[1]}), {kernel}({args}));"
+    out, n = LAUNCH.subn(launch, text)
+    if name == "kernels_light.cu":
+        out, k = FLUSH_OLD.subn("{", out)
+        assert k == 1, "flush_counters pattern changed"
+    assert "<<<" not in out, f"unconverted launch in {name}"
+    return out, n
+
+
+def split_top(s):
+    parts, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "(<[":
+            depth += 1
+        elif ch in ")>]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur); cur = ""
+        else:
+            cur += ch
+    parts.append(cur)
+    return parts
+
+
+def newer(target, sources):
+    return not os.path.exists(target) or any(os.path.getmtime(s) > os.path.getmtime(target) for s in sources)
+
+
+def build(force=False):
+    os.makedirs(GEN, exist_ok=True); os.makedirs(OUT, exist_ok=True)
+    deps = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(HOST, f) for f in os.listdir(HOST)] + \
+           [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))] + \
+           [os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__)]
+    if not force and not newer(LIB, deps):
+        return LIB
+    objs, launches = [], 0
+    for f in CU:
+        text, n = transform(open(os.path.join(SRC, f)).read(), f)
+        launches += n
+        g = os.path.join(GEN, f.replace(".cu", ".emu.cpp"))
+        open(g, "w").write(text)
+        o = os.path.join(OUT, f + ".o")
+        subprocess.run([CXX] + FLAGS + ["-c", g, "-o", o], check=True)
+        objs.append(o)
+    glue = os.path.join(GEN, "emu_globals.cpp")
+    open(glue, "w").write('#include "cuda_emu.h"\nthread_local EmuIdx threadIdx, blockIdx;\nthread_local dim3 blockDim, gridDim;\n')
+    o = os.path.join(OUT, "emu_globals.o")
+    subprocess.run([CXX] + FLAGS + ["-I" + HERE, "-c", glue, "-o", o], check=True)
+    objs.append(o)
+    for f in CPP:
+        o = os.path.join(OUT, f + ".o")
+        subprocess.run([CXX] + FLAGS + ["-c", os.path.join(HOST, f), "-o", o], check=True)
+        objs.append(o)
+    subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs, check=True)
+    print(f"emulator: {launches} launch sites converted -> {LIB}")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

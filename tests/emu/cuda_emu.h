@@ -1,0 +1,118 @@
+// cuda_emu.h — TEST INFRASTRUCTURE.  A host shim for the handful of CUDA constructs the kernels use, so that the kernel
+// SOURCES (bevy_hikari_b200/csrc/*.cu, unmodified except for the launch syntax, see build_emu.py) can be compiled with g++
+// and their LOGIC compared with the oracle without a GPU (tests/test_emulated_kernels.py).  It is not a fallback: the
+// package never loads the library built from it, performance is irrelevant, and nothing here is shipped.
+// Execution model: a launch runs every thread of every block to completion, one after the other (blocks in parallel with
+// OpenMP).  That is equivalent for these kernels: no shared memory, no barriers, no reads of values written by other
+// threads of the same launch; the only cross-thread operations are order-independent atomics.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __grid_constant__
+
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) uint2 { uint32_t x, y; };
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+struct uchar4 { uint8_t x, y, z, w; };
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+
+// CUDA's global min / max overloads
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline size_t min(size_t a, size_t b) { return a < b ? a : b; }
+static inline size_t max(size_t a, size_t b) { return a > b ? a : b; }
+
+struct EmuIdx { unsigned x, y, z; };
+extern thread_local EmuIdx threadIdx, blockIdx;
+extern thread_local dim3 blockDim, gridDim;
+
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
+    uint32_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline uint32_t __shfl_xor_sync(uint32_t, uint32_t, int) { return 0u; }   // see build_emu.py: flush_counters is patched to per-thread adds
+
+// ------------------------------------------------------------------------------------------------ runtime
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801, cudaErrorPeerAccessAlreadyEnabled = 704 };
+typedef struct EmuStream* cudaStream_t;
+typedef struct EmuEvent* cudaEvent_t;
+typedef unsigned long long cudaTextureObject_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+
+static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaMalloc(void** p, size_t bytes) { return posix_memalign(p, 256, bytes ? bytes : 256) == 0 ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < h; ++r) memcpy((char*)d + r * dp, (const char*)s + r * sp, w);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeDevice; a->device = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }   // one process only
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+// ------------------------------------------------------------------------------------------------ launches
+// EMU_LAUNCH(grid, block, kernel_call): every thread of every block, blocks distributed over the host cores
+#define EMU_LAUNCH(GRID, BLOCK, ...)                                                      \
+    do {                                                                                  \
+        const dim3 emu_g = (GRID), emu_b = (BLOCK);                                       \
+        const long long emu_n = (long long)emu_g.x * emu_g.y * emu_g.z;                   \
+        _Pragma("omp parallel for schedule(dynamic, 4)")                                  \
+        for (long long emu_i = 0; emu_i < emu_n; ++emu_i) {                               \
+            gridDim = emu_g; blockDim = emu_b;                                            \
+            blockIdx.x = (unsigned)(emu_i % emu_g.x);                                     \
+            blockIdx.y = (unsigned)((emu_i / emu_g.x) % emu_g.y);                         \
+            blockIdx.z = (unsigned)(emu_i / ((long long)emu_g.x * emu_g.y));              \
+            for (unsigned emu_t = 0; emu_t < emu_b.x * emu_b.y * emu_b.z; ++emu_t) {      \
+                threadIdx.x = emu_t % emu_b.x;                                            \
+                threadIdx.y = (emu_t / emu_b.x) % emu_b.y;                                \
+                threadIdx.z = emu_t / (emu_b.x * emu_b.y);                                \
+                __VA_ARGS__;                                                              \
+            }                                                                             \
+        }                                                                                 \
+    } while (0)

@@ -1,0 +1,28 @@
+"""Kernel logic without a GPU.  tests/emu/ compiles the CUDA kernel sources (bevy_hikari_b200/csrc/*.cu) for the host through
+a small shim of the CUDA constructs they use, behind the same C ABI, and this test runs the `-m gpu` parity tests against
+that build: every plane of every frame must equal the oracle bit for bit there too.  It checks what the kernels COMPUTE
+(indexing, pass wiring, scatter resolve, tiling, upscalers, instance updates); how they run on a B200 is what `-m gpu` on the
+device checks.  The emulated build is test infrastructure: the package never loads it (tests/conftest.py swaps the library
+path only when HK_EMULATE_KERNELS is set)."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+from tests.conftest import ROOT
+
+FILES = ["tests/test_gpu_parity.py", "tests/test_gpu_variants.py", "tests/test_gpu_upscale.py", "tests/test_gpu_dynamic.py",
+         "tests/test_gpu_frame_assembly.py", "tests/test_gpu_zz_examples.py"]
+
+
+def test_gpu_parity_suite_passes_on_emulated_kernels():
+    if not shutil.which("g++") and not os.path.exists("/usr/bin/g++"):
+        pytest.skip("no host C++ compiler")
+    env = dict(os.environ, HK_EMULATE_KERNELS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + FILES, cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=1500)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0, tail
+    assert " passed" in tail and "failed" not in tail, tail

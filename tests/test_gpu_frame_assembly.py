@@ -82,6 +82,8 @@ def _ipc_worker(handle, tile, frames, conn):
 def test_frame_target_across_processes_cuda_ipc():
     """The owner process allocates the frame and renders tile 0; a second process maps the frame through its IPC handle
     and renders tile 1 into it (both on cuda:0 here; across GPUs the same calls go over NVLink)."""
+    from tests.conftest import needs_real_gpu
+    needs_real_gpu()
     b = Bench("cornell", W, H, config="cornell_1080p")
     full = b.device()
     local = b.device(TILES[0][2], TILES[0][3], TILES[0][0], TILES[0][1])

@@ -139,6 +139,8 @@ def test_scene_upload_rejects_out_of_range_references():
 def test_pipelined_readback_equals_blocking():
     """hk_readback_async / hk_readback_wait: frame n's image lands in pinned host memory while frame n + 1 renders, and is
     byte-identical to the blocking read-back of the same frame; the next frame's tone-map write waits for the copy."""
+    from tests.conftest import needs_real_gpu
+    needs_real_gpu()
     import torch
     b = Bench("cornell", 160, 96, config="cornell_1080p")
     a, c = b.device(), b.device()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Build tuning variants of libhikari_b200.so here (nvcc cross-compiles without a GPU) into bevy_hikari_b200/variants/,
-so that one gpurun call can time them all:  HK_LIB=bevy_hikari_b200/variants/<name>.so python bench.py ...
+so that one gpurun call can time them all:  python bench.py --lib bevy_hikari_b200/variants/<name>.so ...
 usage: tools/build_variants.py name='-DFLAG=.. -DFLAG2=..' [name2=...]"""
 import os
 import shutil

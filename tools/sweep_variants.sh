@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs ON THE GPU BOX: times every prebuilt tuning variant (tools/build_variants.py) with a short bench run.
 for so in bevy_hikari_b200/variants/*.so; do
-  HK_LIB=$PWD/$so python bench.py --steps 16 --warmup 4 --no-cpu-baseline 2>/dev/null | grep "^{" | tail -1 | python -c "
+  python bench.py --lib $PWD/$so --steps 16 --warmup 4 --no-cpu-baseline 2>/dev/null | grep "^{" | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
 k = d['kernel_ms']
