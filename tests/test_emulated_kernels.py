@@ -26,3 +26,17 @@ def test_gpu_parity_suite_passes_on_emulated_kernels():
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
     assert r.returncode == 0, tail
     assert " passed" in tail and "failed" not in tail, tail
+
+
+@pytest.mark.parametrize("mode,first,count", [("frames", 5000, 40), ("tiles", 7000, 15)])
+def test_randomised_parity_campaign_on_emulated_kernels(mode, first, count):
+    """tools/fuzz_parity.py with fixed seeds: random scene, size (down to 1 x 1), settings, upscale ratio, camera motion and
+    instance animation (frames); random tile partitions against the unsharded frame (tiles)."""
+    if not os.path.exists("/usr/bin/g++") and not shutil.which("g++"):
+        pytest.skip("no host C++ compiler")
+    env = dict(os.environ, HK_EMULATE_KERNELS="1")
+    if mode == "tiles":
+        env["HK_FUZZ_TILES"] = "1"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), str(first), str(count)], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
