@@ -611,6 +611,11 @@ int hk_prepass_run(hk_context* ctx, const hk_frame_inputs* in) {
 int hk_light_run(hk_context* ctx, const hk_frame_inputs* in) {
     KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
     ctx->launches = 0;
+    // LightNode::run starts with full_screen_albedo (light.rs:645-653).  hk_render_frame has it fused into the G-buffer
+    // kernel; the stand-alone node recomputes it from whatever G-buffer is current (e.g. one supplied with hk_upload_state).
+    rows_deferred(ctx, P, GHOST_TEMPORAL);
+    hk_launch_albedo(P, ctx->stream);
+    ctx->launches += 1;
     return run_light(ctx, P);
 }
 int hk_post_process_run(hk_context* ctx, const hk_frame_inputs* in) {

@@ -241,6 +241,38 @@ def simple():
                      sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 4.0, math.pi / 4.0, 0.0)))
 
 
+def samplers():
+    """Test scene for the texture path (mod.rs:760-799 binds every texture with its own sampler): one ground plane whose
+    uvs run from -1 to 2 so that addressing matters, textured four times over with the earth image under different samplers
+    (repeat / clamp / mirror, linear / nearest, sRGB / linear data), lit by a small emissive sphere with a mirrored emissive
+    texture and the sun."""
+    earth = np.load(os.path.join(SCENES, "earth.npz"))["rgba"][::4, ::4].copy()    # 128 x 64 keeps texels visible
+    combos = [(0, 0, 1, 1), (1, 2, 0, 1), (2, 1, 1, 0), (2, 0, 0, 0)]             # (mode_u, mode_v, linear, srgb); 0 repeat, 1 clamp, 2 mirror
+    textures = [{"rgba": earth, "address_mode_u": u, "address_mode_v": v, "filter_linear": lin, "srgb": srgb} for u, v, lin, srgb in combos]
+    textures.append({"rgba": earth, "address_mode_u": 2, "address_mode_v": 2, "filter_linear": 1, "srgb": 1})
+    pos, nrm, uv, idx = _plane_mesh(1.0)
+    uv = (uv * 3.0 - 1.0).astype(F)
+    meshes = [(pos, nrm, uv, idx), _uv_sphere_mesh(0.5, 24, 12)]
+    mats = []
+    for t in range(4):
+        m = _std_material((1, 1, 1, 1), rough=0.7)
+        m["base_color_texture"] = t
+        mats.append(m)
+    light = _std_material((1, 1, 1, 1), emissive=(1.0, 0.9, 0.8, 0.4))
+    light["emissive_texture"] = 4
+    light["base_color_texture"] = 4
+    mats.append(light)
+    inst_mesh = [0, 0, 0, 0, 1]
+    inst_mat = [0, 1, 2, 3, 4]
+    xf = [_translation(-1.5, 0.0, -1.5, (3.0, 1.0, 3.0)), _translation(1.5, 0.0, -1.5, (3.0, 1.0, 3.0)),
+          _translation(-1.5, 0.0, 1.5, (3.0, 1.0, 3.0)), _translation(1.5, 0.0, 1.5, (3.0, 1.0, 3.0))]
+    m = _ROT_X_NEG_90.copy()
+    m[3, :3] = (0.0, 0.9, 0.0)
+    xf.append(m.reshape(16))
+    return SceneData(meshes, np.array(mats, L.MATERIAL), textures, inst_mesh, inst_mat, xf, eye=(0.0, 3.5, 5.5), target=(0.0, 0.0, 0.0),
+                     sun_illuminance=6000.0, sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 3.0, math.pi / 6.0, 0.0)))
+
+
 def terrain(n=224, seed=7):
     """Stress scene, not a reference example: one n x n-quad displaced grid (2 n^2 triangles — 100 352 at n = 224, the size
     class of the reference's scene.gltf) under a small emissive sphere and the sun; exercises a deep
@@ -273,7 +305,7 @@ def terrain(n=224, seed=7):
                      sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 3.0, math.pi / 5.0, 0.0)))
 
 
-SCENE_BUILDERS = {"cornell": cornell, "city": city, "terrain": terrain, "minimal": minimal, "simple": simple}
+SCENE_BUILDERS = {"cornell": cornell, "city": city, "terrain": terrain, "minimal": minimal, "simple": simple, "samplers": samplers}
 
 # BASELINE.json configs.  All run with Upscale::SmaaTu4x{ratio 1.0}, Taa::None so that the render
 # resolution equals the stated resolution.

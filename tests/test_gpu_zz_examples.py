@@ -45,3 +45,58 @@ def test_simple_example_two_rotating_emissives():
         orc.render_frame(inp)
         compare_all(dev, orc, ALL_PLANES + DENOISED, f)
     assert float(dev.readback(L.OUT_RENDER_EMISSIVE).astype(np.float32)[..., :3].mean()) > 0.005
+
+
+def test_texture_samplers_bit_exact():
+    """every sampler state the texture path distinguishes: repeat / clamp / mirror addressing on either axis, linear and
+    nearest filtering, sRGB and linear data, uvs from -1 to 2 (scenes.samplers)"""
+    b = Bench("samplers", 128, 80, taa=plugin.TAA_NONE, upscale_ratio=1.0, indirect_bounces=2, emissive_spatial_reuse=1)
+    dev, orc = b.device(), b.oracle()
+    dev.set_keep_intermediates(True)
+    for f in range(1, 7):
+        inp = b.moving_inputs(f)
+        dev.render_frame(inp)
+        orc.render_frame(inp)
+        compare_all(dev, orc, ALL_PLANES + DENOISED, f)
+    albedo = dev.readback(L.OUT_ALBEDO).astype(np.float32)[..., :3]
+    inst = np.floor(dev.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)[..., 0]).astype(int)
+    hit = dev.readback(L.OUT_GBUFFER_POSITION)[..., 3] > 0
+    for k in range(4):          # all four differently sampled quadrants are visible and textured (not a flat colour)
+        m = hit & (inst == k)
+        assert m.sum() > 200 and albedo[m].std(axis=0).max() > 0.02, k
+
+
+def test_api_corners():
+    """entry points and refusals the parity tests do not reach"""
+    from bevy_hikari_b200 import _ffi
+    import ctypes as C
+    lib = _ffi.lib()
+    b = Bench("cornell", 48, 32, config="cornell_256")
+    with pytest.raises(_ffi.HikariError, match="tile rectangle"):
+        plugin.HikariPlugin(48, 32, 0, 20, 10)                      # row_begin > row_end
+    with pytest.raises(_ffi.HikariError, match="tile rectangle"):
+        plugin.HikariPlugin(48, 32, 0, 0, 32, None, 0, 64)          # col_end beyond the frame
+    t = b.device(8, 24, 16, 40)
+    allocated, owned = (C.c_uint32 * 4)(), (C.c_uint32 * 4)()
+    assert lib.hk_tile_rect(t.ctx, allocated, owned) == 0
+    assert list(owned) == [16, 40, 8, 24] and list(allocated) == [0, 48, 0, 32]      # +-36 ghost pixels, clamped to the frame
+    a0, a1 = C.c_uint32(), C.c_uint32()
+    assert lib.hk_band_rows(t.ctx, C.byref(a0), C.byref(a1)) == 0 and (a0.value, a1.value) == (0, 32)
+    assert lib.hk_version().startswith(b"hikari_b200")
+    bad = b.inputs(1)
+    bad.frame.direct_validate_interval = 0
+    with pytest.raises(_ffi.HikariError, match="validate interval"):
+        t.render_frame(bad)
+    bufs = b.world.buffers()
+    desc = plugin.scene_desc_from_buffers(bufs)
+    desc.instances = None                                           # count without a pointer
+    with pytest.raises(_ffi.HikariError, match="NULL"):
+        t.update_instances_desc(desc)
+    with pytest.raises(_ffi.HikariError, match="unknown plane"):
+        t.readback_into(99, 0x1000, 16)
+    # per-pass timing and stats are filled when asked for
+    t.set_profiling(True, True)
+    t.render_frame(b.inputs(1))
+    st = t.stats()
+    assert st.kernel_launches == 9 and st.primary_rays == 16 * 24 and st.tlas_rays > 0     # cornell_256: no denoise, no emissive spatial pass
+    assert st.ms_total >= 0.0 and all(m >= 0.0 for m in st.ms_kernel)
