@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE: build tests/emu/_build/libhikari_emu.so — the kernel sources of bevy_hikari_b200/csrc compiled for
 the host through tests/emu/cuda_emu.h, behind the same C ABI, so that the kernels' logic can be compared with the oracle
-without a GPU (tests/test_emulated_kernels.py; HK_LIB=<this library> runs any `-m gpu` test on the CPU during development).
+without a GPU (tests/test_emulated_kernels.py; HK_EMULATE_KERNELS=1 pytest -m gpu ... runs any GPU test on the CPU during development).
 The only source transformations are
   * `kernel<<<grid, block, 0, stream>>>(args)`  ->  `EMU_LAUNCH(grid, block, kernel(args))`
   * flush_counters' warp reduction (shuffles) -> one atomic add per thread (same totals)."""
