@@ -10,6 +10,10 @@
 #include "hk_device.cuh"
 #include "hk_kernels.h"
 
+#ifndef HK_DENOISE_BRANCHFREE
+#define HK_DENOISE_BRANCHFREE 0
+#endif
+
 namespace hkd {
 
 __device__ __forceinline__ vec4 load16(const uint2* plane, size_t i) {
@@ -156,6 +160,50 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
         // tap order of denoise.wgsl:252-268
         const int OX[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
         const int OY[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+#if HK_DENOISE_BRANCHFREE
+        // Tuning variant (off by default; validated bit-exact on the emulated kernels, not yet timed on a GPU): every tap's
+        // loads are unconditional — out-of-frame taps read a clamped, valid address — and go through the read-only path, so
+        // nothing but register pressure keeps the compiler from issuing the loads of later taps during the arithmetic of
+        // earlier ones; only the accumulation is predicated.  Same operations on the same values for every tap that counts.
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int ox = OX[t], oy = OY[t];
+            const int sx = x + ox * STEP, sy = y + oy * STEP;
+            const bool valid = !(sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH);
+            const size_t sidx = render_index(P.band, min(max(sx, 0), P.band.RW - 1), min(max(sy, 0), P.band.RH - 1));
+            const float4 sample_geometry = __ldg(&P.planes.dn_geometry[sidx]);
+            const float sample_instance = __ldg(&P.planes.dn_instance[sidx]);
+            uint2 bits[3];
+#pragma unroll
+            for (int sgl = 0; sgl < 3; ++sgl) bits[sgl] = (sgl < signals) ? __ldg(&P.planes.dn_internal[LEVEL][sgl][sidx]) : make_uint2(0u, 0u);
+            const vec3 sample_normal = f4xyz(sample_geometry);
+            const float sample_depth = sample_geometry.w;
+            const float w_normal = pow16(fmax_(0.0f, dot(normal, sample_normal)));
+            const float w_depth = exp_((-fabsf(depth - sample_depth)) / (fabsf(dot(depth_gradient, v2((float)ox, (float)oy))) + 0.01f));
+            const float w_instance = fmax_(0.0f, 1.0f - fabsf(instance - sample_instance));
+            const float w_geometry = w_normal * w_depth * w_instance;
+            const float k = kernel_at(P, oy + 1, ox + 1);
+#pragma unroll
+            for (int sgl = 0; sgl < 3; ++sgl) {
+                if (sgl >= signals) continue;
+                SignalAcc& a = acc[sgl];
+                uvec2 q; q.x = bits[sgl].x; q.y = bits[sgl].y;
+                vec3 irr = xyz(unpack_rgba16f(q));
+                float sample_luminance = luminance(irr);
+                float w_luminance = exp_((-fabsf(a.lum - sample_luminance)) / a.lum_denominator);
+                float w = clampf(w_geometry * w_luminance, 0.0f, 1.0f) * k;
+                if (valid && !bad3(irr)) {
+                    a.sum_irradiance = a.sum_irradiance + irr * w;
+                    a.sum_w += w;
+                    if (sgl != 0) {
+                        a.ff_moment_1 += sample_luminance;
+                        a.ff_moment_2 += sample_luminance * sample_luminance;
+                        a.ff_count += 1.0f;
+                    }
+                }
+            }
+        }
+#else
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             const int ox = OX[t], oy = OY[t];
@@ -190,6 +238,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
                 }
             }
         }
+
+#endif
 
         vec4 albedo = v4(1.0f);
         if (LEVEL == 3) albedo = load16(P.planes.albedo, gidx);

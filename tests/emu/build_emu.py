@@ -20,7 +20,8 @@ CU = ["context.cu", "kernels_light.cu", "kernels_post.cu", "kernels_upscale.cu"]
 CPP = ["hikari.cpp", "hikari_capi.cpp"]
 CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 FLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-std=c++17", "-w",
-         "-I" + os.path.join(HERE, "include"), "-I" + SRC, "-I" + HOST, "-I" + os.path.join(ROOT, "include")]
+         "-I" + os.path.join(HERE, "include"), "-I" + SRC, "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + \
+        os.environ.get("HK_EMU_EXTRA", "").split()      # e.g. -DHK_DENOISE_BRANCHFREE=1: validate a tuning variant's logic
 
 LAUNCH = re.compile(r"([A-Za-z_][A-Za-z_0-9]*(?:<[^<>;]*>)?)<<<([^;]*?)>>>\(([^;]*)\);")
 FLUSH_OLD = re.compile(r"for \(int o = 16; o > 0; o >>= 1\) \{.*?\n    \}\n    if \(\(threadIdx\.x & 31\) == 0\) \{", re.S)
@@ -63,7 +64,7 @@ def build(force=False):
     deps = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(HOST, f) for f in os.listdir(HOST)] + \
            [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))] + \
            [os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__)]
-    if not force and not newer(LIB, deps):
+    if not force and not newer(LIB, deps) and not os.environ.get("HK_EMU_EXTRA"):
         return LIB
     objs, launches = [], 0
     for f in CU:
