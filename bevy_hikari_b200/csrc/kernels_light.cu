@@ -5,6 +5,10 @@
 #include "hk_device.cuh"
 #include "hk_kernels.h"
 
+#ifndef HK_SPATIAL_EAGER_LOAD
+#define HK_SPATIAL_EAGER_LOAD 0
+#endif
+
 namespace hkd {
 
 template <bool COUNT>
@@ -529,10 +533,24 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
         // (size + 0.5) / size >= 1 + 2^-23 survive rounding), so the two IEEE divisions per neighbour are not needed.
         if (sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH) continue;
         const size_t sidx = render_index(P.band, sx, sy);
+#if HK_SPATIAL_EAGER_LOAD
+        // Tuning variant (off by default; logic validated on the emulated kernels, not yet timed): the neighbour's reservoir
+        // is requested together with its depth instead of after the depth test, so a neighbour exposes one load latency
+        // instead of two; rejected neighbours cost 64 bytes of L1/L2 traffic more.
+        const float* depth_ptr = &P.planes.pos_depth[light_gbuffer_index(P, sx, sy, sidx)].w;
+        const float sample_depth = __ldg(depth_ptr);
+        PackedQuarters packed;
+        packed.q0 = __ldg(&B.reservoir.q[0][sidx]); packed.q1 = __ldg(&B.reservoir.q[1][sidx]);
+        packed.q2 = __ldg(&B.reservoir.q[2][sidx]); packed.q3 = __ldg(&B.reservoir.q[3][sidx]);
+        float depth_ratio = depth / sample_depth;
+        if (depth_ratio < 0.9f || depth_ratio > 1.1f) continue;
+        q = unpack_reservoir(packed);
+#else
         const float sample_depth = P.planes.pos_depth[light_gbuffer_index(P, sx, sy, sidx)].w;
         float depth_ratio = depth / sample_depth;
         if (depth_ratio < 0.9f || depth_ratio > 1.1f) continue;
         q = unpack_reservoir(load_quarters(B.reservoir, sidx));
+#endif
         bool normal_miss = dot(s.visible_normal, q.s.visible_normal) < 0.866f;
         if (q.count < F32_EPSILON || normal_miss) continue;
         vec3 sample_direction = normalize(xyz(q.s.sample_position) - xyz(s.visible_position));
