@@ -47,6 +47,8 @@ SYMBOLS = {
     "hk_readback": (_I, [_P, _I, _P, _SZ]),
     "hk_readback_async": (_I, [_P, _I, _P, _SZ]),
     "hk_readback_wait": (_I, [_P]),
+    "hk_context_set_motion_margin": (_I, [_P, _U32]),
+    "hk_halo_pull": (_I, [_P, _P]),
     "hk_set_frame_target": (_I, [_P, _P, _U32]),
     "hk_frame_alloc": (_I, [_P, C.POINTER(_P), _P]),
     "hk_frame_open": (_I, [_P, _P, C.POINTER(_P)]),

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <unordered_set>
 #include <vector>
@@ -48,6 +49,7 @@ struct hk_context {
     bool copy_in_flight = false;      // a copy has been queued and the compute stream has not yet been ordered behind it
     bool copy_unwaited = false;       // ... and the host has not waited for it
     uint2* frame_target = nullptr; uint32_t frame_pitch = 0;   // hk_set_frame_target
+    int motion_margin = 0;            // extra ghost pixels for exact tiling under camera motion (hk_context_set_motion_margin)
     std::vector<void*> frames_owned, frames_opened;            // hk_frame_alloc / hk_frame_open
     float trace_ms = 0.0f;            // kernel time of the last hk_trace_rays (ms_kernel[HK_K_TRACE_RAYS])
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -95,10 +97,11 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     free_list(ctx->allocations);
     Band b;
     b.W = (int)width; b.H = (int)height; b.r0 = (int)row_begin; b.r1 = (int)row_end; b.cx0 = (int)col_begin; b.cx1 = (int)col_end;
-    b.a0 = b.r0 - GHOST_TEMPORAL < 0 ? 0 : b.r0 - GHOST_TEMPORAL;
-    b.a1 = b.r1 + GHOST_TEMPORAL > b.H ? b.H : b.r1 + GHOST_TEMPORAL;
-    b.ax0 = b.cx0 - GHOST_TEMPORAL < 0 ? 0 : b.cx0 - GHOST_TEMPORAL;
-    b.ax1 = b.cx1 + GHOST_TEMPORAL > b.W ? b.W : b.cx1 + GHOST_TEMPORAL;
+    const int ghost = GHOST_TEMPORAL + ctx->motion_margin;
+    b.a0 = b.r0 - ghost < 0 ? 0 : b.r0 - ghost;
+    b.a1 = b.r1 + ghost > b.H ? b.H : b.r1 + ghost;
+    b.ax0 = b.cx0 - ghost < 0 ? 0 : b.cx0 - ghost;
+    b.ax1 = b.cx1 + ghost > b.W ? b.W : b.cx1 + ghost;
     b.AW = b.ax1 - b.ax0;
     b.RW = b.W; b.RH = b.H; b.RS = b.AW;
     ctx->band = b;
@@ -548,20 +551,20 @@ static int run_prepass(hk_context* ctx, KParams& P) {
     P.gbuffer_current = ctx->gbuffer_current;
     P.planes.pos_depth = ctx->planes.pos_depth_db[ctx->gbuffer_current];
     P.planes.velocity_uv = ctx->planes.velocity_uv_db[ctx->gbuffer_current];
-    rows_deferred(ctx, P, GHOST_TEMPORAL);
+    rows_deferred(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     { KernelTimer t(ctx, HK_K_GBUFFER); hk_launch_gbuffer(P, ctx->count_rays, ctx->stream); }
     return check_launch(ctx);
 }
 static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, light.rs:645-699 (albedo is fused in the prepass)
     const hk_frame_uniform& f = P.in.frame;
-    rows(ctx, P, GHOST_TEMPORAL);
+    rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     // each temporal pass is followed by the resolve of its scatter writes (all allocated rows can be targets)
     { KernelTimer t(ctx, HK_K_DIRECT); hk_launch_direct(P, false, ctx->count_rays, ctx->stream);
       hk_launch_scatter_resolve(P, 0, ctx->stream); ctx->launches += 1; }
     { KernelTimer t(ctx, HK_K_EMISSIVE); hk_launch_direct(P, true, ctx->count_rays, ctx->stream);
       hk_launch_scatter_resolve(P, 1, ctx->stream); ctx->launches += 1; }
     if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_EMISSIVE_SPATIAL); hk_launch_spatial(P, true, ctx->stream); }
-    rows(ctx, P, GHOST_TEMPORAL);
+    rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     { KernelTimer t(ctx, HK_K_INDIRECT); hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
       hk_launch_scatter_resolve(P, 2, ctx->stream); ctx->launches += 1; }
     if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); hk_launch_spatial(P, false, ctx->stream); }
@@ -613,7 +616,7 @@ int hk_light_run(hk_context* ctx, const hk_frame_inputs* in) {
     ctx->launches = 0;
     // LightNode::run starts with full_screen_albedo (light.rs:645-653).  hk_render_frame has it fused into the G-buffer
     // kernel; the stand-alone node recomputes it from whatever G-buffer is current (e.g. one supplied with hk_upload_state).
-    rows_deferred(ctx, P, GHOST_TEMPORAL);
+    rows_deferred(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     hk_launch_albedo(P, ctx->stream);
     ctx->launches += 1;
     return run_light(ctx, P);
@@ -834,6 +837,41 @@ int hk_readback_async(hk_context* ctx, int which, void* pinned_host, size_t byte
     ctx->copy_unwaited = true;
     return HK_OK;
 }
+// ------------------------------------------------------------------------------------------ halo exchange
+int hk_context_set_motion_margin(hk_context* ctx, uint32_t pixels) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    if (pixels > 256u) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "motion margin above 256 pixels");
+    HK_CUDA(cudaSetDevice(ctx->device));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->motion_margin = (int)pixels;
+    const Band b = ctx->band;
+    return allocate_planes(ctx, (uint32_t)b.W, (uint32_t)b.H, (uint32_t)b.cx0, (uint32_t)b.cx1, (uint32_t)b.r0, (uint32_t)b.r1);
+}
+int hk_halo_pull(hk_context* dst, hk_context* src) {
+    if (!dst || !src) return HK_ERR_INVALID_ARGUMENT;
+    if (dst == src) return HK_OK;
+    hk_context* ctx = dst;   // errors are reported on the pulling context
+    const Band& d = dst->band;
+    const Band& s = src->band;
+    if (d.W != s.W || d.H != s.H) return set_error(dst, HK_ERR_INVALID_ARGUMENT, "hk_halo_pull: the two contexts render different frames");
+    // what `src` owns of `dst`'s allocation (tiles of one partition do not overlap, so this is ghost territory of `dst`)
+    const int x0 = std::max(d.ax0, s.cx0), x1 = std::min(d.ax1, s.cx1), y0 = std::max(d.a0, s.r0), y1 = std::min(d.a1, s.r1);
+    if (x0 >= x1 || y0 >= y1) return HK_OK;
+    if (x0 < d.cx1 && x1 > d.cx0 && y0 < d.r1 && y1 > d.r0)
+        return set_error(dst, HK_ERR_INVALID_ARGUMENT, "hk_halo_pull: the owned rectangles of the two contexts overlap");
+    HK_CUDA(cudaSetDevice(dst->device));
+    if (src->device != dst->device) {
+        int can = 0;
+        HK_CUDA(cudaDeviceCanAccessPeer(&can, dst->device, src->device));
+        if (!can) return set_error(dst, HK_ERR_UNSUPPORTED, "no peer access between the two contexts' GPUs");
+        cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) HK_CUDA(e);
+        cudaGetLastError();
+    }
+    hk_launch_halo_copy(dst->planes, d, src->planes, s, x0, x1, y0, y1, dst->stream);
+    return check_launch(dst);
+}
+
 // ------------------------------------------------------------------------------------------ frame assembly
 int hk_set_frame_target(hk_context* ctx, void* frame_device_ptr, uint32_t pitch_pixels) {
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;

@@ -302,6 +302,25 @@ __global__ void __launch_bounds__(CTA_THREADS) k_tone_mapping(const __grid_const
     store_final(P, x, y, color);
 }
 
+// --------------------------------------------------------------------------------------------- halo copy
+// One thread per pixel of the rectangle and per reservoir buffer: 4 x 16-byte loads from the owner's planes (peer memory
+// when the owner is another GPU), 4 stores into this tile's ghost ring.
+struct HaloArgs {
+    ReservoirPlanes dst[10], src[10];
+    Band dst_band, src_band;
+    int x0, y0, w, h;
+};
+__global__ void __launch_bounds__(256) k_halo_copy(const __grid_constant__ HaloArgs A) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)A.w * (size_t)A.h;
+    if (i >= n) return;
+    const int x = A.x0 + (int)(i % (size_t)A.w), y = A.y0 + (int)(i / (size_t)A.w);
+    const size_t si = band_index(A.src_band, x, y), di = band_index(A.dst_band, x, y);
+    const int r = (int)blockIdx.y;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) A.dst[r].q[q][di] = A.src[r].q[q][si];
+}
+
 static dim3 grid_for(const KParams& P) {
     int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
     return dim3((unsigned)((cols + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
@@ -327,6 +346,16 @@ void hk_launch_denoise_level(const KParams& P, int level, int signals, bool fuse
             if (fuse_tone_mapping) k_denoise<3, true><<<g, CTA_THREADS, 0, st>>>(P, signals, keep);
             else k_denoise<3, false><<<g, CTA_THREADS, 0, st>>>(P, signals, keep);
     }
+}
+void hk_launch_halo_copy(const Planes& dst, const Band& dst_band, const Planes& src, const Band& src_band, int x0, int x1, int y0, int y1,
+                         cudaStream_t st) {
+    if (x1 <= x0 || y1 <= y0) return;
+    HaloArgs a;
+    for (int r = 0; r < 10; ++r) { a.dst[r] = dst.reservoir[r]; a.src[r] = src.reservoir[r]; }
+    a.dst_band = dst_band; a.src_band = src_band;
+    a.x0 = x0; a.y0 = y0; a.w = x1 - x0; a.h = y1 - y0;
+    const size_t n = (size_t)a.w * (size_t)a.h;
+    k_halo_copy<<<dim3((unsigned)((n + 255) / 256), 10u, 1u), 256, 0, st>>>(a);
 }
 void hk_launch_tone_mapping(const KParams& P, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;

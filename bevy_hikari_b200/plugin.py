@@ -254,6 +254,13 @@ class HikariPlugin:
     def readback_wait(self):
         check(lib().hk_readback_wait(self.ctx), self.ctx)
 
+    # exact tiling under camera motion
+    def set_motion_margin(self, pixels):
+        check(lib().hk_context_set_motion_margin(self.ctx, int(pixels)), self.ctx)
+
+    def halo_pull(self, source):
+        check(lib().hk_halo_pull(self.ctx, source.ctx), self.ctx)
+
     # frame assembly across tiles / GPUs (hk_set_frame_target)
     def frame_alloc(self):
         p = C.c_void_p()

@@ -193,6 +193,15 @@ int hk_readback_wait(hk_context* ctx);
 int hk_upload_state(hk_context* ctx, int which, const void* host, size_t bytes);  /* inverse of hk_readback (tests) */
 int hk_sync(hk_context* ctx);
 
+/* Exact tiling under camera motion.  A tile's ghost pixels compute their own temporal history, which is exact only while
+ * the camera is static.  hk_halo_pull(dst, src), called after both contexts have finished a frame (and before either
+ * starts the next), overwrites the reservoirs of `dst`'s ghost pixels that `src` owns with `src`'s values (stream-ordered
+ * on `dst`; `src` may be on a peer GPU of the same process).  With every neighbour pulled, the next frame's temporal passes
+ * read exactly what an unsharded render would, provided the per-frame reprojection stays within the motion margin:
+ * hk_context_set_motion_margin widens the ghost ring from 36 to 36 + `pixels` (re-allocates and clears the tile's state). */
+int hk_context_set_motion_margin(hk_context* ctx, uint32_t pixels);
+int hk_halo_pull(hk_context* dst, hk_context* src);
+
 /* Frame assembly for tiled (multi-GPU) rendering.  With a frame target set, every owned pixel of the tone-mapped image is
  * also stored into the full-frame Rgba16Float buffer `frame` (pitch in pixels) at its position in the frame, by the last
  * kernel of hk_render_frame / hk_post_process_run itself.  `frame` may live on another GPU — same process (peer access is

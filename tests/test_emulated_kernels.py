@@ -14,7 +14,7 @@ import pytest
 from tests.conftest import ROOT
 
 FILES = ["tests/test_gpu_parity.py", "tests/test_gpu_variants.py", "tests/test_gpu_upscale.py", "tests/test_gpu_dynamic.py",
-         "tests/test_gpu_frame_assembly.py", "tests/test_gpu_zz_examples.py"]
+         "tests/test_gpu_frame_assembly.py", "tests/test_gpu_zz_examples.py", "tests/test_gpu_zz_halo.py"]
 
 
 def test_gpu_parity_suite_passes_on_emulated_kernels():
@@ -28,7 +28,7 @@ def test_gpu_parity_suite_passes_on_emulated_kernels():
     assert " passed" in tail and "failed" not in tail, tail
 
 
-@pytest.mark.parametrize("mode,first,count", [("frames", 5000, 40), ("tiles", 7000, 15)])
+@pytest.mark.parametrize("mode,first,count", [("frames", 5000, 40), ("tiles", 7000, 15), ("halo", 9000, 12)])
 def test_randomised_parity_campaign_on_emulated_kernels(mode, first, count):
     """tools/fuzz_parity.py with fixed seeds: random scene, size (down to 1 x 1), settings, upscale ratio, camera motion and
     instance animation (frames); random tile partitions against the unsharded frame (tiles)."""
@@ -37,6 +37,8 @@ def test_randomised_parity_campaign_on_emulated_kernels(mode, first, count):
     env = dict(os.environ, HK_EMULATE_KERNELS="1")
     if mode == "tiles":
         env["HK_FUZZ_TILES"] = "1"
+    if mode == "halo":      # random partitions, moving camera, motion margin + hk_halo_pull after every frame
+        env["HK_FUZZ_HALO"] = "1"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), str(first), str(count)], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]

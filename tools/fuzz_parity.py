@@ -79,9 +79,19 @@ def tile_case(seed):
     rects = [(x0, x1, y0, y1) for x0, x1 in zip(xs[:-1], xs[1:]) for y0, y1 in zip(ys[:-1], ys[1:])]
     full = b.device()
     tiles = [b.device(r[2], r[3], r[0], r[1]) for r in rects]
+    halo = bool(os.environ.get("HK_FUZZ_HALO"))       # moving camera + motion margin + halo pulls after every frame
+    step = tuple(rng.uniform(-0.05, 0.05, 3)) if halo else (0.0, 0.0, 0.0)
+    if halo:
+        for t in tiles:
+            t.set_motion_margin(16)
     planes = [L.OUT_TONE_MAPPED, L.OUT_RENDER_DIRECT, L.OUT_RENDER_EMISSIVE, L.OUT_RENDER_INDIRECT] + [L.OUT_RESERVOIR_0 + i for i in range(10)]
     for f in range(1, int(rng.integers(3, 7))):
-        inp = b.inputs(f)
+        if f > 1 and halo:
+            for t in tiles:
+                for other in tiles:
+                    if other is not t:
+                        t.halo_pull(other)
+        inp = b.moving_inputs(f, step=step)
         full.render_frame(inp)
         for t in tiles:
             t.render_frame(inp)
@@ -99,7 +109,7 @@ if __name__ == "__main__":
     failures = 0
     for seed in range(first, first + count):
         try:
-            msg = tile_case(seed) if os.environ.get("HK_FUZZ_TILES") else one_case(seed)
+            msg = tile_case(seed) if (os.environ.get("HK_FUZZ_TILES") or os.environ.get("HK_FUZZ_HALO")) else one_case(seed)
         except Exception as e:   # API errors are findings too
             msg = f"seed {seed}: exception {e!r}"
         if msg:
