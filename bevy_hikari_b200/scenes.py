@@ -273,6 +273,53 @@ def samplers():
                      sun_illuminance=6000.0, sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 3.0, math.pi / 6.0, 0.0)))
 
 
+def soup(seed=0):
+    """Random test scene (tools/fuzz_parity.py): a handful of random triangle meshes — some triangles degenerate, some
+    meshes a single triangle — instanced with random rotations, non-uniform and mirrored scales, random materials, several of
+    them emissive, a random sun.  Nothing here comes from the reference; it exists to take both implementations off the
+    beaten path together."""
+    rng = np.random.default_rng(seed)
+    meshes, mats, inst_mesh, inst_mat, xf = [], [], [], [], []
+    for _ in range(int(rng.integers(2, 6))):
+        n_tris = int(rng.integers(1, 13))
+        centre = rng.uniform(-0.5, 0.5, 3)
+        pos = (centre + rng.uniform(-0.6, 0.6, (3 * n_tris, 3))).astype(F)
+        if n_tris > 2 and rng.integers(0, 2):
+            pos[3:6] = pos[3]                                        # a zero-area triangle
+        if n_tris > 4 and rng.integers(0, 2):
+            pos[7] = pos[6] + (pos[8] - pos[6]) * 0.5                # three collinear points
+        e1, e2 = pos[1::3] - pos[0::3], pos[2::3] - pos[0::3]
+        nrm = np.repeat(np.cross(e1, e2), 3, axis=0)
+        ln = np.linalg.norm(nrm, axis=1, keepdims=True)
+        nrm = np.where(ln > 1e-12, nrm / np.maximum(ln, 1e-12), np.array([[0.0, 1.0, 0.0]])).astype(F)
+        uv = rng.uniform(0, 1, (3 * n_tris, 2)).astype(F)
+        meshes.append((pos, nrm, uv, np.arange(3 * n_tris, dtype=np.uint32)))
+    for _ in range(int(rng.integers(2, 6))):
+        emissive = (0, 0, 0, 1)
+        if rng.integers(0, 3) == 0:
+            emissive = tuple(rng.uniform(0.2, 1.0, 3)) + (float(rng.uniform(0.01, 0.3)),)
+        mats.append(_std_material(tuple(rng.uniform(0.05, 1.0, 3)) + (1.0,), emissive=emissive, rough=float(rng.uniform(0.0, 1.0)),
+                                  metallic=float(rng.choice([0.0, 0.01, 0.5, 1.0])), refl=float(rng.uniform(0.0, 1.0))))
+    for _ in range(int(rng.integers(2, 9))):
+        inst_mesh.append(int(rng.integers(0, len(meshes)))); inst_mat.append(int(rng.integers(0, len(mats))))
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        scale = rng.uniform(0.3, 2.0, 3) * rng.choice([1.0, 1.0, -1.0], 3)
+        m = np.zeros((4, 4), F)
+        m[:3, :3] = (R * scale[None, :]).T          # rows of the array = columns of the matrix
+        m[3, :3] = rng.uniform(-1.5, 1.5, 3)
+        m[3, 3] = 1.0
+        xf.append(m.reshape(16))
+    sun = float(rng.choice([0.0, 3000.0, 20000.0]))
+    d = rng.normal(size=3); d[1] = abs(d[1]) + 0.2
+    return SceneData(meshes, np.array(mats, L.MATERIAL), [], inst_mesh, inst_mat, xf,
+                     eye=tuple(rng.uniform(-1.0, 1.0, 3) + np.array([0.0, 0.5, 4.0])), target=tuple(rng.uniform(-0.5, 0.5, 3)),
+                     sun_illuminance=sun if sun > 0 else None, sun_direction_to_light=tuple(d / np.linalg.norm(d)))
+
+
 def terrain(n=224, seed=7):
     """Stress scene, not a reference example: one n x n-quad displaced grid (2 n^2 triangles — 100 352 at n = 224, the size
     class of the reference's scene.gltf) under a small emissive sphere and the sun; exercises a deep

@@ -28,7 +28,7 @@ def test_gpu_parity_suite_passes_on_emulated_kernels():
     assert " passed" in tail and "failed" not in tail, tail
 
 
-@pytest.mark.parametrize("mode,first,count", [("frames", 5000, 40), ("tiles", 7000, 15), ("halo", 9000, 12)])
+@pytest.mark.parametrize("mode,first,count", [("frames", 5000, 40), ("tiles", 7000, 15), ("halo", 9000, 12), ("soup", 11000, 30)])
 def test_randomised_parity_campaign_on_emulated_kernels(mode, first, count):
     """tools/fuzz_parity.py with fixed seeds: random scene, size (down to 1 x 1), settings, upscale ratio, camera motion and
     instance animation (frames); random tile partitions against the unsharded frame (tiles)."""
@@ -37,6 +37,8 @@ def test_randomised_parity_campaign_on_emulated_kernels(mode, first, count):
     env = dict(os.environ, HK_EMULATE_KERNELS="1")
     if mode == "tiles":
         env["HK_FUZZ_TILES"] = "1"
+    if mode == "soup":      # random triangle soups: degenerate triangles, mirrored / non-uniform instances, several lights
+        env["HK_FUZZ_SOUP"] = "1"
     if mode == "halo":      # random partitions, moving camera, motion margin + hk_halo_pull after every frame
         env["HK_FUZZ_HALO"] = "1"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), str(first), str(count)], cwd=ROOT, env=env,

@@ -23,6 +23,10 @@ from tests.test_gpu_parity import ALL_PLANES, DENOISED, mismatch  # noqa: E402
 def one_case(seed):
     rng = np.random.default_rng(seed)
     scene = rng.choice(["cornell", "cornell", "city", "simple", "minimal"])
+    if os.environ.get("HK_FUZZ_SOUP"):      # random triangle soups (degenerate triangles, mirrored / non-uniform instances, several lights)
+        from bevy_hikari_b200 import scenes
+        scene = f"soup{seed}"
+        scenes.SCENE_BUILDERS[scene] = (lambda seed=seed: scenes.soup(seed))
     w, h = int(rng.integers(1, 97)), int(rng.integers(1, 73))
     ratio = float(rng.choice([1.0, 1.0, 1.0, 1.25, 1.5, 2.0]))
     settings = dict(
