@@ -49,6 +49,9 @@ SYMBOLS = {
     "hk_readback_wait": (_I, [_P]),
     "hk_context_set_motion_margin": (_I, [_P, _U32]),
     "hk_halo_pull": (_I, [_P, _P]),
+    "hk_halo_export": (_I, [_P, _P]),
+    "hk_halo_import": (_I, [_P, _P, C.POINTER(_P)]),
+    "hk_halo_pull_peer": (_I, [_P, _P]),
     "hk_set_frame_target": (_I, [_P, _P, _U32]),
     "hk_frame_alloc": (_I, [_P, C.POINTER(_P), _P]),
     "hk_frame_open": (_I, [_P, _P, C.POINTER(_P)]),

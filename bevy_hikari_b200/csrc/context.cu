@@ -22,6 +22,12 @@ static const int GHOST_DEMOD = 15, GHOST_L0 = 7, GHOST_L1 = 3, GHOST_L2 = 1;
 static const int GHOST_SPATIAL = GHOST_DEMOD + 1;           // 16
 static const int GHOST_TEMPORAL = GHOST_SPATIAL + 20;       // 36
 
+struct hk_halo_peer {   // a neighbour tile of another process, mapped through CUDA IPC (hk_halo_import)
+    Planes planes;       // only reservoir[] is filled
+    Band band;
+    void* mapped[40];
+};
+
 struct hk_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -51,6 +57,7 @@ struct hk_context {
     uint2* frame_target = nullptr; uint32_t frame_pitch = 0;   // hk_set_frame_target
     int motion_margin = 0;            // extra ghost pixels for exact tiling under camera motion (hk_context_set_motion_margin)
     std::vector<void*> frames_owned, frames_opened;            // hk_frame_alloc / hk_frame_open
+    std::vector<hk_halo_peer*> halo_peers;                     // hk_halo_import
     float trace_ms = 0.0f;            // kernel time of the last hk_trace_rays (ms_kernel[HK_K_TRACE_RAYS])
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[HK_K_COUNT][2] = {};   // per-kernel begin/end
@@ -234,6 +241,10 @@ void hk_context_destroy(hk_context* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (void* p : ctx->frames_opened) cudaIpcCloseMemHandle(p);
+    for (hk_halo_peer* peer : ctx->halo_peers) {
+        for (void* p : peer->mapped) if (p) cudaIpcCloseMemHandle(p);
+        delete peer;
+    }
     for (void* p : ctx->frames_owned) cudaFree(p);
     if (ctx->ev_submitted) cudaEventDestroy(ctx->ev_submitted);
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
@@ -838,6 +849,7 @@ int hk_readback_async(hk_context* ctx, int which, void* pinned_host, size_t byte
     return HK_OK;
 }
 // ------------------------------------------------------------------------------------------ halo exchange
+static int halo_rect(hk_context* ctx, const Band& d, const Band& s, int& x0, int& x1, int& y0, int& y1);
 int hk_context_set_motion_margin(hk_context* ctx, uint32_t pixels) {
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;
     if (pixels > 256u) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "motion margin above 256 pixels");
@@ -853,12 +865,10 @@ int hk_halo_pull(hk_context* dst, hk_context* src) {
     hk_context* ctx = dst;   // errors are reported on the pulling context
     const Band& d = dst->band;
     const Band& s = src->band;
-    if (d.W != s.W || d.H != s.H) return set_error(dst, HK_ERR_INVALID_ARGUMENT, "hk_halo_pull: the two contexts render different frames");
-    // what `src` owns of `dst`'s allocation (tiles of one partition do not overlap, so this is ghost territory of `dst`)
-    const int x0 = std::max(d.ax0, s.cx0), x1 = std::min(d.ax1, s.cx1), y0 = std::max(d.a0, s.r0), y1 = std::min(d.a1, s.r1);
+    int x0, x1, y0, y1;
+    int rc = halo_rect(dst, d, s, x0, x1, y0, y1);
+    if (rc != HK_OK) return rc;
     if (x0 >= x1 || y0 >= y1) return HK_OK;
-    if (x0 < d.cx1 && x1 > d.cx0 && y0 < d.r1 && y1 > d.r0)
-        return set_error(dst, HK_ERR_INVALID_ARGUMENT, "hk_halo_pull: the owned rectangles of the two contexts overlap");
     HK_CUDA(cudaSetDevice(dst->device));
     if (src->device != dst->device) {
         int can = 0;
@@ -870,6 +880,68 @@ int hk_halo_pull(hk_context* dst, hk_context* src) {
     }
     hk_launch_halo_copy(dst->planes, d, src->planes, s, x0, x1, y0, y1, dst->stream);
     return check_launch(dst);
+}
+
+static int halo_rect(hk_context* ctx, const Band& d, const Band& s, int& x0, int& x1, int& y0, int& y1) {
+    if (d.W != s.W || d.H != s.H) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "hk_halo_pull: the two contexts render different frames");
+    x0 = std::max(d.ax0, s.cx0); x1 = std::min(d.ax1, s.cx1); y0 = std::max(d.a0, s.r0); y1 = std::min(d.a1, s.r1);
+    if (x0 < x1 && y0 < y1 && x0 < d.cx1 && x1 > d.cx0 && y0 < d.r1 && y1 > d.r0)
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "hk_halo_pull: the owned rectangles of the two contexts overlap");
+    return HK_OK;
+}
+int hk_halo_export(hk_context* ctx, hk_halo_descriptor* out) {
+    if (!ctx || !out) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    for (int r = 0; r < 10; ++r)
+        for (int q = 0; q < 4; ++q) {
+            cudaIpcMemHandle_t h;
+            HK_CUDA(cudaIpcGetMemHandle(&h, ctx->planes.reservoir[r].q[q]));
+            memcpy(out->plane_handles[4 * r + q], &h, 64);
+        }
+    const Band& b = ctx->band;
+    out->frame[0] = b.W; out->frame[1] = b.H;
+    out->allocated[0] = b.ax0; out->allocated[1] = b.ax1; out->allocated[2] = b.a0; out->allocated[3] = b.a1;
+    out->owned[0] = b.cx0; out->owned[1] = b.cx1; out->owned[2] = b.r0; out->owned[3] = b.r1;
+    return HK_OK;
+}
+int hk_halo_import(hk_context* ctx, const hk_halo_descriptor* remote, hk_halo_peer** out) {
+    if (!ctx || !remote || !out) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    hk_halo_peer* peer = new hk_halo_peer();
+    memset(peer->mapped, 0, sizeof(peer->mapped));
+    Band& b = peer->band;
+    b = Band{};
+    b.W = remote->frame[0]; b.H = remote->frame[1];
+    b.ax0 = remote->allocated[0]; b.ax1 = remote->allocated[1]; b.a0 = remote->allocated[2]; b.a1 = remote->allocated[3];
+    b.cx0 = remote->owned[0]; b.cx1 = remote->owned[1]; b.r0 = remote->owned[2]; b.r1 = remote->owned[3];
+    b.AW = b.ax1 - b.ax0; b.RW = b.W; b.RH = b.H; b.RS = b.AW;
+    for (int i = 0; i < 40; ++i) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, remote->plane_handles[i], 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (void* m : peer->mapped) if (m) cudaIpcCloseMemHandle(m);
+            delete peer;
+            return set_error(ctx, HK_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        }
+        peer->mapped[i] = p;
+        peer->planes.reservoir[i / 4].q[i % 4] = static_cast<uint4*>(p);
+    }
+    ctx->halo_peers.push_back(peer);
+    *out = peer;
+    return HK_OK;
+}
+int hk_halo_pull_peer(hk_context* ctx, hk_halo_peer* peer) {
+    if (!ctx || !peer) return HK_ERR_INVALID_ARGUMENT;
+    int x0, x1, y0, y1;
+    int rc = halo_rect(ctx, ctx->band, peer->band, x0, x1, y0, y1);
+    if (rc != HK_OK) return rc;
+    if (x0 >= x1 || y0 >= y1) return HK_OK;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    hk_launch_halo_copy(ctx->planes, ctx->band, peer->planes, peer->band, x0, x1, y0, y1, ctx->stream);
+    return check_launch(ctx);
 }
 
 // ------------------------------------------------------------------------------------------ frame assembly

@@ -261,6 +261,23 @@ class HikariPlugin:
     def halo_pull(self, source):
         check(lib().hk_halo_pull(self.ctx, source.ctx), self.ctx)
 
+    HALO_DESCRIPTOR_BYTES = 40 * 64 + 10 * 4
+
+    def halo_export(self):
+        """bytes of an hk_halo_descriptor (CUDA IPC handles of the reservoir planes + tile rectangles) for another process"""
+        buf = (C.c_uint8 * self.HALO_DESCRIPTOR_BYTES)()
+        check(lib().hk_halo_export(self.ctx, buf), self.ctx)
+        return bytes(buf)
+
+    def halo_import(self, descriptor):
+        buf = (C.c_uint8 * self.HALO_DESCRIPTOR_BYTES).from_buffer_copy(descriptor)
+        peer = C.c_void_p()
+        check(lib().hk_halo_import(self.ctx, buf, C.byref(peer)), self.ctx)
+        return peer
+
+    def halo_pull_peer(self, peer):
+        check(lib().hk_halo_pull_peer(self.ctx, peer), self.ctx)
+
     # frame assembly across tiles / GPUs (hk_set_frame_target)
     def frame_alloc(self):
         p = C.c_void_p()

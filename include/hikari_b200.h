@@ -201,6 +201,20 @@ int hk_sync(hk_context* ctx);
  * hk_context_set_motion_margin widens the ghost ring from 36 to 36 + `pixels` (re-allocates and clears the tile's state). */
 int hk_context_set_motion_margin(hk_context* ctx, uint32_t pixels);
 int hk_halo_pull(hk_context* dst, hk_context* src);
+/* The same between processes (one process per GPU): the owner exports a descriptor — CUDA IPC handles of its forty
+ * reservoir quarter-planes and its tile rectangles — which travels to the neighbour by any channel; the neighbour imports it
+ * once (maps the planes; peer access over NVLink) and pulls after every frame.  Re-export after hk_context_resize* or
+ * hk_context_set_motion_margin (the planes are re-allocated).  Imported peers are released with the importing context. */
+typedef struct hk_halo_descriptor {
+    uint8_t plane_handles[40][64];   /* reservoir r, quarter q at [4 * r + q] */
+    int32_t frame[2];                /* width, height */
+    int32_t allocated[4];            /* col_begin, col_end, row_begin, row_end of the allocation (owned + ghosts) */
+    int32_t owned[4];
+} hk_halo_descriptor;
+typedef struct hk_halo_peer hk_halo_peer;
+int hk_halo_export(hk_context* ctx, hk_halo_descriptor* out);
+int hk_halo_import(hk_context* ctx, const hk_halo_descriptor* remote, hk_halo_peer** out);
+int hk_halo_pull_peer(hk_context* ctx, hk_halo_peer* peer);
 
 /* Frame assembly for tiled (multi-GPU) rendering.  With a frame target set, every owned pixel of the tone-mapped image is
  * also stored into the full-frame Rgba16Float buffer `frame` (pitch in pixels) at its position in the frame, by the last

@@ -93,7 +93,9 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, con
 static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h, &p, sizeof(p)); return cudaSuccess; }
-static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }   // one process only
+// one process only: "opening" a handle gives the exporter's pointer back (real CUDA refuses this inside the exporting process;
+// the two-process paths are exercised on the device, tests/test_gpu_frame_assembly.py, tests/test_gpu_zz_halo.py)
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
 static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 
 // ------------------------------------------------------------------------------------------------ launches

@@ -65,3 +65,97 @@ def test_halo_pull_refusals():
         a.halo_pull(other)
     with pytest.raises(_ffi.HikariError, match="256"):
         a.set_motion_margin(1000)
+
+
+def test_halo_descriptor_path_in_one_process_on_the_emulator():
+    """hk_halo_export / hk_halo_import / hk_halo_pull_peer with both tiles in one process.  Real CUDA refuses to open an IPC
+    handle inside the process that exported it, so this form only runs on the emulated kernels (logic of the descriptor,
+    the mapped-plane bookkeeping and the copy rectangle); the two-process form below runs on the device."""
+    from tests.conftest import EMULATED
+    if not EMULATED:
+        pytest.skip("same-process IPC open exists only in the kernel-logic emulation")
+    rects = [(0, 72, 0, 96), (72, 144, 0, 96)]
+    b = Bench("cornell", 144, 96, config="cornell_1080p")
+    full = b.device()
+    tiles = [b.device(r[2], r[3], r[0], r[1]) for r in rects]
+    for t in tiles:
+        t.set_motion_margin(12)
+    peers = {0: tiles[0].halo_import(tiles[1].halo_export()), 1: tiles[1].halo_import(tiles[0].halo_export())}
+    for f in range(1, 8):
+        inp = b.moving_inputs(f, step=(0.04, 0.01, -0.02))
+        full.render_frame(inp)
+        for t in tiles:
+            t.render_frame(inp)
+        for k in PLANES:
+            whole = full.readback(k)
+            for r, t in zip(rects, tiles):
+                assert mismatch(t.readback(k), whole[r[2]:r[3], r[0]:r[1]]) == 0, (f, k)
+        for i, t in enumerate(tiles):
+            t.halo_pull_peer(peers[i])
+
+
+def _halo_worker(rect, frames, conn):
+    """second process: renders its tile and the unsharded frame, exchanges halos with the parent after every frame"""
+    try:
+        b = Bench("cornell", 144, 96, config="cornell_1080p")
+        full, tile = b.device(), b.device(rect[2], rect[3], rect[0], rect[1])
+        tile.set_motion_margin(12)
+        conn.send(tile.halo_export())
+        peer = tile.halo_import(conn.recv())
+        bad = 0
+        for f in range(1, frames + 1):
+            inp = b.moving_inputs(f, step=(0.04, 0.01, -0.02))
+            full.render_frame(inp)
+            tile.render_frame(inp)
+            tile.sync()
+            for k in PLANES:
+                bad += mismatch(tile.readback(k), full.readback(k)[rect[2]:rect[3], rect[0]:rect[1]])
+            conn.send("rendered"); assert conn.recv() == "rendered"      # both tiles have finished frame f
+            tile.halo_pull_peer(peer)
+            tile.sync()
+            conn.send("pulled"); assert conn.recv() == "pulled"          # nobody starts frame f + 1 before both pulls are done
+        conn.send(("done", bad))
+    except Exception as e:   # pragma: no cover
+        conn.send(("error", repr(e)))
+
+
+def test_halo_exchange_between_two_processes_cuda_ipc():
+    """One process per tile (the bench's shape): descriptors cross a pipe, every frame ends with pull + barrier on both sides;
+    both tiles stay bit-identical to the unsharded render under camera motion.  (Both processes use cuda:0 here; across GPUs
+    the pulls go over NVLink.)"""
+    import multiprocessing as mp
+    from tests.conftest import needs_real_gpu
+    needs_real_gpu()
+    rects = [(0, 72, 0, 96), (72, 144, 0, 96)]
+    frames = 6
+    ctx = mp.get_context("spawn")
+    parent, child = ctx.Pipe()
+    p = ctx.Process(target=_halo_worker, args=(rects[1], frames, child))
+    p.start()
+    b = Bench("cornell", 144, 96, config="cornell_1080p")
+    full, tile = b.device(), b.device(rects[0][2], rects[0][3], rects[0][0], rects[0][1])
+    tile.set_motion_margin(12)
+    assert parent.poll(240), "worker did not start"
+    theirs = parent.recv()
+    assert not isinstance(theirs, tuple), theirs
+    parent.send(tile.halo_export())
+    peer = tile.halo_import(theirs)
+    bad = 0
+    for f in range(1, frames + 1):
+        inp = b.moving_inputs(f, step=(0.04, 0.01, -0.02))
+        full.render_frame(inp)
+        tile.render_frame(inp)
+        tile.sync()
+        for k in PLANES:
+            bad += mismatch(tile.readback(k), full.readback(k)[rects[0][2]:rects[0][3], rects[0][0]:rects[0][1]])
+        assert parent.poll(120); msg = parent.recv(); assert msg == "rendered", msg
+        parent.send("rendered")
+        tile.halo_pull_peer(peer)
+        tile.sync()
+        assert parent.poll(120); msg = parent.recv(); assert msg == "pulled", msg
+        parent.send("pulled")
+    assert parent.poll(120)
+    status, their_bad = parent.recv()
+    p.join(30)
+    assert status == "done", their_bad
+    assert bad == 0 and their_bad == 0, (bad, their_bad)
