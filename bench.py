@@ -248,6 +248,8 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     dev = plugin.HikariPlugin(W, H, cuda_device=local_rank, row_begin=r0, row_end=r1, cuda_stream=stream.cuda_stream,
                               col_begin=x0, col_end=x1)
+    if world_size > 1 and args.halo_margin is not None:
+        dev.set_motion_margin(args.halo_margin)      # re-allocates the tile with 36 + margin ghost pixels (before any pointer is taken)
     dev.upload_scene(world)
 
     # the context's tone-mapped band as a torch tensor (zero copy) for the all-gather
@@ -285,6 +287,14 @@ def run_ours(args):
         if int(ok.item()) == 0:
             frame_targets = None
             args.gather = "nccl"
+    # Exact tiling under camera motion (--halo-margin M, off by default; the benchmark camera is static, so this measures the
+    # cost of the exchange, the exactness is tests/test_gpu_zz_halo.py): every rank maps every other rank's reservoir planes
+    # through CUDA IPC once; after each frame, between two frame barriers, it pulls the part of its ghost ring each owns.
+    halo_peers = []
+    if world_size > 1 and args.halo_margin is not None:
+        descriptors = [None] * world_size
+        dist.all_gather_object(descriptors, dev.halo_export())
+        halo_peers = [dev.halo_import(d) for r, d in enumerate(descriptors) if r != rank]
     frame_no = [0]
 
     def begin_frame():
@@ -298,6 +308,10 @@ def run_ours(args):
         else:
             send_buf[:tile_t.numel()].copy_(tile_t)
             dist.all_gather_into_tensor(frame_buf, send_buf)
+        if halo_peers:                       # every rank has finished the frame (collective above): refresh the ghost ring
+            for peer in halo_peers:
+                dev.halo_pull_peer(peer)
+            dist.all_reduce(landed)          # nobody overwrites reservoirs a neighbour is still reading
     pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
 
     def barrier():
@@ -506,7 +520,8 @@ def run_ours(args):
         "metric": "Mrays/s", "value": round(value, 3), "unit": "Mrays/s", "n_gpus": world_size, "steps": K, "warmup": W_,
         "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "reference asset cornell.glb + blue-noise seed (no synthetic inputs exist for this path)",
-        "config": dict(config_json(args.config, cfg, settings, world_size, args.gather), tiles=[list(t) for t in tiles]),
+        "config": dict(config_json(args.config, cfg, settings, world_size, args.gather), tiles=[list(t) for t in tiles],
+                       **({"halo_margin": args.halo_margin} if (world_size > 1 and args.halo_margin is not None) else {})),
         "rays_per_frame": {"light_tlas": rays[1] / K, "light_blas": rays[2] / K, "primary": rays[0] / K},
         "fps": round(1e3 / ms_per_step, 2),
         "e2e": {"value": round(e2e_value, 3), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / K, 5),
@@ -663,6 +678,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--equal-tiles", action="store_true", help="N > 1: equal grid of tiles instead of cost-balanced strips")
+    ap.add_argument("--halo-margin", type=int, default=None,
+                    help="N > 1: exact tiling under camera motion — ghost ring of 36 + M pixels and a halo pull after every frame")
     ap.add_argument("--lib", default=None, help="tuning: load this build of libhikari_b200.so (tools/build_variants.py) instead of the in-tree one")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = tiles stored straight into rank 0's frame over NVLink (CUDA IPC); nccl = all_gather of tiles")
