@@ -49,6 +49,7 @@ SYMBOLS = {
     "hk_readback_wait": (_I, [_P]),
     "hk_context_set_motion_margin": (_I, [_P, _U32]),
     "hk_halo_pull": (_I, [_P, _P]),
+    "hk_context_enable_tile_upscalers": (_I, [_P, _I]),
     "hk_halo_export": (_I, [_P, _P]),
     "hk_halo_import": (_I, [_P, _P, C.POINTER(_P)]),
     "hk_halo_pull_peer": (_I, [_P, _P]),

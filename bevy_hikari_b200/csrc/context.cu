@@ -21,6 +21,10 @@ using namespace hkd;
 static const int GHOST_DEMOD = 15, GHOST_L0 = 7, GHOST_L1 = 3, GHOST_L2 = 1;
 static const int GHOST_SPATIAL = GHOST_DEMOD + 1;           // 16
 static const int GHOST_TEMPORAL = GHOST_SPATIAL + 20;       // 36
+// Temporal upscalers on a tile: taa_jasmine reads the upscaled image 1 output texel around a pixel, smaa_tu4x_extrapolate the
+// diagonal texels of the neighbouring render pixels, smaa_tu4x the current tone-mapped image up to 2 render pixels away:
+// smaa runs on owned + 2, extrapolate on owned + 1, and the tone-mapped image (with everything upstream) on owned + 4.
+static const int RING_SMAA = 2, RING_EXTRAPOLATE = 1, RING_TONE = 4;
 
 struct hk_halo_peer {   // a neighbour tile of another process, mapped through CUDA IPC (hk_halo_import)
     Planes planes;       // only reservoir[] is filled
@@ -55,6 +59,7 @@ struct hk_context {
     bool copy_in_flight = false;      // a copy has been queued and the compute stream has not yet been ordered behind it
     bool copy_unwaited = false;       // ... and the host has not waited for it
     uint2* frame_target = nullptr; uint32_t frame_pitch = 0;   // hk_set_frame_target
+    bool tile_upscalers = false;      // tile context with planes for the temporal upscalers (hk_context_enable_tile_upscalers)
     int motion_margin = 0;            // extra ghost pixels for exact tiling under camera motion (hk_context_set_motion_margin)
     std::vector<void*> frames_owned, frames_opened;            // hk_frame_alloc / hk_frame_open
     std::vector<hk_halo_peer*> halo_peers;                     // hk_halo_import
@@ -146,7 +151,12 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     HK_CUDA(alloc_plane(ctx, &p.tone_mapped_db[1], ctx->owned_pixels, L));
     p.tone_mapped = p.tone_mapped_db[0];
     p.upscale_output = nullptr; p.taa_output[0] = p.taa_output[1] = nullptr;
-    if (ctx->full_frame) {   // temporal upscalers (K11/K12) run on whole frames only
+    p.tone_ring_db[0] = p.tone_ring_db[1] = nullptr;
+    if (!ctx->full_frame && ctx->tile_upscalers) {   // every image over the allocation (owned + ring + halo)
+        HK_CUDA(alloc_plane(ctx, &p.tone_ring_db[0], n, L));
+        HK_CUDA(alloc_plane(ctx, &p.tone_ring_db[1], n, L));
+    }
+    if (ctx->full_frame || ctx->tile_upscalers) {   // temporal upscalers (K11/K12)
         HK_CUDA(alloc_plane(ctx, &p.upscale_output, 4 * n, L));
         HK_CUDA(alloc_plane(ctx, &p.taa_output[0], 4 * n, L));
         HK_CUDA(alloc_plane(ctx, &p.taa_output[1], 4 * n, L));
@@ -484,8 +494,11 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     const bool ratio1 = in->frame.upscale_ratio == 1.0f;
     if (!(in->frame.upscale_ratio >= 1.0f && in->frame.upscale_ratio <= 2.0f))
         return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "upscale_ratio must be in [1, 2] (Upscale::ratio clamps, lib.rs:501-505)");
-    if ((!ratio1 || in->temporal_upscalers) && !ctx->full_frame)
-        return set_error(ctx, HK_ERR_UNSUPPORTED, "upscale_ratio != 1 and the temporal upscalers need a full-frame context (no tile)");
+    if (!ratio1 && !ctx->full_frame)
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "upscale_ratio != 1 needs a full-frame context (no tile)");
+    if (in->temporal_upscalers && !ctx->full_frame && (!ctx->tile_upscalers || ctx->motion_margin < RING_TONE))
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "the temporal upscalers on a tile need a full-frame context, or hk_context_enable_tile_upscalers "
+                                                  "and a motion margin of at least 4 pixels + the per-frame motion");
     if (in->frame.direct_validate_interval == 0 || in->frame.emissive_validate_interval == 0)
         return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "validate interval must be >= 1");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return set_error(ctx, HK_ERR_CUDA, "cudaSetDevice");
@@ -505,6 +518,7 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     P.gbuffer_current = ctx->gbuffer_current;
     P.frame_target = ratio1 ? ctx->frame_target : nullptr;   // the assembled frame has the output size = render size at ratio 1
     P.frame_pitch = ctx->frame_pitch;
+    P.tile_images = (!ctx->full_frame && in->temporal_upscalers) ? 1 : 0;
     if (!ratio1) {   // scaled_size = (ratio.recip() * size).ceil(), light.rs:622-624; render-size planes use stride RW
         const float scale = 1.0f / in->frame.upscale_ratio;
         P.band.RW = (int)ceilf(scale * (float)P.band.W);
@@ -566,8 +580,10 @@ static int run_prepass(hk_context* ctx, KParams& P) {
     { KernelTimer t(ctx, HK_K_GBUFFER); hk_launch_gbuffer(P, ctx->count_rays, ctx->stream); }
     return check_launch(ctx);
 }
+static int ring_of(const KParams& P) { return P.tile_images ? RING_TONE : 0; }   // extra reach of every pass when a tile feeds the upscalers
 static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, light.rs:645-699 (albedo is fused in the prepass)
     const hk_frame_uniform& f = P.in.frame;
+    const int GHOST_SPATIAL = ::GHOST_SPATIAL + ring_of(P);
     rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     // each temporal pass is followed by the resolve of its scatter writes (all allocated rows can be targets)
     { KernelTimer t(ctx, HK_K_DIRECT); hk_launch_direct(P, false, ctx->count_rays, ctx->stream);
@@ -588,6 +604,8 @@ static void order_behind_copy(hk_context* ctx) {
     ctx->copy_in_flight = false;
 }
 static int run_post(hk_context* ctx, KParams& P, bool fuse) {  // PostProcessNode::run, post_process.rs:1190-1234
+    const int ring = ring_of(P);
+    const int GHOST_DEMOD = ::GHOST_DEMOD + ring, GHOST_L0 = ::GHOST_L0 + ring, GHOST_L1 = ::GHOST_L1 + ring, GHOST_L2 = ::GHOST_L2 + ring;
     if (P.in.denoise) {
         const int signals = (P.in.frame.indirect_bounces == 0) ? 2 : 3;  // post_process.rs:949-954
         { rows(ctx, P, GHOST_DEMOD); KernelTimer t(ctx, HK_K_DEMODULATION); hk_launch_demodulation(P, signals, ctx->stream); }
@@ -595,22 +613,29 @@ static int run_post(hk_context* ctx, KParams& P, bool fuse) {  // PostProcessNod
         { rows(ctx, P, GHOST_L1); KernelTimer t(ctx, HK_K_DENOISE_1); hk_launch_denoise_level(P, 1, signals, false, false, ctx->stream); }
         { rows(ctx, P, GHOST_L2); KernelTimer t(ctx, HK_K_DENOISE_2); hk_launch_denoise_level(P, 2, signals, false, false, ctx->stream); }
         if (fuse) order_behind_copy(ctx);
-        { rows(ctx, P, 0); KernelTimer t(ctx, HK_K_DENOISE_3);
+        { rows(ctx, P, ring); KernelTimer t(ctx, HK_K_DENOISE_3);
           hk_launch_denoise_level(P, 3, signals, fuse, !fuse || ctx->keep_intermediates, ctx->stream); }
         if (!fuse) { order_behind_copy(ctx); KernelTimer t(ctx, HK_K_TONE_MAPPING); hk_launch_tone_mapping(P, ctx->stream); }
     } else {
-        rows(ctx, P, 0);
+        rows(ctx, P, ring);
         order_behind_copy(ctx);
         KernelTimer t(ctx, HK_K_TONE_MAPPING);
         hk_launch_tone_mapping(P, ctx->stream);
     }
-    if (P.in.temporal_upscalers) {   // post_process.rs:1236-1277; make_params guarantees a full-frame context
-        rows(ctx, P, 0);
+    if (P.in.temporal_upscalers) {   // post_process.rs:1236-1277
         const bool smaa = P.in.smaa_tu4x != 0;
-        if (smaa) { KernelTimer t(ctx, HK_K_SMAA_TU4X); hk_launch_smaa_tu4x(P, ctx->stream); ctx->launches += 1; }
-        if (P.in.taa_jitter) {
-            P.row_lo = 0; P.col_lo = 0;
-            P.col_hi = smaa ? 2 * P.band.RW : P.band.RW; P.row_hi = smaa ? 2 * P.band.RH : P.band.RH;
+        if (smaa) {
+            KernelTimer t(ctx, HK_K_SMAA_TU4X);
+            rows(ctx, P, P.tile_images ? RING_SMAA : 0);
+            hk_launch_smaa_tu4x(P, ctx->stream);
+            rows(ctx, P, P.tile_images ? RING_EXTRAPOLATE : 0);
+            hk_launch_smaa_tu4x_extrapolate(P, ctx->stream);
+            ctx->launches += 1;
+        }
+        if (P.in.taa_jitter) {   // over the output pixels of the owned rectangle
+            rows(ctx, P, 0);
+            const int k = smaa ? 2 : 1;
+            P.row_lo *= k; P.row_hi *= k; P.col_lo *= k; P.col_hi *= k;
             KernelTimer t(ctx, HK_K_TAA); hk_launch_taa_jasmine(P, smaa, ctx->stream);
         }
     }
@@ -746,11 +771,14 @@ static bool plane_view(hk_context* ctx, int which, PlaneView* v) {
     const uint32_t cur = ctx->last_number % 2u;
     switch (which) {
         case HK_OUT_TONE_MAPPED: *v = PlaneView{p.tone_mapped_db[ctx->last_upscalers ? cur : 0u], 8, rw, rh, rw}; return true;
-        case HK_OUT_UPSCALED: if (!p.upscale_output) return false; *v = PlaneView{p.upscale_output, 8, 2 * rw, 2 * rh, 2 * rw}; return true;
-        case HK_OUT_TAA: {
-            if (!p.taa_output[0]) return false;
-            const size_t k = ctx->last_smaa ? 2 : 1;
-            *v = PlaneView{p.taa_output[cur], 8, k * rw, k * rh, k * rw};
+        // upscaled images: a full-frame context stores them tightly; a tile over k x its allocation, of which the owned part is served
+        case HK_OUT_UPSCALED: case HK_OUT_TAA: {
+            uint2* base = which == HK_OUT_UPSCALED ? p.upscale_output : p.taa_output[cur];
+            if (!base) return false;
+            const size_t k = (which == HK_OUT_UPSCALED || ctx->last_smaa) ? 2 : 1;
+            if (ctx->full_frame) { *v = PlaneView{base, 8, k * rw, k * rh, k * rw}; return true; }
+            const size_t pitch = k * (size_t)b.AW, first = (k * (size_t)(b.r0 - b.a0)) * pitch + k * (size_t)(b.cx0 - b.ax0);
+            *v = PlaneView{base + first, 8, k * ow, k * oh, pitch};
             return true;
         }
         case HK_OUT_RENDER_DIRECT: case HK_OUT_RENDER_EMISSIVE: case HK_OUT_RENDER_INDIRECT: return render(p.render[which - HK_OUT_RENDER_DIRECT], 8);
@@ -859,6 +887,24 @@ int hk_context_set_motion_margin(hk_context* ctx, uint32_t pixels) {
     const Band b = ctx->band;
     return allocate_planes(ctx, (uint32_t)b.W, (uint32_t)b.H, (uint32_t)b.cx0, (uint32_t)b.cx1, (uint32_t)b.r0, (uint32_t)b.r1);
 }
+int hk_context_enable_tile_upscalers(hk_context* ctx, int enabled) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->tile_upscalers = enabled != 0;
+    const Band b = ctx->band;
+    return allocate_planes(ctx, (uint32_t)b.W, (uint32_t)b.H, (uint32_t)b.cx0, (uint32_t)b.cx1, (uint32_t)b.r0, (uint32_t)b.r1);
+}
+// the images the temporal upscalers carry from frame to frame (tiles): tone-mapped ring planes and TAA history
+static void halo_pull_images(hk_context* dst, const Planes& sp, const Band& sb, int x0, int x1, int y0, int y1) {
+    const Planes& dp = dst->planes;
+    if (!dp.tone_ring_db[0] || !sp.tone_ring_db[0]) return;
+    const int k = dst->last_smaa ? 2 : 1;
+    for (int i = 0; i < 2; ++i) {
+        hk_launch_halo_copy_image(dp.tone_ring_db[i], dst->band, sp.tone_ring_db[i], sb, 1, x0, x1, y0, y1, dst->stream);
+        hk_launch_halo_copy_image(dp.taa_output[i], dst->band, sp.taa_output[i], sb, k, x0, x1, y0, y1, dst->stream);
+    }
+}
 int hk_halo_pull(hk_context* dst, hk_context* src) {
     if (!dst || !src) return HK_ERR_INVALID_ARGUMENT;
     if (dst == src) return HK_OK;
@@ -879,6 +925,7 @@ int hk_halo_pull(hk_context* dst, hk_context* src) {
         cudaGetLastError();
     }
     hk_launch_halo_copy(dst->planes, d, src->planes, s, x0, x1, y0, y1, dst->stream);
+    halo_pull_images(dst, src->planes, s, x0, x1, y0, y1);
     return check_launch(dst);
 }
 

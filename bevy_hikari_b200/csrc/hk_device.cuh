@@ -93,7 +93,8 @@ struct Planes {
     uint2* dn_render[3];
     uint2* tone_mapped;         // owned rectangle only, tightly packed; = tone_mapped_db[frame.number % 2] (post_process.rs:716,979)
     uint2* tone_mapped_db[2];
-    uint2* upscale_output;      // 2 RW x 2 RH (SMAA TU4x), full-frame contexts only
+    uint2* tone_ring_db[2];     // tiles with upscalers: the tone-mapped image over the tile's allocation (owned + 4-px ring + halo)
+    uint2* upscale_output;      // 2 RW x 2 RH (SMAA TU4x); tiles: 2 x the allocation
     uint2* taa_output[2];       // [frame.number % 2] is written
 };
 
@@ -139,6 +140,7 @@ struct KParams {
     // receives this context's owned pixels at their global position; nullptr = none
     uint2* frame_target;
     uint32_t frame_pitch;   // pixels
+    int tile_images;        // 1 = tile context with the temporal upscalers enabled: render-size images are stored over the allocation
 };
 
 // --------------------------------------------------------------------------------------------- raw loads

@@ -16,10 +16,14 @@ void hk_launch_denoise_level(const hkd::KParams& P, int level, int signals, bool
 void hk_launch_tone_mapping(const hkd::KParams& P, cudaStream_t st);
 
 // temporal upscalers (kernels_upscale.cu); full-frame contexts only
-void hk_launch_smaa_tu4x(const hkd::KParams& P, cudaStream_t st);               // smaa_tu4x + smaa_tu4x_extrapolate over the render rectangle
+void hk_launch_smaa_tu4x(const hkd::KParams& P, cudaStream_t st);               // over col_lo..col_hi x row_lo..row_hi (render pixels)
+void hk_launch_smaa_tu4x_extrapolate(const hkd::KParams& P, cudaStream_t st);
 void hk_launch_taa_jasmine(const hkd::KParams& P, bool smaa, cudaStream_t st);  // over col_lo..col_hi x row_lo..row_hi = the output size
 
 // halo exchange between tiles of one frame (kernels_post.cu): copies the ten reservoir buffers of the global pixel rectangle
 // [x0,x1) x [y0,y1) from `src`'s planes into `dst`'s planes; `src` may be peer memory
 void hk_launch_halo_copy(const hkd::Planes& dst, const hkd::Band& dst_band, const hkd::Planes& src, const hkd::Band& src_band,
                          int x0, int x1, int y0, int y1, cudaStream_t st);
+// the same for one Rgba16Float image stored over the tiles' allocations at `scale` x the render resolution
+void hk_launch_halo_copy_image(uint2* dst, const hkd::Band& dst_band, const uint2* src, const hkd::Band& src_band, int scale,
+                               int x0, int x1, int y0, int y1, cudaStream_t st);

@@ -30,6 +30,8 @@ __device__ __forceinline__ void store16(uint2* plane, size_t i, vec4 v) {
 __device__ __forceinline__ void store_final(const KParams& P, int x, int y, vec4 color) {
     uvec2 w = pack_rgba16f(color);
     const uint2 bits = make_uint2(w.x, w.y);
+    if (P.tile_images) P.planes.tone_ring_db[P.in.frame.number % 2u][band_index(P.band, x, y)] = bits;   // incl. the ring the upscalers sample
+    if (!band_owned(P.band, x, y)) return;
     P.planes.tone_mapped[owned_index(P.band, x, y)] = bits;
     if (P.frame_target) P.frame_target[(size_t)y * P.frame_pitch + (size_t)x] = bits;
 }
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
         if (!FUSE_TONE_MAPPING || keep_denoised) P.planes.dn_render[sgl][idx] = make_uint2(w.x, w.y);
         if (FUSE_TONE_MAPPING) color = color + unpack_rgba16f(w);
     }
-    if (FUSE_TONE_MAPPING && band_owned(P.band, x, y)) {
+    if (FUSE_TONE_MAPPING && (P.tile_images || band_owned(P.band, x, y))) {
         vec3 rgb = reinhard_luminance(vmax(xyz(color), 0.0039f));
         color = v4(rgb, color.w);
         if (!(color.w > 0.0f))
@@ -321,6 +323,15 @@ __global__ void __launch_bounds__(256) k_halo_copy(const __grid_constant__ HaloA
     for (int q = 0; q < 4; ++q) A.dst[r].q[q][di] = A.src[r].q[q][si];
 }
 
+__global__ void __launch_bounds__(256) k_halo_copy_image(uint2* dst, Band db, const uint2* src, Band sb, int scale, int x0, int y0, int w, int h) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)w * (size_t)h) return;
+    const int x = x0 + (int)(i % (size_t)w), y = y0 + (int)(i / (size_t)w);     // texel of the scaled image
+    const size_t si = (size_t)(y - scale * sb.a0) * (size_t)(scale * sb.AW) + (size_t)(x - scale * sb.ax0);
+    const size_t di = (size_t)(y - scale * db.a0) * (size_t)(scale * db.AW) + (size_t)(x - scale * db.ax0);
+    dst[di] = src[si];
+}
+
 static dim3 grid_for(const KParams& P) {
     int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
     return dim3((unsigned)((cols + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
@@ -356,6 +367,13 @@ void hk_launch_halo_copy(const Planes& dst, const Band& dst_band, const Planes& 
     a.x0 = x0; a.y0 = y0; a.w = x1 - x0; a.h = y1 - y0;
     const size_t n = (size_t)a.w * (size_t)a.h;
     k_halo_copy<<<dim3((unsigned)((n + 255) / 256), 10u, 1u), 256, 0, st>>>(a);
+}
+void hk_launch_halo_copy_image(uint2* dst, const Band& dst_band, const uint2* src, const Band& src_band, int scale, int x0, int x1, int y0, int y1,
+                               cudaStream_t st) {
+    if (x1 <= x0 || y1 <= y0 || !dst || !src) return;
+    const int w = scale * (x1 - x0), h = scale * (y1 - y0);
+    const size_t n = (size_t)w * (size_t)h;
+    k_halo_copy_image<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, dst_band, src, src_band, scale, scale * x0, scale * y0, w, h);
 }
 void hk_launch_tone_mapping(const KParams& P, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;

@@ -9,19 +9,25 @@
 
 namespace hkd {
 
-struct Image16 {   // Rgba16Float, tightly packed w x h
-    const uint2* t; int w, h;
-    __device__ __forceinline__ vec4 texel(int x, int y) const {
-        x = min(max(x, 0), w - 1); y = min(max(y, 0), h - 1);
-        uint2 u = t[(size_t)y * w + x];
+// An image of w x h texels of which this context stores the window that starts at texel (x0, y0) with row pitch `pitch`
+// (the whole image for a full-frame context; the tile's allocation — owned rectangle + ghost ring — for a tile).
+// Addressing clamps to the IMAGE edge, as the sampler does; the caller guarantees that what it samples lies in the window.
+struct Image16 {   // Rgba16Float
+    const uint2* t; int w, h, x0, y0, ww, wh;      // image size; window origin and size (row pitch = ww)
+    __device__ __forceinline__ vec4 fetch(int x, int y) const {
+        // memory safety on tiles: a sample that leaves the window (motion beyond the margin) reads the window's edge
+        x = min(max(x, x0), x0 + ww - 1); y = min(max(y, y0), y0 + wh - 1);
+        uint2 u = t[(size_t)(y - y0) * (size_t)ww + (size_t)(x - x0)];
         uvec2 q; q.x = u.x; q.y = u.y;
         return unpack_rgba16f(q);
     }
+    __device__ __forceinline__ vec4 texel(int x, int y) const {
+        x = min(max(x, 0), w - 1); y = min(max(y, 0), h - 1);
+        return fetch(x, y);
+    }
     __device__ __forceinline__ vec4 load(int x, int y) const {   // textureLoad: zero outside
         if (x < 0 || y < 0 || x >= w || y >= h) return v4(0.0f);
-        uint2 u = t[(size_t)y * w + x];
-        uvec2 q; q.x = u.x; q.y = u.y;
-        return unpack_rgba16f(q);
+        return fetch(x, y);
     }
     __device__ __forceinline__ vec4 nearest(vec2 uv) const { return texel((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
     __device__ __forceinline__ vec4 linear(vec2 uv) const {
@@ -37,11 +43,12 @@ struct Image16 {   // Rgba16Float, tightly packed w x h
         out[0] = texel(i0, j0 + 1); out[1] = texel(i0 + 1, j0 + 1); out[2] = texel(i0 + 1, j0); out[3] = texel(i0, j0);
     }
 };
-struct Image32 {   // a float4 plane of the (full-frame) G-buffer
-    const float4* t; int w, h;
+struct Image32 {   // a float4 plane of the G-buffer (same windowing)
+    const float4* t; int w, h, x0, y0, ww, wh;
     __device__ __forceinline__ vec4 texel(int x, int y) const {
         x = min(max(x, 0), w - 1); y = min(max(y, 0), h - 1);
-        return f4v(t[(size_t)y * w + x]);
+        x = min(max(x, x0), x0 + ww - 1); y = min(max(y, y0), y0 + wh - 1);
+        return f4v(t[(size_t)(y - y0) * (size_t)ww + (size_t)(x - x0)]);
     }
     __device__ __forceinline__ vec4 nearest(vec2 uv) const { return texel((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
     __device__ __forceinline__ vec4 gather_w(vec2 uv) const {
@@ -101,6 +108,25 @@ __device__ __forceinline__ void store16(uint2* plane, size_t i, vec4 v) {
     uvec2 w = pack_rgba16f(v);
     plane[i] = make_uint2(w.x, w.y);
 }
+// Windows.  Full-frame context: render-size images are tight RW x RH (x scale for the upscaled ones).  Tile (ratio 1):
+// every image is stored over the tile's allocation, scaled by `scale` for the upscaled ones.
+__device__ __forceinline__ Image16 render_image(const KParams& P, const uint2* plane, int scale) {
+    const Band& b = P.band;
+    if (!P.tile_images) return Image16{plane, scale * b.RW, scale * b.RH, 0, 0, scale * b.RW, scale * b.RH};
+    return Image16{plane, scale * b.W, scale * b.H, scale * b.ax0, scale * b.a0, scale * b.AW, scale * (b.a1 - b.a0)};
+}
+__device__ __forceinline__ size_t render_image_index(const KParams& P, int scale, int x, int y) {
+    const Band& b = P.band;
+    if (!P.tile_images) return (size_t)y * (size_t)(scale * b.RW) + (size_t)x;
+    return (size_t)(y - scale * b.a0) * (size_t)(scale * b.AW) + (size_t)(x - scale * b.ax0);
+}
+__device__ __forceinline__ Image32 gbuffer_image(const KParams& P, const float4* plane) {
+    const Band& b = P.band;
+    return Image32{plane, b.W, b.H, b.ax0, b.a0, b.AW, b.a1 - b.a0};
+}
+__device__ __forceinline__ const uint2* tone_plane(const KParams& P, uint32_t which) {
+    return P.tile_images ? P.planes.tone_ring_db[which] : P.planes.tone_mapped_db[which];
+}
 
 // --------------------------------------------------------------------------------------------- smaa_tu4x
 __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x(const __grid_constant__ KParams P) {  // smaa.wgsl:81-199
@@ -109,9 +135,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x(const __grid_constant
     if (!tile_active(P, x, y)) return;
     const int RW = P.band.RW, RH = P.band.RH, OW = 2 * RW, OH = 2 * RH, W = P.band.W, H = P.band.H;
     const uint32_t cur = P.in.frame.number % 2u, prv = 1u - cur;
-    const Image16 render{P.planes.tone_mapped_db[cur], RW, RH}, previous_render{P.planes.tone_mapped_db[prv], RW, RH};
-    const Image32 position{P.planes.pos_depth_db[P.gbuffer_current], W, H}, previous_position{P.planes.pos_depth_db[P.gbuffer_current ^ 1], W, H};
-    const Image32 velocity_uv{P.planes.velocity_uv_db[P.gbuffer_current], W, H}, previous_velocity_uv{P.planes.velocity_uv_db[P.gbuffer_current ^ 1], W, H};
+    const Image16 render = render_image(P, tone_plane(P, cur), 1), previous_render = render_image(P, tone_plane(P, prv), 1);
+    const Image32 position = gbuffer_image(P, P.planes.pos_depth_db[P.gbuffer_current]);
+    const Image32 previous_position = gbuffer_image(P, P.planes.pos_depth_db[P.gbuffer_current ^ 1]);
+    const Image32 velocity_uv = gbuffer_image(P, P.planes.velocity_uv_db[P.gbuffer_current]);
+    const Image32 previous_velocity_uv = gbuffer_image(P, P.planes.velocity_uv_db[P.gbuffer_current ^ 1]);
     const int current_jitter = ((P.in.frame.number & 1u) == 0u) ? 0 : 1;
     const int previous_jitter = 1 - current_jitter;
     const vec2 uv = render_uv(P, x, y);
@@ -129,7 +157,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x(const __grid_constant
     const bool boundary_miss = fabsf(previous_reprojected_uv.x - 0.5f) > 0.5f || fabsf(previous_reprojected_uv.y - 0.5f) > 0.5f;
     auto instance_at = [&](vec2 u) {
         int px = min(max((int)floorf(u.x * (float)W), 0), W - 1), py = min(max((int)floorf(u.y * (float)H), 0), H - 1);
-        return P.planes.instance_material[(size_t)py * W + px].x;
+        px = min(max(px, P.band.ax0), P.band.ax1 - 1); py = min(max(py, P.band.a0), P.band.a1 - 1);     // window safety, see Image16::fetch
+        return P.planes.instance_material[band_index(P.band, px, py)].x;
     };
     const float current_instance = instance_at(previous_output_uv);
     bool instance_miss = false;
@@ -169,16 +198,15 @@ __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x(const __grid_constant
     blend_factor = clampf(-cs, 0.0f, 1.0f);
     vec3 remix_color = xyz(render.linear(previous_output_uv));
     previous_color = mix(previous_color, remix_color, blend_factor);
-    store16(P.planes.upscale_output, (size_t)coy * OW + cox, v4(current_color, 1.0f));
-    store16(P.planes.upscale_output, (size_t)poy * OW + pox, v4(previous_color, 1.0f));
+    store16(P.planes.upscale_output, render_image_index(P, 2, cox, coy), v4(current_color, 1.0f));
+    store16(P.planes.upscale_output, render_image_index(P, 2, pox, poy), v4(previous_color, 1.0f));
 }
 
 __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x_extrapolate(const __grid_constant__ KParams P) {  // smaa.wgsl:201-271
     int x, y;
     tile_pixel(x, y, P);
     if (!tile_active(P, x, y)) return;
-    const int OW = 2 * P.band.RW, OH = 2 * P.band.RH;
-    const Image16 out{P.planes.upscale_output, OW, OH};
+    const Image16 out = render_image(P, P.planes.upscale_output, 2);
     vec4 t = out.load(2 * x, 2 * y), b = out.load(2 * x + 1, 2 * y + 1), n = out.load(2 * x + 1, 2 * y - 1), e = out.load(2 * x + 2, 2 * y);
     vec4 s_ = out.load(2 * x, 2 * y + 2), w = out.load(2 * x - 1, 2 * y + 1);
     auto lum3 = [](vec4 a, vec4 c) { return luminance(vabs(xyz(a) - xyz(c))); };
@@ -192,8 +220,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x_extrapolate(const __g
         color = color + (tt + bb) * factor_xy.y;
         return color * (0.5f * factor_z);
     };
-    store16(P.planes.upscale_output, (size_t)(2 * y + 1) * OW + 2 * x, blend(t, s_, w, b));
-    store16(P.planes.upscale_output, (size_t)(2 * y) * OW + 2 * x + 1, blend(n, b, t, e));
+    store16(P.planes.upscale_output, render_image_index(P, 2, 2 * x, 2 * y + 1), blend(t, s_, w, b));
+    store16(P.planes.upscale_output, render_image_index(P, 2, 2 * x + 1, 2 * y), blend(n, b, t, e));
 }
 
 // ------------------------------------------------------------------------------------------- taa_jasmine
@@ -204,10 +232,13 @@ __global__ void __launch_bounds__(CTA_THREADS) k_taa_jasmine(const __grid_consta
     if (!tile_active(P, x, y)) return;
     const int OW = smaa ? 2 * P.band.RW : P.band.RW, OH = smaa ? 2 * P.band.RH : P.band.RH, W = P.band.W, H = P.band.H;
     const uint32_t cur = P.in.frame.number % 2u, prv = 1u - cur;
-    const Image16 render{smaa ? P.planes.upscale_output : P.planes.tone_mapped_db[cur], OW, OH};
-    const Image16 previous_render{P.planes.taa_output[prv], OW, OH};
-    const Image32 position{P.planes.pos_depth_db[P.gbuffer_current], W, H}, previous_position{P.planes.pos_depth_db[P.gbuffer_current ^ 1], W, H};
-    const Image32 velocity_uv{P.planes.velocity_uv_db[P.gbuffer_current], W, H}, previous_velocity_uv{P.planes.velocity_uv_db[P.gbuffer_current ^ 1], W, H};
+    const int scale = smaa ? 2 : 1;
+    const Image16 render = render_image(P, smaa ? P.planes.upscale_output : tone_plane(P, cur), scale);
+    const Image16 previous_render = render_image(P, P.planes.taa_output[prv], scale);
+    const Image32 position = gbuffer_image(P, P.planes.pos_depth_db[P.gbuffer_current]);
+    const Image32 previous_position = gbuffer_image(P, P.planes.pos_depth_db[P.gbuffer_current ^ 1]);
+    const Image32 velocity_uv = gbuffer_image(P, P.planes.velocity_uv_db[P.gbuffer_current]);
+    const Image32 previous_velocity_uv = gbuffer_image(P, P.planes.velocity_uv_db[P.gbuffer_current ^ 1]);
     auto sample_previous = [&](vec2 u) { return clamp01(xyz(previous_render.linear(u))); };
     auto sample_render = [&](vec2 u) { return RGB_to_YCoCg(clamp01(xyz(render.nearest(u)))); };
     const vec2 size = v2((float)OW, (float)OH);
@@ -232,7 +263,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_taa_jasmine(const __grid_consta
         vec3 previous_pos = xyz(previous_position.nearest(previous_uv + uv_biases[i]));
         position_miss = position_miss || length(xyz(current_position_depth) - previous_pos) > 0.5f;
     }
-    const size_t oidx = (size_t)y * OW + x;
+    const size_t oidx = render_image_index(P, scale, x, y);
     if (!has_content) {
         store16(P.planes.taa_output[cur], oidx, v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]));
         return;
@@ -294,6 +325,9 @@ using namespace hkd;
 void hk_launch_smaa_tu4x(const KParams& P, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_smaa_tu4x<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+}
+void hk_launch_smaa_tu4x_extrapolate(const KParams& P, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_smaa_tu4x_extrapolate<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }
 void hk_launch_taa_jasmine(const KParams& P, bool smaa, cudaStream_t st) {

@@ -258,6 +258,9 @@ class HikariPlugin:
     def set_motion_margin(self, pixels):
         check(lib().hk_context_set_motion_margin(self.ctx, int(pixels)), self.ctx)
 
+    def enable_tile_upscalers(self, enabled=True):
+        check(lib().hk_context_enable_tile_upscalers(self.ctx, 1 if enabled else 0), self.ctx)
+
     def halo_pull(self, source):
         check(lib().hk_halo_pull(self.ctx, source.ctx), self.ctx)
 

@@ -82,7 +82,8 @@ typedef struct hk_frame_inputs {
     uint32_t smaa_tu4x;              /* 1 = Upscale::SmaaTu4x: SMAA_TU4X jitter index rule (prepass.wgsl:31-35) */
     uint32_t temporal_upscalers;     /* 1 = hk_post_process_run continues past tone mapping with smaa_tu4x + smaa_tu4x_extrapolate
                                         (when smaa_tu4x) and taa_jasmine (when taa_jitter) — post_process.rs:1236-1277, the
-                                        "next" rows K11/K12 of SURVEY.md 8(f).  0 = the hot path ends at tone mapping. */
+                                        "next" rows K11/K12 of SURVEY.md 8(f).  0 = the hot path ends at tone mapping.
+                                        Tiles: see hk_context_enable_tile_upscalers. */
 } hk_frame_inputs;
 
 /* Identifiers for hk_get_output / hk_readback / hk_upload_state.  Read-back formats are the reference's texture /
@@ -201,6 +202,11 @@ int hk_sync(hk_context* ctx);
  * hk_context_set_motion_margin widens the ghost ring from 36 to 36 + `pixels` (re-allocates and clears the tile's state). */
 int hk_context_set_motion_margin(hk_context* ctx, uint32_t pixels);
 int hk_halo_pull(hk_context* dst, hk_context* src);
+/* The temporal upscalers (hk_frame_inputs.temporal_upscalers) on a TILE: allocates the tile's copies of the tone-mapped,
+ * upscaled and TAA images over its allocation (re-allocates and clears the tile's state).  Needs upscale_ratio 1, a
+ * motion margin of at least 4 pixels + the per-frame motion, and hk_halo_pull from every neighbour after each frame (it
+ * also carries the tone-mapped and TAA history of the ghost ring).  HK_OUT_UPSCALED / HK_OUT_TAA then serve the owned part. */
+int hk_context_enable_tile_upscalers(hk_context* ctx, int enabled);
 /* The same between processes (one process per GPU): the owner exports a descriptor — CUDA IPC handles of its forty
  * reservoir quarter-planes and its tile rectangles — which travels to the neighbour by any channel; the neighbour imports it
  * once (maps the planes; peer access over NVLink) and pulls after every frame.  Re-export after hk_context_resize* or

@@ -159,3 +159,64 @@ def test_halo_exchange_between_two_processes_cuda_ipc():
     p.join(30)
     assert status == "done", their_bad
     assert bad == 0 and their_bad == 0, (bad, their_bad)
+
+
+@pytest.mark.parametrize("smaa,taa,rects", [
+    (True, True, [(0, 72, 0, 40), (72, 144, 0, 40), (0, 72, 40, 96), (72, 144, 40, 96)]),
+    (True, False, [(0, 60, 0, 96), (60, 144, 0, 96)]),
+    (False, True, [(0, 144, 0, 50), (0, 144, 50, 96)]),
+])
+def test_temporal_upscalers_on_tiles_equal_unsharded(smaa, taa, rects):
+    """The default pipeline's smaa_tu4x / taa_jasmine on tiles: with the upscaler planes enabled, a motion margin and halo
+    pulls (which also carry the tone-mapped and TAA history of the ghost ring), every tile's part of the upscaled and the TAA
+    image equals the full-frame render bit for bit under camera motion."""
+    from bevy_hikari_b200 import plugin
+    b = Bench("cornell", 144, 96, config="cornell_1080p", taa=plugin.TAA_JASMINE if taa else plugin.TAA_NONE,
+              upscale_kind=plugin.UPSCALE_SMAA_TU4X if smaa else plugin.UPSCALE_FSR1, upscale_ratio=1.0)
+    full = b.device()
+    tiles = [b.device(r[2], r[3], r[0], r[1]) for r in rects]
+    for t in tiles:
+        t.set_motion_margin(16)
+        t.enable_tile_upscalers()
+    outputs = ([L.OUT_UPSCALED] if smaa else []) + ([L.OUT_TAA] if taa else [])
+    k_of = {L.OUT_UPSCALED: 2, L.OUT_TAA: 2 if smaa else 1}
+    for f in range(1, 9):
+        inp = b.moving_inputs(f, step=(0.04, 0.01, -0.02))
+        inp.temporal_upscalers = 1
+        full.render_frame(inp)
+        for t in tiles:
+            t.render_frame(inp)
+        for t in tiles:
+            t.sync()
+        for k in PLANES:
+            whole = full.readback(k)
+            for r, t in zip(rects, tiles):
+                assert mismatch(t.readback(k), whole[r[2]:r[3], r[0]:r[1]]) == 0, (f, k)
+        for k in outputs:
+            whole, s = full.readback(k), k_of[k]
+            for r, t in zip(rects, tiles):
+                part = t.readback(k)
+                assert part.shape[:2] == (s * (r[3] - r[2]), s * (r[1] - r[0]))
+                assert mismatch(part, whole[s * r[2]:s * r[3], s * r[0]:s * r[1]]) == 0, (f, k, r)
+        for t in tiles:
+            for other in tiles:
+                if other is not t:
+                    t.halo_pull(other)
+        for t in tiles:
+            t.sync()
+
+
+def test_tile_upscalers_need_their_planes_and_a_margin():
+    from bevy_hikari_b200 import _ffi
+    b = Bench("cornell", 64, 48, config="cornell_256")
+    t = b.device(0, 24)
+    inp = b.inputs(1)
+    inp.temporal_upscalers = 1
+    with pytest.raises(_ffi.HikariError, match="enable_tile_upscalers"):
+        t.render_frame(inp)
+    t.enable_tile_upscalers()
+    with pytest.raises(_ffi.HikariError, match="motion margin"):
+        t.render_frame(inp)                       # planes are there, the margin is not
+    t.set_motion_margin(4)
+    t.render_frame(inp)
+    t.sync()

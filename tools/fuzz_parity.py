@@ -85,10 +85,20 @@ def tile_case(seed):
     tiles = [b.device(r[2], r[3], r[0], r[1]) for r in rects]
     halo = bool(os.environ.get("HK_FUZZ_HALO"))       # moving camera + motion margin + halo pulls after every frame
     step = tuple(rng.uniform(-0.05, 0.05, 3)) if halo else (0.0, 0.0, 0.0)
+    upscalers = halo and bool(rng.integers(0, 2))     # ... and the temporal upscalers on the tiles
+    if upscalers:
+        b.settings.taa = int(rng.integers(0, 2))
+        b.settings.upscale_kind = int(rng.integers(0, 2))
     if halo:
         for t in tiles:
             t.set_motion_margin(16)
+            if upscalers:
+                t.enable_tile_upscalers()
     planes = [L.OUT_TONE_MAPPED, L.OUT_RENDER_DIRECT, L.OUT_RENDER_EMISSIVE, L.OUT_RENDER_INDIRECT] + [L.OUT_RESERVOIR_0 + i for i in range(10)]
+    scaled = []
+    if upscalers:
+        smaa = b.settings.upscale_kind == plugin.UPSCALE_SMAA_TU4X
+        scaled = ([(L.OUT_UPSCALED, 2)] if smaa else []) + ([(L.OUT_TAA, 2 if smaa else 1)] if b.settings.taa == plugin.TAA_JASMINE else [])
     for f in range(1, int(rng.integers(3, 7))):
         if f > 1 and halo:
             for t in tiles:
@@ -96,6 +106,7 @@ def tile_case(seed):
                     if other is not t:
                         t.halo_pull(other)
         inp = b.moving_inputs(f, step=step)
+        inp.temporal_upscalers = 1 if upscalers else 0
         full.render_frame(inp)
         for t in tiles:
             t.render_frame(inp)
@@ -104,6 +115,11 @@ def tile_case(seed):
             for r, t in zip(rects, tiles):
                 if mismatch(t.readback(k), whole[r[2]:r[3], r[0]:r[1]]):
                     return f"tile seed {seed}: {scene} {w}x{h} rects {rects} frame {f} plane {k} {settings}"
+        for k, sc in scaled:
+            whole = full.readback(k)
+            for r, t in zip(rects, tiles):
+                if mismatch(t.readback(k), whole[sc * r[2]:sc * r[3], sc * r[0]:sc * r[1]]):
+                    return f"tile seed {seed}: {scene} {w}x{h} rects {rects} frame {f} upscaled plane {k} {settings}"
     return None
 
 
