@@ -27,9 +27,9 @@ static const int GHOST_TEMPORAL = GHOST_SPATIAL + 20;       // 36
 static const int RING_SMAA = 2, RING_EXTRAPOLATE = 1, RING_TONE = 4;
 
 struct hk_halo_peer {   // a neighbour tile of another process, mapped through CUDA IPC (hk_halo_import)
-    Planes planes;       // only reservoir[] is filled
+    Planes planes;       // only reservoir[] (and tone_ring_db[] / taa_output[] when exported) are filled
     Band band;
-    void* mapped[40];
+    void* mapped[44];
 };
 
 struct hk_context {
@@ -946,6 +946,15 @@ int hk_halo_export(hk_context* ctx, hk_halo_descriptor* out) {
             HK_CUDA(cudaIpcGetMemHandle(&h, ctx->planes.reservoir[r].q[q]));
             memcpy(out->plane_handles[4 * r + q], &h, 64);
         }
+    if (ctx->planes.tone_ring_db[0]) {
+        uint2* images[4] = {ctx->planes.tone_ring_db[0], ctx->planes.tone_ring_db[1], ctx->planes.taa_output[0], ctx->planes.taa_output[1]};
+        for (int i = 0; i < 4; ++i) {
+            cudaIpcMemHandle_t h;
+            HK_CUDA(cudaIpcGetMemHandle(&h, images[i]));
+            memcpy(out->plane_handles[40 + i], &h, 64);
+        }
+        out->has_images = 1;
+    }
     const Band& b = ctx->band;
     out->frame[0] = b.W; out->frame[1] = b.H;
     out->allocated[0] = b.ax0; out->allocated[1] = b.ax1; out->allocated[2] = b.a0; out->allocated[3] = b.a1;
@@ -963,7 +972,9 @@ int hk_halo_import(hk_context* ctx, const hk_halo_descriptor* remote, hk_halo_pe
     b.ax0 = remote->allocated[0]; b.ax1 = remote->allocated[1]; b.a0 = remote->allocated[2]; b.a1 = remote->allocated[3];
     b.cx0 = remote->owned[0]; b.cx1 = remote->owned[1]; b.r0 = remote->owned[2]; b.r1 = remote->owned[3];
     b.AW = b.ax1 - b.ax0; b.RW = b.W; b.RH = b.H; b.RS = b.AW;
-    for (int i = 0; i < 40; ++i) {
+    peer->planes = Planes{};
+    const int handles = remote->has_images ? 44 : 40;
+    for (int i = 0; i < handles; ++i) {
         cudaIpcMemHandle_t h;
         memcpy(&h, remote->plane_handles[i], 64);
         void* p = nullptr;
@@ -974,7 +985,9 @@ int hk_halo_import(hk_context* ctx, const hk_halo_descriptor* remote, hk_halo_pe
             return set_error(ctx, HK_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
         }
         peer->mapped[i] = p;
-        peer->planes.reservoir[i / 4].q[i % 4] = static_cast<uint4*>(p);
+        if (i < 40) peer->planes.reservoir[i / 4].q[i % 4] = static_cast<uint4*>(p);
+        else if (i < 42) peer->planes.tone_ring_db[i - 40] = static_cast<uint2*>(p);
+        else peer->planes.taa_output[i - 42] = static_cast<uint2*>(p);
     }
     ctx->halo_peers.push_back(peer);
     *out = peer;
@@ -988,6 +1001,7 @@ int hk_halo_pull_peer(hk_context* ctx, hk_halo_peer* peer) {
     if (x0 >= x1 || y0 >= y1) return HK_OK;
     HK_CUDA(cudaSetDevice(ctx->device));
     hk_launch_halo_copy(ctx->planes, ctx->band, peer->planes, peer->band, x0, x1, y0, y1, ctx->stream);
+    halo_pull_images(ctx, peer->planes, peer->band, x0, x1, y0, y1);
     return check_launch(ctx);
 }
 

@@ -264,7 +264,7 @@ class HikariPlugin:
     def halo_pull(self, source):
         check(lib().hk_halo_pull(self.ctx, source.ctx), self.ctx)
 
-    HALO_DESCRIPTOR_BYTES = 40 * 64 + 10 * 4
+    HALO_DESCRIPTOR_BYTES = 44 * 64 + 11 * 4
 
     def halo_export(self):
         """bytes of an hk_halo_descriptor (CUDA IPC handles of the reservoir planes + tile rectangles) for another process"""

@@ -208,11 +208,12 @@ int hk_halo_pull(hk_context* dst, hk_context* src);
  * also carries the tone-mapped and TAA history of the ghost ring).  HK_OUT_UPSCALED / HK_OUT_TAA then serve the owned part. */
 int hk_context_enable_tile_upscalers(hk_context* ctx, int enabled);
 /* The same between processes (one process per GPU): the owner exports a descriptor — CUDA IPC handles of its forty
- * reservoir quarter-planes and its tile rectangles — which travels to the neighbour by any channel; the neighbour imports it
+ * reservoir quarter-planes (and, with tile upscalers, its four history images) and its tile rectangles — which travels to the neighbour by any channel; the neighbour imports it
  * once (maps the planes; peer access over NVLink) and pulls after every frame.  Re-export after hk_context_resize* or
  * hk_context_set_motion_margin (the planes are re-allocated).  Imported peers are released with the importing context. */
 typedef struct hk_halo_descriptor {
-    uint8_t plane_handles[40][64];   /* reservoir r, quarter q at [4 * r + q] */
+    uint8_t plane_handles[44][64];   /* reservoir r, quarter q at [4 * r + q]; [40..41] tone-mapped ring, [42..43] TAA history (tile upscalers) */
+    int32_t has_images;              /* 1 = entries 40..43 are valid (hk_context_enable_tile_upscalers on the exporter) */
     int32_t frame[2];                /* width, height */
     int32_t allocated[4];            /* col_begin, col_end, row_begin, row_end of the allocation (owned + ghosts) */
     int32_t owned[4];

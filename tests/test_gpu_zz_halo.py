@@ -74,24 +74,34 @@ def test_halo_descriptor_path_in_one_process_on_the_emulator():
     from tests.conftest import EMULATED
     if not EMULATED:
         pytest.skip("same-process IPC open exists only in the kernel-logic emulation")
+    from bevy_hikari_b200 import plugin
     rects = [(0, 72, 0, 96), (72, 144, 0, 96)]
-    b = Bench("cornell", 144, 96, config="cornell_1080p")
-    full = b.device()
-    tiles = [b.device(r[2], r[3], r[0], r[1]) for r in rects]
-    for t in tiles:
-        t.set_motion_margin(12)
-    peers = {0: tiles[0].halo_import(tiles[1].halo_export()), 1: tiles[1].halo_import(tiles[0].halo_export())}
-    for f in range(1, 8):
-        inp = b.moving_inputs(f, step=(0.04, 0.01, -0.02))
-        full.render_frame(inp)
+    for upscalers in (False, True):
+        b = Bench("cornell", 144, 96, config="cornell_1080p", taa=plugin.TAA_JASMINE if upscalers else plugin.TAA_NONE)
+        full = b.device()
+        tiles = [b.device(r[2], r[3], r[0], r[1]) for r in rects]
         for t in tiles:
-            t.render_frame(inp)
-        for k in PLANES:
-            whole = full.readback(k)
-            for r, t in zip(rects, tiles):
-                assert mismatch(t.readback(k), whole[r[2]:r[3], r[0]:r[1]]) == 0, (f, k)
-        for i, t in enumerate(tiles):
-            t.halo_pull_peer(peers[i])
+            t.set_motion_margin(12)
+            if upscalers:
+                t.enable_tile_upscalers()
+        peers = {0: tiles[0].halo_import(tiles[1].halo_export()), 1: tiles[1].halo_import(tiles[0].halo_export())}
+        scaled = [(L.OUT_UPSCALED, 2), (L.OUT_TAA, 2)] if upscalers else []
+        for f in range(1, 8):
+            inp = b.moving_inputs(f, step=(0.04, 0.01, -0.02))
+            inp.temporal_upscalers = 1 if upscalers else 0
+            full.render_frame(inp)
+            for t in tiles:
+                t.render_frame(inp)
+            for k in PLANES:
+                whole = full.readback(k)
+                for r, t in zip(rects, tiles):
+                    assert mismatch(t.readback(k), whole[r[2]:r[3], r[0]:r[1]]) == 0, (f, k)
+            for k, s in scaled:
+                whole = full.readback(k)
+                for r, t in zip(rects, tiles):
+                    assert mismatch(t.readback(k), whole[s * r[2]:s * r[3], s * r[0]:s * r[1]]) == 0, (f, k)
+            for i, t in enumerate(tiles):
+                t.halo_pull_peer(peers[i])
 
 
 def _halo_worker(rect, frames, conn):
