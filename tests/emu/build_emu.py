@@ -14,7 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "bevy_hikari_b200", "csrc")
 HOST = os.path.join(ROOT, "bevy_hikari_b200", "host")
-GEN, OUT = os.path.join(HERE, "_gen"), os.path.join(HERE, "_build")
+ASAN = bool(os.environ.get("HK_EMU_ASAN"))      # AddressSanitizer build: a memcheck for the kernels' indexing (run python with
+#                                                  LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)
+GEN, OUT = os.path.join(HERE, "_gen"), os.path.join(HERE, "_build_asan" if ASAN else "_build")
 LIB = os.path.join(OUT, "libhikari_emu.so")
 CU = ["context.cu", "kernels_light.cu", "kernels_post.cu", "kernels_upscale.cu"]
 CPP = ["hikari.cpp", "hikari_capi.cpp"]
@@ -22,6 +24,8 @@ CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 FLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-std=c++17", "-w",
          "-I" + os.path.join(HERE, "include"), "-I" + SRC, "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + \
         os.environ.get("HK_EMU_EXTRA", "").split()      # e.g. -DHK_DENOISE_BRANCHFREE=1: validate a tuning variant's logic
+if ASAN:
+    FLAGS = [f for f in FLAGS if f != "-O2"] + ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
 
 LAUNCH = re.compile(r"([A-Za-z_][A-Za-z_0-9]*(?:<[^<>;]*>)?)<<<([^;]*?)>>>\(([^;]*)\);")
 FLUSH_OLD = re.compile(r"for \(int o = 16; o > 0; o >>= 1\) \{.*?\n    \}\n    if \(\(threadIdx\.x & 31\) == 0\) \{", re.S)
@@ -84,7 +88,7 @@ def build(force=False):
         o = os.path.join(OUT, f + ".o")
         subprocess.run([CXX] + FLAGS + ["-c", os.path.join(HOST, f), "-o", o], check=True)
         objs.append(o)
-    subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs, check=True)
+    subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs + (["-fsanitize=address"] if ASAN else []), check=True)
     print(f"emulator: {launches} launch sites converted -> {LIB}")
     return LIB
 
