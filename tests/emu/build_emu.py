@@ -80,7 +80,7 @@ def build(force=False):
         subprocess.run([CXX] + FLAGS + ["-c", g, "-o", o], check=True)
         objs.append(o)
     glue = os.path.join(GEN, "emu_globals.cpp")
-    open(glue, "w").write('#include "cuda_emu.h"\nthread_local EmuIdx threadIdx, blockIdx;\nthread_local dim3 blockDim, gridDim;\n')
+    open(glue, "w").write('#include "cuda_emu.h"\nthread_local EmuIdx threadIdx, blockIdx;\nthread_local dim3 blockDim, gridDim;\n#include <stdlib.h>\nint emu_reverse_order() { static int v = getenv("HK_EMU_REVERSE") ? 1 : 0; return v; }\n')
     o = os.path.join(OUT, "emu_globals.o")
     subprocess.run([CXX] + FLAGS + ["-I" + HERE, "-c", glue, "-o", o], check=True)
     objs.append(o)

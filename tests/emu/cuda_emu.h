@@ -100,17 +100,25 @@ static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 
 // ------------------------------------------------------------------------------------------------ launches
 // EMU_LAUNCH(grid, block, kernel_call): every thread of every block, blocks distributed over the host cores
+// HK_EMU_REVERSE=1 runs blocks and threads in descending order on one host thread: if a launch's result depended on the order
+// in which its threads run (a read of something another thread of the same launch writes), the parity tests would fail in one
+// of the two orders.  They pass in both.
+extern int emu_reverse_order();
 #define EMU_LAUNCH(GRID, BLOCK, ...)                                                      \
     do {                                                                                  \
         const dim3 emu_g = (GRID), emu_b = (BLOCK);                                       \
         const long long emu_n = (long long)emu_g.x * emu_g.y * emu_g.z;                   \
-        _Pragma("omp parallel for schedule(dynamic, 4)")                                  \
-        for (long long emu_i = 0; emu_i < emu_n; ++emu_i) {                               \
+        const unsigned emu_tn = emu_b.x * emu_b.y * emu_b.z;                              \
+        const bool emu_rev = emu_reverse_order() != 0;                                    \
+        _Pragma("omp parallel for schedule(dynamic, 4) if (!emu_rev)")                    \
+        for (long long emu_j = 0; emu_j < emu_n; ++emu_j) {                               \
+            const long long emu_i = emu_rev ? emu_n - 1 - emu_j : emu_j;                  \
             gridDim = emu_g; blockDim = emu_b;                                            \
             blockIdx.x = (unsigned)(emu_i % emu_g.x);                                     \
             blockIdx.y = (unsigned)((emu_i / emu_g.x) % emu_g.y);                         \
             blockIdx.z = (unsigned)(emu_i / ((long long)emu_g.x * emu_g.y));              \
-            for (unsigned emu_t = 0; emu_t < emu_b.x * emu_b.y * emu_b.z; ++emu_t) {      \
+            for (unsigned emu_u = 0; emu_u < emu_tn; ++emu_u) {                           \
+                const unsigned emu_t = emu_rev ? emu_tn - 1 - emu_u : emu_u;              \
                 threadIdx.x = emu_t % emu_b.x;                                            \
                 threadIdx.y = (emu_t / emu_b.x) % emu_b.y;                                \
                 threadIdx.z = emu_t / (emu_b.x * emu_b.y);                                \

@@ -17,10 +17,15 @@ FILES = ["tests/test_gpu_parity.py", "tests/test_gpu_variants.py", "tests/test_g
          "tests/test_gpu_frame_assembly.py", "tests/test_gpu_zz_examples.py", "tests/test_gpu_zz_halo.py"]
 
 
-def test_gpu_parity_suite_passes_on_emulated_kernels():
+@pytest.mark.parametrize("order", ["forward", "reverse"])
+def test_gpu_parity_suite_passes_on_emulated_kernels(order):
+    """reverse: every launch runs its blocks and threads in descending order on one host thread — results must not depend
+    on the order in which the threads of a launch run"""
     if not shutil.which("g++") and not os.path.exists("/usr/bin/g++"):
         pytest.skip("no host C++ compiler")
     env = dict(os.environ, HK_EMULATE_KERNELS="1")
+    if order == "reverse":
+        env["HK_EMU_REVERSE"] = "1"
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + FILES, cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=1500)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
