@@ -100,3 +100,19 @@ def test_api_corners():
     st = t.stats()
     assert st.kernel_launches == 9 and st.primary_rays == 16 * 24 and st.tlas_rays > 0     # cornell_256: no denoise, no emissive spatial pass
     assert st.ms_total >= 0.0 and all(m >= 0.0 for m in st.ms_kernel)
+
+
+@pytest.mark.parametrize("base", [65535, 2 ** 24 - 3, 2 ** 31 - 4, 2 ** 32 - 6])
+def test_large_frame_counters(base):
+    """frame.number after hours of running and across the u32 wrap: noise texture index, halton index, ping-pong parity,
+    validation intervals and the golden-ratio rotation (a float product of the frame number) stay in step with the oracle"""
+    b = Bench("cornell", 64, 40, config="cornell_1080p", taa=plugin.TAA_JASMINE, upscale_ratio=1.5)
+    dev, orc = b.device(), b.oracle()
+    dev.set_keep_intermediates(True)
+    for f in range(1, 7):
+        inp = b.moving_inputs(f)
+        inp.frame.number = (base + f) & 0xFFFFFFFF
+        inp.temporal_upscalers = 1
+        dev.render_frame(inp)
+        orc.render_frame(inp)
+        compare_all(dev, orc, ALL_PLANES + DENOISED + [L.OUT_UPSCALED, L.OUT_TAA], f)
