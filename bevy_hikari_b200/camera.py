@@ -22,6 +22,24 @@ def perspective_infinite_reverse_rh(fov_y, aspect, z_near):
     return m
 
 
+def orthographic_reverse_rh(half_height, aspect, z_near, z_far):
+    """bevy OrthographicProjection::get_projection_matrix: glam Mat4::orthographic_rh(left, right, bottom, top, far, near)
+    (near and far swapped for reverse Z); returned as [col][row].  projection[3][3] == 1 is what light.wgsl:1040 tests."""
+    hw = half_height * aspect
+    left, right, bottom, top = -hw, hw, -half_height, half_height
+    near, far = z_far, z_near                       # the swapped arguments
+    rw, rh, r = 1.0 / (right - left), 1.0 / (top - bottom), 1.0 / (near - far)
+    m = np.zeros((4, 4), F)
+    m[0, 0] = F(rw + rw)
+    m[1, 1] = F(rh + rh)
+    m[2, 2] = F(r)
+    m[3, 0] = F(-(left + right) * rw)
+    m[3, 1] = F(-(top + bottom) * rh)
+    m[3, 2] = F(r * near)
+    m[3, 3] = F(1.0)
+    return m
+
+
 def look_at(eye, target, up=(0.0, 1.0, 0.0)):
     """Transform::from_translation(eye).looking_at(target, up) -> camera world matrix [col][row]."""
     eye, target, up = (np.asarray(v, np.float64) for v in (eye, target, up))

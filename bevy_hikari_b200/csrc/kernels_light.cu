@@ -39,8 +39,14 @@ __device__ __forceinline__ Ray primary_ray(const KParams& P, const mat4& inv_vie
     vec4 p = mul(inv_view_proj, v4(ndc.x, ndc.y, 1.0f, 1.0f));
     vec3 near_point = xyz(p) / p.w;
     Ray ray;
-    ray.origin = v3(P.in.view.world_position[0], P.in.view.world_position[1], P.in.view.world_position[2]);
-    ray.direction = normalize(near_point - ray.origin);
+    if (P.in.view.projection[15] == 1.0f) {   // orthographic (light.wgsl:1040): parallel lines of sight, near plane -> far plane
+        vec4 q = mul(inv_view_proj, v4(ndc.x, ndc.y, 0.0f, 1.0f));
+        ray.origin = near_point;
+        ray.direction = normalize(xyz(q) / q.w - near_point);
+    } else {
+        ray.origin = v3(P.in.view.world_position[0], P.in.view.world_position[1], P.in.view.world_position[2]);
+        ray.direction = normalize(near_point - ray.origin);
+    }
     ray.inv_direction = 1.0f / ray.direction;
     return ray;
 }

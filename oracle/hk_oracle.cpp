@@ -714,8 +714,16 @@ Ray primary_ray(const Ctx& c, float px, float py, vec2 jitter_ndc) {
     vec4 p = mul(ldm(c.in.view.inverse_view_proj), v4(ndc.x, ndc.y, 1.0f, 1.0f));
     vec3 near_point = xyz(p) / p.w;
     Ray ray;
-    ray.origin = ld3(c.in.view.world_position);
-    ray.direction = normalize(near_point - ray.origin);
+    if (is_orthographic(c)) {
+        // parallel projection (what the raster prepass draws for an OrthographicProjection): the line of sight of the pixel
+        // runs from its point on the near plane (NDC z = 1, reverse Z) towards its point on the far plane (NDC z = 0)
+        vec4 q = mul(ldm(c.in.view.inverse_view_proj), v4(ndc.x, ndc.y, 0.0f, 1.0f));
+        ray.origin = near_point;
+        ray.direction = normalize(xyz(q) / q.w - near_point);
+    } else {
+        ray.origin = ld3(c.in.view.world_position);
+        ray.direction = normalize(near_point - ray.origin);
+    }
     ray.inv_direction = 1.0f / ray.direction;
     return ray;
 }

@@ -141,3 +141,17 @@ def city_animation(bench):
     """the emissive earth sphere rotates and bobs (the reference's animated light), one house part slides"""
     return Animation(bench, {1: lambda f: rotation_y_about(0.1 * f, (0.0, 1.0, 0.0), (0.0, 0.05 * np.sin(0.5 * f), 0.0)),
                              2: lambda f: rotation_y_about(0.0, (0, 0, 0), (0.02 * f, 0.0, 0.0))})
+
+
+def orthographic_inputs(bench, frame, half_height=1.3, shift=(0.0, 0.0, 0.0)):
+    """frame inputs for an OrthographicProjection camera at the scene's eye / target (+ `shift` * (frame - 1))"""
+    from bevy_hikari_b200 import camera as cam
+    from bevy_hikari_b200 import plugin
+
+    def view_at(f):
+        eye = tuple(e + s * (f - 1) for e, s in zip(bench.scene.eye, shift))
+        tgt = tuple(t + s * (f - 1) for t, s in zip(bench.scene.target, shift))
+        proj = cam.orthographic_reverse_rh(half_height, bench.width / bench.height, 0.1, 50.0)
+        return cam.make_view(cam.look_at(eye, tgt), proj, bench.width, bench.height)
+    view = view_at(frame)
+    return plugin.make_frame_inputs(bench.settings, frame, view, cam.make_previous_view(view_at(max(frame - 1, 1))), bench.lights)

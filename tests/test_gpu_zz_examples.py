@@ -116,3 +116,16 @@ def test_large_frame_counters(base):
         dev.render_frame(inp)
         orc.render_frame(inp)
         compare_all(dev, orc, ALL_PLANES + DENOISED + [L.OUT_UPSCALED, L.OUT_TAA], f)
+
+
+def test_orthographic_camera_bit_exact():
+    from tests.conftest import orthographic_inputs
+    b = Bench("cornell", 96, 64, config="cornell_1080p")
+    dev, orc = b.device(), b.oracle()
+    dev.set_keep_intermediates(True)
+    for f in range(1, 7):
+        inp = orthographic_inputs(b, f, shift=(0.03, 0.0, 0.0))
+        dev.render_frame(inp)
+        orc.render_frame(inp)
+        compare_all(dev, orc, ALL_PLANES + DENOISED, f)
+    assert (dev.readback(L.OUT_GBUFFER_POSITION)[..., 3] > 0).mean() > 0.35
