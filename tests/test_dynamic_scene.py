@@ -128,3 +128,25 @@ def test_update_instances_equals_full_upload_in_oracle():
         a.render_frame(inp); c.render_frame(inp)
         for k in (L.OUT_TONE_MAPPED, L.OUT_GBUFFER_VELOCITY_UV, L.OUT_RESERVOIR_0 + 9):
             assert np.array_equal(np.ascontiguousarray(a.readback(k)).view(np.uint8), np.ascontiguousarray(c.readback(k)).view(np.uint8)), (f, k)
+
+
+def test_visibility_changes_rebuild_the_instance_list():
+    """instance.rs:357: invisible entities are dropped before the TLAS is built; instance ids are ranks among the visible ones"""
+    b = Bench("cornell", 48, 36, config="cornell_256")
+    w = b.world
+    n = len(w.buffers()["instances"])
+    w.set_instance_visible(6, False)
+    w.previous_transform_system(); w.prepare_instances()
+    bufs = w.buffers()
+    assert len(bufs["instances"]) == n - 1 and len(bufs["instance_nodes"]) == 3 * (n - 1) - 2
+    assert w.previous_models().shape == (n - 1, 16)
+    orc = b.oracle()
+    orc.update_instances_desc(w.scene_desc())
+    orc.prepass(b.inputs(1))
+    ids = np.floor(orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)[..., 0]).astype(int)
+    materials = np.floor(orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)[..., 1]).astype(int)
+    hit = orc.readback(L.OUT_GBUFFER_POSITION)[..., 3] > 0
+    assert ids[hit].max() == n - 2 and 6 not in set(materials[hit])        # the short box (material 6) is gone, the tall box moved up a rank
+    w.set_instance_visible(6, True)
+    w.previous_transform_system(); w.prepare_instances()
+    assert len(w.buffers()["instances"]) == n
