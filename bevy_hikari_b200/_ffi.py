@@ -79,6 +79,8 @@ SYMBOLS = {
     "hikari_world_add_material": (_U32, [_P, _P]),
     "hikari_world_add_texture": (_U32, [_P, C.POINTER(L.TextureDesc)]),
     "hikari_world_add_instance": (_U32, [_P, _U32, _U32, _P, _U32]),
+    "hikari_world_set_material": (None, [_P, _U32, _P]),
+    "hikari_world_prepare_materials": (None, [_P]),
     "hikari_world_prepare": (None, [_P]),
     "hikari_world_prepare_instances": (None, [_P]),
     "hikari_world_set_instance_transform": (None, [_P, _U32, _P]),

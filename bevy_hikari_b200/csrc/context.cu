@@ -40,7 +40,7 @@ struct hk_context {
     size_t band_pixels = 0, owned_pixels = 0;
     std::vector<void*> allocations;        // per-pixel planes
     std::vector<void*> scene_allocations;  // scene buffers: meshes, BLAS nodes, materials, textures
-    struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[7];   // scene buffers rewritten by hk_scene_update_instances (grow-only)
+    struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[8];   // scene buffers rewritten by hk_scene_update_instances (grow-only)
     bool mesh_boxes_match = false;         // BLAS half of DeviceScene::leaf_boxes_match
     uint32_t scene_material_count = 0, scene_asset_node_count = 0, scene_primitive_count = 0;
     Planes planes{};
@@ -331,13 +331,16 @@ static cudaError_t upload_into(hk_context* ctx, hk_context::DevBuf& b, const T**
 // Validation + upload of the per-frame half of the scene (instances, TLAS, emissives, emissive BVH, alias tables,
 // previous model matrices) into `d`.  Frees the previous copies.
 static int upload_instances(hk_context* ctx, const hk_scene_desc* s, DeviceScene& d) {
+    // materials travel with the per-frame half when given (material.rs:139-203 rewrites them whenever a material changes)
+    const bool new_materials = s->materials != nullptr && s->material_count > 0;
+    const uint32_t material_count = new_materials ? s->material_count : ctx->scene_material_count;
     if ((s->instance_count && !s->instances) || (s->instance_node_count && !s->instance_nodes) ||
         (s->emissive_node_count && !s->emissive_nodes) || (s->emissive_count && !s->emissives) || (s->alias_count && !s->alias_table))
         return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "scene buffer pointer is NULL with a non-zero count");
     // validate indices once so that kernels can skip bounds checks
     for (uint32_t i = 0; i < s->instance_count; ++i) {
         const hk_instance& in = s->instances[i];
-        if (in.material >= ctx->scene_material_count || (uint64_t)in.mesh.node_offset + in.mesh.node_count > ctx->scene_asset_node_count)
+        if (in.material >= material_count || (uint64_t)in.mesh.node_offset + in.mesh.node_count > ctx->scene_asset_node_count)
             return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "instance references a material / node range out of bounds");
     }
     // Does every leaf record sit right behind a navigator whose box is the shape's own AABB?  (true for bvh 0.7.1's
@@ -354,6 +357,10 @@ static int upload_instances(hk_context* ctx, const hk_scene_desc* s, DeviceScene
     }
     HK_CUDA(cudaStreamSynchronize(ctx->stream));   // frames in flight still read the buffers that are overwritten below
     d.leaf_boxes_match = boxes_match ? 1u : 0u;
+    if (new_materials) {
+        HK_CUDA(upload_into(ctx, ctx->ibuf[7], &d.materials, s->materials, s->material_count));
+        ctx->scene_material_count = s->material_count;
+    }
     HK_CUDA(upload_into(ctx, ctx->ibuf[0], &d.alias_table, s->alias_table, s->alias_count));
     HK_CUDA(upload_into(ctx, ctx->ibuf[1], &d.instances, s->instances, s->instance_count));
     HK_CUDA(upload_into(ctx, ctx->ibuf[2], &d.instance_nodes, s->instance_nodes, s->instance_node_count));
@@ -414,14 +421,14 @@ int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
     free_list(ctx->scene_allocations);
     ctx->scene_ready = false;
     ctx->mesh_boxes_match = boxes_match;
-    ctx->scene_material_count = s->material_count;
+    ctx->scene_material_count = 0;
     ctx->scene_asset_node_count = s->asset_node_count;
     ctx->scene_primitive_count = s->primitive_count;
     DeviceScene d{};
     HK_CUDA(upload(ctx, &d.vertices, s->vertices, s->vertex_count));
     HK_CUDA(upload(ctx, &d.primitives, s->primitives, s->primitive_count));
     HK_CUDA(upload(ctx, &d.asset_nodes, s->asset_nodes, s->asset_node_count));
-    HK_CUDA(upload(ctx, &d.materials, s->materials, s->material_count));
+    d.materials = nullptr;           // uploaded with the per-frame half below
     d.texture_count = s->texture_count;
     d.textures = nullptr;
     if (s->texture_count) {

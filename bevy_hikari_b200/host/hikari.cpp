@@ -359,6 +359,7 @@ std::vector<hk_alias_entry> GpuMesh::build_alias_table(const float transform[16]
 // ======================================================================================= MeshMaterialWorld
 uint32_t MeshMaterialWorld::add_mesh(const Mesh& mesh) { meshes_.push_back(mesh); return (uint32_t)meshes_.size() - 1; }
 uint32_t MeshMaterialWorld::add_material(const StandardMaterial& m) { materials_in_.push_back(m); return (uint32_t)materials_in_.size() - 1; }
+void MeshMaterialWorld::set_material(uint32_t id, const StandardMaterial& m) { if (id < materials_in_.size()) materials_in_[id] = m; }
 uint32_t MeshMaterialWorld::add_instance(const InstanceDesc& i) { instances_in_.push_back(i); return (uint32_t)instances_in_.size() - 1; }
 void MeshMaterialWorld::set_instance_transform(uint32_t instance, const float transform[16]) {
     if (instance < instances_in_.size()) memcpy(instances_in_[instance].transform, transform, 64);

@@ -133,6 +133,7 @@ public:
     HikariUniversalSettings universal_settings;
     uint32_t add_mesh(const Mesh& mesh);                   // Assets<Mesh>::add + extract (mesh.rs:77-104); id = asset order
     uint32_t add_material(const StandardMaterial& m);      // id = rank in the BTreeMap (material.rs:162-165)
+    void set_material(uint32_t id, const StandardMaterial& m);   // Assets<StandardMaterial> modified -> prepare_material_assets + prepare_instances
     uint32_t add_texture(const hk_texture_desc& t, const uint8_t* pixels);
     uint32_t add_instance(const InstanceDesc& inst);       // id = rank in BTreeMap<Entity,..> (instance.rs:231-239)
     void prepare_mesh_assets();                            // mesh.rs:106-166

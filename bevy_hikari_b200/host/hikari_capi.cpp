@@ -81,7 +81,11 @@ uint32_t hikari_world_add_mesh(hikari_world* w, const float* positions, const fl
                                : (topology == 1 ? PrimitiveTopology::TriangleStrip : PrimitiveTopology::Other);
     return W(w)->add_mesh(m);
 }
-uint32_t hikari_world_add_material(hikari_world* w, const hk_material* m) {
+static StandardMaterial to_standard_material(const hk_material* m);
+void hikari_world_set_material(hikari_world* w, uint32_t id, const hk_material* m) { W(w)->set_material(id, to_standard_material(m)); }
+void hikari_world_prepare_materials(hikari_world* w) { W(w)->prepare_material_assets(); }
+uint32_t hikari_world_add_material(hikari_world* w, const hk_material* m) { return W(w)->add_material(to_standard_material(m)); }
+static StandardMaterial to_standard_material(const hk_material* m) {
     StandardMaterial s;
     memcpy(s.base_color.data(), m->base_color, 16);
     memcpy(s.emissive.data(), m->emissive, 16);
@@ -89,7 +93,7 @@ uint32_t hikari_world_add_material(hikari_world* w, const hk_material* m) {
     s.base_color_texture = m->base_color_texture; s.emissive_texture = m->emissive_texture;
     s.metallic_roughness_texture = m->metallic_roughness_texture; s.normal_map_texture = m->normal_map_texture;
     s.occlusion_texture = m->occlusion_texture;
-    return W(w)->add_material(s);
+    return s;
 }
 uint32_t hikari_world_add_texture(hikari_world* w, const hk_texture_desc* t) { return W(w)->add_texture(*t, t->rgba8); }
 uint32_t hikari_world_add_instance(hikari_world* w, uint32_t mesh, uint32_t material, const float* transform16, uint32_t visible) {

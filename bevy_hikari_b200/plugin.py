@@ -72,6 +72,14 @@ class World:
         m[0] = material_record
         return lib().hikari_world_add_material(self._w, m.ctypes.data)
 
+    def set_material(self, material_id, material_record):
+        m = np.zeros(1, L.MATERIAL)
+        m[0] = material_record
+        lib().hikari_world_set_material(self._w, material_id, m.ctypes.data)
+
+    def prepare_materials(self):
+        lib().hikari_world_prepare_materials(self._w)
+
     def add_texture(self, rgba, address_mode_u=0, address_mode_v=0, filter_linear=1, srgb=1):
         rgba = np.ascontiguousarray(rgba, np.uint8)
         t = L.TextureDesc(rgba.ctypes.data, rgba.shape[1], rgba.shape[0], address_mode_u, address_mode_v, filter_linear, srgb)

@@ -165,10 +165,11 @@ int hk_context_resize_tile(hk_context* ctx, uint32_t width, uint32_t height, uin
 int hk_reset_temporal_state(hk_context* ctx);   /* zero reservoirs, as re-allocation does in light.rs:342-363 */
 
 int hk_scene_upload(hk_context* ctx, const hk_scene_desc* scene);
-/* The per-frame part of the scene, for animated instances: replaces instances, instance_nodes (TLAS), emissives,
+/* The per-frame part of the scene, for animated instances and materials: replaces instances, instance_nodes (TLAS), emissives,
  * emissive_nodes, alias_table and previous_instance_models — what MeshMaterialRenderAssets / InstanceRenderAssets::set +
- * write_buffer rewrite when an instance event fires (instance.rs:352-437) — and leaves meshes, BLAS nodes, materials and
- * textures of the last hk_scene_upload in place.  Only those members of `scene` are read. */
+ * write_buffer rewrite when an instance event fires (instance.rs:352-437) — and, when `materials` is not NULL, the material
+ * records (material.rs:139-203; texture indices keep referring to the uploaded textures).  Meshes, BLAS nodes and textures
+ * of the last hk_scene_upload stay in place.  Only those members of `scene` are read. */
 int hk_scene_update_instances(hk_context* ctx, const hk_scene_desc* scene);
 int hk_set_noise(hk_context* ctx, const uint8_t* rgba8_64x64x16);   /* 16 textures of 64x64 RGBA8, lib.rs:189-219 */
 

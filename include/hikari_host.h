@@ -49,6 +49,10 @@ void hikari_world_destroy(hikari_world* w);
 uint32_t hikari_world_add_mesh(hikari_world* w, const float* positions, const float* normals, const float* uvs,
                                uint32_t vertex_count, const uint32_t* indices, uint32_t index_count, uint32_t topology);
 uint32_t hikari_world_add_material(hikari_world* w, const hk_material* m);
+/* a modified StandardMaterial asset: set, then hikari_world_prepare_materials (material.rs:139-203) and
+ * hikari_world_prepare_instances (emissive list / alias tables depend on the materials), then hikari_plugin_update_instances */
+void hikari_world_set_material(hikari_world* w, uint32_t id, const hk_material* m);
+void hikari_world_prepare_materials(hikari_world* w);
 uint32_t hikari_world_add_texture(hikari_world* w, const hk_texture_desc* t);
 uint32_t hikari_world_add_instance(hikari_world* w, uint32_t mesh, uint32_t material, const float* transform16, uint32_t visible);
 void hikari_world_prepare(hikari_world* w);                               /* prepare_mesh_assets -> materials -> instances */

@@ -1724,6 +1724,7 @@ int hko_scene_update_instances(hko_context* c, const hk_scene_desc* s) {   // in
     assign(c->instance_nodes, s->instance_nodes, s->instance_node_count);
     assign(c->emissive_nodes, s->emissive_nodes, s->emissive_node_count);
     assign(c->emissives, s->emissives, s->emissive_count);
+    if (s->materials && s->material_count) assign(c->materials, s->materials, s->material_count);   // material.rs:139-203
     c->previous_models.clear();
     if (s->previous_instance_models) c->previous_models.assign(s->previous_instance_models, s->previous_instance_models + 16 * (size_t)s->instance_count);
     return HK_OK;

@@ -84,3 +84,28 @@ def test_update_instances_errors():
     t.update_instances(an.step(1))
     t.render_frame(b.inputs(1))
     t.sync()
+
+
+def test_animated_materials_bit_exact():
+    """A StandardMaterial modified every frame (the light's emissive colour pulses, a wall changes colour and roughness):
+    materials, emissive list and alias tables are rebuilt on the host and replaced through hk_scene_update_instances."""
+    b = Bench("cornell", 96, 64, config="cornell_1080p")
+    dev, orc = b.device(), b.oracle()
+    dev.set_keep_intermediates(True)
+    w = b.world
+    mats = b.scene.materials.copy()
+    for f in range(1, 9):
+        light = mats[4].copy()
+        light["emissive"] = (1.0, 0.6 + 0.05 * f, 0.3, 0.5 + 0.06 * f) if f != 5 else (0.0, 0.0, 0.0, 1.0)   # frame 5: the light is switched off
+        wall = mats[3].copy()
+        wall["base_color"] = (0.2 + 0.1 * f, 0.9 - 0.1 * f, 0.3, 1.0)
+        wall["perceptual_roughness"] = 0.1 * f
+        w.set_material(4, light); w.set_material(3, wall)
+        w.prepare_materials(); w.previous_transform_system(); w.prepare_instances()
+        assert len(w.buffers()["emissives"]) == (0 if f == 5 else 1)
+        dev.update_instances(w)
+        orc.update_instances_desc(w.scene_desc())
+        inp = b.inputs(f)
+        dev.render_frame(inp)
+        orc.render_frame(inp)
+        compare_all(dev, orc, ALL_PLANES + DENOISED, f)
