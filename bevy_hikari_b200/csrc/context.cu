@@ -532,6 +532,7 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
         P.band.RH = (int)ceilf(scale * (float)P.band.H);
         P.band.RS = P.band.RW;
     }
+    P.inv_rw = 1.0f / (float)P.band.RW; P.inv_rh = 1.0f / (float)P.band.RH;
     ctx->last_render_w = P.band.RW; ctx->last_render_h = P.band.RH; ctx->last_smaa = in->smaa_tu4x != 0; ctx->last_number = in->frame.number;
     P.counters = ctx->count_rays ? ctx->counters : nullptr;
     P.noise = ctx->noise;

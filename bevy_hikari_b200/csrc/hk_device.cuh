@@ -140,6 +140,7 @@ struct KParams {
     // receives this context's owned pixels at their global position; nullptr = none
     uint2* frame_target;
     uint32_t frame_pitch;   // pixels
+    float inv_rw, inv_rh;   // RN(1 / RW), RN(1 / RH), computed on the host (HK_SPATIAL_FAST_DIV)
     int tile_images;        // 1 = tile context with the temporal upscalers enabled: render-size images are stored over the allocation
 };
 

@@ -8,6 +8,9 @@
 #ifndef HK_SPATIAL_EAGER_LOAD
 #define HK_SPATIAL_EAGER_LOAD 0
 #endif
+#ifndef HK_SPATIAL_FAST_DIV
+#define HK_SPATIAL_FAST_DIV 0
+#endif
 
 namespace hkd {
 
@@ -568,7 +571,17 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
         vec2 unit = normalize(offset);
         for (uint32_t j = 1u; j <= tap_count; j += 1u) {
             float tap_dist = T.tap_dist[i][j - 1u];
+#if HK_SPATIAL_FAST_DIV
+            // Tuning variant (off by default): x / C for the frame constant C as q = x * y, r = fma(-q, C, x), fma(r, y, q)
+            // with y = RN(1 / C) from the host — the correctly rounded quotient whenever it is a normal number
+            // (tools/check_runtime_division.cpp: all 2^32 inputs for the benchmark extents); a subnormal quotient is absorbed
+            // by the addition to uv >= 0.5 / size.
+            const vec2 tap_offset = tap_dist * unit;
+            const float qx = tap_offset.x * P.inv_rw, qy = tap_offset.y * P.inv_rh;
+            vec2 tap_uv = uv + v2(fmaf(fmaf(-qx, size_f.x, tap_offset.x), P.inv_rw, qx), fmaf(fmaf(-qy, size_f.y, tap_offset.y), P.inv_rh, qy));
+#else
             vec2 tap_uv = uv + (tap_dist * unit) / size_f;
+#endif
             vec2 tap_deferred_uv = jittered_deferred_uv(P, tap_uv, 0.25f);
             int tx = f32_to_i32(tap_deferred_uv.x * (float)P.band.W), ty = f32_to_i32(tap_deferred_uv.y * (float)P.band.H);
             float tap_depth = 0.0f;  // out-of-bounds textureLoad -> 0

@@ -3,7 +3,7 @@
 # spent and is validated only on the emulated kernels (tests/emu/); this confirms it on the device and times the two prepared
 # tuning variants.  Before calling (on the CPU box, nvcc cross-compiles):
 #     python tools/build_variants.py denoise='-DHK_DENOISE_BRANCHFREE=1' spatial='-DHK_SPATIAL_EAGER_LOAD=1' \
-#            both='-DHK_DENOISE_BRANCHFREE=1 -DHK_SPATIAL_EAGER_LOAD=1'
+#            fastdiv='-DHK_SPATIAL_FAST_DIV=1' all='-DHK_DENOISE_BRANCHFREE=1 -DHK_SPATIAL_EAGER_LOAD=1 -DHK_SPATIAL_FAST_DIV=1'
 #     gpurun --timeout 1200 -- tools/next_round_first_call.sh
 mkdir -p gpurun_out
 echo "== device suite, newest tests first"
