@@ -170,6 +170,39 @@ def city():
                      sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 4.0, math.pi / 4.0, 0.0)))
 
 
+def town():
+    """examples/scene.rs:54-143 (BASELINE configs[2]): ground plane scaled (10000,1,10000) at y = -3, assets/models/scene.gltf
+    (84 meshes / instances, 120 440 triangles, 66 materials, 52 base-colour textures, shipped box-filtered to <= 256 px),
+    emissive UV sphere r = 0.5 at (2,2,0) with the earth texture, sun 100 klx rotated XYZ(-pi/4, pi/4, 0), camera
+    (-20,10,20) -> origin.  Instance order = entity order: the two PbrBundles spawned in `setup` precede the entities the
+    glTF scene spawner creates once the asset has loaded."""
+    tm, tmat, ttex, tim, timat, tixf = _load_npz("town", texture_offset=1)
+    meshes, mat_list, textures = [], [], []
+    inst_mesh, inst_mat, inst_xf = [], [], []
+    # ground (scene.rs:60-76)
+    meshes.append(_plane_mesh(1.0)); mat_list.append(_std_material(base=(0.8, 0.7, 0.6, 1.0), rough=0.9))
+    inst_mesh.append(0); inst_mat.append(0); inst_xf.append(_translation(0.0, -3.0, 0.0, (10000.0, 1.0, 10000.0)))
+    # emissive sphere (scene.rs:85-107); bevy's default image sampler clamps
+    earth = np.load(os.path.join(SCENES, "earth.npz"))["rgba"]
+    textures.append({"rgba": earth, "address_mode_u": 1, "address_mode_v": 1, "filter_linear": 1, "srgb": 1})
+    sphere_mat = _std_material(base=(1, 1, 1, 1), emissive=(1.0, 1.0, 1.0, 0.5))
+    sphere_mat["base_color_texture"] = 0
+    sphere_mat["emissive_texture"] = 0
+    meshes.append(_uv_sphere_mesh(0.5, 36, 18)); mat_list.append(sphere_mat)
+    rot = np.zeros((4, 4), F)   # Quat::from_rotation_x(-pi/2)
+    rot[0, 0] = 1.0; rot[1, 2] = -1.0; rot[2, 1] = 1.0; rot[3, :] = (2.0, 2.0, 0.0, 1.0)
+    inst_mesh.append(1); inst_mat.append(1); inst_xf.append(rot.reshape(16))
+    # the glTF scene, Transform::default() (scene.rs:79-83)
+    mesh0, mat0 = len(meshes), len(mat_list)
+    meshes.extend(tm); mat_list.extend(list(tmat)); textures.extend(ttex)
+    for me, ma, xf in zip(tim, timat, tixf):
+        inst_mesh.append(mesh0 + int(me)); inst_mat.append(mat0 + int(ma)); inst_xf.append(np.asarray(xf, F))
+    mats = np.array(mat_list, L.MATERIAL)
+    return SceneData(meshes, mats, textures, inst_mesh, inst_mat, inst_xf, eye=(-20.0, 10.0, 20.0), target=(0.0, 0.0, 0.0),
+                     sun_illuminance=100000.0,
+                     sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 4.0, math.pi / 4.0, 0.0)))
+
+
 def _box_mesh(sx=1.0, sy=1.0, sz=1.0):
     """bevy shape::Box::new(sx, sy, sz) (shape::Cube { size } = Box::new(size, size, size)): 24 vertices, 6 faces in
     bevy's order (+z, -z, +x, -x, +y, -y), two triangles per face."""
@@ -352,7 +385,7 @@ def terrain(n=224, seed=7):
                      sun_direction_to_light=tuple(cam.euler_xyz_back(-math.pi / 3.0, math.pi / 5.0, 0.0)))
 
 
-SCENE_BUILDERS = {"cornell": cornell, "city": city, "terrain": terrain, "minimal": minimal, "simple": simple, "samplers": samplers}
+SCENE_BUILDERS = {"cornell": cornell, "city": city, "town": town, "terrain": terrain, "minimal": minimal, "simple": simple, "samplers": samplers}
 
 # BASELINE.json configs.  All run with Upscale::SmaaTu4x{ratio 1.0}, Taa::None so that the render
 # resolution equals the stated resolution.
@@ -365,6 +398,10 @@ CONFIGS = {
     "cornell_1080p": dict(scene="cornell", width=1920, height=1080,
                           settings=dict(indirect_bounces=2, denoise=1, temporal_reuse=1, emissive_spatial_reuse=1,
                                         indirect_spatial_reuse=1)),
+    # configs[2]: examples/scene.rs 1920x1080, 3 bounces, emissive + indirect spatial reuse
+    "scene_1080p": dict(scene="town", width=1920, height=1080,
+                        settings=dict(indirect_bounces=3, denoise=1, temporal_reuse=1, emissive_spatial_reuse=1,
+                                      indirect_spatial_reuse=1)),
     # configs[3]: city 3840x2160, 2 bounces, indirect spatial + denoise, row bands over 4 GPUs
     "city_4k": dict(scene="city", width=3840, height=2160,
                     settings=dict(indirect_bounces=2, denoise=1, temporal_reuse=1, emissive_spatial_reuse=0,

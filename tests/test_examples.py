@@ -84,3 +84,27 @@ def test_simple_example_samples_both_emissives():
     assert near_a.mean() > 0.15 and near_b.sum() > 50 and near_a.sum() > 3 * near_b.sum(), (near_a.sum(), near_b.sum())
     emissive = orc.readback(L.OUT_RENDER_EMISSIVE).astype(np.float32)[..., :3]
     assert emissive.mean() > 0.01 and np.isfinite(emissive).all()
+
+
+def test_town_scene_of_config_3():
+    """examples/scene.rs (BASELINE configs[2]): assets/models/scene.gltf — the largest BLAS set of the configs (121 666
+    primitives, 364 826 asset nodes) — host builder against the numpy builder, counts against the asset, and the oracle's
+    G-buffer against brute force over all world triangles."""
+    sc = scenes.town()
+    pb = compare_builds(sc)
+    inst = pb["instances"]
+    check_bvh(pb["instance_nodes"], inst["min"], inst["max"])
+    assert len(inst) == 86 and len(pb["instance_nodes"]) == 3 * 86 - 2
+    assert len(pb["primitives"]) == 120440 + 1224 + 2 and len(pb["asset_nodes"]) == 3 * len(pb["primitives"]) - 2 * 86
+    assert len(pb["materials"]) == 68 and len(pb["emissives"]) == 1 and int(pb["emissives"]["instance"][0]) == 1
+    assert np.allclose(pb["emissives"]["position"][0], [2.0, 2.0, 0.0], atol=1e-6)
+    b = Bench("town", 96, 54, config="scene_1080p")
+    covered = gbuffer_matches_brute_force(b, np.array([-20.0, 10.0, 20.0]))
+    assert covered.mean() > 0.9            # the 10 km ground plane fills the frame below the horizon
+    orc = b.oracle()
+    for f in range(1, 4):
+        orc.render_frame(b.inputs(f))
+    tm = orc.readback(L.OUT_TONE_MAPPED).astype(np.float32)
+    assert np.isfinite(tm).all() and 0.05 < tm[..., :3].mean() < 0.6
+    direct = orc.readback(L.OUT_RENDER_DIRECT).astype(np.float32)[..., :3].sum(axis=2)
+    assert (direct[covered] > 0.05).mean() > 0.2 and (direct[covered] == 0).mean() > 0.05    # sun-lit and shadowed parts

@@ -129,3 +129,20 @@ def test_orthographic_camera_bit_exact():
         orc.render_frame(inp)
         compare_all(dev, orc, ALL_PLANES + DENOISED, f)
     assert (dev.readback(L.OUT_GBUFFER_POSITION)[..., 3] > 0).mean() > 0.35
+
+
+def test_town_scene_of_config_3():
+    """BASELINE configs[2] (examples/scene.rs: scene.gltf, 120 440 triangles in 84 meshes, 52 textures, sun + emissive sphere, 3
+    bounces, both spatial reuses, denoise) at a small frame size: every plane of every frame bit-equal to the oracle, static
+    and moving camera"""
+    b = Bench("town", 160, 90, config="scene_1080p")
+    dev, orc = b.device(), b.oracle()
+    dev.set_keep_intermediates(True)
+    dev.set_profiling(True, False)         # the ray-counting kernel variants
+    for f in range(1, 6):
+        inp = b.inputs(f) if f < 3 else b.moving_inputs(f, step=(0.3, 0.1, -0.2))
+        dev.render_frame(inp)
+        orc.render_frame(inp)
+        compare_all(dev, orc, ALL_PLANES + DENOISED, f)
+    st = dev.stats()
+    assert st.blas_rays > 0 and st.tlas_rays > 160 * 90 * 2     # sun + paths of up to 3 bounces (most leave the town after one)

@@ -9,6 +9,9 @@ are committed:
   scenes/cornell.npz              <- assets/models/cornell.glb         (examples/cornell.rs:40)
   scenes/city.npz                 <- assets/models/Low Poly/Big House{, 2, 3}.glb (examples/city.rs:56-202), meshes
                                      + materials + textures only; the instance list is built in scenes.py
+  scenes/town.npz                 <- assets/models/scene.gltf          (examples/scene.rs:80-84; BASELINE configs[2]),
+                                     84 meshes / 120 440 triangles / 66 materials; the 52 embedded PNGs are shipped
+                                     box-filtered to at most 256 x 256 (--scene)
 
 A scene file holds what a Bevy app would hand to the plugin: meshes (position/normal/uv/indices per glTF
 primitive), per-instance (mesh, material, world transform), StandardMaterial parameters, RGBA8 textures.
@@ -44,6 +47,20 @@ def load_glb(path):
             binchunk = body
         off += 8 + clen
     return js, [binchunk]
+
+
+def load_gltf(path):
+    """.gltf with embedded (data: URI) or side-car buffers."""
+    import base64
+    js = json.load(open(path))
+    bufs = []
+    for b in js["buffers"]:
+        uri = b["uri"]
+        if uri.startswith("data:"):
+            bufs.append(base64.b64decode(uri.split(",", 1)[1]))
+        else:
+            bufs.append(open(os.path.join(os.path.dirname(path), uri), "rb").read())
+    return js, bufs
 
 
 COMP = {5120: np.int8, 5121: np.uint8, 5122: np.int16, 5123: np.uint16, 5125: np.uint32, 5126: np.float32}
@@ -121,7 +138,7 @@ def decode_image(js, bufs, image_index, base_dir):
 
 def convert_gltf(path, max_tex=None):
     """Return dict of arrays: meshes, instances (depth-first node order), materials, textures."""
-    js, bufs = load_glb(path)
+    js, bufs = load_gltf(path) if path.endswith(".gltf") else load_glb(path)
     out = {}
     meshes = []       # one entry per glTF primitive
     prim_of_mesh = {}  # (mesh, prim) -> flat mesh index
@@ -244,6 +261,11 @@ def main():
             np.savez_compressed(f"{ROOT}/scenes/{name}.npz", **h)
             print(name, "meshes", int(h["mesh_count"]), "instances", len(h["inst_mesh"]), "textures", int(h["tex_count"]),
                   "tris", sum(len(h[f"m{i}_idx"]) // 3 for i in range(int(h["mesh_count"]))))
+    if "--scene" in sys.argv:
+        t = convert_gltf(f"{REF}/assets/models/scene.gltf", max_tex=256)
+        np.savez_compressed(f"{ROOT}/scenes/town.npz", **t)
+        print("town: meshes", int(t["mesh_count"]), "instances", len(t["inst_mesh"]), "materials", len(t["mat_base_color"]),
+              "textures", int(t["tex_count"]), "tris", sum(len(t[f"m{i}_idx"]) // 3 for i in range(int(t["mesh_count"]))))
 
 
 if __name__ == "__main__":
