@@ -184,6 +184,11 @@ def plan_tiles(width, height, world, coverage=None, background_weight=0.15):
     return [(0, width, cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+ASSET_OF = {"cornell": "cornell.glb", "city": "Low Poly/Big House{, 2, 3}.glb + Earth/earth_daymap.jpg",
+            "town": "scene.gltf + Earth/earth_daymap.jpg, textures box-filtered to <= 256 px", "terrain": "procedural stress scene",
+            "minimal": "bevy shapes", "simple": "bevy shapes", "samplers": "procedural"}
+
+
 def make_bench(config):
     from bevy_hikari_b200 import plugin, scenes
     cfg = scenes.CONFIGS[config]
@@ -519,7 +524,7 @@ def run_ours(args):
     out = {
         "metric": "Mrays/s", "value": round(value, 3), "unit": "Mrays/s", "n_gpus": world_size, "steps": K, "warmup": W_,
         "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "reference asset cornell.glb + blue-noise seed (no synthetic inputs exist for this path)",
+        "dtype": "f32", "data": f"reference assets ({ASSET_OF[cfg['scene']]}) + blue-noise seed (no synthetic inputs exist for this path)",
         "config": dict(config_json(args.config, cfg, settings, world_size, args.gather), tiles=[list(t) for t in tiles],
                        **({"halo_margin": args.halo_margin} if (world_size > 1 and args.halo_margin is not None) else {})),
         "rays_per_frame": {"light_tlas": rays[1] / K, "light_blas": rays[2] / K, "primary": rays[0] / K},
@@ -662,7 +667,7 @@ def run_reference(args):
               f"rustc + a Vulkan ICD, neither exists offline")
     out = {"impl": "reference", "metric": "Mrays/s", "value": round(value, 4), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": K,
            "warmup": W_, "ms_per_step": round(dt / K * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f32", "data": "reference asset cornell.glb + blue-noise seed",
+           "dtype": "f32", "data": f"reference assets ({ASSET_OF[cfg['scene']]}) + blue-noise seed",
            "config": config_json(args.config, cfg, settings, world_size),
            "cpu_baseline": {"value": round(value, 4), "unit": "Mrays/s", "cores": orc.threads, "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
