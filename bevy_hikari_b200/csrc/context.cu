@@ -47,7 +47,7 @@ struct hk_context {
     DeviceScene scene{};
     bool scene_ready = false, noise_ready = false;
     bool full_frame = true;            // the context owns the whole frame (no tile): upscale_ratio > 1 and the upscalers need it
-    int last_render_w = 0, last_render_h = 0; bool last_smaa = false, last_upscalers = false; uint32_t last_number = 0;   // of the last frame, for read-back sizes
+    int last_render_w = 0, last_render_h = 0; bool last_smaa = false, last_upscalers = false, last_fsr = false; uint32_t last_number = 0;   // of the last frame, for read-back sizes
     int gbuffer_current = 0;           // index of the "current" position / velocity_uv planes; toggled by every prepass
     uint8_t* noise = nullptr;
     Counters* counters = nullptr;
@@ -150,7 +150,7 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     HK_CUDA(alloc_plane(ctx, &p.tone_mapped_db[0], ctx->owned_pixels, L));
     HK_CUDA(alloc_plane(ctx, &p.tone_mapped_db[1], ctx->owned_pixels, L));
     p.tone_mapped = p.tone_mapped_db[0];
-    p.upscale_output = nullptr; p.taa_output[0] = p.taa_output[1] = nullptr;
+    p.upscale_output = nullptr; p.upscale_sharpen_output = nullptr; p.taa_output[0] = p.taa_output[1] = nullptr;
     p.tone_ring_db[0] = p.tone_ring_db[1] = nullptr;
     if (!ctx->full_frame && ctx->tile_upscalers) {   // every image over the allocation (owned + ring + halo)
         HK_CUDA(alloc_plane(ctx, &p.tone_ring_db[0], n, L));
@@ -161,6 +161,7 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
         HK_CUDA(alloc_plane(ctx, &p.taa_output[0], 4 * n, L));
         HK_CUDA(alloc_plane(ctx, &p.taa_output[1], 4 * n, L));
     }
+    if (ctx->full_frame) HK_CUDA(alloc_plane(ctx, &p.upscale_sharpen_output, n, L));   // FSR RCAS result (Upscale::Fsr1)
     return HK_OK;
 }
 
@@ -506,6 +507,10 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     if (in->temporal_upscalers && !ctx->full_frame && (!ctx->tile_upscalers || ctx->motion_margin < RING_TONE))
         return set_error(ctx, HK_ERR_UNSUPPORTED, "the temporal upscalers on a tile need a full-frame context, or hk_context_enable_tile_upscalers "
                                                   "and a motion margin of at least 4 pixels + the per-frame motion");
+    if (in->temporal_upscalers && in->fsr1 && in->smaa_tu4x)
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "fsr1 and smaa_tu4x are the two variants of one enum (Upscale, lib.rs:475-490)");
+    if (in->temporal_upscalers && in->fsr1 && !ctx->full_frame)
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "FSR1 needs a full-frame context (no tile)");
     if (in->frame.direct_validate_interval == 0 || in->frame.emissive_validate_interval == 0)
         return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "validate interval must be >= 1");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return set_error(ctx, HK_ERR_CUDA, "cudaSetDevice");
@@ -534,6 +539,7 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     }
     P.inv_rw = 1.0f / (float)P.band.RW; P.inv_rh = 1.0f / (float)P.band.RH;
     ctx->last_render_w = P.band.RW; ctx->last_render_h = P.band.RH; ctx->last_smaa = in->smaa_tu4x != 0; ctx->last_number = in->frame.number;
+    ctx->last_fsr = in->temporal_upscalers && in->fsr1;
     P.counters = ctx->count_rays ? ctx->counters : nullptr;
     P.noise = ctx->noise;
     float s, c;
@@ -645,6 +651,13 @@ static int run_post(hk_context* ctx, KParams& P, bool fuse) {  // PostProcessNod
             const int k = smaa ? 2 : 1;
             P.row_lo *= k; P.row_hi *= k; P.col_lo *= k; P.col_hi *= k;
             KernelTimer t(ctx, HK_K_TAA); hk_launch_taa_jasmine(P, smaa, ctx->stream);
+        }
+        if (P.in.fsr1) {   // post_process.rs:1279-1308: EASU then RCAS over the camera target (full-frame context, checked above)
+            P.row_lo = 0; P.row_hi = P.band.H; P.col_lo = 0; P.col_hi = P.band.W;
+            KernelTimer t(ctx, HK_K_FSR1);
+            hk_launch_fsr_easu(P, ctx->stream);
+            hk_launch_fsr_rcas(P, ctx->stream);
+            ctx->launches += 1;
         }
     }
     return check_launch(ctx);
@@ -780,9 +793,13 @@ static bool plane_view(hk_context* ctx, int which, PlaneView* v) {
     switch (which) {
         case HK_OUT_TONE_MAPPED: *v = PlaneView{p.tone_mapped_db[ctx->last_upscalers ? cur : 0u], 8, rw, rh, rw}; return true;
         // upscaled images: a full-frame context stores them tightly; a tile over k x its allocation, of which the owned part is served
+        case HK_OUT_FSR_SHARPENED:
+            if (!p.upscale_sharpen_output) return false;
+            *v = PlaneView{p.upscale_sharpen_output, 8, (size_t)b.W, (size_t)b.H, (size_t)b.W}; return true;
         case HK_OUT_UPSCALED: case HK_OUT_TAA: {
             uint2* base = which == HK_OUT_UPSCALED ? p.upscale_output : p.taa_output[cur];
             if (!base) return false;
+            if (which == HK_OUT_UPSCALED && ctx->last_fsr) { *v = PlaneView{base, 8, (size_t)b.W, (size_t)b.H, (size_t)b.W}; return true; }
             const size_t k = (which == HK_OUT_UPSCALED || ctx->last_smaa) ? 2 : 1;
             if (ctx->full_frame) { *v = PlaneView{base, 8, k * rw, k * rh, k * rw}; return true; }
             const size_t pitch = k * (size_t)b.AW, first = (k * (size_t)(b.r0 - b.a0)) * pitch + k * (size_t)(b.cx0 - b.ax0);
@@ -807,8 +824,8 @@ extern "C" {
 int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes) {
     if (!ctx || !device_ptr) return HK_ERR_INVALID_ARGUMENT;
     PlaneView v;
-    if ((which != HK_OUT_TONE_MAPPED && which != HK_OUT_UPSCALED && which != HK_OUT_TAA) || !plane_view(ctx, which, &v))
-        return set_error(ctx, HK_ERR_UNSUPPORTED, "only the final images (tone-mapped, upscaled, TAA) are exposed as device pointers");
+    if ((which != HK_OUT_TONE_MAPPED && which != HK_OUT_UPSCALED && which != HK_OUT_TAA && which != HK_OUT_FSR_SHARPENED) || !plane_view(ctx, which, &v))
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "only the final images (tone-mapped, upscaled, TAA, FSR-sharpened) are exposed as device pointers");
     *device_ptr = v.ptr;
     if (bytes) *bytes = v.w * v.h * v.bpp;
     return HK_OK;
@@ -866,8 +883,8 @@ int hk_readback(hk_context* ctx, int which, void* host, size_t bytes) { return t
 int hk_readback_async(hk_context* ctx, int which, void* pinned_host, size_t bytes) {
     if (!ctx || !pinned_host) return HK_ERR_INVALID_ARGUMENT;
     PlaneView v;
-    if ((which != HK_OUT_TONE_MAPPED && which != HK_OUT_UPSCALED && which != HK_OUT_TAA) || !plane_view(ctx, which, &v))
-        return set_error(ctx, HK_ERR_UNSUPPORTED, "hk_readback_async serves the final images (tone-mapped, upscaled, TAA)");
+    if ((which != HK_OUT_TONE_MAPPED && which != HK_OUT_UPSCALED && which != HK_OUT_TAA && which != HK_OUT_FSR_SHARPENED) || !plane_view(ctx, which, &v))
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "hk_readback_async serves the final images (tone-mapped, upscaled, TAA, FSR-sharpened)");
     if (bytes != v.w * v.h * v.bpp) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
     HK_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->copy_stream) {

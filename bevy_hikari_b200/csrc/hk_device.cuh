@@ -94,7 +94,8 @@ struct Planes {
     uint2* tone_mapped;         // owned rectangle only, tightly packed; = tone_mapped_db[frame.number % 2] (post_process.rs:716,979)
     uint2* tone_mapped_db[2];
     uint2* tone_ring_db[2];     // tiles with upscalers: the tone-mapped image over the tile's allocation (owned + 4-px ring + halo)
-    uint2* upscale_output;      // 2 RW x 2 RH (SMAA TU4x); tiles: 2 x the allocation
+    uint2* upscale_output;      // 2 RW x 2 RH (SMAA TU4x); tiles: 2 x the allocation.  W x H under Upscale::Fsr1 (the EASU result)
+    uint2* upscale_sharpen_output;   // W x H, full-frame contexts: the RCAS result (post_process.rs:723 upscale_output[1])
     uint2* taa_output[2];       // [frame.number % 2] is written
 };
 

@@ -19,6 +19,9 @@ void hk_launch_tone_mapping(const hkd::KParams& P, cudaStream_t st);
 void hk_launch_smaa_tu4x(const hkd::KParams& P, cudaStream_t st);               // over col_lo..col_hi x row_lo..row_hi (render pixels)
 void hk_launch_smaa_tu4x_extrapolate(const hkd::KParams& P, cudaStream_t st);
 void hk_launch_taa_jasmine(const hkd::KParams& P, bool smaa, cudaStream_t st);  // over col_lo..col_hi x row_lo..row_hi = the output size
+// FSR 1.0 (Upscale::Fsr1): over col_lo..col_hi x row_lo..row_hi = the camera target; full-frame contexts only
+void hk_launch_fsr_easu(const hkd::KParams& P, cudaStream_t st);   // taa_output / tone-mapped (render size) -> upscale_output (W x H)
+void hk_launch_fsr_rcas(const hkd::KParams& P, cudaStream_t st);   // upscale_output -> upscale_sharpen_output
 
 // halo exchange between tiles of one frame (kernels_post.cu): copies the ten reservoir buffers of the global pixel rectangle
 // [x0,x1) x [y0,y1) from `src`'s planes into `dst`'s planes; `src` may be peer memory

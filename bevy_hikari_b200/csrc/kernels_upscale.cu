@@ -1,7 +1,7 @@
 // kernels_upscale.cu — the temporal upscalers that follow tone mapping in the default HikariSettings pipeline
 // (SURVEY.md 8(f) rank 1): smaa_tu4x + smaa_tu4x_extrapolate (src/shaders/smaa.wgsl:81-271) and taa_jasmine
-// (src/shaders/taa.wgsl:79-170), dispatched by PostProcessNode::run (src/post_process.rs:1236-1277).
-// Full-frame contexts only.  Texture addressing (both samplers clamp-to-edge, post_process.rs:697-708):
+// (src/shaders/taa.wgsl:79-170), dispatched by PostProcessNode::run (src/post_process.rs:1236-1277), and FSR 1.0 EASU + RCAS
+// (Upscale::Fsr1, post_process.rs:1279-1308; rank 4).  Texture addressing (both samplers clamp-to-edge, post_process.rs:697-708):
 //   nearest: texel floor(uv * size);  linear: bilinear around uv * size - 0.5 with fp32 weights;
 //   textureGather: the 2x2 bilinear footprint as (x: (i0,j1), y: (i1,j1), z: (i1,j0), w: (i0,j0)).
 #include "hk_device.cuh"
@@ -313,6 +313,110 @@ __global__ void __launch_bounds__(CTA_THREADS) k_taa_jasmine(const __grid_consta
     store16(P.planes.taa_output[cur], oidx, v4(output, original_color.w));
 }
 
+// --------------------------------------------------------------------------------------------- FSR 1.0 (Upscale::Fsr1)
+// EASU + RCAS as the reference's SPIR-V blobs compute them (src/shaders/fsr/source.zip: FSR_Pass.glsl with SAMPLE_SLOW_FALLBACK
+// -> FsrEasuF ffx_fsr1.h:315-437, FsrRcasF :684-772; dispatched by post_process.rs:1279-1308).  One thread per OUTPUT pixel of
+// the camera target; the 12 (EASU) / 5 (RCAS) taps of neighbouring threads overlap almost completely and are served by L1.
+// Algorithmic bytes per launch: EASU 8 B x render pixels read + 8 B x target pixels written; RCAS 16 B x target pixels.
+// accumulation order of FsrEasuF (:423-434): b c i j f e k l h g o n — the order is part of the result (fp32 sums)
+enum { TB = 0, TC = 1, TI = 2, TJ = 3, TF = 4, TE = 5, TK = 6, TL = 7, TH = 8, TG = 9, TO = 10, TN = 11 };
+
+__device__ __forceinline__ void easu_edge(float& dir_x, float& dir_y, float& len, float w, float a, float b, float c, float d, float e) {
+    // '+' of lumas: a above, b left, c centre, d right, e below (FsrEasuSetF :275-313)
+    float gx = d - b, gy = e - a;
+    float sx = clampf(fabsf(gx) * fsr_rcp_lo(fmax_(fabsf(d - c), fabsf(c - b))), 0.0f, 1.0f);
+    float sy = clampf(fabsf(gy) * fsr_rcp_lo(fmax_(fabsf(e - c), fabsf(c - a))), 0.0f, 1.0f);
+    dir_x += gx * w;
+    len += (sx * sx) * w;
+    dir_y += gy * w;
+    len += (sy * sy) * w;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) k_fsr_easu(const __grid_constant__ KParams P, const FsrEasuConstants con) {
+    int x, y;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
+    const uint32_t cur = P.in.frame.number % 2u;
+    const Band& bd = P.band;
+    const Image16 input{P.in.taa_jitter ? P.planes.taa_output[cur] : P.planes.tone_mapped_db[cur], bd.RW, bd.RH, 0, 0, bd.RW, bd.RH};
+    float px = (float)x * con.scale_x + con.offset_x, py = (float)y * con.scale_y + con.offset_y;
+    const float fxf = floorf(px), fyf = floorf(py);
+    px -= fxf; py -= fyf;
+    const int fx = (int)fxf, fy = (int)fyf;
+    // texel offsets of the taps from f, in accumulation order; both loops are fully unrolled, the tables fold into immediates
+    constexpr int TAP_DX[12] = {0, 1, -1, 0, 0, -1, 1, 2, 2, 1, 1, 0}, TAP_DY[12] = {-1, -1, 1, 1, 0, 0, 1, 1, 0, 0, 2, 2};
+    vec3 t[12];
+    float l[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {   // four clamped texel fetches per emulated gather (texture_gather.glsl), 12 distinct texels
+        t[k] = xyz(input.texel(fx + TAP_DX[k], fy + TAP_DY[k]));
+        l[k] = t[k].z * 0.5f + (t[k].x * 0.5f + t[k].y);
+    }
+    float dir_x = 0.0f, dir_y = 0.0f, len = 0.0f;
+    easu_edge(dir_x, dir_y, len, (1.0f - px) * (1.0f - py), l[TB], l[TE], l[TF], l[TG], l[TJ]);
+    easu_edge(dir_x, dir_y, len, px * (1.0f - py), l[TC], l[TF], l[TG], l[TH], l[TK]);
+    easu_edge(dir_x, dir_y, len, (1.0f - px) * py, l[TF], l[TI], l[TJ], l[TK], l[TN]);
+    easu_edge(dir_x, dir_y, len, px * py, l[TG], l[TJ], l[TK], l[TL], l[TO]);
+    float r = dir_x * dir_x + dir_y * dir_y;
+    const bool flat = r < (1.0f / 32768.0f);
+    r = flat ? 1.0f : fsr_rsq_lo(r);
+    dir_x = (flat ? 1.0f : dir_x) * r;
+    dir_y = dir_y * r;
+    len = len * 0.5f;
+    len *= len;
+    const float stretch = (dir_x * dir_x + dir_y * dir_y) * fsr_rcp_lo(fmax_(fabsf(dir_x), fabsf(dir_y)));
+    const float len_x = 1.0f + (stretch - 1.0f) * len, len_y = 1.0f + -0.5f * len;
+    const float lob = 0.5f + ((1.0f / 4.0f - 0.04f) - 0.5f) * len;
+    const float clp = fsr_rcp_lo(lob);
+    vec3 acc = v3(0.0f, 0.0f, 0.0f);
+    float wsum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {   // FsrEasuTapF :239-273
+        const float ox = (float)TAP_DX[k] - px, oy = (float)TAP_DY[k] - py;
+        const float vx = ((ox * dir_x) + (oy * dir_y)) * len_x, vy = ((ox * (-dir_y)) + (oy * dir_x)) * len_y;
+        const float d2 = fmin_(vx * vx + vy * vy, clp);
+        float wb = (2.0f / 5.0f) * d2 + -1.0f, wa = lob * d2 + -1.0f;
+        wb *= wb; wa *= wa;
+        wb = (25.0f / 16.0f) * wb + (-(25.0f / 16.0f - 1.0f));
+        const float w = wb * wa;
+        acc = acc + t[k] * w;
+        wsum += w;
+    }
+    // de-ring against the 2x2 centre f g j k
+    auto lo = [](float a, float b, float c, float d) { return fmin_(fmin_(a, fmin_(b, c)), d); };
+    auto hi = [](float a, float b, float c, float d) { return fmax_(fmax_(a, fmax_(b, c)), d); };
+    const float inv = 1.0f / wsum;
+    vec3 pix;
+    pix.x = fmin_(hi(t[TF].x, t[TG].x, t[TJ].x, t[TK].x), fmax_(lo(t[TF].x, t[TG].x, t[TJ].x, t[TK].x), acc.x * inv));
+    pix.y = fmin_(hi(t[TF].y, t[TG].y, t[TJ].y, t[TK].y), fmax_(lo(t[TF].y, t[TG].y, t[TJ].y, t[TK].y), acc.y * inv));
+    pix.z = fmin_(hi(t[TF].z, t[TG].z, t[TJ].z, t[TK].z), fmax_(lo(t[TF].z, t[TG].z, t[TJ].z, t[TK].z), acc.z * inv));
+    store16(P.planes.upscale_output, (size_t)y * (size_t)bd.W + (size_t)x, v4(pix, 1.0f));
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) k_fsr_rcas(const __grid_constant__ KParams P, const float sharp) {
+    int x, y;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
+    const Band& bd = P.band;
+    const Image16 input{P.planes.upscale_output, bd.W, bd.H, 0, 0, bd.W, bd.H};
+    // all five loads first (texelFetch, zero outside the image), then arithmetic
+    const vec3 b = xyz(input.load(x, y - 1)), d = xyz(input.load(x - 1, y)), e = xyz(input.load(x, y));
+    const vec3 f = xyz(input.load(x + 1, y)), h = xyz(input.load(x, y + 1));
+    auto channel_lobe = [](float bb, float dd, float ee, float ff, float hh) {
+        const float mn = fmin_(fmin_(bb, fmin_(dd, ff)), hh), mx = fmax_(fmax_(bb, fmax_(dd, ff)), hh);
+        const float hit_min = fmin_(mn, ee) * (1.0f / (4.0f * mx));
+        const float hit_max = (1.0f - fmax_(mx, ee)) * (1.0f / (4.0f * mn + -4.0f));
+        return fmax_(-hit_min, hit_max);
+    };
+    const float lr = channel_lobe(b.x, d.x, e.x, f.x, h.x), lg = channel_lobe(b.y, d.y, e.y, f.y, h.y), lb = channel_lobe(b.z, d.z, e.z, f.z, h.z);
+    const float lobe = fmax_(-FSR_RCAS_LIMIT, fmin_(fmax_(lr, fmax_(lg, lb)), 0.0f)) * sharp;
+    const float rcp = fsr_rcp_med(4.0f * lobe + 1.0f);
+    const vec3 pix = v3((lobe * b.x + lobe * d.x + lobe * h.x + lobe * f.x + e.x) * rcp,
+                        (lobe * b.y + lobe * d.y + lobe * h.y + lobe * f.y + e.y) * rcp,
+                        (lobe * b.z + lobe * d.z + lobe * h.z + lobe * f.z + e.z) * rcp);
+    store16(P.planes.upscale_sharpen_output, (size_t)y * (size_t)bd.W + (size_t)x, v4(pix, 1.0f));
+}
+
 static dim3 grid_for(const KParams& P) {
     int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
     return dim3((unsigned)((cols + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
@@ -333,4 +437,14 @@ void hk_launch_smaa_tu4x_extrapolate(const KParams& P, cudaStream_t st) {
 void hk_launch_taa_jasmine(const KParams& P, bool smaa, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_taa_jasmine<<<grid_for(P), CTA_THREADS, 0, st>>>(P, smaa ? 1 : 0);
+}
+void hk_launch_fsr_easu(const KParams& P, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+    // FsrConstantsUniform (post_process.rs:518-534): input viewport = input size = scaled_size, output = the camera target
+    const hk::FsrEasuConstants con = hk::fsr_easu_constants((float)P.band.RW, (float)P.band.RH, (float)P.band.W, (float)P.band.H);
+    k_fsr_easu<<<grid_for(P), CTA_THREADS, 0, st>>>(P, con);
+}
+void hk_launch_fsr_rcas(const KParams& P, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+    k_fsr_rcas<<<grid_for(P), CTA_THREADS, 0, st>>>(P, hk::fsr_rcas_constant(P.in.fsr_sharpness));
 }

@@ -53,6 +53,8 @@ hk_frame_inputs make_frame_inputs(const HikariSettings& settings, const FrameCou
     in.denoise = settings.denoise ? 1u : 0u;
     in.taa_jitter = settings.taa == Taa::Jasmine ? 1u : 0u;               // prepass.rs:193-196 TEMPORAL_ANTI_ALIASING
     in.smaa_tu4x = settings.upscale.kind == Upscale::SmaaTu4x ? 1u : 0u;  // prepass.rs:197-199 SMAA_TU4X
+    in.fsr1 = settings.upscale.kind == Upscale::Fsr1 ? 1u : 0u;           // post_process.rs:1279
+    in.fsr_sharpness = settings.upscale.sharpness();                      // FsrConstantsUniform::sharpness, post_process.rs:530
     return in;
 }
 

@@ -68,7 +68,8 @@ class Lights(C.Structure):
 
 class FrameInputs(C.Structure):
     _fields_ = [("frame", FrameUniform), ("view", View), ("previous_view", PreviousView), ("lights", Lights),
-                ("denoise", C.c_uint32), ("taa_jitter", C.c_uint32), ("smaa_tu4x", C.c_uint32), ("temporal_upscalers", C.c_uint32)]
+                ("denoise", C.c_uint32), ("taa_jitter", C.c_uint32), ("smaa_tu4x", C.c_uint32), ("temporal_upscalers", C.c_uint32),
+                ("fsr1", C.c_uint32), ("fsr_sharpness", C.c_float)]
 
 
 class TextureDesc(C.Structure):
@@ -97,7 +98,7 @@ class FrameStats(C.Structure):
 
 
 KERNEL_NAMES = ["gbuffer", "direct", "emissive", "emissive_spatial", "indirect", "indirect_spatial", "demodulation",
-                "denoise_0", "denoise_1", "denoise_2", "denoise_3", "tone_mapping", "smaa_tu4x", "taa"]
+                "denoise_0", "denoise_1", "denoise_2", "denoise_3", "tone_mapping", "smaa_tu4x", "taa", "fsr1"]
 
 
 RAY = np.dtype({"names": ["origin", "max_distance", "direction", "early_distance", "exclude_instance"],
@@ -112,14 +113,14 @@ assert C.sizeof(View) == 6 * 64 + 32 and C.sizeof(Lights) == 48
 OUT_TONE_MAPPED, OUT_RENDER_DIRECT, OUT_RENDER_EMISSIVE, OUT_RENDER_INDIRECT = 0, 1, 2, 3
 OUT_VARIANCE_DIRECT, OUT_VARIANCE_EMISSIVE, OUT_VARIANCE_INDIRECT, OUT_ALBEDO = 4, 5, 6, 7
 OUT_DENOISED_DIRECT, OUT_DENOISED_EMISSIVE, OUT_DENOISED_INDIRECT = 8, 9, 10
-OUT_UPSCALED, OUT_TAA = 11, 12
+OUT_UPSCALED, OUT_TAA, OUT_FSR_SHARPENED = 11, 12, 13
 OUT_GBUFFER_POSITION, OUT_GBUFFER_NORMAL, OUT_GBUFFER_DEPTH_GRADIENT = 16, 17, 18
 OUT_GBUFFER_INSTANCE_MATERIAL, OUT_GBUFFER_VELOCITY_UV = 19, 20
 OUT_RESERVOIR_0 = 32
 
 # bytes per pixel and numpy view of each read-back plane
 OUT_FORMATS = {}
-for _k in (0, 1, 2, 3, 7, 8, 9, 10, 11, 12):
+for _k in (0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 13):
     OUT_FORMATS[_k] = (8, np.float16, 4)
 for _k in (4, 5, 6):
     OUT_FORMATS[_k] = (4, np.float32, 1)

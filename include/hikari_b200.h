@@ -84,6 +84,11 @@ typedef struct hk_frame_inputs {
                                         (when smaa_tu4x) and taa_jasmine (when taa_jitter) — post_process.rs:1236-1277, the
                                         "next" rows K11/K12 of SURVEY.md 8(f).  0 = the hot path ends at tone mapping.
                                         Tiles: see hk_context_enable_tile_upscalers. */
+    uint32_t fsr1;                   /* 1 = Upscale::Fsr1 (lib.rs:476-483): with temporal_upscalers, hk_post_process_run ends with
+                                        FSR 1.0 EASU (render size -> camera target size; input = taa_output when taa_jitter else
+                                        the tone-mapped image, post_process.rs:1037-1040) and RCAS (post_process.rs:1279-1308).
+                                        Excludes smaa_tu4x.  Full-frame contexts only. */
+    float fsr_sharpness;             /* Upscale::sharpness(), lib.rs:507-512: RCAS stops, 0 = sharpest (FsrConstantsUniform) */
 } hk_frame_inputs;
 
 /* Identifiers for hk_get_output / hk_readback / hk_upload_state.  Read-back formats are the reference's texture /
@@ -101,8 +106,11 @@ enum {
     HK_OUT_DENOISED_DIRECT = 8,  /* Rgba16Float           post_process.rs:714 denoise_render[0] */
     HK_OUT_DENOISED_EMISSIVE = 9,
     HK_OUT_DENOISED_INDIRECT = 10,
-    HK_OUT_UPSCALED = 11,        /* Rgba16Float, 2x render size   post_process.rs:718-722 upscale_output[0] (SMAA TU4x) */
+    HK_OUT_UPSCALED = 11,        /* Rgba16Float   post_process.rs:718-724 upscale_output[0]: 2x render size (SMAA TU4x) or the camera
+                                    target size (Fsr1: the EASU result) */
     HK_OUT_TAA = 12,             /* Rgba16Float, 2x render size with SMAA TU4x else render size   post_process.rs:726-731 taa_output[current] */
+    HK_OUT_FSR_SHARPENED = 13,   /* Rgba16Float, camera target size   upscale_output[1]: the RCAS result, what the overlay presents
+                                    under Upscale::Fsr1 (overlay.rs:228) */
     HK_OUT_GBUFFER_POSITION = 16,           /* Rgba32Float 16 B/px */
     HK_OUT_GBUFFER_NORMAL = 17,             /* Rgba8Snorm   4 B/px */
     HK_OUT_GBUFFER_DEPTH_GRADIENT = 18,     /* Rg32Float    8 B/px */
@@ -134,7 +142,8 @@ enum {   /* indices into hk_frame_stats.ms_kernel */
     HK_K_TONE_MAPPING = 11,
     HK_K_SMAA_TU4X = 12,         /* smaa_tu4x + smaa_tu4x_extrapolate (only with temporal_upscalers) */
     HK_K_TAA = 13,               /* taa_jasmine (only with temporal_upscalers) */
-    HK_K_COUNT = 14,
+    HK_K_FSR1 = 14,              /* FSR 1.0 EASU + RCAS (only with temporal_upscalers and fsr1) */
+    HK_K_COUNT = 15,
     HK_K_TRACE_RAYS = 15         /* kernel time of the last hk_trace_rays call (always filled) */
 };
 
@@ -185,7 +194,7 @@ int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes);
  * (light.rs:622-624); HK_OUT_UPSCALED (and HK_OUT_TAA after smaa_tu4x) = twice the render size (post_process.rs:718-731). */
 int hk_output_extent(hk_context* ctx, int which, uint32_t* width, uint32_t* height);
 int hk_readback(hk_context* ctx, int which, void* host, size_t bytes);            /* synchronises */
-/* Pipelined read-back of a final image (HK_OUT_TONE_MAPPED / HK_OUT_UPSCALED / HK_OUT_TAA) for a presentation loop: the
+/* Pipelined read-back of a final image (HK_OUT_TONE_MAPPED / HK_OUT_UPSCALED / HK_OUT_TAA / HK_OUT_FSR_SHARPENED) for a presentation loop: the
  * copy into `pinned_host` (page-locked memory) is queued on an internal copy stream behind all work submitted so far and
  * the call returns at once.  The next frame can be submitted immediately — on the device, its first write to a final
  * image waits for the copy.  hk_readback_wait blocks the host until the last queued copy has landed.  One copy may be

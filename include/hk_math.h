@@ -403,4 +403,25 @@ HK_HD vec3 reinhard_luminance(vec3 color) {
     return color * (l_new / l_old);
 }
 
+// ------------------------------------------------------------------------------------ FSR 1.0 primitives
+// The approximations AMD's ffx_a.h builds EASU / RCAS on (src/shaders/fsr/source.zip: ffx_a.h:1843-1845) — integer
+// arithmetic on the float's bits, hence exactly defined — and the two constant blocks FSR_Pass.glsl computes in `main`
+// (ffx_fsr1.h:156-201 FsrEasuCon, :662-672 FsrRcasCon) with ARcpF1(x) = 1 / x (ffx_a.h:737) as an IEEE division.
+HK_HD float fsr_rcp_lo(float a) { return u2f(0x7ef07ebbu - f2u(a)); }                 // APrxLoRcpF1
+HK_HD float fsr_rcp_med(float a) { float b = u2f(0x7ef19fffu - f2u(a)); return b * (-b * a + 2.0f); }   // APrxMedRcpF1
+HK_HD float fsr_rsq_lo(float a) { return u2f(0x5f347d74u - (f2u(a) >> 1)); }          // APrxLoRsqF1
+struct FsrEasuConstants {   // con0 .. con3 as floats (the GLSL passes them around as bit patterns)
+    float scale_x, scale_y, offset_x, offset_y;   // con0: output pixel -> input pixel position.  con1 .. con3 only place the
+};                                                // four gathers on texel corners (ffx_fsr1.h:175-201): see fsr_easu below
+HK_HD FsrEasuConstants fsr_easu_constants(float input_viewport_w, float input_viewport_h, float output_w, float output_h) {
+    FsrEasuConstants c;
+    c.scale_x = input_viewport_w * (1.0f / output_w);
+    c.scale_y = input_viewport_h * (1.0f / output_h);
+    c.offset_x = 0.5f * input_viewport_w * (1.0f / output_w) - 0.5f;
+    c.offset_y = 0.5f * input_viewport_h * (1.0f / output_h) - 0.5f;
+    return c;
+}
+HK_HD float fsr_rcas_constant(float sharpness) { return exp2_(-sharpness); }           // FsrRcasCon: stops -> linear
+constexpr float FSR_RCAS_LIMIT = 0.25f - (1.0f / 16.0f);                               // ffx_fsr1.h:654
+
 }  // namespace hk

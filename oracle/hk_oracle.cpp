@@ -106,7 +106,8 @@ struct hko_context {
     std::vector<float> denoise_internal_variance;
     std::vector<uvec2> denoise_render[3];
     std::vector<uvec2> tone_mapping_output[2];   // [frame.number % 2] is written (post_process.rs:716,979)
-    std::vector<uvec2> upscale_output;           // 2 RW x 2 RH (post_process.rs:718-722)
+    std::vector<uvec2> upscale_output;           // 2 RW x 2 RH (post_process.rs:718-722); W x H under Upscale::Fsr1 (:723)
+    std::vector<uvec2> upscale_sharpen_output;   // upscale_output[1], W x H: FSR RCAS result (post_process.rs:723,1079-1086)
     std::vector<uvec2> taa_output[2];            // 2 RW x 2 RH with SMAA TU4x, else RW x RH (post_process.rs:726-731)
     // per-frame
     hk_frame_inputs in;
@@ -1562,6 +1563,143 @@ void pass_smaa_tu4x_extrapolate(Ctx& c) {  // smaa.wgsl:201-271
     });
 }
 
+// ----------------------------------------------------------------------------- FSR 1.0 (Upscale::Fsr1), SURVEY 8(f) rank 4
+// The reference ships EASU and RCAS as SPIR-V built from AMD's FidelityFX sources, which sit next to the blobs
+// (src/shaders/fsr/source.zip: FSR_Pass.glsl, ffx_fsr1.h, ffx_a.h, texture_gather.glsl; compile.bat).  This restates the
+// variant that build selects: SAMPLE_SLOW_FALLBACK = 1 -> the 32-bit paths FsrEasuF / FsrRcasF, no FSR_RCAS_DENOISE, no alpha
+// pass-through, `hdr == 0` (post_process.rs:531), constants computed per invocation from FsrConstantsUniform
+// (post_process.rs:518-534: viewport = input size = scaled_size, output = the camera target).
+// Texture access: texture_gather.glsl emulates textureGather by four bilinear taps half a texel around the gather point,
+// i.e. exactly at the centres of the four texels (linear sampler, clamp-to-edge, post_process.rs:703-708,879) — restated as
+// four clamped texel fetches; FsrRcasLoadF is texelFetch, zero outside the image like every textureLoad here.
+
+// FsrEasuSetF, ffx_fsr1.h:275-313: one corner's contribution to gradient direction and edge length
+inline void fsr_easu_set(vec2& dir, float& len, float w, float lA, float lB, float lC, float lD, float lE) {
+    float dc = lD - lC, cb = lC - lB;
+    float lenX = fmax_(fabsf(dc), fabsf(cb));
+    lenX = fsr_rcp_lo(lenX);
+    float dirX = lD - lB;
+    dir.x += dirX * w;
+    lenX = clampf(fabsf(dirX) * lenX, 0.0f, 1.0f);
+    lenX *= lenX;
+    len += lenX * w;
+    float ec = lE - lC, ca = lC - lA;
+    float lenY = fmax_(fabsf(ec), fabsf(ca));
+    lenY = fsr_rcp_lo(lenY);
+    float dirY = lE - lA;
+    dir.y += dirY * w;
+    lenY = clampf(fabsf(dirY) * lenY, 0.0f, 1.0f);
+    lenY *= lenY;
+    len += lenY * w;
+}
+// FsrEasuTapF, ffx_fsr1.h:239-273
+inline void fsr_easu_tap(vec3& aC, float& aW, vec2 off, vec2 dir, vec2 len, float lob, float clp, vec3 col) {
+    vec2 v;
+    v.x = (off.x * dir.x) + (off.y * dir.y);
+    v.y = (off.x * (-dir.y)) + (off.y * dir.x);
+    v = v * len;
+    float d2 = v.x * v.x + v.y * v.y;
+    d2 = fmin_(d2, clp);
+    float wB = (2.0f / 5.0f) * d2 + -1.0f;
+    float wA = lob * d2 + -1.0f;
+    wB *= wB;
+    wA *= wA;
+    wB = (25.0f / 16.0f) * wB + (-(25.0f / 16.0f - 1.0f));
+    float w = wB * wA;
+    aC = aC + col * w;
+    aW += w;
+}
+inline vec3 min3v(vec3 a, vec3 b) { return v3(fmin_(a.x, b.x), fmin_(a.y, b.y), fmin_(a.z, b.z)); }
+inline vec3 max3v(vec3 a, vec3 b) { return v3(fmax_(a.x, b.x), fmax_(a.y, b.y), fmax_(a.z, b.z)); }
+
+void pass_fsr_easu(Ctx& c) {   // FSR_Pass.glsl main + CurrFilter (SAMPLE_EASU), FsrEasuF ffx_fsr1.h:315-437
+    const uint32_t cur = c.in.frame.number % 2u;
+    // upscale_input_texture, post_process.rs:1037-1040; both are scaled_size textures under Fsr1 (post_process.rs:716,726-729)
+    Image16 input{c.in.taa_jitter ? &c.taa_output[cur] : &c.tone_mapping_output[cur], c.RW, c.RH};
+    const FsrEasuConstants con = fsr_easu_constants((float)c.RW, (float)c.RH, (float)c.W, (float)c.H);
+    for_pixels(c, c.W, c.H, [&](int x, int y) {
+        vec2 pp = v2((float)x * con.scale_x + con.offset_x, (float)y * con.scale_y + con.offset_y);
+        vec2 fp = v2(floorf(pp.x), floorf(pp.y));
+        pp = pp - fp;
+        const int fx = (int)fp.x, fy = (int)fp.y;
+        auto T = [&](int dx, int dy) { return xyz(input.texel(fx + dx, fy + dy)); };
+        //    b c
+        //  e f g h
+        //  i j k l
+        //    n o
+        vec3 b = T(0, -1), cc = T(1, -1), e = T(-1, 0), f = T(0, 0), g = T(1, 0), h = T(2, 0);
+        vec3 i = T(-1, 1), j = T(0, 1), k = T(1, 1), l = T(2, 1), n = T(0, 2), o = T(1, 2);
+        auto luma2 = [](vec3 t) { return t.z * 0.5f + (t.x * 0.5f + t.y); };
+        float bL = luma2(b), cL = luma2(cc), eL = luma2(e), fL = luma2(f), gL = luma2(g), hL = luma2(h);
+        float iL = luma2(i), jL = luma2(j), kL = luma2(k), lL = luma2(l), nL = luma2(n), oL = luma2(o);
+        vec2 dir = v2(0.0f, 0.0f);
+        float len = 0.0f;
+        fsr_easu_set(dir, len, (1.0f - pp.x) * (1.0f - pp.y), bL, eL, fL, gL, jL);
+        fsr_easu_set(dir, len, pp.x * (1.0f - pp.y), cL, fL, gL, hL, kL);
+        fsr_easu_set(dir, len, (1.0f - pp.x) * pp.y, fL, iL, jL, kL, nL);
+        fsr_easu_set(dir, len, pp.x * pp.y, gL, jL, kL, lL, oL);
+        vec2 dir2 = dir * dir;
+        float dirR = dir2.x + dir2.y;
+        const bool zro = dirR < (1.0f / 32768.0f);
+        dirR = fsr_rsq_lo(dirR);
+        dirR = zro ? 1.0f : dirR;
+        dir.x = zro ? 1.0f : dir.x;
+        dir = dir * dirR;
+        len = len * 0.5f;
+        len *= len;
+        float stretch = (dir.x * dir.x + dir.y * dir.y) * fsr_rcp_lo(fmax_(fabsf(dir.x), fabsf(dir.y)));
+        vec2 len2 = v2(1.0f + (stretch - 1.0f) * len, 1.0f + -0.5f * len);
+        float lob = 0.5f + ((1.0f / 4.0f - 0.04f) - 0.5f) * len;
+        float clp = fsr_rcp_lo(lob);
+        vec3 min4 = min3v(min3v(f, min3v(g, j)), k);
+        vec3 max4 = max3v(max3v(f, max3v(g, j)), k);
+        vec3 aC = v3(0.0f, 0.0f, 0.0f);
+        float aW = 0.0f;
+        fsr_easu_tap(aC, aW, v2(0.0f, -1.0f) - pp, dir, len2, lob, clp, b);
+        fsr_easu_tap(aC, aW, v2(1.0f, -1.0f) - pp, dir, len2, lob, clp, cc);
+        fsr_easu_tap(aC, aW, v2(-1.0f, 1.0f) - pp, dir, len2, lob, clp, i);
+        fsr_easu_tap(aC, aW, v2(0.0f, 1.0f) - pp, dir, len2, lob, clp, j);
+        fsr_easu_tap(aC, aW, v2(0.0f, 0.0f) - pp, dir, len2, lob, clp, f);
+        fsr_easu_tap(aC, aW, v2(-1.0f, 0.0f) - pp, dir, len2, lob, clp, e);
+        fsr_easu_tap(aC, aW, v2(1.0f, 1.0f) - pp, dir, len2, lob, clp, k);
+        fsr_easu_tap(aC, aW, v2(2.0f, 1.0f) - pp, dir, len2, lob, clp, l);
+        fsr_easu_tap(aC, aW, v2(2.0f, 0.0f) - pp, dir, len2, lob, clp, h);
+        fsr_easu_tap(aC, aW, v2(1.0f, 0.0f) - pp, dir, len2, lob, clp, g);
+        fsr_easu_tap(aC, aW, v2(1.0f, 2.0f) - pp, dir, len2, lob, clp, o);
+        fsr_easu_tap(aC, aW, v2(0.0f, 2.0f) - pp, dir, len2, lob, clp, n);
+        vec3 pix = min3v(max4, max3v(min4, aC * (1.0f / aW)));
+        c.upscale_output[(size_t)y * c.W + x] = pack_rgba16f(v4(pix, 1.0f));   // imageStore(OutputTexture, pos, AF4(c, 1))
+    });
+}
+
+void pass_fsr_rcas(Ctx& c) {   // FSR_Pass.glsl CurrFilter (SAMPLE_RCAS), FsrRcasF ffx_fsr1.h:684-772
+    Image16 input{&c.upscale_output, c.W, c.H};
+    const float sharp = fsr_rcas_constant(c.in.fsr_sharpness);
+    for_pixels(c, c.W, c.H, [&](int x, int y) {
+        auto Ld = [&](int dx, int dy) { ivec2 p; p.x = x + dx; p.y = y + dy; return xyz(input.load(p)); };
+        //    b
+        //  d e f
+        //    h
+        vec3 b = Ld(0, -1), d = Ld(-1, 0), e = Ld(0, 0), f = Ld(1, 0), h = Ld(0, 1);
+        auto min4f = [](float p, float q, float r, float s_) { return fmin_(fmin_(p, fmin_(q, r)), s_); };   // min(AMin3F1(b,d,f),h)
+        auto max4f = [](float p, float q, float r, float s_) { return fmax_(fmax_(p, fmax_(q, r)), s_); };
+        vec3 mn4 = v3(min4f(b.x, d.x, f.x, h.x), min4f(b.y, d.y, f.y, h.y), min4f(b.z, d.z, f.z, h.z));
+        vec3 mx4 = v3(max4f(b.x, d.x, f.x, h.x), max4f(b.y, d.y, f.y, h.y), max4f(b.z, d.z, f.z, h.z));
+        auto lobe_of = [](float mn, float mx, float ec) {
+            float hitMin = fmin_(mn, ec) * (1.0f / (4.0f * mx));
+            float hitMax = (1.0f - fmax_(mx, ec)) * (1.0f / (4.0f * mn + -4.0f));
+            return fmax_(-hitMin, hitMax);
+        };
+        float lobeR = lobe_of(mn4.x, mx4.x, e.x), lobeG = lobe_of(mn4.y, mx4.y, e.y), lobeB = lobe_of(mn4.z, mx4.z, e.z);
+        float lobe = fmax_(-FSR_RCAS_LIMIT, fmin_(fmax_(lobeR, fmax_(lobeG, lobeB)), 0.0f)) * sharp;
+        float rcpL = fsr_rcp_med(4.0f * lobe + 1.0f);
+        vec3 pix = v3((lobe * b.x + lobe * d.x + lobe * h.x + lobe * f.x + e.x) * rcpL,
+                      (lobe * b.y + lobe * d.y + lobe * h.y + lobe * f.y + e.y) * rcpL,
+                      (lobe * b.z + lobe * d.z + lobe * h.z + lobe * f.z + e.z) * rcpL);
+        c.upscale_sharpen_output[(size_t)y * c.W + x] = pack_rgba16f(v4(pix, 1.0f));
+    });
+}
+
 void pass_taa_jasmine(Ctx& c) {  // taa.wgsl:79-170
     const uint32_t cur = c.in.frame.number % 2u, prev = 1u - cur;
     const bool smaa = c.in.smaa_tu4x != 0;
@@ -1671,9 +1809,10 @@ void post_process_node(Ctx& c) {  // PostProcessNode::run, post_process.rs:1140-
         }
     }
     pass_tone_mapping(c);
-    if (c.in.temporal_upscalers) {   // post_process.rs:1236-1277 (K11/K12); FSR1 blobs are out of scope
+    if (c.in.temporal_upscalers) {   // post_process.rs:1236-1308 (K11/K12 and FSR1)
         if (c.in.smaa_tu4x) { pass_smaa_tu4x(c); pass_smaa_tu4x_extrapolate(c); }
         if (c.in.taa_jitter) pass_taa_jasmine(c);
+        if (c.in.fsr1 && !c.in.smaa_tu4x) { pass_fsr_easu(c); pass_fsr_rcas(c); }
     }
 }
 
@@ -1706,6 +1845,7 @@ int hko_context_create(hko_context** out, uint32_t width, uint32_t height, int t
     c->denoise_internal_variance.assign(n, 0.0f);
     for (int i = 0; i < 2; ++i) { c->tone_mapping_output[i].assign(n, z2); c->taa_output[i].assign(4 * n, z2); }
     c->upscale_output.assign(4 * n, z2);
+    c->upscale_sharpen_output.assign(n, z2);
     c->previous_position.assign(n, v4(0.0f)); c->previous_velocity_uv.assign(n, v4(0.0f));
     memset(&c->in, 0, sizeof(c->in));
     *out = c;
@@ -1781,7 +1921,7 @@ int hko_render_frame(hko_context* c, const hk_frame_inputs* in) {
     return HK_OK;
 }
 // single passes, for per-pass parity from identical inputs.  pass ids: 0 albedo, 1 direct(sun), 2 direct(emissive),
-// 3 spatial(emissive), 4 indirect, 5 spatial(indirect), 6 denoise chain of signal `arg`, 7 tone mapping
+// 3 spatial(emissive), 4 indirect, 5 spatial(indirect), 6 denoise chain of signal `arg`, 7 tone mapping, 8 FSR EASU, 9 FSR RCAS
 int hko_run_pass(hko_context* c, const hk_frame_inputs* in, int pass, int arg) {
     int e = begin(c, in); if (e) return e;
     switch (pass) {
@@ -1797,6 +1937,8 @@ int hko_run_pass(hko_context* c, const hk_frame_inputs* in, int pass, int arg) {
             else { pass_denoise<0, true>(*c, arg); pass_denoise<1, true>(*c, arg); pass_denoise<2, true>(*c, arg); pass_denoise<3, true>(*c, arg); }
             break;
         case 7: pass_tone_mapping(*c); break;
+        case 8: pass_fsr_easu(*c); break;
+        case 9: pass_fsr_rcas(*c); break;
         default: return HK_ERR_INVALID_ARGUMENT;
     }
     return HK_OK;
@@ -1809,7 +1951,8 @@ static void* plane(hko_context* c, int which, size_t* bytes) {
     auto RR = [&](void* p, size_t b, size_t count) { *bytes = b * count; return p; };
     switch (which) {
         case HK_OUT_TONE_MAPPED: return RR(c->tone_mapping_output[c->in.frame.number % 2u].data(), 8, nr);
-        case HK_OUT_UPSCALED: return RR(c->upscale_output.data(), 8, 4 * nr);
+        case HK_OUT_UPSCALED: return RR(c->upscale_output.data(), 8, c->in.fsr1 ? n : 4 * nr);
+        case HK_OUT_FSR_SHARPENED: return RR(c->upscale_sharpen_output.data(), 8, n);
         case HK_OUT_TAA: return RR(c->taa_output[c->in.frame.number % 2u].data(), 8, smaa ? 4 * nr : nr);
         case HK_OUT_RENDER_DIRECT: case HK_OUT_RENDER_EMISSIVE: case HK_OUT_RENDER_INDIRECT:
             return RR(c->render[which - HK_OUT_RENDER_DIRECT].data(), 8, nr);
@@ -1832,8 +1975,9 @@ int hko_output_extent(hko_context* c, int which, uint32_t* width, uint32_t* heig
     size_t b = 0;
     if (!plane(c, which, &b)) return fail(c, HK_ERR_INVALID_ARGUMENT, "bad plane id");
     const bool deferred = which == HK_OUT_ALBEDO || (which >= HK_OUT_GBUFFER_POSITION && which <= HK_OUT_GBUFFER_VELOCITY_UV);
-    const int k = (which == HK_OUT_UPSCALED || (which == HK_OUT_TAA && c->in.smaa_tu4x)) ? 2 : 1;
-    *width = (uint32_t)(deferred ? c->W : k * c->RW); *height = (uint32_t)(deferred ? c->H : k * c->RH);
+    const bool fsr = c->in.fsr1 && (which == HK_OUT_UPSCALED || which == HK_OUT_FSR_SHARPENED);   // the camera target size
+    const int k = ((which == HK_OUT_UPSCALED && !c->in.fsr1) || (which == HK_OUT_TAA && c->in.smaa_tu4x)) ? 2 : 1;
+    *width = (uint32_t)((deferred || fsr) ? c->W : k * c->RW); *height = (uint32_t)((deferred || fsr) ? c->H : k * c->RH);
     return HK_OK;
 }
 int hko_readback(hko_context* c, int which, void* host, size_t bytes) {

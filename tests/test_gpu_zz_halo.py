@@ -193,6 +193,7 @@ def test_temporal_upscalers_on_tiles_equal_unsharded(smaa, taa, rects):
     for f in range(1, 9):
         inp = b.moving_inputs(f, step=(0.04, 0.01, -0.02))
         inp.temporal_upscalers = 1
+        inp.fsr1 = 0        # not SMAA = "TAA only" here: FSR1 itself runs on full-frame contexts only (tests/test_gpu_zz_fsr.py)
         full.render_frame(inp)
         for t in tiles:
             t.render_frame(inp)

@@ -36,7 +36,8 @@ def one_case(seed):
         max_temporal_reuse_count=int(rng.choice([1, 2, 8, 50, 200])), max_spatial_reuse_count=int(rng.choice([1, 10, 800])),
         max_reservoir_lifetime=float(rng.choice([0.5, 1.0, 2.0, 100.0])), solar_angle=float(rng.choice([0.0, 0.046, 0.3])),
         max_indirect_luminance=float(rng.choice([0.1, 10.0, 1e6])),
-        taa=int(rng.integers(0, 2)), upscale_kind=int(rng.integers(0, 2)), upscale_ratio=ratio)
+        taa=int(rng.integers(0, 2)), upscale_kind=int(rng.integers(0, 2)), upscale_ratio=ratio,
+        upscale_sharpness=float(rng.choice([0.0, 0.2, 1.0, 2.0])))
     upscalers = bool(rng.integers(0, 2))
     b = Bench(str(scene), w, h, **settings)
     dev, orc = b.device(), b.oracle()
@@ -50,7 +51,8 @@ def one_case(seed):
         an = Animation(b, {int(i): (lambda f, a=a, t=t: rotation_y_about(a * f, (0.0, 0.5, 0.0), tuple(t * f))) for i in ids})
     planes = ALL_PLANES + (DENOISED if settings["denoise"] else [])
     if upscalers:
-        planes = planes + ([L.OUT_UPSCALED] if settings["upscale_kind"] == plugin.UPSCALE_SMAA_TU4X else []) + \
+        # Upscale::SmaaTu4x: upscale_output[0]; Upscale::Fsr1: the EASU and RCAS images
+        planes = planes + ([L.OUT_UPSCALED] if settings["upscale_kind"] == plugin.UPSCALE_SMAA_TU4X else [L.OUT_UPSCALED, L.OUT_FSR_SHARPENED]) + \
                  ([L.OUT_TAA] if settings["taa"] == plugin.TAA_JASMINE else [])
     frames = int(rng.integers(2, 7))
     for f in range(1, frames + 1):
@@ -107,6 +109,7 @@ def tile_case(seed):
                         t.halo_pull(other)
         inp = b.moving_inputs(f, step=step)
         inp.temporal_upscalers = 1 if upscalers else 0
+        inp.fsr1 = 0          # FSR1 needs a full-frame context; on tiles Upscale::Fsr1 here means "TAA only"
         full.render_frame(inp)
         for t in tiles:
             t.render_frame(inp)

@@ -7,13 +7,15 @@
 #     gpurun --timeout 1200 -- tools/next_round_first_call.sh
 mkdir -p gpurun_out
 echo "== device suite, newest tests first"
-python -m pytest tests/test_gpu_zz_examples.py tests/test_gpu_zz_halo.py -m gpu -q 2>&1 | tail -6
-python -m pytest tests -m gpu -q --deselect tests/test_gpu_zz_examples.py --deselect tests/test_gpu_zz_halo.py 2>&1 | tail -4
+python -m pytest tests/test_gpu_zz_fsr.py tests/test_gpu_zz_examples.py tests/test_gpu_zz_halo.py -m gpu -q 2>&1 | tail -6
+python -m pytest tests -m gpu -q --deselect tests/test_gpu_zz_fsr.py --deselect tests/test_gpu_zz_examples.py --deselect tests/test_gpu_zz_halo.py 2>&1 | tail -4
 echo "== tuning variants (per-kernel ms; make a variant the default if its kernels drop)"
 python bench.py --steps 16 --warmup 4 --no-cpu-baseline 2>/dev/null | grep "^{" | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); k = d['kernel_ms']
 print('default       ', 'ms/frame %.3f' % d['ms_per_step'], ' '.join('%s=%.3f' % (n[:8], k[n]) for n in k))"
 [ -d bevy_hikari_b200/variants ] && tools/sweep_variants.sh
+echo "== BASELINE configs[2] (examples/scene.rs), never timed on a device so far"
+python bench.py --config scene_1080p --steps 16 --warmup 4 2>/dev/null | grep "^{" | tee gpurun_out/bench_r2_scene1080p.json | cut -c1-400
 echo "== bench line"
 python bench.py --steps 32 --warmup 8 2>/dev/null | grep "^{" | tee gpurun_out/bench_r2_first.json | cut -c1-400
