@@ -1,0 +1,306 @@
+"""`indirect_lit_ambient`, single bounce, for a pixel with no history (SURVEY.md 8(a) row P3 — the heaviest kernel of the path —
+with F3-F7), pinned from the outside.  A SECOND, independent restatement of src/shaders/light.wgsl:1263-1498 (the
+non-MULTIPLE_BOUNCES body) as numpy arithmetic written from the WGSL:
+  cosine-hemisphere bounce ray about the normalised G-buffer normal (:537-549, utils.wgsl normal_basis) -> closest hit over
+  EVERY world triangle by float64 brute force (no TLAS / BLAS) -> hit_info (interpolated, inverse-transpose-transformed,
+  normalised normal; :496-520) -> select_light_candidate at the hit point, both branches: emissive pick / alias table /
+  barycentric point / light hit / solid-angle density, and the fall-back to the (here absent or present) sun cone
+  (:599-708) -> shadow ray by brute force -> input_radiance (:842-872) -> shading at the hit with roughness forced to 1,
+  divided by the light density (:1417-1441) -> at the visible point the target  luminance(shading(..)) / cosine density ,
+  the reservoir update from empty and  r.w  (:1461-1480) -> render[2].
+Fed with the oracle's G-buffer it must reproduce the oracle's `render[2]`.  The brute-force hit distance is float64 in world
+space, the oracle's is fp32 in object space, so hit positions differ in the last bits and a little of that survives the
+Rgba16Float store; pixels with a grazing ray anywhere on the path are left out (counted, 3 % in cornell).  Measured:
+cornell 99.75 - 99.8 % of the texels bit-identical, 99.98 % within 1 f16 ulp (one shadow-ray flip in 4 000 pixels); minimal.rs
+(sun, sky misses -> the ambient branch) 100 %; a random triangle soup with three emissive instances 99.9 %.  CPU only."""
+import numpy as np
+import pytest
+
+from bevy_hikari_b200 import layout as L
+from bevy_hikari_b200 import plugin
+from tests.conftest import Bench
+from tests.test_direct_lit_numpy import (DISTANCE_MAX, F, GOLDEN_RATIO, INV_PI, RAY_BIAS, TAU, dot, fract, luminance, normalize,
+                                          saturate, shade_lit, ulps16)
+from tests.test_emissive_lit_numpy import LEAF, moller_trumbore, world_tris_of
+
+PI = F(3.141592653589793)
+INV_TAU = F(0.159154943)
+DONT_SAMPLE = 0x80000000
+
+
+def normal_basis_mul(n, v):                              # utils.wgsl normal_basis(n) * v, per row
+    s = np.fmin(np.sign(n[:, 2]) * F(2.0) + F(1.0), F(1.0))
+    with np.errstate(all="ignore"):
+        u = F(-1.0) / (s + n[:, 2])
+    w = n[:, 0] * n[:, 1] * u
+    t = np.stack([F(1.0) + s * n[:, 0] * n[:, 0] * u, s * w, -s * n[:, 0]], 1)
+    b = np.stack([w, s + n[:, 1] * n[:, 1] * u, -n[:, 1]], 1)
+    return (t * v[:, 0:1] + b * v[:, 1:2] + n * v[:, 2:3]).astype(F)
+
+
+def env_brdf_approx(f0, perceptual_roughness, NoV):       # bevy_pbr EnvBRDFApprox
+    c0 = np.array([-1.0, -0.0275, -0.572, 0.022], F)
+    c1 = np.array([1.0, 0.0425, 1.04, -0.04], F)
+    r = perceptual_roughness[..., None] * c0 + c1
+    a004 = np.fmin(r[..., 0] * r[..., 0], np.exp2(F(-9.28) * NoV)) * r[..., 0] + r[..., 1]
+    A, B = F(-1.04) * a004 + r[..., 2], F(1.04) * a004 + r[..., 3]
+    return f0 * A[..., None] + B[..., None]
+
+
+def shading(V, N, Lv, mat, radiance4, ambient_color, roughness_override=None):
+    """light.wgsl shading(): mix(lit, ambient, 1 - alpha).  `mat` = MATERIAL records (NO_TEXTURE form of retreive_surface)."""
+    rough = np.clip(mat["perceptual_roughness"], F(0.089), F(1.0))
+    rough = rough * rough
+    if roughness_override is not None:
+        rough = np.full_like(rough, F(roughness_override))
+    lit = shade_lit_rough(V, N, Lv, mat, radiance4[..., :3], rough)
+    base = mat["base_color"][..., :3]
+    metallic, reflectance = mat["metallic"][..., None], mat["reflectance"][..., None]
+    F0 = F(0.16) * reflectance * reflectance * (F(1.0) - metallic) + base * metallic
+    diffuse_color = base * (F(1.0) - metallic)
+    NoV = np.fmax(dot(N, V), F(0.0001))
+    amb = (env_brdf_approx(diffuse_color, np.ones_like(rough), NoV) + env_brdf_approx(F0, rough, NoV)) * ambient_color   # occlusion = 1
+    a = (F(1.0) - radiance4[..., 3])[..., None]
+    return lit * (F(1.0) - a) + amb * a
+
+
+def shade_lit_rough(V, N, Lv, mat, radiance, rough):
+    base = mat["base_color"][..., :3]
+    metallic, reflectance = mat["metallic"][..., None], mat["reflectance"][..., None]
+    F0 = F(0.16) * reflectance * reflectance * (F(1.0) - metallic) + base * metallic
+    diffuse_color = base * (F(1.0) - metallic)
+    with np.errstate(all="ignore"):
+        H = normalize(Lv + V)
+        NoL, NoH, LoH = saturate(dot(N, Lv)), saturate(dot(N, H)), saturate(dot(Lv, H))
+        NoV = np.fmax(dot(N, V), F(0.0001))
+        f90 = F(0.5) + F(2.0) * rough * LoH * LoH
+        sch = lambda f9, x: F(1.0) + (f9 - F(1.0)) * np.power(F(1.0) - x, F(5.0))
+        diffuse = diffuse_color * (sch(f90, NoL) * sch(f90, NoV) * INV_PI)[..., None]
+        a = NoH * rough
+        k = rough / (F(1.0) - NoH * NoH + a * a)
+        D = k * k * INV_PI
+        a2 = rough * rough
+        Vis = F(0.5) / (NoL * np.sqrt((NoV - a2 * NoV) * NoV + a2) + NoV * np.sqrt((NoL - a2 * NoL) * NoL + a2))
+        f90s = saturate(F0[..., 0] * F(16.5) + F0[..., 1] * F(16.5) + F0[..., 2] * F(16.5))
+        Fr = F0 + (f90s[..., None] - F0) * np.power(F(1.0) - LoH, F(5.0))[..., None]
+        out = ((D * Vis)[..., None] * Fr + diffuse) * radiance * NoL[..., None]
+    return out
+
+
+class Scene:
+    def __init__(self, b):
+        self.bufs = b.world.buffers()
+        self.n_inst = len(self.bufs["instances"])
+        self.tris, self.vidx, self.inst = zip(*[world_tris_of(self.bufs, i) for i in range(self.n_inst)])
+        self.all_tris = np.concatenate(self.tris)
+        self.owner = np.concatenate([np.full(len(t), i) for i, t in enumerate(self.tris)])
+        self.local = np.concatenate([np.arange(len(t)) for t in self.tris])
+        self.sun = np.array(list(b.lights.direction_to_light), F)
+        self.sun_color = np.array(list(b.lights.directional_color), F)[:3]
+        self.ambient = np.array(list(b.lights.ambient_color), F)[:3]
+        self.cos_solar = np.cos(F(b.settings.solar_angle)).astype(F)
+
+    def closest(self, origin, direction, chunk=192):
+        """closest hit over all triangles: distance, instance, local triangle, u, v, grazing flag"""
+        n = len(origin)
+        T = np.full(n, np.inf); K = np.zeros(n, np.int64); U = np.zeros(n); V = np.zeros(n); G = np.zeros(n, bool)
+        a, b, c = self.all_tris[:, 0], self.all_tris[:, 1], self.all_tris[:, 2]
+        for k0 in range(0, n, chunk):
+            sl = slice(k0, k0 + chunk)
+            t, edge, u, v = moller_trumbore(origin[sl].astype(np.float64), direction[sl].astype(np.float64), a, b, c)
+            k = np.argmin(t, 1); r = np.arange(len(k))
+            T[sl], K[sl], U[sl], V[sl] = t[r, k], k, u[r, k], v[r, k]
+            second = np.partition(t, 1, axis=1)[:, 1] if t.shape[1] > 1 else np.full(len(k), np.inf)
+            with np.errstate(invalid="ignore"):
+                G[sl] = (edge.min(1) < 2e-3) | (np.abs(second - t[r, k]) < 1e-4)          # edge, or two surfaces at one distance
+        return T, self.owner[K], self.local[K], U.astype(F), V.astype(F), G
+
+    def occluded(self, origin, direction, t_max, exclude, chunk=192):
+        n = len(origin)
+        out = np.zeros(n, bool); G = np.zeros(n, bool)
+        a, b, c = self.all_tris[:, 0], self.all_tris[:, 1], self.all_tris[:, 2]
+        for k0 in range(0, n, chunk):
+            sl = slice(k0, k0 + chunk)
+            t, edge, _, _ = moller_trumbore(origin[sl].astype(np.float64), direction[sl].astype(np.float64), a, b, c)
+            t = np.where(self.owner[None, :] == exclude[sl, None], np.inf, t)
+            out[sl] = (t < t_max[sl, None]).any(1)
+            with np.errstate(invalid="ignore"):
+                G[sl] = (edge.min(1) < 2e-3) | (np.abs(t - t_max[sl, None]) < 1e-3).any(1)
+        return out, G
+
+    def hit_normal(self, inst_id, tri, u, v):
+        """hit_info (:496-520): v0.n + u (v1.n - v0.n) + v (v2.n - v0.n), through the inverse transpose, normalised"""
+        out = np.zeros((len(inst_id), 3), F)
+        for i in np.unique(inst_id):
+            m = inst_id == i
+            inst = self.inst[i]
+            verts = self.bufs["vertices"][int(inst["mesh"]["vertex"]) + self.vidx[i][tri[m]].astype(np.int64)]
+            n0, n1, n2 = verts["normal"][:, 0], verts["normal"][:, 1], verts["normal"][:, 2]
+            n_obj = n0 + u[m, None] * (n1 - n0) + v[m, None] * (n2 - n0)
+            itm = inst["inverse_transpose_model"].reshape(4, 4)[:3, :3]
+            out[m] = normalize((n_obj[:, 0:1] * itm[0] + n_obj[:, 1:2] * itm[1] + n_obj[:, 2:3] * itm[2]).astype(F))
+        return out
+
+    def select_light_candidate(self, rand, position, normal, own_instance):
+        """light.wgsl:599-708.  Returns direction, p, max_distance, emissive_instance (DONT_SAMPLE = sun fall-back), the light's
+        material (for its radiance) and a grazing flag."""
+        n = len(position)
+        # directional part (:611-616): cone sample about the sun
+        z = F(1.0) - (F(1.0) - self.cos_solar) * rand[:, 2]
+        theta = TAU * rand[:, 3]
+        r = np.sqrt(F(1.0) - z * z)
+        cone = np.stack([r * np.cos(theta), r * np.sin(theta), z], 1).astype(F)
+        rand_direction = normal_basis_mul(np.tile(self.sun, (n, 1)), cone)
+        direction = rand_direction.copy(); p = np.ones(n, F); t_max = np.full(n, np.inf)
+        emissive_instance = np.full(n, DONT_SAMPLE, np.int64); graze = np.zeros(n, bool)
+        light_material = np.zeros(n, np.int64)
+        leaves = [int(e) - LEAF for e in self.bufs["emissive_nodes"]["entry_index"] if int(e) >= LEAF]
+        count = np.zeros(n, F); rand_1d = rand[:, 0].copy(); chosen = np.full(n, -1, np.int64)
+        for e in leaves:
+            em = self.bufs["emissives"][e]
+            inside = (position > em["position"] - em["radius"]).all(1) & (position < em["position"] + em["radius"]).all(1) & \
+                     (own_instance != int(em["instance"]))
+            rand_1d = np.where(inside, fract(rand_1d + GOLDEN_RATIO), rand_1d)
+            count = np.where(inside, count + F(1.0), count)
+            with np.errstate(all="ignore"):
+                chosen = np.where(inside & (rand_1d < F(1.0) / count), e, chosen)
+        for e in leaves:
+            sel = np.nonzero(chosen == e)[0]
+            if not len(sel):
+                continue
+            em = self.bufs["emissives"][e]
+            light = int(em["instance"]); inst = self.inst[light]
+            rnd = rand[sel]
+            n_alias = int(em["alias_table_count"])
+            alias_index = np.minimum((rnd[:, 0] * F(n_alias)).astype(np.int64), n_alias - 1)
+            entry = self.bufs["alias_table"][int(em["alias_table_offset"]) + alias_index]
+            primitive = np.where(rnd[:, 1] < entry["prob"], entry["index"].astype(np.int64), alias_index)
+            srx = np.sqrt(rnd[:, 2]); bx, by = F(1.0) - srx, rnd[:, 3] * srx
+            local = self.bufs["primitives"][int(inst["mesh"]["primitive"]) + primitive]["vertices"]["position"]
+            p_local = bx[:, None] * local[:, 0] + by[:, None] * local[:, 1] + (F(1.0) - bx - by)[:, None] * local[:, 2]
+            hp = np.concatenate([p_local, np.ones((len(sel), 1), F)], 1) @ inst["model"].reshape(4, 4)
+            p_world = (hp[:, :3] / hp[:, 3:4]).astype(F)
+            P, N = position[sel], normal[sel]
+            origin = (P + N * RAY_BIAS).astype(F)
+            d = normalize(p_world - P).astype(F)
+            tl = self.tris[light]
+            t_all, edge, u_all, v_all = moller_trumbore(origin.astype(np.float64), d.astype(np.float64), tl[:, 0], tl[:, 1], tl[:, 2])
+            k = np.argmin(t_all, 1); rr = np.arange(len(sel))
+            t_light = t_all[rr, k]
+            found = (dot(d, N) > 0) & np.isfinite(t_light)
+            n_world = self.hit_normal(np.full(len(sel), light), k, u_all[rr, k].astype(F), v_all[rr, k].astype(F))
+            hit_pos = (origin + d * t_light.astype(F)[:, None]).astype(F)
+            delta = hit_pos - P
+            with np.errstate(all="ignore"):
+                pdf = dot(delta, delta) / np.abs(dot(d, n_world) * F(em["surface_area"])) / count[sel]
+            direction[sel] = np.where(found[:, None], d, rand_direction[sel])
+            p[sel] = np.where(found, pdf, F(1.0))
+            t_max[sel] = np.where(found, t_light, np.inf)
+            emissive_instance[sel] = np.where(found, light, DONT_SAMPLE)
+            light_material[sel] = int(inst["material"])
+            graze[sel] = edge.min(1) < 2e-3
+        return direction, p, t_max, emissive_instance, light_material, graze
+
+
+def indirect_numpy(b, orc, frame_number, noise):
+    sc = Scene(b)
+    pos = orc.readback(L.OUT_GBUFFER_POSITION)
+    g_normal = np.maximum(orc.readback(L.OUT_GBUFFER_NORMAL).astype(F) / F(127.0), F(-1.0))[..., :3]
+    im = orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)
+    H, W = pos.shape[:2]
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    tex = noise.reshape(16, 64, 64, 4)[frame_number % 16].astype(F) / F(255.0)
+    nu = (xs.astype(F) + F(frame_number) + F(0.5)) / F(64.0)
+    nv = (ys.astype(F) + F(frame_number) + F(0.5)) / F(64.0)
+    random = tex[np.floor(nv * F(64.0)).astype(np.int64) % 64, np.floor(nu * F(64.0)).astype(np.int64) % 64]
+    random = fract(random + F(frame_number) * GOLDEN_RATIO).reshape(-1, 4)
+    covered = (pos[..., 3] >= F(1.1920929e-7)).reshape(-1)
+    idx = np.nonzero(covered)[0]
+    P = pos[..., :3].reshape(-1, 3)[idx]
+    with np.errstate(all="ignore"):
+        N = normalize(g_normal.reshape(-1, 3)[idx])                      # :1289 — normalised here, unlike direct_lit
+    rnd = random[idx]
+    material = np.floor(im[..., 1]).astype(np.int64).reshape(-1)[idx]
+    # bounce ray (:1389-1393)
+    r = np.sqrt(rnd[:, 0]); theta = F(2.0) * PI * rnd[:, 1]
+    tx, ty = r * np.cos(theta), r * np.sin(theta)
+    dz = np.sqrt(F(1.0) - (tx * tx + ty * ty))
+    pdf = F(2.0) * INV_TAU * dz
+    origin = (P + N * RAY_BIAS).astype(F)
+    direction = normal_basis_mul(N, np.stack([tx, ty, dz], 1).astype(F))
+    t_hit, h_inst, h_tri, h_u, h_v, graze = sc.closest(origin, direction)
+    hit = np.isfinite(t_hit)
+    t32 = np.where(hit, t_hit, 0.0).astype(F)
+    sample_pos = np.where(hit[:, None], origin + direction * t32[:, None], origin + direction * DISTANCE_MAX).astype(F)
+    sample_normal = np.zeros_like(P)
+    sample_normal[hit] = sc.hit_normal(h_inst[hit], h_tri[hit], h_u[hit], h_v[hit])
+    radiance = np.zeros((len(idx), 4), F)
+    # miss: ambient only, alpha 0 (:1445-1449)
+    radiance[~hit, :3] = sc.ambient
+    # hit: one light sample at the hit point (:1408-1441)
+    hs = np.nonzero(hit)[0]
+    if len(hs):
+        sp, sn = sample_pos[hs], sample_normal[hs]
+        c_dir, c_p, c_tmax, c_em, c_mat, c_graze = sc.select_light_candidate(rnd[hs], sp, sn, h_inst[hs])
+        graze[hs] |= c_graze
+        trace = (dot(c_dir, sn) > 0) & (c_p > 0)
+        s_origin = (sp + sn * RAY_BIAS).astype(F)
+        occ, og = sc.occluded(s_origin, c_dir, np.where(np.isfinite(c_tmax), c_tmax, 3.4e38), c_em)
+        graze[hs] |= og & trace
+        sample_directional = c_em == DONT_SAMPLE
+        in_rad = np.zeros((len(hs), 4), F)
+        # input_radiance (:842-872)
+        hit_directional = dot(c_dir, np.tile(sc.sun, (len(hs), 1))) >= sc.cos_solar
+        free = ~occ
+        # unoccluded + emissive candidate: info still names the light (from select_light_candidate) -> its radiance, alpha 1
+        em_mats = sc.bufs["materials"][c_mat]
+        em_rad = F(255.0) * em_mats["emissive"][:, 3:4] * em_mats["emissive"][:, :3]
+        in_rad[:, 3] = 1.0
+        in_rad[:, :3] = np.where((free & ~sample_directional)[:, None], em_rad, F(0.0))
+        sun_seen = free & sample_directional & hit_directional
+        in_rad[:, :3] = np.where(sun_seen[:, None], sc.sun_color, in_rad[:, :3])
+        sky = free & sample_directional & ~hit_directional                     # nothing hit, outside the cone: alpha 0, radiance 0
+        in_rad[sky, 3] = 0.0
+        hit_mats = sc.bufs["materials"][np.array([int(sc.inst[i]["material"]) for i in h_inst[hs]])]
+        with np.errstate(all="ignore"):
+            out = shading(normalize(P[hs] - sp), sn, c_dir, hit_mats, in_rad, sc.ambient, roughness_override=1.0) / c_p[:, None]
+        out = np.where(trace[:, None], out, F(0.0))
+        radiance[hs, :3] = out
+        radiance[hs, 3] = np.where(trace, F(1.0), F(0.0))                       # s.radiance += vec4(out, 1) only when traced
+    # at the visible point (:1461-1480)
+    view = normalize(np.array(list(b.view.world_position), F) - P)
+    mats = sc.bufs["materials"][material]
+    with np.errstate(all="ignore"):
+        sample_radiance = shading(view, N, normalize(sample_pos - P), mats, radiance, sc.ambient)
+        w_new = np.where(pdf > 0, luminance(sample_radiance) / pdf, F(0.0))
+        taken = w_new > 0
+        r_w = np.where(taken, w_new / (F(1.0) * luminance(sample_radiance)), F(0.0))
+        color = np.where(taken[:, None], sample_radiance * r_w[:, None], F(0.0))
+    textured = (mats["base_color_texture"] != 0xFFFFFFFF) | (mats["emissive_texture"] != 0xFFFFFFFF)
+    full = np.zeros((H * W, 3), F); full[idx] = color
+    ex = np.zeros(H * W, bool); ex[idx] = graze | textured
+    return full.reshape(H, W, 3), ex.reshape(H, W), covered.reshape(H, W)
+
+
+@pytest.mark.parametrize("scene,size,frames", [("cornell", (80, 80), (1, 2)), ("minimal", (80, 56), (1,)), ("soup5", (80, 56), (1,))])
+def test_oracle_indirect_single_bounce_equals_independent_numpy_restatement(scene, size, frames):
+    if scene.startswith("soup"):
+        from bevy_hikari_b200 import scenes
+        scenes.SCENE_BUILDERS[scene] = lambda: scenes.soup(int(scene[4:]))
+    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=0, denoise=0, indirect_bounces=1,
+              emissive_spatial_reuse=0, indirect_spatial_reuse=0)
+    orc = b.oracle()
+    noise = plugin.load_noise()
+    for f in range(1, max(frames) + 1):
+        orc.render_frame(b.inputs(f))
+        if f not in frames:
+            continue
+        want, excluded, covered = indirect_numpy(b, orc, f, noise)
+        got = orc.readback(L.OUT_RENDER_INDIRECT).astype(F)
+        clean = covered & ~excluded
+        d = ulps16(got[..., :3], want).max(-1)
+        assert (got[..., :3].sum(-1) > 0).sum() > 0.2 * covered.sum()
+        assert excluded.sum() <= 0.15 * covered.sum(), (f, int(excluded.sum()), int(covered.sum()))
+        assert (d[clean] == 0).mean() >= 0.99 and (d[clean] <= 1).mean() >= 0.998, (f, float((d[clean] == 0).mean()), float((d[clean] <= 1).mean()))
+        assert (d[clean] > 2).sum() <= 3, (f, int((d[clean] > 2).sum()))
+        assert (got[..., 3][covered] == 1).all() and not got[~covered].any()
