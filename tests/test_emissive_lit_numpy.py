@@ -36,8 +36,10 @@ def moller_trumbore(o, d, a, b, c):
     v = (q * d[:, None, :]).sum(-1) * inv
     t = (q * ac).sum(-1) * inv
     inside = np.minimum(np.minimum(u, v), 1.0 - u - v)
-    hit = ok & (inside >= 0) & (t > 1e-7)
-    return np.where(hit, t, np.inf), np.where(ok & (t > 1e-7), np.abs(inside), np.inf), u, v
+    hit = ok & (inside >= 0) & (t > 1.1920929e-7)                      # intersects_triangle: distance > F32_EPSILON (:393)
+    margin = np.where(ok & (t > 1.1920929e-7), np.abs(inside), np.inf)
+    margin = np.where(ok & (inside >= 0) & (np.abs(t) < 1e-5), 0.0, margin)   # a surface through the ray origin: verdict hangs on the epsilon
+    return np.where(hit, t, np.inf), margin, u, v
 
 
 def world_tris_of(bufs, i):
