@@ -157,6 +157,9 @@ class Scene:
         direction = rand_direction.copy(); p = np.ones(n, F); t_max = np.full(n, np.inf)
         emissive_instance = np.full(n, DONT_SAMPLE, np.int64); graze = np.zeros(n, bool)
         light_material = np.zeros(n, np.int64)
+        # *info = empty_hit_info(position, rand_direction) (:618, :488-494); the fall-back of :696-702 uses the biased origin
+        self.info_position = np.concatenate([position + rand_direction * DISTANCE_MAX, np.zeros((n, 1), F)], 1).astype(F)
+        self.info_normal = np.zeros((n, 3), F)
         leaves = [int(e) - LEAF for e in self.bufs["emissive_nodes"]["entry_index"] if int(e) >= LEAF]
         count = np.zeros(n, F); rand_1d = rand[:, 0].copy(); chosen = np.full(n, -1, np.int64)
         for e in leaves:
@@ -202,6 +205,9 @@ class Scene:
             emissive_instance[sel] = np.where(found, light, DONT_SAMPLE)
             light_material[sel] = int(inst["material"])
             graze[sel] = edge.min(1) < 2e-3
+            fall_back = np.concatenate([origin + d * DISTANCE_MAX, np.zeros((len(sel), 1), F)], 1)
+            self.info_position[sel] = np.where(found[:, None], np.concatenate([hit_pos, np.ones((len(sel), 1), F)], 1), fall_back)
+            self.info_normal[sel] = np.where(found[:, None], n_world, F(0.0))
         return direction, p, t_max, emissive_instance, light_material, graze
 
 

@@ -1,0 +1,222 @@
+"""Temporal ReSTIR with history, pinned from the outside on the emissive `direct_lit` pass —
+the pass that lights cornell.  A SECOND, independent restatement, in numpy from the WGSL, of what happens to a pixel that
+HAS a reservoir from the previous frame:
+  unpack_reservoir (:77-106: f16 pairs, unorm16 random numbers, snorm8 normals with lifetime / sample_position.w in the
+  fourth byte, instance id as a float) -> check_previous_reservoir (:917-935) -> the new candidate of this frame ->
+  update_reservoir with rand = fract(sum(random)) and the keep-or-replace rule (:146-171) -> the M clamp of temporal_restir
+  (:937-952) -> r.w, lifetime + 1, the variance estimate (:1216-1224) -> pack_reservoir (:108-136) and the shaded output.
+The previous frame's reservoir buffer is read back from the oracle and handed to the restatement; its result is compared
+with the oracle's NEW reservoir buffer field by field (bits of the packed record) and with render[1].  Static camera, so a
+pixel's history is its own record (previous_uv = uv).  Pixels whose candidate ray grazes an edge are left out (counted).
+Measured (cornell, frames 2-4, M clamp 3): every packed field but sample_position bit-identical on >= 99.5 % of the records
+(sample_position: kept samples bit-identical, replaced ones within 5e-6), count exact, render[1] 99.9 % bit-identical.
+It also confirmed a consequence of the WGSL that is easy to miss: `visible_instance` travels with the SAMPLE, so a record whose
+sample was never replaced stores instance 0 and is rejected by the instance test one frame later (a third of cornell's
+pixels at frame 2) — the oracle does the same.  CPU only."""
+import numpy as np
+import pytest
+
+from bevy_hikari_b200 import layout as L
+from bevy_hikari_b200 import plugin
+from tests.conftest import Bench
+from tests.test_direct_lit_numpy import F, GOLDEN_RATIO, RAY_BIAS, dot, fract, luminance, normalize, ulps16
+from tests.test_indirect_numpy import DONT_SAMPLE, Scene, shading
+
+U = np.uint32
+
+
+def unpack_f16x2(w):
+    w = np.asarray(w, U)
+    return (w & U(0xFFFF)).astype(np.uint16).view(np.float16).astype(F), (w >> U(16)).astype(np.uint16).view(np.float16).astype(F)
+
+
+def pack_f16x2(a, b):
+    with np.errstate(over="ignore"):                                       # w2_sum beyond 65504 stores as +inf, as pack2x16float does
+        return _pack_f16x2(a, b)
+
+
+def _pack_f16x2(a, b):
+    return np.asarray(a, F).astype(np.float16).view(np.uint16).astype(U) | (np.asarray(b, F).astype(np.float16).view(np.uint16).astype(U) << U(16))
+
+
+def unpack_unorm16x2(w):
+    w = np.asarray(w, U)
+    return (w & U(0xFFFF)).astype(F) / F(65535.0), (w >> U(16)).astype(F) / F(65535.0)
+
+
+def pack_unorm16x2(a, b):
+    q = lambda x: np.floor(F(0.5) + F(65535.0) * np.clip(x, F(0.0), F(1.0))).astype(U)
+    return q(a) | (q(b) << U(16))
+
+
+def unpack_snorm8x4(w):
+    w = np.asarray(w, U)
+    b = np.stack([(w >> U(8 * k)) & U(0xFF) for k in range(4)], -1).astype(np.uint8).view(np.int8).astype(F)
+    return np.maximum(b / F(127.0), F(-1.0))
+
+
+def pack_snorm8x4(v):
+    # clamp as min(max(v, -1), 1) with IEEE minNum / maxNum: the normalised zero normal of a never-replaced sample is NaN and
+    # packs as -127 under the rule hk_math.h fixes for both implementations (WGSL leaves it open)
+    q = np.floor(F(0.5) + F(127.0) * np.fmin(np.fmax(v, F(-1.0)), F(1.0))).astype(np.int32) & 0xFF
+    return (q[..., 0] | (q[..., 1] << 8) | (q[..., 2] << 16) | (q[..., 3] << 24)).astype(U)
+
+
+def unpack_reservoir(p):
+    r = {}
+    r["count"], r["w"] = unpack_f16x2(p["reservoir"][..., 0])
+    r["w_sum"], r["w2_sum"] = unpack_f16x2(p["reservoir"][..., 1])
+    a, b_ = unpack_f16x2(p["radiance"][..., 0]); c, d = unpack_f16x2(p["radiance"][..., 1])
+    r["radiance"] = np.stack([a, b_, c, d], -1)
+    a, b_ = unpack_unorm16x2(p["random"][..., 0]); c, d = unpack_unorm16x2(p["random"][..., 1])
+    r["random"] = np.stack([a, b_, c, d], -1)
+    t2 = unpack_snorm8x4(p["visible_normal"])
+    r["visible_position"] = p["visible_position"].astype(F)
+    with np.errstate(all="ignore"):
+        r["visible_normal"] = normalize(t2[..., :3])
+    r["lifetime"] = F(127.0) * (F(1.0) + t2[..., 3])
+    t2 = unpack_snorm8x4(p["sample_normal"])
+    r["sample_position"] = np.concatenate([p["sample_position"][..., :3], t2[..., 3:4]], -1).astype(F)
+    with np.errstate(all="ignore"):
+        r["sample_normal"] = normalize(t2[..., :3])
+    r["visible_instance"] = p["sample_position"][..., 3].astype(np.int64)
+    return r
+
+
+def temporal_emissive_numpy(b, orc, frame_number, noise, previous):
+    sc = Scene(b)
+    pos = orc.readback(L.OUT_GBUFFER_POSITION)
+    g_normal = np.maximum(orc.readback(L.OUT_GBUFFER_NORMAL).astype(F) / F(127.0), F(-1.0))[..., :3]
+    im = orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)
+    H, W = pos.shape[:2]
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    tex = noise.reshape(16, 64, 64, 4)[frame_number % 16].astype(F) / F(255.0)
+    nu = (xs.astype(F) + F(frame_number) + F(0.5)) / F(64.0)
+    nv = (ys.astype(F) + F(frame_number) + F(0.5)) / F(64.0)
+    random = tex[np.floor(nv * F(64.0)).astype(np.int64) % 64, np.floor(nu * F(64.0)).astype(np.int64) % 64]
+    random = fract(random + F(frame_number) * GOLDEN_RATIO).reshape(-1, 4)
+    covered = (pos[..., 3] >= F(1.1920929e-7)).reshape(-1)
+    idx = np.nonzero(covered)[0]
+    P = pos[..., :3].reshape(-1, 3)[idx]; depth = pos[..., 3].reshape(-1)[idx]
+    N = g_normal.reshape(-1, 3)[idx]                                       # raw, not normalised (:1071)
+    rnd = random[idx]
+    instance = np.floor(im[..., 0]).astype(np.int64).reshape(-1)[idx]
+    material = np.floor(im[..., 1]).astype(np.int64).reshape(-1)[idx]
+    n = len(idx)
+    # --- the candidate of this frame (:1104-1151, EMISSIVE_LIT)
+    c_dir, c_p, c_tmax, c_em, c_mat, graze = sc.select_light_candidate(rnd, P, N, instance)
+    info_pos, info_nrm = sc.info_position.copy(), sc.info_normal.copy()
+    trace = (dot(c_dir, N) > 0) & (c_p > 0) & (c_em != DONT_SAMPLE)
+    origin = (P + N * RAY_BIAS).astype(F)
+    occ, og = sc.occluded(origin, c_dir, np.where(np.isfinite(c_tmax), c_tmax, 3.4e38), c_em)
+    graze |= og & trace
+    lit = trace & ~occ
+    em = sc.bufs["materials"][c_mat]["emissive"]
+    s_radiance = np.zeros((n, 4), F)
+    s_radiance[:, :3] = np.where(lit[:, None], F(255.0) * em[:, 3:4] * em[:, :3], F(0.0))
+    s_radiance[:, 3] = np.where(trace, F(1.0), F(0.0))                     # input_radiance alpha = 1 whenever it was called
+    # an occluded shadow ray rewrites info with the occluder (:526-533): position is traversal-order dependent, but such a
+    # candidate has weight 0 and can never enter the reservoir, so it is not needed
+    with np.errstate(all="ignore"):
+        w_new = np.where(c_p > 0, luminance(s_radiance[:, :3]) / c_p, F(0.0))
+    # --- history (:1089-1095): the pixel's own record of the previous frame
+    prev = unpack_reservoir(previous.reshape(-1)[idx])
+    with np.errstate(all="ignore"):
+        ratio = prev["visible_position"][:, 3] / depth
+        ratio = np.where(ratio < 1.0, F(1.0) / ratio, ratio)
+        depth_miss = ratio > F(1.05) * (F(1.0) + F(0.5) * rnd[:, 0])
+        miss = depth_miss | (dot(N, prev["visible_normal"]) < F(0.9)) | (prev["visible_instance"] != instance)
+    r = {k: (np.where(miss.reshape((-1,) + (1,) * (v.ndim - 1)), 0, v)).astype(v.dtype) for k, v in prev.items()}
+    # --- update_reservoir + clamp (:146-171, :937-952)
+    r["w_sum"] = r["w_sum"] + w_new
+    r["w2_sum"] = r["w2_sum"] + w_new * w_new
+    r["count"] = r["count"] + F(1.0)
+    rand = fract(rnd[:, 0] + rnd[:, 1] + rnd[:, 2] + rnd[:, 3])
+    with np.errstate(all="ignore"):
+        take = rand < w_new / r["w_sum"]
+    new = dict(radiance=s_radiance, random=rnd, sample_position=info_pos, sample_normal=info_nrm)
+    for k, v in new.items():
+        r[k] = np.where(take[:, None], v, r[k]).astype(F)
+    # (*r).s = s replaces the WHOLE sample, visible_instance included; visible_position / visible_normal are refreshed for
+    # every pixel afterwards (:1213-1214) but visible_instance is not: a record whose sample was never replaced keeps
+    # instance 0 and fails the instance test of the next frame unless the pixel shows instance 0
+    r["visible_instance"] = np.where(take, instance, r["visible_instance"])
+    m = F(b.settings.max_temporal_reuse_count)
+    over = r["count"] > m
+    with np.errstate(all="ignore"):
+        r["w_sum"] = np.where(over, r["w_sum"] * (m / r["count"]), r["w_sum"])
+        r["w2_sum"] = np.where(over, r["w2_sum"] * (m / r["count"]), r["w2_sum"])
+        r["count"] = np.where(over, m, r["count"])
+        total = r["count"] * luminance(r["radiance"][:, :3])
+        r["w"] = np.where(total > 0, r["w_sum"] / total, F(0.0))
+        r["lifetime"] = r["lifetime"] + F(1.0)
+        variance = r["w2_sum"] / r["count"] - np.power(r["w_sum"] / r["count"], F(2.0))
+        variance = np.fmin(np.where(r["count"] < 1.0, variance, variance / r["count"]), F(10.0))
+        variance_scale = r["w2_sum"] / r["count"] / np.fmax(r["count"], F(1.0))       # the minuend: the estimate is a difference of two such terms
+    # --- pack (:108-136) with this frame's visible point
+    packed = np.zeros(n, L.PACKED_RESERVOIR)
+    packed["reservoir"][:, 0] = pack_f16x2(r["count"], r["w"]); packed["reservoir"][:, 1] = pack_f16x2(r["w_sum"], r["w2_sum"])
+    packed["radiance"][:, 0] = pack_f16x2(r["radiance"][:, 0], r["radiance"][:, 1])
+    packed["radiance"][:, 1] = pack_f16x2(r["radiance"][:, 2], r["radiance"][:, 3])
+    packed["random"][:, 0] = pack_unorm16x2(r["random"][:, 0], r["random"][:, 1])
+    packed["random"][:, 1] = pack_unorm16x2(r["random"][:, 2], r["random"][:, 3])
+    packed["visible_position"] = np.concatenate([P, depth[:, None]], 1)
+    packed["sample_position"] = np.concatenate([r["sample_position"][:, :3], r["visible_instance"].astype(F)[:, None]], 1)
+    packed["visible_normal"] = pack_snorm8x4(np.concatenate([N, (r["lifetime"] / F(127.0) - F(1.0))[:, None]], 1))
+    packed["sample_normal"] = pack_snorm8x4(np.concatenate([r["sample_normal"], r["sample_position"][:, 3:4]], 1))
+    # --- output (:1230-1259, no RENDER_EMISSIVE on this pipeline)
+    view = normalize(np.array(list(b.view.world_position), F) - P)
+    with np.errstate(all="ignore"):
+        out = shading(view, N, normalize(r["sample_position"][:, :3] - P), sc.bufs["materials"][material], r["radiance"], sc.ambient)
+        out = out * r["w"][:, None]
+    return idx, packed, out.astype(F), (variance.astype(F), variance_scale.astype(F)), graze, take, miss
+
+
+@pytest.mark.parametrize("scene,size", [("cornell", (72, 72)), ("soup5", (80, 56))])
+def test_oracle_temporal_reuse_equals_independent_numpy_restatement(scene, size):
+    if scene.startswith("soup"):
+        from bevy_hikari_b200 import scenes
+        scenes.SCENE_BUILDERS[scene] = lambda: scenes.soup(int(scene[4:]))
+    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=1, denoise=0, indirect_bounces=1,
+              emissive_spatial_reuse=0, indirect_spatial_reuse=0, max_temporal_reuse_count=3)     # M clamp reached at frame 4
+    orc = b.oracle()
+    noise = plugin.load_noise()
+    H, W = size[1], size[0]
+    replaced = kept = clamped = rejected = 0
+    for f in range(1, 5):                                  # emissive_validate_interval = 5: frames 1..4 take new candidates only
+        inp = b.inputs(f)
+        assert f % inp.frame.emissive_validate_interval != 0
+        read_buffer = L.OUT_RESERVOIR_0 + 2 + (f % 2)      # light.rs:518-546: binding 0 = buf[base + head], binding 1 = buf[base + 1 - head]
+        previous = orc.readback(read_buffer).copy()
+        orc.render_frame(inp)
+        if f == 1:
+            assert not previous.view(np.uint8).any()       # zeroed history
+            continue
+        idx, packed, out, variance, graze, take, miss = temporal_emissive_numpy(b, orc, f, noise, previous)
+        written = orc.readback(L.OUT_RESERVOIR_0 + 2 + 1 - (f % 2)).reshape(-1)[idx]
+        clean = ~graze
+        assert clean.mean() > 0.9
+        for field in ("radiance", "random", "visible_position", "visible_normal", "sample_normal"):
+            same = (written[field] == packed[field]) if written[field].ndim == 1 else (written[field] == packed[field]).all(-1)
+            assert same[clean].mean() >= 0.995, (f, field, float(same[clean].mean()))
+        # sample_position is stored in fp32: a kept sample is copied bit for bit, a replaced one carries the hit point, whose
+        # distance the oracle computes in fp32 object space and this checker in float64 world space
+        sp_same = (written["sample_position"] == packed["sample_position"]).all(-1)
+        assert sp_same[clean & ~take].mean() >= 0.999
+        err = np.abs(written["sample_position"][clean] - packed["sample_position"][clean]).max(-1)
+        assert (err <= 5e-6).mean() >= 0.98 and err.max() <= 2e-4, (f, float((err <= 5e-6).mean()), float(err.max()))
+        # (count, w, w_sum, w2_sum) as f16: count exactly, the sums within an ulp (fp32 order of the candidate's weight)
+        gc, gw = unpack_f16x2(written["reservoir"][:, 0]); wc, ww = unpack_f16x2(packed["reservoir"][:, 0])
+        assert np.array_equal(gc[clean], wc[clean])
+        for got, want in ((gw, ww), unpack_f16x2(written["reservoir"][:, 1])[:1] + unpack_f16x2(packed["reservoir"][:, 1])[:1]):
+            assert (ulps16(got[clean], want[clean]) <= 1).mean() >= 0.995
+        render = orc.readback(L.OUT_RENDER_EMISSIVE).astype(F).reshape(-1, 4)[idx]
+        d = ulps16(render[:, :3], out).max(-1)
+        assert (d[clean] <= 1).mean() >= 0.99 and (d[clean] == 0).mean() >= 0.97, (f, float((d[clean] <= 1).mean()), float((d[clean] == 0).mean()))
+        got_var = orc.readback(L.OUT_VARIANCE_EMISSIVE).reshape(-1)[idx]
+        variance, scale = variance
+        assert (np.abs(got_var[clean] - variance[clean]) <= 1e-4 * scale[clean] + 1e-7).all()     # cancellation: relative to the terms, not to the difference
+        replaced += int((take & clean).sum()); kept += int((~take & clean & ~miss).sum()); clamped += int((wc[clean] == 3).sum() if f == 4 else 0)
+        rejected += int((miss & clean).sum())
+    # both outcomes of the update, the clamp and the rejection of a stale record (instance test) were exercised
+    assert replaced > 50 and kept > 50 and clamped > 50 and rejected > 0, (replaced, kept, clamped, rejected)
