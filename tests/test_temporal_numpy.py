@@ -83,7 +83,8 @@ def unpack_reservoir(p):
     return r
 
 
-def temporal_emissive_numpy(b, orc, frame_number, noise, previous):
+def temporal_emissive_numpy(b, orc, frame_number, noise, previous, inp=None):
+    """`inp` = the frame inputs when the camera moves: history is then fetched at previous_uv = uv - velocity (:1089-1090)"""
     sc = Scene(b)
     pos = orc.readback(L.OUT_GBUFFER_POSITION)
     g_normal = np.maximum(orc.readback(L.OUT_GBUFFER_NORMAL).astype(F) / F(127.0), F(-1.0))[..., :3]
@@ -119,8 +120,18 @@ def temporal_emissive_numpy(b, orc, frame_number, noise, previous):
     # candidate has weight 0 and can never enter the reservoir, so it is not needed
     with np.errstate(all="ignore"):
         w_new = np.where(c_p > 0, luminance(s_radiance[:, :3]) / c_p, F(0.0))
-    # --- history (:1089-1095): the pixel's own record of the previous frame
-    prev = unpack_reservoir(previous.reshape(-1)[idx])
+    # --- history (:1089-1095, :181-190): the record at previous_uv = uv - velocity (the pixel's own under a static camera)
+    pu = (xs.reshape(-1)[idx].astype(F) + F(0.5)) / F(W); pv = (ys.reshape(-1)[idx].astype(F) + F(0.5)) / F(H)
+    if inp is not None:
+        velocity = orc.readback(L.OUT_GBUFFER_VELOCITY_UV).reshape(-1, 4)[idx, :2]
+        pu, pv = pu - velocity[:, 0], pv - velocity[:, 1]
+    inside = (np.abs(pu - F(0.5)) < F(0.5)) & (np.abs(pv - F(0.5)) < F(0.5))
+    pcx = np.clip(np.trunc(pu * F(W)).astype(np.int64), 0, W - 1); pcy = np.clip(np.trunc(pv * F(H)).astype(np.int64), 0, H - 1)
+    fetched = previous.reshape(-1)[pcy * W + pcx].copy()
+    fetched[~inside] = np.zeros((), L.PACKED_RESERVOIR)                     # var r: Reservoir — all zero, NOT unpack(zero record)
+    prev = unpack_reservoir(fetched)
+    for k_, v_ in prev.items():                                            # unpack of an absent record would yield lifetime 127 and NaN normals
+        prev[k_] = np.where(inside.reshape((-1,) + (1,) * (v_.ndim - 1)), v_, 0).astype(v_.dtype)
     with np.errstate(all="ignore"):
         ratio = prev["visible_position"][:, 3] / depth
         ratio = np.where(ratio < 1.0, F(1.0) / ratio, ratio)
@@ -165,10 +176,16 @@ def temporal_emissive_numpy(b, orc, frame_number, noise, previous):
     packed["visible_normal"] = pack_snorm8x4(np.concatenate([N, (r["lifetime"] / F(127.0) - F(1.0))[:, None]], 1))
     packed["sample_normal"] = pack_snorm8x4(np.concatenate([r["sample_normal"], r["sample_position"][:, 3:4]], 1))
     # --- output (:1230-1259, no RENDER_EMISSIVE on this pipeline)
-    view = normalize(np.array(list(b.view.world_position), F) - P)
+    eye = np.array(list((inp.view if inp is not None else b.view).world_position), F)
+    view = normalize(eye - P)
     with np.errstate(all="ignore"):
         out = shading(view, N, normalize(r["sample_position"][:, :3] - P), sc.bufs["materials"][material], r["radiance"], sc.ambient)
         out = out * r["w"][:, None]
+    # the invalidation scatter (:1092-1095): a rejected history zeroes the previous-SPATIAL record it was fetched from
+    in_frame = (np.abs(pu - F(0.5)) <= F(0.5)) & (np.abs(pv - F(0.5)) <= F(0.5))
+    scatter_targets = (pcy * W + pcx)[miss & in_frame]
+    temporal_emissive_numpy.scatter_targets = scatter_targets
+    temporal_emissive_numpy.scatter_writers = idx[miss & in_frame]
     return idx, packed, out.astype(F), (variance.astype(F), variance_scale.astype(F)), graze, take, miss
 
 
@@ -220,3 +237,56 @@ def test_oracle_temporal_reuse_equals_independent_numpy_restatement(scene, size)
         rejected += int((miss & clean).sum())
     # both outcomes of the update, the clamp and the rejection of a stale record (instance test) were exercised
     assert replaced > 50 and kept > 50 and clamped > 50 and rejected > 0, (replaced, kept, clamped, rejected)
+
+
+def test_oracle_temporal_reuse_and_invalidation_scatter_under_camera_motion():
+    """translating camera: history is fetched at the re-projected pixel, rejected where depth / normal / instance disagree, and
+    every rejection zeroes the previous-spatial record at the re-projected pixel (light.wgsl:1092-1095, the racy scatter the
+    kernels resolve deterministically) — the buffer the oracle leaves behind must be the buffer before the pass with exactly
+    those records replaced by a packed empty reservoir"""
+    W, H = 80, 64
+    b = Bench("cornell", W, H, taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=1, denoise=0, indirect_bounces=1,
+              emissive_spatial_reuse=0, indirect_spatial_reuse=0)
+    orc = b.oracle()
+    noise = plugin.load_noise()
+    empty = np.zeros((), L.PACKED_RESERVOIR)
+    empty["visible_normal"] = pack_snorm8x4(np.array([[0.0, 0.0, 0.0, -1.0]], F))[0]        # lifetime 0 -> 0 / 127 - 1
+    scattered = rejected = 0
+    for f in range(1, 5):
+        inp = b.moving_inputs(f, step=(0.08, 0.03, -0.05))
+        head = f % 2
+        orc.prepass(inp)
+        orc.run_pass(inp, 0); orc.run_pass(inp, 1)                              # albedo, sun pass (scatters into the same buffer)
+        previous = orc.readback(L.OUT_RESERVOIR_0 + 2 + head).copy()
+        spatial_before = orc.readback(L.OUT_RESERVOIR_0 + 4 + head).reshape(-1).copy()
+        orc.run_pass(inp, 2)                                                    # the emissive pass under test
+        spatial_after = orc.readback(L.OUT_RESERVOIR_0 + 4 + head).reshape(-1).copy()
+        written = orc.readback(L.OUT_RESERVOIR_0 + 2 + 1 - head).reshape(-1)
+        render = orc.readback(L.OUT_RENDER_EMISSIVE).astype(F).reshape(-1, 4)
+        orc.run_pass(inp, 4)                                                    # the rest of the frame's light passes
+        if f == 1:
+            continue
+        idx, packed, out, variance, graze, take, miss = temporal_emissive_numpy(b, orc, f, noise, previous, inp)
+        clean = ~graze
+        w = written[idx]
+        for field in ("radiance", "random", "visible_position", "visible_normal", "sample_normal"):
+            same = (w[field] == packed[field]) if w[field].ndim == 1 else (w[field] == packed[field]).all(-1)
+            assert same[clean].mean() >= 0.99, (f, field, float(same[clean].mean()))
+        gc, _ = unpack_f16x2(w["reservoir"][:, 0]); wc, _ = unpack_f16x2(packed["reservoir"][:, 0])
+        assert (gc[clean] == wc[clean]).mean() >= 0.995
+        d = ulps16(render[idx, :3], out).max(-1)
+        assert (d[clean] <= 1).mean() >= 0.985, (f, float((d[clean] <= 1).mean()))
+        # scatter: covered pixels that rejected their history + background pixels (:1059-1063 write their own record)
+        expected = spatial_before.copy()
+        background = np.setdiff1d(np.arange(W * H), idx)
+        bg = np.zeros((), L.PACKED_RESERVOIR)
+        bg["visible_normal"] = empty["visible_normal"]; bg["reservoir"][0] = pack_f16x2(F(1.0), F(0.0))     # set_reservoir(&r, s, 0.0): count 1
+        # the oracle's rule for the race: writers in raster order, the last one wins (DESIGN.md 2, deviation 2)
+        writes = [(int(wr), int(tg), empty) for wr, tg in zip(temporal_emissive_numpy.scatter_writers, temporal_emissive_numpy.scatter_targets)]
+        writes += [(int(px), int(px), bg) for px in background]
+        for _, tg, value in sorted(writes, key=lambda t: t[0]):
+            expected[tg] = value
+        same = (expected.view(np.uint8).reshape(-1, 64) == spatial_after.view(np.uint8).reshape(-1, 64)).all(1)
+        assert same.mean() >= 0.998, (f, float(same.mean()))
+        scattered += len(temporal_emissive_numpy.scatter_targets); rejected += int(miss.sum())
+    assert scattered > 200 and rejected >= scattered
