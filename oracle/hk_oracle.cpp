@@ -7,6 +7,10 @@
 //
 // PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path and
 // cannot be built here (no rustc / wgpu / Vulkan), so this restatement is anchored on the WGSL source alone.
+// What stands in for a pin: every pass below is held against a SECOND restatement written independently from the WGSL
+// (whole-image numpy programs with brute-force float64 ray queries, tests/test_*_numpy.py; agreement table in DESIGN.md 2),
+// plus physical anchors (tests/test_estimator.py) — evidence that this file reads the WGSL the way a second reader does,
+// not evidence about what a wgpu driver computes.
 // Deviations that are forced and documented:
 //   * the G-buffer is ray-cast (hko_prepass) instead of rasterised (prepass.wgsl:40-100) — same five planes, same
 //     formats, oracle-defined coverage;
