@@ -90,15 +90,20 @@ def test_frame_target_across_processes_cuda_ipc():
     frame, handle = full.frame_alloc()
     ctx = mp.get_context("spawn")
     parent, child = ctx.Pipe()
-    p = ctx.Process(target=_ipc_worker, args=(handle, TILES[1], 3, child))
+    p = ctx.Process(target=_ipc_worker, args=(handle, TILES[1], 3, child), daemon=True)
     p.start()
-    for f in range(1, 4):
-        inp = b.inputs(f)
-        full.render_frame(inp)
-        local.set_frame_target(frame, W)
-        local.render_frame(inp)
-    local.sync()
-    assert parent.poll(180), "worker did not answer"
-    assert parent.recv() == "ok"
-    p.join(30)
+    try:
+        for f in range(1, 4):
+            inp = b.inputs(f)
+            full.render_frame(inp)
+            local.set_frame_target(frame, W)
+            local.render_frame(inp)
+        local.sync()
+        assert parent.poll(180), "worker did not answer"
+        assert parent.recv() == "ok"
+        p.join(30)
+    finally:                          # the worker never outlives the test, whatever failed
+        if p.is_alive():
+            p.terminate()
+        p.join(10)
     assert mismatch(full.frame_read(frame), full.readback(L.OUT_TONE_MAPPED)) == 0

@@ -110,8 +110,12 @@ def _halo_worker(rect, frames, conn):
         b = Bench("cornell", 144, 96, config="cornell_1080p")
         full, tile = b.device(), b.device(rect[2], rect[3], rect[0], rect[1])
         tile.set_motion_margin(12)
+        def recv():                       # never block for ever: a parent that failed must not leave this process behind
+            if not conn.poll(180):
+                raise TimeoutError("parent went silent")
+            return conn.recv()
         conn.send(tile.halo_export())
-        peer = tile.halo_import(conn.recv())
+        peer = tile.halo_import(recv())
         bad = 0
         for f in range(1, frames + 1):
             inp = b.moving_inputs(f, step=(0.04, 0.01, -0.02))
@@ -120,13 +124,16 @@ def _halo_worker(rect, frames, conn):
             tile.sync()
             for k in PLANES:
                 bad += mismatch(tile.readback(k), full.readback(k)[rect[2]:rect[3], rect[0]:rect[1]])
-            conn.send("rendered"); assert conn.recv() == "rendered"      # both tiles have finished frame f
+            conn.send("rendered"); assert recv() == "rendered"           # both tiles have finished frame f
             tile.halo_pull_peer(peer)
             tile.sync()
-            conn.send("pulled"); assert conn.recv() == "pulled"          # nobody starts frame f + 1 before both pulls are done
+            conn.send("pulled"); assert recv() == "pulled"               # nobody starts frame f + 1 before both pulls are done
         conn.send(("done", bad))
     except Exception as e:   # pragma: no cover
-        conn.send(("error", repr(e)))
+        try:
+            conn.send(("error", repr(e)))
+        except Exception:
+            pass
 
 
 def test_halo_exchange_between_two_processes_cuda_ipc():
@@ -140,8 +147,17 @@ def test_halo_exchange_between_two_processes_cuda_ipc():
     frames = 6
     ctx = mp.get_context("spawn")
     parent, child = ctx.Pipe()
-    p = ctx.Process(target=_halo_worker, args=(rects[1], frames, child))
+    p = ctx.Process(target=_halo_worker, args=(rects[1], frames, child), daemon=True)   # daemon: never waited for at interpreter exit
     p.start()
+    try:
+        _halo_parent(parent, p, rects, frames)
+    finally:                              # whatever happened above, the worker does not outlive the test
+        if p.is_alive():
+            p.terminate()
+        p.join(10)
+
+
+def _halo_parent(parent, p, rects, frames):
     b = Bench("cornell", 144, 96, config="cornell_1080p")
     full, tile = b.device(), b.device(rects[0][2], rects[0][3], rects[0][0], rects[0][1])
     tile.set_motion_margin(12)
