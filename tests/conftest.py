@@ -23,6 +23,16 @@ def pytest_configure(config):
         _ffi.LIB_PATH = build_emu.build()
 
 
+def pytest_collection_modifyitems(config, items):
+    """A hung kernel or a dead-locked peer must fail ONE test, not take the whole GPU tier (and the box) with it: every `gpu`
+    test gets a wall-clock limit when pytest-timeout is installed (it is in this image)."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(900))
+
+
 def needs_real_gpu():
     """for the few tests that exercise the CUDA runtime itself (pinned memory, IPC) rather than kernel logic"""
     if EMULATED:
