@@ -5,6 +5,14 @@
 #include "hk_device.cuh"
 #include "hk_kernels.h"
 
+// NO_TEXTURE specialisation (light.rs:141-143: the reference compiles its light shaders with NO_TEXTURE when the scene has no
+// texture at all, light.wgsl:729-747 vs :749-793).  TEX = false instantiations see texture_count == 0 as a compile-time constant,
+// so the bilinear sampler, the wrap modes and the four texture look-ups per retreive_surface are not in the kernel at all; the
+// launchers pick them when the uploaded scene has no textures (cornell).  Values are identical by construction — the same
+// `if (sc.texture_count != 0u)` decides, at compile time instead of at run time.  -DHK_NO_TEXTURE_VARIANT=0 keeps one variant.
+#ifndef HK_NO_TEXTURE_VARIANT
+#define HK_NO_TEXTURE_VARIANT 1
+#endif
 #ifndef HK_SPATIAL_EAGER_LOAD
 #define HK_SPATIAL_EAGER_LOAD 0
 #endif
@@ -54,7 +62,14 @@ __device__ __forceinline__ Ray primary_ray(const KParams& P, const mat4& inv_vie
     return ray;
 }
 
-template <bool COUNT>
+template <bool TEX>
+__device__ __forceinline__ DeviceScene scene_variant(const DeviceScene& scene) {
+    DeviceScene sc = scene;
+    if (!TEX) sc.texture_count = 0u;     // constant-folds every `sc.texture_count != 0u` below it
+    return sc;
+}
+
+template <bool COUNT, bool TEX = true>
 __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__ KParams P) {
     int x, y;
     tile_pixel(x, y, P);
@@ -83,7 +98,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__
             P.planes.velocity_uv[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             P.planes.albedo[idx] = make_uint2(0u, 0u);
         } else {
-            const DeviceScene& sc = P.scene;
+            const DeviceScene sc = scene_variant<TEX>(P.scene);
             const hk_instance* inst = sc.instances + hit.instance_index;
             const hk_primitive* prim = sc.primitives + hit.primitive_index;
             uint32_t vbase = __ldg(&inst->mesh.vertex);
@@ -207,7 +222,7 @@ __device__ __forceinline__ size_t light_gbuffer_index(const KParams& P, int x, i
 
 // --------------------------------------------------------------------------------------- P2: direct_lit
 // light.wgsl:1044-1261.  EMISSIVE_LIT=false is the sun pass (+RENDER_EMISSIVE), true is the emissive pass.
-template <bool EMISSIVE_LIT, bool COUNT>
+template <bool EMISSIVE_LIT, bool COUNT, bool TEX = true>
 __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __grid_constant__ KParams P) {
     constexpr int SIGNAL = EMISSIVE_LIT ? 1 : 0;
     constexpr bool RENDER_EMISSIVE = !EMISSIVE_LIT;
@@ -216,7 +231,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
     const bool active = tile_active(P, x, y);
     uint32_t n_tlas = 0, n_blas = 0;
     if (active) {
-        const DeviceScene& sc = P.scene;
+        const DeviceScene sc = scene_variant<TEX>(P.scene);
         const hk_frame_uniform& frame = P.in.frame;
         const size_t idx = render_index(P.band, x, y);
         const size_t gidx = light_gbuffer_index(P, x, y, idx);
@@ -343,14 +358,14 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
 // ----------------------------------------------------------------------------- P3: indirect_lit_ambient
 // light.wgsl:1263-1498.  One kernel covers both the single-bounce and the MULTIPLE_BOUNCES variants: the reference's
 // single-bounce body is the loop body for n == 0 without the luminance clamp, so MULTI only switches those two bits.
-template <bool MULTI, bool COUNT>
+template <bool MULTI, bool COUNT, bool TEX = true>
 __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(const __grid_constant__ KParams P) {
     int x, y;
     tile_pixel(x, y, P);
     const bool active = tile_active(P, x, y);
     uint32_t n_tlas = 0, n_blas = 0;
     if (active) {
-        const DeviceScene& sc = P.scene;
+        const DeviceScene sc = scene_variant<TEX>(P.scene);
         const hk_frame_uniform& frame = P.in.frame;
         const size_t idx = render_index(P.band, x, y);
         const size_t gidx = light_gbuffer_index(P, x, y, idx);
@@ -475,7 +490,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
 // ----------------------------------------------------------------------------------- P4: spatial_reuse
 // light.wgsl:1500-1684.  The reference's 8x8 workgroup cache holds unpack(reservoir_buffer[..]) of this dispatch's
 // read-only input, so gathering neighbours straight from the planes (L1/L2-resident) is value-identical.
-template <bool EMISSIVE_LIT>
+template <bool EMISSIVE_LIT, bool TEX = true>
 __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const __grid_constant__ KParams P) {
     constexpr int SIGNAL = EMISSIVE_LIT ? 1 : 2;
     constexpr uint32_t SPATIAL_REUSE_COUNT = EMISSIVE_LIT ? 8u : 16u;   // light.wgsl:246-252
@@ -484,7 +499,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
     int x, y;
     tile_pixel(x, y, P);
     if (!tile_active(P, x, y)) return;
-    const DeviceScene& sc = P.scene;
+    const DeviceScene sc = scene_variant<TEX>(P.scene);
     const hk_frame_uniform& frame = P.in.frame;
     const size_t idx = render_index(P.band, x, y);
     const size_t gidx = light_gbuffer_index(P, x, y, idx);
@@ -664,9 +679,12 @@ static dim3 grid_for(const KParams& P) {
 
 using namespace hkd;
 
+static inline bool no_texture(const KParams& P) { return HK_NO_TEXTURE_VARIANT && P.scene.texture_count == 0u; }
+
 void hk_launch_gbuffer(const KParams& P, bool count, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     if (count) k_gbuffer<true><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+    else if (no_texture(P)) k_gbuffer<false, false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
     else k_gbuffer<false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }
 void hk_launch_albedo(const KParams& P, cudaStream_t st) {
@@ -676,17 +694,32 @@ void hk_launch_albedo(const KParams& P, cudaStream_t st) {
 void hk_launch_direct(const KParams& P, bool emissive, bool count, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     dim3 g = grid_for(P);
+    if (!count && no_texture(P)) {       // the timed variants of an untextured scene
+        if (emissive) k_direct<true, false, false><<<g, CTA_THREADS, 0, st>>>(P);
+        else k_direct<false, false, false><<<g, CTA_THREADS, 0, st>>>(P);
+        return;
+    }
     if (emissive) { if (count) k_direct<true, true><<<g, CTA_THREADS, 0, st>>>(P); else k_direct<true, false><<<g, CTA_THREADS, 0, st>>>(P); }
     else { if (count) k_direct<false, true><<<g, CTA_THREADS, 0, st>>>(P); else k_direct<false, false><<<g, CTA_THREADS, 0, st>>>(P); }
 }
 void hk_launch_indirect(const KParams& P, bool multi, bool count, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     dim3 g = grid_for(P);
+    if (!count && no_texture(P)) {
+        if (multi) k_indirect<true, false, false><<<g, CTA_THREADS, 0, st>>>(P);
+        else k_indirect<false, false, false><<<g, CTA_THREADS, 0, st>>>(P);
+        return;
+    }
     if (multi) { if (count) k_indirect<true, true><<<g, CTA_THREADS, 0, st>>>(P); else k_indirect<true, false><<<g, CTA_THREADS, 0, st>>>(P); }
     else { if (count) k_indirect<false, true><<<g, CTA_THREADS, 0, st>>>(P); else k_indirect<false, false><<<g, CTA_THREADS, 0, st>>>(P); }
 }
 void hk_launch_spatial(const KParams& P, bool emissive, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+    if (no_texture(P)) {
+        if (emissive) k_spatial<true, false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+        else k_spatial<false, false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+        return;
+    }
     if (emissive) k_spatial<true><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
     else k_spatial<false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }
