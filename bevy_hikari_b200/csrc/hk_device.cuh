@@ -522,6 +522,9 @@ __device__ __forceinline__ vec3 compute_emissive_radiance(vec4 emissive) { retur
 // Texture fetch for the textured variant (light.wgsl:756): manual bilinear on pre-decoded float4 texels so that the
 // weights are fp32 like the oracle's (CUDA texture units filter with 9-bit weights).
 __device__ __forceinline__ int wrap_coord(int i, int n, uint32_t mode) {
+    // texel coordinates of uv in [0, 1) are already inside the texture: every addressing mode is the identity there, and the
+    // integer modulo by a run-time size (an emulated division on the GPU) is only needed for coordinates that really wrap
+    if ((unsigned)i < (unsigned)n) return i;
     if (mode == 0u) { i %= n; if (i < 0) i += n; return i; }
     if (mode == 1u) return min(max(i, 0), n - 1);
     int period = 2 * n; i %= period; if (i < 0) i += period;
