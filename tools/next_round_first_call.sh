@@ -4,6 +4,7 @@
 # tuning variants.  Before calling (on the CPU box, nvcc cross-compiles):
 #     python tools/build_variants.py denoise='-DHK_DENOISE_BRANCHFREE=1' spatial='-DHK_SPATIAL_EAGER_LOAD=1' \
 #            fastdiv='-DHK_SPATIAL_FAST_DIV=1' all='-DHK_DENOISE_BRANCHFREE=1 -DHK_SPATIAL_EAGER_LOAD=1 -DHK_SPATIAL_FAST_DIV=1' \
+#            surface_loop='-DHK_SURFACE_LOOP=1'   (textured scenes only: time it with --config city_4k / scene_1080p) \
 #            generic_texture_path='-DHK_NO_TEXTURE_VARIANT=0'      (the round-1 kernels: the default now picks NO_TEXTURE variants for cornell)
 #     gpurun --timeout 1200 -- tools/next_round_first_call.sh
 mkdir -p gpurun_out
