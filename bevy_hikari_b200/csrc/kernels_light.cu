@@ -13,6 +13,9 @@
 #ifndef HK_NO_TEXTURE_VARIANT
 #define HK_NO_TEXTURE_VARIANT 1
 #endif
+#ifndef HK_NOVAL_VARIANT
+#define HK_NOVAL_VARIANT 1          // 0: k_direct always uses the instantiation that tests for a validation frame at run time
+#endif
 #ifndef HK_SPATIAL_EAGER_LOAD
 #define HK_SPATIAL_EAGER_LOAD 0
 #endif
@@ -222,7 +225,11 @@ __device__ __forceinline__ size_t light_gbuffer_index(const KParams& P, int x, i
 
 // --------------------------------------------------------------------------------------- P2: direct_lit
 // light.wgsl:1044-1261.  EMISSIVE_LIT=false is the sun pass (+RENDER_EMISSIVE), true is the emissive pass.
-template <bool EMISSIVE_LIT, bool COUNT, bool TEX = true>
+// NOVAL = true: instantiation for the frames that are NOT validation frames (frame.number % validate_interval != 0, a launch-wide
+// fact the launcher knows): the whole validation block — a second select_light_candidate with its own emissive-BVH walk and BLAS
+// traversal, a second TLAS traversal, the reset logic — is not in the kernel (2 of 3 sun frames, 4 of 5 emissive frames at the
+// default intervals).  The generic instantiation decides the same thing at run time; values are identical.
+template <bool EMISSIVE_LIT, bool COUNT, bool TEX = true, bool NOVAL = false>
 __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __grid_constant__ KParams P) {
     constexpr int SIGNAL = EMISSIVE_LIT ? 1 : 0;
     constexpr bool RENDER_EMISSIVE = !EMISSIVE_LIT;
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
 
             const uint32_t validate_interval = EMISSIVE_LIT ? frame.emissive_validate_interval : frame.direct_validate_interval;
             const uint32_t select_light_instance = EMISSIVE_LIT ? instance_id : DONT_SAMPLE_EMISSIVE;
-            const bool validation_frame = (frame.number % validate_interval) == 0u;
+            const bool validation_frame = NOVAL ? false : (frame.number % validate_interval) == 0u;
 
             if (!validation_frame || r.count < 4.0f) {
                 LightCandidate cand = select_light_candidate<COUNT>(sc, env, s.random, position, normal, select_light_instance, info, n_blas);
@@ -694,6 +701,18 @@ void hk_launch_albedo(const KParams& P, cudaStream_t st) {
 void hk_launch_direct(const KParams& P, bool emissive, bool count, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     dim3 g = grid_for(P);
+    const uint32_t interval = emissive ? P.in.frame.emissive_validate_interval : P.in.frame.direct_validate_interval;
+    const bool noval = HK_NOVAL_VARIANT && !count && (P.in.frame.number % interval) != 0u;
+    if (noval) {                         // not a validation frame: the lean instantiation
+        if (no_texture(P)) {
+            if (emissive) k_direct<true, false, false, true><<<g, CTA_THREADS, 0, st>>>(P);
+            else k_direct<false, false, false, true><<<g, CTA_THREADS, 0, st>>>(P);
+        } else {
+            if (emissive) k_direct<true, false, true, true><<<g, CTA_THREADS, 0, st>>>(P);
+            else k_direct<false, false, true, true><<<g, CTA_THREADS, 0, st>>>(P);
+        }
+        return;
+    }
     if (!count && no_texture(P)) {       // the timed variants of an untextured scene
         if (emissive) k_direct<true, false, false><<<g, CTA_THREADS, 0, st>>>(P);
         else k_direct<false, false, false><<<g, CTA_THREADS, 0, st>>>(P);

@@ -5,6 +5,7 @@
 #     python tools/build_variants.py denoise='-DHK_DENOISE_BRANCHFREE=1' spatial='-DHK_SPATIAL_EAGER_LOAD=1' \
 #            fastdiv='-DHK_SPATIAL_FAST_DIV=1' all='-DHK_DENOISE_BRANCHFREE=1 -DHK_SPATIAL_EAGER_LOAD=1 -DHK_SPATIAL_FAST_DIV=1' \
 #            surface_loop='-DHK_SURFACE_LOOP=1'   (textured scenes only: time it with --config city_4k / scene_1080p) \
+#            generic_direct='-DHK_NOVAL_VARIANT=0' \
 #            generic_texture_path='-DHK_NO_TEXTURE_VARIANT=0'      (the round-1 kernels: the default now picks NO_TEXTURE variants for cornell)
 #     gpurun --timeout 1200 -- tools/next_round_first_call.sh
 mkdir -p gpurun_out
