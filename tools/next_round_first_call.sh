@@ -10,8 +10,8 @@
 #     gpurun --timeout 1200 -- tools/next_round_first_call.sh
 mkdir -p gpurun_out
 echo "== device suite, newest tests first"
-python -m pytest tests/test_gpu_zz_fsr.py tests/test_gpu_zz_examples.py tests/test_gpu_zz_halo.py -m gpu -q 2>&1 | tail -6
-python -m pytest tests -m gpu -q --deselect tests/test_gpu_zz_fsr.py --deselect tests/test_gpu_zz_examples.py --deselect tests/test_gpu_zz_halo.py 2>&1 | tail -4
+python -m pytest tests/test_gpu_zz_*.py -m gpu -q 2>&1 | tail -8
+python -m pytest tests -m gpu -q $(for f in tests/test_gpu_zz_*.py; do echo --deselect $f; done) 2>&1 | tail -4
 echo "== tuning variants (per-kernel ms; make a variant the default if its kernels drop)"
 python bench.py --steps 16 --warmup 4 --no-cpu-baseline 2>/dev/null | grep "^{" | python -c "
 import sys, json
