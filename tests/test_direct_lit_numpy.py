@@ -97,6 +97,18 @@ def direct_sun_numpy(b, orc, frame_number, noise):
     pos = orc.readback(L.OUT_GBUFFER_POSITION)
     normal = np.maximum(orc.readback(L.OUT_GBUFFER_NORMAL).astype(F) / F(127.0), F(-1.0))[..., :3]
     im = orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)
+    ratio = F(b.settings.upscale_ratio)
+    if ratio != 1.0:
+        # render below the output resolution (light.rs:622-624): the pass runs over ceil(size / ratio) pixels and reads the
+        # full-size G-buffer at jittered_deferred_coords(uv) = i32((uv -+ 0.25 texel * (ratio - 1)) * size)  (:1007-1017)
+        DH, DW = pos.shape[:2]
+        H, W = int(np.ceil(F(1.0) / ratio * F(DH))), int(np.ceil(F(1.0) / ratio * F(DW)))
+        ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+        sel = F(-0.25) if (frame_number & 1) == 0 else F(0.25)
+        du = (xs.astype(F) + F(0.5)) / F(W) + sel * (F(1.0) / F(DW)) * (ratio - F(1.0))
+        dv = (ys.astype(F) + F(0.5)) / F(H) + sel * (F(1.0) / F(DH)) * (ratio - F(1.0))
+        dx, dy = np.trunc(du * F(DW)).astype(np.int64), np.trunc(dv * F(DH)).astype(np.int64)
+        pos, normal, im = pos[dy, dx], normal[dy, dx], im[dy, dx]
     H, W = pos.shape[:2]
     ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     position, depth = pos[..., :3], pos[..., 3]
@@ -156,10 +168,11 @@ def ulps16(a, b):
     return np.abs(ia - ib)
 
 
-@pytest.mark.parametrize("scene,size,frames", [("minimal", (96, 64), (1, 2, 4)), ("simple", (112, 64), (1, 5))])
-def test_oracle_direct_sun_equals_independent_numpy_restatement(scene, size, frames):
+@pytest.mark.parametrize("scene,size,frames,ratio", [("minimal", (96, 64), (1, 2, 4), 1.0), ("simple", (112, 64), (1, 5), 1.0),
+                                                     ("minimal", (120, 80), (1, 2), 1.5), ("minimal", (120, 80), (2,), 2.0)])
+def test_oracle_direct_sun_equals_independent_numpy_restatement(scene, size, frames, ratio):
     # temporal_reuse = 0: the reservoir is never stored (:1226-1228), so every frame starts from an empty history
-    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=0, denoise=0, indirect_bounces=1)
+    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=ratio, temporal_reuse=0, denoise=0, indirect_bounces=1)
     orc = b.oracle()
     noise = plugin.load_noise()
     for f in range(1, max(frames) + 1):
