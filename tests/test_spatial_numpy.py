@@ -67,15 +67,25 @@ def compute_jacobian(q, s_visible_position):             # :985-1004, r = the ow
 
 
 def spatial_numpy(b, orc, frame_number, emissive, temporal, previous_spatial):
-    pos = orc.readback(L.OUT_GBUFFER_POSITION)
-    im = orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)
-    H, W = pos.shape[:2]
+    pos_full = orc.readback(L.OUT_GBUFFER_POSITION)
+    im_full = orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)
+    DH, DW = pos_full.shape[:2]
+    H, W = temporal.shape[:2]                              # render size = ceil(size / ratio) (light.rs:622-624)
+    ratio = F(b.settings.upscale_ratio)
+    sel = F(-0.25) if (frame_number & 1) == 0 else F(0.25)
+
+    def deferred(u_, v_):
+        """jittered_deferred_coords (:1007-1017): i32((uv -+ 0.25 texel * (ratio - 1)) * size); identity at ratio 1"""
+        du = u_ + sel * (F(1.0) / F(DW)) * (ratio - F(1.0)); dv = v_ + sel * (F(1.0) / F(DH)) * (ratio - F(1.0))
+        return np.trunc(du * F(DW)).astype(np.int64), np.trunc(dv * F(DH)).astype(np.int64)
     n = H * W
     ys, xs = [a.reshape(-1) for a in np.meshgrid(np.arange(H), np.arange(W), indexing="ij")]
-    depth_img = pos[..., 3]
-    depth = depth_img.reshape(-1)
-    position = pos[..., :3].reshape(-1, 3)
-    mats = b.world.buffers()["materials"][np.floor(im[..., 1]).astype(np.int64).reshape(-1)]
+    u = (xs.astype(F) + F(0.5)) / F(W); v = (ys.astype(F) + F(0.5)) / F(H)
+    gx, gy = deferred(u, v)
+    depth_img = pos_full[..., 3]
+    depth = depth_img[gy, gx]
+    position = pos_full[gy, gx, :3]
+    mats = b.world.buffers()["materials"][np.floor(im_full[gy, gx, 1]).astype(np.int64)]
     ambient = np.array(list(b.lights.ambient_color), F)[:3]
     own = unpack_reservoir(temporal.reshape(-1))
     covered = depth >= F(1.1920929e-7)
@@ -95,7 +105,6 @@ def spatial_numpy(b, orc, frame_number, emissive, temporal, previous_spatial):
     count_n, reach = (8, F(10.0)) if emissive else (16, F(20.0))
     rotation = s["random"][:, 0] + s["random"][:, 1] + s["random"][:, 2] + s["random"][:, 3]
     frame_random = F(hash_u32(frame_number)) / F(4294967295.0)
-    u = (xs.astype(F) + F(0.5)) / F(W); v = (ys.astype(F) + F(0.5)) / F(H)
     stats = dict(merged=0, depth=0, normal=0, back=0, occluded=0, outside=0)
     for i in range(1, count_n + 1):
         angle = TAU * fract(F(i) * GOLDEN_RATIO + rotation + frame_random)
@@ -107,11 +116,12 @@ def spatial_numpy(b, orc, frame_number, emissive, temporal, previous_spatial):
         stats["outside"] += int((covered & ~ok).sum())
         cx, cy = np.clip(sx, 0, W - 1), np.clip(sy, 0, H - 1)
         sidx = cy * W + cx
-        sample_depth = depth[sidx]
+        sgx, sgy = deferred(su, sv)                                             # sample_deferred_coords (:1576)
+        sample_depth = depth_img[np.clip(sgy, 0, DH - 1), np.clip(sgx, 0, DW - 1)]
         q = {k: own[k][sidx] for k in own}
         with np.errstate(all="ignore"):
-            ratio = depth / sample_depth
-            passed = ok & ~((ratio < F(0.9)) | (ratio > F(1.1)))
+            depth_ratio = depth / sample_depth
+            passed = ok & ~((depth_ratio < F(0.9)) | (depth_ratio > F(1.1)))
             stats["depth"] += int((ok & ~passed).sum()); ok = passed
             passed = ok & ~((q["count"] < F(1.1920929e-7)) | (dot(s["visible_normal"], q["visible_normal"]) < F(0.866)))
             stats["normal"] += int((ok & ~passed).sum()); ok = passed
@@ -127,9 +137,9 @@ def spatial_numpy(b, orc, frame_number, emissive, temporal, previous_spatial):
             for j in range(1, taps + 1):
                 dist = F(j) * interval
                 tu, tv = u + (dist * ux) / F(W), v + (dist * uy) / F(H)
-                tx, ty = np.trunc(tu * F(W)).astype(np.int64), np.trunc(tv * F(H)).astype(np.int64)
-                inside = (tx >= 0) & (tx < W) & (ty >= 0) & (ty < H)
-                tap_depth = np.where(inside, depth_img[np.clip(ty, 0, H - 1), np.clip(tx, 0, W - 1)], F(0.0))
+                tx, ty = deferred(tu, tv)                                       # tap_deferred_coords (:1617); textureLoad outside = 0
+                inside = (tx >= 0) & (tx < DW) & (ty >= 0) & (ty < DH)
+                tap_depth = np.where(inside, depth_img[np.clip(ty, 0, DH - 1), np.clip(tx, 0, DW - 1)], F(0.0))
                 t = F(j) / F(taps + 1)
                 ref = depth * (F(1.0) - t) + sample_depth * t
                 occluded |= ~occluded & (tap_depth > ref + F(0.00001))
@@ -174,9 +184,10 @@ def spatial_numpy(b, orc, frame_number, emissive, temporal, previous_spatial):
     return packed, render.astype(F), variance.astype(F), use_variance & covered, covered, stats
 
 
-@pytest.mark.parametrize("scene,size,emissive", [("cornell", (72, 72), False), ("cornell", (72, 72), True), ("minimal", (80, 56), False)])
-def test_oracle_spatial_reuse_equals_independent_numpy_restatement(scene, size, emissive):
-    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=1, denoise=0, indirect_bounces=2,
+@pytest.mark.parametrize("scene,size,emissive,ratio", [("cornell", (72, 72), False, 1.0), ("cornell", (72, 72), True, 1.0), ("minimal", (80, 56), False, 1.0),
+                                                       ("cornell", (120, 100), False, 1.5), ("cornell", (128, 96), True, 2.0)])
+def test_oracle_spatial_reuse_equals_independent_numpy_restatement(scene, size, emissive, ratio):
+    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=ratio, temporal_reuse=1, denoise=0, indirect_bounces=2,
               emissive_spatial_reuse=1, indirect_spatial_reuse=1, max_spatial_reuse_count=40)
     orc = b.oracle()
     t_base, s_base, signal, spatial_pass = (2, 4, 1, 3) if emissive else (6, 8, 2, 5)
@@ -212,6 +223,6 @@ def test_oracle_spatial_reuse_equals_independent_numpy_restatement(scene, size, 
     # every branch of the neighbour loop was taken many times
     print(scene, emissive, totals)
     if scene == "cornell":
-        assert totals["merged"] > 5000 and all(totals[k] > 20 for k in ("depth", "normal", "occluded", "outside")), totals
+        assert totals["merged"] > 3000 and all(totals[k] > 20 for k in ("depth", "normal", "occluded", "outside")), totals
     else:       # a receding ground plane: most neighbours fail the depth-ratio test
         assert totals["merged"] > 500 and totals["depth"] > 5000, totals
