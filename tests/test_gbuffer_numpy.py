@@ -128,3 +128,89 @@ def test_oracle_gbuffer_equals_independent_numpy_computation(scene, size):
     d = ulps16(albedo[sel, :3], want_albedo).max(-1)
     assert len(sel) > 500 and (d == 0).mean() >= 0.99 and d.max() <= 1, (len(sel), float((d == 0).mean()), int(d.max()))
     assert (albedo[sel, 3] == 1).all() and not albedo[pos[:, 3] < F(1.1920929e-7)].any()
+
+
+# ------------------------------------------------------------------------------------------- textured surfaces
+def decode_texture(t):
+    """RGBA8 -> float32 texels: sRGB transfer on rgb when the image is an sRGB one (base colour / emissive slots), alpha linear"""
+    a = t["rgba"].astype(np.float64) / 255.0
+    if t["srgb"]:
+        rgb = a[..., :3]
+        a[..., :3] = np.where(rgb <= 0.04045, rgb / 12.92, ((rgb + 0.055) / 1.055) ** 2.4)
+    return a.astype(F)
+
+
+def wrap(i, n, mode):                                    # address modes: 0 repeat, 1 clamp-to-edge, 2 mirror-repeat
+    if mode == 0:
+        return np.mod(i, n)
+    if mode == 1:
+        return np.clip(i, 0, n - 1)
+    j = np.mod(i, 2 * n)
+    return np.where(j < n, j, 2 * n - 1 - j)
+
+
+def sample(t, texels, u, v):
+    """textureSampleLevel(textures[id], samplers[id], uv, 0.0) with fp32 bilinear weights (deviation 4)"""
+    h, w = texels.shape[:2]
+    mu, mv = t["address_mode_u"], t["address_mode_v"]
+    if not t["filter_linear"]:
+        return texels[wrap(np.floor(v * F(h)).astype(np.int64), h, mv), wrap(np.floor(u * F(w)).astype(np.int64), w, mu)]
+    fx, fy = u * F(w) - F(0.5), v * F(h) - F(0.5)
+    x0, y0 = np.floor(fx), np.floor(fy)
+    ax, ay = (fx - x0)[:, None], (fy - y0)[:, None]
+    x0, y0 = x0.astype(np.int64), y0.astype(np.int64)
+    xa, xb, ya, yb = wrap(x0, w, mu), wrap(x0 + 1, w, mu), wrap(y0, h, mv), wrap(y0 + 1, h, mv)
+    top = texels[ya, xa] * (F(1) - ax) + texels[ya, xb] * ax
+    bot = texels[yb, xa] * (F(1) - ax) + texels[yb, xb] * ax
+    return top * (F(1) - ay) + bot * ay
+
+
+@pytest.mark.parametrize("scene,size", [("samplers", (128, 80)), ("city", (128, 72))])
+def test_oracle_textured_surfaces_equal_independent_numpy_sampler(scene, size):
+    """retreive_surface with textures (light.wgsl:749-781) through `full_screen_albedo`: every sampler state the texture path
+    distinguishes (repeat / clamp / mirror on either axis, nearest and linear, sRGB and linear data, uvs from -1 to 2) in
+    scenes.samplers, and the glTF textures of the city houses"""
+    W, H = size
+    b = Bench(scene, W, H, taa=plugin.TAA_NONE, upscale_ratio=1.0, denoise=0, indirect_bounces=1)
+    orc = b.oracle()
+    inp = b.inputs(1)
+    orc.prepass(inp)
+    orc.run_pass(inp, 0)
+    pos = orc.readback(L.OUT_GBUFFER_POSITION).reshape(-1, 4)
+    nrm = orc.readback(L.OUT_GBUFFER_NORMAL).reshape(-1, 4)
+    im = orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL).reshape(-1, 2)
+    vu = orc.readback(L.OUT_GBUFFER_VELOCITY_UV).reshape(-1, 4)
+    albedo = orc.readback(L.OUT_ALBEDO).astype(F).reshape(-1, 4)
+    sel = np.nonzero(pos[:, 3] >= F(1.1920929e-7))[0]
+    mats = b.world.buffers()["materials"][np.floor(im[sel, 1]).astype(np.int64)]
+    textures = [dict(t, texels=decode_texture(t)) for t in b.scene.textures]
+    u, v = vu[sel, 2], vu[sel, 3]
+    base = mats["base_color"].copy()
+    metallic = mats["metallic"].copy()
+    occlusion = np.ones(len(sel), F)
+    used = set()
+    for slot, apply in (("base_color_texture", "base"), ("metallic_roughness_texture", "metallic"), ("occlusion_texture", "occlusion")):
+        ids = mats[slot]
+        for tid in np.unique(ids[ids != 0xFFFFFFFF]):
+            m = ids == tid
+            t = textures[int(tid)]
+            s = sample(t, t["texels"], u[m], v[m])
+            used.add((t["address_mode_u"], t["address_mode_v"], t["filter_linear"], t["srgb"]))
+            if apply == "base":
+                base[m] = base[m] * s
+            elif apply == "metallic":
+                metallic[m] = metallic[m] * s[:, 0]
+            else:
+                occlusion[m] = s[:, 0]
+    Vd = normalize(np.array(list(inp.view.world_position), F) - pos[sel, :3])
+    Nn = np.maximum(nrm[sel].astype(F) / F(127.0), F(-1.0))[:, :3]
+    reflectance = mats["reflectance"][:, None]
+    rough = np.clip(mats["perceptual_roughness"], F(0.089), F(1.0)); rough = rough * rough
+    F0 = F(0.16) * reflectance * reflectance * (F(1.0) - metallic[:, None]) + base[:, :3] * metallic[:, None]
+    NoV = np.fmax(dot(Nn, Vd), F(0.0001))
+    want = (env_brdf_approx(base[:, :3] * (F(1.0) - metallic[:, None]), np.ones_like(rough), NoV) + env_brdf_approx(F0, rough, NoV)) * occlusion[:, None]
+    d = ulps16(albedo[sel, :3], want).max(-1)
+    textured = mats["base_color_texture"] != 0xFFFFFFFF
+    assert textured.sum() > 500 and (d[textured] == 0).mean() >= 0.99 and d.max() <= 1, (int(textured.sum()), float((d[textured] == 0).mean()), int(d.max()))
+    if scene == "samplers":     # all three address modes, both filters, both encodings were sampled
+        assert {m for mu, mv, _, _ in used for m in (mu, mv)} == {0, 1, 2} and {f for _, _, f, _ in used} == {0, 1} and {s for *_, s in used} == {0, 1}, used
