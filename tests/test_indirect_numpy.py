@@ -50,7 +50,7 @@ def env_brdf_approx(f0, perceptual_roughness, NoV):       # bevy_pbr EnvBRDFAppr
     return f0 * A[..., None] + B[..., None]
 
 
-def shading(V, N, Lv, mat, radiance4, ambient_color, roughness_override=None):
+def shading(V, N, Lv, mat, radiance4, ambient_color, roughness_override=None, occlusion=None):
     """light.wgsl shading(): mix(lit, ambient, 1 - alpha).  `mat` = MATERIAL records (NO_TEXTURE form of retreive_surface)."""
     rough = np.clip(mat["perceptual_roughness"], F(0.089), F(1.0))
     rough = rough * rough
@@ -62,7 +62,10 @@ def shading(V, N, Lv, mat, radiance4, ambient_color, roughness_override=None):
     F0 = F(0.16) * reflectance * reflectance * (F(1.0) - metallic) + base * metallic
     diffuse_color = base * (F(1.0) - metallic)
     NoV = np.fmax(dot(N, V), F(0.0001))
-    amb = (env_brdf_approx(diffuse_color, np.ones_like(rough), NoV) + env_brdf_approx(F0, rough, NoV)) * ambient_color   # occlusion = 1
+    amb = (env_brdf_approx(diffuse_color, np.ones_like(rough), NoV) + env_brdf_approx(F0, rough, NoV))
+    if occlusion is not None:
+        amb = occlusion[..., None] * amb
+    amb = amb * ambient_color
     a = (F(1.0) - radiance4[..., 3])[..., None]
     return lit * (F(1.0) - a) + amb * a
 
@@ -102,6 +105,40 @@ class Scene:
         self.sun_color = np.array(list(b.lights.directional_color), F)[:3]
         self.ambient = np.array(list(b.lights.ambient_color), F)[:3]
         self.cos_solar = np.cos(F(b.settings.solar_angle)).astype(F)
+        from tests.test_gbuffer_numpy import decode_texture
+        self.textures = [dict(t, texels=decode_texture(t)) for t in b.scene.textures]
+
+    def hit_uv(self, inst_id, tri, u, v):
+        """hit_info (:505-512): uv0 + u (uv1 - uv0) + v (uv2 - uv0)"""
+        out = np.zeros((len(inst_id), 2), F)
+        for i in np.unique(inst_id):
+            m = inst_id == i
+            inst = self.inst[i]
+            verts = self.bufs["vertices"][int(inst["mesh"]["vertex"]) + self.vidx[i][tri[m]].astype(np.int64)]
+            t = np.stack([verts["u"], verts["v"]], -1)
+            out[m] = t[:, 0] + u[m, None] * (t[:, 1] - t[:, 0]) + v[m, None] * (t[:, 2] - t[:, 0])
+        return out
+
+    def surfaces(self, material_ids, uv):
+        """retreive_surface (:729-781): material records with the textures multiplied in at `uv`, and the occlusion factor"""
+        from tests.test_gbuffer_numpy import sample
+        mats = self.bufs["materials"][material_ids].copy()
+        occlusion = np.ones(len(mats), F)
+        for slot in ("base_color_texture", "emissive_texture", "metallic_roughness_texture", "occlusion_texture"):
+            ids = mats[slot]
+            for tid in np.unique(ids[ids != 0xFFFFFFFF]):
+                m = ids == tid
+                t = self.textures[int(tid)]
+                tex = sample(t, t["texels"], uv[m, 0], uv[m, 1])
+                if slot == "base_color_texture":
+                    mats["base_color"][m] = mats["base_color"][m] * tex
+                elif slot == "emissive_texture":
+                    mats["emissive"][m] = mats["emissive"][m] * tex
+                elif slot == "metallic_roughness_texture":
+                    mats["metallic"][m] = mats["metallic"][m] * tex[:, 0]
+                else:
+                    occlusion[m] = tex[:, 0]
+        return mats, occlusion
 
     def closest(self, origin, direction, chunk=192):
         """closest hit over all triangles: distance, instance, local triangle, u, v, grazing flag"""
@@ -160,6 +197,7 @@ class Scene:
         # *info = empty_hit_info(position, rand_direction) (:618, :488-494); the fall-back of :696-702 uses the biased origin
         self.info_position = np.concatenate([position + rand_direction * DISTANCE_MAX, np.zeros((n, 1), F)], 1).astype(F)
         self.info_normal = np.zeros((n, 3), F)
+        self.info_uv = np.zeros((n, 2), F)
         leaves = [int(e) - LEAF for e in self.bufs["emissive_nodes"]["entry_index"] if int(e) >= LEAF]
         count = np.zeros(n, F); rand_1d = rand[:, 0].copy(); chosen = np.full(n, -1, np.int64)
         for e in leaves:
@@ -208,6 +246,7 @@ class Scene:
             fall_back = np.concatenate([origin + d * DISTANCE_MAX, np.zeros((len(sel), 1), F)], 1)
             self.info_position[sel] = np.where(found[:, None], np.concatenate([hit_pos, np.ones((len(sel), 1), F)], 1), fall_back)
             self.info_normal[sel] = np.where(found[:, None], n_world, F(0.0))
+            self.info_uv[sel] = self.hit_uv(np.full(len(sel), light), k, u_all[rr, k].astype(F), v_all[rr, k].astype(F))
         return direction, p, t_max, emissive_instance, light_material, graze
 
 
@@ -244,7 +283,7 @@ def trace_bounce(sc, P, N, rnd):
         hit_directional = dot(c_dir, np.tile(sc.sun, (len(hs), 1))) >= sc.cos_solar
         free = ~occ
         # unoccluded + emissive candidate: info still names the light (from select_light_candidate) -> its radiance, alpha 1
-        em_mats = sc.bufs["materials"][c_mat]
+        em_mats, _ = sc.surfaces(c_mat, sc.info_uv)                             # retreive_emissive at the light's uv (:783-793)
         em_rad = F(255.0) * em_mats["emissive"][:, 3:4] * em_mats["emissive"][:, :3]
         in_rad[:, 3] = 1.0
         in_rad[:, :3] = np.where((free & ~sample_directional)[:, None], em_rad, F(0.0))
@@ -252,10 +291,10 @@ def trace_bounce(sc, P, N, rnd):
         in_rad[:, :3] = np.where(sun_seen[:, None], sc.sun_color, in_rad[:, :3])
         sky = free & sample_directional & ~hit_directional                     # nothing hit, outside the cone: alpha 0, radiance 0
         in_rad[sky, 3] = 0.0
-        hit_mats = sc.bufs["materials"][np.array([int(sc.inst[i]["material"]) for i in h_inst[hs]])]
+        hit_mats, hit_occ = sc.surfaces(np.array([int(sc.inst[i]["material"]) for i in h_inst[hs]]), sc.hit_uv(h_inst[hs], h_tri[hs], h_u[hs], h_v[hs]))
         bview = normalize(P[hs] - sp)
         with np.errstate(all="ignore"):
-            o = shading(bview, sn, c_dir, hit_mats, in_rad, sc.ambient, roughness_override=1.0) / c_p[:, None]
+            o = shading(bview, sn, c_dir, hit_mats, in_rad, sc.ambient, roughness_override=1.0, occlusion=hit_occ) / c_p[:, None]
         out[hs] = np.where(trace[:, None], o, F(0.0))
         traced[hs] = trace
         # env_brdf (:891-908) with surface.roughness = 1
@@ -264,8 +303,7 @@ def trace_bounce(sc, P, N, rnd):
         F0 = F(0.16) * reflectance * reflectance * (F(1.0) - metallic) + base * metallic
         NoV = np.fmax(dot(sn, bview), F(0.0001))
         one = np.ones(len(hs), F)
-        transport[hs] = env_brdf_approx(base * (F(1.0) - metallic), one, NoV) + env_brdf_approx(F0, one, NoV)
-        graze[hs] |= (hit_mats["base_color_texture"] != 0xFFFFFFFF) | (hit_mats["emissive_texture"] != 0xFFFFFFFF)
+        transport[hs] = hit_occ[:, None] * (env_brdf_approx(base * (F(1.0) - metallic), one, NoV) + env_brdf_approx(F0, one, NoV))
     return hit, sample_pos, sample_normal, pdf, out, traced, transport, graze
 
 
@@ -330,21 +368,22 @@ def indirect_numpy(b, orc, frame_number, noise):
             alive[h] = True
     # at the visible point (:1461-1480)
     view = normalize(np.array(list(b.view.world_position), F) - P)
-    mats = sc.bufs["materials"][material]
+    vu = orc.readback(L.OUT_GBUFFER_VELOCITY_UV).reshape(-1, 4)[idx, 2:]
+    mats, occ = sc.surfaces(material, vu)
     with np.errstate(all="ignore"):
-        sample_radiance = shading(view, N, normalize(sample_pos - P), mats, radiance, sc.ambient)
+        sample_radiance = shading(view, N, normalize(sample_pos - P), mats, radiance, sc.ambient, occlusion=occ)
         w_new = np.where(pdf > 0, luminance(sample_radiance) / pdf, F(0.0))
         taken = w_new > 0
         r_w = np.where(taken, w_new / (F(1.0) * luminance(sample_radiance)), F(0.0))
         color = np.where(taken[:, None], sample_radiance * r_w[:, None], F(0.0))
-    textured = (mats["base_color_texture"] != 0xFFFFFFFF) | (mats["emissive_texture"] != 0xFFFFFFFF)
     full = np.zeros((H * W, 3), F); full[idx] = color
-    ex = np.zeros(H * W, bool); ex[idx] = graze | textured
+    ex = np.zeros(H * W, bool); ex[idx] = graze
     return full.reshape(H, W, 3), ex.reshape(H, W), covered.reshape(H, W)
 
 
 @pytest.mark.parametrize("scene,size,frames,bounces", [("cornell", (80, 80), (1, 2), 1), ("minimal", (80, 56), (1,), 1), ("soup5", (80, 56), (1,), 1),
-                                                       ("cornell", (80, 80), (1, 2), 2), ("cornell", (64, 64), (1,), 4), ("minimal", (80, 56), (2,), 3)])
+                                                       ("cornell", (80, 80), (1, 2), 2), ("cornell", (64, 64), (1,), 4), ("minimal", (80, 56), (2,), 3),
+                                                       ("samplers", (96, 64), (1, 2), 1), ("samplers", (96, 64), (1,), 3)])      # textured surfaces and a textured light
 def test_oracle_indirect_equals_independent_numpy_restatement(scene, size, frames, bounces):
     if scene.startswith("soup"):
         from bevy_hikari_b200 import scenes
