@@ -29,6 +29,7 @@ F = np.float32
 U32_MAX = 0xFFFFFFFF
 EPSILON = F(0.00001)
 NUM_BUCKETS = 6
+SWAP_CHILDREN = False      # True: flatten the right child before the left one (never what bvh 0.7.1 does; a test hook)
 INF = F(np.inf)
 
 
@@ -138,6 +139,8 @@ class _Bvh:
                 out.append(pack(empty_mn, empty_mx, U32_MAX, next_shape, n[1]))
                 return next_shape
             _, l_mn, l_mx, l_index, r_mn, r_mx, r_index = n
+            if SWAP_CHILDREN:      # test hook (tests/test_bvh_topology_invariance.py): a different, equally valid visit order
+                l_mn, l_mx, l_index, r_mn, r_mx, r_index = r_mn, r_mx, r_index, l_mn, l_mx, l_index
             after_l = branch(l_mn, l_mx, l_index, next_free)
             return branch(r_mn, r_mx, r_index, after_l)
 
