@@ -19,8 +19,14 @@ def RGB_to_YCoCg(c):
                      -c[..., 0] / F(4) + c[..., 1] / F(2) - c[..., 2] / F(4)], -1)
 
 
+def clamp01(a):
+    # clamp = min(max(x, 0), 1) with IEEE minNum / maxNum (the rule include/hk_math.h fixes where WGSL leaves NaN open): NaN -> 0.
+    # It matters: the variance under the square root can round below zero in one channel, and the clipped colour is then NaN there.
+    return np.fmin(np.fmax(a, F(0)), F(1))
+
+
 def YCoCg_to_RGB(c):
-    return np.clip(np.stack([c[..., 0] + c[..., 1] - c[..., 2], c[..., 0] + c[..., 2], c[..., 0] - c[..., 1] - c[..., 2]], -1), F(0), F(1))
+    return clamp01(np.stack([c[..., 0] + c[..., 1] - c[..., 2], c[..., 0] + c[..., 2], c[..., 0] - c[..., 1] - c[..., 2]], -1))
 
 
 class Tex:
@@ -97,7 +103,7 @@ def taa_numpy(render, previous_render, position, previous_position, velocity_uv,
     off12 = w2 / (w1 + w2)
     ts = np.array([tx, ty], F)
     p0, p3, p12 = (tp1 - F(1.0)) * ts, (tp1 + F(2.0)) * ts, (tp1 + off12) * ts
-    fetch = lambda a, b_: np.clip(previous_render.linear(a, b_)[..., :3], F(0), F(1))
+    fetch = lambda a, b_: clamp01(previous_render.linear(a, b_)[..., :3])
     prev = np.zeros(current.shape, F)
     prev = prev + fetch(p12[..., 0], p0[..., 1]) * w12[..., 0:1] * w0[..., 1:2]
     prev = prev + fetch(p0[..., 0], p12[..., 1]) * w0[..., 0:1] * w12[..., 1:2]
@@ -105,7 +111,7 @@ def taa_numpy(render, previous_render, position, previous_position, velocity_uv,
     prev = prev + fetch(p3[..., 0], p12[..., 1]) * w3[..., 0:1] * w12[..., 1:2]
     prev = prev + fetch(p12[..., 0], p3[..., 1]) * w12[..., 0:1] * w3[..., 1:2]
     clip_it = boundary_miss | (position_miss & velocity_miss & depth_miss)
-    srt = lambda a, b_: RGB_to_YCoCg(np.clip(render.nearest(a, b_)[..., :3], F(0), F(1)))
+    srt = lambda a, b_: RGB_to_YCoCg(clamp01(render.nearest(a, b_)[..., :3]))
     s = [srt(u - tx, v + ty), srt(u, v + ty), srt(u + tx, v + ty), srt(u - tx, v), RGB_to_YCoCg(current), srt(u + tx, v),
          srt(u - tx, v - ty), srt(u, v - ty), srt(u + tx, v - ty)]
     m1 = s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7] + s[8]
@@ -151,3 +157,27 @@ def test_oracle_taa_equals_independent_numpy_restatement(scene, config, size):
             clipped_total += int(clipped.sum())
         prev_position, prev_velocity = position.copy(), velocity.copy()
     assert clipped_total > 50          # the disocclusion branch ran
+
+
+def test_oracle_taa_after_smaa_tu4x_the_default_pipeline():
+    """HikariSettings::default(): Upscale::SMAA_TU_2_0 + Taa::Jasmine — TAA runs on the SMAA-upscaled image (twice the render size,
+    post_process.rs:1010-1014, 726-731) and blends with 0.1 / upscale_ratio"""
+    size, ratio = (112, 80), 2.0
+    b = Bench("cornell", size[0], size[1], config="cornell_1080p", taa=plugin.TAA_JASMINE, upscale_kind=plugin.UPSCALE_SMAA_TU4X,
+              upscale_ratio=ratio, clear_color=(0.2, 0.3, 0.4, 1.0))
+    orc = b.oracle()
+    prev_position = prev_velocity = None
+    for f in range(1, 7):
+        inp = b.moving_inputs(f, step=(0.06, 0.02, -0.04))
+        inp.temporal_upscalers = 1
+        previous_taa = orc.readback(L.OUT_TAA).copy() if f > 1 else None
+        orc.render_frame(inp)
+        position, velocity = orc.readback(L.OUT_GBUFFER_POSITION), orc.readback(L.OUT_GBUFFER_VELOCITY_UV)
+        if f > 2:
+            upscaled = orc.readback(L.OUT_UPSCALED).astype(F)
+            assert upscaled.shape[:2] == (size[1], size[0]) == orc.readback(L.OUT_TAA).shape[:2]       # 2 x ceil(size / 2)
+            want, clipped = taa_numpy(Tex(upscaled), Tex(previous_taa.astype(F)), Tex(position), Tex(prev_position), Tex(velocity),
+                                      Tex(prev_velocity), ratio, (0.2, 0.3, 0.4, 1.0))
+            d = ulps16(orc.readback(L.OUT_TAA).astype(F), want).max(-1)
+            assert (d == 0).mean() >= 0.995 and (d <= 1).mean() >= 0.999, (f, float((d == 0).mean()), float((d <= 1).mean()))
+        prev_position, prev_velocity = position.copy(), velocity.copy()
