@@ -93,14 +93,17 @@ def shade_lit(V, N, Lv, mat, radiance):                 # light.wgsl shading() -
     return (specular + diffuse) * radiance * NoL[..., None]
 
 
-def direct_sun_numpy(b, orc, frame_number, noise):
+def gbuffer_at_render_pixels(b, orc, frame_number):
+    """(position+depth, snorm-decoded normal, instance/material, velocity/uv) as the light passes see them: one entry per RENDER
+    pixel.  Rendering below the output resolution (light.rs:622-624) runs the passes over ceil(size / ratio) pixels that read the
+    full-size G-buffer at jittered_deferred_coords(uv) = i32((uv -+ 0.25 texel * (ratio - 1)) * size)  (light.wgsl:1007-1017);
+    at ratio 1 that is the identity."""
     pos = orc.readback(L.OUT_GBUFFER_POSITION)
     normal = np.maximum(orc.readback(L.OUT_GBUFFER_NORMAL).astype(F) / F(127.0), F(-1.0))[..., :3]
     im = orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)
+    vu = orc.readback(L.OUT_GBUFFER_VELOCITY_UV)
     ratio = F(b.settings.upscale_ratio)
     if ratio != 1.0:
-        # render below the output resolution (light.rs:622-624): the pass runs over ceil(size / ratio) pixels and reads the
-        # full-size G-buffer at jittered_deferred_coords(uv) = i32((uv -+ 0.25 texel * (ratio - 1)) * size)  (:1007-1017)
         DH, DW = pos.shape[:2]
         H, W = int(np.ceil(F(1.0) / ratio * F(DH))), int(np.ceil(F(1.0) / ratio * F(DW)))
         ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
@@ -108,7 +111,12 @@ def direct_sun_numpy(b, orc, frame_number, noise):
         du = (xs.astype(F) + F(0.5)) / F(W) + sel * (F(1.0) / F(DW)) * (ratio - F(1.0))
         dv = (ys.astype(F) + F(0.5)) / F(H) + sel * (F(1.0) / F(DH)) * (ratio - F(1.0))
         dx, dy = np.trunc(du * F(DW)).astype(np.int64), np.trunc(dv * F(DH)).astype(np.int64)
-        pos, normal, im = pos[dy, dx], normal[dy, dx], im[dy, dx]
+        pos, normal, im, vu = pos[dy, dx], normal[dy, dx], im[dy, dx], vu[dy, dx]
+    return pos, normal, im, vu
+
+
+def direct_sun_numpy(b, orc, frame_number, noise):
+    pos, normal, im, _ = gbuffer_at_render_pixels(b, orc, frame_number)
     H, W = pos.shape[:2]
     ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     position, depth = pos[..., :3], pos[..., 3]

@@ -16,8 +16,8 @@ import pytest
 from bevy_hikari_b200 import layout as L
 from bevy_hikari_b200 import plugin
 from tests.conftest import Bench
-from tests.test_direct_lit_numpy import (DISTANCE_MAX, F, GOLDEN_RATIO, RAY_BIAS, dot, fract, luminance, normalize, shade_lit,
-                                          ulps16)
+from tests.test_direct_lit_numpy import (DISTANCE_MAX, F, GOLDEN_RATIO, RAY_BIAS, dot, fract, gbuffer_at_render_pixels, luminance, normalize,
+                                          shade_lit, ulps16)
 
 LEAF = 0x80000000
 NONE = 0xFFFFFFFF
@@ -55,9 +55,7 @@ def world_tris_of(bufs, i):
 
 def emissive_numpy(b, orc, frame_number, noise):
     bufs = b.world.buffers()
-    pos = orc.readback(L.OUT_GBUFFER_POSITION)
-    normal = np.maximum(orc.readback(L.OUT_GBUFFER_NORMAL).astype(F) / F(127.0), F(-1.0))[..., :3]
-    im = orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)
+    pos, normal, im, _ = gbuffer_at_render_pixels(b, orc, frame_number)
     H, W = pos.shape[:2]
     ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     position, depth = pos[..., :3].reshape(-1, 3), pos[..., 3].reshape(-1)
@@ -160,12 +158,13 @@ def emissive_numpy(b, orc, frame_number, noise):
     return color.reshape(H, W, 3), excluded.reshape(H, W), covered2, sampled.reshape(H, W)
 
 
-@pytest.mark.parametrize("scene,size,frames", [("cornell", (96, 96), (1, 2, 4)), ("soup5", (96, 64), (1, 2)), ("soup8", (96, 64), (1,))])
-def test_oracle_direct_emissive_equals_independent_numpy_restatement(scene, size, frames):
+@pytest.mark.parametrize("scene,size,frames,ratio", [("cornell", (96, 96), (1, 2, 4), 1.0), ("soup5", (96, 64), (1, 2), 1.0), ("soup8", (96, 64), (1,), 1.0),
+                                                     ("cornell", (120, 120), (1, 2), 1.5)])
+def test_oracle_direct_emissive_equals_independent_numpy_restatement(scene, size, frames, ratio):
     if scene.startswith("soup"):
         from bevy_hikari_b200 import scenes
         scenes.SCENE_BUILDERS[scene] = lambda: scenes.soup(int(scene[4:]))      # several emissive instances, mirrored / skewed transforms
-    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=0, denoise=0, indirect_bounces=1,
+    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=ratio, temporal_reuse=0, denoise=0, indirect_bounces=1,
               emissive_spatial_reuse=0)
     orc = b.oracle()
     noise = plugin.load_noise()

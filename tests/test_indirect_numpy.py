@@ -309,9 +309,8 @@ def trace_bounce(sc, P, N, rnd):
 
 def indirect_numpy(b, orc, frame_number, noise):
     sc = Scene(b)
-    pos = orc.readback(L.OUT_GBUFFER_POSITION)
-    g_normal = np.maximum(orc.readback(L.OUT_GBUFFER_NORMAL).astype(F) / F(127.0), F(-1.0))[..., :3]
-    im = orc.readback(L.OUT_GBUFFER_INSTANCE_MATERIAL)
+    from tests.test_direct_lit_numpy import gbuffer_at_render_pixels
+    pos, g_normal, im, vu_plane = gbuffer_at_render_pixels(b, orc, frame_number)
     H, W = pos.shape[:2]
     ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     tex = noise.reshape(16, 64, 64, 4)[frame_number % 16].astype(F) / F(255.0)
@@ -368,7 +367,7 @@ def indirect_numpy(b, orc, frame_number, noise):
             alive[h] = True
     # at the visible point (:1461-1480)
     view = normalize(np.array(list(b.view.world_position), F) - P)
-    vu = orc.readback(L.OUT_GBUFFER_VELOCITY_UV).reshape(-1, 4)[idx, 2:]
+    vu = vu_plane.reshape(-1, 4)[idx, 2:]
     mats, occ = sc.surfaces(material, vu)
     with np.errstate(all="ignore"):
         sample_radiance = shading(view, N, normalize(sample_pos - P), mats, radiance, sc.ambient, occlusion=occ)
@@ -384,11 +383,21 @@ def indirect_numpy(b, orc, frame_number, noise):
 @pytest.mark.parametrize("scene,size,frames,bounces", [("cornell", (80, 80), (1, 2), 1), ("minimal", (80, 56), (1,), 1), ("soup5", (80, 56), (1,), 1),
                                                        ("cornell", (80, 80), (1, 2), 2), ("cornell", (64, 64), (1,), 4), ("minimal", (80, 56), (2,), 3),
                                                        ("samplers", (96, 64), (1, 2), 1), ("samplers", (96, 64), (1,), 3)])      # textured surfaces and a textured light
-def test_oracle_indirect_equals_independent_numpy_restatement(scene, size, frames, bounces):
+def test_oracle_indirect_equals_independent_numpy_restatement(scene, size, frames, bounces, ratio=1.0):
+    run_indirect_case(scene, size, frames, bounces, ratio)
+
+
+@pytest.mark.parametrize("scene,size,frames,bounces,ratio", [("cornell", (120, 100), (1, 2), 2, 1.5), ("samplers", (128, 96), (2,), 1, 2.0)])
+def test_oracle_indirect_below_the_output_resolution(scene, size, frames, bounces, ratio):
+    """the same pass over ceil(size / ratio) render pixels, G-buffer read through jittered_deferred_coords"""
+    run_indirect_case(scene, size, frames, bounces, ratio)
+
+
+def run_indirect_case(scene, size, frames, bounces, ratio):
     if scene.startswith("soup"):
         from bevy_hikari_b200 import scenes
         scenes.SCENE_BUILDERS[scene] = lambda: scenes.soup(int(scene[4:]))
-    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=0, denoise=0, indirect_bounces=bounces,
+    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=ratio, temporal_reuse=0, denoise=0, indirect_bounces=bounces,
               emissive_spatial_reuse=0, indirect_spatial_reuse=0)
     orc = b.oracle()
     noise = plugin.load_noise()
