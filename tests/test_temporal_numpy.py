@@ -83,6 +83,22 @@ def unpack_reservoir(p):
     return r
 
 
+def pack_records(r, visible_position, visible_normal):
+    """pack_reservoir (:108-136) of a reservoir dict with the given visible point"""
+    n = len(r["count"])
+    packed = np.zeros(n, L.PACKED_RESERVOIR)
+    packed["reservoir"][:, 0] = pack_f16x2(r["count"], r["w"]); packed["reservoir"][:, 1] = pack_f16x2(r["w_sum"], r["w2_sum"])
+    packed["radiance"][:, 0] = pack_f16x2(r["radiance"][:, 0], r["radiance"][:, 1])
+    packed["radiance"][:, 1] = pack_f16x2(r["radiance"][:, 2], r["radiance"][:, 3])
+    packed["random"][:, 0] = pack_unorm16x2(r["random"][:, 0], r["random"][:, 1])
+    packed["random"][:, 1] = pack_unorm16x2(r["random"][:, 2], r["random"][:, 3])
+    packed["visible_position"] = visible_position
+    packed["sample_position"] = np.concatenate([r["sample_position"][:, :3], r["visible_instance"].astype(F)[:, None]], 1)
+    packed["visible_normal"] = pack_snorm8x4(np.concatenate([visible_normal, (r["lifetime"] / F(127.0) - F(1.0))[:, None]], 1))
+    packed["sample_normal"] = pack_snorm8x4(np.concatenate([r["sample_normal"], r["sample_position"][:, 3:4]], 1))
+    return packed
+
+
 def temporal_emissive_numpy(b, orc, frame_number, noise, previous, inp=None):
     """`inp` = the frame inputs when the camera moves: history is then fetched at previous_uv = uv - velocity (:1089-1090)"""
     sc = Scene(b)
@@ -193,6 +209,9 @@ def temporal_emissive_numpy(b, orc, frame_number, noise, previous, inp=None):
             lum_ratio = luminance(validate_radiance[:, :3]) / np.fmax(luminance(r["radiance"][:, :3]), F(0.0001))
             reset = (lum_ratio > F(1.25)) | (lum_ratio < F(0.8))
             w_val = np.where(v_p > 0, luminance(s_val["radiance"][:, :3]) / v_p, F(0.0))
+        # the reservoir as it stands BEFORE the reset is what store_previous_spatial_reservoir receives (:1199-1202): its own
+        # visible point (the history's, or this frame's where block A replaced the sample), w not yet recomputed
+        temporal_emissive_numpy.before_reset = pack_records(r, r["visible_position"], r["visible_normal"])
         # a reset installs `s` whatever its weight: where s is this frame's OCCLUDED candidate, its position is the occluder's
         # (traversal-order dependent, :526-533) — left out
         graze |= reset & ~established & occ & trace
@@ -384,3 +403,57 @@ def test_oracle_validation_frames_equal_independent_numpy_restatement():
     # (frame 2) or with +3 % (frame 8) only reservoirs whose stored radiance is 0 while the validation ray arrives (or the
     # reverse) reset
     assert resets[4] > 2 * resets[2] and resets[6] > 2 * resets[8] and kept_validations > 1000 and validation_only > 200, (resets, kept_validations, validation_only)
+
+
+def test_oracle_validation_scatter_equals_independent_numpy_restatement():
+    """the third kind of write into the previous-spatial buffer (light.wgsl:1199-1202): a validation frame that finds the light
+    changed stores the reservoir AS IT WAS into the record it was fetched from, before resetting it — compared record by record
+    with the buffer the oracle's emissive pass leaves behind"""
+    W, H = 64, 64
+    b = Bench("cornell", W, H, taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=1, denoise=0, indirect_bounces=1,
+              emissive_spatial_reuse=0, indirect_spatial_reuse=0, emissive_validate_interval=2, direct_validate_interval=5)
+    orc = b.oracle()
+    noise = plugin.load_noise()
+    w = b.world
+    light_material = int(w.buffers()["instances"][int(w.buffers()["emissives"][0]["instance"])]["material"])
+    base = b.scene.materials[light_material].copy()
+    empty = np.zeros((), L.PACKED_RESERVOIR)
+    empty["visible_normal"] = pack_snorm8x4(np.array([[0.0, 0.0, 0.0, -1.0]], F))[0]
+    stored = 0
+    for f in range(1, 5):
+        m = base.copy()
+        m["emissive"] = (base["emissive"][0], base["emissive"][1], base["emissive"][2], base["emissive"][3] * (2.0 if f >= 4 else 1.0))
+        w.set_material(light_material, m)
+        w.prepare_materials(); w.previous_transform_system(); w.prepare_instances()
+        orc.update_instances_desc(w.scene_desc())
+        inp = b.inputs(f)
+        head = f % 2
+        orc.prepass(inp)
+        orc.run_pass(inp, 0); orc.run_pass(inp, 1)
+        previous = orc.readback(L.OUT_RESERVOIR_0 + 2 + head).copy()
+        before = orc.readback(L.OUT_RESERVOIR_0 + 4 + head).reshape(-1).copy()
+        orc.run_pass(inp, 2)
+        after = orc.readback(L.OUT_RESERVOIR_0 + 4 + head).reshape(-1).copy()
+        orc.run_pass(inp, 4)
+        if f != 4:
+            continue
+        idx, packed, out, variance, graze, take, miss = temporal_emissive_numpy(b, orc, f, noise, previous)
+        reset = temporal_emissive_numpy.reset
+        records = temporal_emissive_numpy.before_reset
+        expected = before.copy()
+        background = np.setdiff1d(np.arange(W * H), idx)
+        bg = np.zeros((), L.PACKED_RESERVOIR)
+        bg["visible_normal"] = empty["visible_normal"]; bg["reservoir"][0] = pack_f16x2(F(1.0), F(0.0))
+        writes = [(int(px), int(px), empty) for px in idx[miss]]                    # rejected history (static camera: own pixel)
+        writes += [(int(px), int(px), bg) for px in background]
+        order = {int(px): k for k, px in enumerate(idx)}
+        for px in idx[reset]:                                                       # the validation store comes after the miss store of the same pixel
+            writes.append((int(px) + 0.5, int(px), records[order[int(px)]]))
+        for _, tg, value in sorted(writes, key=lambda t: t[0]):
+            expected[tg] = value
+        clean_px = idx[~graze]
+        same = (expected.view(np.uint8).reshape(-1, 64) == after.view(np.uint8).reshape(-1, 64)).all(1)
+        assert same[clean_px].mean() >= 0.99, float(same[clean_px].mean())
+        assert same[background].all()
+        stored = int(reset[~graze].sum())
+    assert stored > 300                                                              # the doubled light reset every lit reservoir
