@@ -307,7 +307,9 @@ def trace_bounce(sc, P, N, rnd):
     return hit, sample_pos, sample_normal, pdf, out, traced, transport, graze
 
 
-def indirect_numpy(b, orc, frame_number, noise):
+def indirect_numpy(b, orc, frame_number, noise, previous=None):
+    """previous = the packed reservoir buffer the pass reads (static camera: a pixel's history is its own record); None = no
+    history, the reservoir starts empty"""
     sc = Scene(b)
     from tests.test_direct_lit_numpy import gbuffer_at_render_pixels
     pos, g_normal, im, vu_plane = gbuffer_at_render_pixels(b, orc, frame_number)
@@ -372,9 +374,50 @@ def indirect_numpy(b, orc, frame_number, noise):
     with np.errstate(all="ignore"):
         sample_radiance = shading(view, N, normalize(sample_pos - P), mats, radiance, sc.ambient, occlusion=occ)
         w_new = np.where(pdf > 0, luminance(sample_radiance) / pdf, F(0.0))
-        taken = w_new > 0
-        r_w = np.where(taken, w_new / (F(1.0) * luminance(sample_radiance)), F(0.0))
-        color = np.where(taken[:, None], sample_radiance * r_w[:, None], F(0.0))
+    if previous is None:
+        with np.errstate(all="ignore"):
+            taken = w_new > 0
+            r_w = np.where(taken, w_new / (F(1.0) * luminance(sample_radiance)), F(0.0))
+            color = np.where(taken[:, None], sample_radiance * r_w[:, None], F(0.0))
+    else:
+        # temporal ReSTIR with history (:1452-1497): unlike direct_lit, r.w normalises by the luminance of the SHADED reservoir
+        # sample, evaluated with the sample's own (stored) visible point before that is refreshed
+        from tests.test_temporal_numpy import pack_records, unpack_reservoir
+        depth = pos[..., 3].reshape(-1)[idx]
+        instance = np.floor(im[..., 0]).astype(np.int64).reshape(-1)[idx]
+        prev = unpack_reservoir(previous.reshape(-1)[idx])
+        with np.errstate(all="ignore"):
+            ratio_d = prev["visible_position"][:, 3] / depth
+            ratio_d = np.where(ratio_d < 1.0, F(1.0) / ratio_d, ratio_d)
+            miss = (ratio_d > F(1.05) * (F(1.0) + F(0.5) * rnd[:, 0])) | (dot(N, prev["visible_normal"]) < F(0.9)) | (prev["visible_instance"] != instance)
+        r = {k: np.where(miss.reshape((-1,) + (1,) * (v.ndim - 1)), 0, v).astype(v.dtype) for k, v in prev.items()}
+        with np.errstate(all="ignore"):
+            r["w_sum"] = r["w_sum"] + w_new
+            r["w2_sum"] = r["w2_sum"] + w_new * w_new
+            r["count"] = r["count"] + F(1.0)
+            take = fract(rnd[:, 0] + rnd[:, 1] + rnd[:, 2] + rnd[:, 3]) < w_new / r["w_sum"]
+        s_visible_position = np.concatenate([P, depth[:, None]], 1).astype(F)
+        # s.sample_position.w: 1 on a hit, 0 on a miss (hit_info, :516-519)
+        hit_flag = (np.abs(sample_pos - (P + N * RAY_BIAS)).max(1) < F(60000.0)).astype(F)
+        new = dict(radiance=radiance, random=rnd, sample_position=np.concatenate([sample_pos, hit_flag[:, None]], 1).astype(F), sample_normal=sample_normal,
+                   visible_position=s_visible_position, visible_normal=N)
+        for k, v in new.items():
+            r[k] = np.where(take[:, None], v, r[k]).astype(F)
+        r["visible_instance"] = np.where(take, instance, r["visible_instance"])
+        m = F(b.settings.max_temporal_reuse_count)
+        with np.errstate(all="ignore"):
+            over = r["count"] > m
+            r["w_sum"] = np.where(over, r["w_sum"] * (m / r["count"]), r["w_sum"])
+            r["w2_sum"] = np.where(over, r["w2_sum"] * (m / r["count"]), r["w2_sum"])
+            r["count"] = np.where(over, m, r["count"])
+            out_radiance = shading(view, r["visible_normal"], normalize(r["sample_position"][:, :3] - r["visible_position"][:, :3]), mats, r["radiance"],
+                                   sc.ambient, occlusion=occ)
+            total = r["count"] * luminance(out_radiance)
+            r["w"] = np.where(total > 0, r["w_sum"] / total, F(0.0))
+            r["lifetime"] = r["lifetime"] + F(1.0)
+            color = out_radiance * r["w"][:, None]
+        indirect_numpy.packed = pack_records(r, s_visible_position, N)
+        indirect_numpy.idx, indirect_numpy.take, indirect_numpy.miss = idx, take, miss
     full = np.zeros((H * W, 3), F); full[idx] = color
     ex = np.zeros(H * W, bool); ex[idx] = graze
     return full.reshape(H, W, 3), ex.reshape(H, W), covered.reshape(H, W)
@@ -417,3 +460,38 @@ def run_indirect_case(scene, size, frames, bounces, ratio):
         far = (d > 2) & (np.abs(got[..., :3] - want).max(-1) > 2e-3 * np.abs(want).max(-1))
         assert (far & clean).sum() <= 2, (f, int((far & clean).sum()))
         assert (got[..., 3][covered] == 1).all() and not got[~covered].any()
+
+
+@pytest.mark.parametrize("scene,size,bounces", [("cornell", (72, 72), 2), ("minimal", (80, 56), 1)])
+def test_oracle_indirect_with_history_equals_independent_numpy_restatement(scene, size, bounces):
+    """temporal ReSTIR of the indirect pass (light.wgsl:1452-1497) over frames 2-5: history fetched, checked, merged with the new
+    path sample by the target function, clamped to M, normalised by the shaded reservoir sample — render[2] and the written
+    reservoir records against the oracle"""
+    from tests.test_temporal_numpy import unpack_f16x2
+    b = Bench(scene, size[0], size[1], taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=1, denoise=0, indirect_bounces=bounces,
+              emissive_spatial_reuse=0, indirect_spatial_reuse=0, max_temporal_reuse_count=3)
+    orc = b.oracle()
+    noise = plugin.load_noise()
+    kept = replaced = 0
+    for f in range(1, 6):
+        previous = orc.readback(L.OUT_RESERVOIR_0 + 6 + (f % 2)).copy()            # light.rs:518-546: buffers [6, 7] are the indirect temporal pair
+        orc.render_frame(b.inputs(f))
+        if f == 1:
+            continue
+        want, excluded, covered = indirect_numpy(b, orc, f, noise, previous)
+        got = orc.readback(L.OUT_RENDER_INDIRECT).astype(F)
+        clean = covered & ~excluded
+        d = ulps16(got[..., :3], want).max(-1)
+        far = (d > 2) & (np.abs(got[..., :3] - want).max(-1) > 2e-3 * np.abs(want).max(-1))
+        assert (d[clean] == 0).mean() >= 0.99 and (d[clean] <= 1).mean() >= 0.998 and (far & clean).sum() <= 3, (f, float((d[clean] <= 1).mean()), int((far & clean).sum()))
+        idx, take = indirect_numpy.idx, indirect_numpy.take
+        ok = ~excluded.reshape(-1)[idx]
+        written = orc.readback(L.OUT_RESERVOIR_0 + 6 + 1 - (f % 2)).reshape(-1)[idx]
+        packed = indirect_numpy.packed
+        gc, _ = unpack_f16x2(written["reservoir"][:, 0]); wc, _ = unpack_f16x2(packed["reservoir"][:, 0])
+        assert (gc[ok] == wc[ok]).mean() >= 0.995
+        for field in ("random", "visible_position", "visible_normal"):
+            same = (written[field] == packed[field]) if written[field].ndim == 1 else (written[field] == packed[field]).all(-1)
+            assert same[ok].mean() >= 0.985, (f, field, float(same[ok].mean()))
+        kept += int((~take & ok).sum()); replaced += int((take & ok).sum())
+    assert kept > 1000 and replaced > 1000
