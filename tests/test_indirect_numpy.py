@@ -181,7 +181,7 @@ class Scene:
             out[m] = normalize((n_obj[:, 0:1] * itm[0] + n_obj[:, 1:2] * itm[1] + n_obj[:, 2:3] * itm[2]).astype(F))
         return out
 
-    def select_light_candidate(self, rand, position, normal, own_instance):
+    def select_light_candidate(self, rand, position, normal, own_instance, sample_emissive=True):
         """light.wgsl:599-708.  Returns direction, p, max_distance, emissive_instance (DONT_SAMPLE = sun fall-back), the light's
         material (for its radiance) and a grazing flag."""
         n = len(position)
@@ -199,6 +199,8 @@ class Scene:
         self.info_normal = np.zeros((n, 3), F)
         self.info_uv = np.zeros((n, 2), F)
         leaves = [int(e) - LEAF for e in self.bufs["emissive_nodes"]["entry_index"] if int(e) >= LEAF]
+        if not sample_emissive:      # instance == DONT_SAMPLE_EMISSIVE: the sun pass returns before the emissive walk (:620-622)
+            leaves = []
         count = np.zeros(n, F); rand_1d = rand[:, 0].copy(); chosen = np.full(n, -1, np.int64)
         for e in leaves:
             em = self.bufs["emissives"][e]

@@ -99,8 +99,9 @@ def pack_records(r, visible_position, visible_normal):
     return packed
 
 
-def temporal_emissive_numpy(b, orc, frame_number, noise, previous, inp=None):
-    """`inp` = the frame inputs when the camera moves: history is then fetched at previous_uv = uv - velocity (:1089-1090)"""
+def temporal_emissive_numpy(b, orc, frame_number, noise, previous, inp=None, emissive=True):
+    """`inp` = the frame inputs when the camera moves: history is then fetched at previous_uv = uv - velocity (:1089-1090).
+    emissive = False restates the sun pipeline of the same entry point (sample_directional, DONT_SAMPLE_EMISSIVE, RENDER_EMISSIVE)."""
     sc = Scene(b)
     pos = orc.readback(L.OUT_GBUFFER_POSITION)
     g_normal = np.maximum(orc.readback(L.OUT_GBUFFER_NORMAL).astype(F) / F(127.0), F(-1.0))[..., :3]
@@ -121,17 +122,24 @@ def temporal_emissive_numpy(b, orc, frame_number, noise, previous, inp=None):
     material = np.floor(im[..., 1]).astype(np.int64).reshape(-1)[idx]
     n = len(idx)
     # --- the candidate of this frame (:1104-1151, EMISSIVE_LIT)
-    c_dir, c_p, c_tmax, c_em, c_mat, graze = sc.select_light_candidate(rnd, P, N, instance)
+    c_dir, c_p, c_tmax, c_em, c_mat, graze = sc.select_light_candidate(rnd, P, N, instance, sample_emissive=emissive)
     info_pos, info_nrm = sc.info_position.copy(), sc.info_normal.copy()
-    trace = (dot(c_dir, N) > 0) & (c_p > 0) & (c_em != DONT_SAMPLE)
+    trace = (dot(c_dir, N) > 0) & (c_p > 0)
+    if emissive:
+        trace &= c_em != DONT_SAMPLE
     origin = (P + N * RAY_BIAS).astype(F)
-    occ, og = sc.occluded(origin, c_dir, np.where(np.isfinite(c_tmax), c_tmax, 3.4e38), c_em)
+    occ, og = sc.occluded(origin, c_dir, np.where(np.isfinite(c_tmax), c_tmax, 3.4e38), c_em if emissive else np.full(n, -1, np.int64))
     graze |= og & trace
     lit = trace & ~occ
-    em = sc.bufs["materials"][c_mat]["emissive"]
     s_radiance = np.zeros((n, 4), F)
-    s_radiance[:, :3] = np.where(lit[:, None], F(255.0) * em[:, 3:4] * em[:, :3], F(0.0))
-    s_radiance[:, 3] = np.where(trace, F(1.0), F(0.0))                     # input_radiance alpha = 1 whenever it was called
+    if emissive:
+        em = sc.bufs["materials"][c_mat]["emissive"]
+        s_radiance[:, :3] = np.where(lit[:, None], F(255.0) * em[:, 3:4] * em[:, :3], F(0.0))
+        s_radiance[:, 3] = np.where(trace, F(1.0), F(0.0))                 # input_radiance alpha = 1 whenever it was called
+    else:                                                                  # input_radiance(ray, info, true, DONT_SAMPLE_EMISSIVE, false), :842-872
+        in_cone = dot(c_dir, np.tile(sc.sun, (n, 1))) >= sc.cos_solar
+        s_radiance[:, :3] = np.where((lit & in_cone)[:, None], sc.sun_color, F(0.0))
+        s_radiance[:, 3] = np.where(trace & (occ | in_cone), F(1.0), F(0.0))   # an unoccluded ray outside the cone is "ambient": alpha 0
     # an occluded shadow ray rewrites info with the occluder (:526-533): position is traversal-order dependent, but such a
     # candidate has weight 0 and can never enter the reservoir, so it is not needed
     with np.errstate(all="ignore"):
@@ -155,7 +163,7 @@ def temporal_emissive_numpy(b, orc, frame_number, noise, previous, inp=None):
         miss = depth_miss | (dot(N, prev["visible_normal"]) < F(0.9)) | (prev["visible_instance"] != instance)
     r = {k: (np.where(miss.reshape((-1,) + (1,) * (v.ndim - 1)), 0, v)).astype(v.dtype) for k, v in prev.items()}
     # --- block A (:1104-1153): a new candidate unless this is a validation frame with an established reservoir
-    interval = int(b.settings.emissive_validate_interval)
+    interval = int(b.settings.emissive_validate_interval if emissive else b.settings.direct_validate_interval)
     validation = frame_number % interval == 0
     do_new = np.full(n, not validation) | (r["count"] < F(4.0))
     s_now = dict(radiance=np.where(do_new[:, None], s_radiance, F(0.0)), random=rnd,
@@ -187,20 +195,28 @@ def temporal_emissive_numpy(b, orc, frame_number, noise, previous, inp=None):
         # --- block B (:1155-1208): re-derive the reservoir sample's light point from ITS random numbers and visible point, shoot the
         # ray from the CURRENT visible point towards the stored sample position, compare what arrives with what was stored
         with np.errstate(all="ignore"):
-            v_dir, v_p, v_tmax, v_em, v_mat, v_graze = sc.select_light_candidate(r["random"], r["visible_position"][:, :3].copy(), r["visible_normal"].copy(), instance)
+            v_dir, v_p, v_tmax, v_em, v_mat, v_graze = sc.select_light_candidate(r["random"], r["visible_position"][:, :3].copy(), r["visible_normal"].copy(), instance,
+                                                                                 sample_emissive=emissive)
             v_info_pos, v_info_nrm = sc.info_position.copy(), sc.info_normal.copy()
             ray_dir = normalize(r["sample_position"][:, :3] - P).astype(F)
-            v_trace = (dot(v_dir, r["visible_normal"]) > 0) & (v_p > 0) & (v_em != DONT_SAMPLE)
+            v_trace = (dot(v_dir, r["visible_normal"]) > 0) & (v_p > 0)
+            if emissive:
+                v_trace &= v_em != DONT_SAMPLE
             ray_dir = np.where(np.isfinite(ray_dir), ray_dir, F(0.0))
-        v_occ, v_og = sc.occluded(origin, ray_dir, np.where(np.isfinite(v_tmax), v_tmax, 3.4e38), v_em)
+        v_occ, v_og = sc.occluded(origin, ray_dir, np.where(np.isfinite(v_tmax), v_tmax, 3.4e38), v_em if emissive else np.full(n, -1, np.int64))
         established = r["count"] >= F(4.0)
         # an occluded validation ray of an established reservoir stores the occluder's position, which depends on the
         # traversal order (any-hit): not reproducible by brute force, left out
         graze |= (v_graze & v_trace) | (v_og & v_trace) | (v_occ & v_trace & established)
-        v_em_mat = sc.bufs["materials"][v_mat]["emissive"]
         validate_radiance = np.zeros((n, 4), F)
-        validate_radiance[:, :3] = np.where((v_trace & ~v_occ)[:, None], F(255.0) * v_em_mat[:, 3:4] * v_em_mat[:, :3], F(0.0))
-        validate_radiance[:, 3] = np.where(v_trace, F(1.0), F(0.0))
+        if emissive:
+            v_em_mat = sc.bufs["materials"][v_mat]["emissive"]
+            validate_radiance[:, :3] = np.where((v_trace & ~v_occ)[:, None], F(255.0) * v_em_mat[:, 3:4] * v_em_mat[:, :3], F(0.0))
+            validate_radiance[:, 3] = np.where(v_trace, F(1.0), F(0.0))
+        else:
+            v_cone = dot(ray_dir, np.tile(sc.sun, (n, 1))) >= sc.cos_solar
+            validate_radiance[:, :3] = np.where((v_trace & ~v_occ & v_cone)[:, None], sc.sun_color, F(0.0))
+            validate_radiance[:, 3] = np.where(v_trace & (v_occ | v_cone), F(1.0), F(0.0))
         s_val = dict(radiance=np.where(established[:, None], validate_radiance, s_now["radiance"]),
                      random=np.where(established[:, None], r["random"], rnd),
                      sample_position=np.where(established[:, None], v_info_pos, s_now["sample_position"]),
@@ -243,8 +259,11 @@ def temporal_emissive_numpy(b, orc, frame_number, noise, previous, inp=None):
     eye = np.array(list((inp.view if inp is not None else b.view).world_position), F)
     view = normalize(eye - P)
     with np.errstate(all="ignore"):
-        out = shading(view, N, normalize(r["sample_position"][:, :3] - P), sc.bufs["materials"][material], r["radiance"], sc.ambient)
+        surface = sc.bufs["materials"][material]
+        out = shading(view, N, normalize(r["sample_position"][:, :3] - P), surface, r["radiance"], sc.ambient)
         out = out * r["w"][:, None]
+        if not emissive:                                                   # RENDER_EMISSIVE on the sun pipeline (light.rs:409-412)
+            out = out + F(255.0) * surface["emissive"][:, 3:4] * surface["emissive"][:, :3]
     # the invalidation scatter (:1092-1095): a rejected history zeroes the previous-SPATIAL record it was fetched from
     in_frame = (np.abs(pu - F(0.5)) <= F(0.5)) & (np.abs(pv - F(0.5)) <= F(0.5))
     scatter_targets = (pcy * W + pcx)[miss & in_frame]
@@ -457,3 +476,36 @@ def test_oracle_validation_scatter_equals_independent_numpy_restatement():
         assert same[background].all()
         stored = int(reset[~graze].sum())
     assert stored > 300                                                              # the doubled light reset every lit reservoir
+
+
+def test_oracle_sun_pass_with_history_and_validation_equals_independent_numpy_restatement():
+    """the same entry point specialised as the sun pipeline (sample_directional, no emissive walk, RENDER_EMISSIVE) on minimal.rs over
+    frames 2-7: history, M clamp, and the validation branch on frames 3 and 6 (direct_validate_interval = 3; frame 6 validates
+    established reservoirs)"""
+    W, H = 88, 60
+    b = Bench("minimal", W, H, taa=plugin.TAA_NONE, upscale_ratio=1.0, temporal_reuse=1, denoise=0, indirect_bounces=1,
+              emissive_spatial_reuse=0, indirect_spatial_reuse=0, max_temporal_reuse_count=6)
+    orc = b.oracle()
+    noise = plugin.load_noise()
+    validated = 0
+    for f in range(1, 8):
+        inp = b.inputs(f)
+        previous = orc.readback(L.OUT_RESERVOIR_0 + 0 + (f % 2)).copy()          # buffers [0, 1]: the sun pass's temporal pair (light.rs:518-546)
+        orc.render_frame(inp)
+        if f == 1:
+            continue
+        idx, packed, out, variance, graze, take, miss = temporal_emissive_numpy(b, orc, f, noise, previous, emissive=False)
+        written = orc.readback(L.OUT_RESERVOIR_0 + 0 + 1 - (f % 2)).reshape(-1)[idx]
+        clean = ~graze
+        assert clean.mean() > 0.9
+        for field in ("radiance", "random", "visible_position", "visible_normal", "sample_normal"):
+            same = (written[field] == packed[field]) if written[field].ndim == 1 else (written[field] == packed[field]).all(-1)
+            assert same[clean].mean() >= 0.99, (f, field, float(same[clean].mean()))
+        gc, _ = unpack_f16x2(written["reservoir"][:, 0]); wc, _ = unpack_f16x2(packed["reservoir"][:, 0])
+        assert (gc[clean] == wc[clean]).mean() >= 0.995, (f, float((gc[clean] == wc[clean]).mean()))
+        render = orc.readback(L.OUT_RENDER_DIRECT).astype(F).reshape(-1, 4)[idx]
+        d = ulps16(render[:, :3], out).max(-1)
+        assert (d[clean] <= 1).mean() >= 0.99, (f, float((d[clean] <= 1).mean()))
+        if f % 3 == 0:
+            validated += int((wc[clean] >= 4).sum()) if f == 6 else 0
+    assert validated > 500
