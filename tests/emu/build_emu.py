@@ -68,7 +68,12 @@ def build(force=False):
     deps = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(HOST, f) for f in os.listdir(HOST)] + \
            [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))] + \
            [os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__)]
-    if not force and not newer(LIB, deps) and not os.environ.get("HK_EMU_EXTRA"):
+    # the library on disk must have been built from the current sources AND with the current flags: a tuning-variant or sanitizer
+    # build (HK_EMU_EXTRA) left behind must not be mistaken for the default build by the next run
+    stamp = os.path.join(OUT, "flags.txt")
+    wanted = " ".join(FLAGS)
+    have = open(stamp).read() if os.path.exists(stamp) else None
+    if not force and not newer(LIB, deps) and have == wanted:
         return LIB
     objs, launches = [], 0
     for f in CU:
@@ -89,6 +94,7 @@ def build(force=False):
         subprocess.run([CXX] + FLAGS + ["-c", os.path.join(HOST, f), "-o", o], check=True)
         objs.append(o)
     subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs + (["-fsanitize=address"] if ASAN else []), check=True)
+    open(stamp, "w").write(wanted)
     print(f"emulator: {launches} launch sites converted -> {LIB}")
     return LIB
 
