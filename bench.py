@@ -56,7 +56,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md).  Started BEFORE the warm-up frames and left running through both
+    timed arms: spawning nvidia-smi takes hundreds of milliseconds of driver initialisation, which stalls kernel launches of every
+    process on the box — round 1 started it right before a 14 ms timed region at 8 GPUs and measured its own start-up.  Samples carry
+    host timestamps; `window(t0, t1)` summarises the ones taken under load."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -69,24 +72,32 @@ class ClockSampler:
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:      # first sample printed: start-up is over
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.15)
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+
+    def window(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm, mx, reasons = [], [], set()
-        for l in self.lines:
+        for t, l in self.lines:
+            if t < t0 or t > t1 + 0.11:
+                continue
             p = [x.strip() for x in l.split(",")]
             if len(p) < 9:
                 continue
@@ -98,7 +109,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "warm-up + both timed arms (sampler started before the warm-up; 100 ms period)"}
 
 
 GHOST = 36   # rows / columns a tile renders beyond its own rectangle (bevy_hikari_b200/csrc/context.cu GHOST_TEMPORAL)
@@ -211,7 +223,10 @@ def config_json(config, cfg, settings, world_size, gather="peer"):
                             "--equal-tiles), " + ("tiles stored by the tone-map kernel into rank 0's frame over NVLink (CUDA IPC) + a 4-byte "
                                                  "all-reduce as the frame barrier" if gather == "peer" else
                                                  "one all-gather of the tone-mapped tiles")) if world_size > 1 else "single GPU",
-            "l2": "per-frame working set (>1 GB of planes) exceeds L2; no explicit flush"}
+            "l2": ((f"per-frame working set ({876 * cfg['width'] * cfg['height'] / 1e6:.0f} MB of per-pixel planes) exceeds the 126 MB L2; no explicit flush")
+                   if 876 * cfg["width"] * cfg["height"] > 2 * 126e6 else
+                   (f"per-frame working set ({876 * cfg['width'] * cfg['height'] / 1e6:.0f} MB) fits L2 and is NOT flushed between frames: "
+                    "consecutive frames of a frame loop are L2-warm by nature; not a roofline configuration"))}
 
 
 # ================================================================================================== ours
@@ -339,45 +354,25 @@ def run_ours(args):
         return [float(v) for v in t.tolist()]
 
     W_, K = args.warmup, args.steps
+    dev.set_temporal_upscalers(False)        # the benchmarked path ends at the tone-mapped image (SmaaTu4x{ratio 1}, Taa::None)
 
     def frame_inputs(n):
         return plugin.make_frame_inputs(settings, n, view, pview, lights)
 
-    # ---------------------------------------------------------------- device-resident arm ("value")
-    dev.reset_temporal_state()
-    # per-kernel CUDA events inside the timed region at N = 1 (the roofline's kernel time is measured there); at N > 1 the
-    # 28 event records per frame are a visible share of a sub-millisecond frame and the per-kernel times come from the
-    # replay below only
-    dev.set_profiling(False, world_size == 1)
     inputs = [frame_inputs(n) for n in range(1, W_ + K + 1)]
-    for n in range(W_):
-        begin_frame()
-        dev.render_frame(inputs[n])
-        if world_size > 1:
-            gather_frame()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # long before any timed region (see ClockSampler)
+    barrier()
+    t_load_begin = time.time()
+
+    # ------------------------------------------------ replay 1: per-kernel times (every kernel bracketed with events, one sync per
+    # frame) -> which kernel dominates; outside every timed region
+    dev.set_profiling(False, True)
+    dev.set_profiling_kernel(-1)
+    dev.reset_temporal_state()
     kernel_ms = np.zeros(len(L.KERNEL_NAMES))
     launches = 0
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for n in range(W_, W_ + K):
-        begin_frame()
-        dev.render_frame(inputs[n])
-        if world_size > 1:
-            gather_frame()
-        # stats of the PREVIOUS frame would need a sync; collect per-kernel times after the loop from a replay below
-    e1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = reduce_max(e0.elapsed_time(e1))
-    ms_per_step = ms_total / K
-
-    # per-kernel times: same frames again (timed per frame, synchronised per frame so events can be read)
-    dev.set_profiling(False, True)
-    dev.reset_temporal_state()
     for n in range(W_ + K):
         dev.render_frame(inputs[n])
         if n >= W_:
@@ -386,8 +381,9 @@ def run_ours(args):
             launches += st.kernel_launches
     kernel_ms /= K
     launches_per_frame = launches // K + (1 if world_size > 1 else 0)
+    dominant = int(np.argmax(kernel_ms))
 
-    # exact ray counts of the timed frames: replay with the counting kernel variants
+    # ------------------------------------------------ replay 2: exact ray counts of the timed frames (counting kernel variants)
     dev.reset_temporal_state()
     dev.set_profiling(True, False)
     rays = np.zeros(3)
@@ -398,12 +394,44 @@ def run_ours(args):
             rays += np.array([st.primary_rays, st.tlas_rays, st.blas_rays], dtype=np.float64)
     rays = np.array(reduce_sum(list(rays)))
     light_rays = rays[1] + rays[2]
-    value = light_rays / (ms_total * 1e-3) / 1e6
+
+    # ---------------------------------------------------------------- device-resident arm ("value")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    frame_events = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+
+    def measure_value():
+        """W warm-up frames, then exactly K frames between barrier + synchronize; inside the timed region the only event records
+        are one per frame (per-frame times) and, at N = 1, the two that bracket the dominant kernel (hk_set_profiling_kernel)."""
+        dev.reset_temporal_state()
+        dev.set_profiling(False, False)
+        dev.set_profiling_kernel(dominant if world_size == 1 else -1)
+        frame_no[0] = 0
+        for n in range(W_):
+            begin_frame()
+            dev.render_frame(inputs[n])
+            if world_size > 1:
+                gather_frame()
+        if world_size == 1:
+            dev.set_profiling_kernel(dominant)   # restart the ring: only timed frames are averaged
+        barrier()
+        e0.record(stream)
+        for n in range(W_, W_ + K):
+            begin_frame()
+            dev.render_frame(inputs[n])
+            if world_size > 1:
+                gather_frame()
+            frame_events[n - W_].record(stream)
+        e1.record(stream)
+        barrier()
+        per_frame = [e0.elapsed_time(frame_events[0])] + [frame_events[i - 1].elapsed_time(frame_events[i]) for i in range(1, K)]
+        dom_live = None
+        if world_size == 1:
+            st = dev.stats()
+            dom_live = float(st.ms_kernel[dominant]) if st.timed_frames else None
+            dev.set_profiling_kernel(-1)
+        return reduce_max(e0.elapsed_time(e1)), per_frame, dom_live
 
     # ---------------------------------------------------------------- end-to-end arm ("e2e")
-    dev.set_profiling(False, False)
-    dev.reset_temporal_state()
-    dev.frame_counter = 0
     h2d = ctypes.sizeof(L.FrameInputs)
     # Presentation-loop form: frame n's tile is copied to pinned host memory on the context's copy stream while frame
     # n + 1 renders (hk_readback_async); the host sees every frame's result, one frame later.  Two pinned buffers alternate.
@@ -430,7 +458,7 @@ def run_ours(args):
             dev.run_frame(settings, view, pview, lights)
             if rank == 0 and not first:
                 stream.wait_event(copied)            # frame barrier n is ordered behind copy n - 1
-            dist.all_reduce(landed)
+            gather_frame()
             if rank == 0:
                 ready = torch.cuda.Event()
                 ready.record(stream)
@@ -449,22 +477,94 @@ def run_ours(args):
             dev.run_frame(settings, view, pview, lights)                      # host structs -> kernel parameters
             dev.readback_wait()                                               # frame n - 1 has landed in host memory
             dev.readback_async(L.OUT_TONE_MAPPED, host_bufs[n & 1], nbytes)   # D2H of this frame's tile, overlapping the next frame
+            if world_size > 1:
+                gather_frame()
 
         def e2e_finish():
             dev.readback_wait()                                               # the last frame's result too
-    for n in range(W_):
-        e2e_step(n, n == 0)
-    e2e_finish()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for n in range(K):
-        e2e_step(n, n == 0)
-    e2e_finish()
-    e1.record(stream)
-    barrier()
-    e2e_ms = reduce_max(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+
+    def measure_e2e():
+        dev.set_profiling(False, False)
+        dev.set_profiling_kernel(-1)
+        dev.reset_temporal_state()
+        dev.frame_counter = 0
+        frame_no[0] = 0
+        for n in range(W_):
+            e2e_step(n, n == 0)
+        e2e_finish()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for n in range(K):
+            e2e_step(n, n == 0)
+        e2e_finish()
+        e1.record(stream)
+        barrier()
+        return reduce_max(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+
+    # The two arms time the same K frames; the end-to-end one adds the read-back, which overlaps the next frame, so they must agree
+    # closely.  A disagreement beyond 15 % means one of them measured something else (round 1, 8 GPUs: 5x) — measure again, once,
+    # and say so.
+    attempts = []
+    for attempt in range(2):
+        ms_total, per_frame, dom_live = measure_value()
+        e2e_ms = measure_e2e()
+        attempts.append({"value_ms_per_step": round(ms_total / K, 5), "e2e_ms_per_step": round(e2e_ms / K, 5)})
+        if abs(ms_total - e2e_ms) <= 0.15 * min(ms_total, e2e_ms):
+            break
+    agreement = abs(ms_total - e2e_ms) / min(ms_total, e2e_ms)
+    ms_per_step = ms_total / K
+    value = light_rays / (ms_total * 1e-3) / 1e6
     e2e_value = light_rays / (e2e_ms * 1e-3) / 1e6
+    t_load_end = time.time()
+    if rank == 0:
+        sampler.stop()
+    clocks = sampler.window(t_load_begin, t_load_end) if rank == 0 else None
+
+    # ------------------------------------------------ N > 1: is the frame the ranks assembled the frame one GPU renders?
+    # Outside every timed region.  Frames 1..3 from zeroed state through the same tiles + frame assembly as the timed loop; rank 0
+    # reads the assembled frame, renders the same three frames unsharded on its own GPU and compares byte for byte (and with the
+    # hash committed in tests/golden/frame_hashes.json for this config and build, if there is one).
+    frame_check = None
+    if world_size > 1 and frame_targets and not args.no_frame_check:
+        import hashlib
+        dev.set_profiling(False, False)
+        dev.reset_temporal_state()
+        frame_no[0] = 0
+        CHECK_FRAMES = 3
+        for n in range(CHECK_FRAMES):
+            begin_frame()
+            dev.render_frame(inputs[n])
+            gather_frame()
+        barrier()
+        if rank == 0:
+            assembled = dev.frame_read(frame_targets[(frame_no[0] - 1) & 1])
+            frame_check = {"frames": CHECK_FRAMES, "assembled_sha256": hashlib.sha256(assembled.tobytes()).hexdigest()}
+            try:
+                full = plugin.HikariPlugin(W, H, cuda_device=local_rank)
+                full.upload_scene(world)
+                for n in range(CHECK_FRAMES):
+                    full.render_frame(inputs[n])
+                unsharded = full.readback(L.OUT_TONE_MAPPED)
+                full.close()
+                frame_check["unsharded_sha256"] = hashlib.sha256(unsharded.tobytes()).hexdigest()
+                frame_check["identical"] = bool(assembled.tobytes() == unsharded.tobytes())
+                if not frame_check["identical"]:
+                    frame_check["differing_pixels"] = int(np.any(assembled != unsharded, axis=-1).sum())
+            except Exception as e:       # e.g. not enough memory for an unsharded 8K context next to the tile
+                frame_check["unsharded_error"] = str(e)[:200]
+            stored = stored_frame_hash(args.config, CHECK_FRAMES)
+            if stored:
+                frame_check["stored_sha256"] = stored
+                frame_check["matches_stored"] = stored == frame_check["assembled_sha256"]
+        barrier()
+    elif world_size == 1 and args.print_frame_hash:
+        import hashlib
+        dev.set_profiling(False, False)
+        dev.reset_temporal_state()
+        for n in range(3):
+            dev.render_frame(inputs[n])
+        frame_check = {"frames": 3, "unsharded_sha256": hashlib.sha256(dev.readback(L.OUT_TONE_MAPPED).tobytes()).hexdigest()}
 
     # ------------------------------------------------ animated scene: cost of the per-frame scene half (not in `value`)
     # one instance moves -> previous_transform_system + prepare_instances on the host (TLAS, emissive BVH, alias tables;
@@ -498,7 +598,10 @@ def run_ours(args):
     peak, peak_kind = peaks()
     signals = 3 if settings.indirect_bounces else 2
     ran = [(kernel_ms[i], name) for i, name in enumerate(L.KERNEL_NAMES) if kernel_ms[i] > 0]
-    dom_ms, dom = max(ran)
+    dom = L.KERNEL_NAMES[dominant]
+    # N = 1: the dominant kernel's duration measured LIVE inside the timed region (mean over its K launches, 2 event records per
+    # frame); N > 1: from the per-kernel replay of the same frames on this rank
+    dom_ms = dom_live if dom_live else float(kernel_ms[dominant])
     rows_launched = {"gbuffer": 36, "direct": 36, "emissive": 36, "indirect": 36, "emissive_spatial": 16, "indirect_spatial": 16,
                      "demodulation": 15, "denoise_0": 7, "denoise_1": 3, "denoise_2": 1, "denoise_3": 0, "tone_mapping": 0}
     def launch_pixels(name):
@@ -533,7 +636,13 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(launches_per_frame * K),
         "kernel_ms": {name: round(float(kernel_ms[i]), 5) for i, name in enumerate(L.KERNEL_NAMES) if kernel_ms[i] > 0},
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+        "kernel_ms_source": "replay of the timed frames with every kernel bracketed by CUDA events (outside the timed region)",
+        "frame_ms": {"min": round(min(per_frame), 5), "median": round(float(np.median(per_frame)), 5), "max": round(max(per_frame), 5),
+                     "note": "per-frame CUDA-event times of the timed region on rank 0"},
+        "value_vs_e2e": {"relative_difference": round(agreement, 4), "within_15_percent": bool(agreement <= 0.15), "attempts": attempts},
+        "roofline": {"bound": "hbm", "kernel": dom, "kernel_ms": round(dom_ms, 5),
+                     "kernel_ms_source": "live, timed region" if dom_live else "replay",
+                     "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "frame": {"bytes_per_pixel": frame_bpp, "achieved": round(frame_achieved, 2),
@@ -542,6 +651,8 @@ def run_ours(args):
     }
     if scene_update:
         out["scene_update"] = scene_update
+    if frame_check:
+        out["frame_check"] = frame_check
     if world_size == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(args.config, seconds_budget=25.0)
     print(json.dumps(out), flush=True)
@@ -550,6 +661,16 @@ def run_ours(args):
 
 
 # ============================================================================================ CPU arms
+def stored_frame_hash(config, frames):
+    """sha256 of the tone-mapped frame `frames` of `config` rendered unsharded on one GPU with the default build, committed by
+    tools/record_frame_hashes (tests/golden/frame_hashes.json); None when there is none"""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "frame_hashes.json")) as f:
+            return json.load(f).get(f"{config}:frame{frames}")
+    except Exception:
+        return None
+
+
 def host_threads():
     """usable host cores: affinity mask, capped by the cgroup CPU quota (os.cpu_count() reports the whole machine)"""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -641,15 +762,35 @@ def cpu_baseline_sample(config, seconds_budget):
                       f"oracle = C++/OpenMP restatement of the reference WGSL; the reference (Rust+wgpu) cannot be built offline"}
 
 
+def reference_sample_size(config, W_, K, budget_s=150.0):
+    """The reference arm renders the TRUE configuration when W + K frames of it fit the time budget on this box's host cores;
+    otherwise the largest of 1/2, 1/4, 1/8 of the resolution (per axis) that does.  Estimated from one frame at 1/8 resolution
+    (cost per pixel is resolution independent for this path)."""
+    from bevy_hikari_b200 import plugin, scenes
+    cfg = scenes.CONFIGS[config]
+    W, H = cfg["width"], cfg["height"]
+    pw, ph = max(W // 8, 16), max(H // 8, 16)
+    orc, settings, view, pview, lights = oracle_for(config, pw, ph)
+    orc.render_frame(plugin.make_frame_inputs(settings, 1, view, pview, lights))
+    t0 = time.perf_counter()
+    orc.render_frame(plugin.make_frame_inputs(settings, 2, view, pview, lights))
+    per_pixel = (time.perf_counter() - t0) / (pw * ph)
+    orc.close()
+    for div in (1, 2, 4, 8):
+        w, h = W // div, H // div
+        if per_pixel * w * h * (W_ + K) <= budget_s or div == 8:
+            return w, h, div
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from bevy_hikari_b200 import plugin, scenes
+    from bevy_hikari_b200 import plugin, scenes       # host mirror only (libhikari_host.so): no CUDA library is mapped by this arm
     cfg = scenes.CONFIGS[args.config]
-    w, h = cfg["width"] // 4, cfg["height"] // 4
-    orc, settings, view, pview, lights = oracle_for(args.config, w, h)
     W_, K = args.warmup, args.steps
+    w, h, div = reference_sample_size(args.config, W_, K)
+    orc, settings, view, pview, lights = oracle_for(args.config, w, h)
     for n in range(1, W_ + 1):
         orc.render_frame(plugin.make_frame_inputs(settings, n, view, pview, lights))
     orc.stats()
@@ -657,20 +798,30 @@ def run_reference(args):
     t0 = time.perf_counter()
     for n in range(W_ + 1, W_ + K + 1):
         orc.render_frame(plugin.make_frame_inputs(settings, n, view, pview, lights))
+        st = orc.stats()
+        rays += st.tlas_rays + st.blas_rays
     dt = time.perf_counter() - t0
-    st = orc.stats()
-    rays = st.tlas_rays + st.blas_rays
     value = rays / dt / 1e6
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    sample = (f"each step = one frame of {args.config} at {w}x{h} (1/16 of the pixels; rays/pixel are resolution independent), "
-              f"CPU restatement of the reference WGSL (oracle/hk_oracle.cpp, OpenMP); the reference's own wgpu path needs "
-              f"rustc + a Vulkan ICD, neither exists offline")
+    full = div == 1
+    sample = ((f"each step = one frame of {args.config} at its full {w}x{h}" if full else
+               f"each step = one frame of {args.config} rendered at {w}x{h} (1/{div * div} of the configuration's {cfg['width']}x{cfg['height']} "
+               f"pixels, the largest size whose {W_ + K} frames fit the time budget on these cores; rays per pixel do not depend on resolution)") +
+              "; CPU restatement of the reference WGSL (oracle/hk_oracle.cpp, OpenMP) — the reference's own wgpu path needs rustc + a Vulkan "
+              "ICD, neither exists offline")
+    config = config_json(args.config, cfg, settings, world_size)
+    config["rendered_width"], config["rendered_height"], config["rendered_pixel_fraction"] = w, h, round(1.0 / (div * div), 6)
+    ms_step = dt / K * 1e3
     out = {"impl": "reference", "metric": "Mrays/s", "value": round(value, 4), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": K,
-           "warmup": W_, "ms_per_step": round(dt / K * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "warmup": W_, "ms_per_step": round(ms_step, 3),
+           "ms_per_step_note": ("full configuration" if full else f"for the {w}x{h} sample; x{div * div} for the configuration's pixel count"),
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32", "data": f"reference assets ({ASSET_OF[cfg['scene']]}) + blue-noise seed",
-           "config": config_json(args.config, cfg, settings, world_size),
+           "config": config,
            "cpu_baseline": {"value": round(value, 4), "unit": "Mrays/s", "cores": orc.threads, "kind": "port", "sample": sample},
-           "e2e": {"value": round(value, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "e2e": {"value": round(value, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "libraries": "oracle/libhk_oracle.so + bevy_hikari_b200/libhikari_host.so (scene preparation); the CUDA library is not loaded",
+           "mapped_cuda_library": any("libhikari_b200" in l for l in open("/proc/self/maps"))}
     print(json.dumps(out), flush=True)
 
 
@@ -685,6 +836,8 @@ def main():
     ap.add_argument("--equal-tiles", action="store_true", help="N > 1: equal grid of tiles instead of cost-balanced strips")
     ap.add_argument("--halo-margin", type=int, default=None,
                     help="N > 1: exact tiling under camera motion — ghost ring of 36 + M pixels and a halo pull after every frame")
+    ap.add_argument("--no-frame-check", action="store_true", help="N > 1: skip the assembled-frame == unsharded-frame check")
+    ap.add_argument("--print-frame-hash", action="store_true", help="N = 1: add the sha256 of frame 3 (for tests/golden/frame_hashes.json)")
     ap.add_argument("--lib", default=None, help="tuning: load this build of libhikari_b200.so (tools/build_variants.py) instead of the in-tree one")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = tiles stored straight into rank 0's frame over NVLink (CUDA IPC); nccl = all_gather of tiles")

@@ -7,7 +7,8 @@ import os
 from . import layout as L
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhikari_b200.so")   # the one product library; there is no fallback if it is missing
+LIB_PATH = os.path.join(HERE, "libhikari_b200.so")   # the product library (CUDA + C ABI); there is no fallback if it is missing
+HOST_LIB_PATH = os.path.join(HERE, "libhikari_host.so")   # the host mirror up to hikari_make_frame_inputs: pure CPU, no CUDA
 
 HK_OK = 0
 HK_ERR_INVALID_ARGUMENT, HK_ERR_CUDA, HK_ERR_NOT_READY, HK_ERR_OUT_OF_MEMORY, HK_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
@@ -61,6 +62,7 @@ SYMBOLS = {
     "hk_sync": (_I, [_P]),
     "hk_trace_rays": (_I, [_P, _P, _SZ, _P]),
     "hk_set_profiling": (_I, [_P, _I, _I]),
+    "hk_set_profiling_kernel": (_I, [_P, _I]),
     "hk_set_keep_intermediates": (_I, [_P, _I]),
     "hk_get_stats": (_I, [_P, C.POINTER(L.FrameStats)]),
     "hk_band_rows": (_I, [_P, C.POINTER(_U32), C.POINTER(_U32)]),
@@ -102,6 +104,23 @@ SYMBOLS = {
 }
 
 _lib = None
+_host_lib = None
+# symbols of include/hikari_host.h that live in libhikari_host.so (no CUDA behind them)
+HOST_ONLY = [n for n in SYMBOLS if n.startswith("hikari_") and not n.startswith("hikari_plugin_")]
+
+
+def host_lib():
+    """libhikari_host.so alone: scene preparation, settings, frame uniforms.  CPU-only consumers (bench.py --impl reference,
+    the oracle's tests) use this and never map the CUDA library."""
+    global _host_lib
+    if _host_lib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError(f"{HOST_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _host_lib = C.CDLL(HOST_LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name in HOST_ONLY:
+            fn = getattr(_host_lib, name)
+            fn.restype, fn.argtypes = SYMBOLS[name]
+    return _host_lib
 
 
 def lib():
@@ -110,6 +129,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(nvcc, sm_100a). There is no fallback path.")
+        host_lib()                 # dependency of the CUDA library (also found through its $ORIGIN rpath)
         _lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(_lib, name)   # AttributeError if the library does not export a declared symbol

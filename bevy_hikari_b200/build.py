@@ -1,5 +1,10 @@
-"""Build libhikari_b200.so in-tree: hand-written CUDA for sm_100a + the C++ host mirror, linked into one shared
-library that exports the C ABI of include/hikari_b200.h and include/hikari_host.h.
+"""Build the two product libraries in-tree:
+
+  libhikari_host.so   the C++ host mirror up to hikari_make_frame_inputs (scene preparation, settings, frame uniforms):
+                      pure CPU, no CUDA dependency — what a CPU-only consumer (the reference arm of bench.py) loads
+  libhikari_b200.so   hand-written CUDA for sm_100a + the nodes / HikariPlugin that call it; exports the C ABI of
+                      include/hikari_b200.h and, through its dependency on libhikari_host.so ($ORIGIN rpath), every symbol
+                      of include/hikari_host.h
 
 nvcc cross-compiles without a GPU.  Flags that matter:
   -gencode arch=compute_100a,code=sm_100a   B200 only, no PTX fallback for other architectures
@@ -7,6 +12,9 @@ nvcc cross-compiles without a GPU.  Flags that matter:
                                             include/hk_math.h, which is what makes device results comparable bit-for-bit
                                             with the CPU oracle
   -lineinfo                                 ncu source page maps to these files
+
+A stamp (_build/flags.txt) records the full flag list of the objects on disk: a tuning build (HK_NVCC_EXTRA=...) left
+behind is rebuilt by the next default build instead of being mistaken for it.
 """
 import os
 import subprocess
@@ -18,14 +26,16 @@ ROOT = os.path.dirname(HERE)
 INC = os.path.join(ROOT, "include")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libhikari_b200.so")
+HOST_LIB = os.path.join(HERE, "libhikari_host.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 
 CU = ["csrc/context.cu", "csrc/kernels_light.cu", "csrc/kernels_post.cu", "csrc/kernels_upscale.cu"]
-CPP = ["host/hikari.cpp", "host/hikari_capi.cpp"]
-HEADERS = ["csrc/hk_device.cuh", "csrc/hk_kernels.h", "host/hikari.hpp", "../include/hk_math.h", "../include/hk_layout.h",
-           "../include/hikari_b200.h", "../include/hikari_host.h"]
+CPP_HOST = ["host/hikari.cpp", "host/hikari_capi.cpp"]                     # -> libhikari_host.so
+CPP_PLUGIN = ["host/hikari_plugin.cpp", "host/hikari_plugin_capi.cpp"]     # -> libhikari_b200.so (they call hk_*)
+HEADERS = ["csrc/hk_device.cuh", "csrc/hk_kernels.h", "host/hikari.hpp", "host/hikari_settings_convert.hpp",
+           "../include/hk_math.h", "../include/hk_layout.h", "../include/hikari_b200.h", "../include/hikari_host.h"]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-I", INC, "-I", os.path.join(HERE, "csrc")]
@@ -46,37 +56,47 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
-def build(force=False, verbose=False, ptxas_info=False):
-    os.makedirs(OBJ, exist_ok=True)
+def build(force=False, verbose=False, ptxas_info=False, out=None):
+    """Builds both libraries; returns the path of libhikari_b200.so.  `out`: write the CUDA library there instead (tuning
+    variants, tools/build_variants.py) — its objects go to a scratch directory and the default build is left alone."""
     extra_env = os.environ.get("HK_NVCC_EXTRA", "").split()   # tuning experiments, e.g. -DHK_MINB_INDIRECT=5
-    if extra_env:
+    obj_dir = OBJ if out is None else os.path.join(OBJ, "variant_" + os.path.splitext(os.path.basename(out))[0])
+    lib = LIB if out is None else out
+    os.makedirs(obj_dir, exist_ok=True)
+    stamp = os.path.join(obj_dir, "flags.txt")
+    wanted = " ".join(NVCC_FLAGS + extra_env + ["|"] + CXX_FLAGS)
+    have = open(stamp).read() if os.path.exists(stamp) else None
+    if have != wanted:
         force = True
     headers = [os.path.join(HERE, h) for h in HEADERS]
-    jobs = []
-    objs = []
+    jobs, cuda_objs, host_objs = [], [], []
     for src in CU:
         s = os.path.join(HERE, src)
-        o = os.path.join(OBJ, os.path.basename(src) + ".o")
-        objs.append(o)
+        o = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        cuda_objs.append(o)
         if force or _newer(o, [s] + headers):
             extra = (["-Xptxas", "-v"] if ptxas_info else []) + extra_env
             jobs.append([NVCC] + NVCC_FLAGS + extra + ["-c", s, "-o", o])
-    for src in CPP:
+    for src in CPP_HOST + CPP_PLUGIN:
         s = os.path.join(HERE, src)
-        o = os.path.join(OBJ, os.path.basename(src) + ".o")
-        objs.append(o)
+        o = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        (host_objs if src in CPP_HOST else cuda_objs).append(o)
         if force or _newer(o, [s] + headers):
             jobs.append([CXX] + CXX_FLAGS + ["-c", s, "-o", o])
     logs = []
     if jobs:
         with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
             logs = list(ex.map(_run, jobs))
-    if jobs or not os.path.exists(LIB):
-        logs.append(_run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                                "-cudart", "static", "-Xcompiler", "-fPIC"]))
+    if jobs or not os.path.exists(HOST_LIB):
+        logs.append(_run([CXX, "-shared", "-o", HOST_LIB] + host_objs))
+    if jobs or not os.path.exists(lib):
+        logs.append(_run([NVCC, "-shared", "-o", lib] + cuda_objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+                                                                      "-Xcompiler", "-fPIC", "-L", HERE, "-lhikari_host",
+                                                                      "-Xlinker", "-rpath,$ORIGIN", "-Xlinker", "-rpath," + HERE]))
+    open(stamp, "w").write(wanted)
     if verbose or ptxas_info:
         print("\n".join(l for l in logs if l.strip()))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
+#include <set>
 #include <string>
 #include <unordered_set>
 #include <vector>
@@ -42,10 +44,14 @@ struct hk_context {
     std::vector<void*> scene_allocations;  // scene buffers: meshes, BLAS nodes, materials, textures
     struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[8];   // scene buffers rewritten by hk_scene_update_instances (grow-only)
     bool mesh_boxes_match = false;         // BLAS half of DeviceScene::leaf_boxes_match
-    uint32_t scene_material_count = 0, scene_asset_node_count = 0, scene_primitive_count = 0;
+    uint32_t scene_material_count = 0, scene_asset_node_count = 0, scene_primitive_count = 0, scene_vertex_count = 0, scene_texture_count = 0;
+    std::vector<hk_node> host_asset_nodes;                 // copy of the uploaded BLAS records: index validation of later instance updates
+    std::vector<uint32_t> host_primitive_vertex_index;     // 3 per primitive (hk_primitive_vertex::index), same purpose
+    std::set<std::array<uint32_t, 4>> mesh_range_checked;   // hk_mesh_index values whose leaves have been validated
     Planes planes{};
     DeviceScene scene{};
     bool scene_ready = false, noise_ready = false;
+    bool planes_ready = false;         // allocate_planes completed: every pointer of `planes` is valid
     bool full_frame = true;            // the context owns the whole frame (no tile): upscale_ratio > 1 and the upscalers need it
     int last_render_w = 0, last_render_h = 0; bool last_smaa = false, last_upscalers = false, last_fsr = false; uint32_t last_number = 0;   // of the last frame, for read-back sizes
     int gbuffer_current = 0;           // index of the "current" position / velocity_uv planes; toggled by every prepass
@@ -66,6 +72,13 @@ struct hk_context {
     float trace_ms = 0.0f;            // kernel time of the last hk_trace_rays (ms_kernel[HK_K_TRACE_RAYS])
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[HK_K_COUNT][2] = {};   // per-kernel begin/end
+    // hk_set_profiling_kernel: only ONE kernel is bracketed with events (2 records per frame instead of 28 + 4), into a ring, so
+    // that a timed region can carry the dominant kernel's live duration without synchronising per frame or perturbing the frame
+    int time_only = -1;                    // -1 = every kernel (time_passes), else the HK_K_* index
+    static const int RING = 256;
+    cudaEvent_t ring[RING][2] = {};
+    uint32_t ring_frames = 0;              // frames recorded since hk_set_profiling_kernel
+    bool ring_hit = false;                 // the selected kernel ran in the current frame
     bool kran[HK_K_COUNT] = {};
     hk_frame_stats stats{};
     uint32_t launches = 0;
@@ -106,7 +119,15 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
                            uint32_t row_begin, uint32_t row_end) {
     if (width == 0 || height == 0 || row_begin >= row_end || row_end > height || col_begin >= col_end || col_end > width)
         return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "bad size or tile rectangle");
+    // Everything derived from the old planes dies with them: the read-back geometry of the last frame, the frame target
+    // (validated against the old width) and the "planes are usable" flag, which only a complete allocation sets again —
+    // a cudaMalloc failing half-way leaves the context refusing to render instead of holding dangling pointers.
+    ctx->planes_ready = false;
+    ctx->last_render_w = ctx->last_render_h = 0; ctx->last_number = 0;
+    ctx->last_smaa = ctx->last_upscalers = ctx->last_fsr = false;
+    ctx->frame_target = nullptr; ctx->frame_pitch = 0;
     free_list(ctx->allocations);
+    ctx->planes = Planes{};
     Band b;
     b.W = (int)width; b.H = (int)height; b.r0 = (int)row_begin; b.r1 = (int)row_end; b.cx0 = (int)col_begin; b.cx1 = (int)col_end;
     const int ghost = GHOST_TEMPORAL + ctx->motion_margin;
@@ -162,6 +183,7 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
         HK_CUDA(alloc_plane(ctx, &p.taa_output[1], 4 * n, L));
     }
     if (ctx->full_frame) HK_CUDA(alloc_plane(ctx, &p.upscale_sharpen_output, n, L));   // FSR RCAS result (Upscale::Fsr1)
+    ctx->planes_ready = true;
     return HK_OK;
 }
 
@@ -268,6 +290,8 @@ void hk_context_destroy(hk_context* ctx) {
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < HK_K_COUNT; ++i)
         for (int j = 0; j < 2; ++j) if (ctx->kev[i][j]) cudaEventDestroy(ctx->kev[i][j]);
+    for (int i = 0; i < hk_context::RING; ++i)
+        for (int j = 0; j < 2; ++j) if (ctx->ring[i][j]) cudaEventDestroy(ctx->ring[i][j]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -278,6 +302,12 @@ int hk_context_resize(hk_context* ctx, uint32_t width, uint32_t height, uint32_t
 int hk_context_resize_tile(hk_context* ctx, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
                            uint32_t row_begin, uint32_t row_end) {
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    // The reference re-allocates (and zeroes) the reservoirs only when size.x * size.y changes (light.rs:342-363); a host that
+    // calls resize every frame (prepare_light_textures runs every frame) must not lose its temporal state or pay ~100 cudaMallocs.
+    const Band& b = ctx->band;
+    if (ctx->planes_ready && (int)width == b.W && (int)height == b.H && (int)col_begin == b.cx0 && (int)col_end == b.cx1 &&
+        (int)row_begin == b.r0 && (int)row_end == b.r1)
+        return HK_OK;
     HK_CUDA(cudaSetDevice(ctx->device));
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->copy_stream) HK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
@@ -287,6 +317,7 @@ int hk_context_resize_tile(hk_context* ctx, uint32_t width, uint32_t height, uin
 
 int hk_reset_temporal_state(hk_context* ctx) {
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    if (!ctx->planes_ready) return set_error(ctx, HK_ERR_NOT_READY, "per-pixel planes are not allocated (a resize failed)");
     HK_CUDA(cudaSetDevice(ctx->device));
     for (int r = 0; r < 10; ++r)
         for (int q = 0; q < 4; ++q) HK_CUDA(cudaMemsetAsync(ctx->planes.reservoir[r].q[q], 0, ctx->band_pixels * sizeof(uint4), ctx->stream));
@@ -338,11 +369,65 @@ static int upload_instances(hk_context* ctx, const hk_scene_desc* s, DeviceScene
     if ((s->instance_count && !s->instances) || (s->instance_node_count && !s->instance_nodes) ||
         (s->emissive_node_count && !s->emissive_nodes) || (s->emissive_count && !s->emissives) || (s->alias_count && !s->alias_table))
         return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "scene buffer pointer is NULL with a non-zero count");
-    // validate indices once so that kernels can skip bounds checks
+    // Validate every index the kernels follow, once, so that they can skip bounds checks (wgpu's robust buffer access would clamp
+    // a bad index; here a malformed host buffer is refused instead of read out of bounds).
     for (uint32_t i = 0; i < s->instance_count; ++i) {
         const hk_instance& in = s->instances[i];
         if (in.material >= material_count || (uint64_t)in.mesh.node_offset + in.mesh.node_count > ctx->scene_asset_node_count)
             return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "instance references a material / node range out of bounds");
+        if (in.mesh.primitive > ctx->scene_primitive_count || in.mesh.vertex > ctx->scene_vertex_count)
+            return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "instance references a primitive / vertex range out of bounds");
+        // every leaf of the instance's BLAS must name a primitive inside the primitive buffer, and every link a record of its range
+        const std::array<uint32_t, 4> mesh_key = {in.mesh.vertex, in.mesh.primitive, in.mesh.node_offset, in.mesh.node_count};
+        if (!ctx->mesh_range_checked.count(mesh_key)) {
+            const std::vector<hk_node>& nodes = ctx->host_asset_nodes;
+            for (uint32_t k = 0; k < in.mesh.node_count; ++k) {
+                const hk_node& nd = nodes[in.mesh.node_offset + k];
+                if (nd.entry_index >= 0x80000000u) {
+                    const uint64_t pid = (uint64_t)in.mesh.primitive + (nd.entry_index - 0x80000000u);
+                    if (pid >= ctx->scene_primitive_count)
+                        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "BLAS leaf references a primitive out of bounds");
+                    const uint32_t* vi = &ctx->host_primitive_vertex_index[3 * pid];
+                    for (int c = 0; c < 3; ++c)
+                        if ((uint64_t)in.mesh.vertex + vi[c] >= ctx->scene_vertex_count)
+                            return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "primitive references a vertex out of bounds");
+                } else if (nd.entry_index > in.mesh.node_count) {
+                    return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "BLAS entry link out of its mesh's node range");
+                }
+            }
+            ctx->mesh_range_checked.insert(mesh_key);
+        }
+    }
+    if (new_materials && ctx->scene_texture_count != 0xFFFFFFFFu) {
+        for (uint32_t i = 0; i < s->material_count; ++i) {
+            const hk_material& m = s->materials[i];
+            const uint32_t ids[5] = {m.base_color_texture, m.emissive_texture, m.metallic_roughness_texture, m.normal_map_texture, m.occlusion_texture};
+            for (uint32_t id : ids)
+                if (id != 0xFFFFFFFFu && id >= ctx->scene_texture_count)
+                    return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "material references a texture out of bounds");
+        }
+    }
+    for (uint32_t i = 0; i < s->instance_node_count; ++i) {
+        const hk_node& nd = s->instance_nodes[i];
+        if (nd.entry_index >= 0x80000000u) {
+            if (nd.entry_index - 0x80000000u >= s->instance_count)
+                return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "TLAS leaf references an instance out of bounds");
+        }
+    }
+    for (uint32_t i = 0; i < s->emissive_node_count; ++i) {
+        const hk_node& nd = s->emissive_nodes[i];
+        if (nd.entry_index >= 0x80000000u && nd.entry_index - 0x80000000u >= s->emissive_count)
+            return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "emissive BVH leaf references an emissive out of bounds");
+    }
+    for (uint32_t i = 0; i < s->emissive_count; ++i) {
+        const hk_emissive& em = s->emissives[i];
+        if (em.instance >= s->instance_count || (uint64_t)em.alias_table_offset + em.alias_table_count > s->alias_count || em.alias_table_count == 0)
+            return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "emissive references an instance / alias-table slice out of bounds");
+        // alias entries index triangles of the emissive instance's mesh
+        const hk_instance& ei = s->instances[em.instance];
+        for (uint32_t k = 0; k < em.alias_table_count; ++k)
+            if ((uint64_t)ei.mesh.primitive + s->alias_table[em.alias_table_offset + k].index >= ctx->scene_primitive_count)
+                return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "alias-table entry references a primitive out of bounds");
     }
     // Does every leaf record sit right behind a navigator whose box is the shape's own AABB?  (true for bvh 0.7.1's
     // flatten_custom, which is what the reference uploads; then the kernels skip the re-derived leaf box test.)
@@ -425,6 +510,15 @@ int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
     ctx->scene_material_count = 0;
     ctx->scene_asset_node_count = s->asset_node_count;
     ctx->scene_primitive_count = s->primitive_count;
+    ctx->scene_vertex_count = s->vertex_count;
+    ctx->scene_texture_count = s->texture_count;
+    ctx->host_asset_nodes.assign(s->asset_nodes, s->asset_nodes + s->asset_node_count);
+    ctx->mesh_range_checked.clear();
+    ctx->host_primitive_vertex_index.resize(3 * (size_t)s->primitive_count);
+    for (uint32_t i = 0; i < s->primitive_count; ++i)
+        for (int c = 0; c < 3; ++c) ctx->host_primitive_vertex_index[3 * (size_t)i + c] = s->primitives[i].vertices[c].index;
+    // primitives index vertices relative to their mesh's vertex base: the largest index of each mesh is checked per instance
+    // below through mesh.vertex + index < vertex_count for the primitives of its leaves
     DeviceScene d{};
     HK_CUDA(upload(ctx, &d.vertices, s->vertices, s->vertex_count));
     HK_CUDA(upload(ctx, &d.primitives, s->primitives, s->primitive_count));
@@ -499,6 +593,7 @@ int hk_set_noise(hk_context* ctx, const uint8_t* rgba) {
 static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
     if (!ctx || !in) return HK_ERR_INVALID_ARGUMENT;
     if (!ctx->scene_ready || !ctx->noise_ready) return set_error(ctx, HK_ERR_NOT_READY, "scene or noise not uploaded");
+    if (!ctx->planes_ready) return set_error(ctx, HK_ERR_NOT_READY, "per-pixel planes are not allocated (a resize failed)");
     const bool ratio1 = in->frame.upscale_ratio == 1.0f;
     if (!(in->frame.upscale_ratio >= 1.0f && in->frame.upscale_ratio <= 2.0f))
         return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "upscale_ratio must be in [1, 2] (Upscale::ratio clamps, lib.rs:501-505)");
@@ -579,9 +674,15 @@ struct KernelTimer {  // brackets one launch with events when pass timing is on
     hk_context* c; int k;
     KernelTimer(hk_context* ctx, int kernel) : c(ctx), k(kernel) {
         c->launches += 1;
-        if (c->time_passes) { cudaEventRecord(c->kev[k][0], c->stream); c->kran[k] = true; }
+        if (c->time_only >= 0) {
+            if (c->time_only == k && c->ring[0][0]) { cudaEventRecord(c->ring[c->ring_frames % hk_context::RING][0], c->stream); c->ring_hit = true; }
+        } else if (c->time_passes) { cudaEventRecord(c->kev[k][0], c->stream); c->kran[k] = true; }
     }
-    ~KernelTimer() { if (c->time_passes) cudaEventRecord(c->kev[k][1], c->stream); }
+    ~KernelTimer() {
+        if (c->time_only >= 0) {
+            if (c->time_only == k && c->ring[0][0]) cudaEventRecord(c->ring[c->ring_frames % hk_context::RING][1], c->stream);
+        } else if (c->time_passes) cudaEventRecord(c->kev[k][1], c->stream);
+    }
 };
 
 static int run_prepass(hk_context* ctx, KParams& P) {
@@ -687,7 +788,8 @@ int hk_render_frame(hk_context* ctx, const hk_frame_inputs* in) {
     KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
     ctx->launches = 0;
     for (int i = 0; i < HK_K_COUNT; ++i) ctx->kran[i] = false;
-    const bool t = ctx->time_passes;
+    ctx->ring_hit = false;
+    const bool t = ctx->time_passes && ctx->time_only < 0;
     if (ctx->count_rays) HK_CUDA(cudaMemsetAsync(ctx->counters, 0, sizeof(Counters), ctx->stream));
     if (t) cudaEventRecord(ctx->ev[0], ctx->stream);
     rc = run_prepass(ctx, P); if (rc) return rc;
@@ -696,6 +798,7 @@ int hk_render_frame(hk_context* ctx, const hk_frame_inputs* in) {
     if (t) cudaEventRecord(ctx->ev[2], ctx->stream);
     rc = run_post(ctx, P, true); if (rc) return rc;
     if (t) cudaEventRecord(ctx->ev[3], ctx->stream);
+    if (ctx->ring_hit) ctx->ring_frames += 1;
     return HK_OK;
 }
 
@@ -711,6 +814,16 @@ int hk_set_profiling(hk_context* ctx, int count_rays, int time_passes) {
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;
     ctx->count_rays = count_rays != 0;
     ctx->time_passes = time_passes != 0;
+    return HK_OK;
+}
+int hk_set_profiling_kernel(hk_context* ctx, int kernel) {
+    if (!ctx || kernel >= HK_K_COUNT) return HK_ERR_INVALID_ARGUMENT;
+    HK_CUDA(cudaSetDevice(ctx->device));
+    ctx->time_only = kernel < 0 ? -1 : kernel;
+    ctx->ring_frames = 0;
+    if (kernel >= 0 && !ctx->ring[0][0])
+        for (int i = 0; i < hk_context::RING; ++i)
+            for (int j = 0; j < 2; ++j) HK_CUDA(cudaEventCreate(&ctx->ring[i][j]));
     return HK_OK;
 }
 int hk_set_keep_intermediates(hk_context* ctx, int keep) {
@@ -729,7 +842,13 @@ int hk_get_stats(hk_context* ctx, hk_frame_stats* out) {
         HK_CUDA(cudaMemcpy(&h, ctx->counters, sizeof(h), cudaMemcpyDeviceToHost));
         out->primary_rays = h.primary; out->tlas_rays = h.tlas; out->blas_rays = h.blas;
     }
-    if (ctx->time_passes) {
+    if (ctx->time_only >= 0) {   // mean live duration of the one selected kernel over the frames recorded in the ring
+        const uint32_t n = ctx->ring_frames < (uint32_t)hk_context::RING ? ctx->ring_frames : (uint32_t)hk_context::RING;
+        double sum = 0.0;
+        for (uint32_t i = 0; i < n; ++i) { float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ring[i][0], ctx->ring[i][1]); sum += ms; }
+        if (n) out->ms_kernel[ctx->time_only] = (float)(sum / n);
+        out->timed_frames = n;
+    } else if (ctx->time_passes) {
         cudaEventElapsedTime(&out->ms_prepass, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&out->ms_light, ctx->ev[1], ctx->ev[2]);
         cudaEventElapsedTime(&out->ms_post_process, ctx->ev[2], ctx->ev[3]);
@@ -779,6 +898,7 @@ __global__ void k_scatter_reservoir(ReservoirPlanes b, Band band, size_t n, cons
 // rectangle (width x height, in pixels) that is transferred and the row pitch of the plane in pixels.
 struct PlaneView { void* ptr; size_t bpp, w, h, pitch; };
 static bool plane_view(hk_context* ctx, int which, PlaneView* v) {
+    if (!ctx->planes_ready) return false;
     const Planes& p = ctx->planes;
     const Band& b = ctx->band;
     const size_t ow = (size_t)(b.cx1 - b.cx0), oh = (size_t)(b.r1 - b.r0);
@@ -846,6 +966,7 @@ int hk_output_extent(hk_context* ctx, int which, uint32_t* width, uint32_t* heig
 static int transfer(hk_context* ctx, int which, void* host, size_t bytes, bool to_host) {
     if (!ctx || !host) return HK_ERR_INVALID_ARGUMENT;
     HK_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->planes_ready) return set_error(ctx, HK_ERR_NOT_READY, "per-pixel planes are not allocated (a resize failed)");
     if (which >= HK_OUT_RESERVOIR_0 && which < HK_OUT_RESERVOIR_0 + 10) {
         Band rb = ctx->band;   // rectangle of the reservoir buffer in render space
         if (ctx->last_render_w != 0 && (ctx->last_render_w != rb.W || ctx->last_render_h != rb.H)) {

@@ -1,7 +1,9 @@
 // hikari.hpp — host side of the drop-in, in C++ because the reference's host language (Rust) is not available in
 // this image.  It mirrors the reference's plugin surface for the hot path — same type names, same field names,
 // same defaults, same error behaviour — and sits strictly ABOVE the C ABI of include/hikari_b200.h: nothing in
-// here touches CUDA; it only prepares the bytes the C ABI takes and calls hk_*().
+// here touches CUDA; it only prepares the bytes the C ABI takes and calls hk_*().  Two libraries: libhikari_host.so holds
+// everything up to and including make_frame_inputs (pure CPU, no CUDA dependency); the nodes and HikariPlugin, which call
+// hk_*(), are linked into libhikari_b200.so (hikari_plugin.cpp), which depends on libhikari_host.so.
 //
 //   hikari::HikariSettings / Taa / Upscale / HikariUniversalSettings      src/lib.rs:372-513
 //   hikari::graph::NAME, graph::node::*                                   src/lib.rs:43-51
@@ -207,9 +209,14 @@ public:
     int run_frame(const HikariSettings& settings, const ViewInputs& view);
     hk_context* context() const { return ctx_; }
     FrameCounter counter;
-    // run the temporal upscalers after tone mapping (smaa_tu4x / taa_jasmine as `settings` select them,
-    // post_process.rs:1236-1277).  Off by default: the sharded / benchmarked path ends at the tone-mapped image.
-    bool temporal_upscalers = false;
+    // Run the temporal upscalers after tone mapping — smaa_tu4x (+ extrapolate) under Upscale::SmaaTu4x, taa_jasmine under
+    // Taa::Jasmine, FSR1 EASU + RCAS under Upscale::Fsr1 — exactly when `settings` select them, as PostProcessNode::run does
+    // (post_process.rs:1236-1308).  On by default: HikariSettings::default() then gives the reference's default pipeline end to
+    // end.  A caller that ends the path at the tone-mapped image (the sharded benchmark; SURVEY 8(d) runs SmaaTu4x{ratio 1}
+    // without the upscale passes) sets it to false; run_frame then also drops the prepass jitter those passes would resolve.
+    // Tiles: the upscalers need hk_context_enable_tile_upscalers + a motion margin (HK_ERR_UNSUPPORTED otherwise), and
+    // upscale ratios above 1 / FSR1 need a full-frame context.
+    bool temporal_upscalers = true;
     std::string last_error() const;
 
 private:

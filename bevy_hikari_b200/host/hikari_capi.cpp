@@ -7,27 +7,7 @@
 
 using namespace hikari;
 
-static HikariSettings to_cpp(const hikari_settings* s) {
-    HikariSettings r;
-    r.direct_validate_interval = s->direct_validate_interval;
-    r.emissive_validate_interval = s->emissive_validate_interval;
-    r.max_temporal_reuse_count = s->max_temporal_reuse_count;
-    r.max_spatial_reuse_count = s->max_spatial_reuse_count;
-    r.max_reservoir_lifetime = s->max_reservoir_lifetime;
-    r.solar_angle = s->solar_angle;
-    r.indirect_bounces = s->indirect_bounces;
-    r.max_indirect_luminance = s->max_indirect_luminance;
-    for (int i = 0; i < 4; ++i) r.clear_color[i] = s->clear_color[i];
-    r.temporal_reuse = s->temporal_reuse != 0;
-    r.emissive_spatial_reuse = s->emissive_spatial_reuse != 0;
-    r.indirect_spatial_reuse = s->indirect_spatial_reuse != 0;
-    r.denoise = s->denoise != 0;
-    r.taa = s->taa == HIKARI_TAA_NONE ? Taa::None : Taa::Jasmine;
-    r.upscale.kind = s->upscale_kind == HIKARI_UPSCALE_FSR1 ? Upscale::Fsr1 : Upscale::SmaaTu4x;
-    r.upscale.ratio_value = s->upscale_ratio;
-    r.upscale.sharpness_value = s->upscale_sharpness;
-    return r;
-}
+#include "hikari_settings_convert.hpp"
 
 extern "C" {
 
@@ -112,30 +92,5 @@ int hikari_world_mesh_error(hikari_world* w, uint32_t mesh) {
     const auto& e = W(w)->mesh_errors();
     return mesh < e.size() ? (int)e[mesh] : -1;
 }
-
-// ---------------------------------------------------------------------------------------------- plugin
-hikari_plugin* hikari_plugin_create(void) { return reinterpret_cast<hikari_plugin*>(new HikariPlugin()); }
-void hikari_plugin_destroy(hikari_plugin* p) { delete reinterpret_cast<HikariPlugin*>(p); }
-static HikariPlugin* P(hikari_plugin* p) { return reinterpret_cast<HikariPlugin*>(p); }
-int hikari_plugin_build(hikari_plugin* p, int cuda_device, uint32_t width, uint32_t height, uint32_t row_begin,
-                        uint32_t row_end, const uint8_t* noise, void* cuda_stream) {
-    return P(p)->build(cuda_device, width, height, row_begin, row_end, noise, cuda_stream);
-}
-int hikari_plugin_build_tile(hikari_plugin* p, int cuda_device, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
-                             uint32_t row_begin, uint32_t row_end, const uint8_t* noise, void* cuda_stream) {
-    return P(p)->build_tile(cuda_device, width, height, col_begin, col_end, row_begin, row_end, noise, cuda_stream);
-}
-int hikari_plugin_upload_scene(hikari_plugin* p, hikari_world* w) { return P(p)->upload_scene(*W(w)); }
-int hikari_plugin_update_instances(hikari_plugin* p, hikari_world* w) { return P(p)->update_instances(*W(w)); }
-int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk_view* view,
-                            const hk_previous_view* previous_view, const hk_lights* lights) {
-    ViewInputs v;
-    v.view = *view; v.previous_view = *previous_view; v.lights = *lights;
-    return P(p)->run_frame(to_cpp(s), v);
-}
-hk_context* hikari_plugin_context(hikari_plugin* p) { return P(p)->context(); }
-uint64_t hikari_plugin_frame_counter(hikari_plugin* p) { return P(p)->counter.value; }
-void hikari_plugin_set_frame_counter(hikari_plugin* p, uint64_t v) { P(p)->counter.value = (size_t)v; }
-void hikari_plugin_set_temporal_upscalers(hikari_plugin* p, int enabled) { P(p)->temporal_upscalers = enabled != 0; }
 
 }  // extern "C"

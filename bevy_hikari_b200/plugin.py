@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _ffi
 from . import layout as L
-from ._ffi import Settings, check, lib
+from ._ffi import Settings, check, host_lib, lib
 
 TAA_JASMINE, TAA_NONE = 0, 1
 UPSCALE_FSR1, UPSCALE_SMAA_TU4X = 0, 1
@@ -16,13 +16,13 @@ NOISE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 
 
 def graph_name():
-    return lib().hikari_graph_name().decode()
+    return host_lib().hikari_graph_name().decode()
 
 
 def HikariSettings(**overrides):
     """HikariSettings::default() (src/lib.rs:435-455) with keyword overrides, as a ctypes struct."""
     s = Settings()
-    lib().hikari_settings_default(C.byref(s))
+    host_lib().hikari_settings_default(C.byref(s))
     for k, v in overrides.items():
         if k == "clear_color":
             s.clear_color[:] = list(v)
@@ -35,7 +35,7 @@ def HikariSettings(**overrides):
 
 def make_frame_inputs(settings, frame_counter, view, previous_view, lights, temporal_upscalers=False):
     out = L.FrameInputs()
-    lib().hikari_make_frame_inputs(C.byref(settings), int(frame_counter), C.byref(view), C.byref(previous_view),
+    host_lib().hikari_make_frame_inputs(C.byref(settings), int(frame_counter), C.byref(view), C.byref(previous_view),
                                    C.byref(lights), C.byref(out))
     out.temporal_upscalers = 1 if temporal_upscalers else 0
     return out
@@ -51,12 +51,12 @@ class World:
     """MeshMaterialPlugin's render-world state: meshes, materials, textures, instances -> the nine GPU buffers."""
 
     def __init__(self):
-        self._w = lib().hikari_world_create()
+        self._w = host_lib().hikari_world_create()
         self._keep = []
 
     def __del__(self):
         if getattr(self, "_w", None):
-            lib().hikari_world_destroy(self._w)
+            host_lib().hikari_world_destroy(self._w)
             self._w = None
 
     def add_mesh(self, positions, normals, uvs, indices=None, topology=0):
@@ -64,47 +64,47 @@ class World:
         n = len(arrs[0]) if arrs[0] is not None else 0
         idx = None if indices is None else np.ascontiguousarray(indices, np.uint32).reshape(-1)
         ptr = lambda a: None if a is None else a.ctypes.data
-        return lib().hikari_world_add_mesh(self._w, ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), n, ptr(idx),
+        return host_lib().hikari_world_add_mesh(self._w, ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), n, ptr(idx),
                                            0 if idx is None else idx.size, topology)
 
     def add_material(self, material_record):
         m = np.zeros(1, L.MATERIAL)
         m[0] = material_record
-        return lib().hikari_world_add_material(self._w, m.ctypes.data)
+        return host_lib().hikari_world_add_material(self._w, m.ctypes.data)
 
     def set_material(self, material_id, material_record):
         m = np.zeros(1, L.MATERIAL)
         m[0] = material_record
-        lib().hikari_world_set_material(self._w, material_id, m.ctypes.data)
+        host_lib().hikari_world_set_material(self._w, material_id, m.ctypes.data)
 
     def prepare_materials(self):
-        lib().hikari_world_prepare_materials(self._w)
+        host_lib().hikari_world_prepare_materials(self._w)
 
     def add_texture(self, rgba, address_mode_u=0, address_mode_v=0, filter_linear=1, srgb=1):
         rgba = np.ascontiguousarray(rgba, np.uint8)
         t = L.TextureDesc(rgba.ctypes.data, rgba.shape[1], rgba.shape[0], address_mode_u, address_mode_v, filter_linear, srgb)
-        return lib().hikari_world_add_texture(self._w, C.byref(t))
+        return host_lib().hikari_world_add_texture(self._w, C.byref(t))
 
     def add_instance(self, mesh, material, transform16, visible=True):
         t = np.ascontiguousarray(transform16, np.float32).reshape(16)
-        return lib().hikari_world_add_instance(self._w, mesh, material, t.ctypes.data, 1 if visible else 0)
+        return host_lib().hikari_world_add_instance(self._w, mesh, material, t.ctypes.data, 1 if visible else 0)
 
     def prepare(self):
-        lib().hikari_world_prepare(self._w)
+        host_lib().hikari_world_prepare(self._w)
 
     # animated instances (transform.rs:31-44, instance.rs:352-437)
     def set_instance_transform(self, instance, transform16):
         t = np.ascontiguousarray(transform16, np.float32).reshape(16)
-        lib().hikari_world_set_instance_transform(self._w, instance, t.ctypes.data)
+        host_lib().hikari_world_set_instance_transform(self._w, instance, t.ctypes.data)
 
     def set_instance_visible(self, instance, visible):
-        lib().hikari_world_set_instance_visible(self._w, instance, 1 if visible else 0)
+        host_lib().hikari_world_set_instance_visible(self._w, instance, 1 if visible else 0)
 
     def previous_transform_system(self):
-        lib().hikari_world_previous_transform_system(self._w)
+        host_lib().hikari_world_previous_transform_system(self._w)
 
     def prepare_instances(self):
-        lib().hikari_world_prepare_instances(self._w)
+        host_lib().hikari_world_prepare_instances(self._w)
 
     def previous_models(self):
         d = self.scene_desc()
@@ -113,11 +113,11 @@ class World:
         return np.frombuffer(C.string_at(d.previous_instance_models, d.instance_count * 64), np.float32).reshape(-1, 16).copy()
 
     def mesh_error(self, mesh):
-        return lib().hikari_world_mesh_error(self._w, mesh)
+        return host_lib().hikari_world_mesh_error(self._w, mesh)
 
     def scene_desc(self):
         d = L.SceneDesc()
-        lib().hikari_world_scene_desc(self._w, C.byref(d))
+        host_lib().hikari_world_scene_desc(self._w, C.byref(d))
         return d
 
     def buffers(self):
@@ -232,6 +232,7 @@ class HikariPlugin:
     def sync(self): check(lib().hk_sync(self.ctx), self.ctx)
     def reset_temporal_state(self): check(lib().hk_reset_temporal_state(self.ctx), self.ctx)
     def set_profiling(self, count_rays, time_passes): check(lib().hk_set_profiling(self.ctx, int(count_rays), int(time_passes)), self.ctx)
+    def set_profiling_kernel(self, kernel): check(lib().hk_set_profiling_kernel(self.ctx, int(kernel)), self.ctx)
     def set_keep_intermediates(self, keep): check(lib().hk_set_keep_intermediates(self.ctx, int(keep)), self.ctx)
 
     def stats(self):

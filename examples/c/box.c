@@ -5,7 +5,7 @@
  * default), run HikariPlugin for a few frames with HikariSettings::default() overrides, read the tone-mapped image back.
  * Scene: a floor, a box and a small emissive quad above them (a poor man's cornell).
  *
- *   gcc -O2 -Iinclude examples/c/box.c -Lbevy_hikari_b200 -lhikari_b200 -lm -Wl,-rpath,$PWD/bevy_hikari_b200 -o box
+ *   gcc -O2 -Iinclude examples/c/box.c -Lbevy_hikari_b200 -lhikari_b200 -lhikari_host -lm -Wl,-rpath,$PWD/bevy_hikari_b200 -o box
  *   ./box data/noise_rgba8_64x64x16.bin          (needs a CUDA device: there is no CPU fallback)
  */
 #include <math.h>

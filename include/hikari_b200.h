@@ -126,7 +126,7 @@ typedef struct hk_frame_stats {
     uint64_t blas_rays;          /* stand-alone traverse_bottom calls (light.wgsl:687) */
     float ms_prepass, ms_light, ms_post_process, ms_total;   /* CUDA-event times of the last frame, if enabled */
     uint32_t kernel_launches;    /* kernels launched by the last hk_render_frame */
-    uint32_t _pad;
+    uint32_t timed_frames;       /* hk_set_profiling_kernel mode: frames averaged into ms_kernel[kernel]; 0 otherwise */
     float ms_kernel[16];         /* per-kernel CUDA-event times of the last hk_render_frame, index = HK_K_*; 0 = not run */
 } hk_frame_stats;
 
@@ -246,6 +246,11 @@ int hk_frame_read(hk_context* ctx, const void* frame_device_ptr, void* host, siz
 
 int hk_trace_rays(hk_context* ctx, const hk_ray* rays, size_t n, hk_hit* hits);   /* F3/F4 parity hook */
 int hk_set_profiling(hk_context* ctx, int count_rays, int time_passes);
+/* Low-overhead timing of ONE kernel (HK_K_* index): only its launch is bracketed with CUDA events (2 records per frame), kept in
+ * a ring of 256 frames; hk_get_stats then reports the MEAN duration over the frames rendered since this call in ms_kernel[kernel]
+ * (timed_frames = how many).  bench.py uses it to measure the dominant kernel live inside the timed region without the ~30 event
+ * records of full pass timing.  kernel < 0 restores per-pass timing as selected by hk_set_profiling. */
+int hk_set_profiling_kernel(hk_context* ctx, int kernel);
 int hk_set_keep_intermediates(hk_context* ctx, int keep);   /* 1: hk_render_frame also writes HK_OUT_DENOISED_* */
 int hk_get_stats(hk_context* ctx, hk_frame_stats* out);
 int hk_band_rows(hk_context* ctx, uint32_t* alloc_row_begin, uint32_t* alloc_row_end); /* owned rows +- ghost rows */

@@ -20,7 +20,7 @@ def pytest_configure(config):
         sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
         import build_emu
         from bevy_hikari_b200 import _ffi
-        _ffi.LIB_PATH = build_emu.build()
+        _ffi.LIB_PATH = _ffi.HOST_LIB_PATH = build_emu.build()   # one self-contained library: kernels + the whole host mirror
 
 
 def pytest_collection_modifyitems(config, items):

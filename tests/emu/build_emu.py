@@ -19,7 +19,7 @@ ASAN = bool(os.environ.get("HK_EMU_ASAN"))      # AddressSanitizer build: a memc
 GEN, OUT = os.path.join(HERE, "_gen"), os.path.join(HERE, "_build_asan" if ASAN else "_build")
 LIB = os.path.join(OUT, "libhikari_emu.so")
 CU = ["context.cu", "kernels_light.cu", "kernels_post.cu", "kernels_upscale.cu"]
-CPP = ["hikari.cpp", "hikari_capi.cpp"]
+CPP = ["hikari.cpp", "hikari_capi.cpp", "hikari_plugin.cpp", "hikari_plugin_capi.cpp"]
 CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 FLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-std=c++17", "-w",
          "-I" + os.path.join(HERE, "include"), "-I" + SRC, "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + \
