@@ -16,6 +16,10 @@
 #include "hikari_b200.h"
 #include "hk_kernels.h"
 
+#ifndef HK_POOLED_INDIRECT
+#define HK_POOLED_INDIRECT 1     // 0: the per-pixel k_indirect of round 1 (kept for A/B timing; same values)
+#endif
+
 using namespace hkd;
 
 // Rows a band needs beyond the rows it owns so that owned pixels equal an unsharded render:
@@ -42,7 +46,7 @@ struct hk_context {
     size_t band_pixels = 0, owned_pixels = 0;
     std::vector<void*> allocations;        // per-pixel planes
     std::vector<void*> scene_allocations;  // scene buffers: meshes, BLAS nodes, materials, textures
-    struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[8];   // scene buffers rewritten by hk_scene_update_instances (grow-only)
+    struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[9];   // scene buffers rewritten by hk_scene_update_instances (grow-only)
     bool mesh_boxes_match = false;         // BLAS half of DeviceScene::leaf_boxes_match
     uint32_t scene_material_count = 0, scene_asset_node_count = 0, scene_primitive_count = 0, scene_vertex_count = 0, scene_texture_count = 0;
     std::vector<hk_node> host_asset_nodes;                 // copy of the uploaded BLAS records: index validation of later instance updates
@@ -452,6 +456,29 @@ static int upload_instances(hk_context* ctx, const hk_scene_desc* s, DeviceScene
     HK_CUDA(upload_into(ctx, ctx->ibuf[2], &d.instance_nodes, s->instance_nodes, s->instance_node_count));
     HK_CUDA(upload_into(ctx, ctx->ibuf[3], &d.emissive_nodes, s->emissive_nodes, s->emissive_node_count));
     HK_CUDA(upload_into(ctx, ctx->ibuf[4], &d.emissives, s->emissives, s->emissive_count));
+    {   // compact traversal records + what the pooled kernels stage into shared memory (hk_pool.cuh)
+        std::vector<hk_instance_trav> trav(s->instance_count);
+        for (uint32_t i = 0; i < s->instance_count; ++i) {
+            memcpy(trav[i].inverse_transpose_model, s->instances[i].inverse_transpose_model, 64);
+            trav[i].mesh[0] = s->instances[i].mesh.vertex; trav[i].mesh[1] = s->instances[i].mesh.primitive;
+            trav[i].mesh[2] = s->instances[i].mesh.node_offset; trav[i].mesh[3] = s->instances[i].mesh.node_count;
+        }
+        HK_CUDA(upload_into(ctx, ctx->ibuf[8], &d.instance_trav, trav.data(), trav.size()));
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));      // `trav` dies at the end of this block
+        StagePlan plan{};
+        const uint32_t budget = (uint32_t)HK_STAGE_F4;
+        const uint64_t tlas = 2ull * s->instance_node_count, itrav = 5ull * s->instance_count;
+        if (s->instance_node_count && tlas + itrav <= budget) {
+            plan.tlas_f4 = 0; plan.tlas_count = s->instance_node_count;
+            plan.itrav_f4 = (uint32_t)tlas; plan.itrav_count = s->instance_count;
+            const uint64_t used = tlas + itrav, blas = 2ull * ctx->scene_asset_node_count, prim = 3ull * ctx->scene_primitive_count;
+            if (ctx->scene_asset_node_count && used + blas + prim <= budget) {     // small scene: walked entirely out of shared memory
+                plan.blas_f4 = (uint32_t)used; plan.blas_count = ctx->scene_asset_node_count;
+                plan.prim_f4 = (uint32_t)(used + blas); plan.prim_count = ctx->scene_primitive_count;
+            }
+        }
+        d.stage = plan;
+    }
     d.instance_node_count = s->instance_node_count;
     d.emissive_node_count = s->emissive_node_count;
     d.previous_models = nullptr;
@@ -707,7 +734,9 @@ static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, li
       hk_launch_scatter_resolve(P, 1, ctx->stream); ctx->launches += 1; }
     if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_EMISSIVE_SPATIAL); hk_launch_spatial(P, true, ctx->stream); }
     rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
-    { KernelTimer t(ctx, HK_K_INDIRECT); hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
+    { KernelTimer t(ctx, HK_K_INDIRECT);
+      if (HK_POOLED_INDIRECT) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
+      else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
       hk_launch_scatter_resolve(P, 2, ctx->stream); ctx->launches += 1; }
     if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); hk_launch_spatial(P, false, ctx->stream); }
     return check_launch(ctx);

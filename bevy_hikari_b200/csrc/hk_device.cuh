@@ -48,6 +48,25 @@
 namespace hkd {
 using namespace hk;
 
+// Compact per-instance record of the BVH walk: the 80 bytes of hk_instance (176 B) a TLAS leaf needs once the navigator's box
+// test has passed — transpose(inverse_transpose_model) as stored (light.wgsl:306-316) and the mesh index.  Built at upload
+// (context.cu) so that one TMA bulk copy stages all of them into shared memory (hk_pool.cuh).
+struct hk_instance_trav {
+    float inverse_transpose_model[16];
+    uint32_t mesh[4];          // vertex, primitive, node_offset, node_count
+};
+static_assert(sizeof(hk_instance_trav) == 80, "5 float4 per instance");
+
+// Where each staged scene array lives inside the pooled kernels' shared-memory stage, in float4 units; decided on the host per
+// scene (context.cu).  A count of 0 means "not staged: read from global memory".
+#define HK_STAGE_F4 1024               // float4 slots (16 KB) of staged scene records per CTA
+struct StagePlan {
+    uint32_t tlas_f4, tlas_count;      // instance_nodes: 2 float4 per record
+    uint32_t itrav_f4, itrav_count;    // hk_instance_trav: 5 float4 per instance
+    uint32_t blas_f4, blas_count;      // asset_nodes (whole buffer): 2 float4 per record
+    uint32_t prim_f4, prim_count;      // primitives (whole buffer): 3 float4 per triangle
+};
+
 struct DeviceScene {
     const hk_vertex* vertices;
     const hk_primitive* primitives;
@@ -67,6 +86,8 @@ struct DeviceScene {
     // compared bitwise on the host); both nullptr when no instance moved
     const float4* previous_models;
     const uint32_t* instance_moved;
+    const hk_instance_trav* instance_trav;   // one per instance
+    StagePlan stage;
 };
 
 struct ReservoirPlanes {  // one PackedReservoir buffer as 4 planes
@@ -827,6 +848,40 @@ __device__ __forceinline__ void denoise_deferred_coords(const KParams& P, vec2 u
 }
 __device__ __forceinline__ bool render_allocated(const KParams& P, int x, int y) {
     return P.ratio1 ? band_allocated(P.band, x, y) : (x >= 0 && x < P.band.RW && y >= 0 && y < P.band.RH);
+}
+
+// ------------------------------------------------------------------------------------- shared pass plumbing
+struct PassBuffers {  // bind group 6 (light.rs:518-546)
+    ReservoirPlanes previous_reservoir, reservoir, previous_spatial_reservoir, spatial_reservoir;
+};
+__device__ __forceinline__ PassBuffers bind(const KParams& P, int signal) {
+    const int temporal = (signal == 0) ? 0 : (signal == 1 ? 2 : 6);
+    const int spatial = (signal == 2) ? 8 : 4;
+    const int current = (int)(P.in.frame.number & 1u), previous = 1 - current;
+    PassBuffers b;
+    b.previous_reservoir = P.planes.reservoir[current + temporal];
+    b.reservoir = P.planes.reservoir[previous + temporal];
+    b.previous_spatial_reservoir = P.planes.reservoir[current + spatial];
+    b.spatial_reservoir = P.planes.reservoir[previous + spatial];
+    return b;
+}
+// reprojected pixel of `previous_uv` (light.wgsl:181-190): returns false when outside [0,1) or outside the band
+__device__ __forceinline__ bool previous_pixel(const KParams& P, vec2 previous_uv, bool inclusive, size_t& pidx) {
+    float ax = fabsf(previous_uv.x - 0.5f), ay = fabsf(previous_uv.y - 0.5f);
+    bool inside = inclusive ? (ax <= 0.5f && ay <= 0.5f) : (ax < 0.5f && ay < 0.5f);
+    if (!inside) return false;
+    int px = f32_to_i32(previous_uv.x * (float)P.band.RW), py = f32_to_i32(previous_uv.y * (float)P.band.RH);
+    if (!render_allocated(P, px, py)) return false;
+    pidx = render_index(P.band, px, py);
+    return true;
+}
+__device__ __forceinline__ vec2 pixel_uv(const KParams& P, int x, int y) { return render_uv(P, x, y); }  // coords_to_uv, utils.wgsl:37-39
+// index of the G-buffer texel a light pass reads for render pixel (x, y): jittered_deferred_coords(uv)
+__device__ __forceinline__ size_t light_gbuffer_index(const KParams& P, int x, int y, size_t render_idx) {
+    if (P.ratio1) return render_idx;
+    int dx, dy;
+    light_deferred_coords(P, render_uv(P, x, y), x, y, dx, dy);
+    return band_index(P.band, dx, dy);
 }
 
 // kinds of writes to the previous-spatial buffer, in the order one pixel can issue them

@@ -6,6 +6,8 @@ void hk_launch_gbuffer(const hkd::KParams& P, bool count, cudaStream_t st);
 void hk_launch_albedo(const hkd::KParams& P, cudaStream_t st);
 void hk_launch_direct(const hkd::KParams& P, bool emissive, bool count, cudaStream_t st);
 void hk_launch_indirect(const hkd::KParams& P, bool multi, bool count, cudaStream_t st);
+// pooled (cooperative) form of the indirect pass: shared-memory ray pool, dynamic fetch, TMA-staged scene records (kernels_pool.cu)
+void hk_launch_indirect_pool(const hkd::KParams& P, bool multi, bool count, cudaStream_t st);
 void hk_launch_spatial(const hkd::KParams& P, bool emissive, cudaStream_t st);
 void hk_launch_scatter_resolve(const hkd::KParams& P, int signal, cudaStream_t st);
 void hk_launch_trace_rays(const hkd::DeviceScene& sc, const hk_ray* rays, size_t n, hk_hit* hits, cudaStream_t st);

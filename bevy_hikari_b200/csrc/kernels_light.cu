@@ -189,40 +189,6 @@ __global__ void __launch_bounds__(CTA_THREADS) k_albedo(const __grid_constant__ 
     P.planes.albedo[idx] = make_uint2(alb.x, alb.y);
 }
 
-// ------------------------------------------------------------------------------------- shared pass plumbing
-struct PassBuffers {  // bind group 6 (light.rs:518-546)
-    ReservoirPlanes previous_reservoir, reservoir, previous_spatial_reservoir, spatial_reservoir;
-};
-__device__ __forceinline__ PassBuffers bind(const KParams& P, int signal) {
-    const int temporal = (signal == 0) ? 0 : (signal == 1 ? 2 : 6);
-    const int spatial = (signal == 2) ? 8 : 4;
-    const int current = (int)(P.in.frame.number & 1u), previous = 1 - current;
-    PassBuffers b;
-    b.previous_reservoir = P.planes.reservoir[current + temporal];
-    b.reservoir = P.planes.reservoir[previous + temporal];
-    b.previous_spatial_reservoir = P.planes.reservoir[current + spatial];
-    b.spatial_reservoir = P.planes.reservoir[previous + spatial];
-    return b;
-}
-// reprojected pixel of `previous_uv` (light.wgsl:181-190): returns false when outside [0,1) or outside the band
-__device__ __forceinline__ bool previous_pixel(const KParams& P, vec2 previous_uv, bool inclusive, size_t& pidx) {
-    float ax = fabsf(previous_uv.x - 0.5f), ay = fabsf(previous_uv.y - 0.5f);
-    bool inside = inclusive ? (ax <= 0.5f && ay <= 0.5f) : (ax < 0.5f && ay < 0.5f);
-    if (!inside) return false;
-    int px = f32_to_i32(previous_uv.x * (float)P.band.RW), py = f32_to_i32(previous_uv.y * (float)P.band.RH);
-    if (!render_allocated(P, px, py)) return false;
-    pidx = render_index(P.band, px, py);
-    return true;
-}
-__device__ __forceinline__ vec2 pixel_uv(const KParams& P, int x, int y) { return render_uv(P, x, y); }  // coords_to_uv, utils.wgsl:37-39
-// index of the G-buffer texel a light pass reads for render pixel (x, y): jittered_deferred_coords(uv)
-__device__ __forceinline__ size_t light_gbuffer_index(const KParams& P, int x, int y, size_t render_idx) {
-    if (P.ratio1) return render_idx;
-    int dx, dy;
-    light_deferred_coords(P, render_uv(P, x, y), x, y, dx, dy);
-    return band_index(P.band, dx, dy);
-}
-
 // --------------------------------------------------------------------------------------- P2: direct_lit
 // light.wgsl:1044-1261.  EMISSIVE_LIT=false is the sun pass (+RENDER_EMISSIVE), true is the emissive pass.
 // NOVAL = true: instantiation for the frames that are NOT validation frames (frame.number % validate_interval != 0, a launch-wide

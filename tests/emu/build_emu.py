@@ -3,7 +3,8 @@
 the host through tests/emu/cuda_emu.h, behind the same C ABI, so that the kernels' logic can be compared with the oracle
 without a GPU (tests/test_emulated_kernels.py; HK_EMULATE_KERNELS=1 pytest -m gpu ... runs any GPU test on the CPU during development).
 The only source transformations are
-  * `kernel<<<grid, block, 0, stream>>>(args)`  ->  `EMU_LAUNCH(grid, block, kernel(args))`
+  * `kernel<<<grid, block, 0, stream>>>(args)`  ->  `EMU_LAUNCH(grid, block, kernel(args))`, or `EMU_LAUNCH_COOP(...)` for the
+    cooperative kernels (kc_*): shared memory, __syncthreads, ballots and shuffles run for real, threads as fibers (cuda_emu.h)
   * flush_counters' warp reduction (shuffles) -> one atomic add per thread (same totals)."""
 import os
 import re
@@ -18,7 +19,7 @@ ASAN = bool(os.environ.get("HK_EMU_ASAN"))      # AddressSanitizer build: a memc
 #                                                  LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)
 GEN, OUT = os.path.join(HERE, "_gen"), os.path.join(HERE, "_build_asan" if ASAN else "_build")
 LIB = os.path.join(OUT, "libhikari_emu.so")
-CU = ["context.cu", "kernels_light.cu", "kernels_post.cu", "kernels_upscale.cu"]
+CU = ["context.cu", "kernels_light.cu", "kernels_pool.cu", "kernels_post.cu", "kernels_upscale.cu"]
 CPP = ["hikari.cpp", "hikari_capi.cpp", "hikari_plugin.cpp", "hikari_plugin_capi.cpp"]
 CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 FLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-std=c++17", "-w",
@@ -28,6 +29,7 @@ if ASAN:
     FLAGS = [f for f in FLAGS if f != "-O2"] + ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
 
 LAUNCH = re.compile(r"([A-Za-z_][A-Za-z_0-9]*(?:<[^<>;]*>)?)<<<([^;]*?)>>>\(([^;]*)\);")
+COOPERATIVE = re.compile(r"^kc_")     # kernels with shared memory / barriers / warp collectives: threads of a block run as fibers
 FLUSH_OLD = re.compile(r"for \(int o = 16; o > 0; o >>= 1\) \{.*?\n    \}\n    if \(\(threadIdx\.x & 31\) == 0\) \{", re.S)
 
 
@@ -35,7 +37,8 @@ def transform(text, name):
     def launch(m):
         kernel, cfg, args = m.group(1), m.group(2), m.group(3)
         parts = [p.strip() for p in split_top(cfg)]
-        return f"EMU_LAUNCH(dim3({parts[0]}), dim3({parts[1]}), {kernel}({args}));"
+        macro = "EMU_LAUNCH_COOP" if COOPERATIVE.match(kernel) else "EMU_LAUNCH"
+        return f"{macro}(dim3({parts[0]}), dim3({parts[1]}), {kernel}({args}));"
     out, n = LAUNCH.subn(launch, text)
     if name == "kernels_light.cu":
         out, k = FLUSH_OLD.subn("{", out)
@@ -67,7 +70,7 @@ def build(force=False):
     os.makedirs(GEN, exist_ok=True); os.makedirs(OUT, exist_ok=True)
     deps = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(HOST, f) for f in os.listdir(HOST)] + \
            [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))] + \
-           [os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__)]
+           [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "emu_runtime.cpp"), os.path.abspath(__file__)]
     # the library on disk must have been built from the current sources AND with the current flags: a tuning-variant or sanitizer
     # build (HK_EMU_EXTRA) left behind must not be mistaken for the default build by the next run
     stamp = os.path.join(OUT, "flags.txt")
@@ -84,8 +87,7 @@ def build(force=False):
         o = os.path.join(OUT, f + ".o")
         subprocess.run([CXX] + FLAGS + ["-c", g, "-o", o], check=True)
         objs.append(o)
-    glue = os.path.join(GEN, "emu_globals.cpp")
-    open(glue, "w").write('#include "cuda_emu.h"\nthread_local EmuIdx threadIdx, blockIdx;\nthread_local dim3 blockDim, gridDim;\n#include <stdlib.h>\nint emu_reverse_order() { static int v = getenv("HK_EMU_REVERSE") ? 1 : 0; return v; }\n')
+    glue = os.path.join(HERE, "emu_runtime.cpp")
     o = os.path.join(OUT, "emu_globals.o")
     subprocess.run([CXX] + FLAGS + ["-I" + HERE, "-c", glue, "-o", o], check=True)
     objs.append(o)

@@ -2,10 +2,16 @@
 // SOURCES (bevy_hikari_b200/csrc/*.cu, unmodified except for the launch syntax, see build_emu.py) can be compiled with g++
 // and their LOGIC compared with the oracle without a GPU (tests/test_emulated_kernels.py).  It is not a fallback: the
 // package never loads the library built from it, performance is irrelevant, and nothing here is shipped.
-// Execution model: a launch runs every thread of every block to completion, one after the other (blocks in parallel with
-// OpenMP).  That is equivalent for these kernels: no shared memory, no barriers, no reads of values written by other
-// threads of the same launch; the only cross-thread operations are order-independent atomics.
+// Execution model, two kinds of launch:
+//   EMU_LAUNCH       every thread of every block runs to completion, one after the other (blocks in parallel with OpenMP).
+//                    Equivalent for kernels without shared memory, barriers or warp collectives (k_*).
+//   EMU_LAUNCH_COOP  for the cooperative kernels (kc_*: shared-memory ray pool, __syncthreads, ballots, shuffles, mbarrier):
+//                    the threads of a block are fibers (ucontext) on one host thread; a fiber runs until it reaches a collective
+//                    that is not complete yet, then the scheduler switches to the next runnable one.  __shared__ variables are
+//                    static thread_local, i.e. one copy per host thread = per block in flight.  A collective that can never
+//                    complete (divergent barrier, a lane missing from a ballot) is reported as a deadlock instead of hanging.
 #pragma once
+#define HK_EMU 1
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -52,7 +58,6 @@ static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
     return old;
 }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-static inline uint32_t __shfl_xor_sync(uint32_t, uint32_t, int) { return 0u; }   // see build_emu.py: flush_counters is patched to per-thread adds
 
 // ------------------------------------------------------------------------------------------------ runtime
 typedef int cudaError_t;
@@ -97,6 +102,133 @@ static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { 
 // the two-process paths are exercised on the device, tests/test_gpu_frame_assembly.py, tests/test_gpu_zz_halo.py)
 static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
 static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+
+// ------------------------------------------------------------------------------------- cooperative kernels (fibers)
+#include <ucontext.h>
+#include <stdio.h>
+#include <sys/mman.h>
+
+#include <functional>
+#include <vector>
+
+#define __shared__ static thread_local
+#define HK_NOINLINE __attribute__((noinline))
+
+struct EmuWarpState {
+    uint32_t gen = 0, arrived = 0, pending_mask = 0, alive_mask = 0;
+    uint32_t vals[2][32];
+};
+struct EmuFiber {
+    ucontext_t ctx;
+    void* stack = nullptr;
+    bool done = true;
+    const volatile uint32_t* wait_ptr = nullptr;   // runnable again when *wait_ptr != wait_val
+    uint32_t wait_val = 0;
+};
+struct EmuCta {
+    static const size_t STACK = 512 * 1024;
+    std::vector<EmuFiber> fibers;
+    std::vector<EmuWarpState> warps;
+    ucontext_t sched;
+    unsigned n = 0, current = 0, alive = 0;
+    dim3 bdim;
+    uint32_t bar_gen = 0, bar_arrived = 0, bar_acc[2] = {0, 0}, bar_cnt[2] = {0, 0};
+    std::function<void()> body;
+    void run(const dim3& block, const std::function<void()>& f, bool reverse);
+    void yield_until_changed(const volatile uint32_t* p, uint32_t v);
+    void on_exit_thread();
+};
+extern int emu_reverse_order();
+extern thread_local EmuCta* emu_cta;      // the block this host thread is running cooperatively, or nullptr
+[[noreturn]] void emu_deadlock(const char* what);
+
+static inline unsigned emu_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
+
+// arrive with a 32-bit contribution; returns the generation whose vals[gen & 1][lane] hold every participant's contribution
+static inline uint32_t emu_warp_collect(uint32_t mask, uint32_t value) {
+    EmuCta* c = emu_cta;
+    if (!c) emu_deadlock("warp collective in a kernel launched with EMU_LAUNCH (name it kc_* for a cooperative launch)");
+    const unsigned tid = emu_tid(), lane = tid & 31u;
+    EmuWarpState& w = c->warps[tid >> 5];
+    if (!((mask >> lane) & 1u)) emu_deadlock("lane executes a *_sync collective it is not named in");
+    const uint32_t g = w.gen;
+    w.vals[g & 1u][lane] = value;
+    w.arrived |= 1u << lane;
+    w.pending_mask = mask;
+    const uint32_t need = mask & w.alive_mask;
+    if ((w.arrived & need) == need) { w.arrived = 0; w.gen = g + 1u; }
+    else c->yield_until_changed(&w.gen, g);
+    return g;
+}
+static inline uint32_t __ballot_sync(uint32_t mask, int pred) {
+    const uint32_t g = emu_warp_collect(mask, pred ? 1u : 0u);
+    const EmuWarpState& w = emu_cta->warps[emu_tid() >> 5];
+    uint32_t r = 0;
+    for (unsigned l = 0; l < 32; ++l) if (((mask & w.alive_mask) >> l) & 1u) r |= (w.vals[g & 1u][l] & 1u) << l;
+    return r;
+}
+static inline int __any_sync(uint32_t mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
+static inline int __all_sync(uint32_t mask, int pred) { return __ballot_sync(mask, !pred) == 0u; }
+static inline void __syncwarp(uint32_t mask = 0xffffffffu) { emu_warp_collect(mask, 0u); }
+template <class T> static inline T emu_shfl_from(uint32_t mask, T v, unsigned src_lane) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    uint32_t bits; memcpy(&bits, &v, 4);
+    const uint32_t g = emu_warp_collect(mask, bits);
+    const uint32_t out = emu_cta->warps[emu_tid() >> 5].vals[g & 1u][src_lane & 31u];
+    T r; memcpy(&r, &out, 4);
+    return r;
+}
+template <class T> static inline T __shfl_sync(uint32_t mask, T v, int src) { return emu_shfl_from(mask, v, (unsigned)src); }
+// sequential launches: flush_counters is patched to per-thread adds (build_emu.py) and never reaches this; cooperative launches shuffle for real
+template <class T> static inline T __shfl_xor_sync(uint32_t mask, T v, int lane_mask) { return emu_cta ? emu_shfl_from(mask, v, (emu_tid() & 31u) ^ (unsigned)lane_mask) : T(0); }
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+static inline uint32_t emu_lanemask_lt() { return (1u << (emu_tid() & 31u)) - 1u; }
+
+static inline void emu_block_barrier(int pred, uint32_t* or_out, uint32_t* count_out) {
+    EmuCta* c = emu_cta;
+    if (!c) emu_deadlock("__syncthreads in a kernel launched with EMU_LAUNCH (name it kc_* for a cooperative launch)");
+    const uint32_t g = c->bar_gen;
+    if (pred) { c->bar_acc[g & 1u] = 1u; c->bar_cnt[g & 1u] += 1u; }
+    c->bar_arrived += 1;
+    if (c->bar_arrived >= c->alive) { c->bar_arrived = 0; c->bar_acc[(g + 1u) & 1u] = 0; c->bar_cnt[(g + 1u) & 1u] = 0; c->bar_gen = g + 1u; }
+    else c->yield_until_changed(&c->bar_gen, g);
+    if (or_out) *or_out = c->bar_acc[g & 1u];
+    if (count_out) *count_out = c->bar_cnt[g & 1u];
+}
+static inline void __syncthreads() { emu_block_barrier(0, nullptr, nullptr); }
+static inline int __syncthreads_or(int pred) { uint32_t r; emu_block_barrier(pred, &r, nullptr); return (int)r; }
+static inline int __syncthreads_count(int pred) { uint32_t r; emu_block_barrier(pred, nullptr, &r); return (int)r; }
+
+// shared-memory atomics of the cooperative kernels (one host thread per block: plain read-modify-write)
+static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+
+// wait until a 32-bit word written by another thread of the block changes (the emulated mbarrier of hk_pool.cuh)
+static inline void emu_wait_changed(const volatile uint32_t* p, uint32_t v) {
+    if (*p != v) return;
+    if (!emu_cta) emu_deadlock("wait on another thread's write in a kernel launched with EMU_LAUNCH");
+    emu_cta->yield_until_changed(p, v);
+}
+
+#define EMU_LAUNCH_COOP(GRID, BLOCK, ...)                                                 \
+    do {                                                                                  \
+        const dim3 emu_g = (GRID), emu_b = (BLOCK);                                       \
+        const long long emu_n = (long long)emu_g.x * emu_g.y * emu_g.z;                   \
+        const bool emu_rev = emu_reverse_order() != 0;                                    \
+        _Pragma("omp parallel for schedule(dynamic, 1) if (!emu_rev)")                    \
+        for (long long emu_j = 0; emu_j < emu_n; ++emu_j) {                               \
+            const long long emu_i = emu_rev ? emu_n - 1 - emu_j : emu_j;                  \
+            gridDim = emu_g; blockDim = emu_b;                                            \
+            blockIdx.x = (unsigned)(emu_i % emu_g.x);                                     \
+            blockIdx.y = (unsigned)((emu_i / emu_g.x) % emu_g.y);                         \
+            blockIdx.z = (unsigned)(emu_i / ((long long)emu_g.x * emu_g.y));              \
+            static thread_local EmuCta emu_block;                                         \
+            emu_block.run(emu_b, [&]() { __VA_ARGS__; }, emu_rev);                        \
+        }                                                                                 \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------------ launches
 // EMU_LAUNCH(grid, block, kernel_call): every thread of every block, blocks distributed over the host cores
