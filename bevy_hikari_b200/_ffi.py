@@ -8,6 +8,8 @@ from . import layout as L
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhikari_b200.so")   # the product library (CUDA + C ABI); there is no fallback if it is missing
+EXACT_LIB_PATH = os.path.join(HERE, "libhikari_b200_exact.so")   # same sources, exact arithmetic in every unit: the 0-ulp parity suite
+DEFAULT_FLAVOR = "product"    # tests/conftest.py switches the default to "exact"; the tolerance gate asks for "product" explicitly
 HOST_LIB_PATH = os.path.join(HERE, "libhikari_host.so")   # the host mirror up to hikari_make_frame_inputs: pure CPU, no CUDA
 
 HK_OK = 0
@@ -63,6 +65,8 @@ SYMBOLS = {
     "hk_trace_rays": (_I, [_P, _P, _SZ, _P]),
     "hk_set_profiling": (_I, [_P, _I, _I]),
     "hk_set_profiling_kernel": (_I, [_P, _I]),
+    "hk_set_tuning": (_I, [_P, _I, _I]),
+    "hk_run_pass": (_I, [_P, C.POINTER(L.FrameInputs), _I, _I]),
     "hk_set_keep_intermediates": (_I, [_P, _I]),
     "hk_get_stats": (_I, [_P, C.POINTER(L.FrameStats)]),
     "hk_band_rows": (_I, [_P, C.POINTER(_U32), C.POINTER(_U32)]),
@@ -123,25 +127,34 @@ def host_lib():
     return _host_lib
 
 
-def lib():
+def lib(flavor=None):
+    """the CUDA library: flavor "product" (tolerance build of the units that trace no rays, bevy_hikari_b200/build.py) or "exact";
+    None = DEFAULT_FLAVOR.  An explicit LIB_PATH override (bench.py --lib, the kernel-logic emulation) serves both."""
     global _lib
+    flavor = flavor or DEFAULT_FLAVOR
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+        _lib = {}
+    path = LIB_PATH
+    if flavor == "exact" and LIB_PATH == os.path.join(HERE, "libhikari_b200.so"):
+        path = EXACT_LIB_PATH
+    if path not in _lib:
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(nvcc, sm_100a). There is no fallback path.")
         host_lib()                 # dependency of the CUDA library (also found through its $ORIGIN rpath)
-        _lib = C.CDLL(LIB_PATH)
+        h = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
-            fn = getattr(_lib, name)   # AttributeError if the library does not export a declared symbol
+            fn = getattr(h, name)   # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-    return _lib
+        _lib[path] = h
+    return _lib[path]
 
 
 class HikariError(RuntimeError):
     pass
 
 
-def check(rc, ctx=None):
+def check(rc, ctx=None, handle=None):
     if rc != HK_OK:
-        msg = lib().hk_last_error(ctx)
+        msg = (handle or lib()).hk_last_error(ctx)
         raise HikariError(f"hk error {rc}: {msg.decode() if msg else ''}")

@@ -17,8 +17,8 @@
 #include "hk_kernels.h"
 
 #ifndef HK_POOLED_INDIRECT
-#define HK_POOLED_INDIRECT 1     // 0: the per-pixel k_indirect of round 1 (kept for A/B timing; same values)
-#endif
+#define HK_POOLED_INDIRECT 0     // default of hk_set_tuning(HK_TUNE_POOLED_INDIRECT): 0 = per-pixel k_indirect, 1 = kc_indirect (ray pool).
+#endif                            // Same values either way; measured on B200 (profiles/r2_pooled_indirect_ab.txt) the per-pixel form is faster.
 
 using namespace hkd;
 
@@ -63,6 +63,7 @@ struct hk_context {
     Counters* counters = nullptr;
     SpatialTable* spatial_tables = nullptr;
     bool count_rays = false, time_passes = false, keep_intermediates = false;
+    bool pooled_indirect = HK_POOLED_INDIRECT != 0;   // hk_set_tuning(HK_TUNE_POOLED_INDIRECT)
     // pipelined read-back (hk_readback_async): copy stream + "frame submitted" / "copy landed" events
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_submitted = nullptr, ev_copied = nullptr;
@@ -735,7 +736,7 @@ static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, li
     if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_EMISSIVE_SPATIAL); hk_launch_spatial(P, true, ctx->stream); }
     rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     { KernelTimer t(ctx, HK_K_INDIRECT);
-      if (HK_POOLED_INDIRECT) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
+      if (ctx->pooled_indirect) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
       else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
       hk_launch_scatter_resolve(P, 2, ctx->stream); ctx->launches += 1; }
     if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); hk_launch_spatial(P, false, ctx->stream); }
@@ -813,6 +814,42 @@ int hk_post_process_run(hk_context* ctx, const hk_frame_inputs* in) {
     ctx->launches = 0;
     return run_post(ctx, P, false);
 }
+// Test hook: ONE pass of the path on whatever the planes hold (e.g. state uploaded with hk_upload_state), so that a pass can be
+// compared with the oracle's from identical inputs.  Pass ids as oracle/hk_oracle.cpp hko_run_pass: 0 albedo, 1 direct_lit (sun),
+// 2 direct_lit (emissive), 3 spatial_reuse (emissive), 4 indirect_lit_ambient, 5 spatial_reuse (indirect), 6 the denoise chain
+// (demodulation + four levels, all signals at once; level 3 writes HK_OUT_DENOISED_*), 7 tone mapping.
+int hk_run_pass(hk_context* ctx, const hk_frame_inputs* in, int pass, int arg) {
+    (void)arg;
+    KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
+    ctx->launches = 0;
+    const hk_frame_uniform& f = P.in.frame;
+    const int GS = ::GHOST_SPATIAL + ring_of(P), GT = GHOST_TEMPORAL + ctx->motion_margin;
+    switch (pass) {
+        case 0: rows_deferred(ctx, P, GT); hk_launch_albedo(P, ctx->stream); break;
+        case 1: rows(ctx, P, GT); hk_launch_direct(P, false, ctx->count_rays, ctx->stream); hk_launch_scatter_resolve(P, 0, ctx->stream); break;
+        case 2: rows(ctx, P, GT); hk_launch_direct(P, true, ctx->count_rays, ctx->stream); hk_launch_scatter_resolve(P, 1, ctx->stream); break;
+        case 3: rows(ctx, P, GS); hk_launch_spatial(P, true, ctx->stream); break;
+        case 4:
+            rows(ctx, P, GT);
+            if (ctx->pooled_indirect) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
+            else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
+            hk_launch_scatter_resolve(P, 2, ctx->stream);
+            break;
+        case 5: rows(ctx, P, GS); hk_launch_spatial(P, false, ctx->stream); break;
+        case 6: {
+            const int ring = ring_of(P), signals = (f.indirect_bounces == 0) ? 2 : 3;
+            rows(ctx, P, ::GHOST_DEMOD + ring); hk_launch_demodulation(P, signals, ctx->stream);
+            rows(ctx, P, ::GHOST_L0 + ring); hk_launch_denoise_level(P, 0, signals, false, false, ctx->stream);
+            rows(ctx, P, ::GHOST_L1 + ring); hk_launch_denoise_level(P, 1, signals, false, false, ctx->stream);
+            rows(ctx, P, ::GHOST_L2 + ring); hk_launch_denoise_level(P, 2, signals, false, false, ctx->stream);
+            rows(ctx, P, ring); hk_launch_denoise_level(P, 3, signals, false, true, ctx->stream);
+            break;
+        }
+        case 7: rows(ctx, P, ring_of(P)); order_behind_copy(ctx); hk_launch_tone_mapping(P, ctx->stream); break;
+        default: return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown pass id");
+    }
+    return check_launch(ctx);
+}
 int hk_render_frame(hk_context* ctx, const hk_frame_inputs* in) {
     KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
     ctx->launches = 0;
@@ -844,6 +881,13 @@ int hk_set_profiling(hk_context* ctx, int count_rays, int time_passes) {
     ctx->count_rays = count_rays != 0;
     ctx->time_passes = time_passes != 0;
     return HK_OK;
+}
+int hk_set_tuning(hk_context* ctx, int key, int value) {
+    if (!ctx) return HK_ERR_INVALID_ARGUMENT;
+    switch (key) {
+        case HK_TUNE_POOLED_INDIRECT: ctx->pooled_indirect = value != 0; return HK_OK;
+        default: return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown tuning key");
+    }
 }
 int hk_set_profiling_kernel(hk_context* ctx, int kernel) {
     if (!ctx || kernel >= HK_K_COUNT) return HK_ERR_INVALID_ARGUMENT;

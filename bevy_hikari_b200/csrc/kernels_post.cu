@@ -10,8 +10,9 @@
 #include "hk_device.cuh"
 #include "hk_kernels.h"
 
+// Measured on B200 (profiles/r2_baseline_variants.txt): unconditional, batched tap loads take the four levels from 0.574 to 0.524 ms.
 #ifndef HK_DENOISE_BRANCHFREE
-#define HK_DENOISE_BRANCHFREE 0
+#define HK_DENOISE_BRANCHFREE 1
 #endif
 
 namespace hkd {
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
         const int OX[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
         const int OY[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
 #if HK_DENOISE_BRANCHFREE
-        // Tuning variant (off by default; validated bit-exact on the emulated kernels, not yet timed on a GPU): every tap's
+        // Default since round 2 (timed on B200; -DHK_DENOISE_BRANCHFREE=0 restores the branchy form): every tap's
         // loads are unconditional — out-of-frame taps read a clamped, valid address — and go through the read-only path, so
         // nothing but register pressure keeps the compiler from issuing the loads of later taps during the arithmetic of
         // earlier ones; only the accumulation is predicated.  Same operations on the same values for every tap that counts.

@@ -1,0 +1,195 @@
+// kernels_spatial.cu — spatial reuse of the ReSTIR reservoirs (light.wgsl:1500-1684), both pipelines.  In its own translation unit
+// because it traces no rays: nothing in here decides visibility or an id, so the product build compiles it (like kernels_post.cu)
+// with the tolerance flags of build.py (FMA contraction, approximate division / square root / exp), while the kernels that walk the
+// BVH stay on exact arithmetic.  The exact build compiles it like everything else and is bit-identical to the oracle.
+#include "hk_device.cuh"
+#include "hk_kernels.h"
+
+#ifndef HK_NO_TEXTURE_VARIANT
+#define HK_NO_TEXTURE_VARIANT 1
+#endif
+// Measured on B200 (profiles/r2_baseline_variants.txt): requesting a neighbour's reservoir together with its depth and dividing by
+// the frame size with a host-computed reciprocal (exact whenever the quotient is normal) take 0.93 -> 0.88 ms off the two launches.
+#ifndef HK_SPATIAL_EAGER_LOAD
+#define HK_SPATIAL_EAGER_LOAD 1
+#endif
+#ifndef HK_SPATIAL_FAST_DIV
+#define HK_SPATIAL_FAST_DIV 1
+#endif
+
+namespace hkd {
+
+template <bool TEX>
+__device__ __forceinline__ DeviceScene scene_variant(const DeviceScene& scene) {
+    DeviceScene sc = scene;
+    if (!TEX) sc.texture_count = 0u;     // constant-folds every `sc.texture_count != 0u` below it
+    return sc;
+}
+
+// ----------------------------------------------------------------------------------- P4: spatial_reuse
+// light.wgsl:1500-1684.  The reference's 8x8 workgroup cache holds unpack(reservoir_buffer[..]) of this dispatch's
+// read-only input, so gathering neighbours straight from the planes (L1/L2-resident) is value-identical.
+template <bool EMISSIVE_LIT, bool TEX = true>
+__global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const __grid_constant__ KParams P) {
+    constexpr int SIGNAL = EMISSIVE_LIT ? 1 : 2;
+    constexpr uint32_t SPATIAL_REUSE_COUNT = EMISSIVE_LIT ? 8u : 16u;   // light.wgsl:246-252
+    constexpr float SPATIAL_REUSE_RANGE = EMISSIVE_LIT ? 10.0f : 20.0f;
+    constexpr uint32_t SPATIAL_REUSE_TAPS = 4u;
+    int x, y;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
+    const DeviceScene sc = scene_variant<TEX>(P.scene);
+    const hk_frame_uniform& frame = P.in.frame;
+    const size_t idx = render_index(P.band, x, y);
+    const size_t gidx = light_gbuffer_index(P, x, y, idx);
+    const PassBuffers B = bind(P, SIGNAL);
+    const float4 pd = P.planes.pos_depth[gidx];
+    const float depth = pd.w;
+    const PackedQuarters own = load_quarters(B.reservoir, idx);
+    if (depth < F32_EPSILON) {
+        // store_spatial_reservoir(pack(unpack(x))): keep the re-pack, it is not the identity for every bit pattern
+        store_quarters(B.spatial_reservoir, idx, pack_reservoir(unpack_reservoir(own)));
+        P.planes.render[SIGNAL][idx] = make_uint2(0u, 0u);
+        return;
+    }
+    Reservoir r = unpack_reservoir(own);
+    const ShadeEnv env = make_env(P);
+    const vec3 position = f4xyz(pd);
+    const float2 imf = P.planes.instance_material[gidx];
+    const float4 vu = P.planes.velocity_uv[gidx];
+    const Surface surface = retreive_surface(sc, f32_to_u32(imf.y), v2(vu.z, vu.w));
+    const bool use_spatial_variance = r.count <= 4.0f;
+    const vec2 uv = pixel_uv(P, x, y);
+    const vec2 previous_uv = jittered_deferred_uv(P, uv, 0.25f) - v2(vu.x, vu.y);
+
+    Reservoir q = r;
+    const Sample s = q.s;
+    const float lifetime_limit = (frame.max_reservoir_lifetime <= 1.0f) ? F32_MAX : frame.max_reservoir_lifetime;  // light.wgsl:913-915
+    if (r.lifetime <= lifetime_limit) {
+        size_t pidx;
+        r = zero_reservoir();
+        if (previous_pixel(P, previous_uv, false, pidx)) r = unpack_reservoir(load_quarters(B.previous_spatial_reservoir, pidx));
+    }
+    const vec3 view_direction = calculate_view(env, position);
+    const ShadeCtx shade_ctx = make_shade_ctx(env, view_direction, s.visible_normal, surface);   // shared by every shading below
+    if (EMISSIVE_LIT) {
+        merge_reservoir(r, q, luminance(xyz(q.s.radiance)));
+    } else {
+        vec3 out_radiance = shade(shade_ctx, normalize(xyz(s.sample_position) - xyz(s.visible_position)), s.radiance);
+        merge_reservoir(r, q, luminance(out_radiance));
+    }
+    r.s.visible_position = s.visible_position;
+    r.s.visible_normal = s.visible_normal;
+
+    const vec2 size_f = v2((float)P.band.RW, (float)P.band.RH);
+    const SpatialTable& T = P.spatial_tables[EMISSIVE_LIT ? 1 : 0];
+    const float rotation = sum4(s.random);
+    for (uint32_t i = 1u; i <= SPATIAL_REUSE_COUNT; i += 1u) {
+        float ang = TAU * fract(T.phase[i] + rotation + P.random_frame);
+        const float rad = T.radius[i];
+        float sn, cs;
+        sincos_(ang, &sn, &cs);
+        vec2 offset = rad * v2(cs, sn);
+        int sx = f32_to_i32(offset.x + (float)x), sy = f32_to_i32(offset.y + (float)y);
+        // light.wgsl:1577-1580 tests sample_uv = (coords + 0.5) / size against [0, 1].  For integer coords and size < 2^22
+        // the correctly rounded quotient is < 0 iff coords < 0 and > 1 iff coords >= size ((size - 0.5) / size < 1 and
+        // (size + 0.5) / size >= 1 + 2^-23 survive rounding), so the two IEEE divisions per neighbour are not needed.
+        if (sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH) continue;
+        const size_t sidx = render_index(P.band, sx, sy);
+#if HK_SPATIAL_EAGER_LOAD
+        // Default since round 2 (timed on B200; -DHK_SPATIAL_EAGER_LOAD=0 restores the two-step form): the neighbour's reservoir
+        // is requested together with its depth instead of after the depth test, so a neighbour exposes one load latency
+        // instead of two; rejected neighbours cost 64 bytes of L1/L2 traffic more.
+        const float* depth_ptr = &P.planes.pos_depth[light_gbuffer_index(P, sx, sy, sidx)].w;
+        const float sample_depth = __ldg(depth_ptr);
+        PackedQuarters packed;
+        packed.q0 = __ldg(&B.reservoir.q[0][sidx]); packed.q1 = __ldg(&B.reservoir.q[1][sidx]);
+        packed.q2 = __ldg(&B.reservoir.q[2][sidx]); packed.q3 = __ldg(&B.reservoir.q[3][sidx]);
+        float depth_ratio = depth / sample_depth;
+        if (depth_ratio < 0.9f || depth_ratio > 1.1f) continue;
+        q = unpack_reservoir(packed);
+#else
+        const float sample_depth = P.planes.pos_depth[light_gbuffer_index(P, sx, sy, sidx)].w;
+        float depth_ratio = depth / sample_depth;
+        if (depth_ratio < 0.9f || depth_ratio > 1.1f) continue;
+        q = unpack_reservoir(load_quarters(B.reservoir, sidx));
+#endif
+        bool normal_miss = dot(s.visible_normal, q.s.visible_normal) < 0.866f;
+        if (q.count < F32_EPSILON || normal_miss) continue;
+        vec3 sample_direction = normalize(xyz(q.s.sample_position) - xyz(s.visible_position));
+        if (dot(sample_direction, s.visible_normal) < 0.0f) continue;
+
+        // screen-space depth march towards the neighbour (light.wgsl:1608-1628)
+        const uint32_t tap_count = T.tap_count[i];
+        bool occluded = false;
+        vec2 unit = normalize(offset);
+        for (uint32_t j = 1u; j <= tap_count; j += 1u) {
+            float tap_dist = T.tap_dist[i][j - 1u];
+#if HK_SPATIAL_FAST_DIV
+            // Default since round 2 (-DHK_SPATIAL_FAST_DIV=0 restores the IEEE division): x / C for the frame constant C as q = x * y, r = fma(-q, C, x), fma(r, y, q)
+            // with y = RN(1 / C) from the host — the correctly rounded quotient whenever it is a normal number
+            // (tools/check_runtime_division.cpp: all 2^32 inputs for the benchmark extents); a subnormal quotient is absorbed
+            // by the addition to uv >= 0.5 / size.
+            const vec2 tap_offset = tap_dist * unit;
+            const float qx = tap_offset.x * P.inv_rw, qy = tap_offset.y * P.inv_rh;
+            vec2 tap_uv = uv + v2(fmaf(fmaf(-qx, size_f.x, tap_offset.x), P.inv_rw, qx), fmaf(fmaf(-qy, size_f.y, tap_offset.y), P.inv_rh, qy));
+#else
+            vec2 tap_uv = uv + (tap_dist * unit) / size_f;
+#endif
+            vec2 tap_deferred_uv = jittered_deferred_uv(P, tap_uv, 0.25f);
+            int tx = f32_to_i32(tap_deferred_uv.x * (float)P.band.W), ty = f32_to_i32(tap_deferred_uv.y * (float)P.band.H);
+            float tap_depth = 0.0f;  // out-of-bounds textureLoad -> 0
+            if (tx >= 0 && tx < P.band.W && ty >= 0 && ty < P.band.H) tap_depth = P.planes.pos_depth[band_index(P.band, tx, ty)].w;
+            float ref_depth = mixf(depth, sample_depth, T.tap_ratio[i][j - 1u]);
+            if (tap_depth > ref_depth + 0.00001f) { occluded = true; break; }
+        }
+        if (occluded) continue;
+
+        float jacobian = (q.s.sample_position.w > 0.5f) ? compute_jacobian(q.s, s) : 1.0f;
+        if (EMISSIVE_LIT) {
+            merge_reservoir(r, q, luminance(xyz(q.s.radiance)) / jacobian);
+        } else {
+            vec3 out_radiance = shade(shade_ctx, sample_direction, q.s.radiance);
+            merge_reservoir(r, q, luminance(out_radiance) / jacobian);
+        }
+    }
+
+    float m = (float)frame.max_spatial_reuse_count;
+    if (r.count > m) {
+        r.w_sum *= m / r.count;
+        r.w2_sum *= m / r.count;
+        r.count = m;
+    }
+    vec3 out_radiance = shade(shade_ctx, normalize(xyz(r.s.sample_position) - xyz(s.visible_position)), r.s.radiance);
+    float total_lum = EMISSIVE_LIT ? r.count * luminance(xyz(r.s.radiance)) : r.count * luminance(out_radiance);
+    r.w = (total_lum > 0.0f) ? r.w_sum / total_lum : 0.0f;
+    r.lifetime += 1.0f;
+    store_quarters(B.spatial_reservoir, idx, pack_reservoir(r));
+    if (use_spatial_variance) P.planes.variance[SIGNAL][idx] = variance_of(r);
+    vec3 out_color = r.w * out_radiance;   // RENDER_EMISSIVE is never set on the spatial pipelines (light.rs:433-442)
+    uvec2 o = pack_rgba16f(v4(out_color, 1.0f));
+    P.planes.render[SIGNAL][idx] = make_uint2(o.x, o.y);
+}
+
+
+static dim3 grid_for(const KParams& P) {
+    int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
+    return dim3((unsigned)((cols + TILE_W - 1) / TILE_W), (unsigned)((rows + TILE_H - 1) / TILE_H), 1u);
+}
+
+}  // namespace hkd
+
+using namespace hkd;
+
+static inline bool no_texture(const KParams& P) { return HK_NO_TEXTURE_VARIANT && P.scene.texture_count == 0u; }
+
+void hk_launch_spatial(const KParams& P, bool emissive, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+    if (no_texture(P)) {
+        if (emissive) k_spatial<true, false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+        else k_spatial<false, false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+        return;
+    }
+    if (emissive) k_spatial<true><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+    else k_spatial<false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+}

@@ -11,6 +11,7 @@ from . import layout as L
 from ._ffi import Settings, check, host_lib, lib
 
 TAA_JASMINE, TAA_NONE = 0, 1
+TUNE_POOLED_INDIRECT = 1
 UPSCALE_FSR1, UPSCALE_SMAA_TU4X = 0, 1
 NOISE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "noise_rgba8_64x64x16.bin")
 
@@ -166,24 +167,25 @@ def scene_desc_from_buffers(buffers, textures=()):
 class HikariPlugin:
     """HikariPlugin + one camera with `CameraRenderGraph::new(graph::NAME)` (src/lib.rs:95-370)."""
 
-    def __init__(self, width, height, cuda_device=0, row_begin=0, row_end=None, cuda_stream=None, col_begin=0, col_end=None):
+    def __init__(self, width, height, cuda_device=0, row_begin=0, row_end=None, cuda_stream=None, col_begin=0, col_end=None, flavor=None):
+        self._lib = lib(flavor)        # "product" | "exact" | None = _ffi.DEFAULT_FLAVOR
         self.width, self.height = width, height
         self.row_begin, self.row_end = row_begin, height if row_end is None else row_end
         self.col_begin, self.col_end = col_begin, width if col_end is None else col_end
-        self._p = lib().hikari_plugin_create()
+        self._p = self._lib.hikari_plugin_create()
         noise = load_noise()
-        rc = lib().hikari_plugin_build_tile(self._p, cuda_device, width, height, self.col_begin, self.col_end, self.row_begin,
+        rc = self._lib.hikari_plugin_build_tile(self._p, cuda_device, width, height, self.col_begin, self.col_end, self.row_begin,
                                             self.row_end, noise.ctypes.data, cuda_stream)
         if rc != _ffi.HK_OK:
-            msg = lib().hk_last_error(None).decode()
-            lib().hikari_plugin_destroy(self._p)
+            msg = self._lib.hk_last_error(None).decode()
+            self._lib.hikari_plugin_destroy(self._p)
             self._p = None
             raise _ffi.HikariError(f"HikariPlugin.build failed ({rc}): {msg}")
-        self.ctx = lib().hikari_plugin_context(self._p)
+        self.ctx = self._lib.hikari_plugin_context(self._p)
 
     def close(self):
         if getattr(self, "_p", None):
-            lib().hikari_plugin_destroy(self._p)
+            self._lib.hikari_plugin_destroy(self._p)
             self._p = None
             self.ctx = None
 
@@ -198,51 +200,53 @@ class HikariPlugin:
         return self.col_end - self.col_begin
 
     def upload_scene(self, world):
-        check(lib().hikari_plugin_upload_scene(self._p, world._w), self.ctx)
+        check(self._lib.hikari_plugin_upload_scene(self._p, world._w), self.ctx, self._lib)
 
     def upload_scene_desc(self, desc):
-        check(lib().hk_scene_upload(self.ctx, C.byref(desc)), self.ctx)
+        check(self._lib.hk_scene_upload(self.ctx, C.byref(desc)), self.ctx, self._lib)
 
     def update_instances(self, world):
-        check(lib().hikari_plugin_update_instances(self._p, world._w), self.ctx)
+        check(self._lib.hikari_plugin_update_instances(self._p, world._w), self.ctx, self._lib)
 
     def update_instances_desc(self, desc):
-        check(lib().hk_scene_update_instances(self.ctx, C.byref(desc)), self.ctx)
+        check(self._lib.hk_scene_update_instances(self.ctx, C.byref(desc)), self.ctx, self._lib)
 
     @property
     def frame_counter(self):
-        return lib().hikari_plugin_frame_counter(self._p)
+        return self._lib.hikari_plugin_frame_counter(self._p)
 
     @frame_counter.setter
     def frame_counter(self, v):
-        lib().hikari_plugin_set_frame_counter(self._p, int(v))
+        self._lib.hikari_plugin_set_frame_counter(self._p, int(v))
 
     def set_temporal_upscalers(self, enabled):
-        lib().hikari_plugin_set_temporal_upscalers(self._p, 1 if enabled else 0)
+        self._lib.hikari_plugin_set_temporal_upscalers(self._p, 1 if enabled else 0)
 
     def run_frame(self, settings, view, previous_view, lights):
-        check(lib().hikari_plugin_run_frame(self._p, C.byref(settings), C.byref(view), C.byref(previous_view), C.byref(lights)),
-              self.ctx)
+        check(self._lib.hikari_plugin_run_frame(self._p, C.byref(settings), C.byref(view), C.byref(previous_view), C.byref(lights)),
+              self.ctx, self._lib)
 
     # individual nodes / raw C ABI
-    def prepass(self, inputs): check(lib().hk_prepass_run(self.ctx, C.byref(inputs)), self.ctx)
-    def light(self, inputs): check(lib().hk_light_run(self.ctx, C.byref(inputs)), self.ctx)
-    def post_process(self, inputs): check(lib().hk_post_process_run(self.ctx, C.byref(inputs)), self.ctx)
-    def render_frame(self, inputs): check(lib().hk_render_frame(self.ctx, C.byref(inputs)), self.ctx)
-    def sync(self): check(lib().hk_sync(self.ctx), self.ctx)
-    def reset_temporal_state(self): check(lib().hk_reset_temporal_state(self.ctx), self.ctx)
-    def set_profiling(self, count_rays, time_passes): check(lib().hk_set_profiling(self.ctx, int(count_rays), int(time_passes)), self.ctx)
-    def set_profiling_kernel(self, kernel): check(lib().hk_set_profiling_kernel(self.ctx, int(kernel)), self.ctx)
-    def set_keep_intermediates(self, keep): check(lib().hk_set_keep_intermediates(self.ctx, int(keep)), self.ctx)
+    def prepass(self, inputs): check(self._lib.hk_prepass_run(self.ctx, C.byref(inputs)), self.ctx, self._lib)
+    def light(self, inputs): check(self._lib.hk_light_run(self.ctx, C.byref(inputs)), self.ctx, self._lib)
+    def run_pass(self, inputs, which, arg=0): check(self._lib.hk_run_pass(self.ctx, C.byref(inputs), int(which), int(arg)), self.ctx, self._lib)
+    def post_process(self, inputs): check(self._lib.hk_post_process_run(self.ctx, C.byref(inputs)), self.ctx, self._lib)
+    def render_frame(self, inputs): check(self._lib.hk_render_frame(self.ctx, C.byref(inputs)), self.ctx, self._lib)
+    def sync(self): check(self._lib.hk_sync(self.ctx), self.ctx, self._lib)
+    def reset_temporal_state(self): check(self._lib.hk_reset_temporal_state(self.ctx), self.ctx, self._lib)
+    def set_profiling(self, count_rays, time_passes): check(self._lib.hk_set_profiling(self.ctx, int(count_rays), int(time_passes)), self.ctx, self._lib)
+    def set_tuning(self, key, value): check(self._lib.hk_set_tuning(self.ctx, int(key), int(value)), self.ctx, self._lib)
+    def set_profiling_kernel(self, kernel): check(self._lib.hk_set_profiling_kernel(self.ctx, int(kernel)), self.ctx, self._lib)
+    def set_keep_intermediates(self, keep): check(self._lib.hk_set_keep_intermediates(self.ctx, int(keep)), self.ctx, self._lib)
 
     def stats(self):
         s = L.FrameStats()
-        check(lib().hk_get_stats(self.ctx, C.byref(s)), self.ctx)
+        check(self._lib.hk_get_stats(self.ctx, C.byref(s)), self.ctx, self._lib)
         return s
 
     def output_extent(self, which):
         w, h = C.c_uint32(), C.c_uint32()
-        check(lib().hk_output_extent(self.ctx, which, C.byref(w), C.byref(h)), self.ctx)
+        check(self._lib.hk_output_extent(self.ctx, which, C.byref(w), C.byref(h)), self.ctx, self._lib)
         return w.value, h.value
 
     def readback(self, which, out=None):
@@ -251,79 +255,79 @@ class HikariPlugin:
         n = w * h
         if out is None:
             out = np.empty(n * bpp, np.uint8)
-        check(lib().hk_readback(self.ctx, which, out.ctypes.data, n * bpp), self.ctx)
+        check(self._lib.hk_readback(self.ctx, which, out.ctypes.data, n * bpp), self.ctx, self._lib)
         return view_plane(out[:n * bpp], which, h, w)
 
     def readback_into(self, which, host_ptr, nbytes):
-        check(lib().hk_readback(self.ctx, which, host_ptr, nbytes), self.ctx)
+        check(self._lib.hk_readback(self.ctx, which, host_ptr, nbytes), self.ctx, self._lib)
 
     def readback_async(self, which, pinned_host_ptr, nbytes):
-        check(lib().hk_readback_async(self.ctx, which, pinned_host_ptr, nbytes), self.ctx)
+        check(self._lib.hk_readback_async(self.ctx, which, pinned_host_ptr, nbytes), self.ctx, self._lib)
 
     def readback_wait(self):
-        check(lib().hk_readback_wait(self.ctx), self.ctx)
+        check(self._lib.hk_readback_wait(self.ctx), self.ctx, self._lib)
 
     # exact tiling under camera motion
     def set_motion_margin(self, pixels):
-        check(lib().hk_context_set_motion_margin(self.ctx, int(pixels)), self.ctx)
+        check(self._lib.hk_context_set_motion_margin(self.ctx, int(pixels)), self.ctx, self._lib)
 
     def enable_tile_upscalers(self, enabled=True):
-        check(lib().hk_context_enable_tile_upscalers(self.ctx, 1 if enabled else 0), self.ctx)
+        check(self._lib.hk_context_enable_tile_upscalers(self.ctx, 1 if enabled else 0), self.ctx, self._lib)
 
     def halo_pull(self, source):
-        check(lib().hk_halo_pull(self.ctx, source.ctx), self.ctx)
+        check(self._lib.hk_halo_pull(self.ctx, source.ctx), self.ctx, self._lib)
 
     HALO_DESCRIPTOR_BYTES = 44 * 64 + 11 * 4
 
     def halo_export(self):
         """bytes of an hk_halo_descriptor (CUDA IPC handles of the reservoir planes + tile rectangles) for another process"""
         buf = (C.c_uint8 * self.HALO_DESCRIPTOR_BYTES)()
-        check(lib().hk_halo_export(self.ctx, buf), self.ctx)
+        check(self._lib.hk_halo_export(self.ctx, buf), self.ctx, self._lib)
         return bytes(buf)
 
     def halo_import(self, descriptor):
         buf = (C.c_uint8 * self.HALO_DESCRIPTOR_BYTES).from_buffer_copy(descriptor)
         peer = C.c_void_p()
-        check(lib().hk_halo_import(self.ctx, buf, C.byref(peer)), self.ctx)
+        check(self._lib.hk_halo_import(self.ctx, buf, C.byref(peer)), self.ctx, self._lib)
         return peer
 
     def halo_pull_peer(self, peer):
-        check(lib().hk_halo_pull_peer(self.ctx, peer), self.ctx)
+        check(self._lib.hk_halo_pull_peer(self.ctx, peer), self.ctx, self._lib)
 
     # frame assembly across tiles / GPUs (hk_set_frame_target)
     def frame_alloc(self):
         p = C.c_void_p()
         handle = (C.c_uint8 * 64)()
-        check(lib().hk_frame_alloc(self.ctx, C.byref(p), handle), self.ctx)
+        check(self._lib.hk_frame_alloc(self.ctx, C.byref(p), handle), self.ctx, self._lib)
         return p.value, bytes(handle)
 
     def frame_open(self, handle):
         p = C.c_void_p()
         buf = (C.c_uint8 * 64).from_buffer_copy(handle)
-        check(lib().hk_frame_open(self.ctx, buf, C.byref(p)), self.ctx)
+        check(self._lib.hk_frame_open(self.ctx, buf, C.byref(p)), self.ctx, self._lib)
         return p.value
 
     def set_frame_target(self, device_ptr, pitch_pixels=None):
-        check(lib().hk_set_frame_target(self.ctx, device_ptr, self.width if pitch_pixels is None else pitch_pixels), self.ctx)
+        check(self._lib.hk_set_frame_target(self.ctx, device_ptr, self.width if pitch_pixels is None else pitch_pixels), self.ctx, self._lib)
 
     def frame_read(self, device_ptr):
         out = np.empty(self.width * self.height * 8, np.uint8)
-        check(lib().hk_frame_read(self.ctx, device_ptr, out.ctypes.data, out.size), self.ctx)
+        check(self._lib.hk_frame_read(self.ctx, device_ptr, out.ctypes.data, out.size), self.ctx, self._lib)
         return view_plane(out, L.OUT_TONE_MAPPED, self.height, self.width)
 
     def upload_state(self, which, array):
         a = np.ascontiguousarray(array)
-        check(lib().hk_upload_state(self.ctx, which, a.ctypes.data, a.nbytes), self.ctx)
+        check(self._lib.hk_upload_state(self.ctx, which, a.ctypes.data, a.nbytes), self.ctx, self._lib)
 
     def output_device_pointer(self, which=L.OUT_TONE_MAPPED):
         p, b = C.c_void_p(), C.c_size_t()
-        check(lib().hk_get_output(self.ctx, which, C.byref(p), C.byref(b)), self.ctx)
+        check(self._lib.hk_get_output(self.ctx, which, C.byref(p), C.byref(b)), self.ctx, self._lib)
         return p.value, b.value
 
     def trace_rays(self, rays):
         rays = np.ascontiguousarray(rays, L.RAY)
         hits = np.zeros(len(rays), L.HIT)
-        check(lib().hk_trace_rays(self.ctx, rays.ctypes.data, len(rays), hits.ctypes.data), self.ctx)
+        check(self._lib.hk_trace_rays(self.ctx, rays.ctypes.data, len(rays), hits.ctypes.data), self.ctx, self._lib)
         return hits
 
 

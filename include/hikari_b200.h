@@ -186,6 +186,10 @@ int hk_prepass_run(hk_context* ctx, const hk_frame_inputs* in);
 int hk_light_run(hk_context* ctx, const hk_frame_inputs* in);
 int hk_post_process_run(hk_context* ctx, const hk_frame_inputs* in);
 int hk_render_frame(hk_context* ctx, const hk_frame_inputs* in);     /* prepass -> light -> post process */
+/* Test hook: ONE pass on whatever the planes hold (hk_upload_state), for per-pass comparison with the oracle from identical inputs.
+ * pass: 0 albedo, 1 direct_lit sun, 2 direct_lit emissive, 3 spatial_reuse emissive, 4 indirect_lit_ambient, 5 spatial_reuse indirect,
+ * 6 denoise chain (all signals; writes HK_OUT_DENOISED_*), 7 tone mapping. */
+int hk_run_pass(hk_context* ctx, const hk_frame_inputs* in, int pass, int arg);
 
 int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes);  /* final images only: HK_OUT_TONE_MAPPED (owned
                                                                                      rectangle), HK_OUT_UPSCALED, HK_OUT_TAA */
@@ -251,6 +255,11 @@ int hk_set_profiling(hk_context* ctx, int count_rays, int time_passes);
  * (timed_frames = how many).  bench.py uses it to measure the dominant kernel live inside the timed region without the ~30 event
  * records of full pass timing.  kernel < 0 restores per-pass timing as selected by hk_set_profiling. */
 int hk_set_profiling_kernel(hk_context* ctx, int kernel);
+/* Implementation choices that do not change a single output value (both forms are held to the same parity suite).
+ * HK_TUNE_POOLED_INDIRECT: 1 = the indirect pass runs as kc_indirect (per-CTA shared-memory ray pool, dynamic fetch, TMA-staged scene
+ * records, kernels_pool.cu), 0 = as the per-pixel k_indirect (default: faster on B200 for every benchmark scene). */
+enum { HK_TUNE_POOLED_INDIRECT = 1 };
+int hk_set_tuning(hk_context* ctx, int key, int value);
 int hk_set_keep_intermediates(hk_context* ctx, int keep);   /* 1: hk_render_frame also writes HK_OUT_DENOISED_* */
 int hk_get_stats(hk_context* ctx, hk_frame_stats* out);
 int hk_band_rows(hk_context* ctx, uint32_t* alloc_row_begin, uint32_t* alloc_row_end); /* owned rows +- ghost rows */

@@ -12,6 +12,11 @@
 //   * sin/cos/exp2/exp are the polynomial routines below, not libm / not the SFU approximations;
 //   * pow(x,16) = 4 squarings, pow(x,0.25) = sqrt(sqrt(x)), pow(x,2) = x*x, pow(x,5) = x2*x2*x;
 //   * pack/unpack follow the WGSL spec formulas (floor(0.5 + s*clamp(x))) and RNE for f16.
+//
+// HK_FAST_MATH (device code of the product build's tolerance units only — kernels that trace no rays, see
+// bevy_hikari_b200/build.py): exp2_ is the hardware ex2.approx (2 ulp) instead of the polynomial, and the translation unit is
+// compiled with FMA contraction and approximate division / square root.  sincos_ stays the exact routine everywhere: the
+// spatial-reuse pass turns its result into integer pixel offsets, where an error of 1e-7 radians flips a neighbour now and then.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -113,6 +118,11 @@ HK_HD int32_t f32_to_i32(float f) {
 // ---------------------------------------------------------------------------------- transcendental set
 // 2^x, |rel err| < 2 ulp.  Results below 2^-126 flush to 0, above 2^128 to +inf.
 HK_HD float exp2_(float x) {
+#if defined(HK_FAST_MATH) && defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));     // MUFU.EX2: NaN -> NaN, x < -126 -> subnormal / 0, x >= 128 -> +inf
+    return y;
+#endif
     if (x != x) return x;
     if (x < -126.0f) return 0.0f;
     if (x >= 128.0f) return u2f(0x7F800000u);

@@ -18,7 +18,7 @@ fn main() {
         .flag("-lineinfo").flag("-fmad=false")                          // explicit fmaf only: the parity rule of include/hk_math.h
         .flag("-std=c++17").flag("-O3")
         .include(root.join("include")).include(&csrc);
-    for f in ["context.cu", "kernels_light.cu", "kernels_pool.cu", "kernels_post.cu", "kernels_upscale.cu"] {
+    for f in ["context.cu", "kernels_light.cu", "kernels_pool.cu", "kernels_spatial.cu", "kernels_post.cu", "kernels_upscale.cu"] {
         cuda.file(csrc.join(f));
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }

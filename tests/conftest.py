@@ -23,6 +23,13 @@ def pytest_configure(config):
         _ffi.LIB_PATH = _ffi.HOST_LIB_PATH = build_emu.build()   # one self-contained library: kernels + the whole host mirror
 
 
+    else:
+        # The 0-ulp parity suite runs on the exact flavour of the library (same sources, exact arithmetic in every translation
+        # unit); tests of the product's tolerance contract ask for flavor="product" explicitly (tests/test_gpu_tolerance.py).
+        from bevy_hikari_b200 import _ffi
+        _ffi.DEFAULT_FLAVOR = "exact"
+
+
 def pytest_collection_modifyitems(config, items):
     """A hung kernel or a dead-locked peer must fail ONE test, not take the whole GPU tier (and the box) with it: every `gpu`
     test gets a wall-clock limit when pytest-timeout is installed (it is in this image)."""
@@ -44,7 +51,7 @@ def built_libraries():
     """Both shared libraries must exist; build them if a fresh checkout has not yet (nvcc cross-compiles on CPU)."""
     from bevy_hikari_b200 import _ffi
     from oracle import oracle
-    if not os.path.exists(_ffi.LIB_PATH) or not os.path.exists(oracle.LIB_PATH):
+    if not os.path.exists(_ffi.LIB_PATH) or not os.path.exists(_ffi.EXACT_LIB_PATH) or not os.path.exists(oracle.LIB_PATH):
         import __graft_entry__
         __graft_entry__.build()
     return True
@@ -99,9 +106,9 @@ class Bench:
         o.upload_scene_desc(self.world.scene_desc())
         return o
 
-    def device(self, row_begin=0, row_end=None, col_begin=0, col_end=None):
+    def device(self, row_begin=0, row_end=None, col_begin=0, col_end=None, flavor=None):
         from bevy_hikari_b200 import plugin
-        p = plugin.HikariPlugin(self.width, self.height, 0, row_begin, row_end, None, col_begin, col_end)
+        p = plugin.HikariPlugin(self.width, self.height, 0, row_begin, row_end, None, col_begin, col_end, flavor=flavor)
         p.upload_scene(self.world)
         return p
 

@@ -161,7 +161,11 @@ static inline uint32_t emu_warp_collect(uint32_t mask, uint32_t value) {
     else c->yield_until_changed(&w.gen, g);
     return g;
 }
+// every emulated thread is "converged" only with itself: code that votes over __activemask() (traverse_top) degenerates to a
+// one-lane warp, in sequential and in cooperative launches alike
+static inline uint32_t __activemask() { return 1u << (emu_tid() & 31u); }
 static inline uint32_t __ballot_sync(uint32_t mask, int pred) {
+    if (mask == (1u << (emu_tid() & 31u))) return pred ? mask : 0u;
     const uint32_t g = emu_warp_collect(mask, pred ? 1u : 0u);
     const EmuWarpState& w = emu_cta->warps[emu_tid() >> 5];
     uint32_t r = 0;

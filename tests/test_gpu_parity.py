@@ -235,3 +235,21 @@ def test_large_mesh_bit_exact():
     hd, ho = dev.trace_rays(rays), orc.trace_rays(rays)
     assert hd.tobytes() == ho.tobytes()
     assert (hd["instance_index"] != 0xFFFFFFFF).mean() > 0.15
+
+
+@pytest.mark.parametrize("scene,size,config", [("cornell", (96, 80), "cornell_1080p"), ("city", (112, 64), "city_8k"), ("simple", (80, 64), "cornell_1080p")])
+def test_pooled_indirect_kernel_bit_exact(scene, size, config):
+    """kc_indirect (shared-memory ray pool with dynamic fetch, TMA-staged scene records; hk_set_tuning) writes the same bytes as the
+    oracle — and therefore as the default per-pixel kernel: static and moving camera, 2 and 4 bounces, tiny and deep BLASes."""
+    from bevy_hikari_b200 import plugin
+    b = Bench(scene, size[0], size[1], config=config)
+    dev, orc = b.device(), b.oracle()
+    dev.set_tuning(plugin.TUNE_POOLED_INDIRECT, 1)
+    dev.set_profiling(True, False)
+    for f in range(1, 7):
+        inp = b.inputs(f) if f < 4 else b.moving_inputs(f)
+        dev.render_frame(inp)
+        orc.render_frame(inp)
+        compare_all(dev, orc, ALL_PLANES, f)
+        sd, so = dev.stats(), orc.stats()
+        assert (sd.tlas_rays, sd.blas_rays) == (so.tlas_rays, so.blas_rays), f
