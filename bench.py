@@ -164,36 +164,43 @@ def balanced_cuts(cost, n, align=8):
     return cuts
 
 
-def plan_tiles(width, height, world, coverage=None, background_weight=0.15):
+def plan_tiles(width, height, world, coverage=None, background_weight=0.15, ghost=GHOST):
     """One (x0, x1, y0, y1) per rank.  Without a coverage map: the equal grid of tile().  With one (H' x W' booleans from
-    a low-resolution primary-ray pass, identical on every rank): vertical OR horizontal strips whose cuts equalise the
-    estimated cost (covered pixels + `background_weight` per pixel, ghost pixels included); the direction with the smaller
-    maximum wins.  Tiles then differ in size; the all-gather pads every contribution to the largest tile."""
+    a low-resolution primary-ray pass, identical on every rank): every factorisation cx x cy of `world` is tried — vertical strips,
+    horizontal strips and 2-D grids — with cuts that equalise the estimated cost along each axis (covered pixels +
+    `background_weight` per pixel), and the plan whose most expensive tile INCLUDING ITS GHOST RING is cheapest wins.  A 4 x 2 grid at
+    8 GPUs renders 30 % ghost pixels where 8 strips of a 1080p frame render 56 %.  Ranks run left to right, then top to bottom."""
     if world == 1:
         return [(0, width, 0, height)]
     if coverage is None:
         return [tile(width, height, r, world) for r in range(world)]
     cov = np.asarray(coverage, np.float64)
-    sy, sx = height / cov.shape[0], width / cov.shape[1]
-    cost_map = cov + background_weight                      # per low-res pixel
+    ry, rx = int(round(height / cov.shape[0])), int(round(width / cov.shape[1]))
+    cost = np.repeat(np.repeat(cov + background_weight, ry, axis=0), rx, axis=1)[:height, :width] / (ry * rx)
+    if cost.shape != (height, width):
+        cost = np.pad(cost, ((0, height - cost.shape[0]), (0, width - cost.shape[1])), mode="edge")
+    pre = np.zeros((height + 1, width + 1))
+    pre[1:, 1:] = cost.cumsum(axis=0).cumsum(axis=1)
+
+    def rect(x0, x1, y0, y1):
+        return pre[y1, x1] - pre[y0, x1] - pre[y1, x0] + pre[y0, x0]
+
     best = None
-    for axis, full, scale in ((1, width, sx), (0, height, sy)):
-        line = np.repeat(cost_map.sum(axis=0 if axis == 1 else 1), int(round(scale)))[:full] / scale
-        if len(line) < full:
-            line = np.pad(line, (0, full - len(line)), mode="edge")
-        if full < world * 2 * GHOST:
+    for cx in range(1, world + 1):
+        if world % cx:
             continue
-        cuts = balanced_cuts(line, world)
-        pre = np.concatenate([[0.0], np.cumsum(line)])
-        worst = max(pre[min(full, cuts[r + 1] + GHOST)] - pre[max(0, cuts[r] - GHOST)] for r in range(world))
-        if best is None or worst < best[0]:
-            best = (worst, axis, cuts)
+        cy = world // cx
+        if width < cx * 2 * ghost or height < cy * 2 * ghost:
+            continue
+        xcuts = balanced_cuts(cost.sum(axis=0), cx) if cx > 1 else [0, width]
+        ycuts = balanced_cuts(cost.sum(axis=1), cy) if cy > 1 else [0, height]
+        tiles = [(xcuts[i], xcuts[i + 1], ycuts[j], ycuts[j + 1]) for j in range(cy) for i in range(cx)]
+        worst = max(rect(max(0, x0 - ghost), min(width, x1 + ghost), max(0, y0 - ghost), min(height, y1 + ghost)) for x0, x1, y0, y1 in tiles)
+        if best is None or worst < best[0] * 0.999:
+            best = (worst, tiles)
     if best is None:
         return [tile(width, height, r, world) for r in range(world)]
-    _, axis, cuts = best
-    if axis == 1:
-        return [(cuts[r], cuts[r + 1], 0, height) for r in range(world)]
-    return [(0, width, cuts[r], cuts[r + 1]) for r in range(world)]
+    return best[1]
 
 
 ASSET_OF = {"cornell": "cornell.glb", "city": "Low Poly/Big House{, 2, 3}.glb + Earth/earth_daymap.jpg",
@@ -356,8 +363,22 @@ def run_ours(args):
     W_, K = args.warmup, args.steps
     dev.set_temporal_upscalers(False)        # the benchmarked path ends at the tone-mapped image (SmaaTu4x{ratio 1}, Taa::None)
 
+    # --moving-camera: the camera translates a little every frame (about a pixel of image motion), so that temporal reprojection
+    # crosses tile borders — the case the reservoir-halo exchange (--halo-margin) exists for.  Default: the static benchmark camera.
+    views, pviews = [view] * (W_ + K + 1), [pview] * (W_ + K + 1)
+    if args.moving_camera:
+        from bevy_hikari_b200 import camera as cam
+        step = (0.003, 0.001, -0.002)
+
+        def view_at(f):
+            eye = tuple(e + d * (f - 1) for e, d in zip(scene.eye, step))
+            tgt = tuple(t + d * (f - 1) for t, d in zip(scene.target, step))
+            return cam.make_view(cam.look_at(eye, tgt), cam.perspective_infinite_reverse_rh(scene.fov, W / H, scene.near), W, H)
+        views = [view_at(f) for f in range(1, W_ + K + 2)]
+        pviews = [cam.make_previous_view(view_at(max(f - 1, 1))) for f in range(1, W_ + K + 2)]
+
     def frame_inputs(n):
-        return plugin.make_frame_inputs(settings, n, view, pview, lights)
+        return plugin.make_frame_inputs(settings, n, views[n - 1], pviews[n - 1], lights)
 
     inputs = [frame_inputs(n) for n in range(1, W_ + K + 1)]
     sampler = ClockSampler(local_rank)
@@ -453,9 +474,9 @@ def run_ours(args):
             frame_views = [torch.as_tensor(_Frame(p), device=f"cuda:{local_rank}") for p in frame_targets]
             host_frames = [torch.empty(frame_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
 
-        def e2e_step(n, first):
+        def e2e_step(n, first, i):
             begin_frame()
-            dev.run_frame(settings, view, pview, lights)
+            dev.run_frame(settings, views[i], pviews[i], lights)
             if rank == 0 and not first:
                 stream.wait_event(copied)            # frame barrier n is ordered behind copy n - 1
             gather_frame()
@@ -473,8 +494,8 @@ def run_ours(args):
             if rank == 0:
                 copied.synchronize()
     else:
-        def e2e_step(n, first):
-            dev.run_frame(settings, view, pview, lights)                      # host structs -> kernel parameters
+        def e2e_step(n, first, i):
+            dev.run_frame(settings, views[i], pviews[i], lights)              # host structs -> kernel parameters
             dev.readback_wait()                                               # frame n - 1 has landed in host memory
             dev.readback_async(L.OUT_TONE_MAPPED, host_bufs[n & 1], nbytes)   # D2H of this frame's tile, overlapping the next frame
             if world_size > 1:
@@ -490,13 +511,13 @@ def run_ours(args):
         dev.frame_counter = 0
         frame_no[0] = 0
         for n in range(W_):
-            e2e_step(n, n == 0)
+            e2e_step(n, n == 0, n)
         e2e_finish()
         barrier()
         t0 = time.perf_counter()
         e0.record(stream)
         for n in range(K):
-            e2e_step(n, n == 0)
+            e2e_step(n, n == 0, W_ + n)
         e2e_finish()
         e1.record(stream)
         barrier()
@@ -629,7 +650,8 @@ def run_ours(args):
         "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": f"reference assets ({ASSET_OF[cfg['scene']]}) + blue-noise seed (no synthetic inputs exist for this path)",
         "config": dict(config_json(args.config, cfg, settings, world_size, args.gather), tiles=[list(t) for t in tiles],
-                       **({"halo_margin": args.halo_margin} if (world_size > 1 and args.halo_margin is not None) else {})),
+                       **({"halo_margin": args.halo_margin} if (world_size > 1 and args.halo_margin is not None) else {}),
+                       **({"camera": "translating (0.003, 0.001, -0.002) per frame"} if args.moving_camera else {})),
         "rays_per_frame": {"light_tlas": rays[1] / K, "light_blas": rays[2] / K, "primary": rays[0] / K},
         "fps": round(1e3 / ms_per_step, 2),
         "e2e": {"value": round(e2e_value, 3), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / K, 5),
@@ -834,6 +856,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--equal-tiles", action="store_true", help="N > 1: equal grid of tiles instead of cost-balanced strips")
+    ap.add_argument("--moving-camera", action="store_true", help="translate the camera every frame (temporal reprojection crosses tile borders)")
     ap.add_argument("--halo-margin", type=int, default=None,
                     help="N > 1: exact tiling under camera motion — ghost ring of 36 + M pixels and a halo pull after every frame")
     ap.add_argument("--no-frame-check", action="store_true", help="N > 1: skip the assembled-frame == unsharded-frame check")

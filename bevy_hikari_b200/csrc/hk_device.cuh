@@ -41,11 +41,6 @@
 #ifndef HK_INL_RADIANCE
 #define HK_INL_RADIANCE __forceinline__
 #endif
-// Phase 1 of the BVH walk ends when at most 1 / HK_TRAV_DEFER_DIV of the warp's unfinished lanes are still on interior records
-// (0 = wait for every lane, the round-1 behaviour); see traverse_top.
-#ifndef HK_TRAV_DEFER_DIV
-#define HK_TRAV_DEFER_DIV 4
-#endif
 #ifndef HK_INL_SELECT
 #define HK_INL_SELECT __forceinline__
 #endif
@@ -397,6 +392,9 @@ __device__ __forceinline__ void instance_ray(const hk_instance* inst, const Ray&
 // the TLAS execute the same interior-node code together instead of serialising inner against outer loop — the nested
 // form ran at ~4 active lanes per instruction on secondary rays (ncu, profiles/r1).  Visit order, the strict '<'
 // updates and both early-outs are unchanged, so hits are bit-identical to the nested walk.
+// Round 2 tried to end phase 1 on a warp vote (as soon as at most 1/2 .. 1/8 of the lanes are still on interior records) instead of
+// waiting for the last lane: the votes and the per-lane state machine cost what the shorter waits save (cornell +3..8 %, town / city
+// -4..+6 % for k_indirect; profiles/r2_vote_ended_interior_phase_ab.txt).  Not kept.
 static __device__ HK_INL_TRAVERSE Hit traverse_top(const DeviceScene& sc, const Ray& ray, float max_distance, float early_distance,
                                             uint32_t exclude_instance) {
     Hit hit;
@@ -408,102 +406,75 @@ static __device__ HK_INL_TRAVERSE Hit traverse_top(const DeviceScene& sc, const 
     Ray cur = ray;                 // world-space ray while in the TLAS, object-space ray while in a BLAS
     bool in_blas = false, blas_hit = false;
     uint32_t tlas_resume = 0, instance_index = 0, mesh_primitive = 0;
-    // Per-lane state of the walk.  The lanes that entered together stay in the loop until the last one is done (they would wait at
-    // the reconvergence point behind it anyway), which is what lets them vote.
-    constexpr int STEP = 0, LEAF = 1, END = 2, DONE = 3;
-    int st = STEP;
-    const uint32_t warp = __activemask();
-    uint32_t unfinished = warp;
-    uint32_t entry = 0, exit_index = 0;
     for (;;) {
-        // phase 1 — interior (navigator) records, one per iteration and lane, until the lane stands on a leaf record or its level is
-        // exhausted.  The expensive leaf work below then runs for all lanes that have an event pending instead of the 3-4 that happen
-        // to be in phase with each other.  Round 1 waited here for the LAST lane (measured: interior steps at 8.8 active lanes, leaf
-        // work at 4-5); the vote ends the phase as soon as no more than 1 / HK_TRAV_DEFER_DIV of the unfinished lanes are still
-        // stepping: a lane with a long run of interior records no longer holds 31 others, it just skips this round's phase 2.
-        // A lane's own sequence of records, tests and updates is unchanged, so hits stay bit-identical.
-        for (;;) {
-            if (st == STEP) {
-                if (index < count) {
-                    // both halves of the record in one round trip (a leaf record only needs .w of each)
-                    const float4 n0 = ldg4(&nodes[index]);                                           // min.xyz | entry_index
-                    const float4 n1 = ldg4(reinterpret_cast<const float4*>(&nodes[index]) + 1);      // max.xyz | exit_index
-                    entry = __float_as_uint(n0.w);
-                    exit_index = __float_as_uint(n1.w);
-                    if (entry >= BVH_LEAF_FLAG) st = LEAF;
-                    else index = (slab(cur, f4xyz(n0), f4xyz(n1)) < hit.distance) ? entry : exit_index;
-                } else {
-                    st = END;
-                }
-            }
-            const uint32_t stepping = __ballot_sync(warp, st == STEP);
-#if HK_TRAV_DEFER_DIV > 0
-            if (__popc(stepping) * HK_TRAV_DEFER_DIV <= __popc(unfinished)) break;
-#else
-            if (stepping == 0u) break;
-#endif
+        // phase 1 — every lane steps over interior (navigator) records until it stands on a leaf record or its level is
+        // exhausted.  Lanes reconverge after this loop, so the expensive leaf work below (instance transform, triangle
+        // test) runs with all lanes that have a leaf pending instead of the 3-4 that happen to be in phase with each other.
+        uint32_t entry = 0, exit_index = 0;
+        while (index < count) {
+            // both halves of the record in one round trip (a leaf record only needs .w of each)
+            const float4 n0 = ldg4(&nodes[index]);                                           // min.xyz | entry_index
+            const float4 n1 = ldg4(reinterpret_cast<const float4*>(&nodes[index]) + 1);      // max.xyz | exit_index
+            entry = __float_as_uint(n0.w);
+            exit_index = __float_as_uint(n1.w);
+            if (entry >= BVH_LEAF_FLAG) break;
+            index = (slab(cur, f4xyz(n0), f4xyz(n1)) < hit.distance) ? entry : exit_index;
         }
-        if (st == END) {
-            if (!in_blas) st = DONE;
-            else {
-                // traverse_bottom returned: back to the TLAS record after the instance leaf
-                in_blas = false;
-                st = STEP;
-                if (blas_hit) {
-                    hit.instance_index = instance_index;
-                    if (hit.distance < early_distance) st = DONE;
-                }
-                nodes = sc.instance_nodes; count = sc.instance_node_count; index = tlas_resume;
-                cur = ray;
+        if (index >= count) {
+            if (!in_blas) break;
+            // traverse_bottom returned: back to the TLAS record after the instance leaf
+            in_blas = false;
+            if (blas_hit) {
+                hit.instance_index = instance_index;
+                if (hit.distance < early_distance) break;
             }
-        } else if (st == LEAF) {
-            // phase 2 — leaf record.  A leaf record is only ever reached through its navigator (the record before it), whose
-            // box is the shape's own AABB (bvh 0.7.1 stores the child's joint AABB = min/max of the triangle's vertices, resp.
-            // the instance's min/max) and whose slab test against the same ray and the same hit.distance has just passed.
-            // The reference repeats that test on the re-derived box (light.wgsl:411-414, 456-459); it cannot fail, so it is
-            // skipped — except for the root of a single-shape BVH (index 0), which has no navigator.
-            const bool via_navigator = index != 0u && sc.leaf_boxes_match != 0u;
-            index = exit_index;
-            st = STEP;
-            if (!in_blas) {
-                const uint32_t candidate = entry - BVH_LEAF_FLAG;
-                if (candidate != exclude_instance) {
-                    const hk_instance* inst = sc.instances + candidate;
-                    bool pass = via_navigator;
-                    if (!pass) {
-                        const float4 imin = ldg4(inst->min), imax = ldg4(inst->max);
-                        pass = slab(ray, f4xyz(imin), f4xyz(imax)) < hit.distance;
-                    }
-                    if (pass) {
-                        instance_ray(inst, ray, cur);
-                        const uint4 mesh = ldg4u(&inst->mesh);     // vertex, primitive, node_offset, node_count
-                        in_blas = true; blas_hit = false;
-                        tlas_resume = exit_index; instance_index = candidate; mesh_primitive = mesh.y;
-                        nodes = sc.asset_nodes + mesh.z; count = mesh.w; index = 0;
-                    }
+            nodes = sc.instance_nodes; count = sc.instance_node_count; index = tlas_resume;
+            cur = ray;
+            continue;
+        }
+        // phase 2 — leaf record.  A leaf record is only ever reached through its navigator (the record before it), whose
+        // box is the shape's own AABB (bvh 0.7.1 stores the child's joint AABB = min/max of the triangle's vertices, resp.
+        // the instance's min/max) and whose slab test against the same ray and the same hit.distance has just passed.
+        // The reference repeats that test on the re-derived box (light.wgsl:411-414, 456-459); it cannot fail, so it is
+        // skipped — except for the root of a single-shape BVH (index 0), which has no navigator.
+        const bool via_navigator = index != 0u && sc.leaf_boxes_match != 0u;
+        index = exit_index;
+        if (!in_blas) {
+            const uint32_t candidate = entry - BVH_LEAF_FLAG;
+            if (candidate != exclude_instance) {
+                const hk_instance* inst = sc.instances + candidate;
+                bool pass = via_navigator;
+                if (!pass) {
+                    const float4 imin = ldg4(inst->min), imax = ldg4(inst->max);
+                    pass = slab(ray, f4xyz(imin), f4xyz(imax)) < hit.distance;
                 }
-            } else {
-                const uint32_t primitive_index = mesh_primitive + entry - BVH_LEAF_FLAG;
-                const hk_primitive* prim = sc.primitives + primitive_index;
-                const float4 a = ldg4(&prim->vertices[0]), b = ldg4(&prim->vertices[1]), c = ldg4(&prim->vertices[2]);
-                const vec3 p0 = f4xyz(a), p1 = f4xyz(b), p2 = f4xyz(c);
-                if (via_navigator || slab(cur, vmin(p0, vmin(p1, p2)), vmax(p0, vmax(p1, p2))) < hit.distance) {
-                    float u, v;
-                    const float distance = triangle(cur, p0, p1, p2, u, v);
-                    if (distance < hit.distance) {
-                        hit.u = u; hit.v = v; hit.distance = distance;
-                        hit.primitive_index = primitive_index;
-                        blas_hit = true;
-                        if (distance < early_distance) {           // traverse_bottom returns, traverse_top returns
-                            hit.instance_index = instance_index;
-                            st = DONE;
-                        }
+                if (pass) {
+                    instance_ray(inst, ray, cur);
+                    const uint4 mesh = ldg4u(&inst->mesh);     // vertex, primitive, node_offset, node_count
+                    in_blas = true; blas_hit = false;
+                    tlas_resume = exit_index; instance_index = candidate; mesh_primitive = mesh.y;
+                    nodes = sc.asset_nodes + mesh.z; count = mesh.w; index = 0;
+                }
+            }
+        } else {
+            const uint32_t primitive_index = mesh_primitive + entry - BVH_LEAF_FLAG;
+            const hk_primitive* prim = sc.primitives + primitive_index;
+            const float4 a = ldg4(&prim->vertices[0]), b = ldg4(&prim->vertices[1]), c = ldg4(&prim->vertices[2]);
+            const vec3 p0 = f4xyz(a), p1 = f4xyz(b), p2 = f4xyz(c);
+            if (via_navigator || slab(cur, vmin(p0, vmin(p1, p2)), vmax(p0, vmax(p1, p2))) < hit.distance) {
+                float u, v;
+                const float distance = triangle(cur, p0, p1, p2, u, v);
+                if (distance < hit.distance) {
+                    hit.u = u; hit.v = v; hit.distance = distance;
+                    hit.primitive_index = primitive_index;
+                    blas_hit = true;
+                    if (distance < early_distance) {           // traverse_bottom returns, traverse_top returns
+                        hit.instance_index = instance_index;
+                        break;
                     }
                 }
             }
         }
-        unfinished = __ballot_sync(warp, st != DONE);
-        if (unfinished == 0u) break;
     }
     return hit;
 }
