@@ -2,8 +2,12 @@
 // scheduling on one CUDA stream (what LightNode::run / PostProcessNode::run do with a wgpu command encoder,
 // src/light.rs:590-702, src/post_process.rs:1140-1234), read-back / state upload for tests.
 #include <cuda_runtime.h>
+#ifndef HK_EMU
+#include <cuda.h>            // CUtensorMap + the enums of cuTensorMapEncodeTiled (types only: the entry point is looked up at run time)
+#endif
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,6 +60,10 @@ struct hk_context {
     DeviceScene scene{};
     bool scene_ready = false, noise_ready = false;
     bool planes_ready = false;         // allocate_planes completed: every pointer of `planes` is valid
+    // TMA descriptors of kc_spatial's tiles (hk_tile.cuh): [0] indirect (radius 20, box 56), [1] emissive (radius 10, box 36);
+    // q3 maps per buffer parity: the temporal reservoir the spatial pass reuses is reservoir[base + 1 - (frame.number & 1)]
+    TileMap tm_depth[2], tm_q3[2][2];
+    bool tile_maps_ready = false;
     bool full_frame = true;            // the context owns the whole frame (no tile): upscale_ratio > 1 and the upscalers need it
     int last_render_w = 0, last_render_h = 0; bool last_smaa = false, last_upscalers = false, last_fsr = false; uint32_t last_number = 0;   // of the last frame, for read-back sizes
     int gbuffer_current = 0;           // index of the "current" position / velocity_uv planes; toggled by every prepass
@@ -64,6 +72,7 @@ struct hk_context {
     SpatialTable* spatial_tables = nullptr;
     bool count_rays = false, time_passes = false, keep_intermediates = false;
     bool pooled_indirect = HK_POOLED_INDIRECT != 0;   // hk_set_tuning(HK_TUNE_POOLED_INDIRECT)
+    bool tiled_spatial = true;                        // hk_set_tuning(HK_TUNE_TILED_SPATIAL): kc_spatial (TMA tiles) vs k_spatial (gathers)
     // pipelined read-back (hk_readback_async): copy stream + "frame submitted" / "copy landed" events
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_submitted = nullptr, ev_copied = nullptr;
@@ -120,6 +129,53 @@ static void free_list(std::vector<void*>& list) {
     list.clear();
 }
 
+// One TMA descriptor: a 2-D tensor of `width` x `height` elements of `elem_bytes` (row pitch `pitch_bytes`) read in boxes of
+// box_w x box_h elements, no swizzle, zero fill outside.  Encoded by the driver (cuTensorMapEncodeTiled, looked up through the
+// runtime so that the library does not link libcuda); the kernel-logic emulation keeps a plain description in the same bytes.
+static bool make_tile_map(TileMap* out, void* base, uint32_t elem_bytes, uint64_t width, uint64_t height, uint64_t pitch_bytes, uint32_t box_w, uint32_t box_h) {
+    memset(out, 0, sizeof(*out));
+#ifdef HK_EMU
+    TileMapEmu m{static_cast<const unsigned char*>(base), elem_bytes, (uint32_t)width, (uint32_t)height, (uint32_t)pitch_bytes, box_w, box_h};
+    static_assert(sizeof(TileMapEmu) <= sizeof(TileMap), "emulated descriptor fits");
+    memcpy(out->bytes, &m, sizeof(m));
+    return true;
+#else
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeTiled>(fn);
+        cudaGetLastError();
+        looked_up = true;
+    }
+    if (!encode) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(TileMap), "CUtensorMap is 128 bytes");
+    const cuuint64_t dims[2] = {width, height};
+    const cuuint64_t strides[1] = {pitch_bytes};
+    const cuuint32_t box[2] = {box_w, box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    return encode(reinterpret_cast<CUtensorMap*>(out), dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+#endif
+}
+static bool make_spatial_tile_maps(hk_context* ctx) {
+    const Band& b = ctx->band;
+    const uint64_t rows = (uint64_t)(b.a1 - b.a0), pitch = (uint64_t)b.AW;
+    bool ok = true;
+    for (int v = 0; v < 2 && ok; ++v) {
+        const uint32_t box = 16u + 2u * (v ? 10u : 20u);
+        ok = make_tile_map(&ctx->tm_depth[v], ctx->planes.depth, 4, pitch, rows, pitch * 4, box, box);
+        for (int parity = 0; parity < 2 && ok; ++parity)      // quarter 3 as rows of u32, 4 per pixel
+            ok = make_tile_map(&ctx->tm_q3[v][parity], ctx->planes.reservoir[(v ? 2 : 6) + parity].q[3], 4, pitch * 4, rows, pitch * 16, box * 4, box);
+    }
+    return ok;
+}
+
 static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uint32_t col_begin, uint32_t col_end,
                            uint32_t row_begin, uint32_t row_end) {
     if (width == 0 || height == 0 || row_begin >= row_end || row_end > height || col_begin >= col_end || col_end > width)
@@ -140,7 +196,7 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     b.a1 = b.r1 + ghost > b.H ? b.H : b.r1 + ghost;
     b.ax0 = b.cx0 - ghost < 0 ? 0 : b.cx0 - ghost;
     b.ax1 = b.cx1 + ghost > b.W ? b.W : b.cx1 + ghost;
-    b.AW = b.ax1 - b.ax0;
+    b.AW = hk_plane_pitch(b.ax1 - b.ax0);
     b.RW = b.W; b.RH = b.H; b.RS = b.AW;
     ctx->band = b;
     const size_t n = (size_t)b.AW * (size_t)(b.a1 - b.a0);
@@ -156,6 +212,7 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     HK_CUDA(alloc_plane(ctx, &p.velocity_uv_db[1], n, L));
     p.pos_depth = p.pos_depth_db[0];
     p.velocity_uv = p.velocity_uv_db[0];
+    HK_CUDA(alloc_plane(ctx, &p.depth, n, L));
     HK_CUDA(alloc_plane(ctx, &p.normal, n, L));
     HK_CUDA(alloc_plane(ctx, &p.depth_gradient, n, L));
     HK_CUDA(alloc_plane(ctx, &p.instance_material, n, L));
@@ -188,6 +245,7 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
         HK_CUDA(alloc_plane(ctx, &p.taa_output[1], 4 * n, L));
     }
     if (ctx->full_frame) HK_CUDA(alloc_plane(ctx, &p.upscale_sharpen_output, n, L));   // FSR RCAS result (Upscale::Fsr1)
+    ctx->tile_maps_ready = make_spatial_tile_maps(ctx);     // false: no TMA descriptors (old driver) -> the gather form of the pass
     ctx->planes_ready = true;
     return HK_OK;
 }
@@ -217,6 +275,9 @@ int hk_context_create_tile(hk_context** out, int cuda_device, uint32_t width, ui
     HK_CUDA(cudaSetDevice(cuda_device));
     hk_context* c = new hk_context();
     c->device = cuda_device;
+    // defaults of hk_set_tuning from the environment (A/B runs of one build: HK_TUNE_POOLED_INDIRECT=1, HK_TUNE_TILED_SPATIAL=0)
+    if (const char* e = getenv("HK_TUNE_POOLED_INDIRECT")) c->pooled_indirect = atoi(e) != 0;
+    if (const char* e = getenv("HK_TUNE_TILED_SPATIAL")) c->tiled_spatial = atoi(e) != 0;
     ctx = c;
     if (cuda_stream) c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     else {
@@ -724,6 +785,12 @@ static int run_prepass(hk_context* ctx, KParams& P) {
     return check_launch(ctx);
 }
 static int ring_of(const KParams& P) { return P.tile_images ? RING_TONE : 0; }   // extra reach of every pass when a tile feeds the upscalers
+// spatial_reuse of one pipeline: the TMA-tiled kernel when descriptors exist and render space == G-buffer space, else the gather form
+static void launch_spatial(hk_context* ctx, const KParams& P, bool emissive) {
+    const int v = emissive ? 1 : 0, parity = 1 - (int)(P.in.frame.number & 1u);
+    const bool tiled = ctx->tile_maps_ready && ctx->tiled_spatial;
+    hk_launch_spatial(P, emissive, tiled ? &ctx->tm_depth[v] : nullptr, tiled ? &ctx->tm_q3[v][parity] : nullptr, ctx->stream);
+}
 static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, light.rs:645-699 (albedo is fused in the prepass)
     const hk_frame_uniform& f = P.in.frame;
     const int GHOST_SPATIAL = ::GHOST_SPATIAL + ring_of(P);
@@ -733,13 +800,13 @@ static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, li
       hk_launch_scatter_resolve(P, 0, ctx->stream); ctx->launches += 1; }
     { KernelTimer t(ctx, HK_K_EMISSIVE); hk_launch_direct(P, true, ctx->count_rays, ctx->stream);
       hk_launch_scatter_resolve(P, 1, ctx->stream); ctx->launches += 1; }
-    if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_EMISSIVE_SPATIAL); hk_launch_spatial(P, true, ctx->stream); }
+    if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_EMISSIVE_SPATIAL); launch_spatial(ctx, P, true); }
     rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     { KernelTimer t(ctx, HK_K_INDIRECT);
       if (ctx->pooled_indirect) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
       else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
       hk_launch_scatter_resolve(P, 2, ctx->stream); ctx->launches += 1; }
-    if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); hk_launch_spatial(P, false, ctx->stream); }
+    if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); launch_spatial(ctx, P, false); }
     return check_launch(ctx);
 }
 // the kernels below overwrite the final images: a pipelined read-back of the previous frame must have left them first
@@ -828,14 +895,14 @@ int hk_run_pass(hk_context* ctx, const hk_frame_inputs* in, int pass, int arg) {
         case 0: rows_deferred(ctx, P, GT); hk_launch_albedo(P, ctx->stream); break;
         case 1: rows(ctx, P, GT); hk_launch_direct(P, false, ctx->count_rays, ctx->stream); hk_launch_scatter_resolve(P, 0, ctx->stream); break;
         case 2: rows(ctx, P, GT); hk_launch_direct(P, true, ctx->count_rays, ctx->stream); hk_launch_scatter_resolve(P, 1, ctx->stream); break;
-        case 3: rows(ctx, P, GS); hk_launch_spatial(P, true, ctx->stream); break;
+        case 3: rows(ctx, P, GS); launch_spatial(ctx, P, true); break;
         case 4:
             rows(ctx, P, GT);
             if (ctx->pooled_indirect) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
             else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
             hk_launch_scatter_resolve(P, 2, ctx->stream);
             break;
-        case 5: rows(ctx, P, GS); hk_launch_spatial(P, false, ctx->stream); break;
+        case 5: rows(ctx, P, GS); launch_spatial(ctx, P, false); break;
         case 6: {
             const int ring = ring_of(P), signals = (f.indirect_bounces == 0) ? 2 : 3;
             rows(ctx, P, ::GHOST_DEMOD + ring); hk_launch_demodulation(P, signals, ctx->stream);
@@ -886,6 +953,7 @@ int hk_set_tuning(hk_context* ctx, int key, int value) {
     if (!ctx) return HK_ERR_INVALID_ARGUMENT;
     switch (key) {
         case HK_TUNE_POOLED_INDIRECT: ctx->pooled_indirect = value != 0; return HK_OK;
+        case HK_TUNE_TILED_SPATIAL: ctx->tiled_spatial = value != 0; return HK_OK;
         default: return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown tuning key");
     }
 }
@@ -1069,6 +1137,12 @@ static int transfer(hk_context* ctx, int which, void* host, size_t bytes, bool t
     if (bytes != v.w * v.h * v.bpp) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
     if (to_host) HK_CUDA(cudaMemcpy2DAsync(host, v.w * v.bpp, v.ptr, v.pitch * v.bpp, v.w * v.bpp, v.h, cudaMemcpyDeviceToHost, ctx->stream));
     else HK_CUDA(cudaMemcpy2DAsync(v.ptr, v.pitch * v.bpp, host, v.w * v.bpp, v.w * v.bpp, v.h, cudaMemcpyHostToDevice, ctx->stream));
+    if (!to_host && which == HK_OUT_GBUFFER_POSITION) {      // the planar copy of the depth follows an uploaded position plane
+        KParams P{};
+        P.planes = ctx->planes; P.planes.pos_depth = ctx->planes.pos_depth_db[ctx->gbuffer_current]; P.band = ctx->band;
+        P.row_lo = ctx->band.r0; P.row_hi = ctx->band.r1; P.col_lo = ctx->band.cx0; P.col_hi = ctx->band.cx1;
+        hk_launch_extract_depth(P, ctx->stream);
+    }
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }
@@ -1190,7 +1264,7 @@ int hk_halo_import(hk_context* ctx, const hk_halo_descriptor* remote, hk_halo_pe
     b.W = remote->frame[0]; b.H = remote->frame[1];
     b.ax0 = remote->allocated[0]; b.ax1 = remote->allocated[1]; b.a0 = remote->allocated[2]; b.a1 = remote->allocated[3];
     b.cx0 = remote->owned[0]; b.cx1 = remote->owned[1]; b.r0 = remote->owned[2]; b.r1 = remote->owned[3];
-    b.AW = b.ax1 - b.ax0; b.RW = b.W; b.RH = b.H; b.RS = b.AW;
+    b.AW = hk_plane_pitch(b.ax1 - b.ax0); b.RW = b.W; b.RH = b.H; b.RS = b.AW;
     peer->planes = Planes{};
     const int handles = remote->has_images ? 44 : 40;
     for (int i = 0; i < handles; ++i) {

@@ -100,6 +100,7 @@ struct Planes {
     float2* depth_gradient;
     float2* instance_material;
     float4* velocity_uv;
+    float* depth;               // pos_depth.w of the current frame as a plane of its own: what the TMA tile loads of kc_spatial stage
     float4* pos_depth_db[2];
     float4* velocity_uv_db[2];
     uint2* albedo;
@@ -123,11 +124,16 @@ struct Planes {
     uint2* taa_output[2];       // [frame.number % 2] is written
 };
 
+// Row pitch (in pixels) of every per-pixel plane of an allocation `w` pixels wide: a multiple of 4, so that the pitch of a 4-byte
+// plane is a multiple of 16 bytes (what a TMA tensor map requires of its strides, hk_tile.cuh).  The padding columns are never
+// part of a launch rectangle.
+__host__ __device__ inline int hk_plane_pitch(int w) { return (w + 3) & ~3; }
+
 struct Band {             // the tile of the frame one context renders (whole frame: everything 0..W, 0..H)
     int W, H;             // full image
     int ax0, ax1, a0, a1; // allocated rectangle: columns [ax0,ax1), rows [a0,a1) = owned +- ghost, clamped to the image
     int cx0, cx1, r0, r1; // owned rectangle: columns [cx0,cx1), rows [r0,r1)
-    int AW;               // ax1 - ax0: row stride of the deferred-size planes (G-buffer, albedo)
+    int AW;               // hk_plane_pitch(ax1 - ax0): row stride of the deferred-size planes (G-buffer, albedo)
     // render size = ceil(size / upscale_ratio) (light.rs:622-624).  At ratio 1 (every tiled / benchmark configuration)
     // render space == deferred space and RS == AW; at ratio > 1 (full-frame contexts only) render-size planes use stride RW.
     int RW, RH, RS;

@@ -12,6 +12,13 @@ namespace hkd {
 
 struct alignas(64) TileMap { unsigned char bytes[128]; };
 
+// the CTA's dynamic shared memory (TMA destinations must be 128-byte aligned)
+#ifdef HK_EMU
+#define HK_DYNAMIC_SMEM(name) alignas(128) static thread_local unsigned char name[128 * 1024]
+#else
+#define HK_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
 struct TileMapEmu {          // what the emulated build keeps in TileMap::bytes
     const unsigned char* base;
     uint32_t elem_bytes, width, height, pitch_bytes, box_w, box_h;   // in elements of elem_bytes

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__
         Hit hit = traverse_top(P.scene, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
         if (hit.instance_index == U32_MAX) {
             P.planes.pos_depth[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            P.planes.depth[idx] = 0.0f;
             P.planes.normal[idx] = 0u;
             P.planes.depth_gradient[idx] = make_float2(0.0f, 0.0f);
             P.planes.instance_material[idx] = make_float2(0.0f, 0.0f);
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__
             vec2 velocity = uva - uvb;
             uint32_t packed_normal = pack4x8snorm(v4(world_normal, 1.0f));
             P.planes.pos_depth[idx] = make_float4(world_position.x, world_position.y, world_position.z, depth);
+            P.planes.depth[idx] = depth;
             P.planes.normal[idx] = packed_normal;
             P.planes.depth_gradient[idx] = make_float2(grad.x, grad.y);
             P.planes.instance_material[idx] = make_float2((float)hit.instance_index + 0.5f, (float)material + 0.5f);
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_albedo(const __grid_constant__ 
     if (!tile_active(P, x, y)) return;
     const size_t idx = band_index(P.band, x, y);
     float4 pd = P.planes.pos_depth[idx];
+    P.planes.depth[idx] = pd.w;                        // the planar copy of the depth follows an externally supplied G-buffer too
     if (pd.w < F32_EPSILON) { P.planes.albedo[idx] = make_uint2(0u, 0u); return; }
     ShadeEnv env = make_env(P);
     vec3 normal = xyz(unpack4x8snorm(P.planes.normal[idx]));
@@ -454,6 +457,15 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
     flush_counters<COUNT>(P, 0u, n_tlas, n_blas);
 }
 
+// depth plane <- pos_depth.w (after hk_upload_state of the position plane)
+__global__ void __launch_bounds__(CTA_THREADS) k_extract_depth(const __grid_constant__ KParams P) {
+    int x, y;
+    tile_pixel(x, y, P);
+    if (!tile_active(P, x, y)) return;
+    const size_t idx = band_index(P.band, x, y);
+    P.planes.depth[idx] = P.planes.pos_depth[idx].w;
+}
+
 // ------------------------------------------------------------------------------------------- scatter resolve
 // Applies the winning write of each target pixel to the previous-spatial buffer of `signal` (see Planes::scatter_key).
 __global__ void __launch_bounds__(CTA_THREADS) k_scatter_resolve(const __grid_constant__ KParams P, int signal) {
@@ -508,6 +520,10 @@ void hk_launch_gbuffer(const KParams& P, bool count, cudaStream_t st) {
     if (count) k_gbuffer<true><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
     else if (no_texture(P)) k_gbuffer<false, false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
     else k_gbuffer<false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+}
+void hk_launch_extract_depth(const KParams& P, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+    k_extract_depth<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }
 void hk_launch_albedo(const KParams& P, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;

@@ -257,8 +257,10 @@ int hk_set_profiling(hk_context* ctx, int count_rays, int time_passes);
 int hk_set_profiling_kernel(hk_context* ctx, int kernel);
 /* Implementation choices that do not change a single output value (both forms are held to the same parity suite).
  * HK_TUNE_POOLED_INDIRECT: 1 = the indirect pass runs as kc_indirect (per-CTA shared-memory ray pool, dynamic fetch, TMA-staged scene
- * records, kernels_pool.cu), 0 = as the per-pixel k_indirect (default: faster on B200 for every benchmark scene). */
-enum { HK_TUNE_POOLED_INDIRECT = 1 };
+ * records, kernels_pool.cu), 0 = as the per-pixel k_indirect (default: faster on B200 for every benchmark scene).
+ * HK_TUNE_TILED_SPATIAL: 1 (default) = spatial_reuse runs as kc_spatial (neighbourhood depth + reservoir-quarter tiles staged in shared
+ * memory by TMA, kernels_spatial.cu) whenever the upscale ratio is 1, 0 = as k_spatial (gathers from global memory). */
+enum { HK_TUNE_POOLED_INDIRECT = 1, HK_TUNE_TILED_SPATIAL = 2 };
 int hk_set_tuning(hk_context* ctx, int key, int value);
 int hk_set_keep_intermediates(hk_context* ctx, int keep);   /* 1: hk_render_frame also writes HK_OUT_DENOISED_* */
 int hk_get_stats(hk_context* ctx, hk_frame_stats* out);
