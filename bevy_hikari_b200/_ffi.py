@@ -41,6 +41,7 @@ SYMBOLS = {
     "hk_scene_upload": (_I, [_P, C.POINTER(L.SceneDesc)]),
     "hk_scene_update_instances": (_I, [_P, C.POINTER(L.SceneDesc)]),
     "hk_set_noise": (_I, [_P, _P]),
+    "hk_import_gbuffer": (_I, [_P, _P]),
     "hk_prepass_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
     "hk_light_run": (_I, [_P, C.POINTER(L.FrameInputs)]),
     "hk_post_process_run": (_I, [_P, C.POINTER(L.FrameInputs)]),

@@ -63,6 +63,7 @@ struct hk_context {
     // TMA descriptors of kc_spatial's tiles (hk_tile.cuh): [0] indirect (radius 20, box 56), [1] emissive (radius 10, box 36);
     // q3 maps per buffer parity: the temporal reservoir the spatial pass reuses is reservoir[base + 1 - (frame.number & 1)]
     TileMap tm_depth[2], tm_q3[2][2];
+    TileMap tm_denoise[4][5];          // kc_denoise, per level: tap geometry, instance, the level's three signal planes (box = 16 + 2 x apron)
     bool tile_maps_ready = false;
     bool full_frame = true;            // the context owns the whole frame (no tile): upscale_ratio > 1 and the upscalers need it
     int last_render_w = 0, last_render_h = 0; bool last_smaa = false, last_upscalers = false, last_fsr = false; uint32_t last_number = 0;   // of the last frame, for read-back sizes
@@ -72,6 +73,7 @@ struct hk_context {
     SpatialTable* spatial_tables = nullptr;
     bool count_rays = false, time_passes = false, keep_intermediates = false;
     bool pooled_indirect = HK_POOLED_INDIRECT != 0;   // hk_set_tuning(HK_TUNE_POOLED_INDIRECT)
+    bool tiled_denoise = true;                        // hk_set_tuning(HK_TUNE_TILED_DENOISE): kc_denoise (TMA tiles) vs k_denoise (gathers)
     bool tiled_spatial = true;                        // hk_set_tuning(HK_TUNE_TILED_SPATIAL): kc_spatial (TMA tiles) vs k_spatial (gathers)
     // pipelined read-back (hk_readback_async): copy stream + "frame submitted" / "copy landed" events
     cudaStream_t copy_stream = nullptr;
@@ -172,6 +174,13 @@ static bool make_spatial_tile_maps(hk_context* ctx) {
         ok = make_tile_map(&ctx->tm_depth[v], ctx->planes.depth, 4, pitch, rows, pitch * 4, box, box);
         for (int parity = 0; parity < 2 && ok; ++parity)      // quarter 3 as rows of u32, 4 per pixel
             ok = make_tile_map(&ctx->tm_q3[v][parity], ctx->planes.reservoir[(v ? 2 : 6) + parity].q[3], 4, pitch * 4, rows, pitch * 16, box * 4, box);
+    }
+    for (int level = 0; level < 4 && ok; ++level) {          // kernels_post.cu DenoiseTile<LEVEL>
+        const uint32_t step = 8u >> level, apron = (step + 1u) & ~1u, box = 16u + 2u * apron;
+        ok = make_tile_map(&ctx->tm_denoise[level][0], ctx->planes.dn_geometry, 4, pitch * 4, rows, pitch * 16, box * 4, box) &&
+             make_tile_map(&ctx->tm_denoise[level][1], ctx->planes.dn_instance, 4, pitch, rows, pitch * 4, box, box);
+        for (int sgl = 0; sgl < 3 && ok; ++sgl)
+            ok = make_tile_map(&ctx->tm_denoise[level][2 + sgl], ctx->planes.dn_internal[level][sgl], 4, pitch * 2, rows, pitch * 8, box * 2, box);
     }
     return ok;
 }
@@ -278,6 +287,7 @@ int hk_context_create_tile(hk_context** out, int cuda_device, uint32_t width, ui
     // defaults of hk_set_tuning from the environment (A/B runs of one build: HK_TUNE_POOLED_INDIRECT=1, HK_TUNE_TILED_SPATIAL=0)
     if (const char* e = getenv("HK_TUNE_POOLED_INDIRECT")) c->pooled_indirect = atoi(e) != 0;
     if (const char* e = getenv("HK_TUNE_TILED_SPATIAL")) c->tiled_spatial = atoi(e) != 0;
+    if (const char* e = getenv("HK_TUNE_TILED_DENOISE")) c->tiled_denoise = atoi(e) != 0;
     ctx = c;
     if (cuda_stream) c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     else {
@@ -791,6 +801,7 @@ static void launch_spatial(hk_context* ctx, const KParams& P, bool emissive) {
     const bool tiled = ctx->tile_maps_ready && ctx->tiled_spatial;
     hk_launch_spatial(P, emissive, tiled ? &ctx->tm_depth[v] : nullptr, tiled ? &ctx->tm_q3[v][parity] : nullptr, ctx->stream);
 }
+static const TileMap* denoise_maps(hk_context* ctx, int level) { return (ctx->tile_maps_ready && ctx->tiled_denoise) ? ctx->tm_denoise[level] : nullptr; }
 static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, light.rs:645-699 (albedo is fused in the prepass)
     const hk_frame_uniform& f = P.in.frame;
     const int GHOST_SPATIAL = ::GHOST_SPATIAL + ring_of(P);
@@ -821,12 +832,12 @@ static int run_post(hk_context* ctx, KParams& P, bool fuse) {  // PostProcessNod
     if (P.in.denoise) {
         const int signals = (P.in.frame.indirect_bounces == 0) ? 2 : 3;  // post_process.rs:949-954
         { rows(ctx, P, GHOST_DEMOD); KernelTimer t(ctx, HK_K_DEMODULATION); hk_launch_demodulation(P, signals, ctx->stream); }
-        { rows(ctx, P, GHOST_L0); KernelTimer t(ctx, HK_K_DENOISE_0); hk_launch_denoise_level(P, 0, signals, false, false, ctx->stream); }
-        { rows(ctx, P, GHOST_L1); KernelTimer t(ctx, HK_K_DENOISE_1); hk_launch_denoise_level(P, 1, signals, false, false, ctx->stream); }
-        { rows(ctx, P, GHOST_L2); KernelTimer t(ctx, HK_K_DENOISE_2); hk_launch_denoise_level(P, 2, signals, false, false, ctx->stream); }
+        { rows(ctx, P, GHOST_L0); KernelTimer t(ctx, HK_K_DENOISE_0); hk_launch_denoise_level(P, 0, signals, false, false, denoise_maps(ctx, 0), ctx->stream); }
+        { rows(ctx, P, GHOST_L1); KernelTimer t(ctx, HK_K_DENOISE_1); hk_launch_denoise_level(P, 1, signals, false, false, denoise_maps(ctx, 1), ctx->stream); }
+        { rows(ctx, P, GHOST_L2); KernelTimer t(ctx, HK_K_DENOISE_2); hk_launch_denoise_level(P, 2, signals, false, false, denoise_maps(ctx, 2), ctx->stream); }
         if (fuse) order_behind_copy(ctx);
         { rows(ctx, P, ring); KernelTimer t(ctx, HK_K_DENOISE_3);
-          hk_launch_denoise_level(P, 3, signals, fuse, !fuse || ctx->keep_intermediates, ctx->stream); }
+          hk_launch_denoise_level(P, 3, signals, fuse, !fuse || ctx->keep_intermediates, denoise_maps(ctx, 3), ctx->stream); }
         if (!fuse) { order_behind_copy(ctx); KernelTimer t(ctx, HK_K_TONE_MAPPING); hk_launch_tone_mapping(P, ctx->stream); }
     } else {
         rows(ctx, P, ring);
@@ -865,6 +876,32 @@ int hk_prepass_run(hk_context* ctx, const hk_frame_inputs* in) {
     KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
     ctx->launches = 0;
     return run_prepass(ctx, P);
+}
+// A host that rasterises its own prepass (bevy-hikari's PrepassNode writes five render targets, prepass.rs:285-306, prepass.wgsl:76-99)
+// hands them over as DEVICE pointers: no host copy, no primary rays.  The planes are copied plane by plane, device to device, on the
+// context's stream into the context's own layout (52 B/px: 0.03 ms at 1080p), after the current <-> previous swap PrepassNode::run
+// is preceded by (prepass.rs:427).  hk_light_run + hk_post_process_run then run the path on them.
+int hk_import_gbuffer(hk_context* ctx, const hk_gbuffer_desc* g) {
+    if (!ctx || !g) return HK_ERR_INVALID_ARGUMENT;
+    if (!ctx->planes_ready) return set_error(ctx, HK_ERR_NOT_READY, "per-pixel planes are not allocated (a resize failed)");
+    if (!g->position || !g->normal || !g->depth_gradient || !g->instance_material || !g->velocity_uv)
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "hk_import_gbuffer: all five planes are required");
+    const Band& b = ctx->band;
+    const size_t ow = (size_t)(b.cx1 - b.cx0), oh = (size_t)(b.r1 - b.r0);
+    const size_t pitch[5] = {g->position_pitch_bytes, g->normal_pitch_bytes, g->depth_gradient_pitch_bytes, g->instance_material_pitch_bytes, g->velocity_uv_pitch_bytes};
+    const size_t bpp[5] = {16, 4, 8, 8, 16};
+    for (int i = 0; i < 5; ++i)
+        if (pitch[i] < ow * bpp[i]) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "hk_import_gbuffer: a row pitch is smaller than the owned rectangle's row");
+    HK_CUDA(cudaSetDevice(ctx->device));
+    ctx->gbuffer_current ^= 1;
+    Planes& p = ctx->planes;
+    const size_t first = (size_t)(b.r0 - b.a0) * (size_t)b.AW + (size_t)(b.cx0 - b.ax0);
+    void* dst[5] = {p.pos_depth_db[ctx->gbuffer_current] + first, p.normal + first, p.depth_gradient + first, p.instance_material + first,
+                    p.velocity_uv_db[ctx->gbuffer_current] + first};
+    const void* src[5] = {g->position, g->normal, g->depth_gradient, g->instance_material, g->velocity_uv};
+    for (int i = 0; i < 5; ++i)
+        HK_CUDA(cudaMemcpy2DAsync(dst[i], (size_t)b.AW * bpp[i], src[i], pitch[i], ow * bpp[i], oh, cudaMemcpyDeviceToDevice, ctx->stream));
+    return HK_OK;
 }
 int hk_light_run(hk_context* ctx, const hk_frame_inputs* in) {
     KParams P; int rc = make_params(ctx, in, P); if (rc) return rc;
@@ -906,10 +943,10 @@ int hk_run_pass(hk_context* ctx, const hk_frame_inputs* in, int pass, int arg) {
         case 6: {
             const int ring = ring_of(P), signals = (f.indirect_bounces == 0) ? 2 : 3;
             rows(ctx, P, ::GHOST_DEMOD + ring); hk_launch_demodulation(P, signals, ctx->stream);
-            rows(ctx, P, ::GHOST_L0 + ring); hk_launch_denoise_level(P, 0, signals, false, false, ctx->stream);
-            rows(ctx, P, ::GHOST_L1 + ring); hk_launch_denoise_level(P, 1, signals, false, false, ctx->stream);
-            rows(ctx, P, ::GHOST_L2 + ring); hk_launch_denoise_level(P, 2, signals, false, false, ctx->stream);
-            rows(ctx, P, ring); hk_launch_denoise_level(P, 3, signals, false, true, ctx->stream);
+            rows(ctx, P, ::GHOST_L0 + ring); hk_launch_denoise_level(P, 0, signals, false, false, denoise_maps(ctx, 0), ctx->stream);
+            rows(ctx, P, ::GHOST_L1 + ring); hk_launch_denoise_level(P, 1, signals, false, false, denoise_maps(ctx, 1), ctx->stream);
+            rows(ctx, P, ::GHOST_L2 + ring); hk_launch_denoise_level(P, 2, signals, false, false, denoise_maps(ctx, 2), ctx->stream);
+            rows(ctx, P, ring); hk_launch_denoise_level(P, 3, signals, false, true, denoise_maps(ctx, 3), ctx->stream);
             break;
         }
         case 7: rows(ctx, P, ring_of(P)); order_behind_copy(ctx); hk_launch_tone_mapping(P, ctx->stream); break;
@@ -954,6 +991,7 @@ int hk_set_tuning(hk_context* ctx, int key, int value) {
     switch (key) {
         case HK_TUNE_POOLED_INDIRECT: ctx->pooled_indirect = value != 0; return HK_OK;
         case HK_TUNE_TILED_SPATIAL: ctx->tiled_spatial = value != 0; return HK_OK;
+        case HK_TUNE_TILED_DENOISE: ctx->tiled_denoise = value != 0; return HK_OK;
         default: return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown tuning key");
     }
 }

@@ -16,7 +16,7 @@ void hk_launch_trace_rays(const hkd::DeviceScene& sc, const hk_ray* rays, size_t
 
 // post process: `signals` = 2 or 3 (post_process.rs:949-954)
 void hk_launch_demodulation(const hkd::KParams& P, int signals, cudaStream_t st);
-void hk_launch_denoise_level(const hkd::KParams& P, int level, int signals, bool fuse_tone_mapping, bool keep_denoised, cudaStream_t st);
+void hk_launch_denoise_level(const hkd::KParams& P, int level, int signals, bool fuse_tone_mapping, bool keep_denoised, const hkd::TileMap* maps, cudaStream_t st);
 void hk_launch_tone_mapping(const hkd::KParams& P, cudaStream_t st);
 
 // temporal upscalers (kernels_upscale.cu); full-frame contexts only

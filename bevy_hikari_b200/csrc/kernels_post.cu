@@ -7,7 +7,7 @@
 //     reference's, so results are bit-identical to running the passes one signal at a time;
 //   * level 3 re-modulates with albedo, and (optionally) sums the signals and applies Reinhard tone mapping in the
 //     same thread, so denoise_render[3] never has to be re-read.
-#include "hk_device.cuh"
+#include "hk_tile.cuh"
 #include "hk_kernels.h"
 
 // Measured on B200 (profiles/r2_baseline_variants.txt): unconditional, batched tap loads take the four levels from 0.574 to 0.524 ms.
@@ -286,6 +286,160 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
     }
 }
 
+// ------------------------------------------------------------------------------- denoise level, TMA-staged taps
+// kc_denoise: the same level for upscale ratio 1.  A CTA of 16 x 16 pixels stages its tile grown by the level's tap distance with
+// five TMA tile loads — tap geometry (16 B/px), instance (4 B/px) and the three signals (8 B/px each) — and every one of the 9 x 5
+// tap fetches of a pixel is a shared-memory read: (16 + 2 * STEP)^2 x 44 B = 44 KB at STEP 8, 14 KB at STEP 1, instead of
+// 45 scattered requests per pixel to L1 / L2.  Arithmetic and tap order are k_denoise's.
+template <int LEVEL> struct DenoiseTile {
+    static constexpr int STEP = 8 >> LEVEL;
+    static constexpr int APRON = (STEP + 1) & ~1;             // even, so that a row of the 4-byte plane is a multiple of 16 bytes
+    static constexpr int B = POOL_TILE_W + 2 * APRON;          // 32, 24, 20, 20
+    // sizes rounded up so that every TMA destination starts on a 128-byte boundary
+    static constexpr size_t GEO = ((size_t)B * B * 16 + 127) & ~(size_t)127, INST = ((size_t)B * B * 4 + 127) & ~(size_t)127, SIG = ((size_t)B * B * 8 + 127) & ~(size_t)127;
+    static constexpr size_t SMEM_BYTES = GEO + INST + 3 * SIG + 16;
+};
+struct DenoiseMaps { TileMap geometry, instance, signal[3]; };
+
+template <int LEVEL, bool FUSE_TONE_MAPPING>
+__global__ void __launch_bounds__(POOL_THREADS, 4) kc_denoise(const __grid_constant__ KParams P, const __grid_constant__ DenoiseMaps M, int signals, int keep_denoised) {
+    using DT = DenoiseTile<LEVEL>;
+    constexpr int STEP = DT::STEP, A = DT::APRON, B = DT::B;
+    HK_DYNAMIC_SMEM(smem);
+    float4* s_geo = reinterpret_cast<float4*>(smem);
+    float* s_inst = reinterpret_cast<float*>(smem + DT::GEO);
+    uint2* s_sig[3] = {reinterpret_cast<uint2*>(smem + DT::GEO + DT::INST), reinterpret_cast<uint2*>(smem + DT::GEO + DT::INST + DT::SIG),
+                       reinterpret_cast<uint2*>(smem + DT::GEO + DT::INST + 2 * DT::SIG)};
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + DT::GEO + DT::INST + 3 * DT::SIG);
+    const int tx0 = P.col_lo + (int)blockIdx.x * POOL_TILE_W - A, ty0 = P.row_lo + (int)blockIdx.y * POOL_TILE_H - A;
+    if (threadIdx.x == 0) {
+        mbar_init(s_bar, 1u);
+        mbar_expect_tx(s_bar, (uint32_t)((size_t)B * B * (20 + 8 * (size_t)signals)));      // what the copies deliver
+        const int px = tx0 - P.band.ax0, py = ty0 - P.band.a0;
+        tile_load_2d(s_geo, &M.geometry, 4 * px, py, s_bar);
+        tile_load_2d(s_inst, &M.instance, px, py, s_bar);
+        for (int sgl = 0; sgl < signals; ++sgl) tile_load_2d(s_sig[sgl], &M.signal[sgl], 2 * px, py, s_bar);
+        mbar_complete_emulated(s_bar);
+    }
+    __syncthreads();
+    int x, y;
+    pool_pixel(x, y, P);
+    const bool in_launch = tile_active(P, x, y);
+    const size_t idx = in_launch ? render_index(P.band, x, y) : 0;
+    // what does not come from the tiles first: the copies run meanwhile
+    float2 dg = make_float2(0.0f, 0.0f);
+    float dn_var[3] = {0.0f, 0.0f, 0.0f};
+    uint2 albedo_bits = make_uint2(0u, 0u);
+    if (in_launch) {
+        dg = __ldg(&P.planes.depth_gradient[idx]);
+#pragma unroll
+        for (int sgl = 0; sgl < 3; ++sgl) if (sgl < signals) dn_var[sgl] = __ldg(&P.planes.dn_variance[sgl][idx]);
+        if (LEVEL == 3) albedo_bits = __ldg(&P.planes.albedo[idx]);
+    }
+    mbar_wait(s_bar, 0u);
+    if (!in_launch) return;
+    const int cx = x - tx0, cy = y - ty0;                   // this pixel's cell of the tiles
+    const float4 geometry = s_geo[cy * B + cx];
+    const float depth = geometry.w;
+    vec4 result[3];
+    result[0] = result[1] = result[2] = v4(0.0f);
+    if (!(depth < F32_EPSILON)) {
+        const vec2 depth_gradient = v2(dg.x, dg.y);
+        const vec3 normal = f4xyz(geometry);
+        const float instance = s_inst[cy * B + cx];
+        SignalAcc acc[3];
+#pragma unroll
+        for (int sgl = 0; sgl < 3; ++sgl) {
+            if (sgl >= signals) continue;
+            SignalAcc& a = acc[sgl];
+            a.lum_denominator = 4.0f * pow025(dn_var[sgl]) + 0.001f;
+            const uint2 cb = s_sig[sgl][cy * B + cx];
+            uvec2 cq; cq.x = cb.x; cq.y = cb.y;
+            a.irradiance = xyz(unpack_rgba16f(cq));
+            a.sum_irradiance = a.irradiance * kernel_at(P, 1, 1);
+            a.sum_w = kernel_at(P, 1, 1);
+            if (bad3(a.irradiance)) { a.irradiance = v3(0.0f); a.sum_irradiance = v3(0.0f); a.sum_w = 0.0f; }
+            a.lum = luminance(a.irradiance);
+            a.ff_moment_1 = 0.0f; a.ff_moment_2 = 0.0f; a.ff_count = 0.0f;
+        }
+        const int OX[8] = {-1, 0, 1, -1, 1, -1, 0, 1};          // tap order of denoise.wgsl:252-268
+        const int OY[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int ox = OX[t], oy = OY[t];
+            const int sx = x + ox * STEP, sy = y + oy * STEP;
+            const bool valid = !(sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH);
+            const int cell = (cy + oy * STEP) * B + (cx + ox * STEP);       // always inside the tile; content is zero outside the plane
+            const float4 sample_geometry = s_geo[cell];
+            const float sample_instance = s_inst[cell];
+            const vec3 sample_normal = f4xyz(sample_geometry);
+            const float sample_depth = sample_geometry.w;
+            const float w_normal = pow16(fmax_(0.0f, dot(normal, sample_normal)));
+            const float w_depth = exp_((-fabsf(depth - sample_depth)) / (fabsf(dot(depth_gradient, v2((float)ox, (float)oy))) + 0.01f));
+            const float w_instance = fmax_(0.0f, 1.0f - fabsf(instance - sample_instance));
+            const float w_geometry = w_normal * w_depth * w_instance;
+            const float k = kernel_at(P, oy + 1, ox + 1);
+#pragma unroll
+            for (int sgl = 0; sgl < 3; ++sgl) {
+                if (sgl >= signals) continue;
+                SignalAcc& a = acc[sgl];
+                const uint2 bits = s_sig[sgl][cell];
+                uvec2 qb; qb.x = bits.x; qb.y = bits.y;
+                vec3 irr = xyz(unpack_rgba16f(qb));
+                float sample_luminance = luminance(irr);
+                float w_luminance = exp_((-fabsf(a.lum - sample_luminance)) / a.lum_denominator);
+                float w = clampf(w_geometry * w_luminance, 0.0f, 1.0f) * k;
+                if (valid && !bad3(irr)) {
+                    a.sum_irradiance = a.sum_irradiance + irr * w;
+                    a.sum_w += w;
+                    if (sgl != 0) {
+                        a.ff_moment_1 += sample_luminance;
+                        a.ff_moment_2 += sample_luminance * sample_luminance;
+                        a.ff_count += 1.0f;
+                    }
+                }
+            }
+        }
+        vec4 albedo = v4(1.0f);
+        if (LEVEL == 3) { uvec2 ab; ab.x = albedo_bits.x; ab.y = albedo_bits.y; albedo = unpack_rgba16f(ab); }
+#pragma unroll
+        for (int sgl = 0; sgl < 3; ++sgl) {
+            if (sgl >= signals) continue;
+            SignalAcc& a = acc[sgl];
+            vec3 irradiance = (a.sum_w < 0.0001f) ? v3(0.0f) : a.sum_irradiance / a.sum_w;
+            if (sgl != 0) {
+                float ff_mean = a.ff_moment_1 / a.ff_count;
+                float ff_var = a.ff_moment_2 / a.ff_count - ff_mean * ff_mean;
+                if (a.lum > ff_mean + 3.0f * sqrtf(ff_var)) irradiance = ff_mean / a.lum * irradiance;
+            }
+            vec4 color = v4(irradiance, 1.0f);
+            if (LEVEL == 3) color = color * albedo;
+            result[sgl] = color;
+        }
+    }
+    if (LEVEL < 3) {
+#pragma unroll
+        for (int sgl = 0; sgl < 3; ++sgl)
+            if (sgl < signals) store16(P.planes.dn_internal[LEVEL + 1][sgl], idx, result[sgl]);
+        return;
+    }
+    vec4 color = v4(0.0f);
+#pragma unroll
+    for (int sgl = 0; sgl < 3; ++sgl) {
+        if (sgl >= signals) continue;
+        uvec2 w = pack_rgba16f(result[sgl]);
+        if (!FUSE_TONE_MAPPING || keep_denoised) P.planes.dn_render[sgl][idx] = make_uint2(w.x, w.y);
+        if (FUSE_TONE_MAPPING) color = color + unpack_rgba16f(w);
+    }
+    if (FUSE_TONE_MAPPING && (P.tile_images || band_owned(P.band, x, y))) {
+        vec3 rgb = reinhard_luminance(vmax(xyz(color), 0.0039f));
+        color = v4(rgb, color.w);
+        if (!(color.w > 0.0f))
+            color = v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]);
+        store_final(P, x, y, color);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- tone mapping
 // tone_mapping.wgsl:21-32 stand-alone (denoise off, or nodes run one by one); inputs per post_process.rs:940-954.
 __global__ void __launch_bounds__(CTA_THREADS) k_tone_mapping(const __grid_constant__ KParams P) {
@@ -346,10 +500,34 @@ void hk_launch_demodulation(const KParams& P, int signals, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_demodulation<<<grid_for(P), CTA_THREADS, 0, st>>>(P, signals);
 }
-void hk_launch_denoise_level(const KParams& P, int level, int signals, bool fuse_tone_mapping, bool keep_denoised, cudaStream_t st) {
+template <int LEVEL, bool FUSE>
+static void launch_denoise_tiled(const KParams& P, const DenoiseMaps& maps, int signals, int keep, cudaStream_t st) {
+    const size_t smem = DenoiseTile<LEVEL>::SMEM_BYTES;
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(kc_denoise<LEVEL, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    const int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
+    const dim3 g((unsigned)((cols + POOL_TILE_W - 1) / POOL_TILE_W), (unsigned)((rows + POOL_TILE_H - 1) / POOL_TILE_H), 1u);
+    kc_denoise<LEVEL, FUSE><<<g, POOL_THREADS, smem, st>>>(P, maps, signals, keep);
+}
+// `maps`: the five TMA descriptors of this level's inputs boxed for its tap distance (context.cu), or nullptr / upscale ratio above 1
+// for the gather-from-global form.  maps[0] geometry, [1] instance, [2..4] the level's three signal planes.
+void hk_launch_denoise_level(const KParams& P, int level, int signals, bool fuse_tone_mapping, bool keep_denoised, const TileMap* maps, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     dim3 g = grid_for(P);
     int keep = keep_denoised ? 1 : 0;
+    if (maps && P.ratio1) {
+        DenoiseMaps m;
+        m.geometry = maps[0]; m.instance = maps[1]; m.signal[0] = maps[2]; m.signal[1] = maps[3]; m.signal[2] = maps[4];
+        switch (level) {
+            case 0: launch_denoise_tiled<0, false>(P, m, signals, keep, st); break;
+            case 1: launch_denoise_tiled<1, false>(P, m, signals, keep, st); break;
+            case 2: launch_denoise_tiled<2, false>(P, m, signals, keep, st); break;
+            default:
+                if (fuse_tone_mapping) launch_denoise_tiled<3, true>(P, m, signals, keep, st);
+                else launch_denoise_tiled<3, false>(P, m, signals, keep, st);
+        }
+        return;
+    }
     switch (level) {
         case 0: k_denoise<0, false><<<g, CTA_THREADS, 0, st>>>(P, signals, keep); break;
         case 1: k_denoise<1, false><<<g, CTA_THREADS, 0, st>>>(P, signals, keep); break;

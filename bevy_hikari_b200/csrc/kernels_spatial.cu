@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
 template <bool EMISSIVE_LIT> struct SpatialTile {
     static constexpr int R = EMISSIVE_LIT ? 10 : 20;
     static constexpr int B = POOL_TILE_W + 2 * R;
-    static constexpr size_t DEPTH_BYTES = (size_t)B * B * 4, Q3_BYTES = (size_t)B * B * 16;
+    // every TMA destination starts on a 128-byte boundary
+    static constexpr size_t DEPTH_BYTES = ((size_t)B * B * 4 + 127) & ~(size_t)127, Q3_BYTES = ((size_t)B * B * 16 + 127) & ~(size_t)127;
+    static constexpr uint32_t TX_BYTES = (uint32_t)((size_t)B * B * 20);       // what the two copies deliver
     static constexpr size_t SMEM_BYTES = DEPTH_BYTES + Q3_BYTES + 16;       // + the mbarrier
 };
 
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(POOL_THREADS, EMISSIVE_LIT ? HK_SPATIAL_TILED_
     const int tx0 = P.col_lo + (int)blockIdx.x * POOL_TILE_W - R, ty0 = P.row_lo + (int)blockIdx.y * POOL_TILE_H - R;
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1u);
-        mbar_expect_tx(s_bar, (uint32_t)(ST::DEPTH_BYTES + ST::Q3_BYTES));
+        mbar_expect_tx(s_bar, ST::TX_BYTES);
         tile_load_2d(s_depth, &depth_map, tx0 - P.band.ax0, ty0 - P.band.a0, s_bar);
         tile_load_2d(s_q3, &q3_map, 4 * (tx0 - P.band.ax0), ty0 - P.band.a0, s_bar);      // the plane as rows of u32: 4 per pixel
         mbar_complete_emulated(s_bar);

@@ -11,7 +11,7 @@ from . import layout as L
 from ._ffi import Settings, check, host_lib, lib
 
 TAA_JASMINE, TAA_NONE = 0, 1
-TUNE_POOLED_INDIRECT, TUNE_TILED_SPATIAL = 1, 2
+TUNE_POOLED_INDIRECT, TUNE_TILED_SPATIAL, TUNE_TILED_DENOISE = 1, 2, 3
 UPSCALE_FSR1, UPSCALE_SMAA_TU4X = 0, 1
 NOISE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "noise_rgba8_64x64x16.bin")
 
@@ -225,6 +225,15 @@ class HikariPlugin:
     def run_frame(self, settings, view, previous_view, lights):
         check(self._lib.hikari_plugin_run_frame(self._p, C.byref(settings), C.byref(view), C.byref(previous_view), C.byref(lights)),
               self.ctx, self._lib)
+
+    def import_gbuffer(self, pointers_and_pitches):
+        """hk_import_gbuffer: five (device pointer, row pitch in bytes) pairs in the order position, normal, depth_gradient,
+        instance_material, velocity_uv"""
+        flat = []
+        for ptr, pitch in pointers_and_pitches:
+            flat += [ptr, pitch]
+        desc = (C.c_size_t * 10)(*flat)
+        check(self._lib.hk_import_gbuffer(self.ctx, desc), self.ctx, self._lib)
 
     # individual nodes / raw C ABI
     def prepass(self, inputs): check(self._lib.hk_prepass_run(self.ctx, C.byref(inputs)), self.ctx, self._lib)

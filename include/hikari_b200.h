@@ -182,6 +182,19 @@ int hk_scene_upload(hk_context* ctx, const hk_scene_desc* scene);
 int hk_scene_update_instances(hk_context* ctx, const hk_scene_desc* scene);
 int hk_set_noise(hk_context* ctx, const uint8_t* rgba8_64x64x16);   /* 16 textures of 64x64 RGBA8, lib.rs:189-219 */
 
+/* The five G-buffer render targets of a host-side raster prepass (src/prepass.rs:285-306; formats src/prepass.rs:43-47), as DEVICE
+ * pointers (e.g. the CUDA mapping of the Vulkan images through external memory) with their row pitches, covering the context's owned
+ * rectangle, row-major.  hk_import_gbuffer replaces hk_prepass_run for such a host: it swaps current <-> previous like the prepass
+ * (prepass.rs:427) and copies the planes device-to-device, stream-ordered; then hk_light_run (which starts with full_screen_albedo,
+ * light.rs:645-653) and hk_post_process_run.  ids are stored as id + 0.5 (prepass.wgsl:97); background texels are all zero. */
+typedef struct hk_gbuffer_desc {
+    const void* position;           size_t position_pitch_bytes;            /* Rgba32Float: world position, w = NDC depth (0 = background) */
+    const void* normal;             size_t normal_pitch_bytes;              /* Rgba8Snorm */
+    const void* depth_gradient;     size_t depth_gradient_pitch_bytes;      /* Rg32Float */
+    const void* instance_material;  size_t instance_material_pitch_bytes;   /* Rg32Float: instance + 0.5, material + 0.5 */
+    const void* velocity_uv;        size_t velocity_uv_pitch_bytes;         /* Rgba32Float: velocity.xy, uv */
+} hk_gbuffer_desc;
+int hk_import_gbuffer(hk_context* ctx, const hk_gbuffer_desc* gbuffer);
 int hk_prepass_run(hk_context* ctx, const hk_frame_inputs* in);
 int hk_light_run(hk_context* ctx, const hk_frame_inputs* in);
 int hk_post_process_run(hk_context* ctx, const hk_frame_inputs* in);
@@ -259,8 +272,10 @@ int hk_set_profiling_kernel(hk_context* ctx, int kernel);
  * HK_TUNE_POOLED_INDIRECT: 1 = the indirect pass runs as kc_indirect (per-CTA shared-memory ray pool, dynamic fetch, TMA-staged scene
  * records, kernels_pool.cu), 0 = as the per-pixel k_indirect (default: faster on B200 for every benchmark scene).
  * HK_TUNE_TILED_SPATIAL: 1 (default) = spatial_reuse runs as kc_spatial (neighbourhood depth + reservoir-quarter tiles staged in shared
- * memory by TMA, kernels_spatial.cu) whenever the upscale ratio is 1, 0 = as k_spatial (gathers from global memory). */
-enum { HK_TUNE_POOLED_INDIRECT = 1, HK_TUNE_TILED_SPATIAL = 2 };
+ * memory by TMA, kernels_spatial.cu) whenever the upscale ratio is 1, 0 = as k_spatial (gathers from global memory).
+ * HK_TUNE_TILED_DENOISE: 1 (default) = the a-trous levels run as kc_denoise (the nine taps' planes staged by TMA, kernels_post.cu) at
+ * upscale ratio 1, 0 = as k_denoise. */
+enum { HK_TUNE_POOLED_INDIRECT = 1, HK_TUNE_TILED_SPATIAL = 2, HK_TUNE_TILED_DENOISE = 3 };
 int hk_set_tuning(hk_context* ctx, int key, int value);
 int hk_set_keep_intermediates(hk_context* ctx, int keep);   /* 1: hk_render_frame also writes HK_OUT_DENOISED_* */
 int hk_get_stats(hk_context* ctx, hk_frame_stats* out);

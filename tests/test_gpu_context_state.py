@@ -113,3 +113,39 @@ def test_malformed_scene_buffers_are_refused():
     upload(emissives=bad_emissive)
     d.upload_scene_desc(plugin.scene_desc_from_buffers(bufs))       # the untouched buffers are fine
     d.render_frame(b.inputs(1))
+
+
+def test_import_gbuffer_from_device_pointers():
+    """A host that rasterises its own prepass hands the five render targets over as device pointers with arbitrary row pitches
+    (hk_import_gbuffer instead of hk_prepass_run): light + post-process on them equal the oracle's on the same G-buffer, frame after frame
+    (the current <-> previous swap of the position / velocity planes included)."""
+    from tests.conftest import EMULATED
+    from tests.test_gpu_parity import ALL_PLANES, compare_all
+    b = Bench("cornell", 72, 48, config="cornell_1080p")
+    dev, orc = b.device(), b.oracle()
+    planes = (L.OUT_GBUFFER_POSITION, L.OUT_GBUFFER_NORMAL, L.OUT_GBUFFER_DEPTH_GRADIENT, L.OUT_GBUFFER_INSTANCE_MATERIAL, L.OUT_GBUFFER_VELOCITY_UV)
+    keep = []
+    for f in range(1, 5):
+        inp = b.moving_inputs(f)
+        orc.prepass(inp)
+        desc = []
+        for k in planes:
+            a = np.ascontiguousarray(orc.readback(k))
+            row = a.reshape(a.shape[0], -1).view(np.uint8)
+            padded = np.zeros((row.shape[0], row.shape[1] + 48), np.uint8)          # a pitch wider than the row, as an imported image has
+            padded[:, :row.shape[1]] = row
+            if EMULATED:
+                keep.append(padded)
+                desc.append((padded.ctypes.data, padded.shape[1]))
+            else:
+                import torch
+                t = torch.from_numpy(padded).cuda()
+                keep.append(t)
+                desc.append((t.data_ptr(), padded.shape[1]))
+        if not EMULATED:
+            import torch
+            torch.cuda.synchronize()
+        dev.import_gbuffer(desc)
+        dev.light(inp); dev.post_process(inp)
+        orc.light(inp); orc.post_process(inp)
+        compare_all(dev, orc, ALL_PLANES, f)
