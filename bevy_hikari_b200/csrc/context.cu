@@ -170,17 +170,17 @@ static bool make_spatial_tile_maps(hk_context* ctx) {
     const uint64_t rows = (uint64_t)(b.a1 - b.a0), pitch = (uint64_t)b.AW;
     bool ok = true;
     for (int v = 0; v < 2 && ok; ++v) {
-        const uint32_t box = 16u + 2u * (v ? 10u : 20u);
-        ok = make_tile_map(&ctx->tm_depth[v], ctx->planes.depth, 4, pitch, rows, pitch * 4, box, box);
+        const uint32_t bh = 16u + 2u * (v ? 10u : 20u), bw = (uint32_t)tile_box_width((int)bh);      // kernels_spatial.cu SpatialTile
+        ok = make_tile_map(&ctx->tm_depth[v], ctx->planes.depth, 4, pitch, rows, pitch * 4, bw, bh);
         for (int parity = 0; parity < 2 && ok; ++parity)      // quarter 3 as rows of u32, 4 per pixel
-            ok = make_tile_map(&ctx->tm_q3[v][parity], ctx->planes.reservoir[(v ? 2 : 6) + parity].q[3], 4, pitch * 4, rows, pitch * 16, box * 4, box);
+            ok = make_tile_map(&ctx->tm_q3[v][parity], ctx->planes.reservoir[(v ? 2 : 6) + parity].q[3], 4, pitch * 4, rows, pitch * 16, bw * 4, bh);
     }
     for (int level = 0; level < 4 && ok; ++level) {          // kernels_post.cu DenoiseTile<LEVEL>
-        const uint32_t step = 8u >> level, apron = (step + 1u) & ~1u, box = 16u + 2u * apron;
-        ok = make_tile_map(&ctx->tm_denoise[level][0], ctx->planes.dn_geometry, 4, pitch * 4, rows, pitch * 16, box * 4, box) &&
-             make_tile_map(&ctx->tm_denoise[level][1], ctx->planes.dn_instance, 4, pitch, rows, pitch * 4, box, box);
+        const uint32_t step = 8u >> level, bh = 16u + 2u * step, bw = (uint32_t)tile_box_width((int)bh);
+        ok = make_tile_map(&ctx->tm_denoise[level][0], ctx->planes.dn_geometry, 4, pitch * 4, rows, pitch * 16, bw * 4, bh) &&
+             make_tile_map(&ctx->tm_denoise[level][1], ctx->planes.dn_instance, 4, pitch, rows, pitch * 4, bw, bh);
         for (int sgl = 0; sgl < 3 && ok; ++sgl)
-            ok = make_tile_map(&ctx->tm_denoise[level][2 + sgl], ctx->planes.dn_internal[level][sgl], 4, pitch * 2, rows, pitch * 8, box * 2, box);
+            ok = make_tile_map(&ctx->tm_denoise[level][2 + sgl], ctx->planes.dn_internal[level][sgl], 4, pitch * 2, rows, pitch * 8, bw * 2, bh);
     }
     return ok;
 }

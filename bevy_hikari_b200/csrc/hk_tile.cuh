@@ -3,6 +3,10 @@
 // screen-space depth march) and the a-trous levels.  One thread issues one instruction per plane; the copy engine computes the
 // addresses, zero-fills what lies outside the plane (= what an out-of-bounds textureLoad returns) and signals an mbarrier.
 //
+// The first element of a box must sit on a 16-byte boundary of its plane (measured on B200: a 4-byte plane read at an x that is not a
+// multiple of 4 raises "illegal instruction"), so tiles start at tile_origin_x() — the wanted first column rounded DOWN to a multiple
+// of 4 pixels of the plane — and are TILE_SLACK columns wider than the neighbourhood they must cover.
+//
 // A TileMap is the 128-byte CUtensorMap the driver encodes on the host (context.cu make_tile_map) for one plane and one box size;
 // the kernel-logic emulation (tests/emu) stores a plain description in the same bytes and copies with memcpy.
 #pragma once
@@ -18,6 +22,11 @@ struct alignas(64) TileMap { unsigned char bytes[128]; };
 #else
 #define HK_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #endif
+
+constexpr int TILE_SLACK = 3;
+__host__ __device__ constexpr int tile_box_width(int columns) { return (columns + TILE_SLACK + 3) & ~3; }   // columns needed -> box width
+// plane column (allocation coordinates, may be negative) a tile that must start at or before `wanted` starts at
+__device__ __forceinline__ int tile_origin_x(int wanted) { return (wanted >> 2) << 2; }
 
 struct TileMapEmu {          // what the emulated build keeps in TileMap::bytes
     const unsigned char* base;

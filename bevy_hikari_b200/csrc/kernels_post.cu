@@ -289,14 +289,14 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DENOISE) k_denoise(const 
 // ------------------------------------------------------------------------------- denoise level, TMA-staged taps
 // kc_denoise: the same level for upscale ratio 1.  A CTA of 16 x 16 pixels stages its tile grown by the level's tap distance with
 // five TMA tile loads — tap geometry (16 B/px), instance (4 B/px) and the three signals (8 B/px each) — and every one of the 9 x 5
-// tap fetches of a pixel is a shared-memory read: (16 + 2 * STEP)^2 x 44 B = 44 KB at STEP 8, 14 KB at STEP 1, instead of
+// tap fetches of a pixel is a shared-memory read: 36 x 32 x 44 B = 50 KB at STEP 8, 24 x 18 x 44 B = 19 KB at STEP 1, instead of
 // 45 scattered requests per pixel to L1 / L2.  Arithmetic and tap order are k_denoise's.
 template <int LEVEL> struct DenoiseTile {
     static constexpr int STEP = 8 >> LEVEL;
-    static constexpr int APRON = (STEP + 1) & ~1;             // even, so that a row of the 4-byte plane is a multiple of 16 bytes
-    static constexpr int B = POOL_TILE_W + 2 * APRON;          // 32, 24, 20, 20
+    static constexpr int BH = POOL_TILE_H + 2 * STEP;                    // 32, 24, 20, 18 rows
+    static constexpr int BW = tile_box_width(POOL_TILE_W + 2 * STEP);     // 36, 28, 24, 24 columns (slack for the 16-byte alignment of the box start)
     // sizes rounded up so that every TMA destination starts on a 128-byte boundary
-    static constexpr size_t GEO = ((size_t)B * B * 16 + 127) & ~(size_t)127, INST = ((size_t)B * B * 4 + 127) & ~(size_t)127, SIG = ((size_t)B * B * 8 + 127) & ~(size_t)127;
+    static constexpr size_t GEO = ((size_t)BW * BH * 16 + 127) & ~(size_t)127, INST = ((size_t)BW * BH * 4 + 127) & ~(size_t)127, SIG = ((size_t)BW * BH * 8 + 127) & ~(size_t)127;
     static constexpr size_t SMEM_BYTES = GEO + INST + 3 * SIG + 16;
 };
 struct DenoiseMaps { TileMap geometry, instance, signal[3]; };
@@ -304,18 +304,19 @@ struct DenoiseMaps { TileMap geometry, instance, signal[3]; };
 template <int LEVEL, bool FUSE_TONE_MAPPING>
 __global__ void __launch_bounds__(POOL_THREADS, 4) kc_denoise(const __grid_constant__ KParams P, const __grid_constant__ DenoiseMaps M, int signals, int keep_denoised) {
     using DT = DenoiseTile<LEVEL>;
-    constexpr int STEP = DT::STEP, A = DT::APRON, B = DT::B;
+    constexpr int STEP = DT::STEP, BW = DT::BW, BH = DT::BH;
     HK_DYNAMIC_SMEM(smem);
     float4* s_geo = reinterpret_cast<float4*>(smem);
     float* s_inst = reinterpret_cast<float*>(smem + DT::GEO);
     uint2* s_sig[3] = {reinterpret_cast<uint2*>(smem + DT::GEO + DT::INST), reinterpret_cast<uint2*>(smem + DT::GEO + DT::INST + DT::SIG),
                        reinterpret_cast<uint2*>(smem + DT::GEO + DT::INST + 2 * DT::SIG)};
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + DT::GEO + DT::INST + 3 * DT::SIG);
-    const int tx0 = P.col_lo + (int)blockIdx.x * POOL_TILE_W - A, ty0 = P.row_lo + (int)blockIdx.y * POOL_TILE_H - A;
+    const int px = tile_origin_x(P.col_lo + (int)blockIdx.x * POOL_TILE_W - STEP - P.band.ax0);     // plane column of the tiles' first cell
+    const int tx0 = px + P.band.ax0, ty0 = P.row_lo + (int)blockIdx.y * POOL_TILE_H - STEP;
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1u);
-        mbar_expect_tx(s_bar, (uint32_t)((size_t)B * B * (20 + 8 * (size_t)signals)));      // what the copies deliver
-        const int px = tx0 - P.band.ax0, py = ty0 - P.band.a0;
+        mbar_expect_tx(s_bar, (uint32_t)((size_t)BW * BH * (20 + 8 * (size_t)signals)));      // what the copies deliver
+        const int py = ty0 - P.band.a0;
         tile_load_2d(s_geo, &M.geometry, 4 * px, py, s_bar);
         tile_load_2d(s_inst, &M.instance, px, py, s_bar);
         for (int sgl = 0; sgl < signals; ++sgl) tile_load_2d(s_sig[sgl], &M.signal[sgl], 2 * px, py, s_bar);
@@ -339,21 +340,21 @@ __global__ void __launch_bounds__(POOL_THREADS, 4) kc_denoise(const __grid_const
     mbar_wait(s_bar, 0u);
     if (!in_launch) return;
     const int cx = x - tx0, cy = y - ty0;                   // this pixel's cell of the tiles
-    const float4 geometry = s_geo[cy * B + cx];
+    const float4 geometry = s_geo[cy * BW + cx];
     const float depth = geometry.w;
     vec4 result[3];
     result[0] = result[1] = result[2] = v4(0.0f);
     if (!(depth < F32_EPSILON)) {
         const vec2 depth_gradient = v2(dg.x, dg.y);
         const vec3 normal = f4xyz(geometry);
-        const float instance = s_inst[cy * B + cx];
+        const float instance = s_inst[cy * BW + cx];
         SignalAcc acc[3];
 #pragma unroll
         for (int sgl = 0; sgl < 3; ++sgl) {
             if (sgl >= signals) continue;
             SignalAcc& a = acc[sgl];
             a.lum_denominator = 4.0f * pow025(dn_var[sgl]) + 0.001f;
-            const uint2 cb = s_sig[sgl][cy * B + cx];
+            const uint2 cb = s_sig[sgl][cy * BW + cx];
             uvec2 cq; cq.x = cb.x; cq.y = cb.y;
             a.irradiance = xyz(unpack_rgba16f(cq));
             a.sum_irradiance = a.irradiance * kernel_at(P, 1, 1);
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 4) kc_denoise(const __grid_const
             const int ox = OX[t], oy = OY[t];
             const int sx = x + ox * STEP, sy = y + oy * STEP;
             const bool valid = !(sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH);
-            const int cell = (cy + oy * STEP) * B + (cx + ox * STEP);       // always inside the tile; content is zero outside the plane
+            const int cell = (cy + oy * STEP) * BW + (cx + ox * STEP);       // always inside the tile; content is zero outside the plane
             const float4 sample_geometry = s_geo[cell];
             const float sample_instance = s_inst[cell];
             const vec3 sample_normal = f4xyz(sample_geometry);

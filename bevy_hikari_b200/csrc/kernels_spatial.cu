@@ -186,16 +186,17 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_SPATIAL) k_spatial(const 
 // neighbours can lie in — its own tile grown by the reuse radius (20 px indirect, 10 px emissive):
 //   * the G-buffer depth plane                          (4 B / px):  the neighbour's depth and every tap of the depth march
 //   * quarter 3 of the temporal reservoir being reused (16 B / px):  count + visible normal, i.e. the cheap rejections
-// 56 x 56 x 20 B = 61 KB (indirect) / 36 x 36 x 20 B = 25 KB (emissive) of shared memory.  Per pixel that replaces 16 (8) scattered
+// 60 x 56 x 20 B = 66 KB (indirect) / 40 x 36 x 20 B = 28 KB (emissive) of shared memory.  Per pixel that replaces 16 (8) scattered
 // depth fetches, up to 80 (40) scattered depth-march taps and the 64-byte reservoir fetches of the neighbours that the depth, count
 // and normal tests reject by reads from shared memory; the three remaining quarters of a surviving neighbour are requested together.
 // Arithmetic, test order within a neighbour and merge order are those of k_spatial: same bytes out (exact flavour).
 template <bool EMISSIVE_LIT> struct SpatialTile {
     static constexpr int R = EMISSIVE_LIT ? 10 : 20;
-    static constexpr int B = POOL_TILE_W + 2 * R;
+    static constexpr int BH = POOL_TILE_H + 2 * R;                    // rows of the neighbourhood
+    static constexpr int BW = tile_box_width(POOL_TILE_W + 2 * R);     // columns: + slack for the 16-byte alignment of the box start
     // every TMA destination starts on a 128-byte boundary
-    static constexpr size_t DEPTH_BYTES = ((size_t)B * B * 4 + 127) & ~(size_t)127, Q3_BYTES = ((size_t)B * B * 16 + 127) & ~(size_t)127;
-    static constexpr uint32_t TX_BYTES = (uint32_t)((size_t)B * B * 20);       // what the two copies deliver
+    static constexpr size_t DEPTH_BYTES = ((size_t)BW * BH * 4 + 127) & ~(size_t)127, Q3_BYTES = ((size_t)BW * BH * 16 + 127) & ~(size_t)127;
+    static constexpr uint32_t TX_BYTES = (uint32_t)((size_t)BW * BH * 20);     // what the two copies deliver
     static constexpr size_t SMEM_BYTES = DEPTH_BYTES + Q3_BYTES + 16;       // + the mbarrier
 };
 
@@ -205,18 +206,19 @@ __global__ void __launch_bounds__(POOL_THREADS, EMISSIVE_LIT ? HK_SPATIAL_TILED_
     using ST = SpatialTile<EMISSIVE_LIT>;
     constexpr int SIGNAL = EMISSIVE_LIT ? 1 : 2;
     constexpr uint32_t SPATIAL_REUSE_COUNT = EMISSIVE_LIT ? 8u : 16u;   // light.wgsl:246-252
-    constexpr int R = ST::R, B = ST::B;
+    constexpr int R = ST::R, BW = ST::BW, BH = ST::BH;
     HK_DYNAMIC_SMEM(smem);
     float* s_depth = reinterpret_cast<float*>(smem);
     uint4* s_q3 = reinterpret_cast<uint4*>(smem + ST::DEPTH_BYTES);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + ST::DEPTH_BYTES + ST::Q3_BYTES);
     // tile origin in frame coordinates, and in plane (allocation) coordinates for the copy engine
-    const int tx0 = P.col_lo + (int)blockIdx.x * POOL_TILE_W - R, ty0 = P.row_lo + (int)blockIdx.y * POOL_TILE_H - R;
+    const int px0 = tile_origin_x(P.col_lo + (int)blockIdx.x * POOL_TILE_W - R - P.band.ax0);       // plane column of the tile's first cell
+    const int tx0 = px0 + P.band.ax0, ty0 = P.row_lo + (int)blockIdx.y * POOL_TILE_H - R;
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1u);
         mbar_expect_tx(s_bar, ST::TX_BYTES);
-        tile_load_2d(s_depth, &depth_map, tx0 - P.band.ax0, ty0 - P.band.a0, s_bar);
-        tile_load_2d(s_q3, &q3_map, 4 * (tx0 - P.band.ax0), ty0 - P.band.a0, s_bar);      // the plane as rows of u32: 4 per pixel
+        tile_load_2d(s_depth, &depth_map, px0, ty0 - P.band.a0, s_bar);
+        tile_load_2d(s_q3, &q3_map, 4 * px0, ty0 - P.band.a0, s_bar);      // the plane as rows of u32: 4 per pixel
         mbar_complete_emulated(s_bar);
     }
     __syncthreads();                                    // the barrier is initialised before anybody waits on it
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(POOL_THREADS, EMISSIVE_LIT ? HK_SPATIAL_TILED_
         vec2 offset = rad * v2(cs, sn);
         int sx = f32_to_i32(offset.x + (float)x), sy = f32_to_i32(offset.y + (float)y);
         if (sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH) continue;      // see k_spatial
-        const int tcell = (sy - ty0) * B + (sx - tx0);
+        const int tcell = (sy - ty0) * BW + (sx - tx0);
         const float sample_depth = s_depth[tcell];
         float depth_ratio = depth / sample_depth;
         if (depth_ratio < 0.9f || depth_ratio > 1.1f) continue;
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(POOL_THREADS, EMISSIVE_LIT ? HK_SPATIAL_TILED_
                 // a tap lies between the pixel and its neighbour, hence inside the tile; a float coordinate that rounds one pixel
                 // out of it (never observed) falls back to the plane
                 const int cxl = tx - tx0, cyl = ty - ty0;
-                tap_depth = ((unsigned)cxl < (unsigned)B && (unsigned)cyl < (unsigned)B) ? s_depth[cyl * B + cxl] : P.planes.pos_depth[band_index(P.band, tx, ty)].w;
+                tap_depth = ((unsigned)cxl < (unsigned)BW && (unsigned)cyl < (unsigned)BH) ? s_depth[cyl * BW + cxl] : P.planes.pos_depth[band_index(P.band, tx, ty)].w;
             }
             float ref_depth = mixf(depth, sample_depth, T.tap_ratio[i][j - 1u]);
             if (tap_depth > ref_depth + 0.00001f) { occluded = true; break; }

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 T=r2c5
 echo "== device tests"
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tolerance.py tests/test_gpu_zz_full_resolution.py tests/test_gpu_upscale.py tests/test_gpu_zz_halo.py tests/test_gpu_context_state.py tests/test_gpu_variants.py -m gpu -q -x 2>&1 | tail -5 | tee $O/${T}_pytest.txt
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tolerance.py tests/test_gpu_zz_full_resolution.py tests/test_gpu_upscale.py tests/test_gpu_zz_halo.py tests/test_gpu_context_state.py tests/test_gpu_variants.py -m gpu -q 2>&1 | tail -12 | tee $O/${T}_pytest.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 short() { python - "$1" "$2" <<'PY'
 import json, sys
@@ -31,7 +31,7 @@ for cfg in "cornell_1080p 16 4" "scene_1080p 8 4" "city_4k 6 3"; do
   run tiled "" $1 $2 $3
   HK_TUNE_TILED_SPATIAL=0 run gather_sp "" $1 $2 $3
   HK_TUNE_TILED_DENOISE=0 run gather_dn "" $1 $2 $3
-  for v in sp_ind2 sp_emi4 sp_emi6; do
+  for v in sp_ind2 sp_emi4 sp_emi6 mi6 mi5 md6; do
     [ -f bevy_hikari_b200/variants/$v.so ] && run $v bevy_hikari_b200/variants/$v.so $1 $2 $3
   done
 done
