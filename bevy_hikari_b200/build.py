@@ -110,7 +110,8 @@ def build(force=False, verbose=False, ptxas_info=False, out=None):
             logs = list(ex.map(_run, jobs))
     link = ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xcompiler", "-fPIC", "-L", HERE, "-lhikari_host",
             "-Xlinker", "-rpath,$ORIGIN", "-Xlinker", "-rpath," + HERE]
-    if jobs or not os.path.exists(HOST_LIB):
+    # (variant builds never re-link the host library: several of them run at once and the default build owns it)
+    if (out is None and jobs) or not os.path.exists(HOST_LIB):
         logs.append(_run([CXX, "-shared", "-o", HOST_LIB] + host_objs))
     if jobs or not os.path.exists(lib):
         logs.append(_run([NVCC, "-shared", "-o", lib] + cuda_objs + link))

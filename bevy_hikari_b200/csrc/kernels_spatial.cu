@@ -17,12 +17,14 @@
 #define HK_SPATIAL_FAST_DIV 1
 #endif
 
-// CTAs of 256 threads per SM of the tiled kernel: 61 KB of tiles each for the indirect pipeline (at most 3 fit), 25 KB for the emissive one
+// CTAs of 256 threads per SM of the tiled kernel: 66 KB of tiles each for the indirect pipeline (at most 3 fit), 28 KB for the emissive one.
+// Measured on B200 (profiles/r2_tiled_kernels_ab.txt): 2 CTAs/SM = 126 registers without spills beat 3 CTAs/SM = 80 registers with spills
+// for the indirect pipeline (0.461 vs 0.577 ms on cornell 1080p; the gather form takes 0.516)
 #ifndef HK_SPATIAL_TILED_MINB_INDIRECT
-#define HK_SPATIAL_TILED_MINB_INDIRECT 3
+#define HK_SPATIAL_TILED_MINB_INDIRECT 2
 #endif
 #ifndef HK_SPATIAL_TILED_MINB_EMISSIVE
-#define HK_SPATIAL_TILED_MINB_EMISSIVE 3
+#define HK_SPATIAL_TILED_MINB_EMISSIVE 2
 #endif
 
 namespace hkd {
@@ -276,29 +278,45 @@ __global__ void __launch_bounds__(POOL_THREADS, EMISSIVE_LIT ? HK_SPATIAL_TILED_
     const SpatialTable& T = P.spatial_tables[EMISSIVE_LIT ? 1 : 0];
     const float rotation = sum4(s.random);
     mbar_wait(s_bar, 0u);                               // the tiles have landed
-    for (uint32_t i = 1u; i <= SPATIAL_REUSE_COUNT; i += 1u) {
+    // The neighbours are software-pipelined by one: while neighbour i is unpacked, marched and shaded, the cheap tests of neighbour
+    // i + 1 (shared memory only) have already run and its three remaining quarters are in flight — one exposed L2 latency per pixel
+    // instead of one per surviving neighbour.  Order of the merges, and every value, unchanged.
+    struct Candidate { bool valid; vec2 offset; float sample_depth; uint4 q0, q1, q2, q3; };
+    auto prepare = [&](uint32_t i) -> Candidate {
+        Candidate c;
+        c.valid = false; c.offset = v2(0.0f, 0.0f); c.sample_depth = 0.0f;
+        c.q0 = c.q1 = c.q2 = c.q3 = make_uint4(0u, 0u, 0u, 0u);
+        if (i > SPATIAL_REUSE_COUNT) return c;
         float ang = TAU * fract(T.phase[i] + rotation + P.random_frame);
         const float rad = T.radius[i];
         float sn, cs;
         sincos_(ang, &sn, &cs);
-        vec2 offset = rad * v2(cs, sn);
-        int sx = f32_to_i32(offset.x + (float)x), sy = f32_to_i32(offset.y + (float)y);
-        if (sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH) continue;      // see k_spatial
+        c.offset = rad * v2(cs, sn);
+        int sx = f32_to_i32(c.offset.x + (float)x), sy = f32_to_i32(c.offset.y + (float)y);
+        if (sx < 0 || sy < 0 || sx >= P.band.RW || sy >= P.band.RH) return c;      // see k_spatial
         const int tcell = (sy - ty0) * BW + (sx - tx0);
-        const float sample_depth = s_depth[tcell];
-        float depth_ratio = depth / sample_depth;
-        if (depth_ratio < 0.9f || depth_ratio > 1.1f) continue;
+        c.sample_depth = s_depth[tcell];
+        float depth_ratio = depth / c.sample_depth;
+        if (depth_ratio < 0.9f || depth_ratio > 1.1f) return c;
         // count and visible normal from the staged quarter: the same values unpack_reservoir derives from it below
-        const uint4 n_q3 = s_q3[tcell];
-        {
-            const float n_count = unpack2x16float(n_q3.z).x;
-            const vec3 n_normal = normalize(xyz(unpack4x8snorm(n_q3.x)));
-            if (n_count < F32_EPSILON || dot(s.visible_normal, n_normal) < 0.866f) continue;
-        }
+        c.q3 = s_q3[tcell];
+        const float n_count = unpack2x16float(c.q3.z).x;
+        const vec3 n_normal = normalize(xyz(unpack4x8snorm(c.q3.x)));
+        if (n_count < F32_EPSILON || dot(s.visible_normal, n_normal) < 0.866f) return c;
         const size_t sidx = render_index(P.band, sx, sy);
+        c.q0 = __ldg(&Bf.reservoir.q[0][sidx]); c.q1 = __ldg(&Bf.reservoir.q[1][sidx]); c.q2 = __ldg(&Bf.reservoir.q[2][sidx]);
+        c.valid = true;
+        return c;
+    };
+    Candidate next = prepare(1u);
+    for (uint32_t i = 1u; i <= SPATIAL_REUSE_COUNT; i += 1u) {
+        const Candidate cur = next;
+        next = prepare(i + 1u);
+        if (!cur.valid) continue;
+        const vec2 offset = cur.offset;
+        const float sample_depth = cur.sample_depth;
         PackedQuarters packed;
-        packed.q0 = __ldg(&Bf.reservoir.q[0][sidx]); packed.q1 = __ldg(&Bf.reservoir.q[1][sidx]); packed.q2 = __ldg(&Bf.reservoir.q[2][sidx]);
-        packed.q3 = n_q3;
+        packed.q0 = cur.q0; packed.q1 = cur.q1; packed.q2 = cur.q2; packed.q3 = cur.q3;
         q = unpack_reservoir(packed);
         vec3 sample_direction = normalize(xyz(q.s.sample_position) - xyz(s.visible_position));
         if (dot(sample_direction, s.visible_normal) < 0.0f) continue;
