@@ -68,7 +68,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -110,7 +110,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "window": "warm-up + both timed arms (sampler started before the warm-up; 100 ms period)"}
+                "window": "warm-up + both timed arms (sampler started before the warm-up; 25 ms period)"}
 
 
 GHOST = 36   # rows / columns a tile renders beyond its own rectangle (bevy_hikari_b200/csrc/context.cu GHOST_TEMPORAL)

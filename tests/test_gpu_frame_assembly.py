@@ -67,6 +67,7 @@ def test_peer_gpu_frame_target_same_process():
 
 def _ipc_worker(handle, tile, frames, conn):
     try:
+        _ffi.DEFAULT_FLAVOR = "exact"      # a spawned process does not run conftest.pytest_configure: same flavour as the parent's contexts
         b = Bench("cornell", W, H, config="cornell_1080p")
         dev = b.device(tile[2], tile[3], tile[0], tile[1])
         target = dev.frame_open(handle)

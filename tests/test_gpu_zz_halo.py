@@ -107,6 +107,8 @@ def test_halo_descriptor_path_in_one_process_on_the_emulator():
 def _halo_worker(rect, frames, conn):
     """second process: renders its tile and the unsharded frame, exchanges halos with the parent after every frame"""
     try:
+        from bevy_hikari_b200 import _ffi
+        _ffi.DEFAULT_FLAVOR = "exact"     # a spawned process does not run conftest.pytest_configure: same flavour as the parent's contexts
         b = Bench("cornell", 144, 96, config="cornell_1080p")
         full, tile = b.device(), b.device(rect[2], rect[3], rect[0], rect[1])
         tile.set_motion_margin(12)
