@@ -41,7 +41,7 @@ CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 CU = ["csrc/context.cu", "csrc/kernels_light.cu", "csrc/kernels_pool.cu", "csrc/kernels_spatial.cu", "csrc/kernels_post.cu", "csrc/kernels_upscale.cu"]
 CPP_HOST = ["host/hikari.cpp", "host/hikari_capi.cpp"]                     # -> libhikari_host.so
 CPP_PLUGIN = ["host/hikari_plugin.cpp", "host/hikari_plugin_capi.cpp"]     # -> libhikari_b200.so (they call hk_*)
-HEADERS = ["csrc/hk_device.cuh", "csrc/hk_pool.cuh", "csrc/hk_kernels.h", "host/hikari.hpp", "host/hikari_settings_convert.hpp",
+HEADERS = ["csrc/hk_device.cuh", "csrc/hk_pool.cuh", "csrc/hk_wide.cuh", "csrc/wide_build.h", "csrc/hk_tile.cuh", "csrc/hk_kernels.h", "host/hikari.hpp", "host/hikari_settings_convert.hpp",
            "../include/hk_math.h", "../include/hk_layout.h", "../include/hikari_b200.h", "../include/hikari_host.h"]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",

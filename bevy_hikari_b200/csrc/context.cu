@@ -19,10 +19,16 @@
 
 #include "hikari_b200.h"
 #include "hk_kernels.h"
+#include "wide_build.h"
 
 #ifndef HK_POOLED_INDIRECT
 #define HK_POOLED_INDIRECT 0     // default of hk_set_tuning(HK_TUNE_POOLED_INDIRECT): 0 = per-pixel k_indirect, 1 = kc_indirect (ray pool).
 #endif                            // Same values either way; measured on B200 (profiles/r2_pooled_indirect_ab.txt) the per-pixel form is faster.
+
+#ifndef HK_WIDE_TRAVERSAL_DEFAULT
+#define HK_WIDE_TRAVERSAL_DEFAULT 1   // default of hk_set_tuning(HK_TUNE_WIDE_TRAVERSAL) in the tolerance build (libhikari_b200.so); the exact
+#endif                                // flavour (and the kernel-logic emulation) default to the reference's walk whatever this says
+int hk_tolerance_build();             // kernels_post.cu: 1 when that unit was compiled with the tolerance flags (build.py FAST_FLAGS)
 
 using namespace hkd;
 
@@ -50,7 +56,13 @@ struct hk_context {
     size_t band_pixels = 0, owned_pixels = 0;
     std::vector<void*> allocations;        // per-pixel planes
     std::vector<void*> scene_allocations;  // scene buffers: meshes, BLAS nodes, materials, textures
-    struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[9];   // scene buffers rewritten by hk_scene_update_instances (grow-only)
+    struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[14];  // scene buffers rewritten by hk_scene_update_instances (grow-only)
+    // image-exact traversal mode (hk_wide.cuh): 4-wide trees of the meshes the instances use, rebuilt only when that set changes
+    struct WideMesh { uint32_t base = 0, root = 0xFFFFFFFFu, need = 0; bool ok = false; };
+    std::vector<std::array<uint32_t, 3>> wide_mesh_keys;    // (node_offset, node_count, primitive) in first-use order
+    std::vector<WideMesh> wide_meshes;                      // parallel to wide_mesh_keys
+    uint32_t wide_blas_node_count = 0;
+    uint32_t wide_stack_need = 0;
     bool mesh_boxes_match = false;         // BLAS half of DeviceScene::leaf_boxes_match
     uint32_t scene_material_count = 0, scene_asset_node_count = 0, scene_primitive_count = 0, scene_vertex_count = 0, scene_texture_count = 0;
     std::vector<hk_node> host_asset_nodes;                 // copy of the uploaded BLAS records: index validation of later instance updates
@@ -75,6 +87,7 @@ struct hk_context {
     bool pooled_indirect = HK_POOLED_INDIRECT != 0;   // hk_set_tuning(HK_TUNE_POOLED_INDIRECT)
     bool tiled_denoise = true;                        // hk_set_tuning(HK_TUNE_TILED_DENOISE): kc_denoise (TMA tiles) vs k_denoise (gathers)
     bool tiled_spatial = true;                        // hk_set_tuning(HK_TUNE_TILED_SPATIAL): kc_spatial (TMA tiles) vs k_spatial (gathers)
+    bool wide_traversal = false;                      // hk_set_tuning(HK_TUNE_WIDE_TRAVERSAL): 4-wide ordered walk vs the reference's fixed-order walk
     // pipelined read-back (hk_readback_async): copy stream + "frame submitted" / "copy landed" events
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_submitted = nullptr, ev_copied = nullptr;
@@ -288,6 +301,8 @@ int hk_context_create_tile(hk_context** out, int cuda_device, uint32_t width, ui
     if (const char* e = getenv("HK_TUNE_POOLED_INDIRECT")) c->pooled_indirect = atoi(e) != 0;
     if (const char* e = getenv("HK_TUNE_TILED_SPATIAL")) c->tiled_spatial = atoi(e) != 0;
     if (const char* e = getenv("HK_TUNE_TILED_DENOISE")) c->tiled_denoise = atoi(e) != 0;
+    c->wide_traversal = HK_WIDE_TRAVERSAL_DEFAULT != 0 && hk_tolerance_build() != 0;   // the exact flavour keeps the reference's walk
+    if (const char* e = getenv("HK_TUNE_WIDE_TRAVERSAL")) c->wide_traversal = atoi(e) != 0;
     ctx = c;
     if (cuda_stream) c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     else {
@@ -436,6 +451,72 @@ static cudaError_t upload_into(hk_context* ctx, hk_context::DevBuf& b, const T**
     return e;
 }
 
+// The 4-wide trees of the image-exact traversal mode (hk_wide.cuh / wide_build.h) for the scene in `s`: one tree per distinct mesh
+// (rebuilt only when the set of meshes in use changes), one over the instances (every call), the per-instance entry points and the
+// array-order ranks that settle ties.  d.wide_ready stays 0 — and every launch keeps the reference's walk — when a flat array is not
+// in bvh 0.7.1's layout or the trees could ask for more stack than the walk has.
+static int upload_wide(hk_context* ctx, const hk_scene_desc* s, DeviceScene& d) {
+    d.wide_ready = 0u; d.wide_tlas_root = WIDE_EMPTY;
+    ctx->wide_stack_need = 0;
+    std::vector<std::array<uint32_t, 3>> keys;
+    std::vector<uint32_t> mesh_of(s->instance_count);
+    for (uint32_t i = 0; i < s->instance_count; ++i) {
+        const hk_mesh_index& m = s->instances[i].mesh;
+        const std::array<uint32_t, 3> key = {m.node_offset, m.node_count, m.primitive};
+        size_t k = 0;
+        while (k < keys.size() && keys[k] != key) ++k;      // few distinct meshes (3 in the city, 1 per instance in scene.rs)
+        if (k == keys.size()) keys.push_back(key);
+        mesh_of[i] = (uint32_t)k;
+    }
+    if (keys != ctx->wide_mesh_keys || ctx->ibuf[10].p == nullptr) {
+        std::vector<hk_wide_node> all;
+        std::vector<hk_context::WideMesh> meshes(keys.size());
+        std::vector<uint32_t> prim_rank(ctx->scene_primitive_count, 0u);
+        for (size_t k = 0; k < keys.size(); ++k) {
+            const hk_node* flat = ctx->host_asset_nodes.data() + keys[k][0];
+            uint32_t shapes = 0;
+            for (uint32_t r = 0; r < keys[k][1]; ++r)
+                if (flat[r].entry_index >= 0x80000000u) shapes = std::max(shapes, flat[r].entry_index - 0x80000000u + 1u);
+            hkw::WideTree t = hkw::build_wide(flat, keys[k][1], shapes);
+            meshes[k].ok = t.ok;
+            if (!t.ok) continue;
+            meshes[k].base = (uint32_t)all.size(); meshes[k].root = t.root; meshes[k].need = t.stack_need;
+            all.insert(all.end(), t.nodes.begin(), t.nodes.end());
+            for (uint32_t sh = 0; sh < shapes; ++sh)
+                if (t.rank[sh] != 0xFFFFFFFFu && (uint64_t)keys[k][2] + sh < prim_rank.size()) prim_rank[keys[k][2] + sh] = t.rank[sh];
+        }
+        HK_CUDA(upload_into(ctx, ctx->ibuf[10], &d.wide_blas, all.data(), all.size()));
+        HK_CUDA(upload_into(ctx, ctx->ibuf[13], &d.wide_primitive_rank, prim_rank.data(), prim_rank.size()));
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));      // the staging vectors die at the end of this block
+        ctx->wide_mesh_keys = keys; ctx->wide_meshes = meshes; ctx->wide_blas_node_count = (uint32_t)all.size();
+    } else {
+        d.wide_blas = reinterpret_cast<const hk_wide_node*>(ctx->ibuf[10].p);
+        d.wide_primitive_rank = reinterpret_cast<const uint32_t*>(ctx->ibuf[13].p);
+    }
+    hkw::WideTree tlas = hkw::build_wide(s->instance_nodes, s->instance_node_count, s->instance_count);
+    bool ok = tlas.ok;
+    uint32_t blas_need = 0;
+    std::vector<uint2> entry(s->instance_count);
+    for (uint32_t i = 0; i < s->instance_count; ++i) {
+        const hk_context::WideMesh& m = ctx->wide_meshes[mesh_of[i]];
+        ok = ok && m.ok;
+        entry[i] = make_uint2(m.base, m.root);
+        blas_need = std::max(blas_need, m.need);
+    }
+    if (!tlas.ok) { tlas.nodes.clear(); tlas.rank.assign(s->instance_count, 0u); }
+    HK_CUDA(upload_into(ctx, ctx->ibuf[9], &d.wide_tlas, tlas.nodes.data(), tlas.nodes.size()));
+    HK_CUDA(upload_into(ctx, ctx->ibuf[11], &d.wide_instance, entry.data(), entry.size()));
+    HK_CUDA(upload_into(ctx, ctx->ibuf[12], &d.wide_instance_rank, tlas.rank.data(), tlas.rank.size()));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    // pending TLAS siblings + the BLAS marker + pending BLAS siblings, and the three pushes a node step makes before it pops
+    ctx->wide_stack_need = tlas.stack_need + 1u + blas_need + 3u;
+    if (ok && ctx->wide_stack_need <= (uint32_t)HK_WIDE_STACK) {
+        d.wide_tlas_root = tlas.root;
+        d.wide_ready = 1u;
+    }
+    return HK_OK;
+}
+
 // Validation + upload of the per-frame half of the scene (instances, TLAS, emissives, emissive BVH, alias tables,
 // previous model matrices) into `d`.  Frees the previous copies.
 static int upload_instances(hk_context* ctx, const hk_scene_desc* s, DeviceScene& d) {
@@ -569,7 +650,7 @@ static int upload_instances(hk_context* ctx, const hk_scene_desc* s, DeviceScene
         }
     }
     HK_CUDA(cudaStreamSynchronize(ctx->stream));      // caller's arrays (and `moved`) may be freed after return
-    return HK_OK;
+    return upload_wide(ctx, s, d);
 }
 
 extern "C" {
@@ -613,6 +694,7 @@ int hk_scene_upload(hk_context* ctx, const hk_scene_desc* s) {
     ctx->scene_texture_count = s->texture_count;
     ctx->host_asset_nodes.assign(s->asset_nodes, s->asset_nodes + s->asset_node_count);
     ctx->mesh_range_checked.clear();
+    ctx->wide_mesh_keys.clear(); ctx->wide_meshes.clear();     // new asset nodes: the meshes' 4-wide trees are rebuilt
     ctx->host_primitive_vertex_index.resize(3 * (size_t)s->primitive_count);
     for (uint32_t i = 0; i < s->primitive_count; ++i)
         for (int c = 0; c < 3; ++c) ctx->host_primitive_vertex_index[3 * (size_t)i + c] = s->primitives[i].vertices[c].index;
@@ -791,7 +873,7 @@ static int run_prepass(hk_context* ctx, KParams& P) {
     P.planes.pos_depth = ctx->planes.pos_depth_db[ctx->gbuffer_current];
     P.planes.velocity_uv = ctx->planes.velocity_uv_db[ctx->gbuffer_current];
     rows_deferred(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
-    { KernelTimer t(ctx, HK_K_GBUFFER); hk_launch_gbuffer(P, ctx->count_rays, ctx->stream); }
+    { KernelTimer t(ctx, HK_K_GBUFFER); hk_launch_gbuffer(P, ctx->count_rays, ctx->wide_traversal, ctx->stream); }
     return check_launch(ctx);
 }
 static int ring_of(const KParams& P) { return P.tile_images ? RING_TONE : 0; }   // extra reach of every pass when a tile feeds the upscalers
@@ -807,15 +889,15 @@ static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, li
     const int GHOST_SPATIAL = ::GHOST_SPATIAL + ring_of(P);
     rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     // each temporal pass is followed by the resolve of its scatter writes (all allocated rows can be targets)
-    { KernelTimer t(ctx, HK_K_DIRECT); hk_launch_direct(P, false, ctx->count_rays, ctx->stream);
+    { KernelTimer t(ctx, HK_K_DIRECT); hk_launch_direct(P, false, ctx->count_rays, ctx->wide_traversal, ctx->stream);
       hk_launch_scatter_resolve(P, 0, ctx->stream); ctx->launches += 1; }
-    { KernelTimer t(ctx, HK_K_EMISSIVE); hk_launch_direct(P, true, ctx->count_rays, ctx->stream);
+    { KernelTimer t(ctx, HK_K_EMISSIVE); hk_launch_direct(P, true, ctx->count_rays, ctx->wide_traversal, ctx->stream);
       hk_launch_scatter_resolve(P, 1, ctx->stream); ctx->launches += 1; }
     if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_EMISSIVE_SPATIAL); launch_spatial(ctx, P, true); }
     rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     { KernelTimer t(ctx, HK_K_INDIRECT);
       if (ctx->pooled_indirect) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
-      else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
+      else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->wide_traversal, ctx->stream);
       hk_launch_scatter_resolve(P, 2, ctx->stream); ctx->launches += 1; }
     if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); launch_spatial(ctx, P, false); }
     return check_launch(ctx);
@@ -930,13 +1012,13 @@ int hk_run_pass(hk_context* ctx, const hk_frame_inputs* in, int pass, int arg) {
     const int GS = ::GHOST_SPATIAL + ring_of(P), GT = GHOST_TEMPORAL + ctx->motion_margin;
     switch (pass) {
         case 0: rows_deferred(ctx, P, GT); hk_launch_albedo(P, ctx->stream); break;
-        case 1: rows(ctx, P, GT); hk_launch_direct(P, false, ctx->count_rays, ctx->stream); hk_launch_scatter_resolve(P, 0, ctx->stream); break;
-        case 2: rows(ctx, P, GT); hk_launch_direct(P, true, ctx->count_rays, ctx->stream); hk_launch_scatter_resolve(P, 1, ctx->stream); break;
+        case 1: rows(ctx, P, GT); hk_launch_direct(P, false, ctx->count_rays, ctx->wide_traversal, ctx->stream); hk_launch_scatter_resolve(P, 0, ctx->stream); break;
+        case 2: rows(ctx, P, GT); hk_launch_direct(P, true, ctx->count_rays, ctx->wide_traversal, ctx->stream); hk_launch_scatter_resolve(P, 1, ctx->stream); break;
         case 3: rows(ctx, P, GS); launch_spatial(ctx, P, true); break;
         case 4:
             rows(ctx, P, GT);
             if (ctx->pooled_indirect) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
-            else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
+            else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->wide_traversal, ctx->stream);
             hk_launch_scatter_resolve(P, 2, ctx->stream);
             break;
         case 5: rows(ctx, P, GS); launch_spatial(ctx, P, false); break;
@@ -992,6 +1074,7 @@ int hk_set_tuning(hk_context* ctx, int key, int value) {
         case HK_TUNE_POOLED_INDIRECT: ctx->pooled_indirect = value != 0; return HK_OK;
         case HK_TUNE_TILED_SPATIAL: ctx->tiled_spatial = value != 0; return HK_OK;
         case HK_TUNE_TILED_DENOISE: ctx->tiled_denoise = value != 0; return HK_OK;
+        case HK_TUNE_WIDE_TRAVERSAL: ctx->wide_traversal = value != 0; return HK_OK;
         default: return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown tuning key");
     }
 }
@@ -1037,6 +1120,8 @@ int hk_get_stats(hk_context* ctx, hk_frame_stats* out) {
     }
     out->ms_kernel[HK_K_TRACE_RAYS] = ctx->trace_ms;
     out->kernel_launches = ctx->launches;
+    out->wide_traversal = (ctx->wide_traversal && ctx->scene_ready && ctx->scene.wide_ready) ? 1u : 0u;
+    out->wide_stack_need = ctx->wide_stack_need;
     return HK_OK;
 }
 
@@ -1419,7 +1504,7 @@ int hk_trace_rays(hk_context* ctx, const hk_ray* rays, size_t n, hk_hit* hits) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(hk_ray), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         cudaEventRecord(ctx->ev[0], ctx->stream);
-        hk_launch_trace_rays(ctx->scene, d_rays, n, d_hits, ctx->stream);
+        hk_launch_trace_rays(ctx->scene, d_rays, n, d_hits, ctx->wide_traversal, ctx->stream);
         cudaEventRecord(ctx->ev[1], ctx->stream);
         e = cudaGetLastError();
     }

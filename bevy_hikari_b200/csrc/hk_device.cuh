@@ -67,6 +67,8 @@ struct StagePlan {
     uint32_t prim_f4, prim_count;      // primitives (whole buffer): 3 float4 per triangle
 };
 
+struct hk_wide_node;     // hk_wide.cuh: 4-wide BVH node of the image-exact traversal mode
+
 struct DeviceScene {
     const hk_vertex* vertices;
     const hk_primitive* primitives;
@@ -88,6 +90,14 @@ struct DeviceScene {
     const uint32_t* instance_moved;
     const hk_instance_trav* instance_trav;   // one per instance
     StagePlan stage;
+    // image-exact traversal mode (hk_wide.cuh, built by wide_build.h at upload): 4-wide trees derived from the flat arrays above
+    const hk_wide_node* wide_tlas;           // tree over the instances
+    const hk_wide_node* wide_blas;           // the trees of all meshes, one after the other
+    const uint2* wide_instance;              // per instance: first node of its mesh's tree in wide_blas | root reference
+    const uint32_t* wide_instance_rank;      // per instance: position of its leaf in instance_nodes (array order = the reference's visit order)
+    const uint32_t* wide_primitive_rank;     // per primitive: position of its leaf in its mesh's asset_nodes range
+    uint32_t wide_tlas_root;
+    uint32_t wide_ready;                     // 1 = every tree could be derived and fits the walk's stack
 };
 
 struct ReservoirPlanes {  // one PackedReservoir buffer as 4 planes
@@ -719,8 +729,17 @@ static __device__ HK_INL_RADIANCE vec4 input_radiance(const DeviceScene& sc, con
     return v4(radiance, 1.0f - amb);
 }
 
-// select_light_candidate, light.wgsl:599-708.  COUNT_RAYS adds the stand-alone BLAS ray to *blas_rays.
-template <bool COUNT_RAYS>
+// hk_wide.cuh (defined there; only the WIDE instantiations of the light kernels need the definition)
+#ifndef HK_INL_WIDE
+#define HK_INL_WIDE __forceinline__
+#endif
+template <bool BOTTOM>
+static __device__ HK_INL_WIDE Hit wide_walk(const DeviceScene& sc, const Ray& ray, float max_distance, float early_distance,
+                                            uint32_t exclude_instance, uint32_t instance);
+
+// select_light_candidate, light.wgsl:599-708.  COUNT_RAYS adds the stand-alone BLAS ray to *blas_rays.  WIDE: the BLAS ray towards
+// the light walks the mesh's 4-wide tree (hk_wide.cuh) instead of its flat array.
+template <bool COUNT_RAYS, bool WIDE = false>
 static __device__ HK_INL_SELECT LightCandidate select_light_candidate(const DeviceScene& sc, const ShadeEnv& e, vec4 rnd, vec3 position,
                                                                  vec3 normal, uint32_t instance, HitInfo& info, uint32_t& blas_rays) {
     LightCandidate cand;
@@ -796,7 +815,12 @@ static __device__ HK_INL_SELECT LightCandidate select_light_candidate(const Devi
             if (COUNT_RAYS) blas_rays += 1u;
             Ray r;
             instance_ray(einst, ray, r);
-            found = traverse_bottom(sc, hit, r, mesh.y, mesh.z, mesh.w, 0.0f);
+            if constexpr (WIDE) {
+                hit = wide_walk<true>(sc, r, F32_MAX, 0.0f, DONT_EXCLUDE, cand.emissive_instance);
+                found = hit.primitive_index != U32_MAX;
+            } else {
+                found = traverse_bottom(sc, hit, r, mesh.y, mesh.z, mesh.w, 0.0f);
+            }
         }
         if (found) {
             hit.instance_index = e2.x;
@@ -908,6 +932,12 @@ constexpr int TILE_W = 16, TILE_H = 8, CTA_THREADS = 128;
 #endif
 #ifndef HK_MINB_DIRECT
 #define HK_MINB_DIRECT 8
+#endif
+#ifndef HK_MINB_INDIRECT_WIDE
+#define HK_MINB_INDIRECT_WIDE 6   // the 4-wide walk holds a node's seven 16-byte loads in flight: 80 registers instead of 64
+#endif
+#ifndef HK_MINB_DIRECT_WIDE
+#define HK_MINB_DIRECT_WIDE 6
 #endif
 #ifndef HK_MINB_DENOISE
 #define HK_MINB_DENOISE 8

@@ -3,16 +3,17 @@
 #include "hk_device.cuh"
 #include "hk_tile.cuh"
 
-void hk_launch_gbuffer(const hkd::KParams& P, bool count, cudaStream_t st);
+// `wide`: the image-exact traversal mode (hk_wide.cuh) when the scene's 4-wide trees exist, else the reference's fixed-order walk
+void hk_launch_gbuffer(const hkd::KParams& P, bool count, bool wide, cudaStream_t st);
 void hk_launch_albedo(const hkd::KParams& P, cudaStream_t st);
-void hk_launch_direct(const hkd::KParams& P, bool emissive, bool count, cudaStream_t st);
-void hk_launch_indirect(const hkd::KParams& P, bool multi, bool count, cudaStream_t st);
+void hk_launch_direct(const hkd::KParams& P, bool emissive, bool count, bool wide, cudaStream_t st);
+void hk_launch_indirect(const hkd::KParams& P, bool multi, bool count, bool wide, cudaStream_t st);
 // pooled (cooperative) form of the indirect pass: shared-memory ray pool, dynamic fetch, TMA-staged scene records (kernels_pool.cu)
 void hk_launch_indirect_pool(const hkd::KParams& P, bool multi, bool count, cudaStream_t st);
 void hk_launch_spatial(const hkd::KParams& P, bool emissive, const hkd::TileMap* depth_map, const hkd::TileMap* q3_map, cudaStream_t st);
 void hk_launch_extract_depth(const hkd::KParams& P, cudaStream_t st);   // depth plane <- pos_depth.w over the launch rectangle
 void hk_launch_scatter_resolve(const hkd::KParams& P, int signal, cudaStream_t st);
-void hk_launch_trace_rays(const hkd::DeviceScene& sc, const hk_ray* rays, size_t n, hk_hit* hits, cudaStream_t st);
+void hk_launch_trace_rays(const hkd::DeviceScene& sc, const hk_ray* rays, size_t n, hk_hit* hits, bool wide, cudaStream_t st);
 
 // post process: `signals` = 2 or 3 (post_process.rs:949-954)
 void hk_launch_demodulation(const hkd::KParams& P, int signals, cudaStream_t st);

@@ -38,8 +38,6 @@ struct hk_wide_node {          // 128 bytes, 128-byte aligned
 };
 static_assert(sizeof(hk_wide_node) == 128, "one L2 line per node");
 
-#ifdef __CUDACC__
-
 // Does the new hit (distance equal to the best so far) come before the best hit in the reference's array order?
 __device__ __forceinline__ bool wide_tie_first(const DeviceScene& sc, uint32_t new_instance, uint32_t new_primitive, const Hit& hit) {
     const uint32_t a = __ldg(&sc.wide_instance_rank[new_instance]), b = __ldg(&sc.wide_instance_rank[hit.instance_index]);
@@ -56,8 +54,7 @@ static __device__ HK_INL_WIDE Hit wide_walk(const DeviceScene& sc, const Ray& ra
     Hit hit;
     hit.u = 0.0f; hit.v = 0.0f; hit.distance = max_distance;
     hit.instance_index = U32_MAX; hit.primitive_index = U32_MAX;
-    uint32_t stack_ref[HK_WIDE_STACK];
-    float stack_t[HK_WIDE_STACK];
+    uint2 stack[HK_WIDE_STACK];        // x = reference, y = bits of the entry distance: one 8-byte local store / load per entry
     int sp = 0;
     Ray cur = ray;
     bool in_blas = BOTTOM;
@@ -89,16 +86,16 @@ static __device__ HK_INL_WIDE Hit wide_walk(const DeviceScene& sc, const Ray& ra
             if (t1 < t0) { float t = t0; t0 = t1; t1 = t; uint32_t r = r0; r0 = r1; r1 = r; }
             if (t2 < t0) { float t = t0; t0 = t2; t2 = t; uint32_t r = r0; r0 = r2; r2 = r; }
             if (t3 < t0) { float t = t0; t0 = t3; t3 = t; uint32_t r = r0; r0 = r3; r3 = r; }
-            if (t1 < F32_MAX) { stack_ref[sp] = r1; stack_t[sp] = t1; ++sp; }
-            if (t2 < F32_MAX) { stack_ref[sp] = r2; stack_t[sp] = t2; ++sp; }
-            if (t3 < F32_MAX) { stack_ref[sp] = r3; stack_t[sp] = t3; ++sp; }
+            if (t1 < F32_MAX) { stack[sp] = make_uint2(r1, __float_as_uint(t1)); ++sp; }
+            if (t2 < F32_MAX) { stack[sp] = make_uint2(r2, __float_as_uint(t2)); ++sp; }
+            if (t3 < F32_MAX) { stack[sp] = make_uint2(r3, __float_as_uint(t3)); ++sp; }
             if (t0 < F32_MAX) { ref = r0; continue; }
             // nothing entered: next entry of the stack that is still nearer than the best hit
             ref = WIDE_EMPTY;
             while (sp > 0) {
                 --sp;
-                const uint32_t r = stack_ref[sp];
-                if (r == WIDE_SENTINEL || stack_t[sp] < hit.distance) { ref = r; break; }
+                const uint2 e = stack[sp];
+                if (e.x == WIDE_SENTINEL || __uint_as_float(e.y) < hit.distance) { ref = e.x; break; }
             }
         }
         if (ref == WIDE_EMPTY) break;
@@ -117,7 +114,7 @@ static __device__ HK_INL_WIDE Hit wide_walk(const DeviceScene& sc, const Ray& ra
                 mesh_primitive = __ldg(&inst->mesh.primitive);
                 instance_index = candidate;
                 in_blas = true;
-                stack_ref[sp] = WIDE_SENTINEL; stack_t[sp] = 0.0f; ++sp;
+                stack[sp] = make_uint2(WIDE_SENTINEL, 0u); ++sp;
                 nodes = sc.wide_blas + w.x;
                 ref = w.y;
                 pop = false;
@@ -143,14 +140,12 @@ static __device__ HK_INL_WIDE Hit wide_walk(const DeviceScene& sc, const Ray& ra
             ref = WIDE_EMPTY;
             while (sp > 0) {
                 --sp;
-                const uint32_t r = stack_ref[sp];
-                if (r == WIDE_SENTINEL || stack_t[sp] < hit.distance) { ref = r; break; }
+                const uint2 e = stack[sp];
+                if (e.x == WIDE_SENTINEL || __uint_as_float(e.y) < hit.distance) { ref = e.x; break; }
             }
         }
     }
     return hit;
 }
-
-#endif  // __CUDACC__
 
 }  // namespace hkd

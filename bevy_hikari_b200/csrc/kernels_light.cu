@@ -3,6 +3,7 @@
 // Replaces the compute entry points of src/shaders/light.wgsl dispatched by LightNode::run (src/light.rs:590-702)
 // and the raster prepass (src/shaders/prepass.wgsl, src/prepass.rs:769-851).
 #include "hk_device.cuh"
+#include "hk_wide.cuh"
 #include "hk_kernels.h"
 
 // NO_TEXTURE specialisation (light.rs:141-143: the reference compiles its light shaders with NO_TEXTURE when the scene has no
@@ -32,6 +33,13 @@ __device__ __forceinline__ void flush_counters(const KParams& P, uint32_t primar
         if (tlas) atomicAdd(&P.counters->tlas, (unsigned long long)tlas);
         if (blas) atomicAdd(&P.counters->blas, (unsigned long long)blas);
     }
+}
+
+// traverse_top in the launch's traversal mode: WIDE = the image-exact 4-wide walk (hk_wide.cuh), else the reference's fixed-order walk
+template <bool WIDE>
+__device__ __forceinline__ Hit trace_top(const DeviceScene& sc, const Ray& ray, float max_distance, float early_distance, uint32_t exclude_instance) {
+    if constexpr (WIDE) return wide_walk<false>(sc, ray, max_distance, early_distance, exclude_instance, 0u);
+    else return traverse_top(sc, ray, max_distance, early_distance, exclude_instance);
 }
 
 __device__ __forceinline__ mat4 load_mat4(const float* m) {
@@ -66,7 +74,7 @@ __device__ __forceinline__ DeviceScene scene_variant(const DeviceScene& scene) {
     return sc;
 }
 
-template <bool COUNT, bool TEX = true>
+template <bool COUNT, bool TEX = true, bool WIDE = false>
 __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__ KParams P) {
     int x, y;
     tile_pixel(x, y, P);
@@ -86,7 +94,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__
         }
         Ray ray = primary_ray(P, inv_view_proj, (float)x, (float)y, jitter_ndc);
         n_primary = 1;
-        Hit hit = traverse_top(P.scene, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
+        Hit hit = trace_top<WIDE>(P.scene, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
         if (hit.instance_index == U32_MAX) {
             P.planes.pos_depth[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             P.planes.depth[idx] = 0.0f;
@@ -192,8 +200,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_albedo(const __grid_constant__ 
 // fact the launcher knows): the whole validation block — a second select_light_candidate with its own emissive-BVH walk and BLAS
 // traversal, a second TLAS traversal, the reset logic — is not in the kernel (2 of 3 sun frames, 4 of 5 emissive frames at the
 // default intervals).  The generic instantiation decides the same thing at run time; values are identical.
-template <bool EMISSIVE_LIT, bool COUNT, bool TEX = true, bool NOVAL = false>
-__global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __grid_constant__ KParams P) {
+template <bool EMISSIVE_LIT, bool COUNT, bool TEX = true, bool NOVAL = false, bool WIDE = false>
+__global__ void __launch_bounds__(CTA_THREADS, WIDE ? HK_MINB_DIRECT_WIDE : HK_MINB_DIRECT) k_direct(const __grid_constant__ KParams P) {
     constexpr int SIGNAL = EMISSIVE_LIT ? 1 : 0;
     constexpr bool RENDER_EMISSIVE = !EMISSIVE_LIT;
     int x, y;
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
             const bool validation_frame = NOVAL ? false : (frame.number % validate_interval) == 0u;
 
             if (!validation_frame || r.count < 4.0f) {
-                LightCandidate cand = select_light_candidate<COUNT>(sc, env, s.random, position, normal, select_light_instance, info, n_blas);
+                LightCandidate cand = select_light_candidate<COUNT, WIDE>(sc, env, s.random, position, normal, select_light_instance, info, n_blas);
                 Ray ray;
                 ray.origin = position + normal * RAY_BIAS;
                 ray.direction = cand.direction;
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
                 if (EMISSIVE_LIT) trace_condition = trace_condition && cand.emissive_instance != DONT_SAMPLE_EMISSIVE;
                 if (trace_condition) {
                     if (COUNT) n_tlas += 1u;
-                    Hit hit = traverse_top(sc, ray, cand.max_distance, cand.min_distance, cand.emissive_instance);
+                    Hit hit = trace_top<WIDE>(sc, ray, cand.max_distance, cand.min_distance, cand.emissive_instance);
                     occlude_hit_info(ray, hit, info);
                     s.radiance = EMISSIVE_LIT ? input_radiance(sc, env, ray.direction, info, false, cand.emissive_instance, false)
                                               : input_radiance(sc, env, ray.direction, info, true, DONT_SAMPLE_EMISSIVE, false);
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
             }
 
             if (validation_frame) {
-                LightCandidate cand = select_light_candidate<COUNT>(sc, env, r.s.random, xyz(r.s.visible_position), r.s.visible_normal,
+                LightCandidate cand = select_light_candidate<COUNT, WIDE>(sc, env, r.s.random, xyz(r.s.visible_position), r.s.visible_normal,
                                                                     select_light_instance, info, n_blas);
                 Ray ray;
                 ray.origin = position + normal * RAY_BIAS;
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
                 if (EMISSIVE_LIT) trace_condition = trace_condition && cand.emissive_instance != DONT_SAMPLE_EMISSIVE;
                 if (trace_condition) {
                     if (COUNT) n_tlas += 1u;
-                    Hit hit = traverse_top(sc, ray, cand.max_distance, cand.min_distance, cand.emissive_instance);
+                    Hit hit = trace_top<WIDE>(sc, ray, cand.max_distance, cand.min_distance, cand.emissive_instance);
                     occlude_hit_info(ray, hit, info);
                     validate_radiance = EMISSIVE_LIT ? input_radiance(sc, env, ray.direction, info, false, cand.emissive_instance, false)
                                                      : input_radiance(sc, env, ray.direction, info, true, DONT_SAMPLE_EMISSIVE, false);
@@ -328,8 +336,8 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_DIRECT) k_direct(const __
 // ----------------------------------------------------------------------------- P3: indirect_lit_ambient
 // light.wgsl:1263-1498.  One kernel covers both the single-bounce and the MULTIPLE_BOUNCES variants: the reference's
 // single-bounce body is the loop body for n == 0 without the luminance clamp, so MULTI only switches those two bits.
-template <bool MULTI, bool COUNT, bool TEX = true>
-__global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(const __grid_constant__ KParams P) {
+template <bool MULTI, bool COUNT, bool TEX = true, bool WIDE = false>
+__global__ void __launch_bounds__(CTA_THREADS, WIDE ? HK_MINB_INDIRECT_WIDE : HK_MINB_INDIRECT) k_indirect(const __grid_constant__ KParams P) {
     int x, y;
     tile_pixel(x, y, P);
     const bool active = tile_active(P, x, y);
@@ -376,7 +384,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
                 ray.direction = mul(normal_basis(b_normal), xyz(rand_sample));
                 ray.inv_direction = 1.0f / ray.direction;
                 if (COUNT) n_tlas += 1u;
-                Hit hit = traverse_top(sc, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
+                Hit hit = trace_top<WIDE>(sc, ray, F32_MAX, 0.0f, DONT_EXCLUDE);
                 HitInfo info = hit_info(sc, ray, hit);
                 if (n == 0u) {
                     s.sample_position = info.position;
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
                     vec3 out_radiance = v3(0.0f);
                     Surface surface = retreive_surface(sc, info.material_index, info.uv);
                     surface.roughness = 1.0f;
-                    LightCandidate cand = select_light_candidate<COUNT>(sc, env, b_random, h_position, h_normal, info.instance_index, info, n_blas);
+                    LightCandidate cand = select_light_candidate<COUNT, WIDE>(sc, env, b_random, h_position, h_normal, info.instance_index, info, n_blas);
                     const bool sample_directional = (cand.emissive_instance == DONT_SAMPLE_EMISSIVE);
                     const vec3 bounce_view_direction = normalize(b_position - h_position);
                     if (dot(cand.direction, h_normal) > 0.0f && cand.p > 0.0f) {
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(CTA_THREADS, HK_MINB_INDIRECT) k_indirect(cons
                         ray.direction = cand.direction;
                         ray.inv_direction = 1.0f / ray.direction;
                         if (COUNT) n_tlas += 1u;
-                        hit = traverse_top(sc, ray, cand.max_distance, cand.min_distance, cand.emissive_instance);
+                        hit = trace_top<WIDE>(sc, ray, cand.max_distance, cand.min_distance, cand.emissive_instance);
                         occlude_hit_info(ray, hit, info);
                         vec4 in_radiance = input_radiance(sc, env, ray.direction, info, sample_directional, cand.emissive_instance, false);
                         out_radiance = shading(env, bounce_view_direction, h_normal, ray.direction, surface, in_radiance);
@@ -491,6 +499,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_scatter_resolve(const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------- ray-dump hook
+template <bool WIDE>
 __global__ void k_trace_rays(DeviceScene sc, const hk_ray* rays, size_t n, hk_hit* hits) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -498,7 +507,7 @@ __global__ void k_trace_rays(DeviceScene sc, const hk_ray* rays, size_t n, hk_hi
     r.origin = v3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]);
     r.direction = v3(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]);
     r.inv_direction = 1.0f / r.direction;
-    Hit h = traverse_top(sc, r, rays[i].max_distance, rays[i].early_distance, rays[i].exclude_instance);
+    Hit h = trace_top<WIDE>(sc, r, rays[i].max_distance, rays[i].early_distance, rays[i].exclude_instance);
     hits[i].u = h.u; hits[i].v = h.v; hits[i].distance = h.distance;
     hits[i].instance_index = h.instance_index; hits[i].primitive_index = h.primitive_index;
 }
@@ -514,12 +523,21 @@ static dim3 grid_for(const KParams& P) {
 using namespace hkd;
 
 static inline bool no_texture(const KParams& P) { return HK_NO_TEXTURE_VARIANT && P.scene.texture_count == 0u; }
+// the image-exact traversal mode is a launch-wide choice (hk_set_tuning(HK_TUNE_WIDE_TRAVERSAL)) and needs the derived trees
+static inline bool wide_mode(const KParams& P, bool wide) { return wide && P.scene.wide_ready != 0u; }
 
-void hk_launch_gbuffer(const KParams& P, bool count, cudaStream_t st) {
+void hk_launch_gbuffer(const KParams& P, bool count, bool wide, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
-    if (count) k_gbuffer<true><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
-    else if (no_texture(P)) k_gbuffer<false, false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
-    else k_gbuffer<false><<<grid_for(P), CTA_THREADS, 0, st>>>(P);
+    const dim3 g = grid_for(P);
+    if (wide_mode(P, wide)) {
+        if (count) k_gbuffer<true, true, true><<<g, CTA_THREADS, 0, st>>>(P);
+        else if (no_texture(P)) k_gbuffer<false, false, true><<<g, CTA_THREADS, 0, st>>>(P);
+        else k_gbuffer<false, true, true><<<g, CTA_THREADS, 0, st>>>(P);
+        return;
+    }
+    if (count) k_gbuffer<true><<<g, CTA_THREADS, 0, st>>>(P);
+    else if (no_texture(P)) k_gbuffer<false, false><<<g, CTA_THREADS, 0, st>>>(P);
+    else k_gbuffer<false><<<g, CTA_THREADS, 0, st>>>(P);
 }
 void hk_launch_extract_depth(const KParams& P, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
@@ -529,45 +547,56 @@ void hk_launch_albedo(const KParams& P, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_albedo<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }
-void hk_launch_direct(const KParams& P, bool emissive, bool count, cudaStream_t st) {
-    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+template <bool WIDE>
+static void launch_direct(const KParams& P, bool emissive, bool count, cudaStream_t st) {
     dim3 g = grid_for(P);
     const uint32_t interval = emissive ? P.in.frame.emissive_validate_interval : P.in.frame.direct_validate_interval;
     const bool noval = HK_NOVAL_VARIANT && !count && (P.in.frame.number % interval) != 0u;
     if (noval) {                         // not a validation frame: the lean instantiation
         if (no_texture(P)) {
-            if (emissive) k_direct<true, false, false, true><<<g, CTA_THREADS, 0, st>>>(P);
-            else k_direct<false, false, false, true><<<g, CTA_THREADS, 0, st>>>(P);
+            if (emissive) k_direct<true, false, false, true, WIDE><<<g, CTA_THREADS, 0, st>>>(P);
+            else k_direct<false, false, false, true, WIDE><<<g, CTA_THREADS, 0, st>>>(P);
         } else {
-            if (emissive) k_direct<true, false, true, true><<<g, CTA_THREADS, 0, st>>>(P);
-            else k_direct<false, false, true, true><<<g, CTA_THREADS, 0, st>>>(P);
+            if (emissive) k_direct<true, false, true, true, WIDE><<<g, CTA_THREADS, 0, st>>>(P);
+            else k_direct<false, false, true, true, WIDE><<<g, CTA_THREADS, 0, st>>>(P);
         }
         return;
     }
     if (!count && no_texture(P)) {       // the timed variants of an untextured scene
-        if (emissive) k_direct<true, false, false><<<g, CTA_THREADS, 0, st>>>(P);
-        else k_direct<false, false, false><<<g, CTA_THREADS, 0, st>>>(P);
+        if (emissive) k_direct<true, false, false, false, WIDE><<<g, CTA_THREADS, 0, st>>>(P);
+        else k_direct<false, false, false, false, WIDE><<<g, CTA_THREADS, 0, st>>>(P);
         return;
     }
-    if (emissive) { if (count) k_direct<true, true><<<g, CTA_THREADS, 0, st>>>(P); else k_direct<true, false><<<g, CTA_THREADS, 0, st>>>(P); }
-    else { if (count) k_direct<false, true><<<g, CTA_THREADS, 0, st>>>(P); else k_direct<false, false><<<g, CTA_THREADS, 0, st>>>(P); }
+    if (emissive) { if (count) k_direct<true, true, true, false, WIDE><<<g, CTA_THREADS, 0, st>>>(P); else k_direct<true, false, true, false, WIDE><<<g, CTA_THREADS, 0, st>>>(P); }
+    else { if (count) k_direct<false, true, true, false, WIDE><<<g, CTA_THREADS, 0, st>>>(P); else k_direct<false, false, true, false, WIDE><<<g, CTA_THREADS, 0, st>>>(P); }
 }
-void hk_launch_indirect(const KParams& P, bool multi, bool count, cudaStream_t st) {
+void hk_launch_direct(const KParams& P, bool emissive, bool count, bool wide, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+    if (wide_mode(P, wide)) launch_direct<true>(P, emissive, count, st);
+    else launch_direct<false>(P, emissive, count, st);
+}
+template <bool WIDE>
+static void launch_indirect(const KParams& P, bool multi, bool count, cudaStream_t st) {
     dim3 g = grid_for(P);
     if (!count && no_texture(P)) {
-        if (multi) k_indirect<true, false, false><<<g, CTA_THREADS, 0, st>>>(P);
-        else k_indirect<false, false, false><<<g, CTA_THREADS, 0, st>>>(P);
+        if (multi) k_indirect<true, false, false, WIDE><<<g, CTA_THREADS, 0, st>>>(P);
+        else k_indirect<false, false, false, WIDE><<<g, CTA_THREADS, 0, st>>>(P);
         return;
     }
-    if (multi) { if (count) k_indirect<true, true><<<g, CTA_THREADS, 0, st>>>(P); else k_indirect<true, false><<<g, CTA_THREADS, 0, st>>>(P); }
-    else { if (count) k_indirect<false, true><<<g, CTA_THREADS, 0, st>>>(P); else k_indirect<false, false><<<g, CTA_THREADS, 0, st>>>(P); }
+    if (multi) { if (count) k_indirect<true, true, true, WIDE><<<g, CTA_THREADS, 0, st>>>(P); else k_indirect<true, false, true, WIDE><<<g, CTA_THREADS, 0, st>>>(P); }
+    else { if (count) k_indirect<false, true, true, WIDE><<<g, CTA_THREADS, 0, st>>>(P); else k_indirect<false, false, true, WIDE><<<g, CTA_THREADS, 0, st>>>(P); }
+}
+void hk_launch_indirect(const KParams& P, bool multi, bool count, bool wide, cudaStream_t st) {
+    if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
+    if (wide_mode(P, wide)) launch_indirect<true>(P, multi, count, st);
+    else launch_indirect<false>(P, multi, count, st);
 }
 void hk_launch_scatter_resolve(const KParams& P, int signal, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_scatter_resolve<<<grid_for(P), CTA_THREADS, 0, st>>>(P, signal);
 }
-void hk_launch_trace_rays(const DeviceScene& sc, const hk_ray* rays, size_t n, hk_hit* hits, cudaStream_t st) {
+void hk_launch_trace_rays(const DeviceScene& sc, const hk_ray* rays, size_t n, hk_hit* hits, bool wide, cudaStream_t st) {
     if (n == 0) return;
-    k_trace_rays<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, rays, n, hits);
+    if (wide && sc.wide_ready != 0u) k_trace_rays<true><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, rays, n, hits);
+    else k_trace_rays<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, rays, n, hits);
 }

@@ -559,3 +559,13 @@ void hk_launch_tone_mapping(const KParams& P, cudaStream_t st) {
     if (P.row_hi <= P.row_lo || P.col_hi <= P.col_lo) return;
     k_tone_mapping<<<grid_for(P), CTA_THREADS, 0, st>>>(P);
 }
+
+// which flavour of the library this is (context.cu: default of HK_TUNE_WIDE_TRAVERSAL): this unit is one of the two that the product
+// build compiles with the tolerance flags (build.py FAST_FLAGS, -DHK_FAST_MATH=1)
+int hk_tolerance_build() {
+#ifdef HK_FAST_MATH
+    return 1;
+#else
+    return 0;
+#endif
+}

@@ -94,7 +94,8 @@ class SceneDesc(C.Structure):
 class FrameStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("tlas_rays", C.c_uint64), ("blas_rays", C.c_uint64),
                 ("ms_prepass", C.c_float), ("ms_light", C.c_float), ("ms_post_process", C.c_float), ("ms_total", C.c_float),
-                ("kernel_launches", C.c_uint32), ("timed_frames", C.c_uint32), ("ms_kernel", C.c_float * 16)]
+                ("kernel_launches", C.c_uint32), ("timed_frames", C.c_uint32), ("ms_kernel", C.c_float * 16),
+                ("wide_traversal", C.c_uint32), ("wide_stack_need", C.c_uint32)]
 
 
 KERNEL_NAMES = ["gbuffer", "direct", "emissive", "emissive_spatial", "indirect", "indirect_spatial", "demodulation",

@@ -11,7 +11,7 @@ from . import layout as L
 from ._ffi import Settings, check, host_lib, lib
 
 TAA_JASMINE, TAA_NONE = 0, 1
-TUNE_POOLED_INDIRECT, TUNE_TILED_SPATIAL, TUNE_TILED_DENOISE = 1, 2, 3
+TUNE_POOLED_INDIRECT, TUNE_TILED_SPATIAL, TUNE_TILED_DENOISE, TUNE_WIDE_TRAVERSAL = 1, 2, 3, 4
 UPSCALE_FSR1, UPSCALE_SMAA_TU4X = 0, 1
 NOISE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "noise_rgba8_64x64x16.bin")
 

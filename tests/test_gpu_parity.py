@@ -28,6 +28,24 @@ def mismatch(a, b):
     return int((bits(a) != bits(b)).any(axis=2).sum())
 
 
+def reservoir_mismatch(a, b):
+    """number of PackedReservoir records that differ, under the image-exact traversal mode's contract (include/hikari_b200.h
+    HK_TUNE_WIDE_TRAVERSAL): a record whose sample carries no radiance may differ in sample_position.xyz — the position of whichever
+    occluder the shadow ray met first, which depends on the order of the walk and which no image reads"""
+    diff = (bits(a) != bits(b)).any(axis=2)
+    if not diff.any():
+        return 0
+    dark = ((a["radiance"][..., 0] == 0) & ((a["radiance"][..., 1] & 0xFFFF) == 0) &
+            (b["radiance"][..., 0] == 0) & ((b["radiance"][..., 1] & 0xFFFF) == 0))
+    rest_equal = np.ones(diff.shape, bool)
+    for name in a.dtype.names:
+        if name == "sample_position":
+            rest_equal &= a[name][..., 3] == b[name][..., 3]
+        else:
+            rest_equal &= (a[name] == b[name]).reshape(diff.shape + (-1,)).all(axis=-1)
+    return int((diff & ~(dark & rest_equal)).sum())
+
+
 def compare_all(dev, orc, planes, frame, allow=0):
     bad = {}
     for k in planes:

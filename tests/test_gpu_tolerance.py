@@ -3,7 +3,9 @@ reuse, demodulation, denoise, tone mapping — bevy_hikari_b200/build.py) agains
 
   * integer outputs bit-exact: G-buffer instance / material ids, every plane the tolerance units do not write (G-buffer, albedo,
     sun radiance, the temporal reservoir buffers of all three signals — reservoirs carry visible_instance) — over whole sequences,
-    because the temporal chain never reads what the tolerance units write;
+    because the temporal chain never reads what the tolerance units write.  The product walks the 4-wide trees by default
+    (HK_TUNE_WIDE_TRAVERSAL, csrc/hk_wide.cuh): a reservoir record whose sample carries no radiance may then hold the position of a
+    different occluder (test_gpu_parity.reservoir_mismatch); every other byte is the reference walk's;
   * every pass of a tolerance unit FROM IDENTICAL INPUTS (the oracle's planes uploaded before the pass): Rgba16Float outputs within
     1 f16 ulp, fewer than 1e-4 of the pixels outside that (a discrete decision — reservoir replacement, a rejection threshold — that
     falls the other way under a 1e-7 perturbation), fp32 reservoir fields within 4 ulp on the agreeing pixels;
@@ -15,7 +17,7 @@ import pytest
 
 from bevy_hikari_b200 import layout as L
 from tests.conftest import Bench
-from tests.test_gpu_parity import mismatch
+from tests.test_gpu_parity import mismatch, reservoir_mismatch
 
 pytestmark = pytest.mark.gpu
 
@@ -65,8 +67,10 @@ def test_tolerance_units_per_pass_from_identical_inputs(scene, config, size):
         orc.run_pass(inp, 0); dev.run_pass(inp, 0)
         for p in (1, 2):
             orc.run_pass(inp, p); dev.run_pass(inp, p)
-        for k in EXACT_PLANES[:8] + [L.OUT_RESERVOIR_0 + i for i in (0, 1, 2, 3)]:
+        for k in EXACT_PLANES[:8]:
             assert mismatch(dev.readback(k), orc.readback(k)) == 0, (f, "exact unit", k)
+        for k in [L.OUT_RESERVOIR_0 + i for i in (0, 1, 2, 3)]:
+            assert reservoir_mismatch(dev.readback(k), orc.readback(k)) == 0, (f, "exact unit", k)
         # ---- pass 3: spatial reuse (emissive), from identical inputs
         sync_state(dev, orc)
         orc.run_pass(inp, 3); dev.run_pass(inp, 3)
@@ -75,8 +79,10 @@ def test_tolerance_units_per_pass_from_identical_inputs(scene, config, size):
         assert n <= budget, (f, "emissive spatial", n, m)
         sync_state(dev, orc)
         orc.run_pass(inp, 4); dev.run_pass(inp, 4)
-        for k in (L.OUT_RENDER_INDIRECT, L.OUT_VARIANCE_INDIRECT, L.OUT_RESERVOIR_0 + 6, L.OUT_RESERVOIR_0 + 7):
+        for k in (L.OUT_RENDER_INDIRECT, L.OUT_VARIANCE_INDIRECT):
             assert mismatch(dev.readback(k), orc.readback(k)) == 0, (f, "indirect (exact unit)", k)
+        for k in (L.OUT_RESERVOIR_0 + 6, L.OUT_RESERVOIR_0 + 7):
+            assert reservoir_mismatch(dev.readback(k), orc.readback(k)) == 0, (f, "indirect (exact unit)", k)
         # ---- pass 5: spatial reuse (indirect)
         sync_state(dev, orc)
         orc.run_pass(inp, 5); dev.run_pass(inp, 5)
@@ -114,7 +120,8 @@ def test_ids_and_temporal_chain_stay_bit_exact_over_a_free_running_sequence():
         inp = b.inputs(f) if f < 7 else b.moving_inputs(f)
         dev.render_frame(inp); orc.render_frame(inp)
         for k in EXACT_PLANES:
-            assert mismatch(dev.readback(k), orc.readback(k)) == 0, (f, k)
+            same = reservoir_mismatch if k >= L.OUT_RESERVOIR_0 else mismatch
+            assert same(dev.readback(k), orc.readback(k)) == 0, (f, k)
 
 
 def test_drift_over_64_frames_is_bounded():
