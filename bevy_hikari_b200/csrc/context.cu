@@ -26,7 +26,7 @@
 #endif                            // Same values either way; measured on B200 (profiles/r2_pooled_indirect_ab.txt) the per-pixel form is faster.
 
 #ifndef HK_WIDE_TRAVERSAL_DEFAULT
-#define HK_WIDE_TRAVERSAL_DEFAULT 1   // default of hk_set_tuning(HK_TUNE_WIDE_TRAVERSAL) in the tolerance build (libhikari_b200.so); the exact
+#define HK_WIDE_TRAVERSAL_DEFAULT 1   // default of hk_set_tuning(HK_TUNE_WIDE_TRAVERSAL) in the tolerance build (libhikari_b200.so): 1 = primary rays; the exact
 #endif                                // flavour (and the kernel-logic emulation) default to the reference's walk whatever this says
 int hk_tolerance_build();             // kernels_post.cu: 1 when that unit was compiled with the tolerance flags (build.py FAST_FLAGS)
 
@@ -87,7 +87,9 @@ struct hk_context {
     bool pooled_indirect = HK_POOLED_INDIRECT != 0;   // hk_set_tuning(HK_TUNE_POOLED_INDIRECT)
     bool tiled_denoise = true;                        // hk_set_tuning(HK_TUNE_TILED_DENOISE): kc_denoise (TMA tiles) vs k_denoise (gathers)
     bool tiled_spatial = true;                        // hk_set_tuning(HK_TUNE_TILED_SPATIAL): kc_spatial (TMA tiles) vs k_spatial (gathers)
-    bool wide_traversal = false;                      // hk_set_tuning(HK_TUNE_WIDE_TRAVERSAL): 4-wide ordered walk vs the reference's fixed-order walk
+    int wide_traversal = 0;                           // hk_set_tuning(HK_TUNE_WIDE_TRAVERSAL): 0 = the reference's fixed-order walk, 1 = primary rays
+                                                      // walk the 4-wide trees (scenes deep enough to gain), 3 = every ray does
+    uint32_t wide_tlas_node_count = 0;
     // pipelined read-back (hk_readback_async): copy stream + "frame submitted" / "copy landed" events
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_submitted = nullptr, ev_copied = nullptr;
@@ -301,8 +303,8 @@ int hk_context_create_tile(hk_context** out, int cuda_device, uint32_t width, ui
     if (const char* e = getenv("HK_TUNE_POOLED_INDIRECT")) c->pooled_indirect = atoi(e) != 0;
     if (const char* e = getenv("HK_TUNE_TILED_SPATIAL")) c->tiled_spatial = atoi(e) != 0;
     if (const char* e = getenv("HK_TUNE_TILED_DENOISE")) c->tiled_denoise = atoi(e) != 0;
-    c->wide_traversal = HK_WIDE_TRAVERSAL_DEFAULT != 0 && hk_tolerance_build() != 0;   // the exact flavour keeps the reference's walk
-    if (const char* e = getenv("HK_TUNE_WIDE_TRAVERSAL")) c->wide_traversal = atoi(e) != 0;
+    c->wide_traversal = hk_tolerance_build() != 0 ? HK_WIDE_TRAVERSAL_DEFAULT : 0;      // the exact flavour keeps the reference's walk
+    if (const char* e = getenv("HK_TUNE_WIDE_TRAVERSAL")) c->wide_traversal = atoi(e) & 3;
     ctx = c;
     if (cuda_stream) c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     else {
@@ -504,6 +506,7 @@ static int upload_wide(hk_context* ctx, const hk_scene_desc* s, DeviceScene& d) 
         blas_need = std::max(blas_need, m.need);
     }
     if (!tlas.ok) { tlas.nodes.clear(); tlas.rank.assign(s->instance_count, 0u); }
+    ctx->wide_tlas_node_count = (uint32_t)tlas.nodes.size();
     HK_CUDA(upload_into(ctx, ctx->ibuf[9], &d.wide_tlas, tlas.nodes.data(), tlas.nodes.size()));
     HK_CUDA(upload_into(ctx, ctx->ibuf[11], &d.wide_instance, entry.data(), entry.size()));
     HK_CUDA(upload_into(ctx, ctx->ibuf[12], &d.wide_instance_rank, tlas.rank.data(), tlas.rank.size()));
@@ -845,6 +848,19 @@ static void rows(const hk_context* ctx, KParams& P, int ghost) {   // owned rect
     P.col_lo = b.cx0 - ghost < b.ax0 ? b.ax0 : b.cx0 - ghost;
     P.col_hi = b.cx1 + ghost > b.ax1 ? b.ax1 : b.cx1 + ghost;
 }
+// Which rays walk the 4-wide trees (hk_wide.cuh).  Measured on B200 (profiles/r2_wide_traversal_ab.txt): the ordered walk pays for the
+// coherent closest-hit rays of the prepass (city 4K: 2.34 -> 1.01 ms) and loses on the incoherent rays of the light passes, whose kernels
+// are instruction-fetch bound and grow by the walk's code; a scene as small as cornell gains nothing either way.
+#ifndef HK_WIDE_MIN_NODES
+#define HK_WIDE_MIN_NODES 256
+#endif
+static bool wide_primary(const hk_context* ctx) {
+    if (!ctx->scene_ready || !ctx->scene.wide_ready) return false;
+    if (ctx->wide_traversal == 3) return true;
+    return ctx->wide_traversal == 1 && ctx->wide_blas_node_count + ctx->wide_tlas_node_count >= (uint32_t)HK_WIDE_MIN_NODES;
+}
+static bool wide_light(const hk_context* ctx) { return ctx->scene_ready && ctx->scene.wide_ready && ctx->wide_traversal == 3; }
+
 static int check_launch(hk_context* ctx) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(ctx, HK_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -873,7 +889,7 @@ static int run_prepass(hk_context* ctx, KParams& P) {
     P.planes.pos_depth = ctx->planes.pos_depth_db[ctx->gbuffer_current];
     P.planes.velocity_uv = ctx->planes.velocity_uv_db[ctx->gbuffer_current];
     rows_deferred(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
-    { KernelTimer t(ctx, HK_K_GBUFFER); hk_launch_gbuffer(P, ctx->count_rays, ctx->wide_traversal, ctx->stream); }
+    { KernelTimer t(ctx, HK_K_GBUFFER); hk_launch_gbuffer(P, ctx->count_rays, wide_primary(ctx), ctx->stream); }
     return check_launch(ctx);
 }
 static int ring_of(const KParams& P) { return P.tile_images ? RING_TONE : 0; }   // extra reach of every pass when a tile feeds the upscalers
@@ -889,15 +905,15 @@ static int run_light(hk_context* ctx, KParams& P) {  // LightNode::run order, li
     const int GHOST_SPATIAL = ::GHOST_SPATIAL + ring_of(P);
     rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     // each temporal pass is followed by the resolve of its scatter writes (all allocated rows can be targets)
-    { KernelTimer t(ctx, HK_K_DIRECT); hk_launch_direct(P, false, ctx->count_rays, ctx->wide_traversal, ctx->stream);
+    { KernelTimer t(ctx, HK_K_DIRECT); hk_launch_direct(P, false, ctx->count_rays, wide_light(ctx), ctx->stream);
       hk_launch_scatter_resolve(P, 0, ctx->stream); ctx->launches += 1; }
-    { KernelTimer t(ctx, HK_K_EMISSIVE); hk_launch_direct(P, true, ctx->count_rays, ctx->wide_traversal, ctx->stream);
+    { KernelTimer t(ctx, HK_K_EMISSIVE); hk_launch_direct(P, true, ctx->count_rays, wide_light(ctx), ctx->stream);
       hk_launch_scatter_resolve(P, 1, ctx->stream); ctx->launches += 1; }
     if (f.emissive_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_EMISSIVE_SPATIAL); launch_spatial(ctx, P, true); }
     rows(ctx, P, GHOST_TEMPORAL + ctx->motion_margin);
     { KernelTimer t(ctx, HK_K_INDIRECT);
       if (ctx->pooled_indirect) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
-      else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->wide_traversal, ctx->stream);
+      else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, wide_light(ctx), ctx->stream);
       hk_launch_scatter_resolve(P, 2, ctx->stream); ctx->launches += 1; }
     if (f.indirect_spatial_reuse) { rows(ctx, P, GHOST_SPATIAL); KernelTimer t(ctx, HK_K_INDIRECT_SPATIAL); launch_spatial(ctx, P, false); }
     return check_launch(ctx);
@@ -1012,13 +1028,13 @@ int hk_run_pass(hk_context* ctx, const hk_frame_inputs* in, int pass, int arg) {
     const int GS = ::GHOST_SPATIAL + ring_of(P), GT = GHOST_TEMPORAL + ctx->motion_margin;
     switch (pass) {
         case 0: rows_deferred(ctx, P, GT); hk_launch_albedo(P, ctx->stream); break;
-        case 1: rows(ctx, P, GT); hk_launch_direct(P, false, ctx->count_rays, ctx->wide_traversal, ctx->stream); hk_launch_scatter_resolve(P, 0, ctx->stream); break;
-        case 2: rows(ctx, P, GT); hk_launch_direct(P, true, ctx->count_rays, ctx->wide_traversal, ctx->stream); hk_launch_scatter_resolve(P, 1, ctx->stream); break;
+        case 1: rows(ctx, P, GT); hk_launch_direct(P, false, ctx->count_rays, wide_light(ctx), ctx->stream); hk_launch_scatter_resolve(P, 0, ctx->stream); break;
+        case 2: rows(ctx, P, GT); hk_launch_direct(P, true, ctx->count_rays, wide_light(ctx), ctx->stream); hk_launch_scatter_resolve(P, 1, ctx->stream); break;
         case 3: rows(ctx, P, GS); launch_spatial(ctx, P, true); break;
         case 4:
             rows(ctx, P, GT);
             if (ctx->pooled_indirect) hk_launch_indirect_pool(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->stream);
-            else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, ctx->wide_traversal, ctx->stream);
+            else hk_launch_indirect(P, f.indirect_bounces >= 2, ctx->count_rays, wide_light(ctx), ctx->stream);
             hk_launch_scatter_resolve(P, 2, ctx->stream);
             break;
         case 5: rows(ctx, P, GS); launch_spatial(ctx, P, false); break;
@@ -1074,7 +1090,9 @@ int hk_set_tuning(hk_context* ctx, int key, int value) {
         case HK_TUNE_POOLED_INDIRECT: ctx->pooled_indirect = value != 0; return HK_OK;
         case HK_TUNE_TILED_SPATIAL: ctx->tiled_spatial = value != 0; return HK_OK;
         case HK_TUNE_TILED_DENOISE: ctx->tiled_denoise = value != 0; return HK_OK;
-        case HK_TUNE_WIDE_TRAVERSAL: ctx->wide_traversal = value != 0; return HK_OK;
+        case HK_TUNE_WIDE_TRAVERSAL:
+            if (value < 0 || value > 3 || value == 2) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "HK_TUNE_WIDE_TRAVERSAL takes 0, 1 or 3");
+            ctx->wide_traversal = value; return HK_OK;
         default: return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown tuning key");
     }
 }
@@ -1120,7 +1138,7 @@ int hk_get_stats(hk_context* ctx, hk_frame_stats* out) {
     }
     out->ms_kernel[HK_K_TRACE_RAYS] = ctx->trace_ms;
     out->kernel_launches = ctx->launches;
-    out->wide_traversal = (ctx->wide_traversal && ctx->scene_ready && ctx->scene.wide_ready) ? 1u : 0u;
+    out->wide_traversal = (wide_primary(ctx) ? 1u : 0u) | (wide_light(ctx) ? 2u : 0u);
     out->wide_stack_need = ctx->wide_stack_need;
     return HK_OK;
 }
@@ -1504,7 +1522,7 @@ int hk_trace_rays(hk_context* ctx, const hk_ray* rays, size_t n, hk_hit* hits) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(hk_ray), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         cudaEventRecord(ctx->ev[0], ctx->stream);
-        hk_launch_trace_rays(ctx->scene, d_rays, n, d_hits, ctx->wide_traversal, ctx->stream);
+        hk_launch_trace_rays(ctx->scene, d_rays, n, d_hits, wide_light(ctx), ctx->stream);
         cudaEventRecord(ctx->ev[1], ctx->stream);
         e = cudaGetLastError();
     }

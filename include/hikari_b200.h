@@ -128,7 +128,7 @@ typedef struct hk_frame_stats {
     uint32_t kernel_launches;    /* kernels launched by the last hk_render_frame */
     uint32_t timed_frames;       /* hk_set_profiling_kernel mode: frames averaged into ms_kernel[kernel]; 0 otherwise */
     float ms_kernel[16];         /* per-kernel CUDA-event times of the last hk_render_frame, index = HK_K_*; 0 = not run */
-    uint32_t wide_traversal;     /* 1 = rays walk the scene's 4-wide trees (HK_TUNE_WIDE_TRAVERSAL is on and the trees could be derived) */
+    uint32_t wide_traversal;     /* rays that walk the scene's 4-wide trees (HK_TUNE_WIDE_TRAVERSAL): bit 0 = primary rays, bit 1 = light passes */
     uint32_t wide_stack_need;    /* bound on the stack entries a walk of the uploaded scene's trees can need; 0 = no trees */
 } hk_frame_stats;
 
@@ -278,15 +278,17 @@ int hk_set_profiling_kernel(hk_context* ctx, int kernel);
  * memory by TMA, kernels_spatial.cu) whenever the upscale ratio is 1, 0 = as k_spatial (gathers from global memory).
  * HK_TUNE_TILED_DENOISE: 1 (default) = the a-trous levels run as kc_denoise (the nine taps' planes staged by TMA, kernels_post.cu) at
  * upscale ratio 1, 0 = as k_denoise.
- * HK_TUNE_WIDE_TRAVERSAL: 1 = every ray of the prepass and the light passes walks 4-wide trees derived at hk_scene_upload /
- * hk_scene_update_instances from the uploaded flat BVHs (instance.rs:352-437, mod.rs:185-201) front to back with a short stack
- * (csrc/hk_wide.cuh) instead of the flat arrays in the reference's fixed order (light.wgsl:400-486).  Box and triangle tests, their
- * arithmetic and the tie rule (first in array order among equidistant hits) are the reference's, so G-buffer ids, hit distances and
- * every image are the exact walk's except for rays whose two nearest hits tie within the rounding of a box test; the any-hit
- * OCCLUDER a shadow ray reports (stored with zero-radiance samples, read by no image) depends on the order and differs.  0 = the
- * reference's walk.  Default: 1 in libhikari_b200.so (the tolerance build), 0 in libhikari_b200_exact.so; a scene whose flat arrays
- * are not bvh 0.7.1's flatten_custom layout, or whose trees could overflow the walk's stack, silently keeps the reference's walk
- * (hk_frame_stats.wide_traversal tells). */
+ * HK_TUNE_WIDE_TRAVERSAL: which rays walk 4-wide trees derived at hk_scene_upload / hk_scene_update_instances from the uploaded flat
+ * BVHs (instance.rs:352-437, mod.rs:185-201) front to back with a short stack (csrc/hk_wide.cuh) instead of the flat arrays in the
+ * reference's fixed order (light.wgsl:400-486): 0 = none, 1 = the primary rays of the prepass when the scene's trees have at least 256
+ * nodes (default in libhikari_b200.so, the tolerance build: measured, this is where the ordered walk pays — city 4K prepass 2.34 ->
+ * 1.01 ms — while the incoherent rays of the light passes lose), 3 = every ray of the prepass and the light passes, whatever the
+ * scene's size (A/B runs and the mode's tests).  Box and triangle tests, their arithmetic and the tie rule (first in array order
+ * among equidistant hits) are the reference's, so G-buffer ids, hit distances and every image are the exact walk's except for rays
+ * whose two nearest hits tie within the rounding of a box test; under 3 the any-hit OCCLUDER a shadow ray reports (stored with
+ * zero-radiance samples, read by no image) depends on the order and differs.  Default 0 in libhikari_b200_exact.so.  A scene whose
+ * flat arrays are not bvh 0.7.1's flatten_custom layout, or whose trees could overflow the walk's stack, silently keeps the
+ * reference's walk (hk_frame_stats.wide_traversal: bit 0 = primary rays, bit 1 = light passes). */
 enum { HK_TUNE_POOLED_INDIRECT = 1, HK_TUNE_TILED_SPATIAL = 2, HK_TUNE_TILED_DENOISE = 3, HK_TUNE_WIDE_TRAVERSAL = 4 };
 int hk_set_tuning(hk_context* ctx, int key, int value);
 int hk_set_keep_intermediates(hk_context* ctx, int keep);   /* 1: hk_render_frame also writes HK_OUT_DENOISED_* */

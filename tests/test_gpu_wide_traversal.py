@@ -28,9 +28,9 @@ IMAGES = [L.OUT_RENDER_DIRECT, L.OUT_RENDER_EMISSIVE, L.OUT_RENDER_INDIRECT, L.O
 
 def wide_device(b, **kw):
     dev = b.device(**kw)
-    dev.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 1)
+    dev.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 3)          # every ray, whatever the scene's size
     st = dev.stats()
-    assert st.wide_traversal == 1, f"the scene's 4-wide trees were not derived (stack need {st.wide_stack_need})"
+    assert st.wide_traversal == 3, f"the scene's 4-wide trees were not derived (stack need {st.wide_stack_need})"
     return dev
 
 
@@ -133,11 +133,18 @@ def test_tie_rule_first_in_array_order():
 def test_switch_and_stats():
     b = Bench("cornell", 48, 32, config="cornell_256")
     dev = b.device()
-    dev.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 1)
+    dev.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 3)
     st = dev.stats()
-    assert st.wide_traversal == 1 and 0 < st.wide_stack_need <= 64
+    assert st.wide_traversal == 3 and 0 < st.wide_stack_need <= 64
+    dev.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 1)          # primary rays only, and only for scenes deep enough to gain: cornell is not
+    assert dev.stats().wide_traversal == 0
     dev.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 0)
     assert dev.stats().wide_traversal == 0
+    city = Bench("city", 48, 32, config="city_4k").device()
+    city.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 1)
+    assert city.stats().wide_traversal == 1
+    with pytest.raises(Exception):
+        city.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 2)
 
 
 def test_unparseable_flat_array_keeps_the_reference_walk():
@@ -152,7 +159,7 @@ def test_unparseable_flat_array_keeps_the_reference_walk():
     desc = plugin.scene_desc_from_buffers(bufs)
     dev = plugin.HikariPlugin(48, 32)
     dev.upload_scene_desc(desc)
-    dev.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 1)
+    dev.set_tuning(plugin.TUNE_WIDE_TRAVERSAL, 3)
     assert dev.stats().wide_traversal == 0
     from oracle import oracle
     orc = oracle.Oracle(48, 32, plugin.load_noise())
