@@ -927,11 +927,16 @@ __device__ __forceinline__ void scatter_claim(const KParams& P, size_t target, i
 // 8x4-pixel tiles per warp, 4 warps per CTA (16x8 pixels): ray coherence + whole-sector plane accesses.
 constexpr int TILE_W = 16, TILE_H = 8, CTA_THREADS = 128;
 #ifndef HK_MINB_INDIRECT
-#define HK_MINB_INDIRECT 8   // measured on B200 (tools/tune_launch_bounds.sh): these kernels are latency bound;
-                             // 8 CTAs/SM (<= 64 registers, some spills) beat 3-4 CTAs/SM at 130-160 registers by 20-25 %
+#define HK_MINB_INDIRECT 12  // measured on B200: these kernels are latency / instruction-fetch bound and want warps, not registers.  Round 1
+                             // (tools/tune_launch_bounds.sh): 8 CTAs/SM (64 registers, some spills) beat 3-4 CTAs/SM at 130-160 registers
+                             // by 20-25 %.  Round 2 (profiles/r2_occupancy_sweep.txt): 12 CTAs/SM (40 registers) beat 8 by 2 % (cornell),
+                             // 5 % (scene.rs), 11 % (city); 16 CTAs/SM (32 registers) win another 6 % in the city and lose 4-6 % elsewhere
 #endif
 #ifndef HK_MINB_DIRECT
 #define HK_MINB_DIRECT 8
+#endif
+#ifndef HK_MINB_GBUFFER
+#define HK_MINB_GBUFFER 8    // 64 registers: 2-3 % faster than uncapped (66-78 registers) on every scene (profiles/r2_occupancy_sweep.txt)
 #endif
 #ifndef HK_MINB_INDIRECT_WIDE
 #define HK_MINB_INDIRECT_WIDE 6   // the 4-wide walk holds a node's seven 16-byte loads in flight: 80 registers instead of 64

@@ -75,7 +75,7 @@ __device__ __forceinline__ DeviceScene scene_variant(const DeviceScene& scene) {
 }
 
 template <bool COUNT, bool TEX = true, bool WIDE = false>
-__global__ void __launch_bounds__(CTA_THREADS) k_gbuffer(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, HK_MINB_GBUFFER) k_gbuffer(const __grid_constant__ KParams P) {
     int x, y;
     tile_pixel(x, y, P);
     const bool active = tile_active(P, x, y);
