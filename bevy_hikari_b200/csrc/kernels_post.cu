@@ -504,8 +504,10 @@ void hk_launch_demodulation(const KParams& P, int signals, cudaStream_t st) {
 template <int LEVEL, bool FUSE>
 static void launch_denoise_tiled(const KParams& P, const DenoiseMaps& maps, int signals, int keep, cudaStream_t st) {
     const size_t smem = DenoiseTile<LEVEL>::SMEM_BYTES;
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(kc_denoise<LEVEL, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    static bool configured[64] = {};     // per instantiation AND per device: the attribute belongs to the function on one device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) { cudaFuncSetAttribute(kc_denoise<LEVEL, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured[dev & 63] = true; }
     const int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
     const dim3 g((unsigned)((cols + POOL_TILE_W - 1) / POOL_TILE_W), (unsigned)((rows + POOL_TILE_H - 1) / POOL_TILE_H), 1u);
     kc_denoise<LEVEL, FUSE><<<g, POOL_THREADS, smem, st>>>(P, maps, signals, keep);

@@ -387,8 +387,10 @@ static inline bool no_texture(const KParams& P) { return HK_NO_TEXTURE_VARIANT &
 template <bool EMISSIVE_LIT, bool TEX>
 static void launch_tiled(const KParams& P, const TileMap& depth_map, const TileMap& q3_map, cudaStream_t st) {
     const size_t smem = SpatialTile<EMISSIVE_LIT>::SMEM_BYTES;
-    static bool configured = false;      // per instantiation; the attribute is per function and device-wide state of the module
-    if (!configured) { cudaFuncSetAttribute(kc_spatial<EMISSIVE_LIT, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    static bool configured[64] = {};     // per instantiation AND per device: the attribute belongs to the function on one device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) { cudaFuncSetAttribute(kc_spatial<EMISSIVE_LIT, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured[dev & 63] = true; }
     const int rows = P.row_hi - P.row_lo, cols = P.col_hi - P.col_lo;
     const dim3 g((unsigned)((cols + POOL_TILE_W - 1) / POOL_TILE_W), (unsigned)((rows + POOL_TILE_H - 1) / POOL_TILE_H), 1u);
     kc_spatial<EMISSIVE_LIT, TEX><<<g, POOL_THREADS, smem, st>>>(P, depth_map, q3_map);

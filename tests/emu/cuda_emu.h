@@ -76,6 +76,7 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaMalloc(void** p, size_t bytes) { return posix_memalign(p, 256, bytes ? bytes : 256) == 0 ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
