@@ -78,11 +78,34 @@ def lib():
 PASS_ALBEDO, PASS_DIRECT, PASS_EMISSIVE, PASS_EMISSIVE_SPATIAL, PASS_INDIRECT, PASS_INDIRECT_SPATIAL, PASS_DENOISE, PASS_TONE_MAPPING = range(8)
 
 
+def usable_cpus():
+    """Host cores this process may really use: the affinity mask capped by the cgroup CPU quota.  os.cpu_count() reports the whole
+    machine (128 hardware threads on the GPU box against a 16-CPU quota); an OpenMP team of that size under the quota spends its time
+    being throttled at barriers, which made the device suite's checker several times slower than the thing it checks."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path, parse in (("/sys/fs/cgroup/cpu.max", lambda t: None if t.split()[0] == "max" else float(t.split()[0]) / float(t.split()[1])),
+                        ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", None)):
+        try:
+            text = open(path).read()
+            if parse is None:
+                quota = int(text)
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                cap = quota / period if quota > 0 else None
+            else:
+                cap = parse(text)
+            if cap:
+                n = min(n, max(1, int(cap)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 class Oracle:
     def __init__(self, width, height, noise, threads=None):
         self.width, self.height = width, height
         p = _P()
-        threads = threads or os.cpu_count() or 1
+        threads = threads or usable_cpus()
         self.threads = threads
         rc = lib().hko_context_create(C.byref(p), width, height, threads)
         assert rc == 0
