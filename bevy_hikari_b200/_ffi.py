@@ -62,6 +62,9 @@ SYMBOLS = {
     "hk_frame_open": (_I, [_P, _P, C.POINTER(_P)]),
     "hk_frame_read": (_I, [_P, _P, _P, _SZ]),
     "hk_upload_state": (_I, [_P, _I, _P, _SZ]),
+    "hk_scene_update_transforms": (_I, [_P, _P, _P, _P, _U32]),
+    "hk_scene_readback": (_I, [_P, _I, _P, _SZ]),
+    "hk_scene_buffer_bytes": (_I, [_P, _I, C.POINTER(_SZ)]),
     "hk_sync": (_I, [_P]),
     "hk_trace_rays": (_I, [_P, _P, _SZ, _P]),
     "hk_set_profiling": (_I, [_P, _I, _I]),
@@ -95,12 +98,14 @@ SYMBOLS = {
     "hikari_world_previous_transform_system": (None, [_P]),
     "hikari_world_scene_desc": (None, [_P, C.POINTER(L.SceneDesc)]),
     "hikari_world_mesh_error": (_I, [_P, _U32]),
+    "hikari_world_prepare_instance_transforms": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_U32)]),
     "hikari_plugin_create": (_P, []),
     "hikari_plugin_destroy": (None, [_P]),
     "hikari_plugin_build": (_I, [_P, _I, _U32, _U32, _U32, _U32, _P, _P]),
     "hikari_plugin_build_tile": (_I, [_P, _I, _U32, _U32, _U32, _U32, _U32, _U32, _P, _P]),
     "hikari_plugin_upload_scene": (_I, [_P, _P]),
     "hikari_plugin_update_instances": (_I, [_P, _P]),
+    "hikari_plugin_update_transforms": (_I, [_P, _P, C.POINTER(_I)]),
     "hikari_plugin_run_frame": (_I, [_P, C.POINTER(Settings), C.POINTER(L.View), C.POINTER(L.PreviousView), C.POINTER(L.Lights)]),
     "hikari_plugin_context": (_P, [_P]),
     "hikari_plugin_frame_counter": (_U64, [_P]),

@@ -56,7 +56,14 @@ struct hk_context {
     size_t band_pixels = 0, owned_pixels = 0;
     std::vector<void*> allocations;        // per-pixel planes
     std::vector<void*> scene_allocations;  // scene buffers: meshes, BLAS nodes, materials, textures
-    struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[14];  // scene buffers rewritten by hk_scene_update_instances (grow-only)
+    struct DevBuf { void* p = nullptr; size_t cap = 0; } ibuf[20];  // scene buffers rewritten by hk_scene_update_instances (grow-only);
+                                                                    // 14-19: staging + scratch of hk_scene_update_transforms
+    // hk_scene_update_transforms: what the last full upload fixed, and pinned staging (two slots, so that the host never waits for
+    // the copy of the previous call unless it is two calls behind)
+    uint32_t scene_instance_count = 0, scene_emissive_count = 0;
+    std::vector<uint32_t> wide_mesh_of;                     // per instance: index into wide_meshes
+    struct PinBuf { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; } pin[2];
+    int pin_slot = 0;
     // image-exact traversal mode (hk_wide.cuh): 4-wide trees of the meshes the instances use, rebuilt only when that set changes
     struct WideMesh { uint32_t base = 0, root = 0xFFFFFFFFu, need = 0; bool ok = false; };
     std::vector<std::array<uint32_t, 3>> wide_mesh_keys;    // (node_offset, node_count, primitive) in first-use order
@@ -377,6 +384,7 @@ void hk_context_destroy(hk_context* ctx) {
     free_list(ctx->allocations);
     free_list(ctx->scene_allocations);
     for (auto& b : ctx->ibuf) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    for (auto& b : ctx->pin) { if (b.p) cudaFreeHost(b.p); if (b.ev) cudaEventDestroy(b.ev); b = hk_context::PinBuf(); }
     if (ctx->noise) cudaFree(ctx->noise);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->spatial_tables) cudaFree(ctx->spatial_tables);
@@ -453,6 +461,35 @@ static cudaError_t upload_into(hk_context* ctx, hk_context::DevBuf& b, const T**
     return e;
 }
 
+// The 4-wide tree over the instances (the half of upload_wide that every instance update repeats) from the flat TLAS in `nodes`
+// (host memory); the meshes' trees and ctx->wide_mesh_of are those of the last upload_wide.
+static int upload_wide_tlas(hk_context* ctx, const hk_node* nodes, uint32_t node_count, uint32_t instance_count, DeviceScene& d) {
+    d.wide_ready = 0u; d.wide_tlas_root = WIDE_EMPTY;
+    hkw::WideTree tlas = hkw::build_wide(nodes, node_count, instance_count);
+    bool ok = tlas.ok && ctx->wide_mesh_of.size() == instance_count;
+    uint32_t blas_need = 0;
+    std::vector<uint2> entry(instance_count);
+    for (uint32_t i = 0; i < instance_count && ctx->wide_mesh_of.size() == instance_count; ++i) {
+        const hk_context::WideMesh& m = ctx->wide_meshes[ctx->wide_mesh_of[i]];
+        ok = ok && m.ok;
+        entry[i] = make_uint2(m.base, m.root);
+        blas_need = std::max(blas_need, m.need);
+    }
+    if (!tlas.ok) { tlas.nodes.clear(); tlas.rank.assign(instance_count, 0u); }
+    ctx->wide_tlas_node_count = (uint32_t)tlas.nodes.size();
+    HK_CUDA(upload_into(ctx, ctx->ibuf[9], &d.wide_tlas, tlas.nodes.data(), tlas.nodes.size()));
+    HK_CUDA(upload_into(ctx, ctx->ibuf[11], &d.wide_instance, entry.data(), entry.size()));
+    HK_CUDA(upload_into(ctx, ctx->ibuf[12], &d.wide_instance_rank, tlas.rank.data(), tlas.rank.size()));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    // pending TLAS siblings + the BLAS marker + pending BLAS siblings, and the three pushes a node step makes before it pops
+    ctx->wide_stack_need = tlas.stack_need + 1u + blas_need + 3u;
+    if (ok && ctx->wide_stack_need <= (uint32_t)HK_WIDE_STACK) {
+        d.wide_tlas_root = tlas.root;
+        d.wide_ready = 1u;
+    }
+    return HK_OK;
+}
+
 // The 4-wide trees of the image-exact traversal mode (hk_wide.cuh / wide_build.h) for the scene in `s`: one tree per distinct mesh
 // (rebuilt only when the set of meshes in use changes), one over the instances (every call), the per-instance entry points and the
 // array-order ranks that settle ties.  d.wide_ready stays 0 — and every launch keeps the reference's walk — when a flat array is not
@@ -495,29 +532,8 @@ static int upload_wide(hk_context* ctx, const hk_scene_desc* s, DeviceScene& d) 
         d.wide_blas = reinterpret_cast<const hk_wide_node*>(ctx->ibuf[10].p);
         d.wide_primitive_rank = reinterpret_cast<const uint32_t*>(ctx->ibuf[13].p);
     }
-    hkw::WideTree tlas = hkw::build_wide(s->instance_nodes, s->instance_node_count, s->instance_count);
-    bool ok = tlas.ok;
-    uint32_t blas_need = 0;
-    std::vector<uint2> entry(s->instance_count);
-    for (uint32_t i = 0; i < s->instance_count; ++i) {
-        const hk_context::WideMesh& m = ctx->wide_meshes[mesh_of[i]];
-        ok = ok && m.ok;
-        entry[i] = make_uint2(m.base, m.root);
-        blas_need = std::max(blas_need, m.need);
-    }
-    if (!tlas.ok) { tlas.nodes.clear(); tlas.rank.assign(s->instance_count, 0u); }
-    ctx->wide_tlas_node_count = (uint32_t)tlas.nodes.size();
-    HK_CUDA(upload_into(ctx, ctx->ibuf[9], &d.wide_tlas, tlas.nodes.data(), tlas.nodes.size()));
-    HK_CUDA(upload_into(ctx, ctx->ibuf[11], &d.wide_instance, entry.data(), entry.size()));
-    HK_CUDA(upload_into(ctx, ctx->ibuf[12], &d.wide_instance_rank, tlas.rank.data(), tlas.rank.size()));
-    HK_CUDA(cudaStreamSynchronize(ctx->stream));
-    // pending TLAS siblings + the BLAS marker + pending BLAS siblings, and the three pushes a node step makes before it pops
-    ctx->wide_stack_need = tlas.stack_need + 1u + blas_need + 3u;
-    if (ok && ctx->wide_stack_need <= (uint32_t)HK_WIDE_STACK) {
-        d.wide_tlas_root = tlas.root;
-        d.wide_ready = 1u;
-    }
-    return HK_OK;
+    ctx->wide_mesh_of = mesh_of;
+    return upload_wide_tlas(ctx, s->instance_nodes, s->instance_node_count, s->instance_count, d);
 }
 
 // Validation + upload of the per-frame half of the scene (instances, TLAS, emissives, emissive BVH, alias tables,
@@ -653,6 +669,8 @@ static int upload_instances(hk_context* ctx, const hk_scene_desc* s, DeviceScene
         }
     }
     HK_CUDA(cudaStreamSynchronize(ctx->stream));      // caller's arrays (and `moved`) may be freed after return
+    ctx->scene_instance_count = s->instance_count;
+    ctx->scene_emissive_count = s->emissive_count;
     return upload_wide(ctx, s, d);
 }
 
@@ -759,6 +777,129 @@ int hk_scene_update_instances(hk_context* ctx, const hk_scene_desc* s) {
         return rc;
     }
     ctx->scene = d;
+    return HK_OK;
+}
+
+static bool wide_primary(const hk_context* ctx);
+static bool wide_light(const hk_context* ctx);
+// grow-only device scratch
+static cudaError_t ensure_buf(hk_context::DevBuf& b, size_t bytes) {
+    const size_t need = bytes + 64;
+    if (b.cap >= need) return cudaSuccess;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    const size_t cap = need + need / 2;
+    cudaError_t e = cudaMalloc(&b.p, cap);
+    if (e == cudaSuccess) b.cap = cap;
+    return e;
+}
+
+// SURVEY 8(f) rank 2 — the per-frame half of the scene rebuilt on the device (kernels_scene.cu) from the model matrices alone.
+int hk_scene_update_transforms(hk_context* ctx, const float* models, const float* previous_models, const float* mesh_aabbs, uint32_t instance_count) {
+    if (!ctx || (instance_count && (!models || !mesh_aabbs))) return HK_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene_ready) return set_error(ctx, HK_ERR_NOT_READY, "hk_scene_update_transforms needs a scene from hk_scene_upload");
+    if (instance_count != ctx->scene_instance_count)
+        return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "hk_scene_update_transforms moves the instances of the last upload: their number must be unchanged "
+                                                       "(a changed set goes through hk_scene_update_instances)");
+    const uint32_t n = instance_count, ne = ctx->scene_emissive_count;
+    if (n == 0u) return HK_OK;
+    DeviceScene d = ctx->scene;
+    // the arrays being rebuilt in place must have bvh 0.7.1's sizes (3 m - 2 records over m >= 2 shapes, 1 over one)
+    const uint32_t tlas_records = n == 1u ? 1u : 3u * n - 2u, em_records = ne == 0u ? 0u : (ne == 1u ? 1u : 3u * ne - 2u);
+    if (d.instance_node_count != tlas_records || d.emissive_node_count != em_records)
+        return set_error(ctx, HK_ERR_UNSUPPORTED, "the uploaded TLAS / emissive BVH is not in bvh 0.7.1's flatten_custom layout: use hk_scene_update_instances");
+    HK_CUDA(cudaSetDevice(ctx->device));
+    const size_t mbytes = 64u * (size_t)n, abytes = 24u * (size_t)n;
+    const size_t stage_bytes = mbytes * (previous_models ? 2u : 1u) + abytes;
+    // pinned staging: the caller's arrays are free on return and the host does not wait for the frames in flight
+    hk_context::PinBuf& pin = ctx->pin[ctx->pin_slot];
+    ctx->pin_slot ^= 1;
+    if (!pin.ev) HK_CUDA(cudaEventCreateWithFlags(&pin.ev, cudaEventDisableTiming));
+    if (pin.used) HK_CUDA(cudaEventSynchronize(pin.ev));          // the copy made from this slot two calls ago
+    if (pin.cap < stage_bytes) {
+        if (pin.p) cudaFreeHost(pin.p);
+        pin.p = nullptr; pin.cap = 0;
+        HK_CUDA(cudaMallocHost(&pin.p, stage_bytes + stage_bytes / 2));
+        pin.cap = stage_bytes + stage_bytes / 2;
+    }
+    uint8_t* hp = static_cast<uint8_t*>(pin.p);
+    memcpy(hp, models, mbytes);
+    memcpy(hp + mbytes, mesh_aabbs, abytes);
+    if (previous_models) memcpy(hp + mbytes + abytes, previous_models, mbytes);
+    const uint32_t nmax = n > ne ? n : ne;
+    HK_CUDA(ensure_buf(ctx->ibuf[14], stage_bytes));
+    HK_CUDA(ensure_buf(ctx->ibuf[5], mbytes));
+    HK_CUDA(ensure_buf(ctx->ibuf[6], 4u * (size_t)n));
+    HK_CUDA(ensure_buf(ctx->ibuf[17], 16u * (size_t)nmax));
+    HK_CUDA(ensure_buf(ctx->ibuf[18], 16u * (size_t)nmax));
+    HK_CUDA(ensure_buf(ctx->ibuf[19], hk_scene_bvh_scratch_bytes(nmax)));
+    uint8_t* dp = static_cast<uint8_t*>(ctx->ibuf[14].p);
+    HK_CUDA(cudaMemcpyAsync(dp, hp, stage_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HK_CUDA(cudaEventRecord(pin.ev, ctx->stream));
+    pin.used = true;
+    hk_instance* instances = static_cast<hk_instance*>(ctx->ibuf[1].p);
+    hk_emissive* emissives = static_cast<hk_emissive*>(ctx->ibuf[4].p);
+    float4* box_lo = static_cast<float4*>(ctx->ibuf[17].p);
+    float4* box_hi = static_cast<float4*>(ctx->ibuf[18].p);
+    hk_launch_scene_instances(n, reinterpret_cast<const float4*>(dp), previous_models ? reinterpret_cast<const float4*>(dp + mbytes + abytes) : nullptr,
+                              reinterpret_cast<const float*>(dp + mbytes), instances, static_cast<hk_instance_trav*>(ctx->ibuf[8].p),
+                              static_cast<float4*>(ctx->ibuf[5].p), static_cast<uint32_t*>(ctx->ibuf[6].p), box_lo, box_hi, ctx->stream);
+    hk_launch_build_flat_bvh(n, box_lo, box_hi, ctx->ibuf[19].p, static_cast<hk_node*>(ctx->ibuf[2].p),
+                             reinterpret_cast<uint8_t*>(instances) + offsetof(hk_instance, node_index), (uint32_t)sizeof(hk_instance), ctx->stream);
+    if (ne) {
+        hk_launch_scene_emissives(ne, emissives, instances, d.materials, d.primitives, d.vertices, box_lo, box_hi, ctx->stream);
+        hk_launch_build_flat_bvh(ne, box_lo, box_hi, ctx->ibuf[19].p, static_cast<hk_node*>(ctx->ibuf[3].p),
+                                 reinterpret_cast<uint8_t*>(emissives) + offsetof(hk_emissive, node_index), (uint32_t)sizeof(hk_emissive), ctx->stream);
+    }
+    HK_CUDA(cudaGetLastError());
+    ctx->launches += ne ? 4u : 2u;
+    d.previous_models = static_cast<const float4*>(ctx->ibuf[5].p);
+    d.instance_moved = static_cast<const uint32_t*>(ctx->ibuf[6].p);
+    d.leaf_boxes_match = ctx->mesh_boxes_match ? 1u : 0u;       // every navigator carries its instance's own box by construction
+    d.wide_ready = 0u; d.wide_tlas_root = WIDE_EMPTY;
+    if (wide_primary(ctx) || wide_light(ctx)) {
+        // image-exact traversal mode in use: its 4-wide TLAS is derived on the host from the records just built (one small read-back;
+        // scenes that walk the reference's arrays never reach this and never synchronise)
+        std::vector<hk_node> nodes(tlas_records);
+        HK_CUDA(cudaMemcpyAsync(nodes.data(), ctx->ibuf[2].p, sizeof(hk_node) * (size_t)tlas_records, cudaMemcpyDeviceToHost, ctx->stream));
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        int rc = upload_wide_tlas(ctx, nodes.data(), tlas_records, n, d);
+        if (rc != HK_OK) return rc;
+    }
+    ctx->scene = d;
+    return HK_OK;
+}
+
+// Test / debugging aid: the per-frame scene buffers as they are on the device (what hk_scene_update_transforms built in place).
+static bool scene_buffer(const hk_context* ctx, int which, const void** src, size_t* have) {
+    const DeviceScene& d = ctx->scene;
+    switch (which) {
+        case HK_SCENE_INSTANCES: *src = d.instances; *have = sizeof(hk_instance) * (size_t)ctx->scene_instance_count; return true;
+        case HK_SCENE_INSTANCE_NODES: *src = d.instance_nodes; *have = sizeof(hk_node) * (size_t)d.instance_node_count; return true;
+        case HK_SCENE_EMISSIVES: *src = d.emissives; *have = sizeof(hk_emissive) * (size_t)ctx->scene_emissive_count; return true;
+        case HK_SCENE_EMISSIVE_NODES: *src = d.emissive_nodes; *have = sizeof(hk_node) * (size_t)d.emissive_node_count; return true;
+        case HK_SCENE_PREVIOUS_MODELS: *src = d.previous_models; *have = d.previous_models ? 64u * (size_t)ctx->scene_instance_count : 0u; return true;
+        case HK_SCENE_INSTANCE_MOVED: *src = d.instance_moved; *have = d.instance_moved ? 4u * (size_t)ctx->scene_instance_count : 0u; return true;
+        default: return false;
+    }
+}
+int hk_scene_buffer_bytes(hk_context* ctx, int which, size_t* bytes) {
+    if (!ctx || !bytes) return HK_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene_ready) return set_error(ctx, HK_ERR_NOT_READY, "no scene");
+    const void* src = nullptr;
+    if (!scene_buffer(ctx, which, &src, bytes)) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown scene buffer");
+    return HK_OK;
+}
+int hk_scene_readback(hk_context* ctx, int which, void* host, size_t bytes) {
+    if (!ctx || (!host && bytes)) return HK_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene_ready) return set_error(ctx, HK_ERR_NOT_READY, "no scene");
+    const void* src = nullptr;
+    size_t have = 0;
+    if (!scene_buffer(ctx, which, &src, &have)) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "unknown scene buffer");
+    if (bytes != have) return set_error(ctx, HK_ERR_INVALID_ARGUMENT, "size mismatch");
+    HK_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) HK_CUDA(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }
 

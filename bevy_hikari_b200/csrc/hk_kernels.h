@@ -35,3 +35,14 @@ void hk_launch_halo_copy(const hkd::Planes& dst, const hkd::Band& dst_band, cons
 // the same for one Rgba16Float image stored over the tiles' allocations at `scale` x the render resolution
 void hk_launch_halo_copy_image(uint2* dst, const hkd::Band& dst_band, const uint2* src, const hkd::Band& src_band, int scale,
                                int x0, int x1, int y0, int y1, cudaStream_t st);
+
+// the per-frame half of the scene rebuilt on the device (kernels_scene.cu; hk_scene_update_transforms)
+void hk_launch_scene_instances(uint32_t n, const float4* models, const float4* previous, const float* mesh_aabbs, hk_instance* instances,
+                               hkd::hk_instance_trav* trav, float4* previous_out, uint32_t* moved_out, float4* box_lo, float4* box_hi, cudaStream_t st);
+// bvh 0.7.1 BVH::build + flatten_custom over n boxes into out[0 .. 3n-2); every shape's tree-node index is written to
+// index_base + shape * index_stride.  `scratch`: hk_scene_bvh_scratch_bytes(n) bytes.
+void hk_launch_build_flat_bvh(uint32_t n, const float4* box_lo, const float4* box_hi, void* scratch, hk_node* out, void* index_base,
+                              uint32_t index_stride, cudaStream_t st);
+size_t hk_scene_bvh_scratch_bytes(uint32_t n);
+void hk_launch_scene_emissives(uint32_t ne, hk_emissive* emissives, const hk_instance* instances, const hk_material* materials,
+                               const hk_primitive* primitives, const hk_vertex* vertices, float4* box_lo, float4* box_hi, cudaStream_t st);

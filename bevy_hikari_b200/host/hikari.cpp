@@ -386,6 +386,7 @@ uint32_t MeshMaterialWorld::add_texture(const hk_texture_desc& t, const uint8_t*
 }
 
 void MeshMaterialWorld::prepare_mesh_assets() {  // mesh.rs:106-166
+    mesh_aabb_ok_.clear();
     if (!universal_settings.build_mesh_acceleration_structure) return;
     gpu_meshes_.assign(meshes_.size(), GpuMesh());
     mesh_ok_.assign(meshes_.size(), false);
@@ -439,6 +440,8 @@ void MeshMaterialWorld::prepare_instances() {  // instance.rs:245-444
         const float* previous = d.has_queue ? d.queue[1] : d.transform;        // PreviousMeshUniform::transform = queue[1]
         previous_models.insert(previous_models.end(), previous, previous + 16);
     }
+    kept_.clear();
+    for (const InstanceDesc* d : kept) kept_.push_back({(uint32_t)(d - instances_in_.data()), d->mesh, d->material});
     for (const InstanceDesc* d : kept) {
         const GpuMesh& g = gpu_meshes_[d->mesh];
         // bevy Aabb of the mesh: from_min_max over the positions
@@ -525,6 +528,55 @@ void MeshMaterialWorld::prepare_instances() {  // instance.rs:245-444
         emissive_nodes = build_flat_bvh(mn, mx, &node_index);
         for (size_t i = 0; i < emissives.size(); ++i) emissives[i].node_index = node_index[i];
     }
+}
+
+static void scale_of(const float* m, float scale[3]) {   // glam Mat4::to_scale_rotation_translation().0
+    float det3 = m[0] * (m[5] * m[10] - m[6] * m[9]) - m[4] * (m[1] * m[10] - m[2] * m[9]) + m[8] * (m[1] * m[6] - m[2] * m[5]);
+    scale[0] = length3(m) * (det3 < 0.0f ? -1.0f : 1.0f);
+    scale[1] = length3(m + 4);
+    scale[2] = length3(m + 8);
+}
+
+bool MeshMaterialWorld::prepare_instance_transforms() {
+    if (!universal_settings.build_instance_acceleration_structure) return false;
+    std::vector<const InstanceDesc*> kept;
+    for (const InstanceDesc& d : instances_in_) {
+        if (!d.visible) continue;
+        if (d.mesh >= meshes_.size() || !mesh_ok_[d.mesh] || d.material >= materials.size()) continue;
+        kept.push_back(&d);
+    }
+    if (kept.size() != kept_.size() || kept.size() != instances.size()) return false;
+    for (size_t i = 0; i < kept.size(); ++i)
+        if ((uint32_t)(kept[i] - instances_in_.data()) != kept_[i].entity || kept[i]->mesh != kept_[i].mesh || kept[i]->material != kept_[i].material)
+            return false;
+    // an emissive whose scale left its cached alias table's range needs the table rebuilt: the full path
+    for (const hk_emissive& em : emissives) {
+        const InstanceDesc* d = kept[em.instance];
+        const size_t entity = (size_t)(d - instances_in_.data());
+        if (entity >= alias_table_cache_.size() || !alias_table_cache_[entity].valid) return false;
+        float scale[3];
+        scale_of(d->transform, scale);
+        const CachedAliasTable& c = alias_table_cache_[entity];
+        if (!(fabsf(c.scale[0] - scale[0]) <= 0.01f && fabsf(c.scale[1] - scale[1]) <= 0.01f && fabsf(c.scale[2] - scale[2]) <= 0.01f)) return false;
+    }
+    mesh_aabb_.resize(meshes_.size());
+    mesh_aabb_ok_.resize(meshes_.size(), false);
+    transform_models.clear(); transform_previous.clear(); transform_aabbs.clear();
+    for (const InstanceDesc* d : kept) {
+        if (!mesh_aabb_ok_[d->mesh]) {   // bevy Aabb of the mesh: from_min_max over the positions, as prepare_instances computes it
+            const GpuMesh& g = gpu_meshes_[d->mesh];
+            float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
+            for (const hk_vertex& v : g.vertices)
+                for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], v.position[k]); mx[k] = std::max(mx[k], v.position[k]); }
+            for (int k = 0; k < 3; ++k) { mesh_aabb_[d->mesh][k] = 0.5f * (mx[k] + mn[k]); mesh_aabb_[d->mesh][3 + k] = 0.5f * (mx[k] - mn[k]); }
+            mesh_aabb_ok_[d->mesh] = true;
+        }
+        const float* previous = d->has_queue ? d->queue[1] : d->transform;
+        transform_models.insert(transform_models.end(), d->transform, d->transform + 16);
+        transform_previous.insert(transform_previous.end(), previous, previous + 16);
+        transform_aabbs.insert(transform_aabbs.end(), mesh_aabb_[d->mesh].begin(), mesh_aabb_[d->mesh].end());
+    }
+    return true;
 }
 
 void MeshMaterialWorld::prepare() { prepare_mesh_assets(); prepare_material_assets(); prepare_instances(); }

@@ -149,6 +149,15 @@ public:
     void set_instance_transform(uint32_t instance, const float transform[16]);
     void set_instance_visible(uint32_t instance, bool visible);
     void previous_transform_system();
+    // The transforms-only form of prepare_instances for hk_scene_update_transforms (the device rebuilds AABBs, TLAS, emissives and
+    // the emissive BVH itself): fills transform_models / transform_previous (16 floats per kept instance: GlobalTransform and
+    // PreviousMeshUniform::transform) and transform_aabbs (6 floats: centre and half extents of the mesh's Aabb, instance.rs:293-296)
+    // and returns true — or returns false when the device path does not apply and prepare_instances + hk_scene_update_instances must
+    // run instead: the kept SET of (entity, mesh, material) differs from the last prepare_instances, or an emissive instance's
+    // alias table would be rebuilt (scale moved by more than 0.01 from the cached one, instance.rs:385-397).  Does not touch the
+    // buffers of scene_desc(): after a device update they describe the last prepare_instances, not the device.
+    bool prepare_instance_transforms();
+    std::vector<float> transform_models, transform_previous, transform_aabbs;
     std::vector<float> previous_models;                    // 16 floats per entry of `instances`, queue[1] (or the model itself)
     hk_scene_desc scene_desc() const;                      // views into the vectors below; valid until the next prepare()
     const std::vector<PrepareMeshError>& mesh_errors() const { return mesh_errors_; }
@@ -172,6 +181,10 @@ private:
     std::vector<StandardMaterial> materials_in_;
     std::vector<InstanceDesc> instances_in_;
     struct CachedAliasTable { bool valid = false; float scale[3] = {0, 0, 0}; std::vector<hk_alias_entry> table; };
+    struct KeptInstance { uint32_t entity, mesh, material; };
+    std::vector<KeptInstance> kept_;                       // the instances of the last prepare_instances, in buffer order
+    std::vector<std::array<float, 6>> mesh_aabb_;          // per mesh: centre | half extents, filled on first use
+    std::vector<bool> mesh_aabb_ok_;
     std::vector<CachedAliasTable> alias_table_cache_;      // per entity: Local<HashMap<Entity, (Vec3, Vec<GpuAliasEntry>)>>, instance.rs:253,386-397
     std::vector<hk_texture_desc> textures_;
     std::vector<std::vector<uint8_t>> texture_pixels_;
@@ -204,6 +217,9 @@ public:
     int upload_scene(const MeshMaterialWorld& world);
     // instance-level buffers only (hk_scene_update_instances): what instance.rs:427-435 rewrites when instances change
     int update_instances(const MeshMaterialWorld& world);
+    // Animated instances through the device-side rebuild (hk_scene_update_transforms) whenever only transforms changed since the
+    // last prepare_instances; otherwise world.prepare_instances() + hk_scene_update_instances.  *used_device_path says which.
+    int update_transforms(MeshMaterialWorld& world, bool* used_device_path = nullptr);
     // One frame of the camera's sub-graph: PREPASS -> LIGHT -> POST_PROCESS (lib.rs:258-365).  Increments the counter
     // first, as frame_counter_system does in PostUpdate (view.rs:89-103).
     int run_frame(const HikariSettings& settings, const ViewInputs& view);

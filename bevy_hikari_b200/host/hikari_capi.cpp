@@ -88,6 +88,14 @@ void hikari_world_set_instance_transform(hikari_world* w, uint32_t instance, con
 void hikari_world_set_instance_visible(hikari_world* w, uint32_t instance, uint32_t visible) { W(w)->set_instance_visible(instance, visible != 0); }
 void hikari_world_previous_transform_system(hikari_world* w) { W(w)->previous_transform_system(); }
 void hikari_world_scene_desc(hikari_world* w, hk_scene_desc* out) { *out = W(w)->scene_desc(); }
+int hikari_world_prepare_instance_transforms(hikari_world* w, const float** models, const float** previous_models, const float** mesh_aabbs,
+                                             uint32_t* instance_count) {
+    MeshMaterialWorld* world = W(w);
+    if (!world->prepare_instance_transforms()) return 0;
+    *models = world->transform_models.data(); *previous_models = world->transform_previous.data();
+    *mesh_aabbs = world->transform_aabbs.data(); *instance_count = (uint32_t)(world->transform_models.size() / 16);
+    return 1;
+}
 int hikari_world_mesh_error(hikari_world* w, uint32_t mesh) {
     const auto& e = W(w)->mesh_errors();
     return mesh < e.size() ? (int)e[mesh] : -1;

@@ -32,6 +32,20 @@ int HikariPlugin::update_instances(const MeshMaterialWorld& world) {
     hk_scene_desc d = world.scene_desc();
     return hk_scene_update_instances(ctx_, &d);
 }
+int HikariPlugin::update_transforms(MeshMaterialWorld& world, bool* used_device_path) {
+    if (!ctx_) return HK_ERR_NOT_READY;
+    if (world.prepare_instance_transforms()) {
+        int rc = hk_scene_update_transforms(ctx_, world.transform_models.data(), world.transform_previous.data(), world.transform_aabbs.data(),
+                                            (uint32_t)(world.transform_models.size() / 16));
+        if (rc != HK_ERR_UNSUPPORTED) {      // (a TLAS that is not in bvh 0.7.1's layout keeps the host path)
+            if (used_device_path) *used_device_path = true;
+            return rc;
+        }
+    }
+    if (used_device_path) *used_device_path = false;
+    world.prepare_instances();
+    return update_instances(world);
+}
 int HikariPlugin::run_frame(const HikariSettings& settings, const ViewInputs& view) {
     if (!ctx_) return HK_ERR_NOT_READY;
     counter.value += 1;

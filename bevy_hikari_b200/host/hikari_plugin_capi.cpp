@@ -26,6 +26,12 @@ int hikari_plugin_build_tile(hikari_plugin* p, int cuda_device, uint32_t width, 
 }
 int hikari_plugin_upload_scene(hikari_plugin* p, hikari_world* w) { return P(p)->upload_scene(*W(w)); }
 int hikari_plugin_update_instances(hikari_plugin* p, hikari_world* w) { return P(p)->update_instances(*W(w)); }
+int hikari_plugin_update_transforms(hikari_plugin* p, hikari_world* w, int* used_device_path) {
+    bool used = false;
+    int rc = P(p)->update_transforms(*W(w), &used);
+    if (used_device_path) *used_device_path = used ? 1 : 0;
+    return rc;
+}
 int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk_view* view,
                             const hk_previous_view* previous_view, const hk_lights* lights) {
     ViewInputs v;

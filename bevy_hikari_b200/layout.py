@@ -118,6 +118,7 @@ OUT_UPSCALED, OUT_TAA, OUT_FSR_SHARPENED = 11, 12, 13
 OUT_GBUFFER_POSITION, OUT_GBUFFER_NORMAL, OUT_GBUFFER_DEPTH_GRADIENT = 16, 17, 18
 OUT_GBUFFER_INSTANCE_MATERIAL, OUT_GBUFFER_VELOCITY_UV = 19, 20
 OUT_RESERVOIR_0 = 32
+SCENE_INSTANCES, SCENE_INSTANCE_NODES, SCENE_EMISSIVES, SCENE_EMISSIVE_NODES, SCENE_PREVIOUS_MODELS, SCENE_INSTANCE_MOVED = range(6)   # hk_scene_readback
 
 # bytes per pixel and numpy view of each read-back plane
 OUT_FORMATS = {}

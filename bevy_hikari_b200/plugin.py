@@ -107,6 +107,18 @@ class World:
     def prepare_instances(self):
         host_lib().hikari_world_prepare_instances(self._w)
 
+    def prepare_instance_transforms(self):
+        """The transforms-only form of prepare_instances (hikari_world_prepare_instance_transforms): (models, previous_models,
+        mesh_aabbs) as float32 arrays of 16 / 16 / 6 columns, or None when the device path does not apply."""
+        m, pm, ab, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        if not host_lib().hikari_world_prepare_instance_transforms(self._w, C.byref(m), C.byref(pm), C.byref(ab), C.byref(n)):
+            return None
+        k = n.value
+
+        def arr(ptr, cols):
+            return np.frombuffer(C.string_at(ptr.value, k * cols * 4), np.float32).reshape(k, cols).copy() if k else np.zeros((0, cols), np.float32)
+        return arr(m, 16), arr(pm, 16), arr(ab, 6)
+
     def previous_models(self):
         d = self.scene_desc()
         if not d.previous_instance_models or d.instance_count == 0:
@@ -210,6 +222,30 @@ class HikariPlugin:
 
     def update_instances_desc(self, desc):
         check(self._lib.hk_scene_update_instances(self.ctx, C.byref(desc)), self.ctx, self._lib)
+
+    def update_transforms(self, world):
+        """Animated instances, rebuilt on the device when only transforms changed (hk_scene_update_transforms), else through
+        prepare_instances + hk_scene_update_instances.  Returns True when the device path ran."""
+        used = C.c_int(0)
+        check(self._lib.hikari_plugin_update_transforms(self._p, world._w, C.byref(used)), self.ctx, self._lib)
+        return bool(used.value)
+
+    def update_transforms_arrays(self, models, mesh_aabbs, previous_models=None):
+        """hk_scene_update_transforms on explicit arrays (n x 16, n x 6, optional n x 16)"""
+        models = np.ascontiguousarray(models, np.float32); mesh_aabbs = np.ascontiguousarray(mesh_aabbs, np.float32)
+        prev = None if previous_models is None else np.ascontiguousarray(previous_models, np.float32)
+        check(self._lib.hk_scene_update_transforms(self.ctx, models.ctypes.data, prev.ctypes.data if prev is not None else None,
+                                                   mesh_aabbs.ctypes.data, len(models)), self.ctx, self._lib)
+
+    def scene_readback(self, which):
+        """the per-frame scene buffers as they are on the device (hk_scene_readback), as numpy structured arrays"""
+        dt = {L.SCENE_INSTANCES: L.INSTANCE, L.SCENE_INSTANCE_NODES: L.NODE, L.SCENE_EMISSIVES: L.EMISSIVE, L.SCENE_EMISSIVE_NODES: L.NODE,
+              L.SCENE_PREVIOUS_MODELS: np.dtype((np.float32, 16)), L.SCENE_INSTANCE_MOVED: np.dtype(np.uint32)}[which]
+        nbytes = C.c_size_t(0)
+        check(self._lib.hk_scene_buffer_bytes(self.ctx, int(which), C.byref(nbytes)), self.ctx, self._lib)
+        out = np.zeros(nbytes.value // dt.itemsize, dt)
+        check(self._lib.hk_scene_readback(self.ctx, int(which), out.ctypes.data, out.nbytes), self.ctx, self._lib)
+        return out
 
     @property
     def frame_counter(self):

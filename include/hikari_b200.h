@@ -182,6 +182,30 @@ int hk_scene_upload(hk_context* ctx, const hk_scene_desc* scene);
  * records (material.rs:139-203; texture indices keep referring to the uploaded textures).  Meshes, BLAS nodes and textures
  * of the last hk_scene_upload stay in place.  Only those members of `scene` are read. */
 int hk_scene_update_instances(hk_context* ctx, const hk_scene_desc* scene);
+/* The same per-frame part REBUILT ON THE DEVICE from what actually changed — one model matrix per instance (the
+ * reference does this on the CPU whenever anything moves, instance.rs:352-437, and lists asynchronous acceleration-structure builds as
+ * to do, README.md:27).  For the instances of the last hk_scene_upload / hk_scene_update_instances, same order, same number:
+ *   models            instance_count column-major mat4: GlobalTransform::compute_matrix() (instance.rs:287)
+ *   previous_models   PreviousMeshUniform::transform of every instance (instance.rs:111-128), or NULL = the model each instance had
+ *                     until this call (then call once per frame while anything moves, and once more after it stopped)
+ *   mesh_aabbs        instance_count x {center[3], half_extents[3]}: the bevy `Aabb` of each instance's mesh (instance.rs:293-296)
+ * Kernels on the context's stream recompute every instance's world AABB, model / inverse-transpose matrices and traversal record,
+ * rebuild the TLAS (bvh 0.7.1's bucketed SAH build + flatten_custom, one warp per tree node), every emissive's bounding sphere and
+ * surface area and the emissive BVH: record for record what host/hikari.cpp (= the reference's CPU path) produces
+ * (tests/test_gpu_scene_update.py), without a host round trip: the arrays are staged through pinned memory owned by the context and
+ * are the caller's again on return.  Unchanged by this call, hence the caller's to watch: the SET of instances / meshes / materials
+ * and the alias tables, which the reference rebuilds when an emissive instance's scale moved by more than 0.01 (instance.rs:385-397;
+ * hikari::MeshMaterialWorld::prepare_instance_transforms checks both and says when hk_scene_update_instances is needed instead).
+ * HK_ERR_UNSUPPORTED if the uploaded TLAS / emissive BVH is not in bvh 0.7.1's layout.  When rays walk the 4-wide trees
+ * (HK_TUNE_WIDE_TRAVERSAL in effect for this scene) the 4-wide TLAS is re-derived on the host from the records just built, which
+ * costs one small read-back and a stream synchronisation; otherwise the call never waits for the device. */
+int hk_scene_update_transforms(hk_context* ctx, const float* models, const float* previous_models, const float* mesh_aabbs,
+                               uint32_t instance_count);
+/* Test / debugging aid: the per-frame scene buffers as they are on the device, in the layouts of hk_layout.h. */
+enum { HK_SCENE_INSTANCES = 0, HK_SCENE_INSTANCE_NODES = 1, HK_SCENE_EMISSIVES = 2, HK_SCENE_EMISSIVE_NODES = 3,
+       HK_SCENE_PREVIOUS_MODELS = 4 /* 64 B per instance; empty when nothing moved */, HK_SCENE_INSTANCE_MOVED = 5 /* uint32 per instance */ };
+int hk_scene_buffer_bytes(hk_context* ctx, int which, size_t* bytes);
+int hk_scene_readback(hk_context* ctx, int which, void* host, size_t bytes);   /* bytes = hk_scene_buffer_bytes */
 int hk_set_noise(hk_context* ctx, const uint8_t* rgba8_64x64x16);   /* 16 textures of 64x64 RGBA8, lib.rs:189-219 */
 
 /* The five G-buffer render targets of a host-side raster prepass (src/prepass.rs:285-306; formats src/prepass.rs:43-47), as DEVICE

@@ -64,6 +64,12 @@ void hikari_world_set_instance_visible(hikari_world* w, uint32_t instance, uint3
 void hikari_world_previous_transform_system(hikari_world* w);
 void hikari_world_prepare_instances(hikari_world* w);
 void hikari_world_scene_desc(hikari_world* w, hk_scene_desc* out);        /* pointers valid until the next prepare */
+/* The transforms-only form of prepare_instances, for hk_scene_update_transforms (the device rebuilds AABBs / TLAS / emissives itself):
+ * 1 + the three arrays that call takes (valid until the next call) when only transforms changed since the last prepare_instances;
+ * 0 when the kept set of instances changed or an emissive's alias table must be rebuilt (scale moved by more than 0.01,
+ * instance.rs:385-397): then hikari_world_prepare_instances + hikari_plugin_update_instances. */
+int hikari_world_prepare_instance_transforms(hikari_world* w, const float** models, const float** previous_models, const float** mesh_aabbs,
+                                             uint32_t* instance_count);
 int hikari_world_mesh_error(hikari_world* w, uint32_t mesh);              /* PrepareMeshError as int, 0 = ok */
 
 hikari_plugin* hikari_plugin_create(void);
@@ -74,6 +80,9 @@ int hikari_plugin_build_tile(hikari_plugin* p, int cuda_device, uint32_t width, 
                              uint32_t row_begin, uint32_t row_end, const uint8_t* noise_rgba8_64x64x16, void* cuda_stream);
 int hikari_plugin_upload_scene(hikari_plugin* p, hikari_world* w);
 int hikari_plugin_update_instances(hikari_plugin* p, hikari_world* w);   /* hk_scene_update_instances: instance-level buffers only */
+/* animated instances, device-side: hk_scene_update_transforms when hikari_world_prepare_instance_transforms allows it, else
+ * prepare_instances + hk_scene_update_instances; *used_device_path (may be NULL) says which */
+int hikari_plugin_update_transforms(hikari_plugin* p, hikari_world* w, int* used_device_path);
 int hikari_plugin_run_frame(hikari_plugin* p, const hikari_settings* s, const hk_view* view,
                             const hk_previous_view* previous_view, const hk_lights* lights);
 hk_context* hikari_plugin_context(hikari_plugin* p);

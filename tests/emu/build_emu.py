@@ -19,7 +19,7 @@ ASAN = bool(os.environ.get("HK_EMU_ASAN"))      # AddressSanitizer build: a memc
 #                                                  LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)
 GEN, OUT = os.path.join(HERE, "_gen"), os.path.join(HERE, "_build_asan" if ASAN else "_build")
 LIB = os.path.join(OUT, "libhikari_emu.so")
-CU = ["context.cu", "kernels_light.cu", "kernels_pool.cu", "kernels_spatial.cu", "kernels_post.cu", "kernels_upscale.cu"]
+CU = ["context.cu", "kernels_light.cu", "kernels_pool.cu", "kernels_spatial.cu", "kernels_post.cu", "kernels_upscale.cu", "kernels_scene.cu"]
 CPP = ["hikari.cpp", "hikari_capi.cpp", "hikari_plugin.cpp", "hikari_plugin_capi.cpp"]
 CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 FLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-std=c++17", "-w",
