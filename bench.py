@@ -605,10 +605,31 @@ def run_ours(args):
             dev.update_instances(world)
             t2 = time.perf_counter()
             host_ms.append((t1 - t0) * 1e3); upload_ms.append((t2 - t1) * 1e3)
+        # the same motion through the device-side rebuild (hk_scene_update_transforms, csrc/kernels_scene.cu): host time of the call
+        # (pinned staging + 4 launches, no synchronisation unless rays walk the 4-wide trees) and time until the kernels have run
+        call_ms, done_ms, on_device = [], [], True
+        for n in range(12):
+            moved = base.copy()
+            moved[12] += 0.001 * (n + 13)
+            dev.sync()
+            t0 = time.perf_counter()
+            world.set_instance_transform(len(scene.inst_transform) - 1, moved)
+            world.previous_transform_system()
+            on_device = dev.update_transforms(world) and on_device
+            t1 = time.perf_counter()
+            dev.sync()
+            t2 = time.perf_counter()
+            call_ms.append((t1 - t0) * 1e3); done_ms.append((t2 - t0) * 1e3)
+        world.prepare_instances()          # leave the host mirror's buffers describing the scene on the device
+        dev.update_instances(world)
         d = world.scene_desc()
         scene_update = {"host_rebuild_ms": round(float(np.median(host_ms[2:])), 4), "upload_ms": round(float(np.median(upload_ms[2:])), 4),
+                        "device_rebuild_call_ms": round(float(np.median(call_ms[2:])), 4),
+                        "device_rebuild_done_ms": round(float(np.median(done_ms[2:])), 4), "device_path_taken": bool(on_device),
                         "instances": int(d.instance_count), "tlas_nodes": int(d.instance_node_count), "alias_entries": int(d.alias_count),
-                        "note": "per-frame cost when instances move; outside the timed region of value / e2e (static benchmark scene)"}
+                        "note": "per-frame cost when instances move, host path (prepare_instances + hk_scene_update_instances) against "
+                                "the device-side rebuild (hk_scene_update_transforms: call returns / kernels done); outside the timed "
+                                "region of value / e2e (static benchmark scene)"}
 
     if rank != 0:
         if world_size > 1:

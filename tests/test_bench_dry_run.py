@@ -25,6 +25,8 @@ def test_bench_line_has_the_contract_keys_on_the_emulated_kernels():
     assert d["roofline"]["kernel_ms_source"] == "live, timed region" and d["roofline"]["kernel"] in d["kernel_ms"]
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["d2h_bytes_per_step"] == 256 * 256 * 8
     assert len(d["frame_check"]["unsharded_sha256"]) == 64
+    # animated-scene block: the host path and the device-side rebuild (hk_scene_update_transforms) were both exercised
+    assert d["scene_update"]["device_path_taken"] is True and d["scene_update"]["device_rebuild_done_ms"] > 0
 
 
 def test_reference_arm_never_maps_the_cuda_library():
