@@ -99,6 +99,9 @@ SYMBOLS = {
     "hikari_world_scene_desc": (None, [_P, C.POINTER(L.SceneDesc)]),
     "hikari_world_mesh_error": (_I, [_P, _U32]),
     "hikari_world_prepare_instance_transforms": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_U32)]),
+    "hikari_world_load_gltf": (_I, [_P, C.c_char_p, _P, _P, _P, _P, C.c_char_p, _SZ]),
+    "hikari_decode_png": (_I, [_P, _SZ, _P, C.POINTER(_U32), C.POINTER(_U32)]),
+    "hikari_world_add_shape": (_U32, [_P, _U32, _P]),
     "hikari_plugin_create": (_P, []),
     "hikari_plugin_destroy": (None, [_P]),
     "hikari_plugin_build": (_I, [_P, _I, _U32, _U32, _U32, _U32, _P, _P]),

@@ -39,7 +39,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 
 CU = ["csrc/context.cu", "csrc/kernels_light.cu", "csrc/kernels_pool.cu", "csrc/kernels_spatial.cu", "csrc/kernels_post.cu", "csrc/kernels_upscale.cu", "csrc/kernels_scene.cu"]
-CPP_HOST = ["host/hikari.cpp", "host/hikari_capi.cpp"]                     # -> libhikari_host.so
+CPP_HOST = ["host/hikari.cpp", "host/hikari_capi.cpp", "host/gltf_ingest.cpp"]                     # -> libhikari_host.so
 CPP_PLUGIN = ["host/hikari_plugin.cpp", "host/hikari_plugin_capi.cpp"]     # -> libhikari_b200.so (they call hk_*)
 HEADERS = ["csrc/hk_device.cuh", "csrc/hk_pool.cuh", "csrc/hk_wide.cuh", "csrc/wide_build.h", "csrc/hk_tile.cuh", "csrc/hk_kernels.h", "host/hikari.hpp", "host/hikari_settings_convert.hpp",
            "../include/hk_math.h", "../include/hk_layout.h", "../include/hikari_b200.h", "../include/hikari_host.h"]
@@ -112,7 +112,7 @@ def build(force=False, verbose=False, ptxas_info=False, out=None):
             "-Xlinker", "-rpath,$ORIGIN", "-Xlinker", "-rpath," + HERE]
     # (variant builds never re-link the host library: several of them run at once and the default build owns it)
     if (out is None and jobs) or not os.path.exists(HOST_LIB):
-        logs.append(_run([CXX, "-shared", "-o", HOST_LIB] + host_objs))
+        logs.append(_run([CXX, "-shared", "-o", HOST_LIB] + host_objs + ["-lz"]))
     if jobs or not os.path.exists(lib):
         logs.append(_run([NVCC, "-shared", "-o", lib] + cuda_objs + link))
     if out is None and (jobs or not os.path.exists(EXACT_LIB)):

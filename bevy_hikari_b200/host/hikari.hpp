@@ -190,6 +190,29 @@ private:
     std::vector<std::vector<uint8_t>> texture_pixels_;
 };
 
+// ------------------------------------------------------------------------------------------------ scene ingest (gltf_ingest.cpp)
+// Run-time glTF 2.0 ingest into a MeshMaterialWorld: what `asset_server.load("x.glb#Scene0")` + the extraction systems of
+// src/mesh_material/{mesh,material,instance}.rs hand the render world.  One Mesh per glTF primitive, one StandardMaterial per glTF
+// material (+ StandardMaterial::default() for primitives without one), one instance per (node, primitive) in depth-first node order
+// with the node's world matrix (x `parent_transform`, NULL = identity), one texture per (image, colour space): base colour and
+// emissive sRGB, metallic-roughness / normal / occlusion linear (material.rs:55-87), wrap modes and mag filter from the sampler.
+// PNG is decoded here; other encodings (JPEG) by `decoder` (NULL = fail on them), as image decoding is the host app's job.
+struct GltfImage { std::vector<uint8_t> rgba; uint32_t width = 0, height = 0; };
+typedef bool (*GltfImageDecoder)(const uint8_t* bytes, size_t size, const char* mime_type, void* user, GltfImage* out);
+struct GltfLoadResult {
+    std::vector<uint32_t> meshes, materials, instances, textures;    // ids the world assigned, in glTF order
+    std::string error;
+};
+bool load_gltf(MeshMaterialWorld& world, const char* path, const float* parent_transform, GltfImageDecoder decoder, void* user,
+               GltfLoadResult* out);
+bool decode_png_rgba8(const uint8_t* bytes, size_t size, GltfImage* out);
+// Mesh::from(shape::Plane / UVSphere / Box) of bevy 0.9, the generators the reference's examples spawn (scene.rs:86-113, city.rs:64-90)
+namespace shape {
+Mesh plane(float size);
+Mesh uv_sphere(float radius, uint32_t sectors, uint32_t stacks);
+Mesh box(float x_length, float y_length, float z_length);      // shape::Cube { size } = box(size, size, size)
+}  // namespace shape
+
 // ------------------------------------------------------------------------------------------------ nodes
 struct ViewInputs {                           // what the render graph resolves for the "view" slot (light.rs:596-617)
     hk_view view;

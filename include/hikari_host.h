@@ -72,6 +72,29 @@ int hikari_world_prepare_instance_transforms(hikari_world* w, const float** mode
                                              uint32_t* instance_count);
 int hikari_world_mesh_error(hikari_world* w, uint32_t mesh);              /* PrepareMeshError as int, 0 = ok */
 
+/* Run-time glTF 2.0 ingest (.glb, or .gltf with side-car / data: buffers) into the world: meshes (one per glTF primitive; triangle
+ * lists and strips), materials, instances (depth-first node order, world matrices in glam f32 arithmetic, x parent_transform16 or
+ * identity when NULL) and textures (one per image and colour space; sampler wrap modes / filter) — the rules of
+ * src/mesh_material/{mesh,material,instance}.rs + bevy_gltf, see host/gltf_ingest.cpp.  Call hikari_world_prepare afterwards.
+ * PNG images are decoded by the library; anything else is handed to `decoder` (NULL = such a file fails), called twice per image:
+ * first with rgba_out = NULL to report *width / *height, then with a width*height*4-byte buffer to fill; returns non-zero on success.
+ * Returns 1 on success; on failure 0 and the reason in `error` (truncated to error_capacity).  `counts` (may be NULL) receives the
+ * ids the world assigned: each range is contiguous. */
+typedef int (*hikari_image_decoder)(const uint8_t* bytes, size_t size, const char* mime_type, void* user, uint8_t* rgba_out,
+                                    uint32_t* width, uint32_t* height);
+typedef struct hikari_gltf_counts {
+    uint32_t first_mesh, mesh_count, first_material, material_count, first_instance, instance_count, first_texture, texture_count;
+} hikari_gltf_counts;
+int hikari_world_load_gltf(hikari_world* w, const char* path, const float* parent_transform16, hikari_image_decoder decoder, void* user,
+                           hikari_gltf_counts* counts, char* error, size_t error_capacity);
+/* the library's PNG decoder on its own (8 / 16-bit grey, grey+alpha, RGB, RGBA, palette, 1/2/4-bit grey and palette; non-interlaced):
+ * rgba_out may be NULL to query the size */
+int hikari_decode_png(const uint8_t* bytes, size_t size, uint8_t* rgba_out, uint32_t* width, uint32_t* height);
+/* Mesh::from(shape::*) of bevy 0.9 added as a mesh (returns its id; 0xFFFFFFFF = unknown kind).  params: PLANE {size};
+ * UV_SPHERE {radius, sectors, stacks}; BOX {x_length, y_length, z_length} (shape::Cube{size} = BOX {size, size, size}). */
+enum { HIKARI_SHAPE_PLANE = 0, HIKARI_SHAPE_UV_SPHERE = 1, HIKARI_SHAPE_BOX = 2 };
+uint32_t hikari_world_add_shape(hikari_world* w, uint32_t kind, const float* params);
+
 hikari_plugin* hikari_plugin_create(void);
 void hikari_plugin_destroy(hikari_plugin* p);
 int hikari_plugin_build(hikari_plugin* p, int cuda_device, uint32_t width, uint32_t height, uint32_t row_begin,

@@ -20,7 +20,7 @@ ASAN = bool(os.environ.get("HK_EMU_ASAN"))      # AddressSanitizer build: a memc
 GEN, OUT = os.path.join(HERE, "_gen"), os.path.join(HERE, "_build_asan" if ASAN else "_build")
 LIB = os.path.join(OUT, "libhikari_emu.so")
 CU = ["context.cu", "kernels_light.cu", "kernels_pool.cu", "kernels_spatial.cu", "kernels_post.cu", "kernels_upscale.cu", "kernels_scene.cu"]
-CPP = ["hikari.cpp", "hikari_capi.cpp", "hikari_plugin.cpp", "hikari_plugin_capi.cpp"]
+CPP = ["hikari.cpp", "hikari_capi.cpp", "gltf_ingest.cpp", "hikari_plugin.cpp", "hikari_plugin_capi.cpp"]
 CXX = os.environ.get("HK_CXX", "/usr/bin/g++")
 FLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-std=c++17", "-w",
          "-I" + os.path.join(HERE, "include"), "-I" + SRC, "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + \
@@ -95,7 +95,7 @@ def build(force=False):
         o = os.path.join(OUT, f + ".o")
         subprocess.run([CXX] + FLAGS + ["-c", os.path.join(HOST, f), "-o", o], check=True)
         objs.append(o)
-    subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs + (["-fsanitize=address"] if ASAN else []), check=True)
+    subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs + (["-fsanitize=address"] if ASAN else []) + ["-lz"], check=True)
     open(stamp, "w").write(wanted)
     print(f"emulator: {launches} launch sites converted -> {LIB}")
     return LIB
