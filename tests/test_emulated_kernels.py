@@ -15,7 +15,7 @@ from tests.conftest import ROOT
 
 FILES = ["tests/test_gpu_parity.py", "tests/test_gpu_variants.py", "tests/test_gpu_upscale.py", "tests/test_gpu_dynamic.py",
          "tests/test_gpu_frame_assembly.py", "tests/test_gpu_zz_fsr.py", "tests/test_gpu_zz_examples.py", "tests/test_gpu_zz_halo.py",
-         "tests/test_gpu_wide_traversal.py", "tests/test_gpu_scene_update.py"]
+         "tests/test_gpu_wide_traversal.py", "tests/test_gpu_scene_update.py", "tests/test_gpu_wgsl_golden.py"]
 
 
 @pytest.mark.parametrize("order", ["forward", "reverse"])

@@ -1,0 +1,18 @@
+"""The CUDA path held DIRECTLY against what the reference's own WGSL computes (tests/golden/wgsl_*.npz, see tests/test_wgsl_reference.py
+and tools/make_wgsl_golden.py): every buffer and texture of every frame of the shared sequences, bit for bit, through the C ABI on the
+exact flavour of the library — no oracle in between."""
+import pytest
+
+from tests import wgsl_cases as WC
+from tests.test_wgsl_reference import run_and_compare
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", sorted(WC.CASES))
+def test_cuda_path_reproduces_what_the_reference_shaders_compute(case):
+    def make(bench):
+        dev = bench.device()
+        dev.set_keep_intermediates(True)
+        return dev
+    run_and_compare(case, make, lambda dev, b: dev.update_instances(b.world))

@@ -1,0 +1,63 @@
+"""Sequences shared by tools/make_wgsl_golden.py (which runs them through the reference's own WGSL, translated and executed on the CPU —
+oracle/wgsl/) and by the tests that hold the oracle and the CUDA path against what that produced (tests/golden/wgsl_*.npz).
+
+Each case: a scene, a benchmark configuration's settings, a frame size, a number of frames from zeroed temporal state, a camera
+translation per frame and optionally animated instances.  Per frame and per plane the fixture stores a SHA-256 of the plane's bytes in
+the reference's texture / buffer format (the compared implementations must be bit-identical), plus the last frame's tone-mapped image
+in full for diagnostics."""
+import hashlib
+
+import numpy as np
+
+from bevy_hikari_b200 import layout as L
+
+CASES = {
+    # name: (scene, config, (W, H), frames, camera step per frame, animation or None, settings overrides)
+    "cornell_cfg1": ("cornell", "cornell_256", (64, 64), 8, (0.0, 0.0, 0.0), None, {}),                 # BASELINE configs[0] settings
+    "cornell_cfg2_moving": ("cornell", "cornell_1080p", (80, 48), 9, (0.03, 0.01, -0.02), None, {}),     # configs[1] settings, moving camera
+    "cornell_animated": ("cornell", "cornell_1080p", (72, 48), 7, (0.0, 0.0, 0.0), "cornell", {}),       # instances move every frame
+    "city_cfg4_moving": ("city", "city_4k", (80, 45), 7, (0.05, 0.0, -0.04), None, {}),                  # textures, sun, 13 textures
+    "city_cfg5": ("city", "city_8k", (64, 36), 6, (0.0, 0.0, 0.0), None, {}),                            # 4 bounces, both spatial reuses
+    "simple_two_lights": ("simple", "cornell_1080p", (72, 48), 7, (0.02, 0.0, 0.0), None, {}),           # two emissives: light BVH + alias
+    "samplers": ("samplers", "cornell_1080p", (64, 40), 6, (0.0, 0.0, 0.0), None, {}),                   # wrap modes, nearest / bilinear, textured light
+    "no_denoise_one_bounce": ("simple", "cornell_256", (56, 40), 6, (0.0, 0.02, 0.0), None, {}),
+}
+
+PLANES = ([("albedo", L.OUT_ALBEDO)] + [(f"render{i}", L.OUT_RENDER_DIRECT + i) for i in range(3)] +
+          [(f"variance{i}", L.OUT_VARIANCE_DIRECT + i) for i in range(3)] + [(f"reservoir{i}", L.OUT_RESERVOIR_0 + i) for i in range(10)] +
+          [("tone_mapped", L.OUT_TONE_MAPPED)])
+DENOISED = [(f"denoised{i}", L.OUT_DENOISED_DIRECT + i) for i in range(3)]
+GBUFFER = [L.OUT_GBUFFER_POSITION, L.OUT_GBUFFER_NORMAL, L.OUT_GBUFFER_DEPTH_GRADIENT, L.OUT_GBUFFER_INSTANCE_MATERIAL, L.OUT_GBUFFER_VELOCITY_UV]
+
+
+def digest(array):
+    return hashlib.sha256(np.ascontiguousarray(array).tobytes()).hexdigest()
+
+
+def make_bench(case):
+    from tests.conftest import Bench
+    scene, config, (w, h), frames, step, animation, overrides = CASES[case]
+    return Bench(scene, w, h, config=config, **overrides)
+
+
+def frame_inputs(bench, case, frame):
+    step = CASES[case][4]
+    return bench.moving_inputs(frame, step) if any(step) else bench.inputs(frame)
+
+
+def animate(bench, case, frame):
+    """moves the case's animated instances to their pose of `frame` (host mirror: transforms, previous transforms, prepare_instances);
+    returns True when the scene changed"""
+    if CASES[case][5] is None:
+        return False
+    from tests.conftest import cornell_animation
+    if not hasattr(bench, "_wgsl_anim"):
+        bench._wgsl_anim = cornell_animation(bench)
+    bench._wgsl_anim.step(frame)
+    return True
+
+
+def planes_of(case, bench):
+    denoise = bool(bench.settings.denoise)
+    signals = 3 if bench.settings.indirect_bounces else 2
+    return PLANES + (DENOISED[:signals] if denoise else [])
