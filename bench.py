@@ -802,7 +802,7 @@ def cpu_baseline_sample(config, seconds_budget):
     return {"value": round(rays / t_total / 1e6, 4), "unit": "Mrays/s", "cores": orc.threads, "kind": "port",
             "ms_per_frame_sample": round(t_total / frames * 1e3, 2),
             "sample": f"{frames} frames of {config} at {w}x{h} (1/16 of the pixels, same scene/settings/frame sequence), "
-                      f"oracle = C++/OpenMP restatement of the reference WGSL; the reference (Rust+wgpu) cannot be built offline"}
+                      f"oracle = C++/OpenMP restatement of the reference WGSL, bit-identical to the reference's shader text executed on the CPU (tests/golden/wgsl_*.npz); the reference itself (Rust+wgpu) cannot be built offline"}
 
 
 def reference_sample_size(config, W_, K, budget_s=150.0):

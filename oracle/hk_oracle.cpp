@@ -5,12 +5,19 @@
 // format, exactly as LightNode::run (src/light.rs:590-702) and PostProcessNode::run (src/post_process.rs:1140-1234)
 // dispatch it.  Every function cites the WGSL it follows (paths relative to /root/reference/src/shaders).
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path and
-// cannot be built here (no rustc / wgpu / Vulkan), so this restatement is anchored on the WGSL source alone.
-// What stands in for a pin: every pass below is held against a SECOND restatement written independently from the WGSL
-// (whole-image numpy programs with brute-force float64 ray queries, tests/test_*_numpy.py; agreement table in DESIGN.md 2),
-// plus physical anchors (tests/test_estimator.py) — evidence that this file reads the WGSL the way a second reader does,
-// not evidence about what a wgpu driver computes.
+// PARITY: the compute passes below are PINNED against the reference's own shader text; the host-side scene build and the raster
+// prepass are not.  The reference ships no tests, golden vectors or fixtures for this path and cannot be built
+// here (no rustc / wgpu / Vulkan) — but its hot path IS text: oracle/wgsl/ translates src/shaders/{light,denoise,tone_mapping}.wgsl
+// (read in place under /root/reference) to C++, compiles one library per pipeline specialisation into oracle/_ref/wgsl/ and drives
+// them with the bind-group wiring of src/light.rs / src/post_process.rs.  What that execution of the reference's text computes —
+// every reservoir buffer, radiance / variance plane, albedo, denoised plane and tone-mapped image of every frame of eight
+// free-running sequences — is committed as fixtures (tests/golden/wgsl_*.npz, tools/make_wgsl_golden.py), and this file reproduces
+// every one of them BIT FOR BIT (tests/test_wgsl_reference.py; the CUDA path likewise, tests/test_gpu_wgsl_golden.py).
+// Still a restatement, i.e. parity unpinned there: the G-buffer (the reference rasterises it; the translated passes take it as
+// input), the BVH / alias-table build of the pinned crate bvh 0.7.1 and glam (host/hikari.cpp, restated from the published
+// sources), and the ~60 lines of bevy_pbr 0.9.1 the shaders import (oracle/wgsl/prelude/).  For those the
+// evidence remains a second, independent restatement per pass (tests/test_*_numpy.py; table in DESIGN.md 2) and the physical
+// anchors of tests/test_estimator.py.
 // Deviations that are forced and documented:
 //   * the G-buffer is ray-cast (hko_prepass) instead of rasterised (prepass.wgsl:40-100) — same five planes, same
 //     formats, oracle-defined coverage;
