@@ -132,10 +132,13 @@ class WgslReference:
 
     LIGHT_VARIANTS = {"base": [], "sun": ["RENDER_EMISSIVE"], "emissive": ["EMISSIVE_LIT"], "multi": ["MULTIPLE_BOUNCES"]}
 
-    def __init__(self, scene_buffers, textures, noise, width, height):
+    def __init__(self, scene_buffers, textures, noise, width, height, upscale_ratio=1.0):
         """scene_buffers: dict of the nine storage buffers as numpy records (plugin.World.buffers()); textures: list of
         (rgba8 HxWx4, address_mode_u, address_mode_v, filter_linear, srgb); noise: 16 x 64 x 64 x 4 uint8"""
         self.w, self.h = width, height
+        # scaled_size = (ratio.recip() * size).ceil(), light.rs:321-322 (f32 arithmetic)
+        scale = np.float32(1.0) / np.float32(upscale_ratio)
+        self.rw, self.rh = int(np.ceil(scale * np.float32(width))), int(np.ceil(scale * np.float32(height)))
         self.scene = {k: np.ascontiguousarray(v) for k, v in scene_buffers.items()}
         self.textures = textures
         self.noise = np.ascontiguousarray(noise, np.uint8).reshape(16, 64, 64, 4)
@@ -145,15 +148,16 @@ class WgslReference:
         self.denoise = {(lvl, ff): Module("denoise", [f"DENOISE_LEVEL_{lvl}"] + (["FIREFLY_FILTERING"] if ff else []))
                         for lvl in range(4) for ff in (False, True)}
         self.tone = Module("tone_mapping", [])
-        n = width * height
+        n = width * height                                                   # reservoirs: size.x * size.y records, light.rs:343
+        rw, rh = self.rw, self.rh
         self.reservoir = [np.zeros((n, 16), np.uint32) for _ in range(10)]   # GpuPackedReservoir::default(), light.rs:347-356
-        self.render = [np.zeros((height, width, 4), np.uint16) for _ in range(3)]
-        self.variance = [np.zeros((height, width), np.float32) for _ in range(3)]
-        self.albedo = np.zeros((height, width, 4), np.uint16)
-        self.internal = [np.zeros((height, width, 4), np.uint16) for _ in range(4)]
-        self.internal_variance = np.zeros((height, width), np.float32)
-        self.denoise_render = [np.zeros((height, width, 4), np.uint16) for _ in range(3)]
-        self.tone_mapped = np.zeros((height, width, 4), np.uint16)
+        self.render = [np.zeros((rh, rw, 4), np.uint16) for _ in range(3)]   # scaled_size, light.rs:366-367
+        self.variance = [np.zeros((rh, rw), np.float32) for _ in range(3)]
+        self.albedo = np.zeros((height, width, 4), np.uint16)                # full size, light.rs:368
+        self.internal = [np.zeros((rh, rw, 4), np.uint16) for _ in range(4)]
+        self.internal_variance = np.zeros((rh, rw), np.float32)
+        self.denoise_render = [np.zeros((rh, rw, 4), np.uint16) for _ in range(3)]
+        self.tone_mapped = np.zeros((rh, rw, 4), np.uint16)
         self.gbuffer = None
         self.dummy = np.zeros((1, 1, 4), np.uint8)
 
@@ -220,17 +224,17 @@ class WgslReference:
     def direct_lit(self, inputs, emissive):
         m = self.light["emissive" if emissive else "sun"]
         self._light_groups(m, inputs, 1 if emissive else 0)
-        m.run("direct_lit", self.w, self.h)
+        m.run("direct_lit", self.rw, self.rh)
 
     def indirect_lit_ambient(self, inputs):
         m = self.light["multi" if inputs.frame.indirect_bounces >= 2 else "base"]      # light.rs:668-671
         self._light_groups(m, inputs, 2)
-        m.run("indirect_lit_ambient", self.w, self.h)
+        m.run("indirect_lit_ambient", self.rw, self.rh)
 
     def spatial_reuse(self, inputs, emissive):
         m = self.light["emissive" if emissive else "base"]
         self._light_groups(m, inputs, 1 if emissive else 2)
-        m.run("spatial_reuse", self.w, self.h)
+        m.run("spatial_reuse", self.rw, self.rh)
 
     def light_node(self, inputs):
         self.full_screen_albedo(inputs)
@@ -260,7 +264,7 @@ class WgslReference:
             m.texture("variance_texture", self.variance[signal], R32F)
             m.texture("render_texture", self.render[signal], RGBA16F)
             m.texture("output_texture", self.denoise_render[signal], RGBA16F)
-            m.run("demodulation" if k == 0 else "denoise", self.w, self.h)
+            m.run("demodulation" if k == 0 else "denoise", self.rw, self.rh)
 
     def tone_mapping(self, inputs, denoise, signals=3):
         m = self.tone
@@ -272,7 +276,7 @@ class WgslReference:
         m.texture("emissive_render_texture", src[1], RGBA16F)
         m.texture("indirect_render_texture", src[2] if signals == 3 else fallback, RGBA16F)       # post_process.rs:948-953
         m.texture("output_texture", self.tone_mapped, RGBA16F)
-        m.run("tone_mapping", self.w, self.h)
+        m.run("tone_mapping", self.rw, self.rh)
 
     def post_process_node(self, inputs, denoise):
         signals = 3 if inputs.frame.indirect_bounces else 2

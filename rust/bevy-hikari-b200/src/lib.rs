@@ -156,6 +156,26 @@ pub fn upload_scene(ctx: &HikariB200Context, scene: &ffi::hk_scene_desc, instanc
     }
 }
 
+/// Frames on which only `GlobalTransform`s changed (the common case of an animated scene): the per-frame half of the scene —
+/// instance AABBs and matrices, TLAS, emissives, emissive BVH — is rebuilt ON THE DEVICE from one matrix per instance
+/// (include/hikari_b200.h: hk_scene_update_transforms; replaces the CPU work of src/mesh_material/instance.rs:352-437).
+/// `models` / `previous_models`: `GlobalTransform::compute_matrix().to_cols_array()` of every instance in instance order and its
+/// `GlobalTransformQueue[1]`; `mesh_aabbs`: `[center.x, center.y, center.z, half.x, half.y, half.z]` of each instance's mesh `Aabb`.
+/// The caller keeps the reference's conditions for the full path (instance set changed, or an emissive's scale left its cached alias
+/// table's +-0.01 range, instance.rs:385-397) and calls `upload_scene(.., instances_only = true)` then.
+pub fn update_transforms(ctx: &HikariB200Context, models: &[[f32; 16]], previous_models: Option<&[[f32; 16]]>, mesh_aabbs: &[[f32; 6]]) -> bool {
+    debug_assert!(models.len() == mesh_aabbs.len() && previous_models.map_or(true, |p| p.len() == models.len()));
+    let rc = unsafe {
+        ffi::hk_scene_update_transforms(ctx.0, models.as_ptr() as *const f32, previous_models.map_or(std::ptr::null(), |p| p.as_ptr() as *const f32),
+                                        mesh_aabbs.as_ptr() as *const f32, models.len() as u32)
+    };
+    match rc {
+        ffi::HK_OK => true,
+        ffi::HK_ERR_UNSUPPORTED => false,      // a TLAS that is not in bvh 0.7.1's layout: keep the host path
+        _ => { error!("hk_scene_update_transforms: {}", last_error(ctx.0)); false }
+    }
+}
+
 /// The image the overlay pass presents (src/overlay.rs:226-231): a CUDA device pointer, to be imported into the swap-chain API
 /// through external memory (with `cudarc`: `CudaSlice::from_raw`).
 pub fn presented_image(ctx: &HikariB200Context, settings: &HikariSettings) -> Option<(*mut std::ffi::c_void, usize)> {

@@ -4,7 +4,13 @@ oracle/wgsl/) and by the tests that hold the oracle and the CUDA path against wh
 Each case: a scene, a benchmark configuration's settings, a frame size, a number of frames from zeroed temporal state, a camera
 translation per frame and optionally animated instances.  Per frame and per plane the fixture stores a SHA-256 of the plane's bytes in
 the reference's texture / buffer format (the compared implementations must be bit-identical), plus the last frame's tone-mapped image
-in full for diagnostics."""
+in full for diagnostics.
+
+Render widths are multiples of 8 here, as they are in every BASELINE configuration (1920, 3840, 7680 and their halves).  For other widths
+the reference's shaders have a second data race that only a GPU can "resolve": the dispatch covers ceil(w / 8) * 8 columns, the extra
+invocations read a zero G-buffer (robust access), take the background branch and STORE a reservoir at index x + w * y — which, for
+x >= w, is a pixel at the start of the next row (light.wgsl:1057-1066 with the linear index of :1063; found by executing the shader
+text at 60 x 34).  The oracle and the CUDA path run no out-of-range invocations; DESIGN.md 2 lists this with the other deviations."""
 import hashlib
 
 import numpy as np
@@ -21,6 +27,9 @@ CASES = {
     "simple_two_lights": ("simple", "cornell_1080p", (72, 48), 7, (0.02, 0.0, 0.0), None, {}),           # two emissives: light BVH + alias
     "samplers": ("samplers", "cornell_1080p", (64, 40), 6, (0.0, 0.0, 0.0), None, {}),                   # wrap modes, nearest / bilinear, textured light
     "no_denoise_one_bounce": ("simple", "cornell_256", (56, 40), 6, (0.0, 0.02, 0.0), None, {}),
+    # scaled rendering (Upscale ratio > 1: light / denoise planes at ceil(size / ratio), jittered_deferred_uv / _coords look-ups)
+    "cornell_ratio2": ("cornell", "cornell_1080p", (96, 64), 7, (0.02, 0.0, -0.01), None, {"upscale_ratio": 2.0}),
+    "city_ratio1p5": ("city", "city_4k", (96, 54), 6, (0.0, 0.0, 0.0), None, {"upscale_ratio": 1.5}),
 }
 
 PLANES = ([("albedo", L.OUT_ALBEDO)] + [(f"render{i}", L.OUT_RENDER_DIRECT + i) for i in range(3)] +

@@ -29,7 +29,7 @@ def reference_planes(ref, bench):
     for i in range(3):
         out[f"render{i}"], out[f"variance{i}"], out[f"denoised{i}"] = ref.render[i], ref.variance[i], ref.denoise_render[i]
     for i in range(10):
-        out[f"reservoir{i}"] = ref.reservoir[i]
+        out[f"reservoir{i}"] = ref.reservoir[i][:ref.rw * ref.rh]      # the records the passes index (render size)
     return out
 
 
@@ -37,7 +37,7 @@ def run_case(case):
     bench = WC.make_bench(case)
     w, h = bench.width, bench.height
     textures = [(np.ascontiguousarray(t["rgba"]), t["address_mode_u"], t["address_mode_v"], t["filter_linear"], t["srgb"]) for t in bench.scene.textures]
-    ref = R.WgslReference(bench.world.buffers(), textures, plugin.load_noise(), w, h)
+    ref = R.WgslReference(bench.world.buffers(), textures, plugin.load_noise(), w, h, bench.settings.upscale_ratio)
     orc = bench.oracle()
     frames = WC.CASES[case][3]
     digests = {}
