@@ -822,10 +822,14 @@ int hk_scene_update_transforms(hk_context* ctx, const float* models, const float
         HK_CUDA(cudaMallocHost(&pin.p, stage_bytes + stage_bytes / 2));
         pin.cap = stage_bytes + stage_bytes / 2;
     }
+    // staging layout: models | previous models (optional) | mesh AABBs — the two matrix arrays are read as float4 and must stay
+    // 16-byte aligned for every n (24 n bytes of AABBs in between misaligned `previous` for odd n: a misaligned-address fault on
+    // the device that the host emulation did not see)
+    const size_t aoff = mbytes * (previous_models ? 2u : 1u);
     uint8_t* hp = static_cast<uint8_t*>(pin.p);
     memcpy(hp, models, mbytes);
-    memcpy(hp + mbytes, mesh_aabbs, abytes);
-    if (previous_models) memcpy(hp + mbytes + abytes, previous_models, mbytes);
+    if (previous_models) memcpy(hp + mbytes, previous_models, mbytes);
+    memcpy(hp + aoff, mesh_aabbs, abytes);
     const uint32_t nmax = n > ne ? n : ne;
     HK_CUDA(ensure_buf(ctx->ibuf[14], stage_bytes));
     HK_CUDA(ensure_buf(ctx->ibuf[5], mbytes));
@@ -841,8 +845,8 @@ int hk_scene_update_transforms(hk_context* ctx, const float* models, const float
     hk_emissive* emissives = static_cast<hk_emissive*>(ctx->ibuf[4].p);
     float4* box_lo = static_cast<float4*>(ctx->ibuf[17].p);
     float4* box_hi = static_cast<float4*>(ctx->ibuf[18].p);
-    hk_launch_scene_instances(n, reinterpret_cast<const float4*>(dp), previous_models ? reinterpret_cast<const float4*>(dp + mbytes + abytes) : nullptr,
-                              reinterpret_cast<const float*>(dp + mbytes), instances, static_cast<hk_instance_trav*>(ctx->ibuf[8].p),
+    hk_launch_scene_instances(n, reinterpret_cast<const float4*>(dp), previous_models ? reinterpret_cast<const float4*>(dp + mbytes) : nullptr,
+                              reinterpret_cast<const float*>(dp + aoff), instances, static_cast<hk_instance_trav*>(ctx->ibuf[8].p),
                               static_cast<float4*>(ctx->ibuf[5].p), static_cast<uint32_t*>(ctx->ibuf[6].p), box_lo, box_hi, ctx->stream);
     hk_launch_build_flat_bvh(n, box_lo, box_hi, ctx->ibuf[19].p, static_cast<hk_node*>(ctx->ibuf[2].p),
                              reinterpret_cast<uint8_t*>(instances) + offsetof(hk_instance, node_index), (uint32_t)sizeof(hk_instance), ctx->stream);

@@ -17,7 +17,10 @@ SRC = os.path.join(ROOT, "bevy_hikari_b200", "csrc")
 HOST = os.path.join(ROOT, "bevy_hikari_b200", "host")
 ASAN = bool(os.environ.get("HK_EMU_ASAN"))      # AddressSanitizer build: a memcheck for the kernels' indexing (run python with
 #                                                  LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)
-GEN, OUT = os.path.join(HERE, "_gen"), os.path.join(HERE, "_build_asan" if ASAN else "_build")
+ALIGN = bool(os.environ.get("HK_EMU_ALIGN"))    # UBSan alignment build: float4 / uint4 / float2 ... are alignas'd as on the device and cudaMalloc
+#                                                  returns 256-byte aligned blocks, so a vector access the GPU would fault on ("misaligned
+#                                                  address", sticky) aborts here too — the host's own unaligned moves never notice
+GEN, OUT = os.path.join(HERE, "_gen"), os.path.join(HERE, "_build_asan" if ASAN else ("_build_align" if ALIGN else "_build"))
 LIB = os.path.join(OUT, "libhikari_emu.so")
 CU = ["context.cu", "kernels_light.cu", "kernels_pool.cu", "kernels_spatial.cu", "kernels_post.cu", "kernels_upscale.cu", "kernels_scene.cu"]
 CPP = ["hikari.cpp", "hikari_capi.cpp", "gltf_ingest.cpp", "hikari_plugin.cpp", "hikari_plugin_capi.cpp"]
@@ -27,6 +30,8 @@ FLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fop
         os.environ.get("HK_EMU_EXTRA", "").split()      # e.g. -DHK_DENOISE_BRANCHFREE=1: validate a tuning variant's logic
 if ASAN:
     FLAGS = [f for f in FLAGS if f != "-O2"] + ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
+if ALIGN:
+    FLAGS = [f for f in FLAGS if f != "-O2"] + ["-O1", "-g", "-fsanitize=alignment", "-fno-sanitize-recover=alignment"]
 
 LAUNCH = re.compile(r"([A-Za-z_][A-Za-z_0-9]*(?:<[^<>;]*>)?)<<<([^;]*?)>>>\(([^;]*)\);")
 COOPERATIVE = re.compile(r"^kc_")     # kernels with shared memory / barriers / warp collectives: threads of a block run as fibers
@@ -95,7 +100,7 @@ def build(force=False):
         o = os.path.join(OUT, f + ".o")
         subprocess.run([CXX] + FLAGS + ["-c", os.path.join(HOST, f), "-o", o], check=True)
         objs.append(o)
-    subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs + (["-fsanitize=address"] if ASAN else []) + ["-lz"], check=True)
+    subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs + (["-fsanitize=address"] if ASAN else []) + (["-fsanitize=alignment", "-static-libubsan"] if ALIGN else []) + ["-lz"], check=True)
     open(stamp, "w").write(wanted)
     print(f"emulator: {launches} launch sites converted -> {LIB}")
     return LIB
