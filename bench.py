@@ -662,7 +662,7 @@ def run_ours(args):
     traffic = None   # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this workload
     try:
         if world_size == 1:
-            with open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")) as f:
                 traffic = json.load(f).get(args.config, {}).get(dom)
     except Exception:
         traffic = None
