@@ -234,6 +234,8 @@ class Translator:
                 raise SystemExit("ptr type inside an expression")
             elif kind == "id":
                 out.append(self.ident(v))
+            elif v == "," and k + 1 < len(toks) and toks[k + 1][1] == ")":
+                pass                                  # WGSL allows a trailing comma in argument lists (smaa.wgsl:231-234)
             else:
                 out.append(v)
             k += 1

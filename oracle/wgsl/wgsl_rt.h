@@ -328,6 +328,20 @@ inline vec4<f32> textureSampleLevel(const wgsl_texture& t, const sampler& s, con
     return top * (1.0f - ay) + bottom * ay;
 }
 
+// textureGather(component, t, s, uv): the four texels a bilinear sample at uv would blend, in WGSL's order
+// x = (u_min, v_max), y = (u_max, v_max), z = (u_max, v_min), w = (u_min, v_min); footprint as textureSampleLevel's linear branch
+inline vec4<f32> textureGather(i32 component, const wgsl_texture& t, const sampler& s, const vec2<f32>& uv) {
+    if (!t.p || t.w <= 0 || t.h <= 0) return vec4<f32>(0.0f);
+    const f32 px = uv.x * (f32)t.w - 0.5f, py = uv.y * (f32)t.h - 0.5f;
+    const int x0 = (int)floorf(px), y0 = (int)floorf(py);
+    const int ix0 = wgsl_wrap(x0, t.w, s.mode_u), ix1 = wgsl_wrap(x0 + 1, t.w, s.mode_u);
+    const int iy0 = wgsl_wrap(y0, t.h, s.mode_v), iy1 = wgsl_wrap(y0 + 1, t.h, s.mode_v);
+    const vec4<f32> a = t.load(ix0, iy1), b = t.load(ix1, iy1), c = t.load(ix1, iy0), d = t.load(ix0, iy0);
+    const f32 av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
+    const int k = component & 3;
+    return vec4<f32>(av[k], bv[k], cv[k], dv[k]);
+}
+
 // ------------------------------------------------------------------------------------------------ dispatch
 struct wgsl_ids { vec3<u32> global, local, group, num_groups; u32 local_index = 0; };
 inline wgsl_ids& wgsl_tls() { static thread_local wgsl_ids ids; return ids; }
