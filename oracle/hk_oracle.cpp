@@ -7,7 +7,7 @@
 //
 // PARITY: the compute passes below are PINNED against the reference's own shader text; the host-side scene build and the raster
 // prepass are not.  The reference ships no tests, golden vectors or fixtures for this path and cannot be built
-// here (no rustc / wgpu / Vulkan) — but its hot path IS text: oracle/wgsl/ translates src/shaders/{light,denoise,tone_mapping}.wgsl
+// here (no rustc / wgpu / Vulkan) — but its hot path IS text: oracle/wgsl/ translates src/shaders/{light,denoise,tone_mapping,smaa,taa}.wgsl
 // (read in place under /root/reference) to C++, compiles one library per pipeline specialisation into oracle/_ref/wgsl/ and drives
 // them with the bind-group wiring of src/light.rs / src/post_process.rs.  What that execution of the reference's text computes —
 // every reservoir buffer, radiance / variance plane, albedo, denoised plane and tone-mapped image of every frame of eight

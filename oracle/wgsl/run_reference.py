@@ -6,7 +6,8 @@ reference's render-graph nodes wire their bind groups:
   queue_light_bind_groups src/light.rs:463-555     reservoir buffers (temporal, spatial) = (0,4) sun, (2,4) emissive, (6,8) indirect,
                                                    `current` = frame counter % 2; render / variance texture per pass
   PostProcessNode::run    src/post_process.rs:1140-1234 + bind groups :840-1000: demodulation + four denoise levels per signal
-                                                   (firefly filtering for the emissive and indirect signals only), tone mapping
+                                                   (firefly filtering for the emissive and indirect signals only), tone mapping;
+                                                   :1236-1277 + bind groups :983-1036: smaa_tu4x, smaa_tu4x_extrapolate, taa_jasmine
 
 Only in this container (it needs /root/reference and g++); the libraries it builds live in oracle/_ref/wgsl/ (git-ignored).  The
 G-buffer is an INPUT here: the reference rasterises it (src/prepass.rs + prepass.wgsl, a render pipeline, not translated), so the
@@ -148,6 +149,8 @@ class WgslReference:
         self.denoise = {(lvl, ff): Module("denoise", [f"DENOISE_LEVEL_{lvl}"] + (["FIREFLY_FILTERING"] if ff else []))
                         for lvl in range(4) for ff in (False, True)}
         self.tone = Module("tone_mapping", [])
+        self.smaa = self.taa = None                                          # built on first use (smaa.wgsl / taa.wgsl)
+        self.upscale_ratio = upscale_ratio
         n = width * height                                                   # reservoirs: size.x * size.y records, light.rs:343
         rw, rh = self.rw, self.rh
         self.reservoir = [np.zeros((n, 16), np.uint32) for _ in range(10)]   # GpuPackedReservoir::default(), light.rs:347-356
@@ -157,12 +160,26 @@ class WgslReference:
         self.internal = [np.zeros((rh, rw, 4), np.uint16) for _ in range(4)]
         self.internal_variance = np.zeros((rh, rw), np.float32)
         self.denoise_render = [np.zeros((rh, rw, 4), np.uint16) for _ in range(3)]
-        self.tone_mapped = np.zeros((rh, rw, 4), np.uint16)
+        self.tone_mapping_output = [np.zeros((rh, rw, 4), np.uint16) for _ in range(2)]   # post_process.rs:713, [head] is written
+        self.head = 0                                                        # PostProcessTextures::head = counter % 2 of the last frame run
+        self.upscale_output = None                                           # post_process.rs:715-724 / :726-731, allocated by upscale_node
+        self.taa_output = None
         self.gbuffer = None
+        self.previous_gbuffer = None
         self.dummy = np.zeros((1, 1, 4), np.uint8)
 
+    @property
+    def tone_mapped(self):
+        return self.tone_mapping_output[self.head]
+
     def set_gbuffer(self, position, normal, depth_gradient, instance_material, velocity_uv):
-        """the five G-buffer targets of the prepass (src/prepass.rs:43-47 formats), deferred size"""
+        """the five G-buffer targets of the prepass (src/prepass.rs:43-47 formats), deferred size; what was current becomes the
+        previous_* textures of deferred_bindings.wgsl (prepass.rs:312-321 swaps the two sets every frame; cleared at creation)"""
+        if self.gbuffer is not None:
+            self.previous_gbuffer = self.gbuffer
+        else:
+            self.previous_gbuffer = [np.zeros_like(np.ascontiguousarray(position, np.float32)), None, None, None,
+                                     np.zeros_like(np.ascontiguousarray(velocity_uv, np.float32))]
         self.gbuffer = [np.ascontiguousarray(position, np.float32), np.ascontiguousarray(normal), np.ascontiguousarray(depth_gradient, np.float32),
                         np.ascontiguousarray(instance_material, np.float32), np.ascontiguousarray(velocity_uv, np.float32)]
 
@@ -178,6 +195,9 @@ class WgslReference:
         m.texture("depth_gradient_texture", g[2], RG32F)
         m.texture("instance_material_texture", g[3], RG32F)
         m.texture("velocity_uv_texture", g[4], RGBA32F)
+        p = self.previous_gbuffer
+        m.texture("previous_position_texture", p[0], RGBA32F)                   # read by smaa.wgsl / taa.wgsl only
+        m.texture("previous_velocity_uv_texture", p[4], RGBA32F)
 
     def _light_groups(self, m, inputs, signal):
         m.keep = []
@@ -275,8 +295,44 @@ class WgslReference:
         m.texture("direct_render_texture", src[0], RGBA16F)
         m.texture("emissive_render_texture", src[1], RGBA16F)
         m.texture("indirect_render_texture", src[2] if signals == 3 else fallback, RGBA16F)       # post_process.rs:948-953
-        m.texture("output_texture", self.tone_mapped, RGBA16F)
+        self.head = inputs.frame.number % 2                                                       # post_process.rs:735
+        m.texture("output_texture", self.tone_mapping_output[self.head], RGBA16F)                 # :975-981
         m.run("tone_mapping", self.rw, self.rh)
+
+    # ------------------------------------------------------------------------------------------------ temporal upscalers
+    def _scaled(self, scale):
+        """create_texture(format, scale): (size as f32 * scale).ceil(), post_process.rs:663-667"""
+        return int(np.ceil(np.float32(self.w) * np.float32(scale))), int(np.ceil(np.float32(self.h) * np.float32(scale)))
+
+    def upscale_node(self, inputs, smaa, taa):
+        """post_process.rs:1236-1277: smaa_tu4x + smaa_tu4x_extrapolate over scaled_size, then taa_jasmine over the (doubled) size"""
+        scale = np.float32(1.0) / np.float32(self.upscale_ratio)                                  # settings.upscale.ratio().recip(), :711
+        current, previous = self.head, 1 - self.head
+        if smaa:
+            scale = np.float32(scale * np.float32(2.0))                                           # :717
+            ow, oh = self._scaled(scale)
+            if self.smaa is None:
+                self.smaa = Module("smaa", [])
+                self.upscale_output = np.zeros((oh, ow, 4), np.uint16)
+            m = self.smaa
+            self._post_groups(m, inputs)
+            m.texture("previous_render_texture", self.tone_mapping_output[previous], RGBA16F)     # :983-999
+            m.texture("render_texture", self.tone_mapping_output[current], RGBA16F)
+            m.texture("output_texture", self.upscale_output, RGBA16F)                             # :1001-1008
+            m.run("smaa_tu4x", self.rw, self.rh)                                                  # :1240-1245
+            m.run("smaa_tu4x_extrapolate", self.rw, self.rh)                                      # :1247-1255
+        if taa:
+            tw, th = self._scaled(scale)                                                          # taa_output at the (doubled) scale, :726-729
+            if self.taa is None:
+                self.taa = Module("taa", [])
+                self.taa_output = [np.zeros((th, tw, 4), np.uint16) for _ in range(2)]
+            m = self.taa
+            self._post_groups(m, inputs)
+            m.texture("previous_render_texture", self.taa_output[previous], RGBA16F)              # :1014-1027
+            m.texture("render_texture", self.upscale_output if smaa else self.tone_mapping_output[current], RGBA16F)   # :1010-1013
+            m.texture("output_texture", self.taa_output[current], RGBA16F)                        # :1028-1035
+            sw, sh = (2 * self.rw, 2 * self.rh) if smaa else (self.rw, self.rh)                   # scaled_size *= 2, :1258
+            m.run("taa_jasmine", sw, sh)                                                          # :1271-1276
 
     def post_process_node(self, inputs, denoise):
         signals = 3 if inputs.frame.indirect_bounces else 2

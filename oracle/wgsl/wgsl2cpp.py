@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE — executes the reference's OWN compute shaders on the CPU, to pin the oracle.
 
-The reference's hot path is WGSL (src/shaders/{light,denoise,tone_mapping}.wgsl); nothing in this container can run WGSL (no naga,
+The reference's hot path is WGSL (src/shaders/{light,denoise,tone_mapping,smaa,taa}.wgsl); nothing in this container can run WGSL (no naga,
 no wgpu, no Vulkan).  This script translates those files — read where they lie under /root/reference, never copied into the repo —
 into C++ that g++ compiles against oracle/wgsl/wgsl_rt.h, one shared library per (file, shader-def set) exactly as the reference
 specialises its pipelines (src/light.rs:134-175, src/post_process.rs:396-500).  The generated sources and libraries go to

@@ -16,6 +16,7 @@ import hashlib
 import numpy as np
 
 from bevy_hikari_b200 import layout as L
+from bevy_hikari_b200 import plugin as _P
 
 CASES = {
     # name: (scene, config, (W, H), frames, camera step per frame, animation or None, settings overrides)
@@ -30,7 +31,18 @@ CASES = {
     # scaled rendering (Upscale ratio > 1: light / denoise planes at ceil(size / ratio), jittered_deferred_uv / _coords look-ups)
     "cornell_ratio2": ("cornell", "cornell_1080p", (96, 64), 7, (0.02, 0.0, -0.01), None, {"upscale_ratio": 2.0}),
     "city_ratio1p5": ("city", "city_4k", (96, 54), 6, (0.0, 0.0, 0.0), None, {"upscale_ratio": 1.5}),
+    # the temporal upscalers after tone mapping (smaa.wgsl: smaa_tu4x + smaa_tu4x_extrapolate, taa.wgsl: taa_jasmine), jittered prepass
+    "cornell_default_upscalers": ("cornell", "cornell_1080p", (96, 64), 9, (0.03, 0.01, -0.02), None,        # HikariSettings::default():
+                                  {"taa": _P.TAA_JASMINE, "upscale_kind": _P.UPSCALE_SMAA_TU4X, "upscale_ratio": 2.0}),   # SMAA_TU_2_0 + Jasmine
+    "cornell_smaa_ratio1_taa": ("cornell", "cornell_1080p", (72, 48), 8, (0.02, 0.0, -0.01), "cornell",
+                                {"taa": _P.TAA_JASMINE, "upscale_kind": _P.UPSCALE_SMAA_TU4X, "upscale_ratio": 1.0}),
+    "city_smaa_only_ratio1p5": ("city", "city_4k", (96, 54), 7, (0.04, 0.0, -0.03), None,
+                                {"taa": _P.TAA_NONE, "upscale_kind": _P.UPSCALE_SMAA_TU4X, "upscale_ratio": 1.5}),
+    "simple_taa_only": ("simple", "cornell_1080p", (80, 48), 8, (0.02, 0.01, 0.0), None,
+                        {"taa": _P.TAA_JASMINE, "upscale_kind": _P.UPSCALE_FSR1, "upscale_ratio": 1.0}),      # TAA on the tone-mapped image
 }
+# cases whose frames run with HikariInputs::temporal_upscalers (the passes of post_process.rs:1236-1277 after tone mapping)
+UPSCALER_CASES = {"cornell_default_upscalers", "cornell_smaa_ratio1_taa", "city_smaa_only_ratio1p5", "simple_taa_only"}
 
 PLANES = ([("albedo", L.OUT_ALBEDO)] + [(f"render{i}", L.OUT_RENDER_DIRECT + i) for i in range(3)] +
           [(f"variance{i}", L.OUT_VARIANCE_DIRECT + i) for i in range(3)] + [(f"reservoir{i}", L.OUT_RESERVOIR_0 + i) for i in range(10)] +
@@ -51,7 +63,17 @@ def make_bench(case):
 
 def frame_inputs(bench, case, frame):
     step = CASES[case][4]
-    return bench.moving_inputs(frame, step) if any(step) else bench.inputs(frame)
+    inp = bench.moving_inputs(frame, step) if any(step) else bench.inputs(frame)
+    if case in UPSCALER_CASES:
+        inp.temporal_upscalers = 1
+    return inp
+
+
+def upscalers_of(case, bench):
+    """(smaa, taa) as PostProcessNode::run decides them (post_process.rs:1236,1260)"""
+    if case not in UPSCALER_CASES:
+        return False, False
+    return bench.settings.upscale_kind == _P.UPSCALE_SMAA_TU4X, bench.settings.taa == _P.TAA_JASMINE
 
 
 def animate(bench, case, frame):
@@ -69,4 +91,6 @@ def animate(bench, case, frame):
 def planes_of(case, bench):
     denoise = bool(bench.settings.denoise)
     signals = 3 if bench.settings.indirect_bounces else 2
-    return PLANES + (DENOISED[:signals] if denoise else [])
+    smaa, taa = upscalers_of(case, bench)
+    return (PLANES + (DENOISED[:signals] if denoise else []) + ([("upscaled", L.OUT_UPSCALED)] if smaa else []) +
+            ([("taa", L.OUT_TAA)] if taa else []))

@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Golden vectors from the reference's OWN shaders.  Runs every sequence of tests/wgsl_cases.py through the reference's WGSL
-(/root/reference/src/shaders/{light,denoise,tone_mapping}.wgsl translated to C++ by oracle/wgsl/wgsl2cpp.py and executed on the CPU by
+(/root/reference/src/shaders/{light,denoise,tone_mapping,smaa,taa}.wgsl translated to C++ by oracle/wgsl/wgsl2cpp.py and executed on the CPU by
 oracle/wgsl/run_reference.py, wired as src/light.rs and src/post_process.rs wire the passes) and writes per-frame, per-plane SHA-256
 digests of every buffer and texture the passes produce to tests/golden/wgsl_<case>.npz.
 
 Only in the build container (needs /root/reference + g++).  The G-buffer of each frame is the oracle's (the reference rasterises it:
 a render pipeline, not part of the translated compute path); everything downstream — albedo, both direct_lit pipelines, both
 spatial_reuse pipelines, indirect_lit_ambient (single / multiple bounces), demodulation, the four denoise levels with and without
-firefly filtering, tone mapping, over free-running sequences with validation frames, camera motion and moving instances — is computed
+firefly filtering, tone mapping, SMAA TU4x (+ extrapolation) and TAA, over free-running sequences with validation frames, camera motion and moving instances — is computed
 by the reference's shader text from its own state of the previous frames."""
 import os
 import sys
@@ -30,6 +30,10 @@ def reference_planes(ref, bench):
         out[f"render{i}"], out[f"variance{i}"], out[f"denoised{i}"] = ref.render[i], ref.variance[i], ref.denoise_render[i]
     for i in range(10):
         out[f"reservoir{i}"] = ref.reservoir[i][:ref.rw * ref.rh]      # the records the passes index (render size)
+    if ref.upscale_output is not None:
+        out["upscaled"] = ref.upscale_output
+    if ref.taa_output is not None:
+        out["taa"] = ref.taa_output[ref.head]
     return out
 
 
@@ -50,6 +54,9 @@ def run_case(case):
         ref.set_gbuffer(*[np.ascontiguousarray(orc.readback(k)) for k in WC.GBUFFER])
         ref.light_node(inp)
         ref.post_process_node(inp, bool(bench.settings.denoise))
+        smaa, taa = WC.upscalers_of(case, bench)
+        if smaa or taa:
+            ref.upscale_node(inp, smaa, taa)
         planes = reference_planes(ref, bench)
         for name, _ in WC.planes_of(case, bench):
             digests[f"f{f}_{name}"] = WC.digest(planes[name])
