@@ -85,6 +85,7 @@ struct hk_context {
     TileMap tm_denoise[4][5];          // kc_denoise, per level: tap geometry, instance, the level's three signal planes (box = 16 + 2 x apron)
     bool tile_maps_ready = false;
     bool full_frame = true;            // the context owns the whole frame (no tile): upscale_ratio > 1 and the upscalers need it
+    int last_up_w = 0, last_up_h = 0;   // Band::OW / OH of the last frame
     int last_render_w = 0, last_render_h = 0; bool last_smaa = false, last_upscalers = false, last_fsr = false; uint32_t last_number = 0;   // of the last frame, for read-back sizes
     int gbuffer_current = 0;           // index of the "current" position / velocity_uv planes; toggled by every prepass
     uint8_t* noise = nullptr;
@@ -215,7 +216,7 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     // (validated against the old width) and the "planes are usable" flag, which only a complete allocation sets again —
     // a cudaMalloc failing half-way leaves the context refusing to render instead of holding dangling pointers.
     ctx->planes_ready = false;
-    ctx->last_render_w = ctx->last_render_h = 0; ctx->last_number = 0;
+    ctx->last_render_w = ctx->last_render_h = 0; ctx->last_up_w = ctx->last_up_h = 0; ctx->last_number = 0;
     ctx->last_smaa = ctx->last_upscalers = ctx->last_fsr = false;
     ctx->frame_target = nullptr; ctx->frame_pitch = 0;
     free_list(ctx->allocations);
@@ -228,7 +229,7 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     b.ax0 = b.cx0 - ghost < 0 ? 0 : b.cx0 - ghost;
     b.ax1 = b.cx1 + ghost > b.W ? b.W : b.cx1 + ghost;
     b.AW = hk_plane_pitch(b.ax1 - b.ax0);
-    b.RW = b.W; b.RH = b.H; b.RS = b.AW;
+    b.RW = b.W; b.RH = b.H; b.RS = b.AW; b.OW = 2 * b.W; b.OH = 2 * b.H;
     ctx->band = b;
     const size_t n = (size_t)b.AW * (size_t)(b.a1 - b.a0);
     ctx->band_pixels = n;
@@ -312,6 +313,10 @@ int hk_context_create_tile(hk_context** out, int cuda_device, uint32_t width, ui
     if (const char* e = getenv("HK_TUNE_TILED_DENOISE")) c->tiled_denoise = atoi(e) != 0;
     c->wide_traversal = hk_tolerance_build() != 0 ? HK_WIDE_TRAVERSAL_DEFAULT : 0;      // the exact flavour keeps the reference's walk
     if (const char* e = getenv("HK_TUNE_WIDE_TRAVERSAL")) c->wide_traversal = atoi(e) & 3;
+#ifndef HK_EMU
+    // A/B: ask for the largest L1 split for kernels that use no shared memory (the light kernels keep their spills and the scene there)
+    if (const char* e = getenv("HK_TUNE_PREFER_L1")) { if (atoi(e)) cudaDeviceSetCacheConfig(cudaFuncCachePreferL1); }
+#endif
     ctx = c;
     if (cuda_stream) c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     else {
@@ -961,6 +966,12 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
         P.band.RH = (int)ceilf(scale * (float)P.band.H);
         P.band.RS = P.band.RW;
     }
+    {   // upscale_output after SMAA TU4x: create_texture(format, scale) with scale = ratio.recip() * 2 (post_process.rs:663-667,711,717)
+        const float scale2 = (1.0f / in->frame.upscale_ratio) * 2.0f;
+        P.band.OW = (int)ceilf((float)P.band.W * scale2);
+        P.band.OH = (int)ceilf((float)P.band.H * scale2);
+    }
+    ctx->last_up_w = P.band.OW; ctx->last_up_h = P.band.OH;
     P.inv_rw = 1.0f / (float)P.band.RW; P.inv_rh = 1.0f / (float)P.band.RH;
     ctx->last_render_w = P.band.RW; ctx->last_render_h = P.band.RH; ctx->last_smaa = in->smaa_tu4x != 0; ctx->last_number = in->frame.number;
     ctx->last_fsr = in->temporal_upscalers && in->fsr1;
@@ -1348,7 +1359,12 @@ static bool plane_view(hk_context* ctx, int which, PlaneView* v) {
             if (!base) return false;
             if (which == HK_OUT_UPSCALED && ctx->last_fsr) { *v = PlaneView{base, 8, (size_t)b.W, (size_t)b.H, (size_t)b.W}; return true; }
             const size_t k = (which == HK_OUT_UPSCALED || ctx->last_smaa) ? 2 : 1;
-            if (ctx->full_frame) { *v = PlaneView{base, 8, k * rw, k * rh, k * rw}; return true; }
+            if (ctx->full_frame) {
+                const size_t uw = ctx->last_up_w ? (size_t)ctx->last_up_w : 2 * rw, uh = ctx->last_up_h ? (size_t)ctx->last_up_h : 2 * rh;
+                if (k == 2) *v = PlaneView{base, 8, uw, uh, uw};   // stored tightly at OW x OH
+                else *v = PlaneView{base, 8, rw, rh, rw};
+                return true;
+            }
             const size_t pitch = k * (size_t)b.AW, first = (k * (size_t)(b.r0 - b.a0)) * pitch + k * (size_t)(b.cx0 - b.ax0);
             *v = PlaneView{base + first, 8, k * ow, k * oh, pitch};
             return true;
@@ -1550,7 +1566,7 @@ int hk_halo_import(hk_context* ctx, const hk_halo_descriptor* remote, hk_halo_pe
     b.W = remote->frame[0]; b.H = remote->frame[1];
     b.ax0 = remote->allocated[0]; b.ax1 = remote->allocated[1]; b.a0 = remote->allocated[2]; b.a1 = remote->allocated[3];
     b.cx0 = remote->owned[0]; b.cx1 = remote->owned[1]; b.r0 = remote->owned[2]; b.r1 = remote->owned[3];
-    b.AW = hk_plane_pitch(b.ax1 - b.ax0); b.RW = b.W; b.RH = b.H; b.RS = b.AW;
+    b.AW = hk_plane_pitch(b.ax1 - b.ax0); b.RW = b.W; b.RH = b.H; b.RS = b.AW; b.OW = 2 * b.W; b.OH = 2 * b.H;
     peer->planes = Planes{};
     const int handles = remote->has_images ? 44 : 40;
     for (int i = 0; i < handles; ++i) {

@@ -129,7 +129,7 @@ struct Planes {
     uint2* tone_mapped;         // owned rectangle only, tightly packed; = tone_mapped_db[frame.number % 2] (post_process.rs:716,979)
     uint2* tone_mapped_db[2];
     uint2* tone_ring_db[2];     // tiles with upscalers: the tone-mapped image over the tile's allocation (owned + 4-px ring + halo)
-    uint2* upscale_output;      // 2 RW x 2 RH (SMAA TU4x); tiles: 2 x the allocation.  W x H under Upscale::Fsr1 (the EASU result)
+    uint2* upscale_output;      // Band::OW x OH (SMAA TU4x: ceil(size * 2 / ratio), <= 2 RW x 2 RH); tiles: 2 x the allocation.  W x H under Upscale::Fsr1 (the EASU result)
     uint2* upscale_sharpen_output;   // W x H, full-frame contexts: the RCAS result (post_process.rs:723 upscale_output[1])
     uint2* taa_output[2];       // [frame.number % 2] is written
 };
@@ -147,6 +147,9 @@ struct Band {             // the tile of the frame one context renders (whole fr
     // render size = ceil(size / upscale_ratio) (light.rs:622-624).  At ratio 1 (every tiled / benchmark configuration)
     // render space == deferred space and RS == AW; at ratio > 1 (full-frame contexts only) render-size planes use stride RW.
     int RW, RH, RS;
+    // extent of the SMAA TU4x output (and of the TAA images that follow it): ceil(size * (2 / ratio)) in f32 as create_texture computes it
+    // (post_process.rs:663-667,715-721) — 2 RW x 2 RH except where the two ceilings disagree (ratio 2 on an odd width: W, not W + 1)
+    int OW, OH;
 };
 
 struct Counters { unsigned long long primary, tlas, blas; };
@@ -925,7 +928,14 @@ __device__ __forceinline__ void scatter_claim(const KParams& P, size_t target, i
 }
 
 // 8x4-pixel tiles per warp, 4 warps per CTA (16x8 pixels): ray coherence + whole-sector plane accesses.
-constexpr int TILE_W = 16, TILE_H = 8, CTA_THREADS = 128;
+// HK_CTA_WARPS (2 / 4 / 8; tuning builds): warps of a CTA sit side by side in pairs, so the CTA's tile is 16 x (2 x warps) pixels.  A CTA
+// gives its registers and warp slots back only when its slowest warp ends, and the light kernels' warps end at very different times;
+// the HK_MINB_* values are CTAs per SM and must be scaled with the CTA size by such a build.
+#ifndef HK_CTA_WARPS
+#define HK_CTA_WARPS 4
+#endif
+static_assert(HK_CTA_WARPS == 2 || HK_CTA_WARPS == 4 || HK_CTA_WARPS == 8, "tile_pixel places warps in pairs");
+constexpr int TILE_W = 16, TILE_H = 2 * HK_CTA_WARPS, CTA_THREADS = 32 * HK_CTA_WARPS;
 #ifndef HK_MINB_INDIRECT
 #define HK_MINB_INDIRECT 12  // measured on B200: these kernels are latency / instruction-fetch bound and want warps, not registers.  Round 1
                              // (tools/tune_launch_bounds.sh): 8 CTAs/SM (64 registers, some spills) beat 3-4 CTAs/SM at 130-160 registers

@@ -120,6 +120,22 @@ __device__ __forceinline__ size_t render_image_index(const KParams& P, int scale
     if (!P.tile_images) return (size_t)y * (size_t)(scale * b.RW) + (size_t)x;
     return (size_t)(y - scale * b.a0) * (size_t)(scale * b.AW) + (size_t)(x - scale * b.ax0);
 }
+// The SMAA TU4x output and the TAA images after it: OW x OH texels (Band::OW / OH), stored tightly by a full-frame context and over
+// 2 x the allocation by a tile (ratio 1: OW = 2 W exactly).  A store outside the texture is dropped, as the storage texture drops it.
+__device__ __forceinline__ Image16 upscaled_image(const KParams& P, const uint2* plane) {
+    const Band& b = P.band;
+    if (!P.tile_images) return Image16{plane, b.OW, b.OH, 0, 0, b.OW, b.OH};
+    return Image16{plane, 2 * b.W, 2 * b.H, 2 * b.ax0, 2 * b.a0, 2 * b.AW, 2 * (b.a1 - b.a0)};
+}
+__device__ __forceinline__ void upscaled_store(const KParams& P, uint2* plane, int x, int y, vec4 v) {
+    const Band& b = P.band;
+    if (!P.tile_images) {
+        if (x >= b.OW || y >= b.OH) return;
+        store16(plane, (size_t)y * (size_t)b.OW + (size_t)x, v);
+    } else {
+        store16(plane, (size_t)(y - 2 * b.a0) * (size_t)(2 * b.AW) + (size_t)(x - 2 * b.ax0), v);
+    }
+}
 __device__ __forceinline__ Image32 gbuffer_image(const KParams& P, const float4* plane) {
     const Band& b = P.band;
     return Image32{plane, b.W, b.H, b.ax0, b.a0, b.AW, b.a1 - b.a0};
@@ -133,7 +149,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x(const __grid_constant
     int x, y;
     tile_pixel(x, y, P);
     if (!tile_active(P, x, y)) return;
-    const int RW = P.band.RW, RH = P.band.RH, OW = 2 * RW, OH = 2 * RH, W = P.band.W, H = P.band.H;
+    const int OW = P.tile_images ? 2 * P.band.W : P.band.OW, OH = P.tile_images ? 2 * P.band.H : P.band.OH, W = P.band.W, H = P.band.H;   // textureDimensions(output_texture)
     const uint32_t cur = P.in.frame.number % 2u, prv = 1u - cur;
     const Image16 render = render_image(P, tone_plane(P, cur), 1), previous_render = render_image(P, tone_plane(P, prv), 1);
     const Image32 position = gbuffer_image(P, P.planes.pos_depth_db[P.gbuffer_current]);
@@ -198,15 +214,15 @@ __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x(const __grid_constant
     blend_factor = clampf(-cs, 0.0f, 1.0f);
     vec3 remix_color = xyz(render.linear(previous_output_uv));
     previous_color = mix(previous_color, remix_color, blend_factor);
-    store16(P.planes.upscale_output, render_image_index(P, 2, cox, coy), v4(current_color, 1.0f));
-    store16(P.planes.upscale_output, render_image_index(P, 2, pox, poy), v4(previous_color, 1.0f));
+    upscaled_store(P, P.planes.upscale_output, cox, coy, v4(current_color, 1.0f));
+    upscaled_store(P, P.planes.upscale_output, pox, poy, v4(previous_color, 1.0f));
 }
 
 __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x_extrapolate(const __grid_constant__ KParams P) {  // smaa.wgsl:201-271
     int x, y;
     tile_pixel(x, y, P);
     if (!tile_active(P, x, y)) return;
-    const Image16 out = render_image(P, P.planes.upscale_output, 2);
+    const Image16 out = upscaled_image(P, P.planes.upscale_output);
     vec4 t = out.load(2 * x, 2 * y), b = out.load(2 * x + 1, 2 * y + 1), n = out.load(2 * x + 1, 2 * y - 1), e = out.load(2 * x + 2, 2 * y);
     vec4 s_ = out.load(2 * x, 2 * y + 2), w = out.load(2 * x - 1, 2 * y + 1);
     auto lum3 = [](vec4 a, vec4 c) { return luminance(vabs(xyz(a) - xyz(c))); };
@@ -220,21 +236,23 @@ __global__ void __launch_bounds__(CTA_THREADS) k_smaa_tu4x_extrapolate(const __g
         color = color + (tt + bb) * factor_xy.y;
         return color * (0.5f * factor_z);
     };
-    store16(P.planes.upscale_output, render_image_index(P, 2, 2 * x, 2 * y + 1), blend(t, s_, w, b));
-    store16(P.planes.upscale_output, render_image_index(P, 2, 2 * x + 1, 2 * y), blend(n, b, t, e));
+    upscaled_store(P, P.planes.upscale_output, 2 * x, 2 * y + 1, blend(t, s_, w, b));
+    upscaled_store(P, P.planes.upscale_output, 2 * x + 1, 2 * y, blend(n, b, t, e));
 }
 
 // ------------------------------------------------------------------------------------------- taa_jasmine
-// launched over the OUTPUT size (2 RW x 2 RH after SMAA TU4x, else RW x RH): col_hi / row_hi carry it
+// launched over 2 RW x 2 RH after SMAA TU4x (else RW x RH) as the reference dispatches it: col_hi / row_hi carry it
 __global__ void __launch_bounds__(CTA_THREADS) k_taa_jasmine(const __grid_constant__ KParams P, int smaa) {  // taa.wgsl:79-170
     int x, y;
     tile_pixel(x, y, P);
     if (!tile_active(P, x, y)) return;
-    const int OW = smaa ? 2 * P.band.RW : P.band.RW, OH = smaa ? 2 * P.band.RH : P.band.RH, W = P.band.W, H = P.band.H;
+    // textureDimensions(output_texture): taa_output is created at the scale of upscale_output after SMAA TU4x (post_process.rs:717,726-729)
+    const int OW = smaa ? (P.tile_images ? 2 * P.band.W : P.band.OW) : P.band.RW, OH = smaa ? (P.tile_images ? 2 * P.band.H : P.band.OH) : P.band.RH;
+    const int W = P.band.W, H = P.band.H;
+    if (x >= OW || y >= OH) return;        // the dispatch covers 2 RW x 2 RH (scaled_size *= 2, :1258): invocations outside the texture store nothing
     const uint32_t cur = P.in.frame.number % 2u, prv = 1u - cur;
-    const int scale = smaa ? 2 : 1;
-    const Image16 render = render_image(P, smaa ? P.planes.upscale_output : tone_plane(P, cur), scale);
-    const Image16 previous_render = render_image(P, P.planes.taa_output[prv], scale);
+    const Image16 render = smaa ? upscaled_image(P, P.planes.upscale_output) : render_image(P, tone_plane(P, cur), 1);
+    const Image16 previous_render = smaa ? upscaled_image(P, P.planes.taa_output[prv]) : render_image(P, P.planes.taa_output[prv], 1);
     const Image32 position = gbuffer_image(P, P.planes.pos_depth_db[P.gbuffer_current]);
     const Image32 previous_position = gbuffer_image(P, P.planes.pos_depth_db[P.gbuffer_current ^ 1]);
     const Image32 velocity_uv = gbuffer_image(P, P.planes.velocity_uv_db[P.gbuffer_current]);
@@ -263,9 +281,12 @@ __global__ void __launch_bounds__(CTA_THREADS) k_taa_jasmine(const __grid_consta
         vec3 previous_pos = xyz(previous_position.nearest(previous_uv + uv_biases[i]));
         position_miss = position_miss || length(xyz(current_position_depth) - previous_pos) > 0.5f;
     }
-    const size_t oidx = render_image_index(P, scale, x, y);
+    auto store_output = [&](vec4 v) {
+        if (smaa) upscaled_store(P, P.planes.taa_output[cur], x, y, v);
+        else store16(P.planes.taa_output[cur], render_image_index(P, 1, x, y), v);
+    };
     if (!has_content) {
-        store16(P.planes.taa_output[cur], oidx, v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]));
+        store_output(v4(P.in.frame.clear_color[0], P.in.frame.clear_color[1], P.in.frame.clear_color[2], P.in.frame.clear_color[3]));
         return;
     }
     vec4 pv = previous_velocity_uv.nearest(previous_uv);
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_taa_jasmine(const __grid_consta
         previous_color = YCoCg_to_RGB(previous_color);
     }
     vec3 output = mix(previous_color, current_color, 0.1f / P.in.frame.upscale_ratio);
-    store16(P.planes.taa_output[cur], oidx, v4(output, original_color.w));
+    store_output(v4(output, original_color.w));
 }
 
 // --------------------------------------------------------------------------------------------- FSR 1.0 (Upscale::Fsr1)

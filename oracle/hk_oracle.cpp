@@ -86,6 +86,7 @@ struct ScatterWrite { int32_t index; hk_packed_reservoir value; };
 struct hko_context {
     int W = 0, H = 0;  // full (deferred) size; render size == full size at upscale ratio 1
     int RW = 0, RH = 0;
+    int OW = 0, OH = 0;       // SMAA TU4x output extent: ceil(size * (2 / ratio)) in f32 (post_process.rs:663-667,711,717), <= 2 RW x 2 RH
     // scene (bind group 2)
     std::vector<hk_vertex> vertices;
     std::vector<hk_primitive> primitives;
@@ -117,9 +118,9 @@ struct hko_context {
     std::vector<float> denoise_internal_variance;
     std::vector<uvec2> denoise_render[3];
     std::vector<uvec2> tone_mapping_output[2];   // [frame.number % 2] is written (post_process.rs:716,979)
-    std::vector<uvec2> upscale_output;           // 2 RW x 2 RH (post_process.rs:718-722); W x H under Upscale::Fsr1 (:723)
+    std::vector<uvec2> upscale_output;           // OW x OH <= 2 RW x 2 RH (post_process.rs:715-722); W x H under Upscale::Fsr1 (:723)
     std::vector<uvec2> upscale_sharpen_output;   // upscale_output[1], W x H: FSR RCAS result (post_process.rs:723,1079-1086)
-    std::vector<uvec2> taa_output[2];            // 2 RW x 2 RH with SMAA TU4x, else RW x RH (post_process.rs:726-731)
+    std::vector<uvec2> taa_output[2];            // OW x OH with SMAA TU4x, else RW x RH (post_process.rs:726-731)
     // per-frame
     hk_frame_inputs in;
     struct alignas(64) RayCounters { uint64_t primary = 0, tlas = 0, blas = 0; };
@@ -1476,7 +1477,7 @@ void pass_smaa_tu4x(Ctx& c) {  // smaa.wgsl:81-199
     Image16 render{&c.tone_mapping_output[cur], c.RW, c.RH}, previous_render{&c.tone_mapping_output[prev], c.RW, c.RH};
     Image32 position{&c.position, c.W, c.H}, previous_position{&c.previous_position, c.W, c.H};
     Image32 velocity_uv{&c.velocity_uv, c.W, c.H}, previous_velocity_uv{&c.previous_velocity_uv, c.W, c.H};
-    const int OW = 2 * c.RW, OH = 2 * c.RH;
+    const int OW = c.OW, OH = c.OH;                                          // textureDimensions(output_texture)
     ivec2 input_size; input_size.x = c.RW; input_size.y = c.RH;
     ivec2 output_size; output_size.x = OW; output_size.y = OH;
     const int current_jitter = ((c.in.frame.number & 1u) == 0u) ? 0 : 1;     // current_smaa_jitter :74-76
@@ -1544,13 +1545,16 @@ void pass_smaa_tu4x(Ctx& c) {  // smaa.wgsl:81-199
         blend_factor = clampf(-cs, 0.0f, 1.0f);
         vec3 remix_color = xyz(render.linear(previous_output_uv));
         previous_color = mix(previous_color, remix_color, blend_factor);
-        c.upscale_output[(size_t)current_output_coords.y * OW + current_output_coords.x] = pack_rgba16f(v4(current_color, 1.0f));
-        c.upscale_output[(size_t)previous_output_coords.y * OW + previous_output_coords.x] = pack_rgba16f(v4(previous_color, 1.0f));
+        auto store = [&](ivec2 p, vec4 v) {   // textureStore outside the texture is dropped
+            if (p.x < OW && p.y < OH) c.upscale_output[(size_t)p.y * OW + p.x] = pack_rgba16f(v);
+        };
+        store(current_output_coords, v4(current_color, 1.0f));
+        store(previous_output_coords, v4(previous_color, 1.0f));
     });
 }
 
 void pass_smaa_tu4x_extrapolate(Ctx& c) {  // smaa.wgsl:201-271
-    const int OW = 2 * c.RW, OH = 2 * c.RH;
+    const int OW = c.OW, OH = c.OH;
     Image16 out{&c.upscale_output, OW, OH};
     auto lum3 = [](vec4 a, vec4 b) { return luminance(vabs(xyz(a) - xyz(b))); };
     for_pixels(c, c.RW, c.RH, [&](int x, int y) {
@@ -1569,8 +1573,8 @@ void pass_smaa_tu4x_extrapolate(Ctx& c) {  // smaa.wgsl:201-271
         };
         vec4 x_color = blend(t, s_, w, b);
         vec4 y_color = blend(n, b, t, e);
-        c.upscale_output[(size_t)(2 * y + 1) * OW + 2 * x] = pack_rgba16f(x_color);
-        c.upscale_output[(size_t)(2 * y) * OW + 2 * x + 1] = pack_rgba16f(y_color);
+        if (2 * x < OW && 2 * y + 1 < OH) c.upscale_output[(size_t)(2 * y + 1) * OW + 2 * x] = pack_rgba16f(x_color);
+        if (2 * x + 1 < OW && 2 * y < OH) c.upscale_output[(size_t)(2 * y) * OW + 2 * x + 1] = pack_rgba16f(y_color);
     });
 }
 
@@ -1714,7 +1718,8 @@ void pass_fsr_rcas(Ctx& c) {   // FSR_Pass.glsl CurrFilter (SAMPLE_RCAS), FsrRca
 void pass_taa_jasmine(Ctx& c) {  // taa.wgsl:79-170
     const uint32_t cur = c.in.frame.number % 2u, prev = 1u - cur;
     const bool smaa = c.in.smaa_tu4x != 0;
-    const int OW = smaa ? 2 * c.RW : c.RW, OH = smaa ? 2 * c.RH : c.RH;      // post_process.rs:718-731,1257
+    const int OW = smaa ? c.OW : c.RW, OH = smaa ? c.OH : c.RH;              // post_process.rs:717,726-731; the dispatch over 2 RW x 2 RH (:1258)
+                                                                             // stores nothing outside the texture
     Image16 render{smaa ? &c.upscale_output : &c.tone_mapping_output[cur], OW, OH};   // taa_input_texture, post_process.rs:1011-1014
     Image16 previous_render{&c.taa_output[prev], OW, OH};
     Image32 position{&c.position, c.W, c.H}, previous_position{&c.previous_position, c.W, c.H};
@@ -1920,6 +1925,9 @@ static int begin(hko_context* c, const hk_frame_inputs* in) {
     const float scale = 1.0f / in->frame.upscale_ratio;
     c->RW = (int)ceilf(scale * (float)c->W);
     c->RH = (int)ceilf(scale * (float)c->H);
+    const float scale2 = scale * 2.0f;                 // `scale *= 2.0` before upscale_output / taa_output are created
+    c->OW = (int)ceilf((float)c->W * scale2);
+    c->OH = (int)ceilf((float)c->H * scale2);
     if (c->RW < 1 || c->RH < 1 || c->RW > c->W || c->RH > c->H) return fail(c, HK_ERR_INVALID_ARGUMENT, "upscale_ratio out of range");
     return HK_OK;
 }
@@ -1962,9 +1970,9 @@ static void* plane(hko_context* c, int which, size_t* bytes) {
     auto RR = [&](void* p, size_t b, size_t count) { *bytes = b * count; return p; };
     switch (which) {
         case HK_OUT_TONE_MAPPED: return RR(c->tone_mapping_output[c->in.frame.number % 2u].data(), 8, nr);
-        case HK_OUT_UPSCALED: return RR(c->upscale_output.data(), 8, c->in.fsr1 ? n : 4 * nr);
+        case HK_OUT_UPSCALED: return RR(c->upscale_output.data(), 8, c->in.fsr1 ? n : (size_t)c->OW * c->OH);
         case HK_OUT_FSR_SHARPENED: return RR(c->upscale_sharpen_output.data(), 8, n);
-        case HK_OUT_TAA: return RR(c->taa_output[c->in.frame.number % 2u].data(), 8, smaa ? 4 * nr : nr);
+        case HK_OUT_TAA: return RR(c->taa_output[c->in.frame.number % 2u].data(), 8, smaa ? (size_t)c->OW * c->OH : nr);
         case HK_OUT_RENDER_DIRECT: case HK_OUT_RENDER_EMISSIVE: case HK_OUT_RENDER_INDIRECT:
             return RR(c->render[which - HK_OUT_RENDER_DIRECT].data(), 8, nr);
         case HK_OUT_VARIANCE_DIRECT: case HK_OUT_VARIANCE_EMISSIVE: case HK_OUT_VARIANCE_INDIRECT:
@@ -1988,7 +1996,7 @@ int hko_output_extent(hko_context* c, int which, uint32_t* width, uint32_t* heig
     const bool deferred = which == HK_OUT_ALBEDO || (which >= HK_OUT_GBUFFER_POSITION && which <= HK_OUT_GBUFFER_VELOCITY_UV);
     const bool fsr = c->in.fsr1 && (which == HK_OUT_UPSCALED || which == HK_OUT_FSR_SHARPENED);   // the camera target size
     const int k = ((which == HK_OUT_UPSCALED && !c->in.fsr1) || (which == HK_OUT_TAA && c->in.smaa_tu4x)) ? 2 : 1;
-    *width = (uint32_t)((deferred || fsr) ? c->W : k * c->RW); *height = (uint32_t)((deferred || fsr) ? c->H : k * c->RH);
+    *width = (uint32_t)((deferred || fsr) ? c->W : (k == 2 ? c->OW : c->RW)); *height = (uint32_t)((deferred || fsr) ? c->H : (k == 2 ? c->OH : c->RH));
     return HK_OK;
 }
 int hko_readback(hko_context* c, int which, void* host, size_t bytes) {

@@ -83,23 +83,28 @@ def build(force=False):
     have = open(stamp).read() if os.path.exists(stamp) else None
     if not force and not newer(LIB, deps) and have == wanted:
         return LIB
-    objs, launches = [], 0
+    objs, launches, jobs = [], 0, []
     for f in CU:
         text, n = transform(open(os.path.join(SRC, f)).read(), f)
         launches += n
         g = os.path.join(GEN, f.replace(".cu", ".emu.cpp"))
         open(g, "w").write(text)
         o = os.path.join(OUT, f + ".o")
-        subprocess.run([CXX] + FLAGS + ["-c", g, "-o", o], check=True)
+        jobs.append([CXX] + FLAGS + ["-c", g, "-o", o])
         objs.append(o)
     glue = os.path.join(HERE, "emu_runtime.cpp")
     o = os.path.join(OUT, "emu_globals.o")
-    subprocess.run([CXX] + FLAGS + ["-I" + HERE, "-c", glue, "-o", o], check=True)
+    jobs.append([CXX] + FLAGS + ["-I" + HERE, "-c", glue, "-o", o])
     objs.append(o)
     for f in CPP:
         o = os.path.join(OUT, f + ".o")
-        subprocess.run([CXX] + FLAGS + ["-c", os.path.join(HOST, f), "-o", o], check=True)
+        jobs.append([CXX] + FLAGS + ["-c", os.path.join(HOST, f), "-o", o])
         objs.append(o)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:      # one compiler per translation unit (the sanitizer builds of
+        for r in pool.map(lambda j: subprocess.run(j).returncode, jobs):           # kernels_light take tens of minutes each otherwise in a row)
+            if r != 0:
+                raise SystemExit("emulator build failed")
     subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs + (["-fsanitize=address"] if ASAN else []) + (["-fsanitize=alignment", "-static-libubsan"] if ALIGN else []) + ["-lz"], check=True)
     open(stamp, "w").write(wanted)
     print(f"emulator: {launches} launch sites converted -> {LIB}")

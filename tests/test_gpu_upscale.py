@@ -18,6 +18,12 @@ def scaled(size, ratio):
     return int(np.ceil(np.float32(1.0) / np.float32(ratio) * np.float32(size)))
 
 
+def upscaled(size, ratio):
+    """extent of upscale_output after SMAA TU4x: create_texture(format, ratio.recip() * 2.0) = ceil(size * scale) in f32
+    (post_process.rs:663-667,711,717) — NOT always 2 * scaled(size, ratio): 50 rows at ratio 1.5 render 34 rows and upscale to 67"""
+    return int(np.ceil(np.float32(size) * (np.float32(1.0) / np.float32(ratio) * np.float32(2.0))))
+
+
 @pytest.mark.parametrize("ratio", [2.0, 1.5, 1.3])
 def test_upscale_ratio_bit_exact(ratio):
     """Light + denoise + tone mapping at render size ceil(size / ratio), G-buffer at full size; moving camera so the
@@ -76,14 +82,15 @@ def test_temporal_upscalers_bit_exact(scene, config, size, settings, outputs):
         compare_all(dev, orc, ALL_PLANES + DENOISED + outputs, f)
     if L.OUT_UPSCALED in outputs:
         up = dev.readback(L.OUT_UPSCALED)
-        assert up.shape[:2] == (2 * rh, 2 * rw)
+        assert up.shape[:2] == (upscaled(size[1], ratio), upscaled(size[0], ratio))
         assert np.isfinite(up.astype(np.float32)).all() and float(up[..., :3].astype(np.float32).max()) > 0.05
     if L.OUT_TAA in outputs:
-        k = 2 if settings["upscale_kind"] == plugin.UPSCALE_SMAA_TU4X else 1
+        smaa = settings["upscale_kind"] == plugin.UPSCALE_SMAA_TU4X
+        th, tw = (upscaled(size[1], ratio), upscaled(size[0], ratio)) if smaa else (rh, rw)
         taa = dev.readback(L.OUT_TAA)
-        assert taa.shape[:2] == (k * rh, k * rw)
+        assert taa.shape[:2] == (th, tw)
         ptr, nbytes = dev.output_device_pointer(L.OUT_TAA)
-        assert ptr and nbytes == k * rh * k * rw * 8
+        assert ptr and nbytes == th * tw * 8
 
 
 def test_upscalers_nodes_one_by_one_and_plugin_switch():

@@ -40,9 +40,14 @@ CASES = {
                                 {"taa": _P.TAA_NONE, "upscale_kind": _P.UPSCALE_SMAA_TU4X, "upscale_ratio": 1.5}),
     "simple_taa_only": ("simple", "cornell_1080p", (80, 48), 8, (0.02, 0.01, 0.0), None,
                         {"taa": _P.TAA_JASMINE, "upscale_kind": _P.UPSCALE_FSR1, "upscale_ratio": 1.0}),      # TAA on the tone-mapped image
+    # default settings on an odd window: 127 x 63 renders 64 x 32, and upscale_output = ceil(size * (0.5 * 2)) is 127 x 63, not 128 x 64 —
+    # stores of the last column / row fall outside the texture, every uv of smaa.wgsl / taa.wgsl is computed from the odd extent
+    "cornell_default_upscalers_odd_window": ("cornell", "cornell_1080p", (127, 63), 7, (0.03, 0.01, -0.02), None,
+                                             {"taa": _P.TAA_JASMINE, "upscale_kind": _P.UPSCALE_SMAA_TU4X, "upscale_ratio": 2.0}),
 }
 # cases whose frames run with HikariInputs::temporal_upscalers (the passes of post_process.rs:1236-1277 after tone mapping)
-UPSCALER_CASES = {"cornell_default_upscalers", "cornell_smaa_ratio1_taa", "city_smaa_only_ratio1p5", "simple_taa_only"}
+UPSCALER_CASES = {"cornell_default_upscalers", "cornell_smaa_ratio1_taa", "city_smaa_only_ratio1p5", "simple_taa_only",
+                  "cornell_default_upscalers_odd_window"}
 
 PLANES = ([("albedo", L.OUT_ALBEDO)] + [(f"render{i}", L.OUT_RENDER_DIRECT + i) for i in range(3)] +
           [(f"variance{i}", L.OUT_VARIANCE_DIRECT + i) for i in range(3)] + [(f"reservoir{i}", L.OUT_RESERVOIR_0 + i) for i in range(10)] +
