@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(ROOT, "oracle", "_ref", "wgsl")
 sys.path.insert(0, HERE)
 import wgsl2cpp  # noqa: E402
+import glsl2cpp  # noqa: E402
 
 RGBA32F, RGBA16F, R32F, RG32F, RGBA8SNORM, RGBA8UNORM, RGBA8SRGB = range(7)
 CXXFLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared", "-w", "-I", HERE, "-I", os.path.join(ROOT, "include")]
@@ -50,6 +51,42 @@ def build(shader, defs):
         if r.returncode != 0:
             raise RuntimeError(f"g++ failed on the translation of {shader}.wgsl {defs}:\n{r.stderr[-3000:]}")
     return C.CDLL(so, mode=C.RTLD_LOCAL)
+
+
+def build_fsr(define):
+    """translate + compile one FSR 1.0 pass (src/shaders/fsr/source.zip, oracle/wgsl/glsl2cpp.py); returns the loaded library"""
+    os.makedirs(OUT, exist_ok=True)
+    cpp_text = glsl2cpp.translate(define)
+    rt = open(os.path.join(HERE, "wgsl_rt.h")).read() + open(os.path.join(HERE, "glsl_rt.h")).read()
+    tag = hashlib.sha1((cpp_text + rt + " ".join(CXXFLAGS)).encode()).hexdigest()[:12]
+    name = "fsr_" + define.lower()
+    so = os.path.join(OUT, f"{name}_{tag}.so")
+    if not os.path.exists(so):
+        cpp = os.path.join(OUT, name + ".cpp")
+        open(cpp, "w").write(cpp_text)
+        r = subprocess.run(["g++"] + CXXFLAGS + [cpp, "-o", so], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed on the translation of FSR_Pass.glsl ({define}):\n{r.stderr[-3000:]}")
+    return C.CDLL(so, mode=C.RTLD_LOCAL)
+
+
+class FsrPass:
+    """one FSR 1.0 pass: InputTexture / InputSampler / OutputTexture / const_buffer of FSR_Pass.glsl"""
+
+    def __init__(self, define):
+        self.lib = build_fsr(define)
+        self.lib.bind_input.argtypes = self.lib.bind_output.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        self.lib.bind_sampler.argtypes = [C.c_int] * 3
+        self.lib.set_constants.argtypes = [C.c_float] * 7 + [C.c_uint]
+        self.lib.run.argtypes = [C.c_uint, C.c_uint]
+
+    def run(self, src, dst, constants, groups):
+        assert src.flags["C_CONTIGUOUS"] and dst.flags["C_CONTIGUOUS"]
+        self.lib.bind_input(src.ctypes.data, src.shape[1], src.shape[0], RGBA16F)
+        self.lib.bind_output(dst.ctypes.data, dst.shape[1], dst.shape[0], RGBA16F)
+        self.lib.bind_sampler(1, 1, 1)                         # binding 1 of the sampler group: linear_sampler, clamp to edge
+        self.lib.set_constants(*constants)
+        self.lib.run(*groups)
 
 
 class Module:
@@ -150,6 +187,8 @@ class WgslReference:
                         for lvl in range(4) for ff in (False, True)}
         self.tone = Module("tone_mapping", [])
         self.smaa = self.taa = None                                          # built on first use (smaa.wgsl / taa.wgsl)
+        self.fsr_easu = self.fsr_rcas = None                                 # built on first use (src/shaders/fsr/source.zip)
+        self.fsr_output = None                                               # upscale_output[0] / [1] under Upscale::Fsr1, post_process.rs:723
         self.upscale_ratio = upscale_ratio
         n = width * height                                                   # reservoirs: size.x * size.y records, light.rs:343
         rw, rh = self.rw, self.rh
@@ -303,6 +342,19 @@ class WgslReference:
     def _scaled(self, scale):
         """create_texture(format, scale): (size as f32 * scale).ceil(), post_process.rs:663-667"""
         return int(np.ceil(np.float32(self.w) * np.float32(scale))), int(np.ceil(np.float32(self.h) * np.float32(scale)))
+
+    def fsr_node(self, inputs, taa, sharpness):
+        """post_process.rs:1279-1308: EASU from upscale_input_texture (:1037-1040) into upscale_output[0], RCAS from there into
+        upscale_output[1]; constants as FsrConstantsUniform::extract_component builds them (:519-534); both dispatched over
+        (size * 2 + 15) / 16 workgroups (the surplus ones store outside the image: nothing)"""
+        if self.fsr_easu is None:
+            self.fsr_easu, self.fsr_rcas = FsrPass("SAMPLE_EASU"), FsrPass("SAMPLE_RCAS")
+            self.fsr_output = [np.zeros((self.h, self.w, 4), np.uint16) for _ in range(2)]        # create_texture(format, 1.0) x 2
+        src = self.taa_output[self.head] if taa else self.tone_mapping_output[self.head]
+        constants = (float(self.rw), float(self.rh), float(self.rw), float(self.rh), float(self.w), float(self.h), float(sharpness), 0)
+        groups = ((self.w + 15) // 16, (self.h + 15) // 16)       # the groups that cover the image, of the (2 size + 15) / 16 dispatched
+        self.fsr_easu.run(src, self.fsr_output[0], constants, groups)
+        self.fsr_rcas.run(self.fsr_output[0], self.fsr_output[1], constants, groups)
 
     def upscale_node(self, inputs, smaa, taa):
         """post_process.rs:1236-1277: smaa_tu4x + smaa_tu4x_extrapolate over scaled_size, then taa_jasmine over the (doubled) size"""

@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <functional>
+#include <type_traits>
 #include <thread>
 #include <vector>
 
@@ -56,6 +57,9 @@ template <class T, int N> struct vec : vec_data<T, N> {
     T& operator[](u32 i) { return v[i]; }
     const T& operator[](u32 i) const { return v[i]; }
     template <int... I> vec<T, sizeof...(I)> swz() const { return vec<T, sizeof...(I)>(v[I]...); }
+    // GLSL only (glsl_rt.h): `a != b` on vectors is ONE bool there (any component differs); WGSL has no conversion and never asks for it
+    template <class U = T, class = typename std::enable_if<std::is_same<U, bool>::value>::type>
+    explicit operator bool() const { for (int i = 0; i < N; ++i) if (v[i]) return true; return false; }
 };
 template <class T> using vec2 = vec<T, 2>;
 template <class T> using vec3 = vec<T, 3>;

@@ -44,10 +44,15 @@ CASES = {
     # stores of the last column / row fall outside the texture, every uv of smaa.wgsl / taa.wgsl is computed from the odd extent
     "cornell_default_upscalers_odd_window": ("cornell", "cornell_1080p", (127, 63), 7, (0.03, 0.01, -0.02), None,
                                              {"taa": _P.TAA_JASMINE, "upscale_kind": _P.UPSCALE_SMAA_TU4X, "upscale_ratio": 2.0}),
+    # Upscale::Fsr1: EASU + RCAS (src/shaders/fsr/source.zip: the GLSL of the reference's SPIR-V blobs) after tone mapping / TAA
+    "cornell_fsr_ratio1p5": ("cornell", "cornell_1080p", (96, 64), 6, (0.03, 0.01, -0.02), None,
+                             {"taa": _P.TAA_NONE, "upscale_kind": _P.UPSCALE_FSR1, "upscale_ratio": 1.5, "upscale_sharpness": 0.0}),
+    "city_taa_fsr_ratio2": ("city", "city_4k", (128, 72), 6, (0.04, 0.0, -0.03), None,
+                            {"taa": _P.TAA_JASMINE, "upscale_kind": _P.UPSCALE_FSR1, "upscale_ratio": 2.0, "upscale_sharpness": 0.5}),
 }
 # cases whose frames run with HikariInputs::temporal_upscalers (the passes of post_process.rs:1236-1277 after tone mapping)
 UPSCALER_CASES = {"cornell_default_upscalers", "cornell_smaa_ratio1_taa", "city_smaa_only_ratio1p5", "simple_taa_only",
-                  "cornell_default_upscalers_odd_window"}
+                  "cornell_default_upscalers_odd_window", "cornell_fsr_ratio1p5", "city_taa_fsr_ratio2"}
 
 PLANES = ([("albedo", L.OUT_ALBEDO)] + [(f"render{i}", L.OUT_RENDER_DIRECT + i) for i in range(3)] +
           [(f"variance{i}", L.OUT_VARIANCE_DIRECT + i) for i in range(3)] + [(f"reservoir{i}", L.OUT_RESERVOIR_0 + i) for i in range(10)] +
@@ -81,6 +86,11 @@ def upscalers_of(case, bench):
     return bench.settings.upscale_kind == _P.UPSCALE_SMAA_TU4X, bench.settings.taa == _P.TAA_JASMINE
 
 
+def fsr_of(case, bench):
+    """Upscale::Fsr1 passes run (post_process.rs:1279)"""
+    return case in UPSCALER_CASES and bench.settings.upscale_kind == _P.UPSCALE_FSR1
+
+
 def animate(bench, case, frame):
     """moves the case's animated instances to their pose of `frame` (host mirror: transforms, previous transforms, prepare_instances);
     returns True when the scene changed"""
@@ -98,4 +108,5 @@ def planes_of(case, bench):
     signals = 3 if bench.settings.indirect_bounces else 2
     smaa, taa = upscalers_of(case, bench)
     return (PLANES + (DENOISED[:signals] if denoise else []) + ([("upscaled", L.OUT_UPSCALED)] if smaa else []) +
-            ([("taa", L.OUT_TAA)] if taa else []))
+            ([("taa", L.OUT_TAA)] if taa else []) +
+            ([("fsr_easu", L.OUT_UPSCALED), ("fsr_rcas", L.OUT_FSR_SHARPENED)] if fsr_of(case, bench) else []))

@@ -34,6 +34,8 @@ def reference_planes(ref, bench):
         out["upscaled"] = ref.upscale_output
     if ref.taa_output is not None:
         out["taa"] = ref.taa_output[ref.head]
+    if ref.fsr_output is not None:
+        out["fsr_easu"], out["fsr_rcas"] = ref.fsr_output
     return out
 
 
@@ -57,6 +59,8 @@ def run_case(case):
         smaa, taa = WC.upscalers_of(case, bench)
         if smaa or taa:
             ref.upscale_node(inp, smaa, taa)
+        if WC.fsr_of(case, bench):
+            ref.fsr_node(inp, taa, bench.settings.upscale_sharpness)
         planes = reference_planes(ref, bench)
         for name, _ in WC.planes_of(case, bench):
             digests[f"f{f}_{name}"] = WC.digest(planes[name])
