@@ -5,8 +5,9 @@
 // format, exactly as LightNode::run (src/light.rs:590-702) and PostProcessNode::run (src/post_process.rs:1140-1234)
 // dispatch it.  Every function cites the WGSL it follows (paths relative to /root/reference/src/shaders).
 //
-// PARITY: the compute passes below are PINNED against the reference's own shader text; the host-side scene build and the raster
-// prepass are not.  The reference ships no tests, golden vectors or fixtures for this path and cannot be built
+// PARITY: the compute passes below are PINNED against the reference's own shader text (and the ray-cast G-buffer is held, within a
+// rasteriser's sub-pixel snapping, against prepass.wgsl executed behind a software rasteriser: tests/test_wgsl_prepass.py); the host-side scene build
+// is not.  The reference ships no tests, golden vectors or fixtures for this path and cannot be built
 // here (no rustc / wgpu / Vulkan) — but its hot path IS text: oracle/wgsl/ translates src/shaders/{light,denoise,tone_mapping,smaa,taa}.wgsl
 // (read in place under /root/reference) to C++, compiles one library per pipeline specialisation into oracle/_ref/wgsl/ and drives
 // them with the bind-group wiring of src/light.rs / src/post_process.rs.  What that execution of the reference's text computes —

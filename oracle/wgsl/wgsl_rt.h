@@ -346,6 +346,22 @@ inline vec4<f32> textureGather(i32 component, const wgsl_texture& t, const sampl
     return vec4<f32>(av[k], bv[k], cv[k], dv[k]);
 }
 
+// ------------------------------------------------------------------------------------------------ derivatives (fragment stage)
+// dpdx / dpdy of an arbitrary expression = the difference of that expression between two pixels of the invocation's 2 x 2 quad.  The
+// raster harness (oracle/wgsl/raster_prepass.py) evaluates the fragment function at the quad's pixels first (mode 1: every derivative
+// call records its argument, in call order, into the slot of the pixel being evaluated: 0 / 1 = left / right pixel of the row, 2 / 3 =
+// top / bottom pixel of the column) and then at the pixel itself (mode 2: call k returns the recorded difference) — fine derivatives.
+struct wgsl_derivatives { int mode = 0, slot = 0, n = 0, nx = 0, ny = 0; f32 rec[4][32]; };
+inline wgsl_derivatives& wgsl_derivative_state() { static thread_local wgsl_derivatives d; return d; }
+inline f32 wgsl_derivative(f32 v, int lo, int hi) {
+    wgsl_derivatives& D = wgsl_derivative_state();
+    if (D.mode == 1) { if (D.n < 32) D.rec[D.slot][D.n] = v; D.n += 1; return 0.0f; }
+    if (D.mode == 2) { const int k = D.nx++; return k < 32 ? D.rec[hi][k] - D.rec[lo][k] : 0.0f; }
+    return 0.0f;
+}
+inline f32 dpdx(f32 v) { return wgsl_derivative(v, 0, 1); }
+inline f32 dpdy(f32 v) { return wgsl_derivative(v, 2, 3); }
+
 // ------------------------------------------------------------------------------------------------ dispatch
 struct wgsl_ids { vec3<u32> global, local, group, num_groups; u32 local_index = 0; };
 inline wgsl_ids& wgsl_tls() { static thread_local wgsl_ids ids; return ids; }

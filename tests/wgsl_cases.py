@@ -110,3 +110,40 @@ def planes_of(case, bench):
     return (PLANES + (DENOISED[:signals] if denoise else []) + ([("upscaled", L.OUT_UPSCALED)] if smaa else []) +
             ([("taa", L.OUT_TAA)] if taa else []) +
             ([("fsr_easu", L.OUT_UPSCALED), ("fsr_rcas", L.OUT_FSR_SHARPENED)] if fsr_of(case, bench) else []))
+
+
+# ------------------------------------------------------------------------------------------------ the raster prepass (G-buffer)
+# prepass.wgsl executed through the software rasteriser of oracle/wgsl/raster_prepass.py: scene, config, size, frame compared, camera
+# step, animation, TAA jitter.  The ray-cast G-buffer of oracle and CUDA path is held against it within the bounds of
+# tests/test_wgsl_prepass.py (coverage / ids exact up to edge pixels, values within the sub-pixel snapping of a rasteriser).
+PREPASS_CASES = {
+    # name: (scene, config, (W, H), frame, camera step, animation, taa jitter, fixture committed)
+    "cornell_moving": ("cornell", "cornell_1080p", (96, 64), 3, (0.03, 0.01, -0.02), None, False, True),
+    "cornell_animated_jittered": ("cornell", "cornell_1080p", (96, 64), 4, (0.02, 0.0, 0.0), "cornell", True, True),
+    "city_moving": ("city", "city_4k", (128, 72), 2, (0.05, 0.0, -0.04), None, False, True),
+    "simple_ground_plane": ("simple", "cornell_1080p", (96, 64), 2, (0.02, 0.0, 0.0), None, False, False),      # a quad through the near plane
+    "samplers": ("samplers", "cornell_1080p", (96, 64), 1, (0.0, 0.0, 0.0), None, False, False),
+    "town": ("town", "scene_1080p", (128, 72), 1, (0.0, 0.0, 0.0), None, False, False),                       # examples/scene.rs, 120 k triangles
+    "city_larger": ("city", "city_4k", (256, 144), 2, (0.05, 0.0, -0.04), None, False, False),
+}
+PREPASS_PLANES = [("position", L.OUT_GBUFFER_POSITION), ("normal", L.OUT_GBUFFER_NORMAL), ("depth_gradient", L.OUT_GBUFFER_DEPTH_GRADIENT),
+                  ("instance_material", L.OUT_GBUFFER_INSTANCE_MATERIAL), ("velocity_uv", L.OUT_GBUFFER_VELOCITY_UV)]
+
+
+def prepass_sequence(case):
+    """yields (bench, frame inputs, previous models or None) for frames 1 .. the compared frame of a PREPASS case; the caller renders
+    the G-buffer of every frame (the prepass keeps the previous frame's planes) and compares the last"""
+    from tests.conftest import Bench, cornell_animation
+    scene, config, (w, h), frame, step, animation, taa, _ = PREPASS_CASES[case]
+    kw = dict(taa=_P.TAA_JASMINE, upscale_kind=_P.UPSCALE_FSR1, upscale_ratio=1.0) if taa else {}
+    bench = Bench(scene, w, h, config=config, **kw)
+    anim = cornell_animation(bench) if animation else None
+    for f in range(1, frame + 1):
+        previous_models = None
+        if anim:
+            previous_models = bench.world.buffers()["instances"]["model"].reshape(-1, 16).copy()
+            anim.step(f)
+        inp = bench.moving_inputs(f, step) if any(step) else bench.inputs(f)
+        if taa:
+            inp.temporal_upscalers = 1
+        yield bench, inp, previous_models, anim is not None

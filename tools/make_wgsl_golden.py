@@ -67,10 +67,27 @@ def run_case(case):
     return digests, ref.tone_mapped.copy()
 
 
+def run_prepass_case(case):
+    """the G-buffer of the case's compared frame as prepass.wgsl rasterises it (oracle/wgsl/raster_prepass.py)"""
+    import raster_prepass as RP
+    taa = WC.PREPASS_CASES[case][6]
+    rp = RP.RasterPrepass(taa=taa)
+    out = None
+    for bench, inp, previous_models, _ in WC.prepass_sequence(case):
+        out = rp.render(inp, bench.width, bench.height, bench.scene.meshes, bench.scene.inst_mesh, bench.world.buffers()["instances"], previous_models)
+    return out
+
+
 def main():
     if not R.available():
         raise SystemExit("needs /root/reference and g++ (build container only)")
     out_dir = os.path.join(ROOT, "tests", "golden")
+    if sys.argv[1:2] == ["--prepass"]:
+        for case in (sys.argv[2:] or [c for c, v in WC.PREPASS_CASES.items() if v[7]]):
+            r = run_prepass_case(case)
+            np.savez_compressed(os.path.join(out_dir, f"wgsl_prepass_{case}.npz"), **{k: r[k] for k, _ in WC.PREPASS_PLANES})
+            print(f"prepass {case}: {r['fragments']} fragments shaded, {int((r['position'][..., 3] > 0).sum())} pixels covered")
+        return
     for case in (sys.argv[1:] or WC.CASES):
         digests, last = run_case(case)
         names = sorted(digests)
