@@ -106,9 +106,9 @@ enum {
     HK_OUT_DENOISED_DIRECT = 8,  /* Rgba16Float           post_process.rs:714 denoise_render[0] */
     HK_OUT_DENOISED_EMISSIVE = 9,
     HK_OUT_DENOISED_INDIRECT = 10,
-    HK_OUT_UPSCALED = 11,        /* Rgba16Float   post_process.rs:718-724 upscale_output[0]: 2x render size (SMAA TU4x) or the camera
+    HK_OUT_UPSCALED = 11,        /* Rgba16Float   post_process.rs:718-724 upscale_output[0]: ceil(size * 2 / ratio) (SMAA TU4x; <= 2x render size) or the camera
                                     target size (Fsr1: the EASU result) */
-    HK_OUT_TAA = 12,             /* Rgba16Float, 2x render size with SMAA TU4x else render size   post_process.rs:726-731 taa_output[current] */
+    HK_OUT_TAA = 12,             /* Rgba16Float, the extent of HK_OUT_UPSCALED with SMAA TU4x else render size   post_process.rs:726-731 taa_output[current] */
     HK_OUT_FSR_SHARPENED = 13,   /* Rgba16Float, camera target size   upscale_output[1]: the RCAS result, what the overlay presents
                                     under Upscale::Fsr1 (overlay.rs:228) */
     HK_OUT_GBUFFER_POSITION = 16,           /* Rgba32Float 16 B/px */
@@ -234,7 +234,8 @@ int hk_get_output(hk_context* ctx, int which, void** device_ptr, size_t* bytes);
                                                                                      rectangle), HK_OUT_UPSCALED, HK_OUT_TAA */
 /* Pixels of the rectangle hk_readback / hk_get_output transfer for `which`, under the settings of the last frame run:
  * deferred-size planes (G-buffer, albedo) = the owned rectangle; render-size planes = ceil(size / upscale_ratio)
- * (light.rs:622-624); HK_OUT_UPSCALED (and HK_OUT_TAA after smaa_tu4x) = twice the render size (post_process.rs:718-731). */
+ * (light.rs:622-624); HK_OUT_UPSCALED (and HK_OUT_TAA after smaa_tu4x) = ceil(size * (2 / ratio)) as create_texture computes it (post_process.rs:663-667,
+ * 711-731): twice the render size except where the two ceilings disagree (ratio 2 on an odd width W: W, not W + 1). */
 int hk_output_extent(hk_context* ctx, int which, uint32_t* width, uint32_t* height);
 int hk_readback(hk_context* ctx, int which, void* host, size_t bytes);            /* synchronises */
 /* Pipelined read-back of a final image (HK_OUT_TONE_MAPPED / HK_OUT_UPSCALED / HK_OUT_TAA / HK_OUT_FSR_SHARPENED) for a presentation loop: the
