@@ -16,6 +16,10 @@ from tests.conftest import ROOT
 FILES = ["tests/test_gpu_parity.py", "tests/test_gpu_variants.py", "tests/test_gpu_upscale.py", "tests/test_gpu_dynamic.py",
          "tests/test_gpu_frame_assembly.py", "tests/test_gpu_zz_fsr.py", "tests/test_gpu_zz_examples.py", "tests/test_gpu_zz_halo.py",
          "tests/test_gpu_wide_traversal.py", "tests/test_gpu_scene_update.py", "tests/test_gpu_wgsl_golden.py"]
+# the reverse order runs single-threaded: the files whose kernels have something an order could change (scatter claims / resolve,
+# cooperative tiles and pools, the level-synchronous BVH build, halo copies), not the long fixture sequences once more
+REVERSE_FILES = ["tests/test_gpu_parity.py", "tests/test_gpu_upscale.py", "tests/test_gpu_dynamic.py", "tests/test_gpu_zz_halo.py",
+                 "tests/test_gpu_scene_update.py"]
 
 
 @pytest.mark.parametrize("order", ["forward", "reverse"])
@@ -27,7 +31,15 @@ def test_gpu_parity_suite_passes_on_emulated_kernels(order):
     env = dict(os.environ, HK_EMULATE_KERNELS="1")
     if order == "reverse":
         env["HK_EMU_REVERSE"] = "1"
-    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + FILES, cwd=ROOT, env=env,
+    files = REVERSE_FILES if order == "reverse" else FILES
+    extra = []
+    if order == "reverse":      # one host thread per launch: spread the tests over processes instead (pytest-xdist, when installed)
+        try:
+            import xdist  # noqa: F401
+            extra = ["-n", str(min(4, os.cpu_count() or 1))]
+        except ImportError:
+            pass
+    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + extra + files, cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=1500)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
     assert r.returncode == 0, tail
