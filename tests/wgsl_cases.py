@@ -25,6 +25,7 @@ CASES = {
     "cornell_animated": ("cornell", "cornell_1080p", (72, 48), 7, (0.0, 0.0, 0.0), "cornell", {}),       # instances move every frame
     "city_cfg4_moving": ("city", "city_4k", (80, 45), 7, (0.05, 0.0, -0.04), None, {}),                  # textures, sun, 13 textures
     "city_cfg5": ("city", "city_8k", (64, 36), 6, (0.0, 0.0, 0.0), None, {}),                            # 4 bounces, both spatial reuses
+    "town_cfg3": ("town", "scene_1080p", (64, 40), 5, (0.04, 0.0, -0.03), None, {}),                        # configs[2]: examples/scene.rs, 120 k triangles, 3 bounces
     "simple_two_lights": ("simple", "cornell_1080p", (72, 48), 7, (0.02, 0.0, 0.0), None, {}),           # two emissives: light BVH + alias
     "samplers": ("samplers", "cornell_1080p", (64, 40), 6, (0.0, 0.0, 0.0), None, {}),                   # wrap modes, nearest / bilinear, textured light
     "no_denoise_one_bounce": ("simple", "cornell_256", (56, 40), 6, (0.0, 0.02, 0.0), None, {}),
