@@ -12,7 +12,7 @@
 // (read in place under /root/reference) to C++, compiles one library per pipeline specialisation into oracle/_ref/wgsl/ and drives
 // them with the bind-group wiring of src/light.rs / src/post_process.rs.  What that execution of the reference's text computes —
 // every reservoir buffer, radiance / variance plane, albedo, denoised plane, tone-mapped image, SMAA / TAA / FSR image of every frame
-// of eighteen free-running sequences (FSR 1.0 from the GLSL of src/shaders/fsr/source.zip, oracle/wgsl/glsl2cpp.py) — is committed as fixtures (tests/golden/wgsl_*.npz, tools/make_wgsl_golden.py), and this file reproduces
+// of twenty-three free-running sequences (FSR 1.0 from the GLSL of src/shaders/fsr/source.zip, oracle/wgsl/glsl2cpp.py) — is committed as fixtures (tests/golden/wgsl_*.npz, tools/make_wgsl_golden.py), and this file reproduces
 // every one of them BIT FOR BIT (tests/test_wgsl_reference.py; the CUDA path likewise, tests/test_gpu_wgsl_golden.py).
 // Still a restatement, i.e. parity unpinned there: the G-buffer (the reference rasterises it; the translated passes take it as
 // input), the BVH / alias-table build of the pinned crate bvh 0.7.1 and glam (host/hikari.cpp, restated from the published

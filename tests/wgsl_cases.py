@@ -29,6 +29,15 @@ CASES = {
     "simple_two_lights": ("simple", "cornell_1080p", (72, 48), 7, (0.02, 0.0, 0.0), None, {}),           # two emissives: light BVH + alias
     "samplers": ("samplers", "cornell_1080p", (64, 40), 6, (0.0, 0.0, 0.0), None, {}),                   # wrap modes, nearest / bilinear, textured light
     "no_denoise_one_bounce": ("simple", "cornell_256", (56, 40), 6, (0.0, 0.02, 0.0), None, {}),
+    # HikariSettings away from the BASELINE configurations (the corners tests/test_gpu_variants.py walks on the device)
+    "settings_no_bounces": ("simple", "cornell_1080p", (56, 40), 5, (0.02, 0.0, 0.0), None, {"indirect_bounces": 0}),     # ambient-only indirect pass, two denoised signals
+    "settings_no_temporal_reuse": ("cornell", "cornell_1080p", (56, 40), 5, (0.02, 0.01, 0.0), None, {"temporal_reuse": 0, "denoise": 0}),
+    "settings_lifetime_and_validation": ("cornell", "cornell_1080p", (56, 40), 7, (0.0, 0.0, 0.0), "cornell",
+                                         {"max_reservoir_lifetime": 1.0, "direct_validate_interval": 1, "emissive_validate_interval": 2, "denoise": 0}),
+    "settings_clamps": ("city", "city_8k", (64, 36), 6, (0.03, 0.0, -0.02), None,
+                        {"max_temporal_reuse_count": 2, "max_spatial_reuse_count": 3, "max_indirect_luminance": 0.5}),
+    "settings_sun_disc_and_clear_color": ("city", "city_4k", (64, 36), 5, (0.0, 0.0, 0.0), None,
+                                          {"solar_angle": 0.5, "clear_color": (0.1, 0.2, 0.3, 1.0), "indirect_bounces": 1}),
     # scaled rendering (Upscale ratio > 1: light / denoise planes at ceil(size / ratio), jittered_deferred_uv / _coords look-ups)
     "cornell_ratio2": ("cornell", "cornell_1080p", (96, 64), 7, (0.02, 0.0, -0.01), None, {"upscale_ratio": 2.0}),
     "city_ratio1p5": ("city", "city_4k", (96, 54), 6, (0.0, 0.0, 0.0), None, {"upscale_ratio": 1.5}),
