@@ -64,6 +64,11 @@ CASES = {
 UPSCALER_CASES = {"cornell_default_upscalers", "cornell_smaa_ratio1_taa", "city_smaa_only_ratio1p5", "simple_taa_only",
                   "cornell_default_upscalers_odd_window", "cornell_fsr_ratio1p5", "city_taa_fsr_ratio2"}
 
+# cases added after the round's last GPU minute: reproduced by the CUDA path on the emulated kernels only so far; the device suite runs
+# them LAST (tests/test_gpu_zzz_wgsl_late_cases.py) so that a surprise on the device could not hide the rest of the suite behind `pytest -x`
+LATE_CASES = {"town_cfg3", "settings_no_bounces", "settings_no_temporal_reuse", "settings_lifetime_and_validation", "settings_clamps",
+              "settings_sun_disc_and_clear_color"}
+
 PLANES = ([("albedo", L.OUT_ALBEDO)] + [(f"render{i}", L.OUT_RENDER_DIRECT + i) for i in range(3)] +
           [(f"variance{i}", L.OUT_VARIANCE_DIRECT + i) for i in range(3)] + [(f"reservoir{i}", L.OUT_RESERVOIR_0 + i) for i in range(10)] +
           [("tone_mapped", L.OUT_TONE_MAPPED)])
