@@ -14,11 +14,12 @@
 // every reservoir buffer, radiance / variance plane, albedo, denoised plane, tone-mapped image, SMAA / TAA / FSR image of every frame
 // of twenty-three free-running sequences (FSR 1.0 from the GLSL of src/shaders/fsr/source.zip, oracle/wgsl/glsl2cpp.py) — is committed as fixtures (tests/golden/wgsl_*.npz, tools/make_wgsl_golden.py), and this file reproduces
 // every one of them BIT FOR BIT (tests/test_wgsl_reference.py; the CUDA path likewise, tests/test_gpu_wgsl_golden.py).
-// Still a restatement, i.e. parity unpinned there: the G-buffer (the reference rasterises it; the translated passes take it as
-// input), the BVH / alias-table build of the pinned crate bvh 0.7.1 and glam (host/hikari.cpp, restated from the published
-// sources), and the ~60 lines of bevy_pbr 0.9.1 the shaders import (oracle/wgsl/prelude/).  For those the
-// evidence remains a second, independent restatement per pass (tests/test_*_numpy.py; table in DESIGN.md 2) and the physical
-// anchors of tests/test_estimator.py.
+// The G-buffer, which the reference rasterises and hko_prepass ray-casts, is held against prepass.wgsl executed behind a software
+// rasteriser (oracle/wgsl/raster_prepass.py, tests/test_wgsl_prepass.py): same coverage, same ids up to edge pixels, values within a
+// rasteriser's sub-pixel snapping.  Still a restatement, i.e. parity unpinned there: the BVH / alias-table build of the pinned crate
+// bvh 0.7.1 and glam (host/hikari.cpp, restated from the published sources), and the ~110 lines of bevy_pbr 0.9.1 the shaders import
+// (oracle/wgsl/prelude/).  For those the evidence remains a second, independent restatement per pass
+// (tests/test_*_numpy.py; table in DESIGN.md 2), the topology-invariance test and the physical anchors of tests/test_estimator.py.
 // Deviations that are forced and documented:
 //   * the G-buffer is ray-cast (hko_prepass) instead of rasterised (prepass.wgsl:40-100) — same five planes, same
 //     formats, oracle-defined coverage;
