@@ -29,9 +29,9 @@ FLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fop
          "-I" + os.path.join(HERE, "include"), "-I" + SRC, "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + \
         os.environ.get("HK_EMU_EXTRA", "").split()      # e.g. -DHK_DENOISE_BRANCHFREE=1: validate a tuning variant's logic
 if ASAN:
-    FLAGS = [f for f in FLAGS if f != "-O2"] + ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
+    FLAGS = [f for f in FLAGS if f != "-O2"] + ["-O1", "-g1", "-fno-var-tracking-assignments", "-fsanitize=address", "-fno-omit-frame-pointer"]
 if ALIGN:
-    FLAGS = [f for f in FLAGS if f != "-O2"] + ["-O1", "-g", "-fsanitize=alignment", "-fno-sanitize-recover=alignment"]
+    FLAGS = [f for f in FLAGS if f != "-O2"] + ["-O1", "-g1", "-fsanitize=alignment", "-fno-sanitize-recover=alignment"]
 
 LAUNCH = re.compile(r"([A-Za-z_][A-Za-z_0-9]*(?:<[^<>;]*>)?)<<<([^;]*?)>>>\(([^;]*)\);")
 COOPERATIVE = re.compile(r"^kc_")     # kernels with shared memory / barriers / warp collectives: threads of a block run as fibers
