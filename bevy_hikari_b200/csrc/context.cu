@@ -86,6 +86,8 @@ struct hk_context {
     bool tile_maps_ready = false;
     bool full_frame = true;            // the context owns the whole frame (no tile): upscale_ratio > 1 and the upscalers need it
     int last_up_w = 0, last_up_h = 0;   // Band::OW / OH of the last frame
+    bool last_scaled = false;           // the last frame ran at upscale_ratio != 1: render-size planes are tight RW x RH (even where RW x RH == W x H:
+                                        // ceil(3 / 1.25) = 3), not strided like the deferred-size planes
     int last_render_w = 0, last_render_h = 0; bool last_smaa = false, last_upscalers = false, last_fsr = false; uint32_t last_number = 0;   // of the last frame, for read-back sizes
     int gbuffer_current = 0;           // index of the "current" position / velocity_uv planes; toggled by every prepass
     uint8_t* noise = nullptr;
@@ -216,7 +218,7 @@ static int allocate_planes(hk_context* ctx, uint32_t width, uint32_t height, uin
     // (validated against the old width) and the "planes are usable" flag, which only a complete allocation sets again —
     // a cudaMalloc failing half-way leaves the context refusing to render instead of holding dangling pointers.
     ctx->planes_ready = false;
-    ctx->last_render_w = ctx->last_render_h = 0; ctx->last_up_w = ctx->last_up_h = 0; ctx->last_number = 0;
+    ctx->last_render_w = ctx->last_render_h = 0; ctx->last_up_w = ctx->last_up_h = 0; ctx->last_number = 0; ctx->last_scaled = false;
     ctx->last_smaa = ctx->last_upscalers = ctx->last_fsr = false;
     ctx->frame_target = nullptr; ctx->frame_pitch = 0;
     free_list(ctx->allocations);
@@ -971,7 +973,7 @@ static int make_params(hk_context* ctx, const hk_frame_inputs* in, KParams& P) {
         P.band.OW = (int)ceilf((float)P.band.W * scale2);
         P.band.OH = (int)ceilf((float)P.band.H * scale2);
     }
-    ctx->last_up_w = P.band.OW; ctx->last_up_h = P.band.OH;
+    ctx->last_up_w = P.band.OW; ctx->last_up_h = P.band.OH; ctx->last_scaled = !ratio1;
     P.inv_rw = 1.0f / (float)P.band.RW; P.inv_rh = 1.0f / (float)P.band.RH;
     ctx->last_render_w = P.band.RW; ctx->last_render_h = P.band.RH; ctx->last_smaa = in->smaa_tu4x != 0; ctx->last_number = in->frame.number;
     ctx->last_fsr = in->temporal_upscalers && in->fsr1;
@@ -1340,7 +1342,7 @@ static bool plane_view(hk_context* ctx, int which, PlaneView* v) {
     const Planes& p = ctx->planes;
     const Band& b = ctx->band;
     const size_t ow = (size_t)(b.cx1 - b.cx0), oh = (size_t)(b.r1 - b.r0);
-    const bool scaled = ctx->last_render_w != 0 && (ctx->last_render_w != b.W || ctx->last_render_h != b.H);   // ratio > 1 (full frame)
+    const bool scaled = ctx->last_render_w != 0 && ctx->last_scaled;   // ratio > 1 (full frame)
     const size_t rw = scaled ? (size_t)ctx->last_render_w : ow, rh = scaled ? (size_t)ctx->last_render_h : oh;
     const size_t first_def = (size_t)(b.r0 - b.a0) * (size_t)b.AW + (size_t)(b.cx0 - b.ax0);
     const size_t first_ren = scaled ? 0 : first_def;
@@ -1412,7 +1414,7 @@ static int transfer(hk_context* ctx, int which, void* host, size_t bytes, bool t
     if (!ctx->planes_ready) return set_error(ctx, HK_ERR_NOT_READY, "per-pixel planes are not allocated (a resize failed)");
     if (which >= HK_OUT_RESERVOIR_0 && which < HK_OUT_RESERVOIR_0 + 10) {
         Band rb = ctx->band;   // rectangle of the reservoir buffer in render space
-        if (ctx->last_render_w != 0 && (ctx->last_render_w != rb.W || ctx->last_render_h != rb.H)) {
+        if (ctx->last_render_w != 0 && ctx->last_scaled) {
             rb.cx0 = 0; rb.cx1 = ctx->last_render_w; rb.r0 = 0; rb.r1 = ctx->last_render_h; rb.a0 = 0; rb.ax0 = 0; rb.AW = ctx->last_render_w;
         }
         const size_t n = (size_t)(rb.cx1 - rb.cx0) * (size_t)(rb.r1 - rb.r0);
