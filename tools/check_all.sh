@@ -18,5 +18,7 @@ HK_EMULATE_KERNELS=1 python tools/fuzz_parity.py $SEED 150
 HK_EMULATE_KERNELS=1 HK_FUZZ_SOUP=1 python tools/fuzz_parity.py $((SEED + 1000)) 60
 HK_EMULATE_KERNELS=1 HK_FUZZ_HALO=1 python tools/fuzz_parity.py $((SEED + 2000)) 40
 HK_EMULATE_KERNELS=1 HK_FUZZ_TILES=1 python tools/fuzz_parity.py $((SEED + 3000)) 40
+echo "== the WGSL pin between the fixtures (reference shader text executed vs the oracle, fresh seeds)"
+python tools/fuzz_wgsl_pin.py $((SEED + 4000)) 40
 echo "== static: code size / registers / spills of the light kernels";   python tools/code_size.py | tail -30
 echo "all CPU-side checks passed"
